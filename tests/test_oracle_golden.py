@@ -1,0 +1,72 @@
+"""The oracle against outputs of the reference itself (tests/golden/, made by
+make_golden.py from /root/reference): candidate set, expected curve, window
+features, leaves, probabilities, bedpe text. CPU only."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import peakachu_oracle as po
+from peakachu_b200 import coolio
+from tests.cases import ALL_CASES, FULL_TAP_CASES, Case
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _chromosome(case, lib, ch, model):
+    cfg = case.cfg
+    cname = "chr" + ch.name.lstrip("chr")
+    if cfg["weight"] == "raw":
+        M = po.tocsr(lib.matrix(balance=False, sparse=True).fetch(ch.name))
+        return po.Chromosome(M, model=model, raw_M=M, weights=None, cname=cname, lower=cfg["lower"],
+                             upper=cfg["upper"], res=cfg["res"], width=cfg["w"])
+    M = po.tocsr(lib.matrix(balance=cfg["weight"], sparse=True).fetch(ch.name))
+    raw_M = po.tocsr(lib.matrix(balance=False, sparse=True).fetch(ch.name))
+    weights = lib.bins().fetch(ch.name)[cfg["weight"]].values
+    return po.Chromosome(M, model=model, raw_M=raw_M, weights=weights, cname=cname, lower=cfg["lower"],
+                         upper=cfg["upper"], res=cfg["res"], width=cfg["w"])
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_oracle_taps_match_reference(name, tmp_path):
+    case = Case(name)
+    model = case.model()
+    lib = coolio.Cooler(case.write_cool(tmp_path))
+    for ch in case.chroms:
+        X = _chromosome(case, lib, ch, model)
+        k = ch.name + "/"
+        assert np.array_equal(X.exp_arr, case.z[k + "exp_arr"])              # tap (ii), bit-exact
+        assert np.array_equal(X.ridx, case.z[k + "ridx"])                    # tap (i)
+        assert np.array_equal(X.cidx, case.z[k + "cidx"])
+        fea, clist = X.getwindow(np.stack([X.ridx, X.cidx], axis=1))         # tap (iii)
+        assert np.array_equal(clist, case.z[k + "clist"])
+        sh = case.meta["sha"][ch.name]
+        assert fea.shape[0] == sh["n_windows"]
+        assert _sha(fea) == sh["fea64"]                                      # float64 bit-exact
+        fea32 = fea.astype(np.float32)
+        assert _sha(fea32) == sh["fea32"]
+        leaves = po.forest_apply(case.forest, fea32)                         # tap (iv)
+        assert _sha(leaves.astype(np.int32)) == sh["leaves"]
+        proba = po.forest_proba(case.forest, fea32)
+        assert np.array_equal(proba, case.z[k + "proba"])                    # bit-exact float64
+        if name in FULL_TAP_CASES:
+            assert np.array_equal(fea[:128], case.z[k + "fea64_head"])
+            assert np.array_equal(fea32, case.z[k + "fea32"])
+            assert np.array_equal(leaves, case.z[k + "leaves"])
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_oracle_bedpe_matches_reference(name, tmp_path):
+    case = Case(name)
+    cfg = case.cfg
+    lib = coolio.Cooler(case.write_cool(tmp_path))
+    out = os.path.join(str(tmp_path), "o.bedpe")
+    names = [c.name for c in case.chroms]
+    if cfg.get("genome"):
+        names = [n for n in names if n.lstrip("chr").isdigit() or n.lstrip("chr") == "X"]
+    po.score_map(lib, case.model(), names, weight_name=cfg["weight"], lower=cfg["lower"],
+                 upper=cfg["upper"], res=cfg["res"], min_prob=cfg["min_prob"], output=out)
+    assert open(out).read() == case.bedpe                                    # tap (v)
