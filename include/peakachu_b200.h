@@ -1,0 +1,150 @@
+/*
+ * peakachu_b200 -- C ABI of the B200 (sm_100a) loop-scoring path.
+ *
+ * The reference (tariks/peakachu v2.3) is pure Python and has no FFI. The seam this
+ * library sits behind is the class peakachu/scoreUtils.py:9-135 (`Chromosome`) as
+ * driven by peakachu/score_chromosome.py:3-71 and peakachu/score_genome.py:3-84.
+ * Each entry point below names the reference code it replaces. The binding a
+ * maintainer adds on the reference side is a ctypes stub; see INTEGRATION.md.
+ *
+ * Conventions
+ *  - every call returns 0 on success, a negative PK_E* code on failure;
+ *    pk_last_error() returns a thread-local message for the last failure;
+ *    no C++ exception crosses this boundary.
+ *  - the caller owns every buffer it passes in; the library owns the opaque
+ *    handles it returns until *_destroy.
+ *  - a handle is bound to one CUDA device; all work of a handle is issued on the
+ *    stream given at creation (a cudaStream_t passed as void*, NULL = default
+ *    stream). One host thread per handle at a time.
+ *  - `mem` arguments say where a caller buffer lives: PK_MEM_HOST or PK_MEM_DEVICE.
+ *  - calls are asynchronous on the handle's stream unless they return data to
+ *    host memory (those synchronise the stream).
+ */
+#ifndef PEAKACHU_B200_H
+#define PEAKACHU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PK_OK            0
+#define PK_EINVAL       -1   /* bad argument */
+#define PK_ECUDA        -2   /* CUDA runtime error (message has the cudaError string) */
+#define PK_ENOMEM       -3
+#define PK_ESTATE       -4   /* call out of order (e.g. score before set_expected) */
+#define PK_ECAPACITY    -5   /* caller buffer too small */
+#define PK_EUNSUPPORTED -6
+
+#define PK_MEM_HOST   0
+#define PK_MEM_DEVICE 1
+
+typedef struct pk_forest pk_forest;
+typedef struct pk_chrom pk_chrom;
+
+const char* pk_last_error(void);
+int pk_abi_version(void);
+/* number of visible CUDA devices; fails with PK_ECUDA when there is none */
+int pk_device_count(int* out);
+
+/* ---- forest: replaces model.predict_proba(fea)[:, 1] (scoreUtils.py:109) on the
+ * joblib-loaded sklearn RandomForestClassifier (score_chromosome.py:14). Arrays are
+ * the concatenated per-tree sklearn `tree_` tables (host memory): children are
+ * tree-local indices, -1 for leaves; `leaf_p1[i]` is the class-1 fraction
+ * tree_.value[i,0,1]. Traversal and accumulation order follow sklearn
+ * (_tree.pyx::_apply_dense, _forest.py predict_proba): float32 feature <= float64
+ * threshold goes left, NaN follows missing_go_to_left, float64 sum in tree order,
+ * one divide by n_trees. */
+int pk_forest_create(int device, int32_t n_trees, int32_t n_features,
+                     const int64_t* node_offset /* [n_trees+1] */,
+                     const int32_t* feature, const double* threshold,
+                     const int32_t* left, const int32_t* right,
+                     const uint8_t* missing_left, const double* leaf_p1,
+                     pk_forest** out);
+int pk_forest_destroy(pk_forest* f);
+int pk_forest_info(const pk_forest* f, int32_t* n_trees, int32_t* n_features, int64_t* n_nodes);
+/* parity tap: leaves (tree-local sklearn node id, as estimator.apply) and/or
+ * probabilities for caller-supplied float32 rows. X, leaves, proba are DEVICE
+ * pointers; leaves is [n_rows][n_trees] or NULL; proba is [n_rows] or NULL. */
+int pk_forest_apply(pk_forest* f, const float* X, int64_t n_rows,
+                    int32_t* leaves, double* proba, void* stream);
+
+/* ---- chromosome: replaces scoreUtils.Chromosome (scoreUtils.py:9-135).
+ * lower/upper are the user's -l/-u; the library clamps them like scoreUtils.py:13-14
+ * (lower = max(lower, w+1), upper = min(upper, n-2w)). balanced != 0 is the
+ * `--clr-weight-name <col>` mode (weights given), 0 is `--clr-weight-name raw`. */
+int pk_chrom_create(int device, int32_t n_bins, int32_t width, int32_t lower, int32_t upper,
+                    int balanced, void* stream, pk_chrom** out);
+int pk_chrom_destroy(pk_chrom* c);
+/* effective (clamped) bounds and the expected-curve length upper+2w+1 */
+int pk_chrom_bounds(const pk_chrom* c, int32_t* lower_eff, int32_t* upper_eff, int32_t* exp_len);
+
+/* Upper-triangle pixels of one chromosome (bin1 <= bin2, chromosome-local ids, any
+ * order, duplicates summed as utils.tocsr does, utils.py:10-15) plus the balancing
+ * weight per bin (NULL in raw mode). Builds the dense diagonal-major count band,
+ * the per-bin `valid` mask of utils.calculate_expected (utils.py:146-156) and the
+ * per-diagonal sums (utils.py:160-170, numpy pairwise order). Replaces the
+ * cooler fetches + tocsr + band trim (score_chromosome.py:42-44, scoreUtils.py:30-33). */
+int pk_chrom_upload_pixels(pk_chrom* c, const int32_t* bin1, const int32_t* bin2,
+                           const int32_t* count, int64_t nnz, const double* weights, int mem);
+/* per-diagonal (sum, n_valid) for d = 0..upper+2w, to HOST arrays of exp_len */
+int pk_chrom_diag_sums(pk_chrom* c, double* out_sum, int64_t* out_cnt);
+/* expected curve fitted by the library itself: mean where n_valid > 10, then the
+ * non-increasing isotonic fit + clipped linear interpolation of utils.py:173-176
+ * (the library's own PAVA + interpolation; scikit-learn is not involved). */
+int pk_chrom_fit_expected(pk_chrom* c);
+/* or supply it (HOST arrays of exp_len): exp_arr normalises windows, background
+ * drives the Poisson filter (scoreUtils.py:16-24) */
+int pk_chrom_set_expected(pk_chrom* c, const double* exp_arr, const double* background);
+int pk_chrom_get_expected(pk_chrom* c, double* out_exp /* HOST [exp_len] */);
+
+/* Candidate selection, scoreUtils.py:40-68: raw count > 0 and Poisson upper tail
+ * < 0.01 against background[d] / (w_x * w_y). Restricted to rows x in
+ * [row_begin, row_end) (pass 0, n_bins for the whole chromosome) -- the band
+ * row-tile seam used for multi-GPU sharding. n_candidates (HOST) may be NULL. */
+int pk_chrom_find_candidates(pk_chrom* c, int32_t row_begin, int32_t row_end, int64_t* n_candidates);
+/* parity taps (HOST outputs, reference order: distance asc, row asc) */
+int pk_chrom_candidates(pk_chrom* c, int32_t* out_x, int32_t* out_y, int64_t capacity, int64_t* n);
+/* getwindow tap (scoreUtils.py:70-93) over the current candidates: keep[i] = window
+ * passed the border mask and utils.distance_normalize's filters; fea32/fea64 are
+ * [n_candidates][(2w+1)^2] HOST arrays (either may be NULL), rows of rejected
+ * candidates are left untouched. */
+int pk_chrom_features(pk_chrom* c, uint8_t* keep, float* fea32, double* fea64, int64_t capacity);
+
+/* Chromosome.score (scoreUtils.py:95-125): features -> forest -> keep prob > min_prob
+ * (strict). The reference walks candidates in batches of 100,000 (in its own order,
+ * over the whole chromosome) and silently drops a batch in which <= 1 window
+ * survives the filters (scoreUtils.py:104-108). Every candidate carries its
+ * whole-chromosome rank, so batch ids are right for row tiles too; when the handle
+ * covers the whole chromosome the drop rule is applied on the device, for a row
+ * tile the caller applies it after summing pk_chrom_batch_windows over the tiles.
+ * Records stay on the device until fetched. */
+int pk_chrom_score(pk_chrom* c, pk_forest* f, double min_prob);
+int pk_chrom_result_count(pk_chrom* c, int64_t* n_records, int64_t* n_candidates, int64_t* n_windows);
+/* surviving windows per reference batch (HOST array; n_batches may exceed capacity -> PK_ECAPACITY) */
+int pk_chrom_batch_windows(pk_chrom* c, int64_t* out, int64_t capacity, int64_t* n_batches);
+/* records (x, y, prob, balanced value[, batch id]); out_batch may be NULL.
+ * mem = PK_MEM_HOST: sorted by (x, y) like prob_csr.nonzero() (scoreUtils.py:130).
+ * mem = PK_MEM_DEVICE: device-to-device copy in emission order (unsorted). */
+int pk_chrom_fetch_results(pk_chrom* c, int32_t* out_x, int32_t* out_y, double* out_prob,
+                           double* out_val, int32_t* out_batch, int64_t capacity, int mem);
+
+/* ---- Poisson decision table: crit[k] = smallest float64 mu with
+ * Pr[Poisson(mu) > k] >= 0.01, so that `p < 0.01` <=> `mu < crit[k]`
+ * (scipy.stats.poisson.sf is increasing in mu). HOST output, for tests. */
+int pk_poisson_critical_mu(int32_t k_max, double* out /* [k_max+1] */);
+
+/* the expected-curve fit alone on HOST arrays (test hook for the restated
+ * IsotonicRegression(increasing=False, out_of_bounds='clip') of utils.py:173-176) */
+int pk_fit_expected(const double* sum, const int64_t* cnt, int32_t len, double* out_exp);
+
+/* time spent (ms, CUDA events) in each stage of the last upload/fit/find/score of
+ * this handle: [0] band build, [1] diagonal sums, [2] expected fit, [3] candidate
+ * scan, [4] window features, [5] forest, [6] emit+sort. HOST array of 8. */
+int pk_chrom_stage_ms(pk_chrom* c, float* out_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEAKACHU_B200_H */

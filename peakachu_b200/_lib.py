@@ -1,0 +1,102 @@
+"""ctypes binding of ``libpeakachu_b200.so`` (include/peakachu_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is
+visible, the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpeakachu_b200.so")
+
+PK_MEM_HOST, PK_MEM_DEVICE = 0, 1
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_f64p = C.POINTER(C.c_double)
+c_f32p = C.POINTER(C.c_float)
+c_u8p = C.POINTER(C.c_uint8)
+
+# name -> (restype, argtypes); every symbol declared in include/peakachu_b200.h
+SIGNATURES = {
+    "pk_last_error": (C.c_char_p, []),
+    "pk_abi_version": (C.c_int, []),
+    "pk_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "pk_forest_create": (C.c_int, [C.c_int, C.c_int32, C.c_int32, c_i64p, c_i32p, c_f64p, c_i32p, c_i32p,
+                                   c_u8p, c_f64p, C.POINTER(C.c_void_p)]),
+    "pk_forest_destroy": (C.c_int, [C.c_void_p]),
+    "pk_forest_info": (C.c_int, [C.c_void_p, c_i32p, c_i32p, c_i64p]),
+    "pk_forest_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pk_chrom_create": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int, C.c_void_p,
+                                  C.POINTER(C.c_void_p)]),
+    "pk_chrom_destroy": (C.c_int, [C.c_void_p]),
+    "pk_chrom_bounds": (C.c_int, [C.c_void_p, c_i32p, c_i32p, c_i32p]),
+    "pk_chrom_upload_pixels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    "pk_chrom_diag_sums": (C.c_int, [C.c_void_p, c_f64p, c_i64p]),
+    "pk_chrom_fit_expected": (C.c_int, [C.c_void_p]),
+    "pk_chrom_set_expected": (C.c_int, [C.c_void_p, c_f64p, c_f64p]),
+    "pk_chrom_get_expected": (C.c_int, [C.c_void_p, c_f64p]),
+    "pk_chrom_find_candidates": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_i64p]),
+    "pk_chrom_candidates": (C.c_int, [C.c_void_p, c_i32p, c_i32p, C.c_int64, c_i64p]),
+    "pk_chrom_features": (C.c_int, [C.c_void_p, c_u8p, c_f32p, c_f64p, C.c_int64]),
+    "pk_chrom_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double]),
+    "pk_chrom_result_count": (C.c_int, [C.c_void_p, c_i64p, c_i64p, c_i64p]),
+    "pk_chrom_batch_windows": (C.c_int, [C.c_void_p, c_i64p, C.c_int64, c_i64p]),
+    "pk_chrom_fetch_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int64, C.c_int]),
+    "pk_poisson_critical_mu": (C.c_int, [C.c_int32, c_f64p]),
+    "pk_fit_expected": (C.c_int, [c_f64p, c_i64p, C.c_int32, c_f64p]),
+    "pk_chrom_stage_ms": (C.c_int, [C.c_void_p, c_f32p]),
+}
+
+
+class PKError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("peakachu_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library once; raise if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C peakachu_b200/csrc`). There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise PKError(rc, lib().pk_last_error().decode("utf-8", "replace"))
+
+
+def require_device():
+    n = C.c_int(0)
+    check(lib().pk_device_count(C.byref(n)))
+    return n.value
+
+
+def ptr(a, typ=None):
+    """ctypes pointer to a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(typ) if typ is not None else C.c_void_p(a.ctypes.data)
+
+
+def as_c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)

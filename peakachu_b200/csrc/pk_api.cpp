@@ -1,0 +1,591 @@
+// peakachu_b200: C ABI (include/peakachu_b200.h) -- handle management, forest
+// packing, stage orchestration. No kernels here; see pk_kernels.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "pk_common.cuh"
+
+// launchers implemented in pk_kernels.cu
+int pk_launch_scatter(pk_chrom* c, const int32_t* b1, const int32_t* b2, const int32_t* cnt, int64_t nnz);
+int pk_launch_diag_sums(pk_chrom* c);
+int pk_launch_candidates(pk_chrom* c, const double* d_crit, int kmax, bool write);
+int pk_launch_scan2(pk_chrom* c, long long m);
+int pk_launch_features(pk_chrom* c, double* d_fea64);
+int pk_launch_forest(const pk_forest* f, const float* X, const uint8_t* keep, int64_t n_rows, int32_t* leaves,
+                     double* proba, cudaStream_t stream);
+int pk_launch_emit(pk_chrom* c, double thre);
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+void pk_set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+extern "C" const char* pk_last_error(void) { return g_err.c_str(); }
+extern "C" int pk_abi_version(void) { return 1; }
+
+extern "C" int pk_device_count(int* out) {
+    if (!out) { pk_set_error("pk_device_count: out is NULL"); return PK_EINVAL; }
+    int n = 0;
+    PK_CUDA(cudaGetDeviceCount(&n));
+    if (n <= 0) { pk_set_error("no CUDA device visible"); return PK_ECUDA; }
+    *out = n;
+    return PK_OK;
+}
+
+template <typename T>
+static int dev_alloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e != cudaSuccess) {
+        pk_set_error("cudaMalloc(%zu bytes) -> %s", count * sizeof(T), cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? PK_ENOMEM : PK_ECUDA;
+    }
+    return PK_OK;
+}
+
+template <typename T>
+static void dev_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+// ---------------------------------------------------------------------------
+// Poisson table: per-device copy of the host table
+// ---------------------------------------------------------------------------
+namespace {
+struct DevTable { double* d = nullptr; int32_t kmax = -1; };
+std::mutex g_dev_tab_mu;
+std::map<int, DevTable> g_dev_tab;
+}  // namespace
+
+int pk_poisson_table_device(int device, int32_t k_min_size, const double** d_out, int32_t* k_max_out) {
+    std::lock_guard<std::mutex> lk(g_dev_tab_mu);
+    DevTable& t = g_dev_tab[device];
+    if (t.kmax < k_min_size) {
+        int32_t want = std::max(k_min_size, 8191);
+        if (t.kmax >= 0) want = std::max(want, 2 * t.kmax + 1);
+        const double* host = nullptr;
+        PK_CHECK(pk_poisson_table_host(want, &host));
+        PK_CUDA(cudaSetDevice(device));
+        PK_CUDA(cudaDeviceSynchronize());      // nobody may still read the old copy
+        if (t.d) cudaFree(t.d);
+        t.d = nullptr;
+        PK_CHECK(dev_alloc(&t.d, (size_t)want + 1));
+        PK_CUDA(cudaMemcpy(t.d, host, ((size_t)want + 1) * sizeof(double), cudaMemcpyHostToDevice));
+        t.kmax = want;
+    }
+    *d_out = t.d;
+    *k_max_out = t.kmax;
+    return PK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// forest
+// ---------------------------------------------------------------------------
+static float round_down_f32(double t) {
+    float f = (float)t;
+    if ((double)f > t) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+
+extern "C" int pk_forest_create(int device, int32_t n_trees, int32_t n_features, const int64_t* node_offset,
+                                const int32_t* feature, const double* threshold, const int32_t* left,
+                                const int32_t* right, const uint8_t* missing_left, const double* leaf_p1,
+                                pk_forest** out) {
+    if (!out || !node_offset || !feature || !threshold || !left || !right || !leaf_p1) {
+        pk_set_error("pk_forest_create: NULL argument");
+        return PK_EINVAL;
+    }
+    if (n_trees <= 0 || n_features <= 0 || n_features >= (1 << PK_FEAT_BITS)) {
+        pk_set_error("pk_forest_create: n_trees=%d n_features=%d unsupported (features < %d)", n_trees, n_features,
+                     1 << PK_FEAT_BITS);
+        return PK_EINVAL;
+    }
+    const int64_t total = node_offset[n_trees];
+    if (total <= 0 || total >= (1LL << 31)) { pk_set_error("pk_forest_create: bad node count"); return PK_EINVAL; }
+    std::vector<uint2> nodes((size_t)total);
+    std::vector<int32_t> orig((size_t)total);
+    std::vector<uint32_t> roots((size_t)n_trees);
+    int32_t max_depth = 0;
+    std::vector<int32_t> newid, stack, depth;
+    for (int32_t t = 0; t < n_trees; ++t) {
+        const int64_t o = node_offset[t], cnt = node_offset[t + 1] - o;
+        if (cnt <= 0) { pk_set_error("pk_forest_create: tree %d is empty", t); return PK_EINVAL; }
+        // preorder renumbering: left child directly follows its parent
+        newid.assign((size_t)cnt, -1);
+        stack.clear(); depth.assign((size_t)cnt, 0);
+        stack.push_back(0);
+        int32_t next = 0;
+        while (!stack.empty()) {
+            int32_t v = stack.back(); stack.pop_back();
+            if (v < 0 || v >= cnt || newid[v] != -1) { pk_set_error("pk_forest_create: tree %d is not a tree", t); return PK_EINVAL; }
+            newid[v] = next++;
+            int32_t l = left[o + v], r = right[o + v];
+            if (l != -1) {
+                if (r < 0 || r >= cnt || l < 0 || l >= cnt) { pk_set_error("pk_forest_create: bad child index"); return PK_EINVAL; }
+                depth[l] = depth[r] = depth[v] + 1;
+                max_depth = std::max(max_depth, depth[v] + 1);
+                stack.push_back(r);
+                stack.push_back(l);
+            }
+        }
+        if (next != cnt) { pk_set_error("pk_forest_create: tree %d has unreachable nodes", t); return PK_EINVAL; }
+        for (int32_t v = 0; v < cnt; ++v) {
+            const int64_t p = o + newid[v];
+            orig[(size_t)p] = v;
+            int32_t l = left[o + v], r = right[o + v];
+            if (l == -1) {
+                double val = leaf_p1[o + v];
+                memcpy(&nodes[(size_t)p], &val, 8);
+            } else {
+                int32_t ft = feature[o + v];
+                if (ft < 0 || ft >= n_features) { pk_set_error("pk_forest_create: feature index %d out of range", ft); return PK_EINVAL; }
+                if (newid[l] != newid[v] + 1) { pk_set_error("pk_forest_create: internal preorder error"); return PK_EINVAL; }
+                uint32_t roff = (uint32_t)(newid[r] - newid[v]);
+                if (roff >= (1u << 19)) { pk_set_error("pk_forest_create: tree %d too large (right offset %u)", t, roff); return PK_EUNSUPPORTED; }
+                float thr = round_down_f32(threshold[o + v]);
+                uint32_t meta = (uint32_t)ft | ((missing_left && missing_left[o + v]) ? (1u << 10) : 0u) |
+                                ((left[o + l] == -1) ? (1u << 11) : 0u) | ((left[o + r] == -1) ? (1u << 12) : 0u) |
+                                (roff << 13);
+                uint32_t tb;
+                memcpy(&tb, &thr, 4);
+                nodes[(size_t)p] = make_uint2(tb, meta);
+            }
+        }
+        roots[(size_t)t] = (uint32_t)o | ((left[o] == -1) ? 0x80000000u : 0u);
+    }
+    PK_CUDA(cudaSetDevice(device));
+    pk_forest* f = new pk_forest();
+    f->device = device; f->n_trees = n_trees; f->n_features = n_features; f->n_nodes = total; f->max_depth = max_depth;
+    int r;
+    if ((r = dev_alloc(&f->d_nodes, (size_t)total)) || (r = dev_alloc(&f->d_root, (size_t)n_trees)) ||
+        (r = dev_alloc(&f->d_orig, (size_t)total))) {
+        pk_forest_destroy(f);
+        return r;
+    }
+    PK_CUDA(cudaMemcpy(f->d_nodes, nodes.data(), (size_t)total * sizeof(uint2), cudaMemcpyHostToDevice));
+    PK_CUDA(cudaMemcpy(f->d_root, roots.data(), (size_t)n_trees * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    PK_CUDA(cudaMemcpy(f->d_orig, orig.data(), (size_t)total * sizeof(int32_t), cudaMemcpyHostToDevice));
+    *out = f;
+    return PK_OK;
+}
+
+extern "C" int pk_forest_destroy(pk_forest* f) {
+    if (!f) return PK_OK;
+    cudaSetDevice(f->device);
+    dev_free(f->d_nodes); dev_free(f->d_root); dev_free(f->d_orig);
+    delete f;
+    return PK_OK;
+}
+
+extern "C" int pk_forest_info(const pk_forest* f, int32_t* n_trees, int32_t* n_features, int64_t* n_nodes) {
+    if (!f) { pk_set_error("pk_forest_info: NULL forest"); return PK_EINVAL; }
+    if (n_trees) *n_trees = f->n_trees;
+    if (n_features) *n_features = f->n_features;
+    if (n_nodes) *n_nodes = f->n_nodes;
+    return PK_OK;
+}
+
+extern "C" int pk_forest_apply(pk_forest* f, const float* X, int64_t n_rows, int32_t* leaves, double* proba, void* stream) {
+    if (!f || !X || n_rows < 0) { pk_set_error("pk_forest_apply: bad argument"); return PK_EINVAL; }
+    PK_CUDA(cudaSetDevice(f->device));
+    return pk_launch_forest(f, X, nullptr, n_rows, leaves, proba, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------
+// chromosome
+// ---------------------------------------------------------------------------
+extern "C" int pk_chrom_create(int device, int32_t n_bins, int32_t width, int32_t lower, int32_t upper, int balanced,
+                               void* stream, pk_chrom** out) {
+    if (!out) { pk_set_error("pk_chrom_create: out is NULL"); return PK_EINVAL; }
+    if (n_bins <= 0 || width < 1 || width > PK_MAX_W) {
+        pk_set_error("pk_chrom_create: n_bins=%d width=%d unsupported (1 <= width <= %d)", n_bins, width, PK_MAX_W);
+        return PK_EINVAL;
+    }
+    int32_t lo = std::max(lower, width + 1);               // scoreUtils.py:13
+    int32_t up = std::min(upper, n_bins - 2 * width);      // scoreUtils.py:14
+    if (up + 2 * width < 0) {
+        pk_set_error("pk_chrom_create: chromosome of %d bins is too small for width %d", n_bins, width);
+        return PK_EINVAL;
+    }
+    PK_CUDA(cudaSetDevice(device));
+    pk_chrom* c = new pk_chrom();
+    c->device = device; c->stream = (cudaStream_t)stream;
+    c->n = n_bins; c->w = width; c->S = 2 * width + 1; c->F = c->S * c->S;
+    c->lower = lo; c->upper = up; c->ND = up + 2 * width + 1;
+    c->pitch = ((int64_t)n_bins + 31) / 32 * 32;
+    c->balanced = balanced ? 1 : 0;
+    c->LP = c->pitch / 32 + 8;
+    c->row_begin = 0; c->row_end = n_bins;
+    int r = PK_OK;
+    const size_t bandsz = (size_t)c->ND * (size_t)c->pitch;
+    if ((r = dev_alloc(&c->d_band, bandsz)) || (r = dev_alloc(&c->d_w, (size_t)n_bins)) ||
+        (r = dev_alloc(&c->d_valid, (size_t)n_bins)) || (r = dev_alloc(&c->d_scratch, bandsz)) ||
+        (r = dev_alloc(&c->d_leaf_start, (size_t)c->ND * c->LP)) || (r = dev_alloc(&c->d_leaf_sum, (size_t)c->ND * c->LP)) ||
+        (r = dev_alloc(&c->d_diag_sum, (size_t)c->ND)) || (r = dev_alloc(&c->d_diag_cnt, (size_t)c->ND)) ||
+        (r = dev_alloc(&c->d_exp, (size_t)c->ND)) || (r = dev_alloc(&c->d_bg, (size_t)c->ND)) ||
+        (r = dev_alloc(&c->d_flags, 4)) || (r = dev_alloc(&c->d_counters, 4))) {
+        pk_chrom_destroy(c);
+        return r;
+    }
+    for (auto& e : c->ev) {
+        if (cudaEventCreate(&e) != cudaSuccess) { pk_set_error("cudaEventCreate failed"); pk_chrom_destroy(c); return PK_ECUDA; }
+    }
+    *out = c;
+    return PK_OK;
+}
+
+extern "C" int pk_chrom_destroy(pk_chrom* c) {
+    if (!c) return PK_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream); else cudaDeviceSynchronize();
+    dev_free(c->d_band); dev_free(c->d_w); dev_free(c->d_valid); dev_free(c->d_scratch);
+    dev_free(c->d_leaf_start); dev_free(c->d_leaf_sum); dev_free(c->d_diag_sum); dev_free(c->d_diag_cnt);
+    dev_free(c->d_exp); dev_free(c->d_bg); dev_free(c->d_flags); dev_free(c->d_counters);
+    dev_free(c->d_b1); dev_free(c->d_b2); dev_free(c->d_cnt);
+    dev_free(c->d_cnt_all); dev_free(c->d_cnt_tile); dev_free(c->d_off_all); dev_free(c->d_off_tile);
+    dev_free(c->d_cx); dev_free(c->d_cd); dev_free(c->d_crank);
+    dev_free(c->d_keep); dev_free(c->d_fea32); dev_free(c->d_prob); dev_free(c->d_batch_win);
+    dev_free(c->d_rx); dev_free(c->d_ry); dev_free(c->d_rb); dev_free(c->d_rp); dev_free(c->d_rv);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    delete c;
+    return PK_OK;
+}
+
+extern "C" int pk_chrom_bounds(const pk_chrom* c, int32_t* lower_eff, int32_t* upper_eff, int32_t* exp_len) {
+    if (!c) { pk_set_error("pk_chrom_bounds: NULL handle"); return PK_EINVAL; }
+    if (lower_eff) *lower_eff = c->lower;
+    if (upper_eff) *upper_eff = c->upper;
+    if (exp_len) *exp_len = c->ND;
+    return PK_OK;
+}
+
+static float ev_ms(pk_chrom* c, int a, int b) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+    return ms;
+}
+
+extern "C" int pk_chrom_upload_pixels(pk_chrom* c, const int32_t* bin1, const int32_t* bin2, const int32_t* count,
+                                      int64_t nnz, const double* weights, int mem) {
+    if (!c || nnz < 0 || (nnz > 0 && (!bin1 || !bin2 || !count))) { pk_set_error("pk_chrom_upload_pixels: bad argument"); return PK_EINVAL; }
+    if (c->balanced && !weights) { pk_set_error("pk_chrom_upload_pixels: balanced mode needs weights"); return PK_EINVAL; }
+    PK_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int32_t *p1 = bin1, *p2 = bin2, *pc = count;
+    if (mem == PK_MEM_HOST) {
+        int64_t cap = c->pix_cap;
+        if (nnz > cap || !c->d_b1) {
+            dev_free(c->d_b1); dev_free(c->d_b2); dev_free(c->d_cnt);
+            cap = std::max<int64_t>(nnz, 1024);
+            PK_CHECK(dev_alloc(&c->d_b1, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_b2, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_cnt, (size_t)cap));
+            c->pix_cap = cap;
+        }
+        PK_CUDA(cudaMemcpyAsync(c->d_b1, bin1, (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
+        PK_CUDA(cudaMemcpyAsync(c->d_b2, bin2, (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
+        PK_CUDA(cudaMemcpyAsync(c->d_cnt, count, (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
+        p1 = c->d_b1; p2 = c->d_b2; pc = c->d_cnt;
+    }
+    if (c->balanced)
+        PK_CUDA(cudaMemcpyAsync(c->d_w, weights, (size_t)c->n * sizeof(double),
+                                mem == PK_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    PK_CUDA(cudaEventRecord(c->ev[0], s));
+    PK_CUDA(cudaMemsetAsync(c->d_band, 0, (size_t)c->ND * c->pitch * sizeof(int32_t), s));
+    PK_CUDA(cudaMemsetAsync(c->d_valid, 0, (size_t)c->n, s));
+    PK_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int32_t), s));
+    PK_CHECK(pk_launch_scatter(c, p1, p2, pc, nnz));
+    PK_CUDA(cudaEventRecord(c->ev[1], s));
+    PK_CHECK(pk_launch_diag_sums(c));
+    PK_CUDA(cudaEventRecord(c->ev[2], s));
+    c->has_pixels = true; c->has_expected = false; c->has_candidates = false; c->has_scores = false;
+    return PK_OK;
+}
+
+extern "C" int pk_chrom_diag_sums(pk_chrom* c, double* out_sum, int64_t* out_cnt) {
+    if (!c || !out_sum || !out_cnt) { pk_set_error("pk_chrom_diag_sums: bad argument"); return PK_EINVAL; }
+    if (!c->has_pixels) { pk_set_error("pk_chrom_diag_sums: no pixels uploaded"); return PK_ESTATE; }
+    PK_CUDA(cudaSetDevice(c->device));
+    PK_CUDA(cudaMemcpyAsync(out_sum, c->d_diag_sum, (size_t)c->ND * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PK_CUDA(cudaMemcpyAsync(out_cnt, c->d_diag_cnt, (size_t)c->ND * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    PK_CUDA(cudaStreamSynchronize(c->stream));
+    return PK_OK;
+}
+
+extern "C" int pk_chrom_set_expected(pk_chrom* c, const double* exp_arr, const double* background) {
+    if (!c || !exp_arr || !background) { pk_set_error("pk_chrom_set_expected: bad argument"); return PK_EINVAL; }
+    PK_CUDA(cudaSetDevice(c->device));
+    PK_CUDA(cudaMemcpyAsync(c->d_exp, exp_arr, (size_t)c->ND * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PK_CUDA(cudaMemcpyAsync(c->d_bg, background, (size_t)c->ND * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PK_CUDA(cudaStreamSynchronize(c->stream));   // the host arrays may be pageable temporaries
+    c->has_expected = true; c->has_candidates = false; c->has_scores = false;
+    return PK_OK;
+}
+
+extern "C" int pk_chrom_fit_expected(pk_chrom* c) {
+    if (!c) { pk_set_error("pk_chrom_fit_expected: NULL handle"); return PK_EINVAL; }
+    if (!c->has_pixels) { pk_set_error("pk_chrom_fit_expected: no pixels uploaded"); return PK_ESTATE; }
+    std::vector<double> sum((size_t)c->ND), e((size_t)c->ND);
+    std::vector<long long> cnt((size_t)c->ND);
+    PK_CUDA(cudaSetDevice(c->device));
+    PK_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    PK_CUDA(cudaMemcpyAsync(sum.data(), c->d_diag_sum, (size_t)c->ND * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PK_CUDA(cudaMemcpyAsync(cnt.data(), c->d_diag_cnt, (size_t)c->ND * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    PK_CUDA(cudaStreamSynchronize(c->stream));
+    PK_CHECK(pk_fit_expected_host(sum.data(), cnt.data(), c->ND, e.data()));
+    PK_CUDA(cudaMemcpyAsync(c->d_exp, e.data(), (size_t)c->ND * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PK_CUDA(cudaMemcpyAsync(c->d_bg, e.data(), (size_t)c->ND * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PK_CUDA(cudaEventRecord(c->ev[4], c->stream));
+    PK_CUDA(cudaStreamSynchronize(c->stream));
+    c->has_expected = true; c->has_candidates = false; c->has_scores = false;
+    return PK_OK;
+}
+
+extern "C" int pk_chrom_get_expected(pk_chrom* c, double* out_exp) {
+    if (!c || !out_exp) { pk_set_error("pk_chrom_get_expected: bad argument"); return PK_EINVAL; }
+    if (!c->has_expected) { pk_set_error("pk_chrom_get_expected: expected curve not set"); return PK_ESTATE; }
+    PK_CUDA(cudaSetDevice(c->device));
+    PK_CUDA(cudaMemcpyAsync(out_exp, c->d_exp, (size_t)c->ND * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PK_CUDA(cudaStreamSynchronize(c->stream));
+    return PK_OK;
+}
+
+extern "C" int pk_chrom_find_candidates(pk_chrom* c, int32_t row_begin, int32_t row_end, int64_t* n_candidates) {
+    if (!c) { pk_set_error("pk_chrom_find_candidates: NULL handle"); return PK_EINVAL; }
+    if (!c->has_expected) { pk_set_error("pk_chrom_find_candidates: expected curve not set"); return PK_ESTATE; }
+    if (row_begin < 0 || row_end > c->n || row_begin > row_end) { pk_set_error("pk_chrom_find_candidates: bad row range [%d, %d)", row_begin, row_end); return PK_EINVAL; }
+    PK_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    c->row_begin = row_begin; c->row_end = row_end;
+    c->whole = (row_begin == 0 && row_end == c->n);
+    c->n_cand = c->n_cand_all = 0;
+    const int nd = c->upper - c->lower + 1;
+    PK_CUDA(cudaEventRecord(c->ev[5], s));
+    if (nd > 0) {
+        c->n_chunks = (c->n + 1023) / 1024;
+        const int64_t m = (int64_t)nd * c->n_chunks;
+        if (m + 1 > c->cnt_cap) {
+            dev_free(c->d_cnt_all); dev_free(c->d_cnt_tile); dev_free(c->d_off_all); dev_free(c->d_off_tile);
+            PK_CHECK(dev_alloc(&c->d_cnt_all, (size_t)m + 1)); PK_CHECK(dev_alloc(&c->d_cnt_tile, (size_t)m + 1));
+            PK_CHECK(dev_alloc(&c->d_off_all, (size_t)m + 1)); PK_CHECK(dev_alloc(&c->d_off_tile, (size_t)m + 1));
+            c->cnt_cap = m + 1;
+        }
+        const double* d_crit = nullptr;
+        int32_t kmax = 0;
+        int32_t flags[4] = {0, 0, 0, 0};
+        PK_CUDA(cudaMemcpyAsync(flags, c->d_flags, sizeof flags, cudaMemcpyDeviceToHost, s));
+        PK_CUDA(cudaStreamSynchronize(s));
+        // table covers the largest count in the band (flags[1]); counts above 2^22 are refused
+        PK_CHECK(pk_poisson_table_device(c->device, std::min(flags[1], 1 << 22), &d_crit, &kmax));
+        PK_CHECK(pk_launch_candidates(c, d_crit, kmax, false));
+        PK_CHECK(pk_launch_scan2(c, m));
+        uint32_t tot_all = 0, tot_tile = 0;
+        PK_CUDA(cudaMemcpyAsync(&tot_all, c->d_off_all + m, 4, cudaMemcpyDeviceToHost, s));
+        PK_CUDA(cudaMemcpyAsync(&tot_tile, c->d_off_tile + m, 4, cudaMemcpyDeviceToHost, s));
+        PK_CUDA(cudaMemcpyAsync(flags, c->d_flags, sizeof flags, cudaMemcpyDeviceToHost, s));
+        PK_CUDA(cudaStreamSynchronize(s));
+        if (flags[0]) {
+            pk_set_error("pk_chrom_find_candidates: raw count above the Poisson table limit (2^22)");
+            return PK_EUNSUPPORTED;
+        }
+        c->n_cand_all = tot_all; c->n_cand = tot_tile;
+        if (c->n_cand > c->cand_cap || !c->d_cx) {
+            dev_free(c->d_cx); dev_free(c->d_cd); dev_free(c->d_crank);
+            int64_t cap = std::max<int64_t>(c->n_cand + c->n_cand / 8, 1024);
+            PK_CHECK(dev_alloc(&c->d_cx, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_cd, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_crank, (size_t)cap));
+            c->cand_cap = cap;
+        }
+        PK_CHECK(pk_launch_candidates(c, d_crit, kmax, true));
+    }
+    PK_CUDA(cudaEventRecord(c->ev[6], s));
+    if (n_candidates) *n_candidates = c->n_cand;
+    c->has_candidates = true; c->has_scores = false;
+    return PK_OK;
+}
+
+extern "C" int pk_chrom_candidates(pk_chrom* c, int32_t* out_x, int32_t* out_y, int64_t capacity, int64_t* n) {
+    if (!c || !n) { pk_set_error("pk_chrom_candidates: bad argument"); return PK_EINVAL; }
+    if (!c->has_candidates) { pk_set_error("pk_chrom_candidates: find_candidates not called"); return PK_ESTATE; }
+    *n = c->n_cand;
+    if (!out_x && !out_y) return PK_OK;
+    if (capacity < c->n_cand) { pk_set_error("pk_chrom_candidates: capacity %lld < %lld", (long long)capacity, (long long)c->n_cand); return PK_ECAPACITY; }
+    if (c->n_cand == 0) return PK_OK;
+    PK_CUDA(cudaSetDevice(c->device));
+    std::vector<int32_t> d((size_t)c->n_cand);
+    PK_CUDA(cudaMemcpyAsync(out_x, c->d_cx, (size_t)c->n_cand * 4, cudaMemcpyDeviceToHost, c->stream));
+    PK_CUDA(cudaMemcpyAsync(d.data(), c->d_cd, (size_t)c->n_cand * 4, cudaMemcpyDeviceToHost, c->stream));
+    PK_CUDA(cudaStreamSynchronize(c->stream));
+    if (out_y) for (int64_t i = 0; i < c->n_cand; ++i) out_y[i] = out_x[i] + d[(size_t)i];
+    return PK_OK;
+}
+
+static int ensure_score_buffers(pk_chrom* c) {
+    if (c->n_cand > c->fea_cap || !c->d_keep) {
+        dev_free(c->d_keep); dev_free(c->d_fea32); dev_free(c->d_prob);
+        int64_t cap = std::max<int64_t>(c->n_cand + c->n_cand / 8, 1024);
+        PK_CHECK(dev_alloc(&c->d_keep, (size_t)cap));
+        PK_CHECK(dev_alloc(&c->d_fea32, (size_t)cap * c->F));
+        PK_CHECK(dev_alloc(&c->d_prob, (size_t)cap));
+        c->fea_cap = cap;
+    }
+    if (c->n_cand > c->rec_cap || !c->d_rx) {
+        dev_free(c->d_rx); dev_free(c->d_ry); dev_free(c->d_rb); dev_free(c->d_rp); dev_free(c->d_rv);
+        int64_t cap = std::max<int64_t>(c->n_cand + c->n_cand / 8, 1024);
+        PK_CHECK(dev_alloc(&c->d_rx, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_ry, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_rb, (size_t)cap));
+        PK_CHECK(dev_alloc(&c->d_rp, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_rv, (size_t)cap));
+        c->rec_cap = cap;
+    }
+    c->n_batches = (c->n_cand_all + PK_BATCH - 1) / PK_BATCH;
+    if (c->n_batches + 1 > c->batch_cap || !c->d_batch_win) {
+        dev_free(c->d_batch_win);
+        int64_t cap = std::max<int64_t>(c->n_batches + 1, 64);
+        PK_CHECK(dev_alloc(&c->d_batch_win, (size_t)cap));
+        c->batch_cap = cap;
+    }
+    PK_CUDA(cudaMemsetAsync(c->d_batch_win, 0, (size_t)c->batch_cap * 4, c->stream));
+    PK_CUDA(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream));
+    return PK_OK;
+}
+
+extern "C" int pk_chrom_features(pk_chrom* c, uint8_t* keep, float* fea32, double* fea64, int64_t capacity) {
+    if (!c) { pk_set_error("pk_chrom_features: NULL handle"); return PK_EINVAL; }
+    if (!c->has_candidates) { pk_set_error("pk_chrom_features: find_candidates not called"); return PK_ESTATE; }
+    if (capacity < c->n_cand) { pk_set_error("pk_chrom_features: capacity too small"); return PK_ECAPACITY; }
+    if (c->n_cand == 0) return PK_OK;
+    PK_CUDA(cudaSetDevice(c->device));
+    PK_CHECK(ensure_score_buffers(c));
+    double* d64 = nullptr;
+    if (fea64) PK_CHECK(dev_alloc(&d64, (size_t)c->n_cand * c->F));
+    int r = pk_launch_features(c, d64);
+    if (r == PK_OK) {
+        cudaError_t e = cudaSuccess;
+        if (keep) e = cudaMemcpyAsync(keep, c->d_keep, (size_t)c->n_cand, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && fea32) e = cudaMemcpyAsync(fea32, c->d_fea32, (size_t)c->n_cand * c->F * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && fea64) e = cudaMemcpyAsync(fea64, d64, (size_t)c->n_cand * c->F * 8, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { pk_set_error("pk_chrom_features: %s", cudaGetErrorString(e)); r = PK_ECUDA; }
+    }
+    if (d64) cudaFree(d64);
+    c->has_scores = false;
+    return r;
+}
+
+extern "C" int pk_chrom_score(pk_chrom* c, pk_forest* f, double min_prob) {
+    if (!c || !f) { pk_set_error("pk_chrom_score: NULL handle"); return PK_EINVAL; }
+    if (!c->has_candidates) { pk_set_error("pk_chrom_score: find_candidates not called"); return PK_ESTATE; }
+    if (f->device != c->device) { pk_set_error("pk_chrom_score: forest lives on device %d, chromosome on %d", f->device, c->device); return PK_EINVAL; }
+    if (f->n_features != c->F) { pk_set_error("pk_chrom_score: forest has %d features, window has %d", f->n_features, c->F); return PK_EINVAL; }
+    PK_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    PK_CHECK(ensure_score_buffers(c));
+    PK_CUDA(cudaEventRecord(c->ev[7], s));
+    PK_CHECK(pk_launch_features(c, nullptr));
+    PK_CUDA(cudaEventRecord(c->ev[8], s));
+    PK_CHECK(pk_launch_forest(f, c->d_fea32, c->d_keep, c->n_cand, nullptr, c->d_prob, s));
+    PK_CUDA(cudaEventRecord(c->ev[9], s));
+    PK_CHECK(pk_launch_emit(c, min_prob));
+    PK_CUDA(cudaEventRecord(c->ev[10], s));
+    c->has_scores = true;
+    return PK_OK;
+}
+
+extern "C" int pk_chrom_result_count(pk_chrom* c, int64_t* n_records, int64_t* n_candidates, int64_t* n_windows) {
+    if (!c) { pk_set_error("pk_chrom_result_count: NULL handle"); return PK_EINVAL; }
+    if (!c->has_scores) { pk_set_error("pk_chrom_result_count: score not called"); return PK_ESTATE; }
+    PK_CUDA(cudaSetDevice(c->device));
+    unsigned long long h[4] = {0, 0, 0, 0};
+    PK_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    PK_CUDA(cudaStreamSynchronize(c->stream));
+    if (n_records) *n_records = (int64_t)h[0];
+    if (n_candidates) *n_candidates = c->n_cand;
+    if (n_windows) *n_windows = (int64_t)h[1];
+    return PK_OK;
+}
+
+extern "C" int pk_chrom_batch_windows(pk_chrom* c, int64_t* out, int64_t capacity, int64_t* n_batches) {
+    if (!c || !n_batches) { pk_set_error("pk_chrom_batch_windows: bad argument"); return PK_EINVAL; }
+    if (!c->has_scores) { pk_set_error("pk_chrom_batch_windows: score not called"); return PK_ESTATE; }
+    *n_batches = c->n_batches;
+    if (!out) return PK_OK;
+    if (capacity < c->n_batches) { pk_set_error("pk_chrom_batch_windows: capacity too small"); return PK_ECAPACITY; }
+    PK_CUDA(cudaSetDevice(c->device));
+    std::vector<int32_t> h((size_t)std::max<int64_t>(c->n_batches, 1));
+    PK_CUDA(cudaMemcpyAsync(h.data(), c->d_batch_win, (size_t)c->n_batches * 4, cudaMemcpyDeviceToHost, c->stream));
+    PK_CUDA(cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < c->n_batches; ++i) out[i] = h[(size_t)i];
+    return PK_OK;
+}
+
+extern "C" int pk_chrom_fetch_results(pk_chrom* c, int32_t* out_x, int32_t* out_y, double* out_prob, double* out_val,
+                                      int32_t* out_batch, int64_t capacity, int mem) {
+    if (!c) { pk_set_error("pk_chrom_fetch_results: NULL handle"); return PK_EINVAL; }
+    int64_t n = 0;
+    PK_CHECK(pk_chrom_result_count(c, &n, nullptr, nullptr));
+    if (capacity < n) { pk_set_error("pk_chrom_fetch_results: capacity %lld < %lld records", (long long)capacity, (long long)n); return PK_ECAPACITY; }
+    if (n == 0) return PK_OK;
+    cudaStream_t s = c->stream;
+    if (mem == PK_MEM_DEVICE) {
+        if (out_x) PK_CUDA(cudaMemcpyAsync(out_x, c->d_rx, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+        if (out_y) PK_CUDA(cudaMemcpyAsync(out_y, c->d_ry, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+        if (out_prob) PK_CUDA(cudaMemcpyAsync(out_prob, c->d_rp, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+        if (out_val) PK_CUDA(cudaMemcpyAsync(out_val, c->d_rv, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+        if (out_batch) PK_CUDA(cudaMemcpyAsync(out_batch, c->d_rb, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+        return PK_OK;
+    }
+    std::vector<int32_t> x((size_t)n), y((size_t)n), b((size_t)n);
+    std::vector<double> p((size_t)n), v((size_t)n);
+    PK_CUDA(cudaMemcpyAsync(x.data(), c->d_rx, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    PK_CUDA(cudaMemcpyAsync(y.data(), c->d_ry, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    PK_CUDA(cudaMemcpyAsync(p.data(), c->d_rp, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    PK_CUDA(cudaMemcpyAsync(v.data(), c->d_rv, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    PK_CUDA(cudaMemcpyAsync(b.data(), c->d_rb, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    PK_CUDA(cudaStreamSynchronize(s));
+    std::vector<int64_t> idx((size_t)n);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::sort(idx.begin(), idx.end(), [&](int64_t a, int64_t bb) {
+        return x[(size_t)a] != x[(size_t)bb] ? x[(size_t)a] < x[(size_t)bb] : y[(size_t)a] < y[(size_t)bb];
+    });
+    for (int64_t i = 0; i < n; ++i) {
+        size_t j = (size_t)idx[(size_t)i];
+        if (out_x) out_x[i] = x[j];
+        if (out_y) out_y[i] = y[j];
+        if (out_prob) out_prob[i] = p[j];
+        if (out_val) out_val[i] = v[j];
+        if (out_batch) out_batch[i] = b[j];
+    }
+    return PK_OK;
+}
+
+extern "C" int pk_chrom_stage_ms(pk_chrom* c, float* out_ms) {
+    if (!c || !out_ms) { pk_set_error("pk_chrom_stage_ms: bad argument"); return PK_EINVAL; }
+    PK_CUDA(cudaSetDevice(c->device));
+    PK_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 8; ++i) out_ms[i] = 0.f;
+    out_ms[0] = ev_ms(c, 0, 1);
+    out_ms[1] = ev_ms(c, 1, 2);
+    out_ms[2] = ev_ms(c, 3, 4);
+    out_ms[3] = ev_ms(c, 5, 6);
+    if (c->has_scores) {
+        out_ms[4] = ev_ms(c, 7, 8);
+        out_ms[5] = ev_ms(c, 8, 9);
+        out_ms[6] = ev_ms(c, 9, 10);
+    }
+    return PK_OK;
+}

@@ -1,0 +1,108 @@
+// Shared declarations of the peakachu_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "peakachu_b200.h"
+
+#define PK_BATCH 100000            // scoreUtils.py:104
+#define PK_MAX_W 12                // window half-width limit: (2w+1)^2 <= 625 features
+#define PK_FEAT_BITS 10            // packed node: feature index < 1024
+
+void pk_set_error(const char* fmt, ...);
+
+#define PK_CUDA(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            pk_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return PK_ECUDA;                                                               \
+        }                                                                                  \
+    } while (0)
+
+#define PK_CHECK(call)             \
+    do {                           \
+        int r__ = (call);          \
+        if (r__ != PK_OK) return r__; \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// forest: nodes renumbered in preorder (left child = parent + 1), 8 bytes each.
+//   internal: .x = float32 threshold rounded toward -inf (x_f32 <= t_f64 <=> x_f32 <= .x)
+//             .y = feature[0:10) | missing_go_left<<10 | left_is_leaf<<11 |
+//                  right_is_leaf<<12 | (right - self)<<13
+//   leaf:     the 8 bytes are the float64 class-1 fraction
+// ---------------------------------------------------------------------------
+struct pk_forest {
+    int device = 0;
+    int32_t n_trees = 0, n_features = 0;
+    int64_t n_nodes = 0;
+    uint2* d_nodes = nullptr;        // [n_nodes]
+    uint32_t* d_root = nullptr;      // [n_trees] packed index of the root | (root_is_leaf << 31)
+    int32_t* d_orig = nullptr;       // [n_nodes] tree-local sklearn node id (apply tap)
+    int32_t max_depth = 0;
+};
+
+struct pk_chrom {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int32_t n = 0, w = 0, S = 0, F = 0;
+    int32_t lower = 0, upper = 0;    // effective (clamped)
+    int32_t ND = 0;                  // stored diagonals = upper + 2w + 1 = exp_len
+    int64_t pitch = 0;               // band row pitch (elements)
+    int balanced = 0;
+    // state
+    bool has_pixels = false, has_expected = false, has_candidates = false, has_scores = false;
+    int32_t row_begin = 0, row_end = 0;
+    bool whole = true;
+    // device buffers
+    int32_t* d_band = nullptr;       // [ND][pitch] raw counts, diagonal-major
+    double* d_w = nullptr;           // [n]
+    uint8_t* d_valid = nullptr;      // [n]
+    double* d_scratch = nullptr;     // [ND][pitch] compacted diagonal values
+    int32_t* d_leaf_start = nullptr; // [ND][LP]
+    double* d_leaf_sum = nullptr;    // [ND][LP]
+    int64_t LP = 0;
+    double* d_diag_sum = nullptr;    // [ND]
+    long long* d_diag_cnt = nullptr; // [ND]
+    double* d_exp = nullptr;         // [ND]
+    double* d_bg = nullptr;          // [ND]
+    int32_t* d_flags = nullptr;      // [4]: 0 = poisson table overflow, 1 = max count seen
+    // upload staging
+    int32_t *d_b1 = nullptr, *d_b2 = nullptr, *d_cnt = nullptr;
+    int64_t pix_cap = 0;
+    // candidates
+    int32_t n_chunks = 0;
+    uint32_t* d_cnt_all = nullptr;   // [nd_cand * n_chunks] whole-chromosome counts
+    uint32_t* d_cnt_tile = nullptr;  // same, restricted to the row tile
+    uint32_t* d_off_all = nullptr;   // exclusive scans (+1 total)
+    uint32_t* d_off_tile = nullptr;
+    int64_t cnt_cap = 0;
+    int64_t n_cand = 0, n_cand_all = 0;
+    int64_t cand_cap = 0;
+    int32_t *d_cx = nullptr, *d_cd = nullptr, *d_crank = nullptr;
+    // scoring
+    uint8_t* d_keep = nullptr;
+    float* d_fea32 = nullptr;        // [n_cand][F]
+    int64_t fea_cap = 0;
+    double* d_prob = nullptr;
+    int32_t* d_batch_win = nullptr;  // [n_batches]
+    int64_t n_batches = 0, batch_cap = 0;
+    // records
+    int32_t *d_rx = nullptr, *d_ry = nullptr, *d_rb = nullptr;
+    double *d_rp = nullptr, *d_rv = nullptr;
+    unsigned long long* d_counters = nullptr;   // [4]: 0 = n_records, 1 = n_windows
+    int64_t rec_cap = 0;
+    // timing
+    cudaEvent_t ev[16] = {};
+    float stage_ms[8] = {};
+};
+
+// Poisson decision table (host long double -> float64), per device copy
+int pk_poisson_table_host(int32_t k_max, const double** out);      // grows a process-wide table
+int pk_poisson_table_device(int device, int32_t k_min_size, const double** d_out, int32_t* k_max_out);
+
+// expected-curve fit on the host (PAVA + numpy.interp restatement)
+int pk_fit_expected_host(const double* sum, const long long* cnt, int32_t len, double* out_exp);

@@ -1,0 +1,206 @@
+// Host-side arithmetic of the peakachu_b200 library: the Poisson decision table and
+// the expected-curve fit. Compiled with -ffp-contract=off: every float64 operation
+// below is one IEEE operation, in the order the reference's libraries perform it.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include <stdint.h>
+
+#include "peakachu_b200.h"
+
+void pk_set_error(const char* fmt, ...);
+
+// ---------------------------------------------------------------------------
+// Poisson decision table.
+// Reference: scoreUtils.py:59-67 keeps a pixel when stats.poisson(mu).sf(k) < 0.01.
+// sf(k, mu) = P(k+1, mu) (regularised lower incomplete gamma) is strictly
+// increasing in mu, so the test is mu < crit[k] with crit[k] the smallest float64
+// whose upper tail reaches 0.01. The table is evaluated in 80-bit long double
+// (series for P(a, x), x < a; prefactor through log1p so no large terms cancel).
+// ---------------------------------------------------------------------------
+namespace {
+
+long double stirling_corr(long double a) {
+    long double a2 = a * a, a3 = a2 * a, a5 = a3 * a2, a7 = a5 * a2, a9 = a7 * a2;
+    return 1.0L / (12.0L * a) - 1.0L / (360.0L * a3) + 1.0L / (1260.0L * a5) - 1.0L / (1680.0L * a7) +
+           1.0L / (1188.0L * a9);
+}
+
+// returns P(a, mu) and, through *pref, mu^a e^-mu / Gamma(a+1)
+long double lower_gamma_p(long double a, long double mu, long double* pref) {
+    long double lp;
+    if (a < 32.0L) {
+        lp = a * logl(mu) - mu - lgammal(a + 1.0L);
+    } else {
+        const long double two_pi = 6.283185307179586476925286766559L;
+        long double u = (mu - a) / a;
+        lp = a * (log1pl(u) - u) - 0.5L * logl(two_pi * a) - stirling_corr(a);
+    }
+    long double term = 1.0L, s = 1.0L, den = a;
+    for (int it = 0; it < 10000000; ++it) {
+        den += 1.0L;
+        term *= mu / den;
+        s += term;
+        if (term < s * 1e-22L) break;
+    }
+    long double p = expl(lp);
+    if (pref) *pref = p;
+    return s * p;
+}
+
+double critical_mu(int k) {
+    const long double target = 0.01L;
+    const long double a = (long double)k + 1.0L;
+    long double lo = 0.0L, hi = a;                       // sf(lo) = 0 < target <= sf(hi)
+    long double t = 1.0L - 1.0L / (9.0L * a) - 2.3263478740408408L * sqrtl(1.0L / (9.0L * a));
+    long double mu = a * t * t * t;                      // Wilson-Hilferty start
+    if (!(mu > lo && mu < hi)) mu = 0.5L * a;
+    for (int it = 0; it < 200; ++it) {
+        long double pref;
+        long double f = lower_gamma_p(a, mu, &pref) - target;
+        if (f < 0) lo = mu; else hi = mu;
+        long double pmf = pref * a / mu;                 // d sf / d mu
+        long double nx = mu - f / pmf;
+        if (!(nx > lo && nx < hi)) nx = 0.5L * (lo + hi);
+        if (fabsl(nx - mu) <= 1e-19L * mu || (double)lo == (double)hi) { mu = nx; break; }
+        mu = nx;
+    }
+    double m = (double)mu;
+    // smallest float64 m with sf(k, m) >= target
+    for (int g = 0; g < 64 && lower_gamma_p(a, (long double)m, nullptr) < target; ++g) m = std::nextafter(m, INFINITY);
+    for (int g = 0; g < 64; ++g) {
+        double prev = std::nextafter(m, 0.0);
+        if (lower_gamma_p(a, (long double)prev, nullptr) >= target) m = prev; else break;
+    }
+    return m;
+}
+
+std::mutex g_tab_mu;
+std::vector<double> g_tab;    // index k; [0] = smallest mu with 1 - exp(-mu) >= 0.01
+
+}  // namespace
+
+int pk_poisson_table_host(int32_t k_max, const double** out) {
+    if (k_max < 0 || k_max > (1 << 24)) {
+        pk_set_error("pk_poisson_table_host: k_max %d out of range", k_max);
+        return PK_EINVAL;
+    }
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    size_t have = g_tab.size();
+    if (have < (size_t)k_max + 1) {
+        // grow geometrically; fill in parallel
+        size_t want = std::max<size_t>((size_t)k_max + 1, std::max<size_t>(4096, have * 2));
+        g_tab.resize(want);
+        unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back([=]() {
+                for (size_t k = have + t; k < want; k += nt) g_tab[k] = critical_mu((int)k);
+            });
+        for (auto& x : th) x.join();
+    }
+    *out = g_tab.data();
+    return PK_OK;
+}
+
+extern "C" int pk_poisson_critical_mu(int32_t k_max, double* out) {
+    const double* tab = nullptr;
+    int r = pk_poisson_table_host(k_max, &tab);
+    if (r != PK_OK) return r;
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    std::copy(g_tab.begin(), g_tab.begin() + k_max + 1, out);
+    return PK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Expected curve: utils.py:160-176.
+//   exp[d] = sum[d] / cnt[d] where cnt[d] > 10, else 0
+//   IsotonicRegression(increasing=False, out_of_bounds='clip').fit(d : exp>0).predict(0..len-1)
+// which is scipy's PAVA (Busing 2022, Alg. 1) on the reversed sequence, sklearn's
+// removal of interior points of constant runs, np.clip of the query, and
+// numpy.interp (y[j] when x hits knot j, else slope*(x - x[j]) + y[j]).
+// ---------------------------------------------------------------------------
+int pk_fit_expected_host(const double* sum, const long long* cnt, int32_t len, double* out_exp) {
+    std::vector<double> xs, ys;
+    for (int32_t d = 0; d < len; ++d) {
+        double e = 0.0;
+        if (cnt[d] > 10) e = sum[d] / (double)cnt[d];
+        if (e > 0) { xs.push_back((double)d); ys.push_back(e); }
+    }
+    const int n = (int)xs.size();
+    if (n == 0) {
+        pk_set_error("expected curve: no distance has a positive mean (reference raises in IsotonicRegression.fit)");
+        return PK_EINVAL;
+    }
+    // PAVA on the reversed values, unit weights
+    std::vector<double> x(n), w(n, 1.0);
+    std::vector<int> r(n + 1, -1);
+    for (int i = 0; i < n; ++i) x[i] = ys[n - 1 - i];
+    r[0] = 0;
+    if (n > 1) r[1] = 1;
+    int b = 0;
+    double xb_prev = x[0], wb_prev = w[0];
+    for (int i = 1; i < n; ++i) {
+        b++;
+        double xb = x[i], wb = w[i];
+        if (xb_prev >= xb) {
+            b--;
+            double sb = wb_prev * xb_prev + wb * xb;
+            wb = wb + wb_prev;
+            xb = sb / wb;
+            while (i < n - 1 && xb >= x[i + 1]) {
+                i++;
+                sb = sb + w[i] * x[i];
+                wb = wb + w[i];
+                xb = sb / wb;
+            }
+            while (b > 0 && x[b - 1] >= xb) {
+                b--;
+                sb = sb + w[b] * x[b];
+                wb = wb + w[b];
+                xb = sb / wb;
+            }
+        }
+        x[b] = xb_prev = xb;
+        w[b] = wb_prev = wb;
+        r[b + 1] = i + 1;
+    }
+    int f = n - 1;
+    for (int k = b; k >= 0; --k) {
+        int t = r[k];
+        double xk = x[k];
+        for (int i = f; i >= t; --i) x[i] = xk;
+        f = t - 1;
+    }
+    std::vector<double> yf(n);
+    for (int i = 0; i < n; ++i) yf[i] = x[n - 1 - i];
+    // knots
+    std::vector<double> kx, ky;
+    for (int i = 0; i < n; ++i) {
+        bool keep = (i == 0 || i == n - 1) || (yf[i] != yf[i - 1]) || (yf[i] != yf[i + 1]);
+        if (keep) { kx.push_back(xs[i]); ky.push_back(yf[i]); }
+    }
+    const int m = (int)kx.size();
+    const double xmin = xs[0], xmax = xs[n - 1];
+    for (int32_t d = 0; d < len; ++d) {
+        double T = std::min(std::max((double)d, xmin), xmax);
+        if (m == 1) { out_exp[d] = ky[0]; continue; }
+        int j = (int)(std::upper_bound(kx.begin(), kx.end(), T) - kx.begin()) - 1;   // kx[j] <= T
+        j = std::min(std::max(j, 0), m - 1);
+        if (j == m - 1 || kx[j] == T) { out_exp[d] = ky[j]; continue; }
+        double slope = (ky[j + 1] - ky[j]) / (kx[j + 1] - kx[j]);
+        out_exp[d] = slope * (T - kx[j]) + ky[j];
+    }
+    return PK_OK;
+}
+
+// test hook: the fit alone, HOST arrays
+extern "C" int pk_fit_expected(const double* sum, const int64_t* cnt, int32_t len, double* out_exp) {
+    std::vector<long long> c(cnt, cnt + len);
+    return pk_fit_expected_host(sum, c.data(), len, out_exp);
+}

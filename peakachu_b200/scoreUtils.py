@@ -1,0 +1,252 @@
+"""Host-side mirror of the reference's ``peakachu.scoreUtils`` (scoreUtils.py:9-135).
+
+``Chromosome`` keeps the reference's constructor signature, public attributes
+(``exp_arr``, ``background``, ``ridx``, ``cidx``, ``M``) and methods
+(``score(thre) -> (prob_csr, value_csr)``, ``writeBed(outfil, prob_csr, raw_csr)``),
+but every numeric step runs in the CUDA library through the C ABI
+(``include/peakachu_b200.h``). numpy arrays / scipy matrices are only containers
+at the boundary; there is no CPU implementation of the path in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .forest import FlatForest, flatten_forest
+
+
+class DeviceForest:
+    """A forest packed into device node tables (pk_forest_create)."""
+
+    _cache: dict = {}
+
+    def __init__(self, flat: FlatForest, device: int = 0):
+        L = _lib.lib()
+        self.flat, self.device = flat, device
+        self.handle = C.c_void_p()
+        no = _lib.as_c(flat.node_offset, np.int64)
+        fe = _lib.as_c(flat.feature, np.int32)
+        th = _lib.as_c(flat.threshold, np.float64)
+        le = _lib.as_c(flat.left, np.int32)
+        ri = _lib.as_c(flat.right, np.int32)
+        ml = _lib.as_c(flat.missing_left, np.uint8)
+        p1 = _lib.as_c(flat.leaf_p1, np.float64)
+        _lib.check(L.pk_forest_create(device, flat.n_trees, flat.n_features, _lib.ptr(no, _lib.c_i64p),
+                                      _lib.ptr(fe, _lib.c_i32p), _lib.ptr(th, _lib.c_f64p),
+                                      _lib.ptr(le, _lib.c_i32p), _lib.ptr(ri, _lib.c_i32p),
+                                      _lib.ptr(ml, _lib.c_u8p), _lib.ptr(p1, _lib.c_f64p),
+                                      C.byref(self.handle)))
+
+    @property
+    def width(self):
+        return self.flat.width
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            _lib.lib().pk_forest_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @classmethod
+    def of(cls, model, device: int = 0) -> "DeviceForest":
+        """DeviceForest for a sklearn model / FlatForest / DeviceForest, cached per
+        (object, device) so score_genome uploads the forest once."""
+        if isinstance(model, DeviceForest):
+            if model.device != device:
+                return cls.of(model.flat, device)
+            return model
+        key = (id(model), device)
+        hit = cls._cache.get(key)
+        if hit is not None and hit[0] is model:
+            return hit[1]
+        flat = model if isinstance(model, FlatForest) else flatten_forest(model)
+        df = cls(flat, device)
+        cls._cache[key] = (model, df)
+        return df
+
+
+def _upper_pixels_from_csr(raw_M):
+    """Upper-triangle (bin1, bin2, count) of a symmetric scipy matrix of counts."""
+    from scipy import sparse
+    up = sparse.triu(raw_M, k=0).tocoo()
+    cnt = np.asarray(up.data)
+    icnt = np.rint(cnt).astype(np.int32)
+    if not np.array_equal(icnt, cnt):
+        raise ValueError("raw matrix holds non-integer counts; the CUDA path stores int32 counts")
+    return up.row.astype(np.int32), up.col.astype(np.int32), icnt
+
+
+class Chromosome:
+    """Drop-in for ``peakachu.scoreUtils.Chromosome`` (scoreUtils.py:9-38).
+
+    Reference call sites: score_chromosome.py:45-48,51-54 and score_genome.py:58-61,64-67.
+    ``M`` / ``raw_M`` are scipy CSR matrices as there; in balanced mode the balanced
+    values are recomputed on the device from ``raw_M`` and ``weights`` as
+    ``(w[row] * w[col]) * count`` (what ``cooler`` yields), so ``M`` is only
+    consulted for its shape. Use :meth:`from_pixels` to skip building matrices.
+    """
+
+    def __init__(self, M, model, raw_M=None, weights=None, lower=6, upper=300,
+                 cname="chrm", res=10000, width=5, device=0, stream=None):
+        if raw_M is None:
+            raw_M = M
+        if weights is None and M is not raw_M:
+            raise NotImplementedError(
+                "weights=None with M is not raw_M is the reference's .hic (KR/NONE via straw) branch, "
+                "which is outside this path")
+        b1, b2, cnt = _upper_pixels_from_csr(raw_M)
+        self._init(b1, b2, cnt, weights, int(M.shape[0]), model, lower, upper, cname, res, width, device, stream)
+
+    @classmethod
+    def from_pixels(cls, bin1, bin2, count, weights, n_bins, model, lower=6, upper=300,
+                    cname="chrm", res=10000, width=5, device=0, stream=None):
+        """Build from cooler-style upper-triangle pixel columns (chromosome-local bin
+        ids) and the weight column (None = raw mode)."""
+        self = cls.__new__(cls)
+        self._init(bin1, bin2, count, weights, int(n_bins), model, lower, upper, cname, res, width, device, stream)
+        return self
+
+    # -- construction = upload + band + expected + candidates (scoreUtils.py:13-34) --
+    def _init(self, b1, b2, cnt, weights, n, model, lower, upper, cname, res, width, device, stream):
+        L = _lib.lib()
+        _lib.require_device()
+        self.chromname, self.r, self.w = cname, res, width
+        self.model = model
+        self.n = n
+        self.device = device
+        self.weights = None if weights is None else _lib.as_c(weights, np.float64)
+        self._forest = None
+        self._h = C.c_void_p()
+        _lib.check(L.pk_chrom_create(device, n, width, lower, upper, 0 if weights is None else 1,
+                                     C.c_void_p(stream or 0), C.byref(self._h)))
+        lo, up, el = C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(L.pk_chrom_bounds(self._h, C.byref(lo), C.byref(up), C.byref(el)))
+        self.lower, self.upper, self._exp_len = lo.value, up.value, el.value
+        b1, b2, cnt = _lib.as_c(b1, np.int32), _lib.as_c(b2, np.int32), _lib.as_c(cnt, np.int32)
+        _lib.check(L.pk_chrom_upload_pixels(self._h, _lib.ptr(b1), _lib.ptr(b2), _lib.ptr(cnt), b1.size,
+                                            _lib.ptr(self.weights), _lib.PK_MEM_HOST))
+        _lib.check(L.pk_chrom_fit_expected(self._h))
+        self._exp = None
+        ncand = C.c_int64()
+        _lib.check(L.pk_chrom_find_candidates(self._h, 0, n, C.byref(ncand)))
+        self.n_candidates = ncand.value
+        self._cand = None
+        self.M = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            _lib.lib().pk_chrom_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- reference attributes ------------------------------------------------------
+    @property
+    def exp_arr(self):
+        if self._exp is None:
+            e = np.empty(self._exp_len, dtype=np.float64)
+            _lib.check(_lib.lib().pk_chrom_get_expected(self._h, _lib.ptr(e, _lib.c_f64p)))
+            self._exp = e
+        return self._exp
+
+    @property
+    def background(self):
+        return self.exp_arr
+
+    def _candidates(self):
+        if self._cand is None:
+            n = self.n_candidates
+            x, y = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+            got = C.c_int64()
+            _lib.check(_lib.lib().pk_chrom_candidates(self._h, _lib.ptr(x, _lib.c_i32p), _lib.ptr(y, _lib.c_i32p),
+                                                      n, C.byref(got)))
+            self._cand = (x.astype(np.int64), y.astype(np.int64))
+        return self._cand
+
+    @property
+    def ridx(self):
+        return self._candidates()[0]
+
+    @property
+    def cidx(self):
+        return self._candidates()[1]
+
+    # -- parity tap: getwindow over the current candidates (scoreUtils.py:70-93) ------
+    def window_features(self, want64=False):
+        """(keep mask, float32 features[, float64 features]) for every candidate, in
+        reference order; rows of rejected candidates are zero."""
+        n, F = self.n_candidates, (2 * self.w + 1) ** 2
+        keep = np.zeros(n, dtype=np.uint8)
+        f32 = np.zeros((n, F), dtype=np.float32)
+        f64 = np.zeros((n, F), dtype=np.float64) if want64 else None
+        _lib.check(_lib.lib().pk_chrom_features(self._h, _lib.ptr(keep, _lib.c_u8p), _lib.ptr(f32, _lib.c_f32p),
+                                                _lib.ptr(f64, _lib.c_f64p) if want64 else None, n))
+        return (keep.astype(bool), f32, f64) if want64 else (keep.astype(bool), f32)
+
+    # -- scoring (scoreUtils.py:95-125) -----------------------------------------------
+    def score_records(self, thre=0.5):
+        """(x, y, prob, value) numpy arrays sorted by (x, y)."""
+        L = _lib.lib()
+        if self._forest is None:
+            self._forest = DeviceForest.of(self.model, self.device)
+        _lib.check(L.pk_chrom_score(self._h, self._forest.handle, float(thre)))
+        nrec, ncand, nwin = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(L.pk_chrom_result_count(self._h, C.byref(nrec), C.byref(ncand), C.byref(nwin)))
+        n = nrec.value
+        self.n_windows = nwin.value
+        x, y = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+        p, v = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.float64)
+        _lib.check(L.pk_chrom_fetch_results(self._h, _lib.ptr(x), _lib.ptr(y), _lib.ptr(p), _lib.ptr(v), None,
+                                            n, _lib.PK_MEM_HOST))
+        return x, y, p, v
+
+    def score(self, thre=0.5):
+        from scipy import sparse
+        print("scoring matrix {}".format(self.chromname))
+        print("number of candidates {}".format(self.n_candidates))
+        x, y, p, v = self.score_records(thre)
+        shape = (self.n, self.n)
+        result = sparse.csr_matrix((p, (x, y)), shape=shape)
+        self.M = sparse.csr_matrix((v, (x, y)), shape=shape) if x.size else result
+        return result, self.M
+
+    def stage_ms(self):
+        ms = np.zeros(8, dtype=np.float32)
+        _lib.check(_lib.lib().pk_chrom_stage_ms(self._h, _lib.ptr(ms, _lib.c_f32p)))
+        return dict(zip(("band_build", "diag_sums", "expected_fit", "candidate_scan", "features", "forest",
+                         "emit"), ms.tolist()))
+
+    # -- output (scoreUtils.py:127-135) ------------------------------------------------
+    def writeBed(self, outfil, prob_csr, raw_csr):
+        r, c = prob_csr.nonzero()
+        if r.size:
+            pv = np.asarray(prob_csr[r, c]).ravel()
+            rv = np.asarray(raw_csr[r, c]).ravel()
+        else:
+            pv = rv = np.zeros(0)
+        with open(outfil, "a") as out:
+            out.write(format_bedpe(self.chromname, self.r, r, c, pv, rv))
+
+
+def format_bedpe(chromname, res, r, c, prob, value) -> str:
+    """Rows exactly as scoreUtils.py:131-135 prints them: ints from int32 bin index
+    times resolution, floats through str(numpy.float64) (shortest round-trip repr)."""
+    res = int(res)
+    lines = []
+    for i in range(len(r)):
+        a, b = int(r[i]), int(c[i])
+        lines.append("%s\t%d\t%d\t%s\t%d\t%d\t%s\t%s\n" % (
+            chromname, a * res, (a + 1) * res, chromname, b * res, (b + 1) * res,
+            repr(float(prob[i])), repr(float(value[i]))))
+    return "".join(lines)

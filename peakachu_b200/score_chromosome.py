@@ -1,0 +1,35 @@
+"""``peakachu score_chromosome`` on the CUDA path (mirror of score_chromosome.py:3-71).
+
+Same ``args`` namespace as the reference: path, chrom, model, lower, upper,
+minimum_prob, output, resolution, clr_weight_name (+ optional ``device``).
+"""
+
+
+def main(args):
+    import os
+
+    from . import coolio
+    from .forest import load_model
+    from .scoreUtils import Chromosome, DeviceForest
+
+    if os.path.exists(args.output):                       # score_chromosome.py:11-12
+        os.remove(args.output)
+
+    flat, _ = load_model(args.model)                      # :14
+    correct = False if args.clr_weight_name.lower() == "raw" else args.clr_weight_name   # :17-20
+    width = flat.width                                    # :23
+    device = int(getattr(args, "device", 0) or 0)
+
+    Lib = coolio.open_map(args.path)                      # :33-34 (.hic is outside this path)
+    ccname = args.chrom
+    cikada = "chr" + ccname.lstrip("chr")                 # :37-38
+
+    b1, b2, cnt = Lib.upper_pixels(ccname)                # replaces :42-43 (matrix fetch + tocsr)
+    weights = Lib.weights(ccname, correct) if correct else None   # :44
+    forest = DeviceForest.of(flat, device)
+    X = Chromosome.from_pixels(b1, b2, cnt, weights, Lib.nbins(ccname), forest, lower=args.lower,
+                               upper=args.upper, cname=cikada, res=args.resolution, width=width,
+                               device=device)
+    result, R = X.score(thre=args.minimum_prob)           # :70
+    X.writeBed(args.output, result, R)                    # :71
+    X.close()

@@ -1,0 +1,179 @@
+"""Multi-GPU sharding of ``score_genome``.
+
+One process per GPU (torchrun: RANK / LOCAL_RANK / WORLD_SIZE). Work units are
+chromosomes, plus band row tiles of chromosomes that are larger than an even
+share; units are assigned greedily, largest first, to the least loaded rank.
+Nothing is reduced on the device: every rank returns its records and rank 0
+gathers them over the host backend (gloo) and formats the bedpe text. Row tiles of
+one chromosome return their per-batch window counts so that the reference's "drop
+a 100,000-batch with <= 1 window" rule (scoreUtils.py:104-108) is applied on the
+gathered counts.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def band_pixels(n, lower, upper, w):
+    lo, up = max(lower, w + 1), min(upper, n - 2 * w)
+    if up < lo:
+        return 0
+    k = up - lo + 1
+    return k * n - (lo + up) * k // 2
+
+
+def plan(sizes: dict, world: int, lower: int, upper: int, w: int, split: bool = True):
+    """Greedy largest-first assignment.
+
+    sizes: chromosome -> n_bins. Returns a list (one per rank) of units
+    ``(chrom, row_begin, row_end)``. A chromosome whose band is larger than
+    total/world is cut into equal row tiles (at most ``world``)."""
+    cost = {k: band_pixels(n, lower, upper, w) for k, n in sizes.items()}
+    total = sum(cost.values())
+    units = []
+    for k, n in sizes.items():
+        parts = 1
+        if split and world > 1 and total > 0 and cost[k] > total / world:
+            parts = min(world, int(np.ceil(cost[k] / (total / world))))
+        edges = np.linspace(0, n, parts + 1).astype(int)
+        for i in range(parts):
+            units.append((cost[k] / parts, k, int(edges[i]), int(edges[i + 1])))
+    units.sort(key=lambda u: (-u[0], u[1], u[2]))
+    load = [0.0] * world
+    out = [[] for _ in range(world)]
+    for c, k, a, b in units:
+        r = int(np.argmin(load))
+        load[r] += c
+        out[r].append((k, a, b))
+    return out
+
+
+_GROUP = None
+
+
+def _host_group():
+    global _GROUP
+    import torch.distributed as dist
+    if _GROUP is None:
+        if not dist.is_initialized():
+            dist.init_process_group(backend="gloo")
+            _GROUP = dist.group.WORLD
+        elif dist.get_backend() == "gloo":
+            _GROUP = dist.group.WORLD
+        else:
+            _GROUP = dist.new_group(backend="gloo")
+    return _GROUP
+
+
+def gather_to_rank0(obj, rank, world):
+    """Host-side gather of python objects to rank 0 (gloo group)."""
+    if world == 1:
+        return [obj]
+    import torch.distributed as dist
+    group = _host_group()
+    out = [None] * world if rank == 0 else None
+    dist.gather_object(obj, out, dst=0, group=group)
+    return out
+
+
+def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_prob):
+    """Score this rank's units. Returns {chrom: [tile dict, ...]}."""
+    import ctypes as C
+
+    from . import _lib
+    from .scoreUtils import Chromosome, DeviceForest
+
+    forest = DeviceForest.of(flat, device)
+    L = _lib.lib()
+    out = {}
+    by_chrom = {}
+    for k, a, b in units:
+        by_chrom.setdefault(k, []).append((a, b))
+    for key, tiles in by_chrom.items():
+        b1, b2, cnt = Lib.upper_pixels(key)
+        weights = Lib.weights(key, correct) if correct else None
+        n = Lib.nbins(key)
+        X = Chromosome.from_pixels(b1, b2, cnt, weights, n, forest, lower=lower, upper=upper,
+                                   cname="chr" + key.lstrip("chr"), res=res, width=flat.width, device=device)
+        for a, b in tiles:
+            ncand = C.c_int64()
+            _lib.check(L.pk_chrom_find_candidates(X._h, a, b, C.byref(ncand)))
+            _lib.check(L.pk_chrom_score(X._h, forest.handle, float(min_prob)))
+            nrec = C.c_int64()
+            _lib.check(L.pk_chrom_result_count(X._h, C.byref(nrec), None, None))
+            m = nrec.value
+            x, y, bt = (np.empty(m, np.int32) for _ in range(3))
+            p, v = np.empty(m, np.float64), np.empty(m, np.float64)
+            _lib.check(L.pk_chrom_fetch_results(X._h, _lib.ptr(x), _lib.ptr(y), _lib.ptr(p), _lib.ptr(v),
+                                                _lib.ptr(bt), m, _lib.PK_MEM_HOST))
+            nb = C.c_int64()
+            _lib.check(L.pk_chrom_batch_windows(X._h, None, 0, C.byref(nb)))
+            bw = np.zeros(max(nb.value, 1), np.int64)
+            _lib.check(L.pk_chrom_batch_windows(X._h, _lib.ptr(bw, _lib.c_i64p), bw.size, C.byref(nb)))
+            out.setdefault(key, []).append(dict(row_begin=a, whole=(a == 0 and b == n), x=x, y=y, p=p, v=v,
+                                                batch=bt, batch_windows=bw[:nb.value],
+                                                n_candidates=int(ncand.value)))
+        X.close()
+    return out
+
+
+def merge_tiles(parts):
+    """Combine the row tiles of one chromosome: apply the batch rule on summed window
+    counts (a tile that covered the whole chromosome already applied it on the
+    device), then order by (x, y)."""
+    if len(parts) == 1 and parts[0]["whole"]:
+        q = parts[0]
+        return q["x"], q["y"], q["p"], q["v"]
+    nb = max((q["batch_windows"].size for q in parts), default=0)
+    tot = np.zeros(nb, np.int64)
+    for q in parts:
+        tot[:q["batch_windows"].size] += q["batch_windows"]
+    x = np.concatenate([q["x"] for q in parts])
+    y = np.concatenate([q["y"] for q in parts])
+    p = np.concatenate([q["p"] for q in parts])
+    v = np.concatenate([q["v"] for q in parts])
+    bt = np.concatenate([q["batch"] for q in parts])
+    ok = tot[bt] > 1 if bt.size else np.zeros(0, bool)
+    x, y, p, v = x[ok], y[ok], p[ok], v[ok]
+    order = np.lexsort((y, x))
+    return x[order], y[order], p[order], v[order]
+
+
+def assemble_text(queue, gathered, res, verbose=False):
+    """bedpe text per chromosome from the gathered per-rank tile dicts."""
+    from .scoreUtils import format_bedpe
+    text = {}
+    for key in queue:
+        parts = []
+        for g in gathered:
+            parts.extend(g.get(key, []))
+        parts.sort(key=lambda q: q["row_begin"])
+        cname = "chr" + key.lstrip("chr")
+        if verbose:                                           # scoreUtils.py:97-98
+            print("scoring matrix {}".format(cname))
+            print("number of candidates {}".format(sum(q["n_candidates"] for q in parts)))
+        x, y, p, v = merge_tiles(parts)
+        nz = p != 0                                            # prob_csr.nonzero() drops exact zeros
+        text[key] = format_bedpe(cname, res, x[nz], y[nz], p[nz], v[nz])
+    return text
+
+
+def score_chromosomes(Lib, queue, flat, *, correct, lower, upper, res, min_prob, device=None, verbose=False):
+    """Score ``queue`` across all ranks; on rank 0 returns {chrom: bedpe text}."""
+    rank, world = rank_world()
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    sizes = {k: Lib.nbins(k) for k in queue}
+    assignment = plan(sizes, world, lower, upper, flat.width)
+    mine = score_units(Lib, assignment[rank], flat, correct=correct, lower=lower, upper=upper, res=res,
+                       device=device, min_prob=min_prob)
+    gathered = gather_to_rank0(mine, rank, world)
+    if rank != 0:
+        return {}
+    return assemble_text(queue, gathered, res, verbose=verbose)

@@ -1,0 +1,148 @@
+"""Parity of the CUDA path (through the C ABI) against (a) the golden fixtures made
+by the reference and (b) the numpy oracle on the same inputs. Bit-exact for the
+expected curve, candidate set, float64/float32 features, leaf ids and
+probabilities; byte-identical bedpe text."""
+import argparse
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from tests.cases import ALL_CASES, FULL_TAP_CASES, Case
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_chromosome(case, ch, forest=None):
+    from peakachu_b200.scoreUtils import Chromosome
+    cfg = case.cfg
+    weights = None if cfg["weight"] == "raw" else ch.weights
+    return Chromosome.from_pixels(ch.bin1, ch.bin2, ch.count, weights, ch.n, forest or case.forest,
+                                  lower=cfg["lower"], upper=cfg["upper"], cname="chr" + ch.name.lstrip("chr"),
+                                  res=cfg["res"], width=cfg["w"])
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_taps_match_reference_golden(name):
+    import torch
+    from peakachu_b200 import _lib
+    from peakachu_b200.scoreUtils import DeviceForest
+    case = Case(name)
+    df = DeviceForest.of(case.forest, 0)
+    for ch in case.chroms:
+        k = ch.name + "/"
+        X = _gpu_chromosome(case, ch, df)
+        assert np.array_equal(X.exp_arr, case.z[k + "exp_arr"])                  # (ii) bit-exact
+        assert np.array_equal(X.ridx, case.z[k + "ridx"])                        # (i) set and order
+        assert np.array_equal(X.cidx, case.z[k + "cidx"])
+        keep, f32, f64 = X.window_features(want64=True)                          # (iii)
+        clist = np.stack([X.ridx[keep], X.cidx[keep]], axis=1)
+        assert np.array_equal(clist, case.z[k + "clist"])
+        if name in FULL_TAP_CASES:
+            assert np.array_equal(f64[keep][:128], case.z[k + "fea64_head"])     # float64 bit-exact
+            assert np.array_equal(f32[keep], case.z[k + "fea32"])                # float32 identical
+        import hashlib
+        sh = case.meta["sha"][ch.name]
+        assert hashlib.sha256(np.ascontiguousarray(f64[keep]).tobytes()).hexdigest() == sh["fea64"]
+        assert hashlib.sha256(np.ascontiguousarray(f32[keep]).tobytes()).hexdigest() == sh["fea32"]
+        # (iv) leaves + probabilities from the device forest on those rows
+        xs = torch.from_numpy(np.ascontiguousarray(f32[keep])).cuda()
+        leaves = torch.empty((xs.shape[0], case.forest.n_trees), dtype=torch.int32, device="cuda")
+        proba = torch.empty(xs.shape[0], dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().pk_forest_apply(df.handle, C.c_void_p(xs.data_ptr()), xs.shape[0],
+                                              C.c_void_p(leaves.data_ptr()), C.c_void_p(proba.data_ptr()), None))
+        torch.cuda.synchronize()
+        assert hashlib.sha256(leaves.cpu().numpy().tobytes()).hexdigest() == sh["leaves"]
+        assert np.array_equal(proba.cpu().numpy(), case.z[k + "proba"])          # bit-exact float64
+        if name in FULL_TAP_CASES:
+            assert np.array_equal(leaves.cpu().numpy(), case.z[k + "leaves"])
+        X.close()
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_bedpe_identical_to_reference(name, tmp_path):
+    from peakachu_b200 import score_chromosome, score_genome
+    case = Case(name)
+    cfg = case.cfg
+    cool = case.write_cool(tmp_path)
+    out = os.path.join(str(tmp_path), "gpu.bedpe")
+    ns = argparse.Namespace(path=cool, model=case.pkl, output=out, resolution=cfg["res"], lower=cfg["lower"],
+                            upper=cfg["upper"], minimum_prob=cfg["min_prob"], clr_weight_name=cfg["weight"])
+    if cfg.get("genome"):
+        ns.chroms = ["#", "X"]
+        score_genome.main(ns)
+    else:
+        ns.chrom = case.chroms[0].name
+        score_chromosome.main(ns)
+    assert open(out).read() == case.bedpe                                        # (v)
+
+
+def test_forest_npz_and_pkl_give_same_tables():
+    from peakachu_b200.forest import load_model
+    case = Case("tiny")
+    a, _ = load_model(case.pkl)
+    b = case.forest
+    for f in ("node_offset", "feature", "threshold", "left", "right", "missing_left", "leaf_p1"):
+        assert np.array_equal(getattr(a, f), getattr(b, f))
+
+
+def test_dropin_constructor_with_scipy_matrices(tmp_path):
+    """The reference-shaped constructor Chromosome(M, model, raw_M, weights, ...)."""
+    from oracle import peakachu_oracle as po
+    from peakachu_b200 import coolio
+    from peakachu_b200.scoreUtils import Chromosome
+    case = Case("tiny")
+    cfg = case.cfg
+    lib = coolio.Cooler(case.write_cool(tmp_path))
+    ch = case.chroms[0]
+    M = po.tocsr(lib.matrix(balance="weight", sparse=True).fetch(ch.name))
+    raw_M = po.tocsr(lib.matrix(balance=False, sparse=True).fetch(ch.name))
+    weights = lib.bins().fetch(ch.name)["weight"].values
+    X = Chromosome(M, model=case.model(), raw_M=raw_M, weights=weights, cname="chr1", lower=cfg["lower"],
+                   upper=cfg["upper"], res=cfg["res"], width=cfg["w"])
+    prob, val = X.score(thre=cfg["min_prob"])
+    O = po.Chromosome(M, model=case.model(), raw_M=raw_M, weights=weights, cname="chr1", lower=cfg["lower"],
+                      upper=cfg["upper"], res=cfg["res"], width=cfg["w"])
+    oprob, oval = O.score(thre=cfg["min_prob"])
+    assert (prob != oprob).nnz == 0 and (val != oval).nnz == 0
+    a, b = os.path.join(str(tmp_path), "a"), os.path.join(str(tmp_path), "b")
+    X.writeBed(a, prob, val)
+    O.writeBed(b, oprob, oval)
+    assert open(a).read() == open(b).read() == case.bedpe
+
+
+def test_row_tiles_equal_whole_chromosome():
+    """Band row tiles (the multi-GPU seam) reproduce the whole-chromosome records."""
+    from peakachu_b200 import _lib, shard
+    from peakachu_b200.scoreUtils import DeviceForest
+
+    class OneChrom:
+        def __init__(self, ch): self.ch = ch
+        def upper_pixels(self, k): return self.ch.bin1, self.ch.bin2, self.ch.count
+        def weights(self, k, name): return self.ch.weights
+        def nbins(self, k): return self.ch.n
+
+    case = Case("c1")
+    cfg = case.cfg
+    ch = case.chroms[0]
+    lib = OneChrom(ch)
+    kw = dict(correct="weight", lower=cfg["lower"], upper=cfg["upper"], res=cfg["res"], device=0,
+              min_prob=cfg["min_prob"])
+    whole = shard.score_units(lib, [("chr1", 0, ch.n)], case.forest, **kw)
+    tiles = shard.score_units(lib, [("chr1", 0, 700), ("chr1", 700, 1301), ("chr1", 1301, ch.n)], case.forest, **kw)
+    tw = shard.assemble_text(["chr1"], [whole], cfg["res"])["chr1"]
+    tt = shard.assemble_text(["chr1"], [tiles], cfg["res"])["chr1"]
+    assert tw == tt == case.bedpe
+
+
+def test_errors_are_loud():
+    from peakachu_b200 import _lib
+    L = _lib.lib()
+    h = C.c_void_p()
+    assert L.pk_chrom_create(0, 0, 5, 6, 300, 1, None, C.byref(h)) != 0
+    assert b"n_bins" in L.pk_last_error()
+    _lib.check(L.pk_chrom_create(0, 500, 5, 6, 300, 1, None, C.byref(h)))
+    n = C.c_int64()
+    assert L.pk_chrom_find_candidates(h, 0, 500, C.byref(n)) == -4         # PK_ESTATE: nothing uploaded
+    L.pk_chrom_destroy(h)
