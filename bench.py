@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the loop-scoring hot path (BASELINE.json metric: candidate pixels
+scored / second, window features + RF proba).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: under torchrun)
+  python bench.py --impl reference --steps K --warmup W    CPU arm (oracle port)
+
+A step = one pass of the whole path over one chromosome of the workload
+(BASELINE configs[1]: chr1-scale synthetic, 24,900 bins at 10 kb, w=5, l=6, u=300,
+100-tree forest): pixel scatter -> band, per-diagonal sums, expected fit, Poisson
+candidate scan, window features, forest, threshold emit. "Pixels" are band pixels
+sum_{d=lower..upper}(n-d), the count BASELINE.json quotes (~7.3 M for this map).
+
+`value`  : device-resident inputs (pixel columns + weights already in HBM), timed
+           with CUDA events on the library's stream, L2 flushed between steps.
+`e2e`    : the public API call (Chromosome.from_pixels + score_records) on HOST
+           buffers: H2D of pixels/weights and D2H of the records inside the timing.
+With N ranks every rank scores its own chromosome of the same shape (different
+seed): weak scaling, no collective on the data path; time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_bins, res, lower, upper, w, forest, depth, band)
+    "c2": dict(n=24900, res=10000, lower=6, upper=300, w=5, forest="c2", depth=300.0, band=330,
+               desc="score_chromosome chr1-scale synthetic (24,900 bins, 10 kb, w=5, l=6, u=300, 100-tree RF)"),
+    "c1": dict(n=2000, res=10000, lower=6, upper=300, w=5, forest="c2", depth=300.0, band=330,
+               desc="score_chromosome 2,000-bin synthetic 10 kb (w=5, l=6, u=300, 100-tree RF)"),
+}
+KERNELS_PER_STEP = 8   # scatter, diag_sums, cand count, scan, cand write, features, forest, emit
+
+
+def band_pixels(n, lower, upper, w):
+    lo, up = max(lower, w + 1), min(upper, n - 2 * w)
+    k = up - lo + 1
+    return k * n - (lo + up) * k // 2 if k > 0 else 0
+
+
+def make_map(wl, seed):
+    from peakachu_b200 import synth
+    return synth.make_chromosome("chr1", wl["n"], seed=seed, depth=wl["depth"], band=wl["band"])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([s.strip() for s in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle port on host cores (the only place bench.py runs oracle/)
+# ---------------------------------------------------------------------------
+def cpu_pass(wl, n_bins, seed, model):
+    """One oracle pass (score_chromosome body) on an n_bins chromosome of the same
+    synthetic distribution. Returns (seconds, band pixels, candidates, records)."""
+    import tempfile
+    from oracle import peakachu_oracle as po
+    from peakachu_b200 import coolio, synth
+    ch = synth.make_chromosome("chr1", n_bins, seed=seed, depth=wl["depth"], band=wl["band"])
+    path = os.path.join(tempfile.mkdtemp(), "cpu.pkcool")
+    coolio.PKCool.write(path, [ch], wl["res"])
+    lib = coolio.Cooler(path)
+    t0 = time.perf_counter()
+    st = po.score_map(lib, model, ["chr1"], weight_name="weight", lower=wl["lower"], upper=wl["upper"],
+                      res=wl["res"], min_prob=0.5, output=os.path.join(os.path.dirname(path), "o.bedpe"))
+    dt = time.perf_counter() - t0
+    return dt, band_pixels(n_bins, wl["lower"], wl["upper"], wl["w"]), st[0]["candidates"], st[0]["rows"]
+
+
+def load_sklearn_model(name):
+    import joblib
+    return joblib.load(os.path.join(ROOT, "bench_data", name + ".pkl"))
+
+
+_WORKER_MODEL = {}
+
+
+def _cpu_worker(job):
+    wl, n_bins, seed = job
+    if wl["forest"] not in _WORKER_MODEL:
+        _WORKER_MODEL[wl["forest"]] = load_sklearn_model(wl["forest"])
+    return cpu_pass(wl, n_bins, seed, _WORKER_MODEL[wl["forest"]])
+
+
+def run_reference_arm(args, wl):
+    """The reference path on the host cores: the reference itself is single-threaded
+    (forest n_jobs=1, sequential chromosome loop), so "all host threads" means one
+    process per chromosome, the only parallelism its design admits."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+    workers = max(1, min(os.cpu_count() or 1, args.cpu_workers))
+    n_sample = args.cpu_bins
+    with ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("fork")) as ex:
+        for _ in range(max(args.warmup, 1)):
+            list(ex.map(_cpu_worker, [(wl, 600, 5)] * workers))          # imports, model load
+        tot_t, tot_px = 0.0, 0
+        for s in range(args.steps):
+            t0 = time.perf_counter()
+            res = list(ex.map(_cpu_worker, [(wl, n_sample, 100 + s * workers + i) for i in range(workers)]))
+            tot_t += time.perf_counter() - t0
+            tot_px += sum(r[1] for r in res)
+    val = tot_px / tot_t
+    sample = ("per step: %d chromosomes of %d bins from the c2 synthetic distribution (%d band px each), one "
+              "process each, numpy oracle port of score_chromosome" % (
+                  workers, n_sample, band_pixels(n_sample, wl["lower"], wl["upper"], wl["w"])))
+    print(json.dumps({
+        "impl": "reference", "metric": "candidate pixels scored/sec (window features + RF proba)",
+        "value": val, "unit": "pixels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "pixels": "band pixels sum_{d=l..u}(n-d)"},
+        "cpu_baseline": {"value": val, "unit": "pixels/s", "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-bins", type=int, default=4000, help="chromosome size of the bounded CPU sample")
+    ap.add_argument("--cpu-workers", type=int, default=32, help="processes of the --impl reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+        return
+
+    import torch
+    from peakachu_b200 import _lib
+    from peakachu_b200.forest import FlatForest
+    from peakachu_b200.scoreUtils import Chromosome, DeviceForest
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    L = _lib.lib()
+    _lib.require_device()
+    args.warmup = max(args.warmup, 3)
+
+    flat = FlatForest.load(os.path.join(ROOT, "bench_data", wl["forest"] + "_forest.npz"))
+    forest = DeviceForest.of(flat, local)
+    ch = make_map(wl, seed=1234 + rank)
+    n, w = ch.n, wl["w"]
+    px = band_pixels(n, wl["lower"], wl["upper"], w)
+    nnz = ch.bin1.size
+
+    # ---- device-resident inputs (torch tensors only as buffers) ----
+    stream = torch.cuda.Stream(device=local)
+    d_b1 = torch.from_numpy(ch.bin1).cuda(); d_b2 = torch.from_numpy(ch.bin2).cuda()
+    d_cnt = torch.from_numpy(ch.count).cuda(); d_w = torch.from_numpy(ch.weights).cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    h = C.c_void_p()
+    _lib.check(L.pk_chrom_create(local, n, w, wl["lower"], wl["upper"], 1, C.c_void_p(stream.cuda_stream), C.byref(h)))
+
+    def device_step():
+        _lib.check(L.pk_chrom_upload_pixels(h, C.c_void_p(d_b1.data_ptr()), C.c_void_p(d_b2.data_ptr()),
+                                            C.c_void_p(d_cnt.data_ptr()), nnz, C.c_void_p(d_w.data_ptr()),
+                                            _lib.PK_MEM_DEVICE))
+        _lib.check(L.pk_chrom_fit_expected(h))
+        _lib.check(L.pk_chrom_find_candidates(h, 0, n, None))
+        _lib.check(L.pk_chrom_score(h, forest.handle, 0.5))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_acc = np.zeros(8)
+    barrier()
+    for a, b in ev:
+        flush.fill_(1)                                  # evict L2 (256 MiB > 126 MB), untimed
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            a.record(stream)
+            device_step()
+            b.record(stream)
+        stream.synchronize()
+        ms = np.zeros(8, dtype=np.float32)
+        _lib.check(L.pk_chrom_stage_ms(h, _lib.ptr(ms, _lib.c_f32p)))
+        stage_acc += ms
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    nrec, ncand, nwin = C.c_int64(), C.c_int64(), C.c_int64()
+    _lib.check(L.pk_chrom_result_count(h, C.byref(nrec), C.byref(ncand), C.byref(nwin)))
+
+    # ---- end to end through the public API with host buffers ----
+    def e2e_step():
+        X = Chromosome.from_pixels(ch.bin1, ch.bin2, ch.count, ch.weights, n, forest, lower=wl["lower"],
+                                   upper=wl["upper"], cname="chr1", res=wl["res"], width=w, device=local)
+        out = X.score_records(0.5)
+        X.close()
+        return out
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rec = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = 12 * nnz + 8 * n
+    d2h = 24 * int(rec[0].size)
+
+    # max over ranks
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+    _lib.check(L.pk_chrom_destroy(h))
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    steps = args.steps
+    value = world * px * steps / (dev_ms * 1e-3)
+    e2e_val = world * px * steps / (e2e_ms * 1e-3)
+    stage = dict(zip(("band_build", "diag_sums", "expected_fit", "candidate_scan", "features", "forest", "emit"),
+                     (stage_acc[:7] / steps).tolist()))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    # algorithmic bytes of one chromosome: pixel columns once, weights,
+    # expected curve, emitted records, forest tables once
+    forest_bytes = 8 * flat.n_nodes
+    bytes_alg = 12 * nnz + 8 * n + 8 * (wl["upper"] + 2 * w + 1) + 24 * int(nrec.value) + forest_bytes
+    dom = max(stage, key=stage.get)
+    dom_ms = stage[dom]
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": bytes_alg / (dom_ms * 1e-3) / 1e9, "peak": peak_gbs,
+                "unit": "GB/s", "frac": bytes_alg / (dom_ms * 1e-3) / 1e9 / peak_gbs, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
+                "bytes_alg_per_launch": bytes_alg,
+                "whole_step_frac": bytes_alg / (dev_ms / steps * 1e-3) / 1e9 / peak_gbs}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        model = load_sklearn_model(wl["forest"])
+        cpu_pass(wl, 600, 5, model)
+        dt, cpx, ccand, crows = cpu_pass(wl, 3 * args.cpu_bins, 100, model)
+        cpu = {"value": cpx / dt, "unit": "pixels/s", "cores": 1, "kind": "port",
+               "sample": "one %d-bin chromosome of the same synthetic distribution (%d band px, %d candidates), "
+                         "numpy oracle port of score_chromosome, 1 of %d host threads (the reference is "
+                         "single-threaded), %.1f s" % (3 * args.cpu_bins, cpx, ccand, os.cpu_count(), dt)}
+
+    print(json.dumps({
+        "metric": "candidate pixels scored/sec (window features + RF proba)",
+        "value": value, "unit": "pixels/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "pixels": "band pixels sum_{d=l..u}(n-d) = %d per chromosome" % px,
+                   "per_rank": "one chromosome per rank per step", "candidates_per_step": int(ncand.value),
+                   "windows_per_step": int(nwin.value), "records_per_step": int(nrec.value),
+                   "forest": "%d trees, %d nodes" % (flat.n_trees, flat.n_nodes),
+                   "l2": "flushed between timed steps (256 MiB write, untimed)"},
+        "candidates_per_s": world * int(ncand.value) * steps / (dev_ms * 1e-3),
+        "stage_ms": stage, "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_val, "unit": "pixels/s", "ms_per_step": e2e_ms / steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": KERNELS_PER_STEP * steps, "clocks": clocks,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
