@@ -139,9 +139,14 @@ int pk_poisson_critical_mu(int32_t k_max, double* out /* [k_max+1] */);
  * IsotonicRegression(increasing=False, out_of_bounds='clip') of utils.py:173-176) */
 int pk_fit_expected(const double* sum, const int64_t* cnt, int32_t len, double* out_exp);
 
+/* process-wide tuning knob, for benchmarking: key "fused" = -1 auto (default),
+ * 0 separate feature + forest kernels, 1 / 2 the two fused-kernel tile sizes */
+int pk_set_tuning(const char* key, int value);
+
 /* time spent (ms, CUDA events) in each stage of the last upload/fit/find/score of
  * this handle: [0] band build, [1] diagonal sums, [2] expected fit, [3] candidate
- * scan, [4] window features, [5] forest, [6] emit+sort. HOST array of 8. */
+ * scan, [4] window features (or the fused features+forest kernel, then [5] = 0),
+ * [5] forest, [6] emit. HOST array of 8. */
 int pk_chrom_stage_ms(pk_chrom* c, float* out_ms);
 
 #ifdef __cplusplus

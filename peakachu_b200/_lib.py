@@ -50,6 +50,7 @@ SIGNATURES = {
                                          C.c_int64, C.c_int]),
     "pk_poisson_critical_mu": (C.c_int, [C.c_int32, c_f64p]),
     "pk_fit_expected": (C.c_int, [c_f64p, c_i64p, C.c_int32, c_f64p]),
+    "pk_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
     "pk_chrom_stage_ms": (C.c_int, [C.c_void_p, c_f32p]),
 }
 

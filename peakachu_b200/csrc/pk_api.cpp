@@ -22,6 +22,17 @@ int pk_launch_features(pk_chrom* c, double* d_fea64);
 int pk_launch_forest(const pk_forest* f, const float* X, const uint8_t* keep, int64_t n_rows, int32_t* leaves,
                      double* proba, cudaStream_t stream);
 int pk_launch_emit(pk_chrom* c, double thre);
+int pk_launch_fused(pk_chrom* c, const pk_forest* f, int variant);
+bool pk_fused_supported(int w);
+
+// tuning knobs (pk_set_tuning): fused = -1 auto, 0 unfused kernels, 1 / 2 fused variants
+static int g_tune_fused = -1;
+
+extern "C" int pk_set_tuning(const char* key, int value) {
+    if (key && !strcmp(key, "fused")) { g_tune_fused = value; return PK_OK; }
+    pk_set_error("pk_set_tuning: unknown key %s", key ? key : "(null)");
+    return PK_EINVAL;
+}
 
 // ---------------------------------------------------------------------------
 // errors
@@ -124,6 +135,7 @@ extern "C" int pk_forest_create(int device, int32_t n_trees, int32_t n_features,
     std::vector<uint2> nodes((size_t)total);
     std::vector<int32_t> orig((size_t)total);
     std::vector<uint32_t> roots((size_t)n_trees);
+    std::vector<uint8_t> tdepth((size_t)n_trees);
     int32_t max_depth = 0;
     std::vector<int32_t> newid, stack, depth;
     for (int32_t t = 0; t < n_trees; ++t) {
@@ -133,7 +145,7 @@ extern "C" int pk_forest_create(int device, int32_t n_trees, int32_t n_features,
         newid.assign((size_t)cnt, -1);
         stack.clear(); depth.assign((size_t)cnt, 0);
         stack.push_back(0);
-        int32_t next = 0;
+        int32_t next = 0, this_depth = 0;
         while (!stack.empty()) {
             int32_t v = stack.back(); stack.pop_back();
             if (v < 0 || v >= cnt || newid[v] != -1) { pk_set_error("pk_forest_create: tree %d is not a tree", t); return PK_EINVAL; }
@@ -143,6 +155,7 @@ extern "C" int pk_forest_create(int device, int32_t n_trees, int32_t n_features,
                 if (r < 0 || r >= cnt || l < 0 || l >= cnt) { pk_set_error("pk_forest_create: bad child index"); return PK_EINVAL; }
                 depth[l] = depth[r] = depth[v] + 1;
                 max_depth = std::max(max_depth, depth[v] + 1);
+                this_depth = std::max(this_depth, depth[v] + 1);
                 stack.push_back(r);
                 stack.push_back(l);
             }
@@ -171,19 +184,37 @@ extern "C" int pk_forest_create(int device, int32_t n_trees, int32_t n_features,
             }
         }
         roots[(size_t)t] = (uint32_t)o | ((left[o] == -1) ? 0x80000000u : 0u);
+        if (this_depth > 255) { pk_set_error("pk_forest_create: tree %d deeper than 255", t); return PK_EUNSUPPORTED; }
+        tdepth[(size_t)t] = (uint8_t)this_depth;
+    }
+    // groups of consecutive trees for shared-memory staging
+    std::vector<int4> groups;
+    for (int32_t t = 0; t < n_trees;) {
+        int64_t gbase = node_offset[t] & ~1LL;
+        int32_t t1 = t + 1;
+        while (t1 < n_trees && node_offset[t1 + 1] - gbase <= PK_TREE_BUF_NODES) ++t1;
+        int64_t staged = std::min<int64_t>(node_offset[t1] - gbase, PK_TREE_BUF_NODES);
+        staged = (staged + 1) & ~1LL;                       // 16-byte multiple; array is padded
+        groups.push_back(make_int4(t, t1 - t, (int)gbase, (int)staged));
+        t = t1;
     }
     PK_CUDA(cudaSetDevice(device));
     pk_forest* f = new pk_forest();
     f->device = device; f->n_trees = n_trees; f->n_features = n_features; f->n_nodes = total; f->max_depth = max_depth;
     int r;
-    if ((r = dev_alloc(&f->d_nodes, (size_t)total)) || (r = dev_alloc(&f->d_root, (size_t)n_trees)) ||
-        (r = dev_alloc(&f->d_orig, (size_t)total))) {
+    f->n_groups = (int32_t)groups.size();
+    if ((r = dev_alloc(&f->d_nodes, (size_t)total + 4)) || (r = dev_alloc(&f->d_root, (size_t)n_trees)) ||
+        (r = dev_alloc(&f->d_orig, (size_t)total)) || (r = dev_alloc(&f->d_depth, (size_t)n_trees)) ||
+        (r = dev_alloc(&f->d_groups, groups.size()))) {
         pk_forest_destroy(f);
         return r;
     }
     PK_CUDA(cudaMemcpy(f->d_nodes, nodes.data(), (size_t)total * sizeof(uint2), cudaMemcpyHostToDevice));
     PK_CUDA(cudaMemcpy(f->d_root, roots.data(), (size_t)n_trees * sizeof(uint32_t), cudaMemcpyHostToDevice));
     PK_CUDA(cudaMemcpy(f->d_orig, orig.data(), (size_t)total * sizeof(int32_t), cudaMemcpyHostToDevice));
+    PK_CUDA(cudaMemset(f->d_nodes + total, 0, 4 * sizeof(uint2)));
+    PK_CUDA(cudaMemcpy(f->d_depth, tdepth.data(), (size_t)n_trees, cudaMemcpyHostToDevice));
+    PK_CUDA(cudaMemcpy(f->d_groups, groups.data(), groups.size() * sizeof(int4), cudaMemcpyHostToDevice));
     *out = f;
     return PK_OK;
 }
@@ -191,7 +222,7 @@ extern "C" int pk_forest_create(int device, int32_t n_trees, int32_t n_features,
 extern "C" int pk_forest_destroy(pk_forest* f) {
     if (!f) return PK_OK;
     cudaSetDevice(f->device);
-    dev_free(f->d_nodes); dev_free(f->d_root); dev_free(f->d_orig);
+    dev_free(f->d_nodes); dev_free(f->d_root); dev_free(f->d_orig); dev_free(f->d_depth); dev_free(f->d_groups);
     delete f;
     return PK_OK;
 }
@@ -436,14 +467,23 @@ extern "C" int pk_chrom_candidates(pk_chrom* c, int32_t* out_x, int32_t* out_y, 
     return PK_OK;
 }
 
+static int ensure_feature_buffer(pk_chrom* c) {
+    if (c->n_cand > c->fea_cap || !c->d_fea32) {
+        dev_free(c->d_fea32);
+        int64_t cap = std::max<int64_t>(c->n_cand + c->n_cand / 8, 1024);
+        PK_CHECK(dev_alloc(&c->d_fea32, (size_t)cap * c->F));
+        c->fea_cap = cap;
+    }
+    return PK_OK;
+}
+
 static int ensure_score_buffers(pk_chrom* c) {
-    if (c->n_cand > c->fea_cap || !c->d_keep) {
-        dev_free(c->d_keep); dev_free(c->d_fea32); dev_free(c->d_prob);
+    if (c->n_cand > c->keep_cap || !c->d_keep) {
+        dev_free(c->d_keep); dev_free(c->d_prob);
         int64_t cap = std::max<int64_t>(c->n_cand + c->n_cand / 8, 1024);
         PK_CHECK(dev_alloc(&c->d_keep, (size_t)cap));
-        PK_CHECK(dev_alloc(&c->d_fea32, (size_t)cap * c->F));
         PK_CHECK(dev_alloc(&c->d_prob, (size_t)cap));
-        c->fea_cap = cap;
+        c->keep_cap = cap;
     }
     if (c->n_cand > c->rec_cap || !c->d_rx) {
         dev_free(c->d_rx); dev_free(c->d_ry); dev_free(c->d_rb); dev_free(c->d_rp); dev_free(c->d_rv);
@@ -471,6 +511,7 @@ extern "C" int pk_chrom_features(pk_chrom* c, uint8_t* keep, float* fea32, doubl
     if (c->n_cand == 0) return PK_OK;
     PK_CUDA(cudaSetDevice(c->device));
     PK_CHECK(ensure_score_buffers(c));
+    PK_CHECK(ensure_feature_buffer(c));
     double* d64 = nullptr;
     if (fea64) PK_CHECK(dev_alloc(&d64, (size_t)c->n_cand * c->F));
     int r = pk_launch_features(c, d64);
@@ -496,9 +537,18 @@ extern "C" int pk_chrom_score(pk_chrom* c, pk_forest* f, double min_prob) {
     cudaStream_t s = c->stream;
     PK_CHECK(ensure_score_buffers(c));
     PK_CUDA(cudaEventRecord(c->ev[7], s));
-    PK_CHECK(pk_launch_features(c, nullptr));
-    PK_CUDA(cudaEventRecord(c->ev[8], s));
-    PK_CHECK(pk_launch_forest(f, c->d_fea32, c->d_keep, c->n_cand, nullptr, c->d_prob, s));
+    const bool fused = g_tune_fused != 0 && pk_fused_supported(c->w);
+    if (fused) {
+        // features stay in shared memory; stage [4] reports the fused kernel, [5] is 0
+        if (c->n_cand > 0) PK_CUDA(cudaMemsetAsync(c->d_keep, 0, (size_t)c->n_cand, s));
+        PK_CHECK(pk_launch_fused(c, f, g_tune_fused == 2 ? 1 : 0));
+        PK_CUDA(cudaEventRecord(c->ev[8], s));
+    } else {
+        PK_CHECK(ensure_feature_buffer(c));
+        PK_CHECK(pk_launch_features(c, nullptr));
+        PK_CUDA(cudaEventRecord(c->ev[8], s));
+        PK_CHECK(pk_launch_forest(f, c->d_fea32, c->d_keep, c->n_cand, nullptr, c->d_prob, s));
+    }
     PK_CUDA(cudaEventRecord(c->ev[9], s));
     PK_CHECK(pk_launch_emit(c, min_prob));
     PK_CUDA(cudaEventRecord(c->ev[10], s));

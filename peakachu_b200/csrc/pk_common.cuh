@@ -42,8 +42,17 @@ struct pk_forest {
     uint2* d_nodes = nullptr;        // [n_nodes]
     uint32_t* d_root = nullptr;      // [n_trees] packed index of the root | (root_is_leaf << 31)
     int32_t* d_orig = nullptr;       // [n_nodes] tree-local sklearn node id (apply tap)
+    uint8_t* d_depth = nullptr;      // [n_trees] depth of the deepest leaf
+    // tree groups staged into shared memory by the fused kernel: consecutive trees
+    // whose nodes fit one buffer of PK_TREE_BUF_NODES; a larger tree is its own group
+    // and only its first PK_TREE_BUF_NODES nodes are staged.
+    //   .x first tree, .y number of trees, .z first staged node (even), .w staged nodes (even)
+    int4* d_groups = nullptr;
+    int32_t n_groups = 0;
     int32_t max_depth = 0;
 };
+
+#define PK_TREE_BUF_NODES 2048       // 16 KB per buffer, two buffers per CTA
 
 struct pk_chrom {
     int device = 0;
@@ -86,7 +95,7 @@ struct pk_chrom {
     // scoring
     uint8_t* d_keep = nullptr;
     float* d_fea32 = nullptr;        // [n_cand][F]
-    int64_t fea_cap = 0;
+    int64_t fea_cap = 0, keep_cap = 0;
     double* d_prob = nullptr;
     int32_t* d_batch_win = nullptr;  // [n_batches]
     int64_t n_batches = 0, batch_cap = 0;

@@ -16,17 +16,7 @@
 #include <algorithm>
 
 #include "pk_common.cuh"
-
-// ---------------------------------------------------------------------------
-// small device helpers
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ double pk_value(int cnt, double wr, double wc, int balanced) {
-    // balanced value (w[r] * w[c]) * count; non-finite pixels are trimmed (scoreUtils.py:31)
-    if (cnt == 0) return 0.0;
-    if (!balanced) return (double)cnt;
-    double v = __dmul_rn(__dmul_rn(wr, wc), (double)cnt);
-    return isfinite(v) ? v : 0.0;
-}
+#include "pk_device.cuh"
 
 // ---------------------------------------------------------------------------
 // K1  band build: scatter upper-triangle pixels into the diagonal-major band and
@@ -284,12 +274,7 @@ __global__ void __launch_bounds__(1024) k_scan2(const uint32_t* __restrict__ a, 
 //               t = x[c]*k4; t += (x[c-4]+x[c+4])*k0; ... ; t += (x[c-1]+x[c+1])*k3
 //       min-max (G - min) / (max - min), NaN propagates; cast to float32
 // ---------------------------------------------------------------------------
-__constant__ double c_gk[5] = {0x1.18a9c4fd536c6p-13, 0x1.22724cb7eb269p-8, 0x1.ba4b99d1799abp-5,
-                               0x1.ef8eb9ad499bap-3, 0x1.9884a307594fbp-2};
-
 #define PK_FEAT_WARPS 4
-
-__device__ __forceinline__ int pk_reflect(int i, int S) { return i < 0 ? -i - 1 : (i >= S ? 2 * S - i - 1 : i); }
 
 __global__ void __launch_bounds__(PK_FEAT_WARPS * 32) k_features(
     const int32_t* __restrict__ band, const double* __restrict__ w, const double* __restrict__ expv,
@@ -350,11 +335,11 @@ __global__ void __launch_bounds__(PK_FEAT_WARPS * 32) k_features(
         // gaussian, axis 0 (rows a)
         for (int idx = lane; idx < F; idx += 32) {
             int a = idx / S, b = idx - a * S;
-            double t = __dmul_rn(A[idx], c_gk[4]);
+            double t = __dmul_rn(A[idx], PK_GK[4]);
 #pragma unroll
             for (int j = 4; j >= 1; --j) {
                 double p = A[pk_reflect(a - j, S) * S + b], q = A[pk_reflect(a + j, S) * S + b];
-                t = __dadd_rn(t, __dmul_rn(__dadd_rn(p, q), c_gk[4 - j]));
+                t = __dadd_rn(t, __dmul_rn(__dadd_rn(p, q), PK_GK[4 - j]));
             }
             T[idx] = t;
         }
@@ -364,11 +349,11 @@ __global__ void __launch_bounds__(PK_FEAT_WARPS * 32) k_features(
         bool has_nan = false;
         for (int idx = lane; idx < F; idx += 32) {
             int a = idx / S, b = idx - a * S;
-            double t = __dmul_rn(T[idx], c_gk[4]);
+            double t = __dmul_rn(T[idx], PK_GK[4]);
 #pragma unroll
             for (int j = 4; j >= 1; --j) {
                 double p = T[a * S + pk_reflect(b - j, S)], q = T[a * S + pk_reflect(b + j, S)];
-                t = __dadd_rn(t, __dmul_rn(__dadd_rn(p, q), c_gk[4 - j]));
+                t = __dadd_rn(t, __dmul_rn(__dadd_rn(p, q), PK_GK[4 - j]));
             }
             A[idx] = t;          // A is free again (all lanes passed the previous __syncwarp)
             has_nan |= isnan(t);

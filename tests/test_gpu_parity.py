@@ -60,9 +60,40 @@ def test_taps_match_reference_golden(name):
         X.close()
 
 
+@pytest.fixture
+def tuning():
+    from peakachu_b200 import _lib
+
+    def set_fused(v):
+        _lib.check(_lib.lib().pk_set_tuning(b"fused", v))
+    yield set_fused
+    set_fused(-1)
+
+
+@pytest.mark.parametrize("fused", [0, 1, 2])
 @pytest.mark.parametrize("name", ALL_CASES)
-def test_bedpe_identical_to_reference(name, tmp_path):
+def test_all_window_probabilities_bit_exact(name, fused, tuning):
+    """Every kept window's probability (threshold below 0 keeps them all), through the
+    separate kernels (fused=0) and both fused-kernel variants."""
+    tuning(fused)
+    case = Case(name)
+    for ch in case.chroms:
+        k = ch.name + "/"
+        X = _gpu_chromosome(case, ch)
+        x, y, p, v = X.score_records(-1.0)
+        clist, proba = case.z[k + "clist"], case.z[k + "proba"]
+        order = np.lexsort((clist[:, 1], clist[:, 0]))
+        assert np.array_equal(x, clist[order, 0]) and np.array_equal(y, clist[order, 1])
+        assert np.array_equal(p, proba[order])
+        assert X.n_windows == clist.shape[0]
+        X.close()
+
+
+@pytest.mark.parametrize("fused", [0, 1, 2])
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_bedpe_identical_to_reference(name, fused, tuning, tmp_path):
     from peakachu_b200 import score_chromosome, score_genome
+    tuning(fused)
     case = Case(name)
     cfg = case.cfg
     cool = case.write_cool(tmp_path)
