@@ -23,7 +23,7 @@ int pk_launch_forest(const pk_forest* f, const float* X, const uint8_t* keep, in
                      double* proba, cudaStream_t stream);
 int pk_launch_emit(pk_chrom* c, double thre);
 int pk_launch_fused(pk_chrom* c, const pk_forest* f, int variant);
-bool pk_fused_supported(int w);
+bool pk_fused_supported(int w, int n_trees);
 
 // tuning knobs (pk_set_tuning): fused = -1 auto, 0 unfused kernels, 1 / 2 fused variants
 static int g_tune_fused = -1;
@@ -167,23 +167,23 @@ extern "C" int pk_forest_create(int device, int32_t n_trees, int32_t n_features,
             int32_t l = left[o + v], r = right[o + v];
             if (l == -1) {
                 double val = leaf_p1[o + v];
+                if (!(val >= 0.0) || std::signbit(val)) { pk_set_error("pk_forest_create: leaf value %g is not a fraction", val); return PK_EINVAL; }
                 memcpy(&nodes[(size_t)p], &val, 8);
             } else {
                 int32_t ft = feature[o + v];
                 if (ft < 0 || ft >= n_features) { pk_set_error("pk_forest_create: feature index %d out of range", ft); return PK_EINVAL; }
                 if (newid[l] != newid[v] + 1) { pk_set_error("pk_forest_create: internal preorder error"); return PK_EINVAL; }
                 uint32_t roff = (uint32_t)(newid[r] - newid[v]);
-                if (roff >= (1u << 19)) { pk_set_error("pk_forest_create: tree %d too large (right offset %u)", t, roff); return PK_EUNSUPPORTED; }
+                if (roff >= (1u << 18)) { pk_set_error("pk_forest_create: tree %d too large (right offset %u)", t, roff); return PK_EUNSUPPORTED; }
                 float thr = round_down_f32(threshold[o + v]);
-                uint32_t meta = (uint32_t)ft | ((missing_left && missing_left[o + v]) ? (1u << 10) : 0u) |
-                                ((left[o + l] == -1) ? (1u << 11) : 0u) | ((left[o + r] == -1) ? (1u << 12) : 0u) |
-                                (roff << 13);
+                uint32_t meta = 0x80000000u | ((missing_left && missing_left[o + v]) ? (1u << 30) : 0u) |
+                                (roff << 12) | ((uint32_t)ft << 2);
                 uint32_t tb;
                 memcpy(&tb, &thr, 4);
                 nodes[(size_t)p] = make_uint2(tb, meta);
             }
         }
-        roots[(size_t)t] = (uint32_t)o | ((left[o] == -1) ? 0x80000000u : 0u);
+        roots[(size_t)t] = (uint32_t)o;
         if (this_depth > 255) { pk_set_error("pk_forest_create: tree %d deeper than 255", t); return PK_EUNSUPPORTED; }
         tdepth[(size_t)t] = (uint8_t)this_depth;
     }
@@ -193,9 +193,13 @@ extern "C" int pk_forest_create(int device, int32_t n_trees, int32_t n_features,
         int64_t gbase = node_offset[t] & ~1LL;
         int32_t t1 = t + 1;
         while (t1 < n_trees && node_offset[t1 + 1] - gbase <= PK_TREE_BUF_NODES) ++t1;
+        // the fused kernel walks four trees at a time: prefer multiples of four
+        if (t1 < n_trees && t1 - t > 4 && (t1 - t) % 4) t1 -= (t1 - t) % 4;
+        const bool fits = node_offset[t1] - gbase <= PK_TREE_BUF_NODES;
         int64_t staged = std::min<int64_t>(node_offset[t1] - gbase, PK_TREE_BUF_NODES);
         staged = (staged + 1) & ~1LL;                       // 16-byte multiple; array is padded
-        groups.push_back(make_int4(t, t1 - t, (int)gbase, (int)staged));
+        // .w > 0: every tree of the group is fully staged; < 0: only the first -w nodes are
+        groups.push_back(make_int4(t, t1 - t, (int)gbase, fits ? (int)staged : -(int)staged));
         t = t1;
     }
     PK_CUDA(cudaSetDevice(device));
@@ -537,7 +541,7 @@ extern "C" int pk_chrom_score(pk_chrom* c, pk_forest* f, double min_prob) {
     cudaStream_t s = c->stream;
     PK_CHECK(ensure_score_buffers(c));
     PK_CUDA(cudaEventRecord(c->ev[7], s));
-    const bool fused = g_tune_fused != 0 && pk_fused_supported(c->w);
+    const bool fused = g_tune_fused != 0 && pk_fused_supported(c->w, f->n_trees);
     if (fused) {
         // features stay in shared memory; stage [4] reports the fused kernel, [5] is 0
         if (c->n_cand > 0) PK_CUDA(cudaMemsetAsync(c->d_keep, 0, (size_t)c->n_cand, s));

@@ -31,28 +31,28 @@ void pk_set_error(const char* fmt, ...);
 // ---------------------------------------------------------------------------
 // forest: nodes renumbered in preorder (left child = parent + 1), 8 bytes each.
 //   internal: .x = float32 threshold rounded toward -inf (x_f32 <= t_f64 <=> x_f32 <= .x)
-//             .y = feature[0:10) | missing_go_left<<10 | left_is_leaf<<11 |
-//                  right_is_leaf<<12 | (right - self)<<13
-//   leaf:     the 8 bytes are the float64 class-1 fraction
+//             .y = 1<<31 | missing_go_left<<30 | (right - self)<<12 [18 bits] | feature*4 [12 bits]
+//   leaf:     the 8 bytes are the float64 class-1 fraction (>= 0, so bit 31 of .y is 0)
 // ---------------------------------------------------------------------------
 struct pk_forest {
     int device = 0;
     int32_t n_trees = 0, n_features = 0;
     int64_t n_nodes = 0;
     uint2* d_nodes = nullptr;        // [n_nodes]
-    uint32_t* d_root = nullptr;      // [n_trees] packed index of the root | (root_is_leaf << 31)
+    uint32_t* d_root = nullptr;      // [n_trees] packed index of the root
     int32_t* d_orig = nullptr;       // [n_nodes] tree-local sklearn node id (apply tap)
     uint8_t* d_depth = nullptr;      // [n_trees] depth of the deepest leaf
     // tree groups staged into shared memory by the fused kernel: consecutive trees
     // whose nodes fit one buffer of PK_TREE_BUF_NODES; a larger tree is its own group
     // and only its first PK_TREE_BUF_NODES nodes are staged.
-    //   .x first tree, .y number of trees, .z first staged node (even), .w staged nodes (even)
+    //   .x first tree, .y number of trees, .z first staged node (even),
+    //   .w staged nodes (even); negative when the group's single tree is only partly staged
     int4* d_groups = nullptr;
     int32_t n_groups = 0;
     int32_t max_depth = 0;
 };
 
-#define PK_TREE_BUF_NODES 2048       // 16 KB per buffer, two buffers per CTA
+#define PK_TREE_BUF_NODES 2432       // 19 KB per buffer, two buffers per CTA
 
 struct pk_chrom {
     int device = 0;

@@ -1,16 +1,18 @@
 // peakachu_b200: fused window-features + forest kernel (the dominant stage).
 //
-// One persistent CTA of P threads per SM slot. It repeats:
+// One persistent CTA of P threads (P pixels) per SM slot. It repeats:
 //   phase A  (scoreUtils.py:70-93)  fill a shared-memory feature buffer with up to P
 //            windows that pass the reference's filters. A warp works on two candidates
-//            at a time, one per 16-lane half; lane h of a half owns column h of the
-//            (2W+1)^2 window for the vertical Gaussian pass and row h for the horizontal
-//            pass, so both passes run in registers with one shared-memory transpose.
+//            at a time, one per 16-lane half. All 32 lanes gather the 2*(2W+1)^2 cells in
+//            band-contiguous (window-diagonal) order and balance them; then lane h of a
+//            half owns column h of its window for the vertical Gaussian pass and row h
+//            for the horizontal pass, so both passes run in registers with one
+//            shared-memory transpose in between.
 //   phase B  (scoreUtils.py:109)    one pixel per thread walks the forest. Trees are
 //            staged group by group into two shared-memory buffers with TMA bulk copies
 //            (cp.async.bulk + mbarrier), so node fetches are LDS instead of divergent
-//            global loads; four trees are walked at once per thread for ILP, leaf
-//            values are added in estimator order in float64.
+//            global loads. Four trees are walked at once per thread, branch-free, for
+//            ILP; leaf values are added in estimator order in float64.
 // Features never leave the SM: HBM traffic is the band cells of the windows, the
 // candidate list and one (keep, prob) pair per candidate.
 #include "pk_common.cuh"
@@ -58,28 +60,65 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 template <int W, int P>
 struct FusedSmem {
     static constexpr int S = 2 * W + 1, F = S * S, NW = P / 32;
-    static constexpr size_t fea_bytes = (size_t)P * F * 4;
     static constexpr size_t node_bytes = 2 * (size_t)PK_TREE_BUF_NODES * 8;
-    static constexpr size_t scratch_bytes = (size_t)NW * 2 * F * (8 + 4);
-    static size_t total(int ND) {
-        return node_bytes + fea_bytes + (size_t)((ND + 1) & ~1) * 8 + scratch_bytes + (size_t)P * 4 + (size_t)F * 2 + 64;
+    static constexpr size_t fea_bytes = (size_t)P * F * 4;
+    static constexpr size_t scratch_bytes = (size_t)NW * 2 * F * 8;
+    static size_t total(int ND, int n_trees) {
+        return node_bytes + fea_bytes + (size_t)((ND + 1) & ~1) * 8 + scratch_bytes + (size_t)P * 4 +
+               (size_t)n_trees * 4 + (size_t)((n_trees + 3) & ~3) + (size_t)((F + 1) & ~1) * 2 + (size_t)P + 64;
     }
 };
+
+// ---- phase B primitives: explicit 32-bit shared addresses, predicated loads ----
+__device__ __forceinline__ void lds_node_if(uint32_t addr, bool pred, uint2& nd) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\n@q ld.shared.v2.u32 {%0, %1}, [%2];\n}"
+                 : "+r"(nd.x), "+r"(nd.y) : "r"(addr), "r"((uint32_t)pred));
+}
+// one level of one chain. `nd` is the node at shared address `addr`; an internal node
+// moves to a child and loads it, a leaf stays (its 8 bytes are the leaf value).
+// No branch: the loads are predicated on "internal", the step is selected. NaN features
+// are handled by the caller on a separate path (NaN compares false: always right).
+//   feature byte offset = y & 0xFFC, right-child byte offset = (y >> 9) & 0x1FFFF8
+__device__ __forceinline__ void pk_step(uint32_t xrow_addr, uint32_t& addr, uint2& nd) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q, le;\n"
+        ".reg .u32 t, s;\n"
+        ".reg .f32 x, thr;\n"
+        "setp.lt.s32 q, %2, 0;\n"
+        "and.b32 t, %2, 0xFFC;\n"
+        "add.u32 t, t, %3;\n"
+        "@q ld.shared.f32 x, [t];\n"
+        "mov.b32 thr, %1;\n"
+        "setp.le.f32 le, x, thr;\n"
+        "shr.u32 s, %2, 9;\n"
+        "and.b32 s, s, 0x1FFFF8;\n"
+        "selp.u32 s, 8, s, le;\n"
+        "selp.u32 s, s, 0, q;\n"
+        "add.u32 %0, %0, s;\n"
+        "@q ld.shared.v2.u32 {%1, %2}, [%0];\n"
+        "}"
+        : "+r"(addr), "+r"(nd.x), "+r"(nd.y)
+        : "r"(xrow_addr));
+}
 
 template <int W, int P>
 __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const FusedParams prm) {
     constexpr int S = 2 * W + 1, F = S * S, NW = P / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: node buffers (16 B aligned) | features | exp | per-warp scratch | slot->candidate | lut | barriers
+    // layout: node buffers (16 B aligned) | features | exp | per-warp window scratch | slot->candidate |
+    //         tree roots | tree depths | cell order | nan flags | barriers
     uint2* s_nodes = reinterpret_cast<uint2*>(smem_raw);
     float* s_fea = reinterpret_cast<float*>(smem_raw + FusedSmem<W, P>::node_bytes);
     double* s_exp = reinterpret_cast<double*>(smem_raw + FusedSmem<W, P>::node_bytes + FusedSmem<W, P>::fea_bytes);
     const int ND = prm.ND, NDp = (ND + 1) & ~1;
     double* s_V = s_exp + NDp;                                    // [NW][2][F] float64
-    int32_t* s_C = reinterpret_cast<int32_t*>(s_V + (size_t)NW * 2 * F);   // [NW][2][F] int32
-    int32_t* s_idx = s_C + (size_t)NW * 2 * F;                    // [P]
-    uint16_t* s_lut = reinterpret_cast<uint16_t*>(s_idx + P);     // [F] cell order, diagonal-major
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_lut + F) + 15) & ~(uintptr_t)15);
+    int32_t* s_idx = reinterpret_cast<int32_t*>(s_V + (size_t)NW * 2 * F);   // [P]
+    uint32_t* s_root = reinterpret_cast<uint32_t*>(s_idx + P);    // [n_trees]
+    uint8_t* s_depth = reinterpret_cast<uint8_t*>(s_root + prm.n_trees);     // [n_trees] (padded to 4)
+    uint16_t* s_lut = reinterpret_cast<uint16_t*>(s_depth + ((prm.n_trees + 3) & ~3));   // [F] cell order
+    uint8_t* s_nan = reinterpret_cast<uint8_t*>(s_lut + ((F + 1) & ~1));     // [P]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_nan + P) + 15) & ~(uintptr_t)15);
     __shared__ int s_nkept, s_take, s_done;
     __shared__ long long s_start;
 
@@ -90,6 +129,7 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
 
     // ---- one-time setup -----------------------------------------------------
     for (int i = tid; i < ND; i += P) s_exp[i] = prm.expv[i];
+    for (int i = tid; i < prm.n_trees; i += P) { s_root[i] = prm.roots[i]; s_depth[i] = prm.depth[i]; }
     if (tid == 0) {
         // cells ordered by window diagonal (b - a), then along it: contiguous in the band
         int k = 0;
@@ -108,18 +148,18 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
     auto issue = [&](uint32_t pos) {
         if (tid == 0) {
             const int4 g = prm.groups[pos % G];
-            const uint32_t bytes = (uint32_t)g.w * 8u;
+            const uint32_t bytes = (uint32_t)(g.w < 0 ? -g.w : g.w) * 8u;
             uint64_t* bar = &s_bar[pos & 1];
             mbar_expect_tx(bar, bytes);
             bulk_g2s(s_nodes + (size_t)(pos & 1) * PK_TREE_BUF_NODES, prm.nodes + g.z, bytes, bar);
         }
     };
     issue(0); issued = 1;
-    if (G > 1 || !resident) { issue(1); issued = 2; }
+    if (G > 1) { issue(1); issued = 2; }
     bool first_batch = true;
 
-    double* myV = s_V + (size_t)(wib * 2 + half) * F;
-    int32_t* myC = s_C + (size_t)(wib * 2 + half) * F;
+    double* V0 = s_V + (size_t)(wib * 2) * F;       // both windows of this warp
+    double* myV = V0 + (size_t)half * F;
 
     for (;;) {
         // ================= phase A: features =================
@@ -146,48 +186,41 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
                 if (have) { x = prm.cx[ci]; d = prm.cd[ci]; }
                 const int y = x + d;
                 bool ok = have && (x - W >= 0) && (y + W + 1 <= prm.n);        // scoreUtils.py:75
-                // gather both windows with all 32 lanes, cells in diagonal-major order
+                // gather + balance both windows with all 32 lanes, cells in diagonal-major order
+                int nz0 = 0, nz1 = 0;
                 {
                     const int x0 = __shfl_sync(0xffffffffu, x, 0), d0 = __shfl_sync(0xffffffffu, d, 0);
                     const int x1 = __shfl_sync(0xffffffffu, x, 16), d1 = __shfl_sync(0xffffffffu, d, 16);
                     const bool ok0 = __shfl_sync(0xffffffffu, (int)ok, 0), ok1 = __shfl_sync(0xffffffffu, (int)ok, 16);
-                    int32_t* C0 = s_C + (size_t)(wib * 2) * F;
 #pragma unroll 2
-                    for (int idx = lane; idx < 2 * F; idx += 32) {
+                    for (int i0 = 0; i0 < 2 * F; i0 += 32) {
+                        const int idx = i0 + lane;
                         const int k = idx >= F;
-                        const int cell = s_lut[idx - k * F];
-                        const int a = cell >> 8, b = cell & 255;
-                        const int xx = k ? x1 : x0, dd0 = k ? d1 : d0;
-                        if (k ? ok1 : ok0) {
+                        bool nzf = false;
+                        if (idx < 2 * F && (k ? ok1 : ok0)) {
+                            const int cell = s_lut[idx - k * F];
+                            const int a = cell >> 8, b = cell & 255;
+                            const int xx = k ? x1 : x0, dd0 = k ? d1 : d0;
                             const int r = xx - W + a, c = xx + dd0 - W + b;
                             const int dd = c - r, ad = dd < 0 ? -dd : dd, lo = dd < 0 ? c : r;
-                            int cnt = 0;
-                            if (ad < ND - 1) cnt = __ldg(prm.band + (long long)ad * prm.pitch + lo);   // scoreUtils.py:31
-                            C0[(size_t)k * F + a * S + b] = cnt;
+                            double v = 0.0;
+                            if (ad < ND - 1) {                                 // scoreUtils.py:31
+                                const int cnt = __ldg(prm.band + (long long)ad * prm.pitch + lo);
+                                if (cnt != 0)
+                                    v = pk_value(cnt, prm.balanced ? __ldg(prm.w + r) : 0.0,
+                                                 prm.balanced ? __ldg(prm.w + c) : 0.0, prm.balanced);
+                            }
+                            V0[(size_t)k * F + a * S + b] = v;
+                            nzf = v != 0.0;
                         }
+                        const unsigned bal = __ballot_sync(0xffffffffu, nzf);
+                        const unsigned m1 = __ballot_sync(0xffffffffu, k != 0);
+                        nz0 += __popc(bal & ~m1);
+                        nz1 += __popc(bal & m1);
                     }
                 }
                 __syncwarp();
-                const bool act = ok && (h < S);
-                double v[S];
-                int nz = 0;
-                if (act) {
-                    const double wc = prm.balanced ? prm.w[y - W + h] : 0.0;
-#pragma unroll
-                    for (int a = 0; a < S; ++a) {
-                        const int cnt = myC[a * S + h];
-                        const double wr = prm.balanced ? __ldg(prm.w + x - W + a) : 0.0;
-                        v[a] = pk_value(cnt, wr, wc, prm.balanced);
-                        nz += (v[a] != 0.0);
-                        myV[a * S + h] = v[a];
-                    }
-                }
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
-                __syncwarp();
-                if (ok) {
-                    if ((double)nz < (double)F * 0.1) ok = false;              // utils.py:225
-                }
+                if (ok && (double)(half ? nz1 : nz0) < (double)F * 0.1) ok = false;   // utils.py:225
                 if (ok) {
                     double s = 0.0;                                            // utils.py:228 (numba order)
 #pragma unroll
@@ -197,7 +230,6 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
                     const double ll = __ddiv_rn(s, (double)(W * W));
                     ok = (ll > 0.0) && (__ddiv_rn(myV[W * S + W], ll) > 0.1);  // utils.py:229-232
                 }
-                __syncwarp();                                                  // V is overwritten below
                 const bool kept = ok;                                          // uniform within the half
                 const bool actk = kept && (h < S);
                 int slot = 0;
@@ -208,11 +240,12 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
                 double g[S];
                 if (actk) {
                     // distance normalisation (utils.py:187-200) + vertical pass in registers (column h)
+                    double v[S];
 #pragma unroll
                     for (int a = 0; a < S; ++a) {
                         int dd = d + h - a;
                         dd = dd < 0 ? -dd : dd;
-                        v[a] = __ddiv_rn(v[a], s_exp[dd]);
+                        v[a] = __ddiv_rn(myV[a * S + h], s_exp[dd]);
                     }
 #pragma unroll
                     for (int a = 0; a < S; ++a) {
@@ -220,8 +253,13 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
 #pragma unroll
                         for (int jj = 4; jj >= 1; --jj)
                             t = __dadd_rn(t, __dmul_rn(__dadd_rn(v[pk_reflect(a - jj, S)], v[pk_reflect(a + jj, S)]), PK_GK[4 - jj]));
-                        myV[a * S + h] = t;
+                        g[a] = t;
                     }
+                }
+                __syncwarp();                    // every lane has read its column (and the ll corner)
+                if (actk) {
+#pragma unroll
+                    for (int a = 0; a < S; ++a) myV[a * S + h] = g[a];
                 }
                 __syncwarp();
                 if (actk) {
@@ -246,18 +284,25 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
                     mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                     has_nan |= (bool)__shfl_xor_sync(0xffffffffu, (int)has_nan, o);
                 }
+                bool fnan = false;
                 if (actk) {
                     if (has_nan) { mn = CUDART_NAN; mx = CUDART_NAN; }          // numba min/max propagate NaN
                     const double range = __dsub_rn(mx, mn);
                     float* frow = s_fea + (size_t)slot * F + h * S;
 #pragma unroll
-                    for (int b = 0; b < S; ++b)
-                        frow[b] = __double2float_rn(__ddiv_rn(__dsub_rn(g[b], mn), range));   // utils.py:207
-                    if (h == 0) {
-                        s_idx[slot] = (int)ci;
-                        prm.keep[ci] = 1;
-                        atomicAdd(&prm.batch_win[prm.crank[ci] / PK_BATCH], 1);
+                    for (int b = 0; b < S; ++b) {
+                        const double q = __ddiv_rn(__dsub_rn(g[b], mn), range);   // utils.py:207
+                        fnan |= isnan(q);
+                        frow[b] = __double2float_rn(q);
                     }
+                }
+                // any NaN feature sends this pixel through the missing_go_to_left-aware walk
+                const unsigned nanbal = __ballot_sync(0xffffffffu, fnan);
+                if (kept && h == 0) {
+                    s_idx[slot] = (int)ci;
+                    s_nan[slot] = ((nanbal >> (half * 16)) & 0xffffu) ? 1 : 0;
+                    prm.keep[ci] = 1;
+                    atomicAdd(&prm.batch_win[prm.crank[ci] / PK_BATCH], 1);
                 }
                 __syncwarp();
             }
@@ -273,47 +318,59 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
         if (nkept > 0) {
             const bool mine = tid < nkept;
             const float* xrow = s_fea + (size_t)tid * F;
+            const bool warp_nan = __any_sync(0xffffffffu, mine && s_nan[tid]);
             double acc = 0.0;
             for (int gi = 0; gi < G; ++gi) {
                 const uint32_t pos = resident ? (uint32_t)gi : consumed;
                 if (!resident || first_batch) mbar_wait(&s_bar[pos & 1], (pos >> 1) & 1);
                 const int4 grp = prm.groups[gi];
+                const uint32_t gbase = (uint32_t)grp.z;
+                const bool fits = grp.w > 0;                   // every tree of the group is fully staged
+                const uint32_t staged = (uint32_t)(fits ? grp.w : -grp.w);
                 const uint2* buf = s_nodes + (size_t)(pos & 1) * PK_TREE_BUF_NODES;
-                const uint32_t gbase = (uint32_t)grp.z, staged = (uint32_t)grp.w;
+                const uint32_t buf_addr = smem_u32(buf);
+                const uint32_t xrow_addr = smem_u32(xrow);
+                const int t_end = grp.x + grp.y;
                 if (mine) {
-                    for (int t = grp.x; t < grp.x + grp.y; t += 4) {
-                        uint32_t p[4]; bool run[4]; int maxd = 0;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const bool ex = (t + k) < grp.x + grp.y;
-                            const uint32_t root = ex ? prm.roots[t + k] : 0x80000000u;
-                            p[k] = root & 0x7fffffffu;
-                            run[k] = ex && !(root >> 31);
-                            const int dp = ex ? (int)prm.depth[t + k] : 0;
-                            maxd = dp > maxd ? dp : maxd;
-                        }
-                        for (int lvl = 0; lvl < maxd; ++lvl) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (run[k]) {
-                                    const uint32_t off = p[k] - gbase;
-                                    const uint2 nd = off < staged ? buf[off] : __ldg(prm.nodes + p[k]);
-                                    const float xv = xrow[nd.y & ((1u << PK_FEAT_BITS) - 1u)];
-                                    const bool left = isnan(xv) ? ((nd.y >> 10) & 1u) : (xv <= __uint_as_float(nd.x));
-                                    const bool leaf = left ? ((nd.y >> 11) & 1u) : ((nd.y >> 12) & 1u);
-                                    p[k] = left ? p[k] + 1u : p[k] + (nd.y >> 13);
-                                    run[k] = !leaf;
-                                }
+                    if (fits && !warp_nan) {
+                        for (int t = grp.x; t < t_end; t += 4) {
+                            const bool e1 = t + 1 < t_end, e2 = t + 2 < t_end, e3 = t + 3 < t_end;
+                            // chains past the end of the group re-walk the group's first tree and are dropped
+                            uint32_t a0 = buf_addr + (s_root[t] - gbase) * 8u;
+                            uint32_t a1 = buf_addr + (s_root[e1 ? t + 1 : t] - gbase) * 8u;
+                            uint32_t a2 = buf_addr + (s_root[e2 ? t + 2 : t] - gbase) * 8u;
+                            uint32_t a3 = buf_addr + (s_root[e3 ? t + 3 : t] - gbase) * 8u;
+                            int maxd = s_depth[t];
+                            if (e1) maxd = max(maxd, (int)s_depth[t + 1]);
+                            if (e2) maxd = max(maxd, (int)s_depth[t + 2]);
+                            if (e3) maxd = max(maxd, (int)s_depth[t + 3]);
+                            uint2 n0 = make_uint2(0, 0), n1 = n0, n2 = n0, n3 = n0;
+                            lds_node_if(a0, true, n0); lds_node_if(a1, true, n1);
+                            lds_node_if(a2, true, n2); lds_node_if(a3, true, n3);
+                            for (int lvl = 0; lvl < maxd; ++lvl) {
+                                pk_step(xrow_addr, a0, n0);
+                                pk_step(xrow_addr, a1, n1);
+                                pk_step(xrow_addr, a2, n2);
+                                pk_step(xrow_addr, a3, n3);
                             }
+                            acc = __dadd_rn(acc, __hiloint2double((int)n0.y, (int)n0.x));      // estimator order
+                            if (e1) acc = __dadd_rn(acc, __hiloint2double((int)n1.y, (int)n1.x));
+                            if (e2) acc = __dadd_rn(acc, __hiloint2double((int)n2.y, (int)n2.x));
+                            if (e3) acc = __dadd_rn(acc, __hiloint2double((int)n3.y, (int)n3.x));
                         }
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if ((t + k) < grp.x + grp.y) {
-                                const uint32_t off = p[k] - gbase;
-                                const double lv = off < staged ? reinterpret_cast<const double*>(buf)[off]
-                                                               : __ldg(reinterpret_cast<const double*>(prm.nodes) + p[k]);
-                                acc = __dadd_rn(acc, lv);                      // estimator order
+                    } else {
+                        // general walk: NaN features follow missing_go_to_left; the tail of a tree
+                        // larger than the staging buffer is read from global memory (L2)
+                        for (int t = grp.x; t < t_end; ++t) {
+                            uint32_t p = s_root[t] - gbase;
+                            uint2 nd = p < staged ? buf[p] : __ldg(prm.nodes + gbase + p);
+                            while (PK_NODE_INTERNAL(nd.y)) {
+                                const float xv = xrow[PK_NODE_FEAT(nd.y)];
+                                const bool left = isnan(xv) ? (PK_NODE_MGL(nd.y) != 0u) : (xv <= __uint_as_float(nd.x));
+                                p += left ? 1u : PK_NODE_ROFF(nd.y);
+                                nd = p < staged ? buf[p] : __ldg(prm.nodes + gbase + p);
                             }
+                            acc = __dadd_rn(acc, __hiloint2double((int)nd.y, (int)nd.x));
                         }
                     }
                 }
@@ -340,14 +397,14 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
 
 template <int W, int P>
 static int launch_fused_t(const FusedParams& prm, int ND, int sm_count, cudaStream_t stream) {
-    const size_t smem = FusedSmem<W, P>::total(ND);
+    const size_t smem = FusedSmem<W, P>::total(ND, prm.n_trees);
     if (smem > 227 * 1024 - 256) { pk_set_error("fused kernel: %zu bytes of shared memory needed", smem); return PK_EUNSUPPORTED; }
     static size_t attr_set = 0;      // largest dynamic size opted into so far
     if (smem > attr_set) {
         PK_CUDA(cudaFuncSetAttribute(k_score_fused<W, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(P <= 128 ? 2 : 1, (227 * 1024) / smem));
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(P <= 128 ? 2 : 1, (227 * 1024) / (smem + 1024)));
     long long want = (prm.n_cand + P - 1) / P;
     unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)sm_count * per_sm));
     k_score_fused<W, P><<<grid, P, smem, stream>>>(prm);
@@ -355,7 +412,6 @@ static int launch_fused_t(const FusedParams& prm, int ND, int sm_count, cudaStre
     return PK_OK;
 }
 
-// returns PK_EUNSUPPORTED (without touching the error string) when no fused variant fits
 int pk_launch_fused(pk_chrom* c, const pk_forest* f, int variant) {
     if (c->n_cand == 0) return PK_OK;
     FusedParams prm;
@@ -375,4 +431,4 @@ int pk_launch_fused(pk_chrom* c, const pk_forest* f, int variant) {
     return PK_EUNSUPPORTED;
 }
 
-bool pk_fused_supported(int w) { return w == 5 || w == 7; }
+bool pk_fused_supported(int w, int n_trees) { return (w == 5 || w == 7) && n_trees <= 2048; }

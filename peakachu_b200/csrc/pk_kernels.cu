@@ -387,19 +387,16 @@ __global__ void __launch_bounds__(PK_FEAT_WARPS * 32) k_features(
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double pk_tree_eval(const uint2* __restrict__ nodes, uint32_t root,
                                                const float* __restrict__ xrow, uint32_t* leaf_slot) {
-    uint32_t p = root & 0x7fffffffu;
-    if (!(root >> 31)) {
-        for (;;) {
-            uint2 nd = nodes[p];
-            float xv = xrow[nd.y & ((1u << PK_FEAT_BITS) - 1u)];
-            bool left = isnan(xv) ? ((nd.y >> 10) & 1u) : (xv <= __uint_as_float(nd.x));
-            bool leaf = left ? ((nd.y >> 11) & 1u) : ((nd.y >> 12) & 1u);
-            p = left ? p + 1u : p + (nd.y >> 13);
-            if (leaf) break;
-        }
+    uint32_t p = root;
+    uint2 nd = nodes[p];
+    while (PK_NODE_INTERNAL(nd.y)) {
+        const float xv = xrow[PK_NODE_FEAT(nd.y)];
+        const bool left = isnan(xv) ? (PK_NODE_MGL(nd.y) != 0u) : (xv <= __uint_as_float(nd.x));
+        p = left ? p + 1u : p + PK_NODE_ROFF(nd.y);
+        nd = nodes[p];
     }
     *leaf_slot = p;
-    return reinterpret_cast<const double*>(nodes)[p];
+    return __hiloint2double((int)nd.y, (int)nd.x);
 }
 
 __global__ void __launch_bounds__(128) k_forest(
