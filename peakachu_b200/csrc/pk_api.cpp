@@ -22,7 +22,7 @@ int pk_launch_features(pk_chrom* c, double* d_fea64);
 int pk_launch_forest(const pk_forest* f, const float* X, const uint8_t* keep, int64_t n_rows, int32_t* leaves,
                      double* proba, cudaStream_t stream);
 int pk_launch_emit(pk_chrom* c, double thre);
-int pk_launch_fused(pk_chrom* c, const pk_forest* f, int variant);
+int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant);
 bool pk_fused_supported(int w, int n_trees);
 
 // tuning knobs (pk_set_tuning): fused = -1 auto, 0 unfused kernels, 1 / 2 fused variants
@@ -187,29 +187,13 @@ extern "C" int pk_forest_create(int device, int32_t n_trees, int32_t n_features,
         if (this_depth > 255) { pk_set_error("pk_forest_create: tree %d deeper than 255", t); return PK_EUNSUPPORTED; }
         tdepth[(size_t)t] = (uint8_t)this_depth;
     }
-    // groups of consecutive trees for shared-memory staging
-    std::vector<int4> groups;
-    for (int32_t t = 0; t < n_trees;) {
-        int64_t gbase = node_offset[t] & ~1LL;
-        int32_t t1 = t + 1;
-        while (t1 < n_trees && node_offset[t1 + 1] - gbase <= PK_TREE_BUF_NODES) ++t1;
-        // the fused kernel walks four trees at a time: prefer multiples of four
-        if (t1 < n_trees && t1 - t > 4 && (t1 - t) % 4) t1 -= (t1 - t) % 4;
-        const bool fits = node_offset[t1] - gbase <= PK_TREE_BUF_NODES;
-        int64_t staged = std::min<int64_t>(node_offset[t1] - gbase, PK_TREE_BUF_NODES);
-        staged = (staged + 1) & ~1LL;                       // 16-byte multiple; array is padded
-        // .w > 0: every tree of the group is fully staged; < 0: only the first -w nodes are
-        groups.push_back(make_int4(t, t1 - t, (int)gbase, fits ? (int)staged : -(int)staged));
-        t = t1;
-    }
     PK_CUDA(cudaSetDevice(device));
     pk_forest* f = new pk_forest();
     f->device = device; f->n_trees = n_trees; f->n_features = n_features; f->n_nodes = total; f->max_depth = max_depth;
     int r;
-    f->n_groups = (int32_t)groups.size();
+    f->h_node_offset.assign(node_offset, node_offset + n_trees + 1);
     if ((r = dev_alloc(&f->d_nodes, (size_t)total + 4)) || (r = dev_alloc(&f->d_root, (size_t)n_trees)) ||
-        (r = dev_alloc(&f->d_orig, (size_t)total)) || (r = dev_alloc(&f->d_depth, (size_t)n_trees)) ||
-        (r = dev_alloc(&f->d_groups, groups.size()))) {
+        (r = dev_alloc(&f->d_orig, (size_t)total)) || (r = dev_alloc(&f->d_depth, (size_t)n_trees))) {
         pk_forest_destroy(f);
         return r;
     }
@@ -218,15 +202,42 @@ extern "C" int pk_forest_create(int device, int32_t n_trees, int32_t n_features,
     PK_CUDA(cudaMemcpy(f->d_orig, orig.data(), (size_t)total * sizeof(int32_t), cudaMemcpyHostToDevice));
     PK_CUDA(cudaMemset(f->d_nodes + total, 0, 4 * sizeof(uint2)));
     PK_CUDA(cudaMemcpy(f->d_depth, tdepth.data(), (size_t)n_trees, cudaMemcpyHostToDevice));
-    PK_CUDA(cudaMemcpy(f->d_groups, groups.data(), groups.size() * sizeof(int4), cudaMemcpyHostToDevice));
     *out = f;
+    return PK_OK;
+}
+
+int pk_forest_groups(pk_forest* f, int tbn, int chunk, const int4** d_groups, int32_t* n_groups) {
+    for (auto& g : f->group_tables)
+        if (g.tbn == tbn && g.chunk == chunk) { *d_groups = g.d; *n_groups = g.n; return PK_OK; }
+    const std::vector<int64_t>& off = f->h_node_offset;
+    const int32_t n_trees = f->n_trees;
+    std::vector<int4> groups;
+    for (int32_t t = 0; t < n_trees;) {
+        int64_t gbase = off[t] & ~1LL;
+        int32_t t1 = t + 1;
+        while (t1 < n_trees && off[t1 + 1] - gbase <= tbn) ++t1;
+        if (t1 < n_trees && t1 - t > chunk && (t1 - t) % chunk) t1 -= (t1 - t) % chunk;
+        const bool fits = off[t1] - gbase <= tbn;
+        int64_t staged = std::min<int64_t>(off[t1] - gbase, tbn);
+        staged = (staged + 1) & ~1LL;                       // 16-byte multiple; the node array is padded
+        groups.push_back(make_int4(t, t1 - t, (int)gbase, fits ? (int)staged : -(int)staged));
+        t = t1;
+    }
+    pk_forest::GroupTable gt;
+    gt.tbn = tbn; gt.chunk = chunk; gt.n = (int32_t)groups.size();
+    PK_CUDA(cudaSetDevice(f->device));
+    PK_CHECK(dev_alloc(&gt.d, groups.size()));
+    PK_CUDA(cudaMemcpy(gt.d, groups.data(), groups.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    f->group_tables.push_back(gt);
+    *d_groups = gt.d; *n_groups = gt.n;
     return PK_OK;
 }
 
 extern "C" int pk_forest_destroy(pk_forest* f) {
     if (!f) return PK_OK;
     cudaSetDevice(f->device);
-    dev_free(f->d_nodes); dev_free(f->d_root); dev_free(f->d_orig); dev_free(f->d_depth); dev_free(f->d_groups);
+    dev_free(f->d_nodes); dev_free(f->d_root); dev_free(f->d_orig); dev_free(f->d_depth);
+    for (auto& g : f->group_tables) dev_free(g.d);
     delete f;
     return PK_OK;
 }

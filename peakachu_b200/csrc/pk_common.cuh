@@ -42,17 +42,20 @@ struct pk_forest {
     uint32_t* d_root = nullptr;      // [n_trees] packed index of the root
     int32_t* d_orig = nullptr;       // [n_nodes] tree-local sklearn node id (apply tap)
     uint8_t* d_depth = nullptr;      // [n_trees] depth of the deepest leaf
-    // tree groups staged into shared memory by the fused kernel: consecutive trees
-    // whose nodes fit one buffer of PK_TREE_BUF_NODES; a larger tree is its own group
-    // and only its first PK_TREE_BUF_NODES nodes are staged.
-    //   .x first tree, .y number of trees, .z first staged node (even),
-    //   .w staged nodes (even); negative when the group's single tree is only partly staged
-    int4* d_groups = nullptr;
-    int32_t n_groups = 0;
     int32_t max_depth = 0;
+    std::vector<int64_t> h_node_offset;   // host copy, for building group tables
+    // tree groups staged into shared memory by the fused kernel, one table per
+    // (buffer nodes, chunk) configuration, built on first use (pk_forest_groups)
+    struct GroupTable { int tbn = 0, chunk = 0; int4* d = nullptr; int32_t n = 0; };
+    std::vector<GroupTable> group_tables;
 };
 
-#define PK_TREE_BUF_NODES 2432       // 19 KB per buffer, two buffers per CTA
+// Group table for buffers of `tbn` nodes: consecutive trees whose nodes fit one buffer
+// (trimmed to a multiple of `chunk` trees when more than one chunk fits); a tree larger
+// than the buffer is its own group and only its first `tbn` nodes are staged.
+//   .x first tree, .y number of trees, .z first staged node (even),
+//   .w staged nodes (even); negative when the group's single tree is only partly staged
+int pk_forest_groups(pk_forest* f, int tbn, int chunk, const int4** d_groups, int32_t* n_groups);
 
 struct pk_chrom {
     int device = 0;

@@ -1,18 +1,20 @@
 // peakachu_b200: fused window-features + forest kernel (the dominant stage).
 //
-// One persistent CTA of P threads (P pixels) per SM slot. It repeats:
+// One persistent CTA of P*TPP threads per SM, scoring P pixels per batch. It repeats:
 //   phase A  (scoreUtils.py:70-93)  fill a shared-memory feature buffer with up to P
 //            windows that pass the reference's filters. A warp works on two candidates
-//            at a time, one per 16-lane half. All 32 lanes gather the 2*(2W+1)^2 cells in
-//            band-contiguous (window-diagonal) order and balance them; then lane h of a
-//            half owns column h of its window for the vertical Gaussian pass and row h
-//            for the horizontal pass, so both passes run in registers with one
-//            shared-memory transpose in between.
-//   phase B  (scoreUtils.py:109)    one pixel per thread walks the forest. Trees are
+//            at a time, one per 16-lane half. All 32 lanes gather the 2*(2W+1)^2 band
+//            cells in band-contiguous (window-diagonal) order -- the loads of the next
+//            pair are issued before the current pair is processed -- and balance them;
+//            then lane h of a half owns column h of its window for the vertical Gaussian
+//            pass and row h for the horizontal pass, so both passes run in registers
+//            with one shared-memory transpose in between.
+//   phase B  (scoreUtils.py:109)    TPP threads per pixel walk the forest. Trees are
 //            staged group by group into two shared-memory buffers with TMA bulk copies
 //            (cp.async.bulk + mbarrier), so node fetches are LDS instead of divergent
-//            global loads. Four trees are walked at once per thread, branch-free, for
-//            ILP; leaf values are added in estimator order in float64.
+//            global loads. Each thread walks four trees at once, branch-free; leaf
+//            values are added in estimator order in float64 (with TPP = 2 the second
+//            thread hands its four leaf values over through shared memory).
 // Features never leave the SM: HBM traffic is the band cells of the windows, the
 // candidate list and one (keep, prob) pair per candidate.
 #include "pk_common.cuh"
@@ -57,22 +59,23 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-template <int W, int P>
-struct FusedSmem {
-    static constexpr int S = 2 * W + 1, F = S * S, NW = P / 32;
-    static constexpr size_t node_bytes = 2 * (size_t)PK_TREE_BUF_NODES * 8;
+template <int W, int P, int TPP, int TBN>
+struct FusedCfg {
+    static constexpr int S = 2 * W + 1, F = S * S, NT = P * TPP, NW = NT / 32;
+    static constexpr int NS = (2 * F + 31) / 32;              // gather slots per lane for a window pair
+    static constexpr int CHUNK = 4 * TPP;                     // trees walked per pixel per pass
+    static constexpr size_t node_bytes = 2 * (size_t)TBN * 8;
     static constexpr size_t fea_bytes = (size_t)P * F * 4;
-    static constexpr size_t scratch_bytes = (size_t)NW * 2 * F * 8;
+    static constexpr size_t scratch_bytes = (size_t)NW * 2 * F * 8;   // window scratch; reused for leaf hand-over
+    static_assert(TPP == 1 || scratch_bytes >= 2 * 4 * (size_t)P * 8, "leaf hand-over does not fit the window scratch");
     static size_t total(int ND, int n_trees) {
         return node_bytes + fea_bytes + (size_t)((ND + 1) & ~1) * 8 + scratch_bytes + (size_t)P * 4 +
                (size_t)n_trees * 4 + (size_t)((n_trees + 3) & ~3) + (size_t)((F + 1) & ~1) * 2 + (size_t)P + 64;
     }
 };
 
-// ---- phase B primitives: explicit 32-bit shared addresses, predicated loads ----
-__device__ __forceinline__ void lds_node_if(uint32_t addr, bool pred, uint2& nd) {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\n@q ld.shared.v2.u32 {%0, %1}, [%2];\n}"
-                 : "+r"(nd.x), "+r"(nd.y) : "r"(addr), "r"((uint32_t)pred));
+__device__ __forceinline__ void lds_node(uint32_t addr, uint2& nd) {
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nd.x), "=r"(nd.y) : "r"(addr));
 }
 // one level of one chain. `nd` is the node at shared address `addr`; an internal node
 // moves to a child and loads it, a leaf stays (its 8 bytes are the leaf value).
@@ -102,15 +105,16 @@ __device__ __forceinline__ void pk_step(uint32_t xrow_addr, uint32_t& addr, uint
         : "r"(xrow_addr));
 }
 
-template <int W, int P>
-__global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const FusedParams prm) {
-    constexpr int S = 2 * W + 1, F = S * S, NW = P / 32;
+template <int W, int P, int TPP, int TBN>
+__global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams prm) {
+    using Cfg = FusedCfg<W, P, TPP, TBN>;
+    constexpr int S = Cfg::S, F = Cfg::F, NT = Cfg::NT, NW = Cfg::NW, NS = Cfg::NS, CHUNK = Cfg::CHUNK;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: node buffers (16 B aligned) | features | exp | per-warp window scratch | slot->candidate |
     //         tree roots | tree depths | cell order | nan flags | barriers
     uint2* s_nodes = reinterpret_cast<uint2*>(smem_raw);
-    float* s_fea = reinterpret_cast<float*>(smem_raw + FusedSmem<W, P>::node_bytes);
-    double* s_exp = reinterpret_cast<double*>(smem_raw + FusedSmem<W, P>::node_bytes + FusedSmem<W, P>::fea_bytes);
+    float* s_fea = reinterpret_cast<float*>(smem_raw + Cfg::node_bytes);
+    double* s_exp = reinterpret_cast<double*>(smem_raw + Cfg::node_bytes + Cfg::fea_bytes);
     const int ND = prm.ND, NDp = (ND + 1) & ~1;
     double* s_V = s_exp + NDp;                                    // [NW][2][F] float64
     int32_t* s_idx = reinterpret_cast<int32_t*>(s_V + (size_t)NW * 2 * F);   // [P]
@@ -119,6 +123,7 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
     uint16_t* s_lut = reinterpret_cast<uint16_t*>(s_depth + ((prm.n_trees + 3) & ~3));   // [F] cell order
     uint8_t* s_nan = reinterpret_cast<uint8_t*>(s_lut + ((F + 1) & ~1));     // [P]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_nan + P) + 15) & ~(uintptr_t)15);
+    double* s_lv = s_V;                                           // [2][4][P] leaf hand-over (phase B only)
     __shared__ int s_nkept, s_take, s_done;
     __shared__ long long s_start;
 
@@ -128,8 +133,8 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
     const bool resident = (G <= 2);
 
     // ---- one-time setup -----------------------------------------------------
-    for (int i = tid; i < ND; i += P) s_exp[i] = prm.expv[i];
-    for (int i = tid; i < prm.n_trees; i += P) { s_root[i] = prm.roots[i]; s_depth[i] = prm.depth[i]; }
+    for (int i = tid; i < ND; i += NT) s_exp[i] = prm.expv[i];
+    for (int i = tid; i < prm.n_trees; i += NT) { s_root[i] = prm.roots[i]; s_depth[i] = prm.depth[i]; }
     if (tid == 0) {
         // cells ordered by window diagonal (b - a), then along it: contiguous in the band
         int k = 0;
@@ -151,7 +156,7 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
             const uint32_t bytes = (uint32_t)(g.w < 0 ? -g.w : g.w) * 8u;
             uint64_t* bar = &s_bar[pos & 1];
             mbar_expect_tx(bar, bytes);
-            bulk_g2s(s_nodes + (size_t)(pos & 1) * PK_TREE_BUF_NODES, prm.nodes + g.z, bytes, bar);
+            bulk_g2s(s_nodes + (size_t)(pos & 1) * TBN, prm.nodes + g.z, bytes, bar);
         }
     };
     issue(0); issued = 1;
@@ -160,6 +165,33 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
 
     double* V0 = s_V + (size_t)(wib * 2) * F;       // both windows of this warp
     double* myV = V0 + (size_t)half * F;
+
+    // ---- gather of one window pair: issue the band loads (registers), consume later ----
+    struct Pair { int x, d; bool ok; int cnt[NS]; };
+    auto pair_load = [&](long long start, int take, int j0, Pair& pr) {
+        const int j = j0 + half;
+        const bool have = j < take;
+        pr.x = 0; pr.d = 0;
+        if (have) { pr.x = prm.cx[start + j]; pr.d = prm.cd[start + j]; }
+        pr.ok = have && (pr.x - W >= 0) && (pr.x + pr.d + W + 1 <= prm.n);      // scoreUtils.py:75
+        const int x0 = __shfl_sync(0xffffffffu, pr.x, 0), d0 = __shfl_sync(0xffffffffu, pr.d, 0);
+        const int x1 = __shfl_sync(0xffffffffu, pr.x, 16), d1 = __shfl_sync(0xffffffffu, pr.d, 16);
+        const bool ok0 = __shfl_sync(0xffffffffu, (int)pr.ok, 0), ok1 = __shfl_sync(0xffffffffu, (int)pr.ok, 16);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int idx = s * 32 + lane;
+            const int k = idx >= F;
+            pr.cnt[s] = 0;
+            if (idx < 2 * F && (k ? ok1 : ok0)) {
+                const int cell = s_lut[idx - k * F];
+                const int a = cell >> 8, b = cell & 255;
+                const int xx = k ? x1 : x0, dd0 = k ? d1 : d0;
+                const int r = xx - W + a, c = xx + dd0 - W + b;
+                const int dd = c - r, ad = dd < 0 ? -dd : dd, lo = dd < 0 ? c : r;
+                if (ad < ND - 1) pr.cnt[s] = __ldg(prm.band + (long long)ad * prm.pitch + lo);   // scoreUtils.py:31
+            }
+        }
+    };
 
     for (;;) {
         // ================= phase A: features =================
@@ -177,24 +209,22 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
             __syncthreads();
             const int take = s_take;
             const long long start = s_start;
+            Pair cur, nxt;
+            if (wib * 2 < take) pair_load(start, take, wib * 2, cur);
             for (int j0 = wib * 2; j0 < take; j0 += NW * 2) {
                 // ---- two candidates per warp, one per half ----
-                const int j = j0 + half;
-                const bool have = j < take;
-                const long long ci = start + j;
-                int x = 0, d = 0;
-                if (have) { x = prm.cx[ci]; d = prm.cd[ci]; }
-                const int y = x + d;
-                bool ok = have && (x - W >= 0) && (y + W + 1 <= prm.n);        // scoreUtils.py:75
-                // gather + balance both windows with all 32 lanes, cells in diagonal-major order
+                const long long ci = start + j0 + half;
+                const int x = cur.x, d = cur.d;
+                bool ok = cur.ok;
+                // balance the gathered counts and stage both windows in shared memory
                 int nz0 = 0, nz1 = 0;
                 {
                     const int x0 = __shfl_sync(0xffffffffu, x, 0), d0 = __shfl_sync(0xffffffffu, d, 0);
                     const int x1 = __shfl_sync(0xffffffffu, x, 16), d1 = __shfl_sync(0xffffffffu, d, 16);
                     const bool ok0 = __shfl_sync(0xffffffffu, (int)ok, 0), ok1 = __shfl_sync(0xffffffffu, (int)ok, 16);
-#pragma unroll 2
-                    for (int i0 = 0; i0 < 2 * F; i0 += 32) {
-                        const int idx = i0 + lane;
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        const int idx = s * 32 + lane;
                         const int k = idx >= F;
                         bool nzf = false;
                         if (idx < 2 * F && (k ? ok1 : ok0)) {
@@ -202,14 +232,11 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
                             const int a = cell >> 8, b = cell & 255;
                             const int xx = k ? x1 : x0, dd0 = k ? d1 : d0;
                             const int r = xx - W + a, c = xx + dd0 - W + b;
-                            const int dd = c - r, ad = dd < 0 ? -dd : dd, lo = dd < 0 ? c : r;
                             double v = 0.0;
-                            if (ad < ND - 1) {                                 // scoreUtils.py:31
-                                const int cnt = __ldg(prm.band + (long long)ad * prm.pitch + lo);
-                                if (cnt != 0)
-                                    v = pk_value(cnt, prm.balanced ? __ldg(prm.w + r) : 0.0,
-                                                 prm.balanced ? __ldg(prm.w + c) : 0.0, prm.balanced);
-                            }
+                            const int cnt = cur.cnt[s];
+                            if (cnt != 0)
+                                v = pk_value(cnt, prm.balanced ? __ldg(prm.w + r) : 0.0,
+                                             prm.balanced ? __ldg(prm.w + c) : 0.0, prm.balanced);
                             V0[(size_t)k * F + a * S + b] = v;
                             nzf = v != 0.0;
                         }
@@ -219,6 +246,8 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
                         nz1 += __popc(bal & m1);
                     }
                 }
+                // issue the next pair's loads now; they land while this pair is filtered
+                if (j0 + NW * 2 < take) pair_load(start, take, j0 + NW * 2, nxt);
                 __syncwarp();
                 if (ok && (double)(half ? nz1 : nz0) < (double)F * 0.1) ok = false;   // utils.py:225
                 if (ok) {
@@ -305,6 +334,7 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
                     atomicAdd(&prm.batch_win[prm.crank[ci] / PK_BATCH], 1);
                 }
                 __syncwarp();
+                cur = nxt;
             }
             __syncthreads();
             const int nk_now = s_nkept, done_now = s_done;
@@ -316,10 +346,13 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
 
         // ================= phase B: forest =================
         if (nkept > 0) {
-            const bool mine = tid < nkept;
-            const float* xrow = s_fea + (size_t)tid * F;
-            const bool warp_nan = __any_sync(0xffffffffu, mine && s_nan[tid]);
+            const int pix = tid % P, sub = tid / P;        // sub-thread `sub` walks trees [4*sub, 4*sub+4) of a chunk
+            const bool mine = pix < nkept;
+            const float* xrow = s_fea + (size_t)pix * F;
+            const uint32_t xrow_addr = smem_u32(xrow);
+            const bool warp_nan = __any_sync(0xffffffffu, mine && s_nan[pix]);
             double acc = 0.0;
+            int lvpar = 0;
             for (int gi = 0; gi < G; ++gi) {
                 const uint32_t pos = resident ? (uint32_t)gi : consumed;
                 if (!resident || first_batch) mbar_wait(&s_bar[pos & 1], (pos >> 1) & 1);
@@ -327,15 +360,16 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
                 const uint32_t gbase = (uint32_t)grp.z;
                 const bool fits = grp.w > 0;                   // every tree of the group is fully staged
                 const uint32_t staged = (uint32_t)(fits ? grp.w : -grp.w);
-                const uint2* buf = s_nodes + (size_t)(pos & 1) * PK_TREE_BUF_NODES;
+                const uint2* buf = s_nodes + (size_t)(pos & 1) * TBN;
                 const uint32_t buf_addr = smem_u32(buf);
-                const uint32_t xrow_addr = smem_u32(xrow);
                 const int t_end = grp.x + grp.y;
-                if (mine) {
-                    if (fits && !warp_nan) {
-                        for (int t = grp.x; t < t_end; t += 4) {
-                            const bool e1 = t + 1 < t_end, e2 = t + 2 < t_end, e3 = t + 3 < t_end;
-                            // chains past the end of the group re-walk the group's first tree and are dropped
+                for (int tc = grp.x; tc < t_end; tc += CHUNK) {
+                    const int t = tc + 4 * sub;                // this thread's four trees
+                    double lv0 = 0.0, lv1 = 0.0, lv2 = 0.0, lv3 = 0.0;
+                    const bool e0 = t < t_end, e1 = t + 1 < t_end, e2 = t + 2 < t_end, e3 = t + 3 < t_end;
+                    if (mine && e0) {
+                        if (fits && !warp_nan) {
+                            // chains past the end of the group re-walk tree t and are dropped
                             uint32_t a0 = buf_addr + (s_root[t] - gbase) * 8u;
                             uint32_t a1 = buf_addr + (s_root[e1 ? t + 1 : t] - gbase) * 8u;
                             uint32_t a2 = buf_addr + (s_root[e2 ? t + 2 : t] - gbase) * 8u;
@@ -344,34 +378,61 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
                             if (e1) maxd = max(maxd, (int)s_depth[t + 1]);
                             if (e2) maxd = max(maxd, (int)s_depth[t + 2]);
                             if (e3) maxd = max(maxd, (int)s_depth[t + 3]);
-                            uint2 n0 = make_uint2(0, 0), n1 = n0, n2 = n0, n3 = n0;
-                            lds_node_if(a0, true, n0); lds_node_if(a1, true, n1);
-                            lds_node_if(a2, true, n2); lds_node_if(a3, true, n3);
+                            uint2 n0, n1, n2, n3;
+                            lds_node(a0, n0); lds_node(a1, n1); lds_node(a2, n2); lds_node(a3, n3);
                             for (int lvl = 0; lvl < maxd; ++lvl) {
                                 pk_step(xrow_addr, a0, n0);
                                 pk_step(xrow_addr, a1, n1);
                                 pk_step(xrow_addr, a2, n2);
                                 pk_step(xrow_addr, a3, n3);
                             }
-                            acc = __dadd_rn(acc, __hiloint2double((int)n0.y, (int)n0.x));      // estimator order
-                            if (e1) acc = __dadd_rn(acc, __hiloint2double((int)n1.y, (int)n1.x));
-                            if (e2) acc = __dadd_rn(acc, __hiloint2double((int)n2.y, (int)n2.x));
-                            if (e3) acc = __dadd_rn(acc, __hiloint2double((int)n3.y, (int)n3.x));
+                            lv0 = __hiloint2double((int)n0.y, (int)n0.x);
+                            lv1 = __hiloint2double((int)n1.y, (int)n1.x);
+                            lv2 = __hiloint2double((int)n2.y, (int)n2.x);
+                            lv3 = __hiloint2double((int)n3.y, (int)n3.x);
+                        } else {
+                            // general walk: NaN features follow missing_go_to_left; the tail of a tree
+                            // larger than the staging buffer is read from global memory (L2)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (t + k >= t_end) break;
+                                uint32_t p = s_root[t + k] - gbase;
+                                uint2 nd = p < staged ? buf[p] : __ldg(prm.nodes + gbase + p);
+                                while (PK_NODE_INTERNAL(nd.y)) {
+                                    const float xv = xrow[PK_NODE_FEAT(nd.y)];
+                                    const bool left = isnan(xv) ? (PK_NODE_MGL(nd.y) != 0u) : (xv <= __uint_as_float(nd.x));
+                                    p += left ? 1u : PK_NODE_ROFF(nd.y);
+                                    nd = p < staged ? buf[p] : __ldg(prm.nodes + gbase + p);
+                                }
+                                const double lv = __hiloint2double((int)nd.y, (int)nd.x);
+                                if (k == 0) lv0 = lv; else if (k == 1) lv1 = lv; else if (k == 2) lv2 = lv; else lv3 = lv;
+                            }
+                        }
+                    }
+                    // ordered accumulation: trees tc .. tc+CHUNK-1 in estimator order
+                    if (TPP == 1) {
+                        if (mine) {
+                            acc = __dadd_rn(acc, lv0);
+                            if (e1) acc = __dadd_rn(acc, lv1);
+                            if (e2) acc = __dadd_rn(acc, lv2);
+                            if (e3) acc = __dadd_rn(acc, lv3);
                         }
                     } else {
-                        // general walk: NaN features follow missing_go_to_left; the tail of a tree
-                        // larger than the staging buffer is read from global memory (L2)
-                        for (int t = grp.x; t < t_end; ++t) {
-                            uint32_t p = s_root[t] - gbase;
-                            uint2 nd = p < staged ? buf[p] : __ldg(prm.nodes + gbase + p);
-                            while (PK_NODE_INTERNAL(nd.y)) {
-                                const float xv = xrow[PK_NODE_FEAT(nd.y)];
-                                const bool left = isnan(xv) ? (PK_NODE_MGL(nd.y) != 0u) : (xv <= __uint_as_float(nd.x));
-                                p += left ? 1u : PK_NODE_ROFF(nd.y);
-                                nd = p < staged ? buf[p] : __ldg(prm.nodes + gbase + p);
-                            }
-                            acc = __dadd_rn(acc, __hiloint2double((int)nd.y, (int)nd.x));
+                        double* lvb = s_lv + (size_t)lvpar * 4 * P;
+                        if (sub == 1 && mine) { lvb[pix] = lv0; lvb[P + pix] = lv1; lvb[2 * P + pix] = lv2; lvb[3 * P + pix] = lv3; }
+                        __syncthreads();
+                        if (sub == 0 && mine) {
+                            acc = __dadd_rn(acc, lv0);
+                            if (e1) acc = __dadd_rn(acc, lv1);
+                            if (e2) acc = __dadd_rn(acc, lv2);
+                            if (e3) acc = __dadd_rn(acc, lv3);
+                            const int t4 = tc + 4;
+                            if (t4 < t_end) acc = __dadd_rn(acc, lvb[pix]);
+                            if (t4 + 1 < t_end) acc = __dadd_rn(acc, lvb[P + pix]);
+                            if (t4 + 2 < t_end) acc = __dadd_rn(acc, lvb[2 * P + pix]);
+                            if (t4 + 3 < t_end) acc = __dadd_rn(acc, lvb[3 * P + pix]);
                         }
+                        lvpar ^= 1;
                     }
                 }
                 if (!resident) {
@@ -380,7 +441,7 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
                     issue(issued); ++issued;         // refill it with the group two positions ahead
                 }
             }
-            if (mine) prm.prob[s_idx[tid]] = __ddiv_rn(acc, (double)prm.n_trees);
+            if (mine && sub == 0) prm.prob[s_idx[pix]] = __ddiv_rn(acc, (double)prm.n_trees);
             if (tid == 0) atomicAdd(&prm.counters[1], (unsigned long long)nkept);
             first_batch = false;
         }
@@ -395,39 +456,40 @@ __global__ void __launch_bounds__(P, (P <= 128 ? 2 : 1)) k_score_fused(const Fus
     }
 }
 
-template <int W, int P>
-static int launch_fused_t(const FusedParams& prm, int ND, int sm_count, cudaStream_t stream) {
-    const size_t smem = FusedSmem<W, P>::total(ND, prm.n_trees);
-    if (smem > 227 * 1024 - 256) { pk_set_error("fused kernel: %zu bytes of shared memory needed", smem); return PK_EUNSUPPORTED; }
+template <int W, int P, int TPP, int TBN>
+static int launch_fused_t(FusedParams prm, pk_forest* f, int ND, int sm_count, cudaStream_t stream) {
+    using Cfg = FusedCfg<W, P, TPP, TBN>;
+    PK_CHECK(pk_forest_groups(f, TBN, Cfg::CHUNK, &prm.groups, &prm.n_groups));
+    const size_t smem = Cfg::total(ND, prm.n_trees);
+    if (smem > 227 * 1024 - 64) { pk_set_error("fused kernel: %zu bytes of shared memory needed", smem); return PK_EUNSUPPORTED; }
     static size_t attr_set = 0;      // largest dynamic size opted into so far
     if (smem > attr_set) {
-        PK_CUDA(cudaFuncSetAttribute(k_score_fused<W, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PK_CUDA(cudaFuncSetAttribute(k_score_fused<W, P, TPP, TBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(P <= 128 ? 2 : 1, (227 * 1024) / (smem + 1024)));
     long long want = (prm.n_cand + P - 1) / P;
-    unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)sm_count * per_sm));
-    k_score_fused<W, P><<<grid, P, smem, stream>>>(prm);
+    unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)sm_count));
+    k_score_fused<W, P, TPP, TBN><<<grid, P * TPP, smem, stream>>>(prm);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
 
-int pk_launch_fused(pk_chrom* c, const pk_forest* f, int variant) {
+int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant) {
     if (c->n_cand == 0) return PK_OK;
     FusedParams prm;
     prm.band = c->d_band; prm.w = c->d_w; prm.expv = c->d_exp;
     prm.n = c->n; prm.pitch = c->pitch; prm.balanced = c->balanced; prm.ND = c->ND;
     prm.cx = c->d_cx; prm.cd = c->d_cd; prm.crank = c->d_crank; prm.n_cand = c->n_cand;
-    prm.nodes = f->d_nodes; prm.roots = f->d_root; prm.depth = f->d_depth; prm.groups = f->d_groups;
-    prm.n_groups = f->n_groups; prm.n_trees = f->n_trees;
+    prm.nodes = f->d_nodes; prm.roots = f->d_root; prm.depth = f->d_depth; prm.groups = nullptr;
+    prm.n_groups = 0; prm.n_trees = f->n_trees;
     prm.keep = c->d_keep; prm.prob = c->d_prob; prm.batch_win = c->d_batch_win; prm.counters = c->d_counters;
     prm.next = c->d_counters + 2;
     int sm = 148;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, c->device);
-    if (c->w == 5) return variant == 1 ? launch_fused_t<5, 256>(prm, c->ND, sm, c->stream)
-                                       : launch_fused_t<5, 128>(prm, c->ND, sm, c->stream);
-    if (c->w == 7) return variant == 1 ? launch_fused_t<7, 128>(prm, c->ND, sm, c->stream)
-                                       : launch_fused_t<7, 64>(prm, c->ND, sm, c->stream);
+    if (c->w == 5) return variant == 1 ? launch_fused_t<5, 256, 1, 4224>(prm, f, c->ND, sm, c->stream)
+                                       : launch_fused_t<5, 256, 2, 4224>(prm, f, c->ND, sm, c->stream);
+    if (c->w == 7) return variant == 1 ? launch_fused_t<7, 128, 1, 4224>(prm, f, c->ND, sm, c->stream)
+                                       : launch_fused_t<7, 128, 2, 4224>(prm, f, c->ND, sm, c->stream);
     return PK_EUNSUPPORTED;
 }
 
