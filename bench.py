@@ -41,7 +41,7 @@ WORKLOADS = {
     "c1": dict(n=2000, res=10000, lower=6, upper=300, w=5, forest="c2", depth=300.0, band=330,
                desc="score_chromosome 2,000-bin synthetic 10 kb (w=5, l=6, u=300, 100-tree RF)"),
 }
-KERNELS_PER_STEP = 8   # scatter, diag_sums, cand count, scan, cand write, features, forest, emit
+KERNELS_PER_STEP = 10  # check_sorted, rowptr, band_csr, diag_sums, fit_expected, cand_mark, scan2, cand_write, score_fused, emit
 
 
 def band_pixels(n, lower, upper, w):
@@ -226,7 +226,7 @@ def main():
     def device_step():
         _lib.check(L.pk_chrom_upload_pixels(h, C.c_void_p(d_b1.data_ptr()), C.c_void_p(d_b2.data_ptr()),
                                             C.c_void_p(d_cnt.data_ptr()), nnz, C.c_void_p(d_w.data_ptr()),
-                                            _lib.PK_MEM_DEVICE))
+                                            _lib.PK_MEM_DEVICE | _lib.PK_PIXELS_SORTED))
         _lib.check(L.pk_chrom_fit_expected(h))
         _lib.check(L.pk_chrom_find_candidates(h, 0, n, None))
         _lib.check(L.pk_chrom_score(h, forest.handle, 0.5))
@@ -265,7 +265,8 @@ def main():
     # ---- end to end through the public API with host buffers ----
     def e2e_step():
         X = Chromosome.from_pixels(ch.bin1, ch.bin2, ch.count, ch.weights, n, forest, lower=wl["lower"],
-                                   upper=wl["upper"], cname="chr1", res=wl["res"], width=w, device=local)
+                                   upper=wl["upper"], cname="chr1", res=wl["res"], width=w, device=local,
+                                   sorted_pixels=True)
         out = X.score_records(0.5)
         X.close()
         return out

@@ -39,6 +39,9 @@ extern "C" {
 
 #define PK_MEM_HOST   0
 #define PK_MEM_DEVICE 1
+/* OR-ed into `mem` of pk_chrom_upload_pixels: the pixels are in cooler order (sorted by
+ * bin1, then bin2, bin1 <= bin2). Enables the tiled band build; verified on the device. */
+#define PK_PIXELS_SORTED 0x100
 
 typedef struct pk_forest pk_forest;
 typedef struct pk_chrom pk_chrom;
@@ -88,6 +91,10 @@ int pk_chrom_bounds(const pk_chrom* c, int32_t* lower_eff, int32_t* upper_eff, i
  * cooler fetches + tocsr + band trim (score_chromosome.py:42-44, scoreUtils.py:30-33). */
 int pk_chrom_upload_pixels(pk_chrom* c, const int32_t* bin1, const int32_t* bin2,
                            const int32_t* count, int64_t nnz, const double* weights, int mem);
+/* Same from cooler's own CSR layout: bin1_offset[n_bins+1] (indexes/bin1_offset restricted
+ * to the chromosome, rebased to 0) plus the bin2 / count columns of those pixels. */
+int pk_chrom_upload_csr(pk_chrom* c, const int64_t* bin1_offset, const int32_t* bin2, const int32_t* count,
+                        int64_t nnz, const double* weights, int mem);
 /* per-diagonal (sum, n_valid) for d = 0..upper+2w, to HOST arrays of exp_len */
 int pk_chrom_diag_sums(pk_chrom* c, double* out_sum, int64_t* out_cnt);
 /* expected curve fitted by the library itself: mean where n_valid > 10, then the
@@ -138,6 +145,9 @@ int pk_poisson_critical_mu(int32_t k_max, double* out /* [k_max+1] */);
 /* the expected-curve fit alone on HOST arrays (test hook for the restated
  * IsotonicRegression(increasing=False, out_of_bounds='clip') of utils.py:173-176) */
 int pk_fit_expected(const double* sum, const int64_t* cnt, int32_t len, double* out_exp);
+
+/* return the library's cached device blocks (of destroyed handles) to the driver */
+int pk_release_memory(void);
 
 /* process-wide tuning knob, for benchmarking: key "fused" = -1 auto (default),
  * 0 separate feature + forest kernels, 1 / 2 the two fused-kernel tile sizes */

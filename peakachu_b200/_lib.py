@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpeakachu_b200.so")
 
 PK_MEM_HOST, PK_MEM_DEVICE = 0, 1
+PK_PIXELS_SORTED = 0x100
 
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
@@ -36,6 +37,8 @@ SIGNATURES = {
     "pk_chrom_destroy": (C.c_int, [C.c_void_p]),
     "pk_chrom_bounds": (C.c_int, [C.c_void_p, c_i32p, c_i32p, c_i32p]),
     "pk_chrom_upload_pixels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    "pk_chrom_upload_csr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    "pk_release_memory": (C.c_int, []),
     "pk_chrom_diag_sums": (C.c_int, [C.c_void_p, c_f64p, c_i64p]),
     "pk_chrom_fit_expected": (C.c_int, [C.c_void_p]),
     "pk_chrom_set_expected": (C.c_int, [C.c_void_p, c_f64p, c_f64p]),

@@ -13,11 +13,14 @@
 
 #include "pk_common.cuh"
 
-// launchers implemented in pk_kernels.cu
+// launchers implemented in pk_kernels.cu / pk_stages.cu / pk_fused.cu
 int pk_launch_scatter(pk_chrom* c, const int32_t* b1, const int32_t* b2, const int32_t* cnt, int64_t nnz);
+int pk_launch_band_csr(pk_chrom* c, const long long* rowptr, const int32_t* b2, const int32_t* cnt);
+int pk_launch_rowptr(pk_chrom* c, const int32_t* b1, const int32_t* b2, int64_t nnz, long long* rowptr);
 int pk_launch_diag_sums(pk_chrom* c);
-int pk_launch_candidates(pk_chrom* c, const double* d_crit, int kmax, bool write);
-int pk_launch_scan2(pk_chrom* c, long long m);
+bool pk_fit_on_device_supported(int len);
+int pk_launch_fit_expected(pk_chrom* c);
+int pk_launch_candidates(pk_chrom* c, const double* d_crit, int kmax);
 int pk_launch_features(pk_chrom* c, double* d_fea64);
 int pk_launch_forest(const pk_forest* f, const float* X, const uint8_t* keep, int64_t n_rows, int32_t* leaves,
                      double* proba, cudaStream_t stream);
@@ -60,21 +63,76 @@ extern "C" int pk_device_count(int* out) {
     return PK_OK;
 }
 
-template <typename T>
-static int dev_alloc(T** p, size_t count) {
-    *p = nullptr;
-    if (count == 0) count = 1;
-    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+// ---------------------------------------------------------------------------
+// device memory: a small caching allocator. Handles are created and destroyed per
+// chromosome (as the reference builds one Chromosome object per chromosome), so
+// cudaMalloc/cudaFree -- both synchronising -- must not sit on that path. Freed
+// blocks are kept per device and reused for requests of up to twice their size.
+// ---------------------------------------------------------------------------
+namespace {
+struct Block { void* p; size_t bytes; };
+std::mutex g_pool_mu;
+std::map<int, std::vector<Block>> g_pool_free;         // device -> cached blocks
+std::map<void*, std::pair<int, size_t>> g_pool_live;   // pointer -> (device, bytes)
+}  // namespace
+
+static int pool_alloc(void** out, size_t bytes) {
+    *out = nullptr;
+    if (bytes == 0) bytes = 256;
+    bytes = (bytes + 255) & ~(size_t)255;
+    int dev = 0;
+    PK_CUDA(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        auto& fl = g_pool_free[dev];
+        int best = -1;
+        for (int i = 0; i < (int)fl.size(); ++i)
+            if (fl[i].bytes >= bytes && fl[i].bytes <= 2 * bytes + 4096 && (best < 0 || fl[i].bytes < fl[best].bytes)) best = i;
+        if (best >= 0) {
+            *out = fl[best].p;
+            g_pool_live[*out] = {dev, fl[best].bytes};
+            fl.erase(fl.begin() + best);
+            return PK_OK;
+        }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
     if (e != cudaSuccess) {
-        pk_set_error("cudaMalloc(%zu bytes) -> %s", count * sizeof(T), cudaGetErrorString(e));
+        pk_set_error("cudaMalloc(%zu bytes) -> %s", bytes, cudaGetErrorString(e));
         return e == cudaErrorMemoryAllocation ? PK_ENOMEM : PK_ECUDA;
+    }
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool_live[*out] = {dev, bytes};
+    return PK_OK;
+}
+
+static void pool_free(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_pool_live.find(p);
+    if (it == g_pool_live.end()) { cudaFree(p); return; }
+    g_pool_free[it->second.first].push_back({p, it->second.second});
+    g_pool_live.erase(it);
+}
+
+extern "C" int pk_release_memory(void) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (auto& kv : g_pool_free) {
+        cudaSetDevice(kv.first);
+        cudaDeviceSynchronize();
+        for (auto& b : kv.second) cudaFree(b.p);
+        kv.second.clear();
     }
     return PK_OK;
 }
 
 template <typename T>
+static int dev_alloc(T** p, size_t count) {
+    return pool_alloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+}
+
+template <typename T>
 static void dev_free(T*& p) {
-    if (p) cudaFree(p);
+    pool_free((void*)p);
     p = nullptr;
 }
 
@@ -97,8 +155,7 @@ int pk_poisson_table_device(int device, int32_t k_min_size, const double** d_out
         PK_CHECK(pk_poisson_table_host(want, &host));
         PK_CUDA(cudaSetDevice(device));
         PK_CUDA(cudaDeviceSynchronize());      // nobody may still read the old copy
-        if (t.d) cudaFree(t.d);
-        t.d = nullptr;
+        dev_free(t.d);
         PK_CHECK(dev_alloc(&t.d, (size_t)want + 1));
         PK_CUDA(cudaMemcpy(t.d, host, ((size_t)want + 1) * sizeof(double), cudaMemcpyHostToDevice));
         t.kmax = want;
@@ -259,6 +316,12 @@ extern "C" int pk_forest_apply(pk_forest* f, const float* X, int64_t n_rows, int
 // ---------------------------------------------------------------------------
 // chromosome
 // ---------------------------------------------------------------------------
+static int64_t band_pixels_of(const pk_chrom* c) {
+    int64_t k = (int64_t)c->upper - c->lower + 1;
+    if (k <= 0) return 0;
+    return k * c->n - ((int64_t)c->lower + c->upper) * k / 2;
+}
+
 extern "C" int pk_chrom_create(int device, int32_t n_bins, int32_t width, int32_t lower, int32_t upper, int balanced,
                                void* stream, pk_chrom** out) {
     if (!out) { pk_set_error("pk_chrom_create: out is NULL"); return PK_EINVAL; }
@@ -288,7 +351,8 @@ extern "C" int pk_chrom_create(int device, int32_t n_bins, int32_t width, int32_
         (r = dev_alloc(&c->d_leaf_start, (size_t)c->ND * c->LP)) || (r = dev_alloc(&c->d_leaf_sum, (size_t)c->ND * c->LP)) ||
         (r = dev_alloc(&c->d_diag_sum, (size_t)c->ND)) || (r = dev_alloc(&c->d_diag_cnt, (size_t)c->ND)) ||
         (r = dev_alloc(&c->d_exp, (size_t)c->ND)) || (r = dev_alloc(&c->d_bg, (size_t)c->ND)) ||
-        (r = dev_alloc(&c->d_flags, 4)) || (r = dev_alloc(&c->d_counters, 4))) {
+        (r = dev_alloc(&c->d_flags, 4)) || (r = dev_alloc(&c->d_counters, 4)) || (r = dev_alloc(&c->d_ncand, 2)) ||
+        (r = dev_alloc(&c->d_rowptr, (size_t)n_bins + 1))) {
         pk_chrom_destroy(c);
         return r;
     }
@@ -305,9 +369,10 @@ extern "C" int pk_chrom_destroy(pk_chrom* c) {
     if (c->stream) cudaStreamSynchronize(c->stream); else cudaDeviceSynchronize();
     dev_free(c->d_band); dev_free(c->d_w); dev_free(c->d_valid); dev_free(c->d_scratch);
     dev_free(c->d_leaf_start); dev_free(c->d_leaf_sum); dev_free(c->d_diag_sum); dev_free(c->d_diag_cnt);
-    dev_free(c->d_exp); dev_free(c->d_bg); dev_free(c->d_flags); dev_free(c->d_counters);
+    dev_free(c->d_exp); dev_free(c->d_bg); dev_free(c->d_flags); dev_free(c->d_counters); dev_free(c->d_ncand);
+    dev_free(c->d_rowptr);
     dev_free(c->d_b1); dev_free(c->d_b2); dev_free(c->d_cnt);
-    dev_free(c->d_cnt_all); dev_free(c->d_cnt_tile); dev_free(c->d_off_all); dev_free(c->d_off_tile);
+    dev_free(c->d_cnt_all); dev_free(c->d_cnt_tile); dev_free(c->d_off_all); dev_free(c->d_off_tile); dev_free(c->d_bits);
     dev_free(c->d_cx); dev_free(c->d_cd); dev_free(c->d_crank);
     dev_free(c->d_keep); dev_free(c->d_fea32); dev_free(c->d_prob); dev_free(c->d_batch_win);
     dev_free(c->d_rx); dev_free(c->d_ry); dev_free(c->d_rb); dev_free(c->d_rp); dev_free(c->d_rv);
@@ -330,39 +395,91 @@ static float ev_ms(pk_chrom* c, int a, int b) {
     return ms;
 }
 
-extern "C" int pk_chrom_upload_pixels(pk_chrom* c, const int32_t* bin1, const int32_t* bin2, const int32_t* count,
-                                      int64_t nnz, const double* weights, int mem) {
-    if (!c || nnz < 0 || (nnz > 0 && (!bin1 || !bin2 || !count))) { pk_set_error("pk_chrom_upload_pixels: bad argument"); return PK_EINVAL; }
-    if (c->balanced && !weights) { pk_set_error("pk_chrom_upload_pixels: balanced mode needs weights"); return PK_EINVAL; }
-    PK_CUDA(cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
-    const int32_t *p1 = bin1, *p2 = bin2, *pc = count;
-    if (mem == PK_MEM_HOST) {
-        int64_t cap = c->pix_cap;
-        if (nnz > cap || !c->d_b1) {
-            dev_free(c->d_b1); dev_free(c->d_b2); dev_free(c->d_cnt);
-            cap = std::max<int64_t>(nnz, 1024);
-            PK_CHECK(dev_alloc(&c->d_b1, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_b2, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_cnt, (size_t)cap));
-            c->pix_cap = cap;
-        }
-        PK_CUDA(cudaMemcpyAsync(c->d_b1, bin1, (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
-        PK_CUDA(cudaMemcpyAsync(c->d_b2, bin2, (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
-        PK_CUDA(cudaMemcpyAsync(c->d_cnt, count, (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
-        p1 = c->d_b1; p2 = c->d_b2; pc = c->d_cnt;
+static int stage_pixels(pk_chrom* c, const int32_t** p, int32_t** d_stage, int64_t nnz, int mem) {
+    // host column -> staging buffer on the device (grow-only)
+    if (mem != PK_MEM_HOST || nnz == 0) return PK_OK;
+    PK_CUDA(cudaMemcpyAsync(*d_stage, *p, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
+    *p = *d_stage;
+    return PK_OK;
+}
+
+static int reserve_staging(pk_chrom* c, int64_t nnz, bool need_b1) {
+    if (nnz > c->pix_cap || !c->d_b2 || (need_b1 && !c->d_b1)) {
+        dev_free(c->d_b1); dev_free(c->d_b2); dev_free(c->d_cnt);
+        int64_t cap = std::max<int64_t>(nnz, 1024);
+        PK_CHECK(dev_alloc(&c->d_b1, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_b2, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_cnt, (size_t)cap));
+        c->pix_cap = cap;
     }
-    if (c->balanced)
-        PK_CUDA(cudaMemcpyAsync(c->d_w, weights, (size_t)c->n * sizeof(double),
-                                mem == PK_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
-    PK_CUDA(cudaEventRecord(c->ev[0], s));
-    PK_CUDA(cudaMemsetAsync(c->d_band, 0, (size_t)c->ND * c->pitch * sizeof(int32_t), s));
-    PK_CUDA(cudaMemsetAsync(c->d_valid, 0, (size_t)c->n, s));
-    PK_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int32_t), s));
-    PK_CHECK(pk_launch_scatter(c, p1, p2, pc, nnz));
+    return PK_OK;
+}
+
+static int after_band(pk_chrom* c) {
+    cudaStream_t s = c->stream;
     PK_CUDA(cudaEventRecord(c->ev[1], s));
     PK_CHECK(pk_launch_diag_sums(c));
     PK_CUDA(cudaEventRecord(c->ev[2], s));
     c->has_pixels = true; c->has_expected = false; c->has_candidates = false; c->has_scores = false;
     return PK_OK;
+}
+
+extern "C" int pk_chrom_upload_pixels(pk_chrom* c, const int32_t* bin1, const int32_t* bin2, const int32_t* count,
+                                      int64_t nnz, const double* weights, int mem) {
+    if (!c || nnz < 0 || (nnz > 0 && (!bin1 || !bin2 || !count))) { pk_set_error("pk_chrom_upload_pixels: bad argument"); return PK_EINVAL; }
+    if (c->balanced && !weights) { pk_set_error("pk_chrom_upload_pixels: balanced mode needs weights"); return PK_EINVAL; }
+    const bool sorted = (mem & PK_PIXELS_SORTED) != 0;
+    mem &= ~PK_PIXELS_SORTED;
+    PK_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int32_t *p1 = bin1, *p2 = bin2, *pc = count;
+    if (mem == PK_MEM_HOST) {
+        PK_CHECK(reserve_staging(c, nnz, true));
+        PK_CHECK(stage_pixels(c, &p1, &c->d_b1, nnz, mem));
+        PK_CHECK(stage_pixels(c, &p2, &c->d_b2, nnz, mem));
+        PK_CHECK(stage_pixels(c, &pc, &c->d_cnt, nnz, mem));
+    }
+    if (c->balanced)
+        PK_CUDA(cudaMemcpyAsync(c->d_w, weights, (size_t)c->n * sizeof(double),
+                                mem == PK_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    PK_CUDA(cudaEventRecord(c->ev[0], s));
+    PK_CUDA(cudaMemsetAsync(c->d_valid, 0, (size_t)c->n, s));
+    PK_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int32_t), s));
+    c->declared_sorted = sorted;
+    if (sorted) {
+        // cooler order: derive row offsets on the device, then the tiled CSR build
+        PK_CHECK(pk_launch_rowptr(c, p1, p2, nnz, c->d_rowptr));
+        PK_CHECK(pk_launch_band_csr(c, c->d_rowptr, p2, pc));
+    } else {
+        PK_CUDA(cudaMemsetAsync(c->d_band, 0, (size_t)c->ND * c->pitch * sizeof(int32_t), s));
+        PK_CHECK(pk_launch_scatter(c, p1, p2, pc, nnz));
+    }
+    return after_band(c);
+}
+
+extern "C" int pk_chrom_upload_csr(pk_chrom* c, const int64_t* bin1_offset, const int32_t* bin2, const int32_t* count,
+                                   int64_t nnz, const double* weights, int mem) {
+    if (!c || nnz < 0 || !bin1_offset || (nnz > 0 && (!bin2 || !count))) { pk_set_error("pk_chrom_upload_csr: bad argument"); return PK_EINVAL; }
+    if (c->balanced && !weights) { pk_set_error("pk_chrom_upload_csr: balanced mode needs weights"); return PK_EINVAL; }
+    mem &= ~PK_PIXELS_SORTED;
+    PK_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int32_t *p2 = bin2, *pc = count;
+    const long long* rp = reinterpret_cast<const long long*>(bin1_offset);
+    if (mem == PK_MEM_HOST) {
+        PK_CHECK(reserve_staging(c, nnz, false));
+        PK_CHECK(stage_pixels(c, &p2, &c->d_b2, nnz, mem));
+        PK_CHECK(stage_pixels(c, &pc, &c->d_cnt, nnz, mem));
+        PK_CUDA(cudaMemcpyAsync(c->d_rowptr, bin1_offset, ((size_t)c->n + 1) * 8, cudaMemcpyHostToDevice, s));
+        rp = c->d_rowptr;
+    }
+    if (c->balanced)
+        PK_CUDA(cudaMemcpyAsync(c->d_w, weights, (size_t)c->n * sizeof(double),
+                                mem == PK_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    PK_CUDA(cudaEventRecord(c->ev[0], s));
+    PK_CUDA(cudaMemsetAsync(c->d_valid, 0, (size_t)c->n, s));
+    PK_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int32_t), s));
+    c->declared_sorted = false;      // row offsets given: nothing to verify
+    PK_CHECK(pk_launch_band_csr(c, rp, p2, pc));
+    return after_band(c);
 }
 
 extern "C" int pk_chrom_diag_sums(pk_chrom* c, double* out_sum, int64_t* out_cnt) {
@@ -388,19 +505,38 @@ extern "C" int pk_chrom_set_expected(pk_chrom* c, const double* exp_arr, const d
 extern "C" int pk_chrom_fit_expected(pk_chrom* c) {
     if (!c) { pk_set_error("pk_chrom_fit_expected: NULL handle"); return PK_EINVAL; }
     if (!c->has_pixels) { pk_set_error("pk_chrom_fit_expected: no pixels uploaded"); return PK_ESTATE; }
-    std::vector<double> sum((size_t)c->ND), e((size_t)c->ND);
-    std::vector<long long> cnt((size_t)c->ND);
     PK_CUDA(cudaSetDevice(c->device));
     PK_CUDA(cudaEventRecord(c->ev[3], c->stream));
-    PK_CUDA(cudaMemcpyAsync(sum.data(), c->d_diag_sum, (size_t)c->ND * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    PK_CUDA(cudaMemcpyAsync(cnt.data(), c->d_diag_cnt, (size_t)c->ND * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-    PK_CUDA(cudaStreamSynchronize(c->stream));
-    PK_CHECK(pk_fit_expected_host(sum.data(), cnt.data(), c->ND, e.data()));
-    PK_CUDA(cudaMemcpyAsync(c->d_exp, e.data(), (size_t)c->ND * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    PK_CUDA(cudaMemcpyAsync(c->d_bg, e.data(), (size_t)c->ND * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (pk_fit_on_device_supported(c->ND)) {
+        PK_CHECK(pk_launch_fit_expected(c));      // stays on the stream; a failed fit raises flags[2]
+    } else {
+        std::vector<double> sum((size_t)c->ND), e((size_t)c->ND);
+        std::vector<long long> cnt((size_t)c->ND);
+        PK_CUDA(cudaMemcpyAsync(sum.data(), c->d_diag_sum, (size_t)c->ND * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        PK_CUDA(cudaMemcpyAsync(cnt.data(), c->d_diag_cnt, (size_t)c->ND * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        PK_CUDA(cudaStreamSynchronize(c->stream));
+        PK_CHECK(pk_fit_expected_host(sum.data(), cnt.data(), c->ND, e.data()));
+        PK_CUDA(cudaMemcpyAsync(c->d_exp, e.data(), (size_t)c->ND * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        PK_CUDA(cudaMemcpyAsync(c->d_bg, e.data(), (size_t)c->ND * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        PK_CUDA(cudaStreamSynchronize(c->stream));
+    }
     PK_CUDA(cudaEventRecord(c->ev[4], c->stream));
-    PK_CUDA(cudaStreamSynchronize(c->stream));
     c->has_expected = true; c->has_candidates = false; c->has_scores = false;
+    return PK_OK;
+}
+
+// device flags -> host; turns raised flags into errors where nothing can be retried
+static int read_flags(pk_chrom* c, int32_t flags[4]) {
+    PK_CUDA(cudaMemcpyAsync(flags, c->d_flags, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    PK_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->declared_sorted && (flags[3] & 1)) {
+        pk_set_error("pixels were passed with PK_PIXELS_SORTED but are not sorted by (bin1, bin2) with bin1 <= bin2");
+        return PK_EINVAL;
+    }
+    if (flags[2]) {
+        pk_set_error("expected curve: no distance has a positive mean (reference raises in IsotonicRegression.fit)");
+        return PK_EINVAL;
+    }
     return PK_OK;
 }
 
@@ -408,9 +544,75 @@ extern "C" int pk_chrom_get_expected(pk_chrom* c, double* out_exp) {
     if (!c || !out_exp) { pk_set_error("pk_chrom_get_expected: bad argument"); return PK_EINVAL; }
     if (!c->has_expected) { pk_set_error("pk_chrom_get_expected: expected curve not set"); return PK_ESTATE; }
     PK_CUDA(cudaSetDevice(c->device));
+    int32_t flags[4];
+    PK_CHECK(read_flags(c, flags));
     PK_CUDA(cudaMemcpyAsync(out_exp, c->d_exp, (size_t)c->ND * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     PK_CUDA(cudaStreamSynchronize(c->stream));
     return PK_OK;
+}
+
+static int reserve_candidates(pk_chrom* c, int64_t want) {
+    if (want > c->cand_cap || !c->d_cx) {
+        dev_free(c->d_cx); dev_free(c->d_cd); dev_free(c->d_crank);
+        dev_free(c->d_keep); dev_free(c->d_prob);
+        dev_free(c->d_rx); dev_free(c->d_ry); dev_free(c->d_rb); dev_free(c->d_rp); dev_free(c->d_rv);
+        const int64_t cap = std::max<int64_t>(want, 4096);
+        PK_CHECK(dev_alloc(&c->d_cx, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_cd, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_crank, (size_t)cap));
+        PK_CHECK(dev_alloc(&c->d_keep, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_prob, (size_t)cap));
+        PK_CHECK(dev_alloc(&c->d_rx, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_ry, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_rb, (size_t)cap));
+        PK_CHECK(dev_alloc(&c->d_rp, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_rv, (size_t)cap));
+        c->cand_cap = cap;
+    }
+    return PK_OK;
+}
+
+// candidate scan on the stream; kmin = smallest Poisson table size wanted
+static int run_candidates(pk_chrom* c, int32_t kmin) {
+    cudaStream_t s = c->stream;
+    const int nd = c->upper - c->lower + 1;
+    PK_CUDA(cudaEventRecord(c->ev[5], s));
+    PK_CUDA(cudaMemsetAsync(c->d_ncand, 0, 2 * sizeof(long long), s));
+    if (nd > 0) {
+        c->n_chunks = (c->n + 1023) / 1024;
+        const int64_t m = (int64_t)nd * c->n_chunks;
+        if (m + 1 > c->cnt_cap) {
+            dev_free(c->d_cnt_all); dev_free(c->d_cnt_tile); dev_free(c->d_off_all); dev_free(c->d_off_tile); dev_free(c->d_bits);
+            PK_CHECK(dev_alloc(&c->d_cnt_all, (size_t)m + 1)); PK_CHECK(dev_alloc(&c->d_cnt_tile, (size_t)m + 1));
+            PK_CHECK(dev_alloc(&c->d_off_all, (size_t)m + 1)); PK_CHECK(dev_alloc(&c->d_off_tile, (size_t)m + 1));
+            PK_CHECK(dev_alloc(&c->d_bits, (size_t)m * 32));
+            c->cnt_cap = m + 1;
+        }
+        const double* d_crit = nullptr;
+        int32_t kmax = 0;
+        PK_CHECK(pk_poisson_table_device(c->device, kmin, &d_crit, &kmax));
+        PK_CHECK(pk_launch_candidates(c, d_crit, kmax));
+    }
+    PK_CUDA(cudaEventRecord(c->ev[6], s));
+    return PK_OK;
+}
+
+// read the candidate totals; if a device-side capacity was exceeded, enlarge and redo the scan
+static int settle_candidates(pk_chrom* c) {
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        int32_t flags[4];
+        long long nc[2] = {0, 0};
+        PK_CUDA(cudaMemcpyAsync(nc, c->d_ncand, sizeof nc, cudaMemcpyDeviceToHost, c->stream));
+        PK_CHECK(read_flags(c, flags));
+        c->n_cand = nc[0]; c->n_cand_all = nc[1];
+        const bool table_small = flags[0] != 0, cand_small = (flags[3] & 2) != 0 || c->n_cand > c->cand_cap;
+        if (!table_small && !cand_small) { c->n_cand_known = true; return PK_OK; }
+        if (table_small && flags[1] > (1 << 22)) {
+            pk_set_error("raw count %d above the Poisson table limit (2^22)", flags[1]);
+            return PK_EUNSUPPORTED;
+        }
+        if (cand_small) PK_CHECK(reserve_candidates(c, c->n_cand + c->n_cand / 8 + 1024));
+        const int32_t keep1 = flags[1];
+        PK_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int32_t), c->stream));
+        PK_CUDA(cudaMemcpyAsync(c->d_flags + 1, &keep1, sizeof keep1, cudaMemcpyHostToDevice, c->stream));
+        PK_CHECK(run_candidates(c, table_small ? flags[1] : 0));
+    }
+    pk_set_error("candidate scan did not settle");
+    return PK_ECUDA;
 }
 
 extern "C" int pk_chrom_find_candidates(pk_chrom* c, int32_t row_begin, int32_t row_end, int64_t* n_candidates) {
@@ -418,67 +620,39 @@ extern "C" int pk_chrom_find_candidates(pk_chrom* c, int32_t row_begin, int32_t 
     if (!c->has_expected) { pk_set_error("pk_chrom_find_candidates: expected curve not set"); return PK_ESTATE; }
     if (row_begin < 0 || row_end > c->n || row_begin > row_end) { pk_set_error("pk_chrom_find_candidates: bad row range [%d, %d)", row_begin, row_end); return PK_EINVAL; }
     PK_CUDA(cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
     c->row_begin = row_begin; c->row_end = row_end;
     c->whole = (row_begin == 0 && row_end == c->n);
-    c->n_cand = c->n_cand_all = 0;
-    const int nd = c->upper - c->lower + 1;
-    PK_CUDA(cudaEventRecord(c->ev[5], s));
-    if (nd > 0) {
-        c->n_chunks = (c->n + 1023) / 1024;
-        const int64_t m = (int64_t)nd * c->n_chunks;
-        if (m + 1 > c->cnt_cap) {
-            dev_free(c->d_cnt_all); dev_free(c->d_cnt_tile); dev_free(c->d_off_all); dev_free(c->d_off_tile);
-            PK_CHECK(dev_alloc(&c->d_cnt_all, (size_t)m + 1)); PK_CHECK(dev_alloc(&c->d_cnt_tile, (size_t)m + 1));
-            PK_CHECK(dev_alloc(&c->d_off_all, (size_t)m + 1)); PK_CHECK(dev_alloc(&c->d_off_tile, (size_t)m + 1));
-            c->cnt_cap = m + 1;
-        }
-        const double* d_crit = nullptr;
-        int32_t kmax = 0;
-        int32_t flags[4] = {0, 0, 0, 0};
-        PK_CUDA(cudaMemcpyAsync(flags, c->d_flags, sizeof flags, cudaMemcpyDeviceToHost, s));
-        PK_CUDA(cudaStreamSynchronize(s));
-        // table covers the largest count in the band (flags[1]); counts above 2^22 are refused
-        PK_CHECK(pk_poisson_table_device(c->device, std::min(flags[1], 1 << 22), &d_crit, &kmax));
-        PK_CHECK(pk_launch_candidates(c, d_crit, kmax, false));
-        PK_CHECK(pk_launch_scan2(c, m));
-        uint32_t tot_all = 0, tot_tile = 0;
-        PK_CUDA(cudaMemcpyAsync(&tot_all, c->d_off_all + m, 4, cudaMemcpyDeviceToHost, s));
-        PK_CUDA(cudaMemcpyAsync(&tot_tile, c->d_off_tile + m, 4, cudaMemcpyDeviceToHost, s));
-        PK_CUDA(cudaMemcpyAsync(flags, c->d_flags, sizeof flags, cudaMemcpyDeviceToHost, s));
-        PK_CUDA(cudaStreamSynchronize(s));
-        if (flags[0]) {
-            pk_set_error("pk_chrom_find_candidates: raw count above the Poisson table limit (2^22)");
-            return PK_EUNSUPPORTED;
-        }
-        c->n_cand_all = tot_all; c->n_cand = tot_tile;
-        if (c->n_cand > c->cand_cap || !c->d_cx) {
-            dev_free(c->d_cx); dev_free(c->d_cd); dev_free(c->d_crank);
-            int64_t cap = std::max<int64_t>(c->n_cand + c->n_cand / 8, 1024);
-            PK_CHECK(dev_alloc(&c->d_cx, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_cd, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_crank, (size_t)cap));
-            c->cand_cap = cap;
-        }
-        PK_CHECK(pk_launch_candidates(c, d_crit, kmax, true));
-    }
-    PK_CUDA(cudaEventRecord(c->ev[6], s));
-    if (n_candidates) *n_candidates = c->n_cand;
+    c->n_cand_known = false;
+    // room for 1/8 of the band pixels of the row tile (synthetic and real maps keep 3-6 %);
+    // a device flag reports the rare overflow and the scan is redone with the exact size
+    const int64_t tile_px = band_pixels_of(c) * (int64_t)(row_end - row_begin) / std::max(c->n, 1);
+    PK_CHECK(reserve_candidates(c, tile_px / 8 + 4096));
+    PK_CHECK(run_candidates(c, 0));
     c->has_candidates = true; c->has_scores = false;
+    if (n_candidates) {
+        PK_CHECK(settle_candidates(c));
+        *n_candidates = c->n_cand;
+    }
     return PK_OK;
 }
 
 extern "C" int pk_chrom_candidates(pk_chrom* c, int32_t* out_x, int32_t* out_y, int64_t capacity, int64_t* n) {
     if (!c || !n) { pk_set_error("pk_chrom_candidates: bad argument"); return PK_EINVAL; }
     if (!c->has_candidates) { pk_set_error("pk_chrom_candidates: find_candidates not called"); return PK_ESTATE; }
+    PK_CUDA(cudaSetDevice(c->device));
+    if (!c->n_cand_known) PK_CHECK(settle_candidates(c));
     *n = c->n_cand;
     if (!out_x && !out_y) return PK_OK;
     if (capacity < c->n_cand) { pk_set_error("pk_chrom_candidates: capacity %lld < %lld", (long long)capacity, (long long)c->n_cand); return PK_ECAPACITY; }
     if (c->n_cand == 0) return PK_OK;
-    PK_CUDA(cudaSetDevice(c->device));
-    std::vector<int32_t> d((size_t)c->n_cand);
-    PK_CUDA(cudaMemcpyAsync(out_x, c->d_cx, (size_t)c->n_cand * 4, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<int32_t> xs((size_t)c->n_cand), d((size_t)c->n_cand);
+    PK_CUDA(cudaMemcpyAsync(xs.data(), c->d_cx, (size_t)c->n_cand * 4, cudaMemcpyDeviceToHost, c->stream));
     PK_CUDA(cudaMemcpyAsync(d.data(), c->d_cd, (size_t)c->n_cand * 4, cudaMemcpyDeviceToHost, c->stream));
     PK_CUDA(cudaStreamSynchronize(c->stream));
-    if (out_y) for (int64_t i = 0; i < c->n_cand; ++i) out_y[i] = out_x[i] + d[(size_t)i];
+    for (int64_t i = 0; i < c->n_cand; ++i) {
+        if (out_x) out_x[i] = xs[(size_t)i];
+        if (out_y) out_y[i] = xs[(size_t)i] + d[(size_t)i];
+    }
     return PK_OK;
 }
 
@@ -492,40 +666,28 @@ static int ensure_feature_buffer(pk_chrom* c) {
     return PK_OK;
 }
 
-static int ensure_score_buffers(pk_chrom* c) {
-    if (c->n_cand > c->keep_cap || !c->d_keep) {
-        dev_free(c->d_keep); dev_free(c->d_prob);
-        int64_t cap = std::max<int64_t>(c->n_cand + c->n_cand / 8, 1024);
-        PK_CHECK(dev_alloc(&c->d_keep, (size_t)cap));
-        PK_CHECK(dev_alloc(&c->d_prob, (size_t)cap));
-        c->keep_cap = cap;
-    }
-    if (c->n_cand > c->rec_cap || !c->d_rx) {
-        dev_free(c->d_rx); dev_free(c->d_ry); dev_free(c->d_rb); dev_free(c->d_rp); dev_free(c->d_rv);
-        int64_t cap = std::max<int64_t>(c->n_cand + c->n_cand / 8, 1024);
-        PK_CHECK(dev_alloc(&c->d_rx, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_ry, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_rb, (size_t)cap));
-        PK_CHECK(dev_alloc(&c->d_rp, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_rv, (size_t)cap));
-        c->rec_cap = cap;
-    }
-    c->n_batches = (c->n_cand_all + PK_BATCH - 1) / PK_BATCH;
-    if (c->n_batches + 1 > c->batch_cap || !c->d_batch_win) {
+static int reset_score_state(pk_chrom* c) {
+    // batches are numbered over the whole chromosome's candidates (at most the band pixels)
+    const int64_t nb = band_pixels_of(c) / PK_BATCH + 2;
+    if (nb > c->batch_cap || !c->d_batch_win) {
         dev_free(c->d_batch_win);
-        int64_t cap = std::max<int64_t>(c->n_batches + 1, 64);
-        PK_CHECK(dev_alloc(&c->d_batch_win, (size_t)cap));
-        c->batch_cap = cap;
+        PK_CHECK(dev_alloc(&c->d_batch_win, (size_t)nb));
+        c->batch_cap = nb;
     }
     PK_CUDA(cudaMemsetAsync(c->d_batch_win, 0, (size_t)c->batch_cap * 4, c->stream));
     PK_CUDA(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream));
+    PK_CUDA(cudaMemsetAsync(c->d_keep, 0, (size_t)c->cand_cap, c->stream));
     return PK_OK;
 }
 
 extern "C" int pk_chrom_features(pk_chrom* c, uint8_t* keep, float* fea32, double* fea64, int64_t capacity) {
     if (!c) { pk_set_error("pk_chrom_features: NULL handle"); return PK_EINVAL; }
     if (!c->has_candidates) { pk_set_error("pk_chrom_features: find_candidates not called"); return PK_ESTATE; }
+    PK_CUDA(cudaSetDevice(c->device));
+    if (!c->n_cand_known) PK_CHECK(settle_candidates(c));
     if (capacity < c->n_cand) { pk_set_error("pk_chrom_features: capacity too small"); return PK_ECAPACITY; }
     if (c->n_cand == 0) return PK_OK;
-    PK_CUDA(cudaSetDevice(c->device));
-    PK_CHECK(ensure_score_buffers(c));
+    PK_CHECK(reset_score_state(c));
     PK_CHECK(ensure_feature_buffer(c));
     double* d64 = nullptr;
     if (fea64) PK_CHECK(dev_alloc(&d64, (size_t)c->n_cand * c->F));
@@ -538,27 +700,22 @@ extern "C" int pk_chrom_features(pk_chrom* c, uint8_t* keep, float* fea32, doubl
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { pk_set_error("pk_chrom_features: %s", cudaGetErrorString(e)); r = PK_ECUDA; }
     }
-    if (d64) cudaFree(d64);
+    dev_free(d64);
     c->has_scores = false;
     return r;
 }
 
-extern "C" int pk_chrom_score(pk_chrom* c, pk_forest* f, double min_prob) {
-    if (!c || !f) { pk_set_error("pk_chrom_score: NULL handle"); return PK_EINVAL; }
-    if (!c->has_candidates) { pk_set_error("pk_chrom_score: find_candidates not called"); return PK_ESTATE; }
-    if (f->device != c->device) { pk_set_error("pk_chrom_score: forest lives on device %d, chromosome on %d", f->device, c->device); return PK_EINVAL; }
-    if (f->n_features != c->F) { pk_set_error("pk_chrom_score: forest has %d features, window has %d", f->n_features, c->F); return PK_EINVAL; }
-    PK_CUDA(cudaSetDevice(c->device));
+static int run_score(pk_chrom* c, pk_forest* f, double min_prob) {
     cudaStream_t s = c->stream;
-    PK_CHECK(ensure_score_buffers(c));
+    PK_CHECK(reset_score_state(c));
     PK_CUDA(cudaEventRecord(c->ev[7], s));
     const bool fused = g_tune_fused != 0 && pk_fused_supported(c->w, f->n_trees);
     if (fused) {
         // features stay in shared memory; stage [4] reports the fused kernel, [5] is 0
-        if (c->n_cand > 0) PK_CUDA(cudaMemsetAsync(c->d_keep, 0, (size_t)c->n_cand, s));
         PK_CHECK(pk_launch_fused(c, f, g_tune_fused == 2 ? 1 : 0));
         PK_CUDA(cudaEventRecord(c->ev[8], s));
     } else {
+        if (!c->n_cand_known) PK_CHECK(settle_candidates(c));
         PK_CHECK(ensure_feature_buffer(c));
         PK_CHECK(pk_launch_features(c, nullptr));
         PK_CUDA(cudaEventRecord(c->ev[8], s));
@@ -567,6 +724,17 @@ extern "C" int pk_chrom_score(pk_chrom* c, pk_forest* f, double min_prob) {
     PK_CUDA(cudaEventRecord(c->ev[9], s));
     PK_CHECK(pk_launch_emit(c, min_prob));
     PK_CUDA(cudaEventRecord(c->ev[10], s));
+    return PK_OK;
+}
+
+extern "C" int pk_chrom_score(pk_chrom* c, pk_forest* f, double min_prob) {
+    if (!c || !f) { pk_set_error("pk_chrom_score: NULL handle"); return PK_EINVAL; }
+    if (!c->has_candidates) { pk_set_error("pk_chrom_score: find_candidates not called"); return PK_ESTATE; }
+    if (f->device != c->device) { pk_set_error("pk_chrom_score: forest lives on device %d, chromosome on %d", f->device, c->device); return PK_EINVAL; }
+    if (f->n_features != c->F) { pk_set_error("pk_chrom_score: forest has %d features, window has %d", f->n_features, c->F); return PK_EINVAL; }
+    PK_CUDA(cudaSetDevice(c->device));
+    c->last_forest = f; c->last_thre = min_prob;
+    PK_CHECK(run_score(c, f, min_prob));
     c->has_scores = true;
     return PK_OK;
 }
@@ -575,6 +743,15 @@ extern "C" int pk_chrom_result_count(pk_chrom* c, int64_t* n_records, int64_t* n
     if (!c) { pk_set_error("pk_chrom_result_count: NULL handle"); return PK_EINVAL; }
     if (!c->has_scores) { pk_set_error("pk_chrom_result_count: score not called"); return PK_ESTATE; }
     PK_CUDA(cudaSetDevice(c->device));
+    if (!c->n_cand_known) {
+        // first host look at this scan: if a device-side capacity was exceeded the scan was
+        // redone by settle_candidates and the scoring has to be replayed on the full list
+        int32_t flags[4];
+        PK_CHECK(read_flags(c, flags));
+        const bool overflow = flags[0] != 0 || (flags[3] & 2) != 0;
+        PK_CHECK(settle_candidates(c));
+        if (overflow) PK_CHECK(run_score(c, c->last_forest, c->last_thre));
+    }
     unsigned long long h[4] = {0, 0, 0, 0};
     PK_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     PK_CUDA(cudaStreamSynchronize(c->stream));
@@ -587,10 +764,11 @@ extern "C" int pk_chrom_result_count(pk_chrom* c, int64_t* n_records, int64_t* n
 extern "C" int pk_chrom_batch_windows(pk_chrom* c, int64_t* out, int64_t capacity, int64_t* n_batches) {
     if (!c || !n_batches) { pk_set_error("pk_chrom_batch_windows: bad argument"); return PK_EINVAL; }
     if (!c->has_scores) { pk_set_error("pk_chrom_batch_windows: score not called"); return PK_ESTATE; }
+    PK_CHECK(pk_chrom_result_count(c, nullptr, nullptr, nullptr));
+    c->n_batches = (c->n_cand_all + PK_BATCH - 1) / PK_BATCH;
     *n_batches = c->n_batches;
     if (!out) return PK_OK;
     if (capacity < c->n_batches) { pk_set_error("pk_chrom_batch_windows: capacity too small"); return PK_ECAPACITY; }
-    PK_CUDA(cudaSetDevice(c->device));
     std::vector<int32_t> h((size_t)std::max<int64_t>(c->n_batches, 1));
     PK_CUDA(cudaMemcpyAsync(h.data(), c->d_batch_win, (size_t)c->n_batches * 4, cudaMemcpyDeviceToHost, c->stream));
     PK_CUDA(cudaStreamSynchronize(c->stream));

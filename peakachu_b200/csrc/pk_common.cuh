@@ -81,10 +81,14 @@ struct pk_chrom {
     long long* d_diag_cnt = nullptr; // [ND]
     double* d_exp = nullptr;         // [ND]
     double* d_bg = nullptr;          // [ND]
-    int32_t* d_flags = nullptr;      // [4]: 0 = poisson table overflow, 1 = max count seen
+    // [4]: 0 = a count exceeded the Poisson table, 1 = largest in-band count,
+    //      2 = expected fit failed, 3 = bit0 pixels not sorted / bit1 candidate buffer too small
+    int32_t* d_flags = nullptr;
     // upload staging
     int32_t *d_b1 = nullptr, *d_b2 = nullptr, *d_cnt = nullptr;
     int64_t pix_cap = 0;
+    long long* d_rowptr = nullptr;   // [n+1]
+    bool declared_sorted = false;
     // candidates
     int32_t n_chunks = 0;
     uint32_t* d_cnt_all = nullptr;   // [nd_cand * n_chunks] whole-chromosome counts
@@ -92,8 +96,14 @@ struct pk_chrom {
     uint32_t* d_off_all = nullptr;   // exclusive scans (+1 total)
     uint32_t* d_off_tile = nullptr;
     int64_t cnt_cap = 0;
-    int64_t n_cand = 0, n_cand_all = 0;
+    uint32_t* d_bits = nullptr;      // [nd_cand * n_chunks * 32] one bit per band slot
+    long long* d_ncand = nullptr;    // [2]: candidates in the row tile, in the whole chromosome
+    int64_t n_cand = 0, n_cand_all = 0;   // host copies, valid when n_cand_known
+    bool n_cand_known = false;
     int64_t cand_cap = 0;
+    // last scoring request (replayed if a device-side capacity flag was raised)
+    pk_forest* last_forest = nullptr;
+    double last_thre = 0.0;
     int32_t *d_cx = nullptr, *d_cd = nullptr, *d_crank = nullptr;
     // scoring
     uint8_t* d_keep = nullptr;

@@ -25,7 +25,8 @@
 struct FusedParams {
     const int32_t* band; const double* w; const double* expv;
     int n; long long pitch; int balanced; int ND;
-    const int32_t* cx; const int32_t* cd; const int32_t* crank; long long n_cand;
+    const int32_t* cx; const int32_t* cd; const int32_t* crank;
+    const long long* ncand_dev; long long cand_cap;   // candidate count lives on the device
     const uint2* nodes; const uint32_t* roots; const uint8_t* depth; const int4* groups;
     int n_groups; int n_trees;
     uint8_t* keep; double* prob; int32_t* batch_win; unsigned long long* counters;
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const int half = lane >> 4, h = lane & 15;
     const int G = prm.n_groups;
+    const long long n_cand = min(prm.ncand_dev[0], prm.cand_cap);
     const bool resident = (G <= 2);
 
     // ---- one-time setup -----------------------------------------------------
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
             if (tid == 0) {
                 int free_slots = P - s_nkept;
                 long long st = (long long)atomicAdd(prm.next, (unsigned long long)free_slots);
-                long long rem = prm.n_cand - st;
+                long long rem = n_cand - st;
                 s_start = st;
                 s_take = rem <= 0 ? 0 : (int)(rem < free_slots ? rem : free_slots);
                 if (rem <= free_slots) s_done = 1;
@@ -467,19 +469,18 @@ static int launch_fused_t(FusedParams prm, pk_forest* f, int ND, int sm_count, c
         PK_CUDA(cudaFuncSetAttribute(k_score_fused<W, P, TPP, TBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
-    long long want = (prm.n_cand + P - 1) / P;
-    unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)sm_count));
+    unsigned grid = (unsigned)sm_count;        // persistent: CTAs without work exit at once
     k_score_fused<W, P, TPP, TBN><<<grid, P * TPP, smem, stream>>>(prm);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
 
 int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant) {
-    if (c->n_cand == 0) return PK_OK;
     FusedParams prm;
     prm.band = c->d_band; prm.w = c->d_w; prm.expv = c->d_exp;
     prm.n = c->n; prm.pitch = c->pitch; prm.balanced = c->balanced; prm.ND = c->ND;
-    prm.cx = c->d_cx; prm.cd = c->d_cd; prm.crank = c->d_crank; prm.n_cand = c->n_cand;
+    prm.cx = c->d_cx; prm.cd = c->d_cd; prm.crank = c->d_crank;
+    prm.ncand_dev = c->d_ncand; prm.cand_cap = c->cand_cap;
     prm.nodes = f->d_nodes; prm.roots = f->d_root; prm.depth = f->d_depth; prm.groups = nullptr;
     prm.n_groups = 0; prm.n_trees = f->n_trees;
     prm.keep = c->d_keep; prm.prob = c->d_prob; prm.batch_win = c->d_batch_win; prm.counters = c->d_counters;

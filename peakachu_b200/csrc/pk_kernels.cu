@@ -47,222 +47,6 @@ __global__ void __launch_bounds__(256) k_scatter_pixels(
 }
 
 // ---------------------------------------------------------------------------
-// K2  per-diagonal sums in numpy's pairwise order (utils.py:160-170).
-//     One CTA per distance d. Phase 1 compacts value(x, d) over x with
-//     valid[x] & valid[x+d] into scratch (zeros included, order kept). Phase 2
-//     evaluates numpy's pairwise tree: recursion n > 128 -> (n2 = n/2 - (n/2)%8 | rest);
-//     leaves of <= 128 elements use 8 strided accumulators combined as
-//     ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a sequential tail.
-// ---------------------------------------------------------------------------
-__device__ double pk_leaf_sum(const double* __restrict__ a, int n) {
-    if (n < 8) {
-        double res = 0.0;
-        for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
-        return res;
-    }
-    double r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
-    int i;
-    for (i = 8; i < n - (n % 8); i += 8) {
-        r0 = __dadd_rn(r0, a[i + 0]); r1 = __dadd_rn(r1, a[i + 1]);
-        r2 = __dadd_rn(r2, a[i + 2]); r3 = __dadd_rn(r3, a[i + 3]);
-        r4 = __dadd_rn(r4, a[i + 4]); r5 = __dadd_rn(r5, a[i + 5]);
-        r6 = __dadd_rn(r6, a[i + 6]); r7 = __dadd_rn(r7, a[i + 7]);
-    }
-    double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
-                           __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
-    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
-    return res;
-}
-
-// leaves of numpy's recursion over [0, n), in order; returns their number
-__device__ int pk_enumerate_leaves(int n, int32_t* __restrict__ leaf_start) {
-    int stack_s[40], stack_n[40];
-    int sp = 0, nl = 0;
-    stack_s[0] = 0; stack_n[0] = n; sp = 1;
-    while (sp > 0) {
-        --sp;
-        int s = stack_s[sp], m = stack_n[sp];
-        if (m <= 128) { leaf_start[nl++] = s; continue; }
-        int n2 = m / 2;
-        n2 -= n2 % 8;
-        stack_s[sp] = s + n2; stack_n[sp] = m - n2; ++sp;     // right, popped second
-        stack_s[sp] = s;      stack_n[sp] = n2;     ++sp;     // left, popped first
-    }
-    leaf_start[nl] = n;
-    return nl;
-}
-
-// combine leaf sums along the same recursion (left + right), iteratively
-__device__ double pk_combine(int n, const double* __restrict__ leaf_sum) {
-    // post-order evaluation with an explicit stack of pending sizes / partial values
-    int st_n[40]; unsigned char st_state[40]; double st_val[40];
-    int sp = 0, li = 0;
-    st_n[0] = n; st_state[0] = 0; sp = 1;
-    double ret = 0.0;
-    while (sp > 0) {
-        int top = sp - 1;
-        int m = st_n[top];
-        if (m <= 128) { ret = leaf_sum[li++]; --sp; continue; }
-        int n2 = m / 2;
-        n2 -= n2 % 8;
-        if (st_state[top] == 0) {           // descend left
-            st_state[top] = 1;
-            st_n[sp] = n2; st_state[sp] = 0; ++sp;
-        } else if (st_state[top] == 1) {    // left done -> descend right
-            st_val[top] = ret;
-            st_state[top] = 2;
-            st_n[sp] = m - n2; st_state[sp] = 0; ++sp;
-        } else {                            // both done
-            ret = __dadd_rn(st_val[top], ret);
-            --sp;
-        }
-    }
-    return ret;
-}
-
-__global__ void __launch_bounds__(512) k_diag_sums(
-    const int32_t* __restrict__ band, const double* __restrict__ w, const uint8_t* __restrict__ valid,
-    int n, long long pitch, int balanced, double* __restrict__ scratch,
-    int32_t* __restrict__ leaf_start, double* __restrict__ leaf_sum, long long LP,
-    double* __restrict__ out_sum, long long* __restrict__ out_cnt) {
-    const int d = blockIdx.x;
-    const int len = n - d;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    __shared__ int warp_tot[16];
-    __shared__ int s_base, s_nleaf;
-    double* sc = scratch + (long long)d * pitch;
-    int32_t* ls = leaf_start + (long long)d * LP;
-    double* lsum = leaf_sum + (long long)d * LP;
-    if (tid == 0) s_base = 0;
-    __syncthreads();
-    const int32_t* row = band + (long long)d * pitch;
-    for (int x0 = 0; x0 < len; x0 += 512) {
-        int x = x0 + tid;
-        bool f = (x < len) && valid[x] && valid[x + d];
-        unsigned bal = __ballot_sync(0xffffffffu, f);
-        int rank = __popc(bal & ((1u << lane) - 1u));
-        if (lane == 0) warp_tot[wid] = __popc(bal);
-        __syncthreads();
-        int base = s_base, pre = 0, tot = 0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            int t = warp_tot[k];
-            if (k < wid) pre += t;
-            tot += t;
-        }
-        if (f) sc[base + pre + rank] = pk_value(row[x], balanced ? w[x] : 0.0, balanced ? w[x + d] : 0.0, balanced);
-        __syncthreads();
-        if (tid == 0) s_base = base + tot;
-    }
-    __syncthreads();
-    const int nd = (len > 0) ? s_base : 0;
-    if (tid == 0) s_nleaf = pk_enumerate_leaves(nd, ls);
-    __syncthreads();
-    const int nl = s_nleaf;
-    for (int l = tid; l < nl; l += 512) lsum[l] = pk_leaf_sum(sc + ls[l], ls[l + 1] - ls[l]);
-    __syncthreads();
-    if (tid == 0) {
-        out_sum[d] = pk_combine(nd, lsum);
-        out_cnt[d] = nd;
-    }
-}
-
-// ---------------------------------------------------------------------------
-// K3  Poisson candidate scan (scoreUtils.py:40-68).
-//     candidate <=> count > 0 and mu = bg[d] / (w_x * w_y) satisfies 0 <= mu < crit[count].
-//     Reference order is distance asc, row asc: count per (d, chunk of 1024 rows),
-//     exclusive scan, then an order-preserving write.
-// ---------------------------------------------------------------------------
-#define PK_CHUNK 1024
-
-__device__ __forceinline__ bool pk_is_candidate(int k, int x, int d, double bg, const double* __restrict__ w,
-                                                int balanced, const double* __restrict__ crit, int kmax,
-                                                int32_t* flags) {
-    if (k <= 0) return false;
-    double mu = bg;
-    if (balanced) mu = __ddiv_rn(bg, __dmul_rn(w[x], w[x + d]));
-    if (k > kmax) { atomicOr(&flags[0], 1); return false; }
-    return (mu >= 0.0) && (mu < crit[k]);
-}
-
-template <bool WRITE>
-__global__ void __launch_bounds__(256) k_candidates(
-    const int32_t* __restrict__ band, const double* __restrict__ w, const double* __restrict__ bg,
-    int n, long long pitch, int balanced, int lower, const double* __restrict__ crit, int kmax,
-    int row_begin, int row_end, int n_chunks, uint32_t* __restrict__ cnt_all, uint32_t* __restrict__ cnt_tile,
-    const uint32_t* __restrict__ off_all, const uint32_t* __restrict__ off_tile,
-    int32_t* __restrict__ cx, int32_t* __restrict__ cd, int32_t* __restrict__ crank, int32_t* flags) {
-    const int chunk = blockIdx.x, di = blockIdx.y, d = lower + di;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int len = n - d;
-    const double e = bg[d];
-    const bool d_ok = (len > 0) && (e > 0.0);
-    const int32_t* row = band + (long long)d * pitch;
-    __shared__ int wa[8], wt[8];
-    int base_all = 0, base_tile = 0;
-    const long long slot = (long long)di * n_chunks + chunk;
-    if (WRITE) { base_all = off_all[slot]; base_tile = off_tile[slot]; }
-    int tot_all = 0, tot_tile = 0;
-#pragma unroll
-    for (int j = 0; j < PK_CHUNK / 256; ++j) {
-        int x = chunk * PK_CHUNK + j * 256 + tid;
-        bool c = d_ok && (x < len) && pk_is_candidate(row[x], x, d, e, w, balanced, crit, kmax, flags);
-        bool t = c && (x >= row_begin) && (x < row_end);
-        unsigned ba = __ballot_sync(0xffffffffu, c), bt = __ballot_sync(0xffffffffu, t);
-        if (lane == 0) { wa[wid] = __popc(ba); wt[wid] = __popc(bt); }
-        __syncthreads();
-        int pa = 0, pt = 0, sa = 0, st = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (k < wid) { pa += wa[k]; pt += wt[k]; }
-            sa += wa[k]; st += wt[k];
-        }
-        if (WRITE && t) {
-            unsigned lm = (1u << lane) - 1u;
-            int ra = base_all + tot_all + pa + __popc(ba & lm);
-            int rt = base_tile + tot_tile + pt + __popc(bt & lm);
-            cx[rt] = x; cd[rt] = d; crank[rt] = ra;
-        }
-        tot_all += sa; tot_tile += st;
-        __syncthreads();
-    }
-    if (!WRITE && tid == 0) { cnt_all[slot] = tot_all; cnt_tile[slot] = tot_tile; }
-}
-
-// exclusive scan of two uint32 arrays of length m (+ total at [m]); single CTA
-__global__ void __launch_bounds__(1024) k_scan2(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
-                                                long long m, uint32_t* __restrict__ oa, uint32_t* __restrict__ ob) {
-    __shared__ uint32_t sa[32], sb[32];
-    __shared__ uint32_t carry_a, carry_b;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) { carry_a = 0; carry_b = 0; }
-    __syncthreads();
-    for (long long i0 = 0; i0 < m; i0 += 1024) {
-        long long i = i0 + tid;
-        uint32_t va = (i < m) ? a[i] : 0u, vb = (i < m) ? b[i] : 0u;
-        uint32_t xa = va, xb = vb;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t ta = __shfl_up_sync(0xffffffffu, xa, o), tb = __shfl_up_sync(0xffffffffu, xb, o);
-            if (lane >= o) { xa += ta; xb += tb; }
-        }
-        if (lane == 31) { sa[wid] = xa; sb[wid] = xb; }
-        __syncthreads();
-        uint32_t pa = 0, pb = 0, ta = 0, tb = 0;
-        for (int k = 0; k < 32; ++k) {
-            if (k < wid) { pa += sa[k]; pb += sb[k]; }
-            ta += sa[k]; tb += sb[k];
-        }
-        uint32_t ca = carry_a, cb = carry_b;
-        if (i < m) { oa[i] = ca + pa + xa - va; ob[i] = cb + pb + xb - vb; }
-        __syncthreads();
-        if (tid == 0) { carry_a = ca + ta; carry_b = cb + tb; }
-        __syncthreads();
-    }
-    if (tid == 0) { oa[m] = carry_a; ob[m] = carry_b; }
-}
-
-// ---------------------------------------------------------------------------
 // K4  window features (scoreUtils.py:70-93 + utils.py:180-237 + scipy gaussian_filter
 //     + utils.image_normalize). One warp per candidate; the (2w+1)^2 window lives in
 //     shared memory as float64.
@@ -423,31 +207,35 @@ __global__ void __launch_bounds__(128) k_forest(
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_emit(
     const int32_t* __restrict__ cx, const int32_t* __restrict__ cd, const int32_t* __restrict__ crank,
-    const uint8_t* __restrict__ keep, const double* __restrict__ prob, long long n_cand, double thre,
-    const int32_t* __restrict__ batch_win, int apply_rule,
+    const uint8_t* __restrict__ keep, const double* __restrict__ prob, const long long* __restrict__ ncand_dev,
+    long long cap, double thre, const int32_t* __restrict__ batch_win, int apply_rule,
     const int32_t* __restrict__ band, const double* __restrict__ w, long long pitch, int balanced,
     int32_t* __restrict__ rx, int32_t* __restrict__ ry, double* __restrict__ rp, double* __restrict__ rv,
     int32_t* __restrict__ rb, unsigned long long* __restrict__ counters) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    bool out = false;
-    int x = 0, d = 0, b = 0;
-    double p = 0.0;
-    if (i < n_cand && keep[i]) {
-        p = prob[i];
-        b = crank[i] / PK_BATCH;
-        out = (p > thre) && (!apply_rule || batch_win[b] > 1);
-        x = cx[i]; d = cd[i];
-    }
-    unsigned bal = __ballot_sync(0xffffffffu, out);
-    if (bal == 0) return;
+    const long long n_cand = min(ncand_dev[0], cap);
     const int lane = threadIdx.x & 31;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&counters[0], (unsigned long long)__popc(bal));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (out) {
-        unsigned long long o = base + __popc(bal & ((1u << lane) - 1u));
-        rx[o] = x; ry[o] = x + d; rp[o] = p; rb[o] = b;
-        rv[o] = pk_value(band[(long long)d * pitch + x], balanced ? w[x] : 0.0, balanced ? w[x + d] : 0.0, balanced);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n_round = (n_cand + 31) / 32 * 32;        // whole warps take part in the ballot
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool out = false;
+        int x = 0, d = 0, b = 0;
+        double p = 0.0;
+        if (i < n_cand && keep[i]) {
+            p = prob[i];
+            b = crank[i] / PK_BATCH;
+            out = (p > thre) && (!apply_rule || batch_win[b] > 1);
+            x = cx[i]; d = cd[i];
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, out);
+        if (bal == 0) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&counters[0], (unsigned long long)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (out) {
+            const unsigned long long o = base + __popc(bal & ((1u << lane) - 1u));
+            rx[o] = x; ry[o] = x + d; rp[o] = p; rb[o] = b;
+            rv[o] = pk_value(band[(long long)d * pitch + x], balanced ? w[x] : 0.0, balanced ? w[x + d] : 0.0, balanced);
+        }
     }
 }
 
@@ -459,35 +247,6 @@ int pk_launch_scatter(pk_chrom* c, const int32_t* b1, const int32_t* b2, const i
     unsigned grid = (unsigned)((nnz + 255) / 256);
     k_scatter_pixels<<<grid, 256, 0, c->stream>>>(b1, b2, cnt, nnz, c->d_w, c->n, c->ND, c->pitch,
                                                  c->balanced, c->d_band, c->d_valid, c->d_flags);
-    PK_CUDA(cudaGetLastError());
-    return PK_OK;
-}
-
-int pk_launch_diag_sums(pk_chrom* c) {
-    k_diag_sums<<<c->ND, 512, 0, c->stream>>>(c->d_band, c->d_w, c->d_valid, c->n, c->pitch, c->balanced, c->d_scratch,
-                                              c->d_leaf_start, c->d_leaf_sum, c->LP, c->d_diag_sum, c->d_diag_cnt);
-    PK_CUDA(cudaGetLastError());
-    return PK_OK;
-}
-
-int pk_launch_candidates(pk_chrom* c, const double* d_crit, int kmax, bool write) {
-    int nd = c->upper - c->lower + 1;
-    if (nd <= 0) return PK_OK;
-    dim3 grid(c->n_chunks, nd);
-    if (!write)
-        k_candidates<false><<<grid, 256, 0, c->stream>>>(c->d_band, c->d_w, c->d_bg, c->n, c->pitch, c->balanced, c->lower,
-                                                        d_crit, kmax, c->row_begin, c->row_end, c->n_chunks, c->d_cnt_all,
-                                                        c->d_cnt_tile, nullptr, nullptr, nullptr, nullptr, nullptr, c->d_flags);
-    else
-        k_candidates<true><<<grid, 256, 0, c->stream>>>(c->d_band, c->d_w, c->d_bg, c->n, c->pitch, c->balanced, c->lower,
-                                                       d_crit, kmax, c->row_begin, c->row_end, c->n_chunks, nullptr, nullptr,
-                                                       c->d_off_all, c->d_off_tile, c->d_cx, c->d_cd, c->d_crank, c->d_flags);
-    PK_CUDA(cudaGetLastError());
-    return PK_OK;
-}
-
-int pk_launch_scan2(pk_chrom* c, long long m) {
-    k_scan2<<<1, 1024, 0, c->stream>>>(c->d_cnt_all, c->d_cnt_tile, m, c->d_off_all, c->d_off_tile);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
@@ -520,11 +279,9 @@ int pk_launch_forest(const pk_forest* f, const float* X, const uint8_t* keep, in
 }
 
 int pk_launch_emit(pk_chrom* c, double thre) {
-    if (c->n_cand == 0) return PK_OK;
-    unsigned grid = (unsigned)((c->n_cand + 255) / 256);
-    k_emit<<<grid, 256, 0, c->stream>>>(c->d_cx, c->d_cd, c->d_crank, c->d_keep, c->d_prob, c->n_cand, thre, c->d_batch_win,
-                                        c->whole ? 1 : 0, c->d_band, c->d_w, c->pitch, c->balanced, c->d_rx, c->d_ry,
-                                        c->d_rp, c->d_rv, c->d_rb, c->d_counters);
+    k_emit<<<148 * 4, 256, 0, c->stream>>>(c->d_cx, c->d_cd, c->d_crank, c->d_keep, c->d_prob, c->d_ncand, c->cand_cap, thre,
+                                           c->d_batch_win, c->whole ? 1 : 0, c->d_band, c->d_w, c->pitch, c->balanced,
+                                           c->d_rx, c->d_ry, c->d_rp, c->d_rv, c->d_rb, c->d_counters);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }

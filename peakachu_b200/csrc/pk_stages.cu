@@ -1,0 +1,533 @@
+// peakachu_b200: the stages in front of the scoring kernel -- band build from CSR
+// pixels, per-diagonal sums, expected-curve fit, Poisson candidate scan. All of them
+// run back to back on the handle's stream; none needs the host.
+#include "pk_common.cuh"
+#include "pk_device.cuh"
+
+#include <algorithm>
+
+// ---------------------------------------------------------------------------
+// S1  band build from CSR-ordered pixels (cooler order: sorted by bin1, then bin2).
+//     A CTA owns 32 consecutive rows x0..x0+31. Each warp streams whole rows (its
+//     pixels are contiguous: coalesced loads), scatters counts into a shared-memory
+//     tile T[d][x - x0] and the CTA then writes the tile out as full 128-byte lines,
+//     zeros included -- the band needs no memset and no global atomics.
+//     Side products: valid[] (utils.py:146-156) and the largest in-band count.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_band_csr(
+    const long long* __restrict__ rowptr, const int32_t* __restrict__ b2, const int32_t* __restrict__ cnt,
+    const double* __restrict__ w, int n, int ND, long long pitch, int balanced,
+    int32_t* __restrict__ band, uint8_t* __restrict__ valid, int32_t* __restrict__ flags) {
+    extern __shared__ int32_t s_tile[];                 // [ND][33]
+    const int x0 = blockIdx.x * 32;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    for (int i = tid; i < ND * 33; i += 256) s_tile[i] = 0;
+    __syncthreads();
+    int cmax = 0;
+    for (int xl = wib; xl < 32; xl += 8) {
+        const int x = x0 + xl;
+        if (x >= n) break;
+        const long long p0 = rowptr[x], p1 = rowptr[x + 1];
+        const double wx = balanced ? w[x] : 0.0;
+        bool any = false;
+        for (long long p = p0 + lane; p < p1; p += 32) {
+            const int y = b2[p], c = cnt[p];
+            if (c == 0 || y < x || y >= n) continue;
+            bool fin;
+            if (balanced) fin = isfinite(__dmul_rn(__dmul_rn(wx, w[y]), (double)c));
+            else fin = c > 0;
+            if (fin) { any = true; valid[y] = 1; }
+            const int d = y - x;
+            if (d < ND) {
+                atomicAdd(&s_tile[d * 33 + xl], c);     // duplicates are summed like utils.tocsr
+                cmax = max(cmax, c);
+            }
+        }
+        if (__any_sync(0xffffffffu, any) && lane == 0) valid[x] = 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+    if (lane == 0 && cmax > 0) atomicMax(&flags[1], cmax);
+    __syncthreads();
+    const int x = x0 + lane;
+    if (x < n)
+        for (int d = wib; d < ND; d += 8) band[(long long)d * pitch + x] = s_tile[d * 33 + lane];
+}
+
+// rowptr for pixels sorted by (bin1, bin2): rowptr[x] = first pixel with bin1 >= x
+__global__ void __launch_bounds__(256) k_rowptr(const int32_t* __restrict__ b1, long long nnz, int n,
+                                                long long* __restrict__ rowptr) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    if (x > n) return;
+    long long lo = 0, hi = nnz;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (b1[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    rowptr[x] = lo;
+}
+
+// sortedness check of COO pixels (bin1 non-decreasing, bin1 <= bin2); flags[3] |= 1 if not
+__global__ void __launch_bounds__(256) k_check_sorted(const int32_t* __restrict__ b1, const int32_t* __restrict__ b2,
+                                                      long long nnz, int32_t* __restrict__ flags) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= nnz) return;
+    bool bad = b1[i] > b2[i];
+    if (i + 1 < nnz) bad |= b1[i] > b1[i + 1];
+    if (bad) atomicOr(&flags[3], 1);
+}
+
+// ---------------------------------------------------------------------------
+// S2  per-diagonal sums in numpy's pairwise order (utils.py:160-170).
+//     One CTA per distance d. Each warp owns a contiguous slice of the diagonal:
+//     it counts its valid pairs (valid[x] & valid[x+d]), a block scan turns the
+//     counts into offsets, and the warp writes value(x, d) of its valid pairs,
+//     zeros included and order kept, into the compacted scratch row. numpy's
+//     pairwise tree (n > 128 -> n2 = n/2 - (n/2)%8 | rest; leaves of <= 128
+//     elements with 8 strided accumulators combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)),
+//     then a sequential tail) is evaluated leaf-parallel, combined by one thread.
+// ---------------------------------------------------------------------------
+#define PK_DS_THREADS 512
+#define PK_DS_LEAFCAP 3072
+
+__device__ double pk_leaf_sum(const double* __restrict__ a, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
+        return res;
+    }
+    double r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) {
+        r0 = __dadd_rn(r0, a[i + 0]); r1 = __dadd_rn(r1, a[i + 1]);
+        r2 = __dadd_rn(r2, a[i + 2]); r3 = __dadd_rn(r3, a[i + 3]);
+        r4 = __dadd_rn(r4, a[i + 4]); r5 = __dadd_rn(r5, a[i + 5]);
+        r6 = __dadd_rn(r6, a[i + 6]); r7 = __dadd_rn(r7, a[i + 7]);
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
+                           __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
+// leaves of numpy's recursion over [0, n), in order; returns their number
+__device__ int pk_enumerate_leaves(int n, int32_t* leaf_start, int cap) {
+    int stack_s[40], stack_n[40];
+    int sp = 0, nl = 0;
+    stack_s[0] = 0; stack_n[0] = n; sp = 1;
+    while (sp > 0) {
+        --sp;
+        const int s = stack_s[sp], m = stack_n[sp];
+        if (m <= 128) { if (nl < cap) leaf_start[nl] = s; ++nl; continue; }
+        int n2 = m / 2;
+        n2 -= n2 % 8;
+        stack_s[sp] = s + n2; stack_n[sp] = m - n2; ++sp;     // right, popped second
+        stack_s[sp] = s;      stack_n[sp] = n2;     ++sp;     // left, popped first
+    }
+    if (nl < cap) leaf_start[nl] = n;
+    return nl;
+}
+
+// combine leaf sums along the same recursion (left + right), iteratively
+__device__ double pk_combine(int n, const double* leaf_sum) {
+    int st_n[40]; unsigned char st_state[40]; double st_val[40];
+    int sp = 0, li = 0;
+    st_n[0] = n; st_state[0] = 0; sp = 1;
+    double ret = 0.0;
+    while (sp > 0) {
+        const int top = sp - 1;
+        const int m = st_n[top];
+        if (m <= 128) { ret = leaf_sum[li++]; --sp; continue; }
+        int n2 = m / 2;
+        n2 -= n2 % 8;
+        if (st_state[top] == 0) {
+            st_state[top] = 1;
+            st_n[sp] = n2; st_state[sp] = 0; ++sp;
+        } else if (st_state[top] == 1) {
+            st_val[top] = ret;
+            st_state[top] = 2;
+            st_n[sp] = m - n2; st_state[sp] = 0; ++sp;
+        } else {
+            ret = __dadd_rn(st_val[top], ret);
+            --sp;
+        }
+    }
+    return ret;
+}
+
+__global__ void __launch_bounds__(PK_DS_THREADS) k_diag_sums(
+    const int32_t* __restrict__ band, const double* __restrict__ w, const uint8_t* __restrict__ valid,
+    int n, long long pitch, int balanced, double* __restrict__ scratch,
+    int32_t* __restrict__ g_leaf_start, double* __restrict__ g_leaf_sum, long long LP,
+    double* __restrict__ out_sum, long long* __restrict__ out_cnt) {
+    constexpr int NWARP = PK_DS_THREADS / 32;
+    const int d = blockIdx.x;
+    const int len = n - d;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ int s_wcnt[NWARP], s_nleaf;
+    __shared__ int32_t s_leaf_start[PK_DS_LEAFCAP + 1];
+    __shared__ double s_leaf_sum[PK_DS_LEAFCAP];
+    double* sc = scratch + (long long)d * pitch;
+    const int32_t* row = band + (long long)d * pitch;
+    // slice of this warp: multiple of 32 elements
+    const int per = len > 0 ? (((len + NWARP - 1) / NWARP + 31) & ~31) : 0;
+    const int xb = wid * per, xe = min(len, xb + per);
+    int cntw = 0;
+    for (int x0 = xb; x0 < xe; x0 += 32) {
+        const int x = x0 + lane;
+        const bool f = (x < xe) && valid[x] && valid[x + d];
+        cntw += __popc(__ballot_sync(0xffffffffu, f));
+    }
+    if (lane == 0) s_wcnt[wid] = cntw;
+    __syncthreads();
+    int base = 0, nd = 0;
+#pragma unroll
+    for (int k = 0; k < NWARP; ++k) {
+        const int t = s_wcnt[k];
+        if (k < wid) base += t;
+        nd += t;
+    }
+    for (int x0 = xb; x0 < xe; x0 += 32) {
+        const int x = x0 + lane;
+        const bool f = (x < xe) && valid[x] && valid[x + d];
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (f) sc[base + __popc(bal & ((1u << lane) - 1u))] =
+                   pk_value(row[x], balanced ? w[x] : 0.0, balanced ? w[x + d] : 0.0, balanced);
+        base += __popc(bal);
+    }
+    __syncthreads();                       // scratch row complete (block-scope visibility)
+    int32_t* ls = s_leaf_start;
+    double* lsum = s_leaf_sum;
+    if (tid == 0) {
+        int nl = pk_enumerate_leaves(nd, s_leaf_start, PK_DS_LEAFCAP);
+        if (nl > PK_DS_LEAFCAP) nl = -pk_enumerate_leaves(nd, g_leaf_start + (long long)d * LP, (int)LP - 1);
+        s_nleaf = nl;
+    }
+    __syncthreads();
+    int nl = s_nleaf;
+    if (nl < 0) { nl = -nl; ls = g_leaf_start + (long long)d * LP; lsum = g_leaf_sum + (long long)d * LP; }
+    for (int l = tid; l < nl; l += PK_DS_THREADS) lsum[l] = pk_leaf_sum(sc + ls[l], ls[l + 1] - ls[l]);
+    __syncthreads();
+    if (tid == 0) {
+        out_sum[d] = pk_combine(nd, lsum);
+        out_cnt[d] = nd;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// S3  expected curve on the device (utils.py:160-176): mean where more than 10
+//     valid entries; IsotonicRegression(increasing=False, out_of_bounds='clip')
+//     = PAVA on the reversed positive means (scipy, Busing 2022 Alg. 1), drop
+//     interior points of constant runs (sklearn), clip the query, numpy.interp.
+//     Same operations, same order as pk_host.cpp::pk_fit_expected_host, which the
+//     CPU tests pin against scikit-learn. One CTA; PAVA itself is sequential.
+// ---------------------------------------------------------------------------
+#define PK_FIT_MAX 1024
+
+__global__ void __launch_bounds__(256) k_fit_expected(const double* __restrict__ sum, const long long* __restrict__ cnt,
+                                                      int len, double* __restrict__ out_exp, double* __restrict__ out_bg,
+                                                      int32_t* __restrict__ flags) {
+    __shared__ double s_e[PK_FIT_MAX];      // means, then PAVA values (reversed order)
+    __shared__ double s_w[PK_FIT_MAX];
+    __shared__ double s_kx[PK_FIT_MAX], s_ky[PK_FIT_MAX];
+    __shared__ int s_xs[PK_FIT_MAX], s_r[PK_FIT_MAX + 1];
+    __shared__ int s_n, s_m;
+    const int tid = threadIdx.x;
+    for (int d = tid; d < len; d += 256) {
+        double e = 0.0;
+        if (cnt[d] > 10) e = __ddiv_rn(sum[d], (double)cnt[d]);
+        s_kx[d] = e;                        // borrowed as staging for the means
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int n = 0;
+        for (int d = 0; d < len; ++d)
+            if (s_kx[d] > 0.0) { s_xs[n] = d; s_ky[n] = s_kx[d]; ++n; }
+        s_n = n;
+        if (n > 0) {
+            // PAVA on the reversed values, unit weights
+            for (int i = 0; i < n; ++i) { s_e[i] = s_ky[n - 1 - i]; s_w[i] = 1.0; s_r[i] = -1; }
+            s_r[n] = -1;
+            s_r[0] = 0;
+            if (n > 1) s_r[1] = 1;
+            int b = 0;
+            double xb_prev = s_e[0], wb_prev = s_w[0];
+            for (int i = 1; i < n; ++i) {
+                b++;
+                double xb = s_e[i], wb = s_w[i];
+                if (xb_prev >= xb) {
+                    b--;
+                    double sb = __dadd_rn(__dmul_rn(wb_prev, xb_prev), __dmul_rn(wb, xb));
+                    wb = __dadd_rn(wb, wb_prev);
+                    xb = __ddiv_rn(sb, wb);
+                    while (i < n - 1 && xb >= s_e[i + 1]) {
+                        i++;
+                        sb = __dadd_rn(sb, __dmul_rn(s_w[i], s_e[i]));
+                        wb = __dadd_rn(wb, s_w[i]);
+                        xb = __ddiv_rn(sb, wb);
+                    }
+                    while (b > 0 && s_e[b - 1] >= xb) {
+                        b--;
+                        sb = __dadd_rn(sb, __dmul_rn(s_w[b], s_e[b]));
+                        wb = __dadd_rn(wb, s_w[b]);
+                        xb = __ddiv_rn(sb, wb);
+                    }
+                }
+                s_e[b] = xb_prev = xb;
+                s_w[b] = wb_prev = wb;
+                s_r[b + 1] = i + 1;
+            }
+            int f = n - 1;
+            for (int k = b; k >= 0; --k) {
+                const int t = s_r[k];
+                const double xk = s_e[k];
+                for (int i = f; i >= t; --i) s_e[i] = xk;
+                f = t - 1;
+            }
+            // knots: first, last, and every point that differs from a neighbour (in forward order)
+            int m = 0;
+            for (int i = 0; i < n; ++i) {
+                const double yi = s_e[n - 1 - i];
+                bool keep = (i == 0 || i == n - 1);
+                if (!keep) keep = (yi != s_e[n - i]) || (yi != s_e[n - 2 - i]);
+                if (keep) { s_kx[m] = (double)s_xs[i]; s_ky[m] = yi; ++m; }
+            }
+            s_m = m;
+        } else {
+            atomicOr(&flags[2], 1);         // no positive mean: the reference raises here
+        }
+    }
+    __syncthreads();
+    const int n = s_n, m = s_m;
+    if (n == 0) {
+        for (int d = tid; d < len; d += 256) { out_exp[d] = CUDART_NAN; out_bg[d] = CUDART_NAN; }
+        return;
+    }
+    const double xmin = (double)s_xs[0], xmax = (double)s_xs[n - 1];
+    for (int d = tid; d < len; d += 256) {
+        const double T = fmin(fmax((double)d, xmin), xmax);
+        double v;
+        if (m == 1) {
+            v = s_ky[0];
+        } else {
+            int lo = 0, hi = m;              // upper_bound: first knot > T
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_kx[mid] <= T) lo = mid + 1; else hi = mid;
+            }
+            int j = lo - 1;
+            j = j < 0 ? 0 : (j > m - 1 ? m - 1 : j);
+            if (j == m - 1 || s_kx[j] == T) {
+                v = s_ky[j];
+            } else {
+                const double slope = __ddiv_rn(__dsub_rn(s_ky[j + 1], s_ky[j]), __dsub_rn(s_kx[j + 1], s_kx[j]));
+                v = __dadd_rn(__dmul_rn(slope, __dsub_rn(T, s_kx[j])), s_ky[j]);
+            }
+        }
+        out_exp[d] = v;
+        out_bg[d] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// S4  Poisson candidate scan (scoreUtils.py:40-68).
+//     candidate <=> count > 0 and mu = bg[d] / (w_x * w_y) satisfies 0 <= mu < crit[count].
+//     Reference order is distance asc, row asc. Pass 1 evaluates every band slot
+//     once (4 slots per thread, loads first), keeps one bit per slot and counts per
+//     (distance, 1024-row chunk); a scan gives offsets; pass 2 expands the bits into
+//     the ordered candidate list. Nothing is returned to the host.
+// ---------------------------------------------------------------------------
+#define PK_CHUNK 1024
+
+__global__ void __launch_bounds__(256) k_cand_mark(
+    const int32_t* __restrict__ band, const double* __restrict__ w, const double* __restrict__ bg,
+    int n, long long pitch, int balanced, int lower, const double* __restrict__ crit, int kmax,
+    int row_begin, int row_end, int n_chunks, uint32_t* __restrict__ bits,
+    uint32_t* __restrict__ cnt_all, uint32_t* __restrict__ cnt_tile, int32_t* __restrict__ flags) {
+    const int chunk = blockIdx.x, di = blockIdx.y, d = lower + di;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int len = n - d;
+    const double e = bg[d];
+    const bool d_ok = (len > 0) && (e > 0.0);
+    const int32_t* row = band + (long long)d * pitch;
+    const long long slot = (long long)di * n_chunks + chunk;
+    __shared__ int s_a[8], s_t[8];
+    int k[4];
+    double wx[4], wy[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = chunk * PK_CHUNK + j * 256 + tid;
+        k[j] = (d_ok && x < len) ? row[x] : 0;
+    }
+    if (balanced) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = chunk * PK_CHUNK + j * 256 + tid;
+            wx[j] = k[j] > 0 ? w[x] : 1.0;
+            wy[j] = k[j] > 0 ? w[x + d] : 1.0;
+        }
+    }
+    int tot_a = 0, tot_t = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = chunk * PK_CHUNK + j * 256 + tid;
+        bool c = false;
+        if (k[j] > 0) {
+            double mu = e;
+            if (balanced) mu = __ddiv_rn(e, __dmul_rn(wx[j], wy[j]));
+            if (k[j] > kmax) atomicOr(&flags[0], 1);
+            else c = (mu >= 0.0) && (mu < crit[k[j]]);
+        }
+        const unsigned ba = __ballot_sync(0xffffffffu, c);
+        const unsigned bt = __ballot_sync(0xffffffffu, c && x >= row_begin && x < row_end);
+        if (lane == 0) bits[slot * 32 + j * 8 + wid] = ba;
+        tot_a += __popc(ba);
+        tot_t += __popc(bt);
+    }
+    if (lane == 0) { s_a[wid] = tot_a; s_t[wid] = tot_t; }
+    __syncthreads();
+    if (tid == 0) {
+        int a = 0, t = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { a += s_a[q]; t += s_t[q]; }
+        cnt_all[slot] = a; cnt_tile[slot] = t;
+    }
+}
+
+// exclusive scan of two uint32 arrays of length m; totals -> totals[0..1] (as int64) and at [m]
+__global__ void __launch_bounds__(1024) k_scan2(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
+                                                long long m, uint32_t* __restrict__ oa, uint32_t* __restrict__ ob,
+                                                long long* __restrict__ totals) {
+    __shared__ uint32_t sa[32], sb[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long per = (m + 1023) / 1024;
+    const long long i0 = (long long)tid * per, i1 = min(m, i0 + per);
+    uint32_t la = 0, lb = 0;
+    for (long long i = i0; i < i1; ++i) { la += a[i]; lb += b[i]; }
+    uint32_t xa = la, xb = lb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t ta = __shfl_up_sync(0xffffffffu, xa, o), tb = __shfl_up_sync(0xffffffffu, xb, o);
+        if (lane >= o) { xa += ta; xb += tb; }
+    }
+    if (lane == 31) { sa[wid] = xa; sb[wid] = xb; }
+    __syncthreads();
+    uint32_t pa = 0, pb = 0, ta = 0, tb = 0;
+    for (int k = 0; k < 32; ++k) {
+        if (k < wid) { pa += sa[k]; pb += sb[k]; }
+        ta += sa[k]; tb += sb[k];
+    }
+    uint32_t ra = pa + xa - la, rb = pb + xb - lb;
+    for (long long i = i0; i < i1; ++i) {
+        oa[i] = ra; ob[i] = rb;
+        ra += a[i]; rb += b[i];
+    }
+    if (tid == 0) { oa[m] = ta; ob[m] = tb; totals[0] = tb; totals[1] = ta; }
+}
+
+__global__ void __launch_bounds__(256) k_cand_write(
+    const uint32_t* __restrict__ bits, const uint32_t* __restrict__ off_all, const uint32_t* __restrict__ off_tile,
+    int lower, int row_begin, int row_end, int n_chunks, long long cap,
+    int32_t* __restrict__ cx, int32_t* __restrict__ cd, int32_t* __restrict__ crank, int32_t* __restrict__ flags) {
+    const int chunk = blockIdx.x, di = blockIdx.y, d = lower + di;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long slot = (long long)di * n_chunks + chunk;
+    if (off_all[slot + 1] == off_all[slot]) return;           // no candidate in this chunk
+    __shared__ uint32_t s_pa[32], s_pt[32], s_word[32];
+    if (wid == 0) {
+        // word q covers rows chunk*1024 + (q/8)*256 + (q%8)*32 .. +31, i.e. rows ascend with q
+        const uint32_t word = bits[slot * 32 + lane];
+        const int xw = chunk * PK_CHUNK + (lane >> 3) * 256 + (lane & 7) * 32;
+        uint32_t inr = 0;
+        for (int b = 0; b < 32; ++b)
+            if (xw + b >= row_begin && xw + b < row_end) inr |= 1u << b;
+        uint32_t ca = __popc(word), ct = __popc(word & inr);
+        uint32_t xa = ca, xt = ct;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t ta = __shfl_up_sync(0xffffffffu, xa, o), tt = __shfl_up_sync(0xffffffffu, xt, o);
+            if (lane >= o) { xa += ta; xt += tt; }
+        }
+        s_pa[lane] = off_all[slot] + xa - ca;
+        s_pt[lane] = off_tile[slot] + xt - ct;
+        s_word[lane] = word;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int q = j * 8 + wid;
+        const uint32_t word = s_word[q];
+        const int x = chunk * PK_CHUNK + j * 256 + tid;
+        const bool c = (word >> lane) & 1u;
+        const bool t = c && x >= row_begin && x < row_end;
+        const unsigned bt = __ballot_sync(0xffffffffu, t);
+        if (t) {
+            const unsigned lm = (1u << lane) - 1u;
+            const long long rt = (long long)s_pt[q] + __popc(bt & lm);
+            const uint32_t ra = s_pa[q] + __popc(word & lm);
+            if (rt < cap) { cx[rt] = x; cd[rt] = d; crank[rt] = (int32_t)ra; }
+            else atomicOr(&flags[3], 2);                       // candidate buffer too small
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------
+int pk_launch_band_csr(pk_chrom* c, const long long* rowptr, const int32_t* b2, const int32_t* cnt) {
+    const size_t smem = (size_t)c->ND * 33 * sizeof(int32_t);
+    if (smem > 200 * 1024) { pk_set_error("band build: %d diagonals do not fit a shared-memory tile", c->ND); return PK_EUNSUPPORTED; }
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+        PK_CUDA(cudaFuncSetAttribute(k_band_csr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = smem;
+    }
+    const unsigned grid = (unsigned)((c->n + 31) / 32);
+    k_band_csr<<<grid, 256, smem, c->stream>>>(rowptr, b2, cnt, c->d_w, c->n, c->ND, c->pitch, c->balanced, c->d_band,
+                                               c->d_valid, c->d_flags);
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
+int pk_launch_rowptr(pk_chrom* c, const int32_t* b1, const int32_t* b2, int64_t nnz, long long* rowptr) {
+    if (nnz > 0) {
+        k_check_sorted<<<(unsigned)((nnz + 255) / 256), 256, 0, c->stream>>>(b1, b2, nnz, c->d_flags);
+        PK_CUDA(cudaGetLastError());
+    }
+    k_rowptr<<<(unsigned)((c->n + 1 + 255) / 256), 256, 0, c->stream>>>(b1, nnz, c->n, rowptr);
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
+int pk_launch_diag_sums(pk_chrom* c) {
+    k_diag_sums<<<c->ND, PK_DS_THREADS, 0, c->stream>>>(c->d_band, c->d_w, c->d_valid, c->n, c->pitch, c->balanced,
+                                                        c->d_scratch, c->d_leaf_start, c->d_leaf_sum, c->LP, c->d_diag_sum,
+                                                        c->d_diag_cnt);
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
+bool pk_fit_on_device_supported(int len) { return len <= PK_FIT_MAX; }
+
+int pk_launch_fit_expected(pk_chrom* c) {
+    k_fit_expected<<<1, 256, 0, c->stream>>>(c->d_diag_sum, c->d_diag_cnt, c->ND, c->d_exp, c->d_bg, c->d_flags);
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
+int pk_launch_candidates(pk_chrom* c, const double* d_crit, int kmax) {
+    const int nd = c->upper - c->lower + 1;
+    if (nd <= 0) return PK_OK;
+    const long long m = (long long)nd * c->n_chunks;
+    dim3 grid(c->n_chunks, nd);
+    k_cand_mark<<<grid, 256, 0, c->stream>>>(c->d_band, c->d_w, c->d_bg, c->n, c->pitch, c->balanced, c->lower, d_crit, kmax,
+                                            c->row_begin, c->row_end, c->n_chunks, c->d_bits, c->d_cnt_all, c->d_cnt_tile,
+                                            c->d_flags);
+    PK_CUDA(cudaGetLastError());
+    k_scan2<<<1, 1024, 0, c->stream>>>(c->d_cnt_all, c->d_cnt_tile, m, c->d_off_all, c->d_off_tile, c->d_ncand);
+    PK_CUDA(cudaGetLastError());
+    k_cand_write<<<grid, 256, 0, c->stream>>>(c->d_bits, c->d_off_all, c->d_off_tile, c->lower, c->row_begin, c->row_end,
+                                             c->n_chunks, c->cand_cap, c->d_cx, c->d_cd, c->d_crank, c->d_flags);
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}

@@ -102,19 +102,24 @@ class Chromosome:
                 "weights=None with M is not raw_M is the reference's .hic (KR/NONE via straw) branch, "
                 "which is outside this path")
         b1, b2, cnt = _upper_pixels_from_csr(raw_M)
-        self._init(b1, b2, cnt, weights, int(M.shape[0]), model, lower, upper, cname, res, width, device, stream)
+        self._init(b1, b2, cnt, weights, int(M.shape[0]), model, lower, upper, cname, res, width, device, stream,
+                   sorted_pixels=None)
 
     @classmethod
     def from_pixels(cls, bin1, bin2, count, weights, n_bins, model, lower=6, upper=300,
-                    cname="chrm", res=10000, width=5, device=0, stream=None):
+                    cname="chrm", res=10000, width=5, device=0, stream=None, sorted_pixels=None):
         """Build from cooler-style upper-triangle pixel columns (chromosome-local bin
-        ids) and the weight column (None = raw mode)."""
+        ids) and the weight column (None = raw mode). ``sorted_pixels=True`` promises
+        cooler order (sorted by bin1, then bin2; the device verifies it), ``None``
+        checks on the host, ``False`` takes the order-free scatter path."""
         self = cls.__new__(cls)
-        self._init(bin1, bin2, count, weights, int(n_bins), model, lower, upper, cname, res, width, device, stream)
+        self._init(bin1, bin2, count, weights, int(n_bins), model, lower, upper, cname, res, width, device, stream,
+                   sorted_pixels=sorted_pixels)
         return self
 
     # -- construction = upload + band + expected + candidates (scoreUtils.py:13-34) --
-    def _init(self, b1, b2, cnt, weights, n, model, lower, upper, cname, res, width, device, stream):
+    def _init(self, b1, b2, cnt, weights, n, model, lower, upper, cname, res, width, device, stream,
+              sorted_pixels=None):
         L = _lib.lib()
         _lib.require_device()
         self.chromname, self.r, self.w = cname, res, width
@@ -130,13 +135,16 @@ class Chromosome:
         _lib.check(L.pk_chrom_bounds(self._h, C.byref(lo), C.byref(up), C.byref(el)))
         self.lower, self.upper, self._exp_len = lo.value, up.value, el.value
         b1, b2, cnt = _lib.as_c(b1, np.int32), _lib.as_c(b2, np.int32), _lib.as_c(cnt, np.int32)
+        if sorted_pixels is None:
+            sorted_pixels = bool(b1.size == 0 or (np.all(b1[1:] >= b1[:-1]) and np.all(b1 <= b2)))
+        mem = _lib.PK_MEM_HOST | (_lib.PK_PIXELS_SORTED if sorted_pixels else 0)
         _lib.check(L.pk_chrom_upload_pixels(self._h, _lib.ptr(b1), _lib.ptr(b2), _lib.ptr(cnt), b1.size,
-                                            _lib.ptr(self.weights), _lib.PK_MEM_HOST))
+                                            _lib.ptr(self.weights), mem))
         _lib.check(L.pk_chrom_fit_expected(self._h))
         self._exp = None
-        ncand = C.c_int64()
-        _lib.check(L.pk_chrom_find_candidates(self._h, 0, n, C.byref(ncand)))
-        self.n_candidates = ncand.value
+        # asynchronous: the candidate count is read back only when somebody asks for it
+        _lib.check(L.pk_chrom_find_candidates(self._h, 0, n, None))
+        self._ncand = None
         self._cand = None
         self.M = None
 
@@ -152,6 +160,14 @@ class Chromosome:
             pass
 
     # -- reference attributes ------------------------------------------------------
+    @property
+    def n_candidates(self):
+        if self._ncand is None:
+            got = C.c_int64()
+            _lib.check(_lib.lib().pk_chrom_candidates(self._h, None, None, 0, C.byref(got)))
+            self._ncand = got.value
+        return self._ncand
+
     @property
     def exp_arr(self):
         if self._exp is None:
@@ -205,6 +221,7 @@ class Chromosome:
         _lib.check(L.pk_chrom_result_count(self._h, C.byref(nrec), C.byref(ncand), C.byref(nwin)))
         n = nrec.value
         self.n_windows = nwin.value
+        self._ncand = ncand.value
         x, y = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
         p, v = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.float64)
         _lib.check(L.pk_chrom_fetch_results(self._h, _lib.ptr(x), _lib.ptr(y), _lib.ptr(p), _lib.ptr(v), None,

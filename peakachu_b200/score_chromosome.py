@@ -29,7 +29,7 @@ def main(args):
     forest = DeviceForest.of(flat, device)
     X = Chromosome.from_pixels(b1, b2, cnt, weights, Lib.nbins(ccname), forest, lower=args.lower,
                                upper=args.upper, cname=cikada, res=args.resolution, width=width,
-                               device=device)
+                               device=device, sorted_pixels=True)
     result, R = X.score(thre=args.minimum_prob)           # :70
     X.writeBed(args.output, result, R)                    # :71
     X.close()

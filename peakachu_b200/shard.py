@@ -100,7 +100,8 @@ def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_pro
         weights = Lib.weights(key, correct) if correct else None
         n = Lib.nbins(key)
         X = Chromosome.from_pixels(b1, b2, cnt, weights, n, forest, lower=lower, upper=upper,
-                                   cname="chr" + key.lstrip("chr"), res=res, width=flat.width, device=device)
+                                   cname="chr" + key.lstrip("chr"), res=res, width=flat.width, device=device,
+                                   sorted_pixels=True)
         for a, b in tiles:
             ncand = C.c_int64()
             _lib.check(L.pk_chrom_find_candidates(X._h, a, b, C.byref(ncand)))

@@ -177,3 +177,81 @@ def test_errors_are_loud():
     n = C.c_int64()
     assert L.pk_chrom_find_candidates(h, 0, 500, C.byref(n)) == -4         # PK_ESTATE: nothing uploaded
     L.pk_chrom_destroy(h)
+
+
+def test_upload_paths_agree():
+    """Order-free scatter path, sorted (tiled) path and direct CSR upload build the same
+    band: identical expected curve, candidates and records; a false PK_PIXELS_SORTED
+    promise is reported."""
+    from peakachu_b200 import _lib
+    from peakachu_b200.scoreUtils import Chromosome
+    case = Case("tiny")
+    cfg = case.cfg
+    ch = case.chroms[0]
+    kw = dict(lower=cfg["lower"], upper=cfg["upper"], cname="chr1", res=cfg["res"], width=cfg["w"])
+    A = Chromosome.from_pixels(ch.bin1, ch.bin2, ch.count, ch.weights, ch.n, case.forest, sorted_pixels=True, **kw)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(ch.bin1.size)
+    B = Chromosome.from_pixels(ch.bin1[perm], ch.bin2[perm], ch.count[perm], ch.weights, ch.n, case.forest,
+                               sorted_pixels=False, **kw)
+    assert np.array_equal(A.exp_arr, B.exp_arr) and np.array_equal(A.exp_arr, case.z["chr1/exp_arr"])
+    assert np.array_equal(A.ridx, B.ridx) and np.array_equal(A.cidx, B.cidx)
+    ra, rb = A.score_records(cfg["min_prob"]), B.score_records(cfg["min_prob"])
+    assert all(np.array_equal(u, v) for u, v in zip(ra, rb))
+    # CSR upload through the C ABI
+    L = _lib.lib()
+    h = C.c_void_p()
+    _lib.check(L.pk_chrom_create(0, ch.n, cfg["w"], cfg["lower"], cfg["upper"], 1, None, C.byref(h)))
+    rowptr = np.searchsorted(ch.bin1, np.arange(ch.n + 1)).astype(np.int64)
+    b2, cnt, w = (np.ascontiguousarray(a) for a in (ch.bin2, ch.count, ch.weights))
+    _lib.check(L.pk_chrom_upload_csr(h, _lib.ptr(rowptr), _lib.ptr(b2), _lib.ptr(cnt), b2.size, _lib.ptr(w), _lib.PK_MEM_HOST))
+    _lib.check(L.pk_chrom_fit_expected(h))
+    e = np.zeros(A.exp_arr.size)
+    _lib.check(L.pk_chrom_get_expected(h, _lib.ptr(e, _lib.c_f64p)))
+    assert np.array_equal(e, A.exp_arr)
+    L.pk_chrom_destroy(h)
+    # a broken promise
+    with pytest.raises(_lib.PKError, match="not sorted"):
+        X = Chromosome.from_pixels(ch.bin1[perm], ch.bin2[perm], ch.count[perm], ch.weights, ch.n, case.forest,
+                                   sorted_pixels=True, **kw)
+        X.exp_arr
+    A.close(); B.close()
+
+
+def test_candidate_buffer_overflow_is_replayed():
+    """min_prob below every probability and a map where far more than 1/8 of the band
+    passes the Poisson filter: the device-side capacity flag triggers a transparent redo."""
+    from peakachu_b200 import synth
+    from peakachu_b200.scoreUtils import Chromosome
+    from oracle import peakachu_oracle as po
+    case = Case("tiny")
+    rng = np.random.default_rng(3)
+    n = 300
+    # expected ~1 everywhere, but a third of the band carries a large count
+    xs, ds = np.meshgrid(np.arange(n), np.arange(0, 80), indexing="ij")
+    ok = xs + ds < n
+    b1, b2 = xs[ok].astype(np.int32), (xs + ds)[ok].astype(np.int32)
+    cnt = np.where(rng.random(b1.size) < 0.35, 40, 1).astype(np.int32)
+    order = np.lexsort((b2, b1))
+    b1, b2, cnt = b1[order], b2[order], cnt[order]
+    w = np.full(n, 1.0)
+    X = Chromosome.from_pixels(b1, b2, cnt, w, n, case.forest, lower=6, upper=60, cname="chr1", res=10000, width=5,
+                               sorted_pixels=True)
+    x, y, p, v = X.score_records(-1.0)
+    ch = synth.SynthChrom("chr1", n, b1, b2, cnt, w, np.zeros((0, 2), np.int64))
+    import tempfile, os
+    from peakachu_b200 import coolio
+    path = os.path.join(tempfile.mkdtemp(), "o.pkcool")
+    coolio.PKCool.write(path, [ch], 10000)
+    lib = coolio.Cooler(path)
+    M = po.tocsr(lib.matrix(balance="weight", sparse=True).fetch("chr1"))
+    raw = po.tocsr(lib.matrix(balance=False, sparse=True).fetch("chr1"))
+    O = po.Chromosome(M, model=case.model(), raw_M=raw, weights=w, lower=6, upper=60, cname="chr1", res=10000, width=5)
+    assert X.n_candidates == O.ridx.size and X.n_candidates > po.band_pixels(n, 6, 60, 5) // 8 + 4096 \
+        if hasattr(po, "band_pixels") else X.n_candidates == O.ridx.size
+    assert np.array_equal(X.ridx, O.ridx) and np.array_equal(X.cidx, O.cidx)
+    fea, clist = O.getwindow(np.stack([O.ridx, O.cidx], axis=1))
+    proba = po.forest_proba(case.forest, fea.astype(np.float32))
+    order = np.lexsort((clist[:, 1], clist[:, 0]))
+    assert np.array_equal(x, clist[order, 0]) and np.array_equal(y, clist[order, 1]) and np.array_equal(p, proba[order])
+    X.close()
