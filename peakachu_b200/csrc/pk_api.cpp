@@ -348,7 +348,6 @@ extern "C" int pk_chrom_create(int device, int32_t n_bins, int32_t width, int32_
     const size_t bandsz = (size_t)c->ND * (size_t)c->pitch;
     if ((r = dev_alloc(&c->d_band, bandsz)) || (r = dev_alloc(&c->d_w, (size_t)n_bins)) ||
         (r = dev_alloc(&c->d_valid, (size_t)n_bins)) || (r = dev_alloc(&c->d_scratch, bandsz)) ||
-        (r = dev_alloc(&c->d_leaf_start, (size_t)c->ND * c->LP)) || (r = dev_alloc(&c->d_leaf_sum, (size_t)c->ND * c->LP)) ||
         (r = dev_alloc(&c->d_diag_sum, (size_t)c->ND)) || (r = dev_alloc(&c->d_diag_cnt, (size_t)c->ND)) ||
         (r = dev_alloc(&c->d_exp, (size_t)c->ND)) || (r = dev_alloc(&c->d_bg, (size_t)c->ND)) ||
         (r = dev_alloc(&c->d_flags, 4)) || (r = dev_alloc(&c->d_counters, 4)) || (r = dev_alloc(&c->d_ncand, 2)) ||
@@ -368,7 +367,7 @@ extern "C" int pk_chrom_destroy(pk_chrom* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream); else cudaDeviceSynchronize();
     dev_free(c->d_band); dev_free(c->d_w); dev_free(c->d_valid); dev_free(c->d_scratch);
-    dev_free(c->d_leaf_start); dev_free(c->d_leaf_sum); dev_free(c->d_diag_sum); dev_free(c->d_diag_cnt);
+    dev_free(c->d_diag_sum); dev_free(c->d_diag_cnt);
     dev_free(c->d_exp); dev_free(c->d_bg); dev_free(c->d_flags); dev_free(c->d_counters); dev_free(c->d_ncand);
     dev_free(c->d_rowptr);
     dev_free(c->d_b1); dev_free(c->d_b2); dev_free(c->d_cnt);
@@ -533,7 +532,11 @@ static int read_flags(pk_chrom* c, int32_t flags[4]) {
         pk_set_error("pixels were passed with PK_PIXELS_SORTED but are not sorted by (bin1, bin2) with bin1 <= bin2");
         return PK_EINVAL;
     }
-    if (flags[2]) {
+    if (flags[2] & 2) {
+        pk_set_error("chromosome too long for the per-diagonal sum tables (more than ~116k bins)");
+        return PK_EUNSUPPORTED;
+    }
+    if (flags[2] & 1) {
         pk_set_error("expected curve: no distance has a positive mean (reference raises in IsotonicRegression.fit)");
         return PK_EINVAL;
     }

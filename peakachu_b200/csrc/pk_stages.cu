@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(256) k_check_sorted(const int32_t* __restrict_
 //     then a sequential tail) is evaluated leaf-parallel, combined by one thread.
 // ---------------------------------------------------------------------------
 #define PK_DS_THREADS 512
-#define PK_DS_LEAFCAP 3072
+#define PK_DS_CAP 2048          // leaves per diagonal handled in shared memory (n up to ~116k bins)
+#define PK_DS_LEVELS 14
 
 __device__ double pk_leaf_sum(const double* __restrict__ a, int n) {
     if (n < 8) {
@@ -110,106 +111,145 @@ __device__ double pk_leaf_sum(const double* __restrict__ a, int n) {
     return res;
 }
 
-// leaves of numpy's recursion over [0, n), in order; returns their number
-__device__ int pk_enumerate_leaves(int n, int32_t* leaf_start, int cap) {
-    int stack_s[40], stack_n[40];
-    int sp = 0, nl = 0;
-    stack_s[0] = 0; stack_n[0] = n; sp = 1;
-    while (sp > 0) {
-        --sp;
-        const int s = stack_s[sp], m = stack_n[sp];
-        if (m <= 128) { if (nl < cap) leaf_start[nl] = s; ++nl; continue; }
-        int n2 = m / 2;
-        n2 -= n2 % 8;
-        stack_s[sp] = s + n2; stack_n[sp] = m - n2; ++sp;     // right, popped second
-        stack_s[sp] = s;      stack_n[sp] = n2;     ++sp;     // left, popped first
-    }
-    if (nl < cap) leaf_start[nl] = n;
-    return nl;
-}
-
-// combine leaf sums along the same recursion (left + right), iteratively
-__device__ double pk_combine(int n, const double* leaf_sum) {
-    int st_n[40]; unsigned char st_state[40]; double st_val[40];
-    int sp = 0, li = 0;
-    st_n[0] = n; st_state[0] = 0; sp = 1;
-    double ret = 0.0;
-    while (sp > 0) {
-        const int top = sp - 1;
-        const int m = st_n[top];
-        if (m <= 128) { ret = leaf_sum[li++]; --sp; continue; }
-        int n2 = m / 2;
-        n2 -= n2 % 8;
-        if (st_state[top] == 0) {
-            st_state[top] = 1;
-            st_n[sp] = n2; st_state[sp] = 0; ++sp;
-        } else if (st_state[top] == 1) {
-            st_val[top] = ret;
-            st_state[top] = 2;
-            st_n[sp] = m - n2; st_state[sp] = 0; ++sp;
-        } else {
-            ret = __dadd_rn(st_val[top], ret);
-            --sp;
-        }
-    }
-    return ret;
-}
+// numpy's recursion, one level at a time, all threads: segments (start, size) of level l
+// become those of level l+1 (a segment of more than 128 elements splits into
+// n2 = m/2 - (m/2)%8 and the rest, others are carried over), order preserved. The split
+// bitmask of every level is kept so that the sums can be combined back up the same tree.
+struct DiagSmem {
+    int32_t seg_s[2][PK_DS_CAP];
+    int32_t seg_m[2][PK_DS_CAP];
+    double val[2][PK_DS_CAP];
+    uint32_t split[PK_DS_LEVELS][PK_DS_CAP / 32];
+    uint16_t wpre[PK_DS_LEVELS][PK_DS_CAP / 32];    // splits in the words before this one
+    int32_t nseg[PK_DS_LEVELS + 1];
+    int32_t wcnt[PK_DS_THREADS / 32];
+};
 
 __global__ void __launch_bounds__(PK_DS_THREADS) k_diag_sums(
     const int32_t* __restrict__ band, const double* __restrict__ w, const uint8_t* __restrict__ valid,
     int n, long long pitch, int balanced, double* __restrict__ scratch,
-    int32_t* __restrict__ g_leaf_start, double* __restrict__ g_leaf_sum, long long LP,
-    double* __restrict__ out_sum, long long* __restrict__ out_cnt) {
+    double* __restrict__ out_sum, long long* __restrict__ out_cnt, int32_t* __restrict__ flags) {
     constexpr int NWARP = PK_DS_THREADS / 32;
+    extern __shared__ __align__(16) unsigned char ds_raw[];
+    DiagSmem& sm = *reinterpret_cast<DiagSmem*>(ds_raw);
     const int d = blockIdx.x;
     const int len = n - d;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    __shared__ int s_wcnt[NWARP], s_nleaf;
-    __shared__ int32_t s_leaf_start[PK_DS_LEAFCAP + 1];
-    __shared__ double s_leaf_sum[PK_DS_LEAFCAP];
     double* sc = scratch + (long long)d * pitch;
     const int32_t* row = band + (long long)d * pitch;
-    // slice of this warp: multiple of 32 elements
-    const int per = len > 0 ? (((len + NWARP - 1) / NWARP + 31) & ~31) : 0;
+    // ---- compaction: slice of this warp, multiple of 128 elements ----
+    const int per = len > 0 ? (((len + NWARP - 1) / NWARP + 127) & ~127) : 0;
     const int xb = wid * per, xe = min(len, xb + per);
     int cntw = 0;
-    for (int x0 = xb; x0 < xe; x0 += 32) {
-        const int x = x0 + lane;
-        const bool f = (x < xe) && valid[x] && valid[x + d];
-        cntw += __popc(__ballot_sync(0xffffffffu, f));
+    for (int x0 = xb; x0 < xe; x0 += 128) {
+        bool f[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = x0 + j * 32 + lane;
+            f[j] = (x < xe) && valid[x] && valid[x + d];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cntw += __popc(__ballot_sync(0xffffffffu, f[j]));
     }
-    if (lane == 0) s_wcnt[wid] = cntw;
+    if (lane == 0) sm.wcnt[wid] = cntw;
     __syncthreads();
     int base = 0, nd = 0;
 #pragma unroll
     for (int k = 0; k < NWARP; ++k) {
-        const int t = s_wcnt[k];
+        const int t = sm.wcnt[k];
         if (k < wid) base += t;
         nd += t;
     }
-    for (int x0 = xb; x0 < xe; x0 += 32) {
-        const int x = x0 + lane;
-        const bool f = (x < xe) && valid[x] && valid[x + d];
-        const unsigned bal = __ballot_sync(0xffffffffu, f);
-        if (f) sc[base + __popc(bal & ((1u << lane) - 1u))] =
-                   pk_value(row[x], balanced ? w[x] : 0.0, balanced ? w[x + d] : 0.0, balanced);
-        base += __popc(bal);
+    for (int x0 = xb; x0 < xe; x0 += 128) {
+        bool f[4]; int c[4]; double wa[4], wb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = x0 + j * 32 + lane;
+            f[j] = (x < xe) && valid[x] && valid[x + d];
+            c[j] = f[j] ? row[x] : 0;
+            wa[j] = (f[j] && balanced) ? w[x] : 0.0;
+            wb[j] = (f[j] && balanced) ? w[x + d] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned bal = __ballot_sync(0xffffffffu, f[j]);
+            if (f[j]) sc[base + __popc(bal & ((1u << lane) - 1u))] = pk_value(c[j], wa[j], wb[j], balanced);
+            base += __popc(bal);
+        }
     }
-    __syncthreads();                       // scratch row complete (block-scope visibility)
-    int32_t* ls = s_leaf_start;
-    double* lsum = s_leaf_sum;
-    if (tid == 0) {
-        int nl = pk_enumerate_leaves(nd, s_leaf_start, PK_DS_LEAFCAP);
-        if (nl > PK_DS_LEAFCAP) nl = -pk_enumerate_leaves(nd, g_leaf_start + (long long)d * LP, (int)LP - 1);
-        s_nleaf = nl;
+    // ---- leaf table, level by level ----
+    if (tid == 0) { sm.seg_s[0][0] = 0; sm.seg_m[0][0] = nd; sm.nseg[0] = 1; }
+    __syncthreads();                       // also: scratch row complete (block-scope visibility)
+    int cur = 0, L = 0;
+    bool overflow = false;
+    for (;; ++L) {
+        const int ns = sm.nseg[L];
+        const int nw = (ns + 31) / 32;
+        // split mask of this level
+        for (int i0 = wid * 32; i0 < nw * 32; i0 += PK_DS_THREADS) {
+            const int i = i0 + lane;
+            const bool sp = (i < ns) && sm.seg_m[cur][i] > 128;
+            const unsigned bal = __ballot_sync(0xffffffffu, sp);
+            if (lane == 0) sm.split[L][i0 >> 5] = bal;
+        }
+        __syncthreads();
+        if (wid == 0) {                     // exclusive prefix of the per-word split counts
+            int carry = 0;
+            for (int w0 = 0; w0 < nw; w0 += 32) {
+                const int wi = w0 + lane;
+                const int cnt = wi < nw ? __popc(sm.split[L][wi]) : 0;
+                int x = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+                if (wi < nw) sm.wpre[L][wi] = (uint16_t)(carry + x - cnt);
+                carry += __shfl_sync(0xffffffffu, x, 31);
+            }
+            if (lane == 0) sm.nseg[L + 1] = ns + carry;
+        }
+        __syncthreads();
+        const int ns_next = sm.nseg[L + 1];
+        if (ns_next == ns) break;           // nothing split: level L holds the leaves
+        if (ns_next > PK_DS_CAP || L + 1 >= PK_DS_LEVELS) { overflow = true; break; }
+        for (int i = tid; i < ns; i += PK_DS_THREADS) {
+            const uint32_t word = sm.split[L][i >> 5];
+            const int pos = i + sm.wpre[L][i >> 5] + __popc(word & ((1u << (i & 31)) - 1u));
+            const int s0 = sm.seg_s[cur][i], m = sm.seg_m[cur][i];
+            if ((word >> (i & 31)) & 1u) {
+                int n2 = m / 2;
+                n2 -= n2 % 8;
+                sm.seg_s[cur ^ 1][pos] = s0;          sm.seg_m[cur ^ 1][pos] = n2;
+                sm.seg_s[cur ^ 1][pos + 1] = s0 + n2; sm.seg_m[cur ^ 1][pos + 1] = m - n2;
+            } else {
+                sm.seg_s[cur ^ 1][pos] = s0; sm.seg_m[cur ^ 1][pos] = m;
+            }
+        }
+        __syncthreads();
+        cur ^= 1;
     }
+    if (overflow) {                         // diagonal longer than the shared-memory tables: refuse loudly
+        if (tid == 0) { atomicOr(&flags[2], 2); out_sum[d] = CUDART_NAN; out_cnt[d] = nd; }
+        return;
+    }
+    // ---- leaf sums (8 strided accumulators + tail), one leaf per thread ----
+    const int nl = sm.nseg[L];
+    int vc = 0;
+    for (int l = tid; l < nl; l += PK_DS_THREADS) sm.val[vc][l] = pk_leaf_sum(sc + sm.seg_s[cur][l], sm.seg_m[cur][l]);
     __syncthreads();
-    int nl = s_nleaf;
-    if (nl < 0) { nl = -nl; ls = g_leaf_start + (long long)d * LP; lsum = g_leaf_sum + (long long)d * LP; }
-    for (int l = tid; l < nl; l += PK_DS_THREADS) lsum[l] = pk_leaf_sum(sc + ls[l], ls[l + 1] - ls[l]);
-    __syncthreads();
+    // ---- combine back up: left + right wherever a segment was split ----
+    for (int lv = L - 1; lv >= 0; --lv) {
+        const int ns = sm.nseg[lv];
+        for (int i = tid; i < ns; i += PK_DS_THREADS) {
+            const uint32_t word = sm.split[lv][i >> 5];
+            const int pos = i + sm.wpre[lv][i >> 5] + __popc(word & ((1u << (i & 31)) - 1u));
+            double v = sm.val[vc][pos];
+            if ((word >> (i & 31)) & 1u) v = __dadd_rn(v, sm.val[vc][pos + 1]);
+            sm.val[vc ^ 1][i] = v;
+        }
+        __syncthreads();
+        vc ^= 1;
+    }
     if (tid == 0) {
-        out_sum[d] = pk_combine(nd, lsum);
+        out_sum[d] = sm.val[vc][0];
         out_cnt[d] = nd;
     }
 }
@@ -220,108 +260,141 @@ __global__ void __launch_bounds__(PK_DS_THREADS) k_diag_sums(
 //     = PAVA on the reversed positive means (scipy, Busing 2022 Alg. 1), drop
 //     interior points of constant runs (sklearn), clip the query, numpy.interp.
 //     Same operations, same order as pk_host.cpp::pk_fit_expected_host, which the
-//     CPU tests pin against scikit-learn. One CTA; PAVA itself is sequential.
+//     CPU tests pin against scikit-learn. One CTA; only PAVA itself is sequential.
 // ---------------------------------------------------------------------------
 #define PK_FIT_MAX 1024
+#define PK_FIT_THREADS 256
 
-__global__ void __launch_bounds__(256) k_fit_expected(const double* __restrict__ sum, const long long* __restrict__ cnt,
-                                                      int len, double* __restrict__ out_exp, double* __restrict__ out_bg,
-                                                      int32_t* __restrict__ flags) {
-    __shared__ double s_e[PK_FIT_MAX];      // means, then PAVA values (reversed order)
+// ordered compaction helper: exclusive prefix of per-thread counts over the block
+__device__ __forceinline__ int pk_block_excl_scan(int v, int* s_warp, int* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    int pre = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < PK_FIT_THREADS / 32; ++k) { const int t = s_warp[k]; if (k < wid) pre += t; tot += t; }
+    __syncthreads();
+    *total = tot;
+    return pre + x - v;
+}
+
+__global__ void __launch_bounds__(PK_FIT_THREADS) k_fit_expected(
+    const double* __restrict__ sum, const long long* __restrict__ cnt, int len, double* __restrict__ out_exp,
+    double* __restrict__ out_bg, int32_t* __restrict__ flags) {
+    __shared__ double s_e[PK_FIT_MAX];      // PAVA values (reversed order)
     __shared__ double s_w[PK_FIT_MAX];
     __shared__ double s_kx[PK_FIT_MAX], s_ky[PK_FIT_MAX];
     __shared__ int s_xs[PK_FIT_MAX], s_r[PK_FIT_MAX + 1];
-    __shared__ int s_n, s_m;
+    __shared__ int s_warp[PK_FIT_THREADS / 32], s_nblk;
     const int tid = threadIdx.x;
-    for (int d = tid; d < len; d += 256) {
-        double e = 0.0;
-        if (cnt[d] > 10) e = __ddiv_rn(sum[d], (double)cnt[d]);
-        s_kx[d] = e;                        // borrowed as staging for the means
+    constexpr int PER = PK_FIT_MAX / PK_FIT_THREADS;       // consecutive distances per thread
+    // ---- means and ordered compaction of the positive ones ----
+    double e[PER];
+    int npos = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const int d = tid * PER + j;
+        e[j] = 0.0;
+        if (d < len && cnt[d] > 10) e[j] = __ddiv_rn(sum[d], (double)cnt[d]);
+        npos += e[j] > 0.0;
     }
+    int n;
+    int at = pk_block_excl_scan(npos, s_warp, &n);
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+        if (e[j] > 0.0) { s_xs[at] = tid * PER + j; s_ky[at] = e[j]; ++at; }
     __syncthreads();
-    if (tid == 0) {
-        int n = 0;
-        for (int d = 0; d < len; ++d)
-            if (s_kx[d] > 0.0) { s_xs[n] = d; s_ky[n] = s_kx[d]; ++n; }
-        s_n = n;
-        if (n > 0) {
-            // PAVA on the reversed values, unit weights
-            for (int i = 0; i < n; ++i) { s_e[i] = s_ky[n - 1 - i]; s_w[i] = 1.0; s_r[i] = -1; }
-            s_r[n] = -1;
-            s_r[0] = 0;
-            if (n > 1) s_r[1] = 1;
-            int b = 0;
-            double xb_prev = s_e[0], wb_prev = s_w[0];
-            for (int i = 1; i < n; ++i) {
-                b++;
-                double xb = s_e[i], wb = s_w[i];
-                if (xb_prev >= xb) {
-                    b--;
-                    double sb = __dadd_rn(__dmul_rn(wb_prev, xb_prev), __dmul_rn(wb, xb));
-                    wb = __dadd_rn(wb, wb_prev);
-                    xb = __ddiv_rn(sb, wb);
-                    while (i < n - 1 && xb >= s_e[i + 1]) {
-                        i++;
-                        sb = __dadd_rn(sb, __dmul_rn(s_w[i], s_e[i]));
-                        wb = __dadd_rn(wb, s_w[i]);
-                        xb = __ddiv_rn(sb, wb);
-                    }
-                    while (b > 0 && s_e[b - 1] >= xb) {
-                        b--;
-                        sb = __dadd_rn(sb, __dmul_rn(s_w[b], s_e[b]));
-                        wb = __dadd_rn(wb, s_w[b]);
-                        xb = __ddiv_rn(sb, wb);
-                    }
-                }
-                s_e[b] = xb_prev = xb;
-                s_w[b] = wb_prev = wb;
-                s_r[b + 1] = i + 1;
-            }
-            int f = n - 1;
-            for (int k = b; k >= 0; --k) {
-                const int t = s_r[k];
-                const double xk = s_e[k];
-                for (int i = f; i >= t; --i) s_e[i] = xk;
-                f = t - 1;
-            }
-            // knots: first, last, and every point that differs from a neighbour (in forward order)
-            int m = 0;
-            for (int i = 0; i < n; ++i) {
-                const double yi = s_e[n - 1 - i];
-                bool keep = (i == 0 || i == n - 1);
-                if (!keep) keep = (yi != s_e[n - i]) || (yi != s_e[n - 2 - i]);
-                if (keep) { s_kx[m] = (double)s_xs[i]; s_ky[m] = yi; ++m; }
-            }
-            s_m = m;
-        } else {
-            atomicOr(&flags[2], 1);         // no positive mean: the reference raises here
-        }
-    }
-    __syncthreads();
-    const int n = s_n, m = s_m;
     if (n == 0) {
-        for (int d = tid; d < len; d += 256) { out_exp[d] = CUDART_NAN; out_bg[d] = CUDART_NAN; }
+        if (tid == 0) atomicOr(&flags[2], 1);      // no positive mean: the reference raises here
+        for (int d = tid; d < len; d += PK_FIT_THREADS) { out_exp[d] = CUDART_NAN; out_bg[d] = CUDART_NAN; }
         return;
     }
+    for (int i = tid; i < n; i += PK_FIT_THREADS) { s_e[i] = s_ky[n - 1 - i]; s_w[i] = 1.0; }
+    __syncthreads();
+    // ---- PAVA on the reversed values (sequential; the block top lives in registers) ----
+    if (tid == 0) {
+        s_r[0] = 0;
+        s_r[1] = 1;
+        int b = 0;
+        double xb_prev = s_e[0], wb_prev = 1.0;
+        for (int i = 1; i < n; ++i) {
+            b++;
+            double xb = s_e[i], wb = 1.0;
+            if (xb_prev >= xb) {
+                b--;
+                double sb = __dadd_rn(__dmul_rn(wb_prev, xb_prev), __dmul_rn(wb, xb));
+                wb = __dadd_rn(wb, wb_prev);
+                xb = __ddiv_rn(sb, wb);
+                while (i < n - 1 && xb >= s_e[i + 1]) {
+                    i++;
+                    sb = __dadd_rn(sb, __dmul_rn(1.0, s_e[i]));
+                    wb = __dadd_rn(wb, 1.0);
+                    xb = __ddiv_rn(sb, wb);
+                }
+                while (b > 0 && s_e[b - 1] >= xb) {
+                    b--;
+                    sb = __dadd_rn(sb, __dmul_rn(s_w[b], s_e[b]));
+                    wb = __dadd_rn(wb, s_w[b]);
+                    xb = __ddiv_rn(sb, wb);
+                }
+            }
+            s_e[b] = xb_prev = xb;
+            s_w[b] = wb_prev = wb;
+            s_r[b + 1] = i + 1;
+        }
+        s_nblk = b + 1;
+    }
+    __syncthreads();
+    // ---- expand the blocks into the forward-ordered fit (s_kx borrowed as yf[]) ----
+    const int nblk = s_nblk;
+    for (int k = tid; k < nblk; k += PK_FIT_THREADS) {
+        const double xk = s_e[k];
+        for (int i = s_r[k]; i < s_r[k + 1]; ++i) s_kx[n - 1 - i] = xk;
+    }
+    __syncthreads();
+    // ---- knots: first, last, and every point that differs from a neighbour ----
+    double yv[PER]; int xv[PER]; int nk = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const int i = tid * PER + j;
+        bool keep = false;
+        if (i < n) {
+            const double yi = s_kx[i];
+            keep = (i == 0 || i == n - 1) || (yi != s_kx[i - 1]) || (yi != s_kx[i + 1]);
+            yv[j] = yi; xv[j] = s_xs[i];
+        }
+        if (!keep) xv[j] = -1;
+        nk += keep;
+    }
+    int m;
+    int kat = pk_block_excl_scan(nk, s_warp, &m);      // (its barriers also order the reads of s_kx above)
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+        if (xv[j] >= 0) { s_e[kat] = (double)xv[j]; s_w[kat] = yv[j]; ++kat; }   // knots: x in s_e, y in s_w
+    __syncthreads();
     const double xmin = (double)s_xs[0], xmax = (double)s_xs[n - 1];
-    for (int d = tid; d < len; d += 256) {
+    for (int d = tid; d < len; d += PK_FIT_THREADS) {
         const double T = fmin(fmax((double)d, xmin), xmax);
         double v;
         if (m == 1) {
-            v = s_ky[0];
+            v = s_w[0];
         } else {
             int lo = 0, hi = m;              // upper_bound: first knot > T
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (s_kx[mid] <= T) lo = mid + 1; else hi = mid;
+                if (s_e[mid] <= T) lo = mid + 1; else hi = mid;
             }
             int j = lo - 1;
             j = j < 0 ? 0 : (j > m - 1 ? m - 1 : j);
-            if (j == m - 1 || s_kx[j] == T) {
-                v = s_ky[j];
+            if (j == m - 1 || s_e[j] == T) {
+                v = s_w[j];
             } else {
-                const double slope = __ddiv_rn(__dsub_rn(s_ky[j + 1], s_ky[j]), __dsub_rn(s_kx[j + 1], s_kx[j]));
-                v = __dadd_rn(__dmul_rn(slope, __dsub_rn(T, s_kx[j])), s_ky[j]);
+                const double slope = __ddiv_rn(__dsub_rn(s_w[j + 1], s_w[j]), __dsub_rn(s_e[j + 1], s_e[j]));
+                v = __dadd_rn(__dmul_rn(slope, __dsub_rn(T, s_e[j])), s_w[j]);
             }
         }
         out_exp[d] = v;
@@ -500,9 +573,14 @@ int pk_launch_rowptr(pk_chrom* c, const int32_t* b1, const int32_t* b2, int64_t 
 }
 
 int pk_launch_diag_sums(pk_chrom* c) {
-    k_diag_sums<<<c->ND, PK_DS_THREADS, 0, c->stream>>>(c->d_band, c->d_w, c->d_valid, c->n, c->pitch, c->balanced,
-                                                        c->d_scratch, c->d_leaf_start, c->d_leaf_sum, c->LP, c->d_diag_sum,
-                                                        c->d_diag_cnt);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PK_CUDA(cudaFuncSetAttribute(k_diag_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiagSmem)));
+        attr_set = true;
+    }
+    k_diag_sums<<<c->ND, PK_DS_THREADS, sizeof(DiagSmem), c->stream>>>(c->d_band, c->d_w, c->d_valid, c->n, c->pitch,
+                                                                       c->balanced, c->d_scratch, c->d_diag_sum,
+                                                                       c->d_diag_cnt, c->d_flags);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
@@ -510,7 +588,7 @@ int pk_launch_diag_sums(pk_chrom* c) {
 bool pk_fit_on_device_supported(int len) { return len <= PK_FIT_MAX; }
 
 int pk_launch_fit_expected(pk_chrom* c) {
-    k_fit_expected<<<1, 256, 0, c->stream>>>(c->d_diag_sum, c->d_diag_cnt, c->ND, c->d_exp, c->d_bg, c->d_flags);
+    k_fit_expected<<<1, PK_FIT_THREADS, 0, c->stream>>>(c->d_diag_sum, c->d_diag_cnt, c->ND, c->d_exp, c->d_bg, c->d_flags);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }

@@ -1,0 +1,70 @@
+"""The N > 1 host path of score_genome on CPU: two gloo ranks take their share of the
+plan (chromosomes and band row tiles), "score" it (records cut from the reference's
+golden bedpe), rank 0 gathers on the host and must reproduce the file byte for byte."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from peakachu_b200 import shard
+from tests.cases import GOLDEN
+
+
+def _records():
+    rec = {}
+    for line in open(os.path.join(GOLDEN, "genome.bedpe")):
+        p = line.split("\t")
+        key = p[0][3:]
+        rec.setdefault(key, []).append((int(p[1]) // 10000, int(p[4]) // 10000, float(p[6]), float(p[7])))
+    return {k: np.array(v) for k, v in rec.items()}
+
+
+SIZES = {"1": 700, "2": 450, "X": 520}
+
+
+def _fake_units(units, rec):
+    out = {}
+    for key, a, b in units:
+        r = rec[key]
+        sel = r[(r[:, 0] >= a) & (r[:, 0] < b)]
+        out.setdefault(key, []).append(dict(
+            row_begin=a, whole=(a == 0 and b == SIZES[key]), x=sel[:, 0].astype(np.int32), y=sel[:, 1].astype(np.int32),
+            p=sel[:, 2].copy(), v=sel[:, 3].copy(), batch=np.zeros(len(sel), np.int32),
+            batch_windows=np.array([max(len(sel), 2)], np.int64), n_candidates=len(sel)))
+    return out
+
+
+def _worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rec = _records()
+    queue = ["1", "2", "X"]
+    asg = shard.plan(SIZES, world, 6, 80, 5)
+    assert any(len({k for k, _, _ in u}) for u in asg)
+    mine = _fake_units(asg[rank], rec)
+    gathered = shard.gather_to_rank0(mine, rank, world)
+    if rank == 0:
+        text = shard.assemble_text(queue, gathered, 10000)
+        with open(os.path.join(tmp, "out.bedpe"), "w") as fh:
+            for k in queue:
+                fh.write(text[k])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_reproduces_bedpe(tmp_path):
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert open(os.path.join(str(tmp_path), "out.bedpe")).read() == open(os.path.join(GOLDEN, "genome.bedpe")).read()
+
+
+def test_plan_splits_large_chromosome_into_row_tiles():
+    asg = shard.plan({"1": 24926, "21": 4813}, 4, 6, 300, 5)
+    tiles = sorted((a, b) for u in asg for k, a, b in u if k == "1")
+    assert len(tiles) == 4 and tiles[0][0] == 0 and tiles[-1][1] == 24926
+    assert all(t0[1] == t1[0] for t0, t1 in zip(tiles, tiles[1:]))
