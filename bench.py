@@ -41,7 +41,7 @@ WORKLOADS = {
     "c1": dict(n=2000, res=10000, lower=6, upper=300, w=5, forest="c2", depth=300.0, band=330,
                desc="score_chromosome 2,000-bin synthetic 10 kb (w=5, l=6, u=300, 100-tree RF)"),
 }
-KERNELS_PER_STEP = 10  # check_sorted, rowptr, band_csr, diag_sums, fit_expected, cand_mark, scan2, cand_write, score_fused, emit
+KERNELS_PER_STEP = 8   # band_csr, diag_sums, fit_expected, cand_mark, scan2, cand_write, score_fused, emit
 
 
 def band_pixels(n, lower, upper, w):
@@ -215,18 +215,19 @@ def main():
     px = band_pixels(n, wl["lower"], wl["upper"], w)
     nnz = ch.bin1.size
 
-    # ---- device-resident inputs (torch tensors only as buffers) ----
+    # ---- device-resident inputs (torch tensors only as buffers): cooler's CSR columns ----
     stream = torch.cuda.Stream(device=local)
-    d_b1 = torch.from_numpy(ch.bin1).cuda(); d_b2 = torch.from_numpy(ch.bin2).cuda()
+    rowptr = np.searchsorted(ch.bin1, np.arange(n + 1)).astype(np.int64)      # indexes/bin1_offset
+    d_rp = torch.from_numpy(rowptr).cuda(); d_b2 = torch.from_numpy(ch.bin2).cuda()
     d_cnt = torch.from_numpy(ch.count).cuda(); d_w = torch.from_numpy(ch.weights).cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     h = C.c_void_p()
     _lib.check(L.pk_chrom_create(local, n, w, wl["lower"], wl["upper"], 1, C.c_void_p(stream.cuda_stream), C.byref(h)))
 
     def device_step():
-        _lib.check(L.pk_chrom_upload_pixels(h, C.c_void_p(d_b1.data_ptr()), C.c_void_p(d_b2.data_ptr()),
-                                            C.c_void_p(d_cnt.data_ptr()), nnz, C.c_void_p(d_w.data_ptr()),
-                                            _lib.PK_MEM_DEVICE | _lib.PK_PIXELS_SORTED))
+        _lib.check(L.pk_chrom_upload_csr(h, C.c_void_p(d_rp.data_ptr()), C.c_void_p(d_b2.data_ptr()),
+                                         C.c_void_p(d_cnt.data_ptr()), nnz, C.c_void_p(d_w.data_ptr()),
+                                         _lib.PK_MEM_DEVICE))
         _lib.check(L.pk_chrom_fit_expected(h))
         _lib.check(L.pk_chrom_find_candidates(h, 0, n, None))
         _lib.check(L.pk_chrom_score(h, forest.handle, 0.5))
@@ -262,11 +263,17 @@ def main():
     nrec, ncand, nwin = C.c_int64(), C.c_int64(), C.c_int64()
     _lib.check(L.pk_chrom_result_count(h, C.byref(nrec), C.byref(ncand), C.byref(nwin)))
 
-    # ---- end to end through the public API with host buffers ----
+    # ---- end to end through the public API with host buffers (pinned, as a reader would fill them) ----
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    p_rp, p_b2, p_cnt, p_w = pinned(rowptr), pinned(ch.bin2), pinned(ch.count), pinned(ch.weights)
+
     def e2e_step():
-        X = Chromosome.from_pixels(ch.bin1, ch.bin2, ch.count, ch.weights, n, forest, lower=wl["lower"],
-                                   upper=wl["upper"], cname="chr1", res=wl["res"], width=w, device=local,
-                                   sorted_pixels=True)
+        X = Chromosome.from_csr(p_rp.numpy(), p_b2.numpy(), p_cnt.numpy(), p_w.numpy(), n, forest,
+                                lower=wl["lower"], upper=wl["upper"], cname="chr1", res=wl["res"], width=w,
+                                device=local)
         out = X.score_records(0.5)
         X.close()
         return out
@@ -280,7 +287,7 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
-    h2d = 12 * nnz + 8 * n
+    h2d = 8 * nnz + 8 * (n + 1) + 8 * n
     d2h = 24 * int(rec[0].size)
 
     # max over ranks
@@ -308,7 +315,7 @@ def main():
     # algorithmic bytes of one chromosome: pixel columns once, weights,
     # expected curve, emitted records, forest tables once
     forest_bytes = 8 * flat.n_nodes
-    bytes_alg = 12 * nnz + 8 * n + 8 * (wl["upper"] + 2 * w + 1) + 24 * int(nrec.value) + forest_bytes
+    bytes_alg = 12 * nnz + 8 * n + 8 * (wl["upper"] + 2 * w + 1) + 24 * int(nrec.value) + forest_bytes   # SURVEY 8(d)
     dom = max(stage, key=stage.get)
     dom_ms = stage[dom]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": bytes_alg / (dom_ms * 1e-3) / 1e9, "peak": peak_gbs,

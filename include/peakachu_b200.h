@@ -146,6 +146,10 @@ int pk_poisson_critical_mu(int32_t k_max, double* out /* [k_max+1] */);
  * IsotonicRegression(increasing=False, out_of_bounds='clip') of utils.py:173-176) */
 int pk_fit_expected(const double* sum, const int64_t* cnt, int32_t len, double* out_exp);
 
+/* device self-test: the reciprocal-based division used by the feature kernel against IEEE
+ * division on n pseudo-random / adversarial operand pairs; *mismatches must come back 0 */
+int pk_selftest_divide(int device, int64_t n, uint64_t seed, int64_t* mismatches);
+
 /* return the library's cached device blocks (of destroyed handles) to the driver */
 int pk_release_memory(void);
 

@@ -96,6 +96,17 @@ class PKCool:
         b2 = (self.bin2_id[lo:hi] - off).astype(np.int32)
         return b1, b2, np.ascontiguousarray(self.count[lo:hi], dtype=np.int32)
 
+    def upper_pixels_csr(self, chrom: str):
+        """(bin1_offset int64[n+1] rebased to 0, bin2 int32, count int32): cooler's
+        ``indexes/bin1_offset`` restricted to the chromosome plus its pixel columns."""
+        i = self._cid(chrom)
+        lo, hi = self._pix_lo[i], self._pix_hi[i]
+        off = self.chrom_offset[i]
+        n = self.nbins(chrom)
+        rp = np.searchsorted(self.bin1_id[lo:hi], np.arange(off, off + n + 1), side="left").astype(np.int64)
+        b2 = (self.bin2_id[lo:hi] - off).astype(np.int32)
+        return rp, b2, np.ascontiguousarray(self.count[lo:hi], dtype=np.int32)
+
     def weights(self, chrom: str, name: str) -> np.ndarray:
         if name not in self.weight_columns:
             raise KeyError("no weight column %r in %s" % (name, self.path))

@@ -28,6 +28,17 @@ int pk_launch_emit(pk_chrom* c, double thre);
 int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant);
 bool pk_fused_supported(int w, int n_trees);
 
+int pk_run_selftest_divide(long long n, unsigned long long seed, long long* mismatches);
+
+extern "C" int pk_selftest_divide(int device, int64_t n, uint64_t seed, int64_t* mismatches) {
+    if (!mismatches || n < 0) { pk_set_error("pk_selftest_divide: bad argument"); return PK_EINVAL; }
+    PK_CUDA(cudaSetDevice(device));
+    long long m = 0;
+    PK_CHECK(pk_run_selftest_divide(n, seed, &m));
+    *mismatches = m;
+    return PK_OK;
+}
+
 // tuning knobs (pk_set_tuning): fused = -1 auto, 0 unfused kernels, 1 / 2 fused variants
 static int g_tune_fused = -1;
 

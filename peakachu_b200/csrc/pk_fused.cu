@@ -70,10 +70,23 @@ struct FusedCfg {
     static constexpr size_t scratch_bytes = (size_t)NW * 2 * F * 8;   // window scratch; reused for leaf hand-over
     static_assert(TPP == 1 || scratch_bytes >= 2 * 4 * (size_t)P * 8, "leaf hand-over does not fit the window scratch");
     static size_t total(int ND, int n_trees) {
-        return node_bytes + fea_bytes + (size_t)((ND + 1) & ~1) * 8 + scratch_bytes + (size_t)P * 4 +
+        return node_bytes + fea_bytes + 2 * (size_t)((ND + 1) & ~1) * 8 + scratch_bytes + (size_t)P * 4 +
                (size_t)n_trees * 4 + (size_t)((n_trees + 3) & ~3) + (size_t)((F + 1) & ~1) * 2 + (size_t)P + 64;
     }
 };
+
+// a / b, correctly rounded, from a correctly rounded reciprocal r = RN(1/b): two
+// residual corrections (q' = q + (a - b q) r with exact FMA residuals). The first makes q
+// faithful, the second is then correctly rounded (Markstein). Valid away from
+// overflow/underflow; callers take __ddiv_rn otherwise. Checked against __ddiv_rn on the
+// device by pk_selftest_divide.
+__device__ __forceinline__ double pk_div_r(double a, double b, double r) {
+    double q = __dmul_rn(a, r);
+    q = __fma_rn(__fma_rn(-b, q, a), r, q);
+    q = __fma_rn(__fma_rn(-b, q, a), r, q);
+    return q;
+}
+__device__ __forceinline__ bool pk_div_safe(double v) { return v >= 1e-100 && v <= 1e100; }   // false for NaN
 
 __device__ __forceinline__ void lds_node(uint32_t addr, uint2& nd) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nd.x), "=r"(nd.y) : "r"(addr));
@@ -117,7 +130,8 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
     float* s_fea = reinterpret_cast<float*>(smem_raw + Cfg::node_bytes);
     double* s_exp = reinterpret_cast<double*>(smem_raw + Cfg::node_bytes + Cfg::fea_bytes);
     const int ND = prm.ND, NDp = (ND + 1) & ~1;
-    double* s_V = s_exp + NDp;                                    // [NW][2][F] float64
+    double* s_rexp = s_exp + NDp;                                 // RN(1 / exp)
+    double* s_V = s_rexp + NDp;                                   // [NW][2][F] float64
     int32_t* s_idx = reinterpret_cast<int32_t*>(s_V + (size_t)NW * 2 * F);   // [P]
     uint32_t* s_root = reinterpret_cast<uint32_t*>(s_idx + P);    // [n_trees]
     uint8_t* s_depth = reinterpret_cast<uint8_t*>(s_root + prm.n_trees);     // [n_trees] (padded to 4)
@@ -125,7 +139,7 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
     uint8_t* s_nan = reinterpret_cast<uint8_t*>(s_lut + ((F + 1) & ~1));     // [P]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_nan + P) + 15) & ~(uintptr_t)15);
     double* s_lv = s_V;                                           // [2][4][P] leaf hand-over (phase B only)
-    __shared__ int s_nkept, s_take, s_done;
+    __shared__ int s_nkept, s_take, s_done, s_expbad;
     __shared__ long long s_start;
 
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -135,7 +149,14 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
     const bool resident = (G <= 2);
 
     // ---- one-time setup -----------------------------------------------------
-    for (int i = tid; i < ND; i += NT) s_exp[i] = prm.expv[i];
+    if (tid == 0) s_expbad = 0;
+    __syncthreads();
+    for (int i = tid; i < ND; i += NT) {
+        const double e = prm.expv[i];
+        s_exp[i] = e;
+        s_rexp[i] = __ddiv_rn(1.0, e);
+        if (!pk_div_safe(e)) s_expbad = 1;
+    }
     for (int i = tid; i < prm.n_trees; i += NT) { s_root[i] = prm.roots[i]; s_depth[i] = prm.depth[i]; }
     if (tid == 0) {
         // cells ordered by window diagonal (b - a), then along it: contiguous in the band
@@ -220,6 +241,7 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                 bool ok = cur.ok;
                 // balance the gathered counts and stage both windows in shared memory
                 int nz0 = 0, nz1 = 0;
+                bool odd = false;            // a value outside the range where pk_div_r is proven
                 {
                     const int x0 = __shfl_sync(0xffffffffu, x, 0), d0 = __shfl_sync(0xffffffffu, d, 0);
                     const int x1 = __shfl_sync(0xffffffffu, x, 16), d1 = __shfl_sync(0xffffffffu, d, 16);
@@ -241,6 +263,7 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                                              prm.balanced ? __ldg(prm.w + c) : 0.0, prm.balanced);
                             V0[(size_t)k * F + a * S + b] = v;
                             nzf = v != 0.0;
+                            odd |= nzf && !pk_div_safe(v);
                         }
                         const unsigned bal = __ballot_sync(0xffffffffu, nzf);
                         const unsigned m1 = __ballot_sync(0xffffffffu, k != 0);
@@ -251,6 +274,7 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                 // issue the next pair's loads now; they land while this pair is filtered
                 if (j0 + NW * 2 < take) pair_load(start, take, j0 + NW * 2, nxt);
                 __syncwarp();
+                const bool fastdiv = !__any_sync(0xffffffffu, odd) && !s_expbad;
                 if (ok && (double)(half ? nz1 : nz0) < (double)F * 0.1) ok = false;   // utils.py:225
                 if (ok) {
                     double s = 0.0;                                            // utils.py:228 (numba order)
@@ -276,7 +300,8 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                     for (int a = 0; a < S; ++a) {
                         int dd = d + h - a;
                         dd = dd < 0 ? -dd : dd;
-                        v[a] = __ddiv_rn(myV[a * S + h], s_exp[dd]);
+                        v[a] = fastdiv ? pk_div_r(myV[a * S + h], s_exp[dd], s_rexp[dd])
+                                       : __ddiv_rn(myV[a * S + h], s_exp[dd]);
                     }
 #pragma unroll
                     for (int a = 0; a < S; ++a) {
@@ -319,10 +344,13 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                 if (actk) {
                     if (has_nan) { mn = CUDART_NAN; mx = CUDART_NAN; }          // numba min/max propagate NaN
                     const double range = __dsub_rn(mx, mn);
+                    const bool fr = pk_div_safe(range) && mx <= 1e100;         // else: plain IEEE division
+                    const double rr = __ddiv_rn(1.0, range);
                     float* frow = s_fea + (size_t)slot * F + h * S;
 #pragma unroll
                     for (int b = 0; b < S; ++b) {
-                        const double q = __ddiv_rn(__dsub_rn(g[b], mn), range);   // utils.py:207
+                        const double num = __dsub_rn(g[b], mn);
+                        const double q = fr ? pk_div_r(num, range, rr) : __ddiv_rn(num, range);   // utils.py:207
                         fnan |= isnan(q);
                         frow[b] = __double2float_rn(q);
                     }
@@ -355,9 +383,16 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
             const bool warp_nan = __any_sync(0xffffffffu, mine && s_nan[pix]);
             double acc = 0.0;
             int lvpar = 0;
+            // one warp polls the mbarrier, the others wait at the CTA barrier (no spinning warps)
+            if (!resident || first_batch) {
+                if (wib == 0) {
+                    if (resident) { for (uint32_t q = 0; q < issued; ++q) mbar_wait(&s_bar[q & 1], 0); }
+                    else mbar_wait(&s_bar[consumed & 1], (consumed >> 1) & 1);
+                }
+                __syncthreads();
+            }
             for (int gi = 0; gi < G; ++gi) {
                 const uint32_t pos = resident ? (uint32_t)gi : consumed;
-                if (!resident || first_batch) mbar_wait(&s_bar[pos & 1], (pos >> 1) & 1);
                 const int4 grp = prm.groups[gi];
                 const uint32_t gbase = (uint32_t)grp.z;
                 const bool fits = grp.w > 0;                   // every tree of the group is fully staged
@@ -411,36 +446,32 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                             }
                         }
                     }
+                    // After the last chunk of a group the buffer is handed back: one barrier covers
+                    // "everyone is done with it", "the next group has landed" and the leaf hand-over.
+                    const bool rotate = !resident && (tc + CHUNK >= t_end);
+                    double* lvb = s_lv + (size_t)lvpar * 4 * P;
+                    if (TPP == 2 && sub == 1 && mine) { lvb[pix] = lv0; lvb[P + pix] = lv1; lvb[2 * P + pix] = lv2; lvb[3 * P + pix] = lv3; }
+                    if (rotate && wib == 0) mbar_wait(&s_bar[(consumed + 1) & 1], ((consumed + 1) >> 1) & 1);
+                    if (TPP == 2 || rotate) __syncthreads();
+                    if (rotate) {
+                        ++consumed;
+                        issue(issued); ++issued;     // refill the freed buffer with the group two positions ahead
+                    }
                     // ordered accumulation: trees tc .. tc+CHUNK-1 in estimator order
-                    if (TPP == 1) {
-                        if (mine) {
-                            acc = __dadd_rn(acc, lv0);
-                            if (e1) acc = __dadd_rn(acc, lv1);
-                            if (e2) acc = __dadd_rn(acc, lv2);
-                            if (e3) acc = __dadd_rn(acc, lv3);
-                        }
-                    } else {
-                        double* lvb = s_lv + (size_t)lvpar * 4 * P;
-                        if (sub == 1 && mine) { lvb[pix] = lv0; lvb[P + pix] = lv1; lvb[2 * P + pix] = lv2; lvb[3 * P + pix] = lv3; }
-                        __syncthreads();
-                        if (sub == 0 && mine) {
-                            acc = __dadd_rn(acc, lv0);
-                            if (e1) acc = __dadd_rn(acc, lv1);
-                            if (e2) acc = __dadd_rn(acc, lv2);
-                            if (e3) acc = __dadd_rn(acc, lv3);
+                    if (mine && sub == 0) {
+                        acc = __dadd_rn(acc, lv0);
+                        if (e1) acc = __dadd_rn(acc, lv1);
+                        if (e2) acc = __dadd_rn(acc, lv2);
+                        if (e3) acc = __dadd_rn(acc, lv3);
+                        if (TPP == 2) {
                             const int t4 = tc + 4;
                             if (t4 < t_end) acc = __dadd_rn(acc, lvb[pix]);
                             if (t4 + 1 < t_end) acc = __dadd_rn(acc, lvb[P + pix]);
                             if (t4 + 2 < t_end) acc = __dadd_rn(acc, lvb[2 * P + pix]);
                             if (t4 + 3 < t_end) acc = __dadd_rn(acc, lvb[3 * P + pix]);
                         }
-                        lvpar ^= 1;
                     }
-                }
-                if (!resident) {
-                    __syncthreads();                 // everyone is done with this buffer
-                    ++consumed;
-                    issue(issued); ++issued;         // refill it with the group two positions ahead
+                    lvpar ^= 1;
                 }
             }
             if (mine && sub == 0) prm.prob[s_idx[pix]] = __ddiv_rn(acc, (double)prm.n_trees);
@@ -495,3 +526,56 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant) {
 }
 
 bool pk_fused_supported(int w, int n_trees) { return (w == 5 || w == 7) && n_trees <= 2048; }
+
+// ---------------------------------------------------------------------------
+// self-test of pk_div_r against IEEE division (pk_selftest_divide)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pk_mix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+// random double with exponent in [-emax, emax] and a random / adversarial significand
+__device__ __forceinline__ double pk_rand_double(unsigned long long r, unsigned long long r2, int emax) {
+    unsigned long long mant = r & 0xFFFFFFFFFFFFFull;
+    const int mode = (int)(r2 & 7);
+    if (mode == 0) mant = 0;                                   // powers of two
+    else if (mode == 1) mant = 0xFFFFFFFFFFFFFull;             // all ones
+    else if (mode == 2) mant &= 0xFFFFF00000000ull;            // short significands
+    else if (mode == 3) mant |= 0xFFFFFFFFull;                 // long runs of ones
+    const int e = (int)((r2 >> 8) % (unsigned)(2 * emax + 1)) - emax;
+    return __longlong_as_double((long long)(((unsigned long long)(1023 + e) << 52) | mant));
+}
+__global__ void k_selftest_divide(long long n, unsigned long long seed, unsigned long long* mismatches) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long r0 = pk_mix64(seed + 4 * i), r1 = pk_mix64(seed + 4 * i + 1);
+        const unsigned long long r2 = pk_mix64(seed + 4 * i + 2), r3 = pk_mix64(seed + 4 * i + 3);
+        const double b = pk_rand_double(r0, r1, 100);
+        double a = pk_rand_double(r2, r3, 100);
+        const int kind = (int)((r3 >> 40) & 7);
+        if (kind == 0) a = b;                                                   // quotient 1
+        else if (kind == 1) a = __dmul_rn(b, (double)(1 + (r3 >> 48) % 1000));  // near-exact quotients
+        else if (kind == 2) a = __dmul_rn(b, pk_rand_double(r2, r3, 0) * 0.5);  // a in (b/2, b): the min-max case
+        else if (kind == 3) a = 0.0;
+        if (a != 0.0 && !(a >= 1e-200 && a <= 1e200)) continue;
+        const double q = pk_div_r(a, b, __ddiv_rn(1.0, b));
+        if (__double_as_longlong(q) != __double_as_longlong(__ddiv_rn(a, b))) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+int pk_run_selftest_divide(long long n, unsigned long long seed, long long* mismatches) {
+    unsigned long long* d = nullptr;
+    PK_CUDA(cudaMalloc((void**)&d, 8));
+    PK_CUDA(cudaMemset(d, 0, 8));
+    k_selftest_divide<<<148 * 8, 256>>>(n, seed, d);
+    PK_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    PK_CUDA(cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *mismatches = (long long)h;
+    return PK_OK;
+}

@@ -255,3 +255,12 @@ def test_candidate_buffer_overflow_is_replayed():
     order = np.lexsort((clist[:, 1], clist[:, 0]))
     assert np.array_equal(x, clist[order, 0]) and np.array_equal(y, clist[order, 1]) and np.array_equal(p, proba[order])
     X.close()
+
+
+def test_reciprocal_division_is_ieee_exact():
+    """pk_div_r (two FMA corrections of a*RN(1/b)) against __ddiv_rn on 2e9 operand pairs,
+    including quotient 1, near-exact quotients, all-ones significands and a in (b/2, b)."""
+    from peakachu_b200 import _lib
+    bad = C.c_int64(-1)
+    _lib.check(_lib.lib().pk_selftest_divide(0, 2_000_000_000, 12345, C.byref(bad)))
+    assert bad.value == 0
