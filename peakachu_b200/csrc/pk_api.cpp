@@ -353,12 +353,12 @@ extern "C" int pk_chrom_create(int device, int32_t n_bins, int32_t width, int32_
     c->lower = lo; c->upper = up; c->ND = up + 2 * width + 1;
     c->pitch = ((int64_t)n_bins + 31) / 32 * 32;
     c->balanced = balanced ? 1 : 0;
-    c->LP = c->pitch / 32 + 8;
     c->row_begin = 0; c->row_end = n_bins;
     int r = PK_OK;
     const size_t bandsz = (size_t)c->ND * (size_t)c->pitch;
     if ((r = dev_alloc(&c->d_band, bandsz)) || (r = dev_alloc(&c->d_w, (size_t)n_bins)) ||
-        (r = dev_alloc(&c->d_valid, (size_t)n_bins)) || (r = dev_alloc(&c->d_scratch, bandsz)) ||
+        (r = dev_alloc(&c->d_valid, (size_t)n_bins)) || (r = dev_alloc(&c->d_vbits, (size_t)n_bins / 32 + 4)) ||
+        (r = dev_alloc(&c->d_scratch, bandsz)) ||
         (r = dev_alloc(&c->d_diag_sum, (size_t)c->ND)) || (r = dev_alloc(&c->d_diag_cnt, (size_t)c->ND)) ||
         (r = dev_alloc(&c->d_exp, (size_t)c->ND)) || (r = dev_alloc(&c->d_bg, (size_t)c->ND)) ||
         (r = dev_alloc(&c->d_flags, 4)) || (r = dev_alloc(&c->d_counters, 4)) || (r = dev_alloc(&c->d_ncand, 2)) ||
@@ -377,7 +377,7 @@ extern "C" int pk_chrom_destroy(pk_chrom* c) {
     if (!c) return PK_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream); else cudaDeviceSynchronize();
-    dev_free(c->d_band); dev_free(c->d_w); dev_free(c->d_valid); dev_free(c->d_scratch);
+    dev_free(c->d_band); dev_free(c->d_w); dev_free(c->d_valid); dev_free(c->d_vbits); dev_free(c->d_scratch);
     dev_free(c->d_diag_sum); dev_free(c->d_diag_cnt);
     dev_free(c->d_exp); dev_free(c->d_bg); dev_free(c->d_flags); dev_free(c->d_counters); dev_free(c->d_ncand);
     dev_free(c->d_rowptr);
@@ -544,7 +544,7 @@ static int read_flags(pk_chrom* c, int32_t flags[4]) {
         return PK_EINVAL;
     }
     if (flags[2] & 2) {
-        pk_set_error("chromosome too long for the per-diagonal sum tables (more than ~116k bins)");
+        pk_set_error("chromosome too long for the per-diagonal sum tables (more than ~230k bins)");
         return PK_EUNSUPPORTED;
     }
     if (flags[2] & 1) {

@@ -73,10 +73,8 @@ struct pk_chrom {
     int32_t* d_band = nullptr;       // [ND][pitch] raw counts, diagonal-major
     double* d_w = nullptr;           // [n]
     uint8_t* d_valid = nullptr;      // [n]
+    uint32_t* d_vbits = nullptr;     // [ceil(n/32)] the same, one bit per bin
     double* d_scratch = nullptr;     // [ND][pitch] compacted diagonal values
-    int32_t* d_leaf_start = nullptr; // [ND][LP]
-    double* d_leaf_sum = nullptr;    // [ND][LP]
-    int64_t LP = 0;
     double* d_diag_sum = nullptr;    // [ND]
     long long* d_diag_cnt = nullptr; // [ND]
     double* d_exp = nullptr;         // [ND]

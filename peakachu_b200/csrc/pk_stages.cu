@@ -30,17 +30,32 @@ __global__ void __launch_bounds__(256) k_band_csr(
         const long long p0 = rowptr[x], p1 = rowptr[x + 1];
         const double wx = balanced ? w[x] : 0.0;
         bool any = false;
-        for (long long p = p0 + lane; p < p1; p += 32) {
-            const int y = b2[p], c = cnt[p];
-            if (c == 0 || y < x || y >= n) continue;
-            bool fin;
-            if (balanced) fin = isfinite(__dmul_rn(__dmul_rn(wx, w[y]), (double)c));
-            else fin = c > 0;
-            if (fin) { any = true; valid[y] = 1; }
-            const int d = y - x;
-            if (d < ND) {
-                atomicAdd(&s_tile[d * 33 + xl], c);     // duplicates are summed like utils.tocsr
-                cmax = max(cmax, c);
+        for (long long pb = p0; pb < p1; pb += 128) {
+            int y[4], c[4];
+            double wy[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long p = pb + j * 32 + lane;
+                y[j] = -1; c[j] = 0;
+                if (p < p1) { y[j] = b2[p]; c[j] = cnt[p]; }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (c[j] == 0 || y[j] < x || y[j] >= n) c[j] = 0;
+                wy[j] = (balanced && c[j] != 0) ? w[y[j]] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (c[j] == 0) continue;
+                bool fin;
+                if (balanced) fin = isfinite(__dmul_rn(__dmul_rn(wx, wy[j]), (double)c[j]));
+                else fin = c[j] > 0;
+                if (fin) { any = true; valid[y[j]] = 1; }
+                const int d = y[j] - x;
+                if (d < ND) {
+                    atomicAdd(&s_tile[d * 33 + xl], c[j]);     // duplicates are summed like utils.tocsr
+                    cmax = max(cmax, c[j]);
+                }
             }
         }
         if (__any_sync(0xffffffffu, any) && lane == 0) valid[x] = 1;
@@ -77,6 +92,19 @@ __global__ void __launch_bounds__(256) k_check_sorted(const int32_t* __restrict_
     if (bad) atomicOr(&flags[3], 1);
 }
 
+// valid[] bytes -> one bit per bin (word i covers bins 32i .. 32i+31); two padding words of 0
+__global__ void __launch_bounds__(256) k_valid_bits(const uint8_t* __restrict__ valid, int n, uint32_t* __restrict__ vbits,
+                                                    int n_words) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_words) return;
+    uint32_t m = 0;
+    for (int b = 0; b < 32; ++b) {
+        const int x = i * 32 + b;
+        if (x < n && valid[x]) m |= 1u << b;
+    }
+    vbits[i] = m;
+}
+
 // ---------------------------------------------------------------------------
 // S2  per-diagonal sums in numpy's pairwise order (utils.py:160-170).
 //     One CTA per distance d. Each warp owns a contiguous slice of the diagonal:
@@ -88,7 +116,6 @@ __global__ void __launch_bounds__(256) k_check_sorted(const int32_t* __restrict_
 //     then a sequential tail) is evaluated leaf-parallel, combined by one thread.
 // ---------------------------------------------------------------------------
 #define PK_DS_THREADS 512
-#define PK_DS_CAP 2048          // leaves per diagonal handled in shared memory (n up to ~116k bins)
 #define PK_DS_LEVELS 14
 
 __device__ double pk_leaf_sum(const double* __restrict__ a, int n) {
@@ -115,42 +142,51 @@ __device__ double pk_leaf_sum(const double* __restrict__ a, int n) {
 // become those of level l+1 (a segment of more than 128 elements splits into
 // n2 = m/2 - (m/2)%8 and the rest, others are carried over), order preserved. The split
 // bitmask of every level is kept so that the sums can be combined back up the same tree.
+template <int CAP>                 // leaves per diagonal handled in shared memory (n up to ~57 * CAP bins)
 struct DiagSmem {
-    int32_t seg_s[2][PK_DS_CAP];
-    int32_t seg_m[2][PK_DS_CAP];
-    double val[2][PK_DS_CAP];
-    uint32_t split[PK_DS_LEVELS][PK_DS_CAP / 32];
-    uint16_t wpre[PK_DS_LEVELS][PK_DS_CAP / 32];    // splits in the words before this one
+    int32_t seg_s[2][CAP];
+    int32_t seg_m[2][CAP];
+    double val[2][CAP];
+    uint32_t split[PK_DS_LEVELS][CAP / 32];
+    uint16_t wpre[PK_DS_LEVELS][CAP / 32];      // splits in the words before this one
     int32_t nseg[PK_DS_LEVELS + 1];
     int32_t wcnt[PK_DS_THREADS / 32];
 };
 
+// pair mask of bins x0..x0+31 on diagonal d: valid[x] & valid[x+d], from the bit vector
+__device__ __forceinline__ uint32_t pk_pair_word(const uint32_t* __restrict__ vb, int x0, int d) {
+    const int y0 = x0 + d;
+    const uint32_t lo = vb[y0 >> 5], hi = vb[(y0 >> 5) + 1];
+    return vb[x0 >> 5] & __funnelshift_r(lo, hi, y0 & 31);
+}
+
+template <int CAP>
 __global__ void __launch_bounds__(PK_DS_THREADS) k_diag_sums(
-    const int32_t* __restrict__ band, const double* __restrict__ w, const uint8_t* __restrict__ valid,
+    const int32_t* __restrict__ band, const double* __restrict__ w, const uint32_t* __restrict__ vbits, int n_words,
     int n, long long pitch, int balanced, double* __restrict__ scratch,
     double* __restrict__ out_sum, long long* __restrict__ out_cnt, int32_t* __restrict__ flags) {
     constexpr int NWARP = PK_DS_THREADS / 32;
     extern __shared__ __align__(16) unsigned char ds_raw[];
-    DiagSmem& sm = *reinterpret_cast<DiagSmem*>(ds_raw);
+    DiagSmem<CAP>& sm = *reinterpret_cast<DiagSmem<CAP>*>(ds_raw);
+    uint32_t* s_vb = reinterpret_cast<uint32_t*>(ds_raw + sizeof(DiagSmem<CAP>));     // [n_words + 2]
     const int d = blockIdx.x;
     const int len = n - d;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double* sc = scratch + (long long)d * pitch;
     const int32_t* row = band + (long long)d * pitch;
-    // ---- compaction: slice of this warp, multiple of 128 elements ----
-    const int per = len > 0 ? (((len + NWARP - 1) / NWARP + 127) & ~127) : 0;
+    for (int i = tid; i < n_words + 2; i += PK_DS_THREADS) s_vb[i] = i < n_words ? vbits[i] : 0u;
+    __syncthreads();
+    // ---- compaction: slice of this warp, a multiple of 256 elements ----
+    const int per = len > 0 ? (((len + NWARP - 1) / NWARP + 255) & ~255) : 0;
     const int xb = wid * per, xe = min(len, xb + per);
     int cntw = 0;
-    for (int x0 = xb; x0 < xe; x0 += 128) {
-        bool f[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int x = x0 + j * 32 + lane;
-            f[j] = (x < xe) && valid[x] && valid[x + d];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cntw += __popc(__ballot_sync(0xffffffffu, f[j]));
+    for (int x0 = xb + lane * 32; x0 < xe; x0 += 1024) {
+        uint32_t m = pk_pair_word(s_vb, x0, d);
+        if (x0 + 32 > xe) m &= (1u << (xe - x0)) - 1u;       // xe - x0 in [1, 31]
+        cntw += __popc(m);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cntw += __shfl_xor_sync(0xffffffffu, cntw, o);
     if (lane == 0) sm.wcnt[wid] = cntw;
     __syncthreads();
     int base = 0, nd = 0;
@@ -160,21 +196,22 @@ __global__ void __launch_bounds__(PK_DS_THREADS) k_diag_sums(
         if (k < wid) base += t;
         nd += t;
     }
-    for (int x0 = xb; x0 < xe; x0 += 128) {
-        bool f[4]; int c[4]; double wa[4], wb[4];
+    for (int x0 = xb; x0 < xe; x0 += 256) {
+        uint32_t m[8]; int c[8]; double wa[8], wb[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int x = x0 + j * 32 + lane;
-            f[j] = (x < xe) && valid[x] && valid[x + d];
-            c[j] = f[j] ? row[x] : 0;
-            wa[j] = (f[j] && balanced) ? w[x] : 0.0;
-            wb[j] = (f[j] && balanced) ? w[x + d] : 0.0;
+        for (int j = 0; j < 8; ++j) {
+            const int xw = x0 + j * 32, x = xw + lane;
+            m[j] = xw < xe ? pk_pair_word(s_vb, xw, d) : 0u;
+            if (xw < xe && xw + 32 > xe) m[j] &= (1u << (xe - xw)) - 1u;
+            const bool f = (m[j] >> lane) & 1u;
+            c[j] = f ? __ldg(row + x) : 0;
+            wa[j] = (f && balanced) ? __ldg(w + x) : 0.0;
+            wb[j] = (f && balanced) ? __ldg(w + x + d) : 0.0;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const unsigned bal = __ballot_sync(0xffffffffu, f[j]);
-            if (f[j]) sc[base + __popc(bal & ((1u << lane) - 1u))] = pk_value(c[j], wa[j], wb[j], balanced);
-            base += __popc(bal);
+        for (int j = 0; j < 8; ++j) {
+            if ((m[j] >> lane) & 1u) sc[base + __popc(m[j] & ((1u << lane) - 1u))] = pk_value(c[j], wa[j], wb[j], balanced);
+            base += __popc(m[j]);
         }
     }
     // ---- leaf table, level by level ----
@@ -209,7 +246,7 @@ __global__ void __launch_bounds__(PK_DS_THREADS) k_diag_sums(
         __syncthreads();
         const int ns_next = sm.nseg[L + 1];
         if (ns_next == ns) break;           // nothing split: level L holds the leaves
-        if (ns_next > PK_DS_CAP || L + 1 >= PK_DS_LEVELS) { overflow = true; break; }
+        if (ns_next > CAP || L + 1 >= PK_DS_LEVELS) { overflow = true; break; }
         for (int i = tid; i < ns; i += PK_DS_THREADS) {
             const uint32_t word = sm.split[L][i >> 5];
             const int pos = i + sm.wpre[L][i >> 5] + __popc(word & ((1u << (i & 31)) - 1u));
@@ -572,17 +609,28 @@ int pk_launch_rowptr(pk_chrom* c, const int32_t* b1, const int32_t* b2, int64_t 
     return PK_OK;
 }
 
-int pk_launch_diag_sums(pk_chrom* c) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        PK_CUDA(cudaFuncSetAttribute(k_diag_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiagSmem)));
-        attr_set = true;
+template <int CAP>
+static int launch_diag_sums_t(pk_chrom* c, int n_words) {
+    const size_t smem = sizeof(DiagSmem<CAP>) + ((size_t)n_words + 2) * 4;
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
+        PK_CUDA(cudaFuncSetAttribute(k_diag_sums<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = smem;
     }
-    k_diag_sums<<<c->ND, PK_DS_THREADS, sizeof(DiagSmem), c->stream>>>(c->d_band, c->d_w, c->d_valid, c->n, c->pitch,
-                                                                       c->balanced, c->d_scratch, c->d_diag_sum,
-                                                                       c->d_diag_cnt, c->d_flags);
+    k_diag_sums<CAP><<<c->ND, PK_DS_THREADS, smem, c->stream>>>(c->d_band, c->d_w, c->d_vbits, n_words, c->n, c->pitch,
+                                                                c->balanced, c->d_scratch, c->d_diag_sum, c->d_diag_cnt,
+                                                                c->d_flags);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
+}
+
+int pk_launch_diag_sums(pk_chrom* c) {
+    const int n_words = (c->n + 31) / 32;
+    k_valid_bits<<<(n_words + 255) / 256, 256, 0, c->stream>>>(c->d_valid, c->n, c->d_vbits, n_words);
+    PK_CUDA(cudaGetLastError());
+    // leaves of numpy's tree hold at least 57 elements
+    if (c->n <= 57 * 1024) return launch_diag_sums_t<1024>(c, n_words);
+    return launch_diag_sums_t<4096>(c, n_words);
 }
 
 bool pk_fit_on_device_supported(int len) { return len <= PK_FIT_MAX; }
