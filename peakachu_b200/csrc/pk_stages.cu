@@ -118,24 +118,32 @@ __global__ void __launch_bounds__(256) k_valid_bits(const uint8_t* __restrict__ 
 #define PK_DS_THREADS 512
 #define PK_DS_LEVELS 14
 
-__device__ double pk_leaf_sum(const double* __restrict__ a, int n) {
-    if (n < 8) {
-        double res = 0.0;
-        for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
-        return res;
-    }
-    double r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
-    int i;
-    for (i = 8; i < n - (n % 8); i += 8) {
-        r0 = __dadd_rn(r0, a[i + 0]); r1 = __dadd_rn(r1, a[i + 1]);
-        r2 = __dadd_rn(r2, a[i + 2]); r3 = __dadd_rn(r3, a[i + 3]);
-        r4 = __dadd_rn(r4, a[i + 4]); r5 = __dadd_rn(r5, a[i + 5]);
-        r6 = __dadd_rn(r6, a[i + 6]); r7 = __dadd_rn(r7, a[i + 7]);
-    }
-    double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
-                           __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
-    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
-    return res;
+// numpy's leaf: eight strided accumulators r_j = a[j] + a[j+8] + ..., combined as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the n%8 tail added one by one. Eight lanes
+// (an aligned octet of a warp) take one accumulator each: all of a lane's values are
+// loaded before the first add, so a leaf costs one memory latency, not sixteen.
+// Every lane of the warp must call it; lanes of an octet share (a, n); n <= 128.
+__device__ __forceinline__ double pk_leaf_sum8(const double* __restrict__ a, int n, int j /* lane & 7 */) {
+    const int nb = n < 8 ? 0 : (n - (n % 8));      // elements covered by the accumulators
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (j + 8 * i < nb) ? a[j + 8 * i] : 0.0;
+    double tail[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) tail[i] = (j == 0 && nb + i < n) ? a[nb + i] : 0.0;
+    double r = v[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i)
+        if (j + 8 * i < nb) r = __dadd_rn(r, v[i]);
+    // pairwise combine across the octet (addition is commutative, so the partner order is free)
+    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+    if (n < 8) r = 0.0;                              // numpy: plain loop from 0.0 for short arrays
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+        if (nb + i < n) r = __dadd_rn(r, tail[i]);
+    return r;                                         // valid in lane j == 0
 }
 
 // numpy's recursion, one level at a time, all threads: segments (start, size) of level l
@@ -270,7 +278,12 @@ __global__ void __launch_bounds__(PK_DS_THREADS) k_diag_sums(
     // ---- leaf sums (8 strided accumulators + tail), one leaf per thread ----
     const int nl = sm.nseg[L];
     int vc = 0;
-    for (int l = tid; l < nl; l += PK_DS_THREADS) sm.val[vc][l] = pk_leaf_sum(sc + sm.seg_s[cur][l], sm.seg_m[cur][l]);
+    for (int l0 = 0; l0 < nl; l0 += PK_DS_THREADS / 8) {          // uniform trip count: shuffles inside
+        const int l = l0 + (tid >> 3);
+        const bool have = l < nl;
+        const double r = pk_leaf_sum8(sc + (have ? sm.seg_s[cur][l] : 0), have ? sm.seg_m[cur][l] : 0, tid & 7);
+        if (have && (tid & 7) == 0) sm.val[vc][l] = r;
+    }
     __syncthreads();
     // ---- combine back up: left + right wherever a segment was split ----
     for (int lv = L - 1; lv >= 0; --lv) {
