@@ -270,25 +270,32 @@ def main():
         return t
     p_rp, p_b2, p_cnt, p_w = pinned(rowptr), pinned(ch.bin2), pinned(ch.count), pinned(ch.weights)
 
-    def e2e_step():
-        X = Chromosome.from_csr(p_rp.numpy(), p_b2.numpy(), p_cnt.numpy(), p_w.numpy(), n, forest,
-                                lower=wl["lower"], upper=wl["upper"], cname="chr1", res=wl["res"], width=w,
-                                device=local)
-        out = X.score_records(0.5)
-        X.close()
-        return out
+    class PinnedMap:
+        """K chromosomes of the workload shape backed by the pinned columns above: what
+        coolio.open_map hands to the scoring API, minus the file."""
+        def nbins(self, key): return n
+        def weights(self, key, name): return p_w.numpy()
+        def upper_pixels_csr(self, key): return p_rp.numpy(), p_b2.numpy(), p_cnt.numpy()
 
-    for _ in range(2):
-        e2e_step()
+    from peakachu_b200 import shard
+
+    def e2e_run(k):
+        # the public multi-chromosome entry point (score_genome's engine): per chromosome an
+        # H2D of its columns, the kernels, a D2H of its records; chromosomes are pipelined
+        units = [("chr%d" % (i + 1), 0, n) for i in range(k)]
+        return shard.score_units(PinnedMap(), units, flat, correct="weight", lower=wl["lower"], upper=wl["upper"],
+                                 res=wl["res"], device=local, min_prob=0.5)
+
+    e2e_run(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        rec = e2e_step()
+    res_e2e = e2e_run(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    rec = [res_e2e["chr1"][0]["x"]]
     clocks = sampler.stop() if rank == 0 else None
     h2d = 8 * nnz + 8 * (n + 1) + 8 * n
-    d2h = 24 * int(rec[0].size)
+    d2h = 28 * int(rec[0].size)
 
     # max over ranks
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -347,7 +354,9 @@ def main():
         "candidates_per_s": world * int(ncand.value) * steps / (dev_ms * 1e-3),
         "stage_ms": stage, "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_val, "unit": "pixels/s", "ms_per_step": e2e_ms / steps,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "peakachu_b200.shard.score_units (engine of score_genome), pinned host columns, "
+                       "three chromosomes in flight"},
         "gpu_launches": KERNELS_PER_STEP * steps, "clocks": clocks,
     }))
     if world > 1:

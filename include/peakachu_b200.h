@@ -150,6 +150,11 @@ int pk_fit_expected(const double* sum, const int64_t* cnt, int32_t len, double* 
  * division on n pseudo-random / adversarial operand pairs; *mismatches must come back 0 */
 int pk_selftest_divide(int device, int64_t n, uint64_t seed, int64_t* mismatches);
 
+/* a non-blocking CUDA stream for pk_chrom_create, for callers that do not bring their own
+ * (two handles on two streams overlap one chromosome's upload with another's kernels) */
+int pk_stream_create(int device, void** out);
+int pk_stream_destroy(int device, void* stream);
+
 /* return the library's cached device blocks (of destroyed handles) to the driver */
 int pk_release_memory(void);
 

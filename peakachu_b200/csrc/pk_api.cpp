@@ -26,6 +26,10 @@ int pk_launch_forest(const pk_forest* f, const float* X, const uint8_t* keep, in
                      double* proba, cudaStream_t stream);
 int pk_launch_emit(pk_chrom* c, double thre);
 int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant);
+size_t pk_sort_temp_bytes(long long n);
+int pk_launch_sort_records(pk_chrom* c, long long n, unsigned long long* keys_in, unsigned long long* keys_out,
+                           uint32_t* idx_in, uint32_t* idx_out, void* temp, size_t temp_bytes, unsigned char* packed,
+                           long long off_f64, int key_bits);
 bool pk_fused_supported(int w, int n_trees);
 
 int pk_run_selftest_divide(long long n, unsigned long long seed, long long* mismatches);
@@ -125,6 +129,53 @@ static void pool_free(void* p) {
     g_pool_live.erase(it);
 }
 
+// pinned host staging buffers are process-wide and reused (cudaMallocHost / cudaFreeHost
+// synchronise the device)
+namespace {
+std::mutex g_hstage_mu;
+std::vector<std::pair<unsigned char*, size_t>> g_hstage_free;
+}  // namespace
+
+static int hstage_acquire(unsigned char** out, size_t* out_bytes, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lk(g_hstage_mu);
+        for (size_t i = 0; i < g_hstage_free.size(); ++i)
+            if (g_hstage_free[i].second >= bytes) {
+                *out = g_hstage_free[i].first; *out_bytes = g_hstage_free[i].second;
+                g_hstage_free.erase(g_hstage_free.begin() + i);
+                return PK_OK;
+            }
+    }
+    const size_t want = std::max<size_t>(bytes + bytes / 4, 1 << 20);
+    cudaError_t e = cudaMallocHost((void**)out, want);
+    if (e != cudaSuccess) { pk_set_error("cudaMallocHost(%zu): %s", want, cudaGetErrorString(e)); return PK_ENOMEM; }
+    *out_bytes = want;
+    return PK_OK;
+}
+
+static void hstage_release(unsigned char* p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_hstage_mu);
+    g_hstage_free.push_back({p, bytes});
+}
+
+extern "C" int pk_stream_create(int device, void** out) {
+    if (!out) { pk_set_error("pk_stream_create: out is NULL"); return PK_EINVAL; }
+    PK_CUDA(cudaSetDevice(device));
+    cudaStream_t s = nullptr;
+    PK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *out = (void*)s;
+    return PK_OK;
+}
+
+extern "C" int pk_stream_destroy(int device, void* stream) {
+    if (!stream) return PK_OK;
+    PK_CUDA(cudaSetDevice(device));
+    PK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    PK_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+    return PK_OK;
+}
+
 extern "C" int pk_release_memory(void) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     for (auto& kv : g_pool_free) {
@@ -133,6 +184,9 @@ extern "C" int pk_release_memory(void) {
         for (auto& b : kv.second) cudaFree(b.p);
         kv.second.clear();
     }
+    std::lock_guard<std::mutex> lk2(g_hstage_mu);
+    for (auto& b : g_hstage_free) cudaFreeHost(b.first);
+    g_hstage_free.clear();
     return PK_OK;
 }
 
@@ -387,6 +441,7 @@ extern "C" int pk_chrom_destroy(pk_chrom* c) {
     dev_free(c->d_keep); dev_free(c->d_fea32); dev_free(c->d_prob); dev_free(c->d_batch_win);
     dev_free(c->d_rx); dev_free(c->d_ry); dev_free(c->d_rb); dev_free(c->d_rp); dev_free(c->d_rv);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    hstage_release(c->h_stage, c->h_stage_bytes);
     delete c;
     return PK_OK;
 }
@@ -806,27 +861,41 @@ extern "C" int pk_chrom_fetch_results(pk_chrom* c, int32_t* out_x, int32_t* out_
         if (out_batch) PK_CUDA(cudaMemcpyAsync(out_batch, c->d_rb, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
         return PK_OK;
     }
-    std::vector<int32_t> x((size_t)n), y((size_t)n), b((size_t)n);
-    std::vector<double> p((size_t)n), v((size_t)n);
-    PK_CUDA(cudaMemcpyAsync(x.data(), c->d_rx, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-    PK_CUDA(cudaMemcpyAsync(y.data(), c->d_ry, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-    PK_CUDA(cudaMemcpyAsync(p.data(), c->d_rp, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
-    PK_CUDA(cudaMemcpyAsync(v.data(), c->d_rv, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
-    PK_CUDA(cudaMemcpyAsync(b.data(), c->d_rb, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-    PK_CUDA(cudaStreamSynchronize(s));
-    std::vector<int64_t> idx((size_t)n);
-    std::iota(idx.begin(), idx.end(), 0);
-    std::sort(idx.begin(), idx.end(), [&](int64_t a, int64_t bb) {
-        return x[(size_t)a] != x[(size_t)bb] ? x[(size_t)a] < x[(size_t)bb] : y[(size_t)a] < y[(size_t)bb];
-    });
-    for (int64_t i = 0; i < n; ++i) {
-        size_t j = (size_t)idx[(size_t)i];
-        if (out_x) out_x[i] = x[j];
-        if (out_y) out_y[i] = y[j];
-        if (out_prob) out_prob[i] = p[j];
-        if (out_val) out_val[i] = v[j];
-        if (out_batch) out_batch[i] = b[j];
+    // sort by (x, y) on the device, pack, one copy into pinned staging, split on the host
+    const long long off_f64 = ((12 * n + 7) / 8) * 8;
+    const size_t packed_bytes = (size_t)off_f64 + 16 * (size_t)n;
+    const size_t temp_bytes = pk_sort_temp_bytes(n);
+    unsigned long long *k0 = nullptr, *k1 = nullptr;
+    uint32_t *i0 = nullptr, *i1 = nullptr;
+    unsigned char *temp = nullptr, *packed = nullptr;
+    int r = PK_OK;
+    if ((r = dev_alloc(&k0, (size_t)n)) || (r = dev_alloc(&k1, (size_t)n)) || (r = dev_alloc(&i0, (size_t)n)) ||
+        (r = dev_alloc(&i1, (size_t)n)) || (r = dev_alloc(&temp, temp_bytes)) || (r = dev_alloc(&packed, packed_bytes))) {
+        dev_free(k0); dev_free(k1); dev_free(i0); dev_free(i1); dev_free(temp); dev_free(packed);
+        return r;
     }
+    if (packed_bytes > c->h_stage_bytes) {
+        hstage_release(c->h_stage, c->h_stage_bytes);
+        c->h_stage = nullptr; c->h_stage_bytes = 0;
+        r = hstage_acquire(&c->h_stage, &c->h_stage_bytes, packed_bytes);
+    }
+    int key_bits = 32;
+    for (int nb = c->n; nb > 0; nb >>= 1) ++key_bits;      // x needs bits(n) bits above the 32 bits of y
+    if (r == PK_OK) r = pk_launch_sort_records(c, n, k0, k1, i0, i1, temp, temp_bytes, packed, off_f64, std::min(key_bits, 64));
+    if (r == PK_OK) {
+        cudaError_t e = cudaMemcpyAsync(c->h_stage, packed, packed_bytes, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { pk_set_error("pk_chrom_fetch_results: %s", cudaGetErrorString(e)); r = PK_ECUDA; }
+    }
+    dev_free(k0); dev_free(k1); dev_free(i0); dev_free(i1); dev_free(temp); dev_free(packed);
+    PK_CHECK(r);
+    const int32_t* hi = reinterpret_cast<const int32_t*>(c->h_stage);
+    const double* hd = reinterpret_cast<const double*>(c->h_stage + off_f64);
+    if (out_x) memcpy(out_x, hi, (size_t)n * 4);
+    if (out_y) memcpy(out_y, hi + n, (size_t)n * 4);
+    if (out_batch) memcpy(out_batch, hi + 2 * n, (size_t)n * 4);
+    if (out_prob) memcpy(out_prob, hd, (size_t)n * 8);
+    if (out_val) memcpy(out_val, hd + n, (size_t)n * 8);
     return PK_OK;
 }
 

@@ -115,6 +115,8 @@ struct pk_chrom {
     double *d_rp = nullptr, *d_rv = nullptr;
     unsigned long long* d_counters = nullptr;   // [4]: 0 = n_records, 1 = n_windows
     int64_t rec_cap = 0;
+    unsigned char* h_stage = nullptr;   // pinned staging for fetch_results
+    size_t h_stage_bytes = 0;
     // timing
     cudaEvent_t ev[16] = {};
     float stage_ms[8] = {};

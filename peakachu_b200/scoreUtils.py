@@ -107,31 +107,32 @@ class Chromosome:
 
     @classmethod
     def from_pixels(cls, bin1, bin2, count, weights, n_bins, model, lower=6, upper=300,
-                    cname="chrm", res=10000, width=5, device=0, stream=None, sorted_pixels=None):
+                    cname="chrm", res=10000, width=5, device=0, stream=None, sorted_pixels=None,
+                    first_tile=None):
         """Build from cooler-style upper-triangle pixel columns (chromosome-local bin
         ids) and the weight column (None = raw mode). ``sorted_pixels=True`` promises
         cooler order (sorted by bin1, then bin2; the device verifies it), ``None``
         checks on the host, ``False`` takes the order-free scatter path."""
         self = cls.__new__(cls)
         self._init(bin1, bin2, count, weights, int(n_bins), model, lower, upper, cname, res, width, device, stream,
-                   sorted_pixels=sorted_pixels)
+                   sorted_pixels=sorted_pixels, first_tile=first_tile)
         return self
 
     @classmethod
     def from_csr(cls, bin1_offset, bin2, count, weights, n_bins, model, lower=6, upper=300,
-                 cname="chrm", res=10000, width=5, device=0, stream=None):
+                 cname="chrm", res=10000, width=5, device=0, stream=None, first_tile=None):
         """Build from cooler's CSR layout: ``indexes/bin1_offset`` of the chromosome
         (rebased to 0, int64[n_bins+1]) plus the ``bin2_id`` (chromosome-local) and
         ``count`` columns of its pixels. 8 bytes per pixel cross the bus instead of 12.
         Arrays may live in pinned host memory (e.g. views of pinned torch tensors)."""
         self = cls.__new__(cls)
         self._init(None, bin2, count, weights, int(n_bins), model, lower, upper, cname, res, width, device, stream,
-                   bin1_offset=bin1_offset)
+                   bin1_offset=bin1_offset, first_tile=first_tile)
         return self
 
     # -- construction = upload + band + expected + candidates (scoreUtils.py:13-34) --
     def _init(self, b1, b2, cnt, weights, n, model, lower, upper, cname, res, width, device, stream,
-              sorted_pixels=None, bin1_offset=None):
+              sorted_pixels=None, bin1_offset=None, first_tile=None):
         L = _lib.lib()
         _lib.require_device()
         self.chromname, self.r, self.w = cname, res, width
@@ -147,14 +148,17 @@ class Chromosome:
         _lib.check(L.pk_chrom_bounds(self._h, C.byref(lo), C.byref(up), C.byref(el)))
         self.lower, self.upper, self._exp_len = lo.value, up.value, el.value
         b2, cnt = _lib.as_c(b2, np.int32), _lib.as_c(cnt, np.int32)
+        self._keepalive = [b2, cnt]          # uploads are asynchronous when the source is pinned
         if bin1_offset is not None:
             rp = _lib.as_c(bin1_offset, np.int64)
+            self._keepalive.append(rp)
             if rp.size != n + 1:
                 raise ValueError("bin1_offset must have n_bins + 1 entries")
             _lib.check(L.pk_chrom_upload_csr(self._h, _lib.ptr(rp), _lib.ptr(b2), _lib.ptr(cnt), b2.size,
                                              _lib.ptr(self.weights), _lib.PK_MEM_HOST))
         else:
             b1 = _lib.as_c(b1, np.int32)
+            self._keepalive.append(b1)
             if sorted_pixels is None:
                 sorted_pixels = bool(b1.size == 0 or (np.all(b1[1:] >= b1[:-1]) and np.all(b1 <= b2)))
             mem = _lib.PK_MEM_HOST | (_lib.PK_PIXELS_SORTED if sorted_pixels else 0)
@@ -163,7 +167,8 @@ class Chromosome:
         _lib.check(L.pk_chrom_fit_expected(self._h))
         self._exp = None
         # asynchronous: the candidate count is read back only when somebody asks for it
-        _lib.check(L.pk_chrom_find_candidates(self._h, 0, n, None))
+        ra, rb = first_tile if first_tile is not None else (0, n)     # band row tile (multi-GPU seam)
+        _lib.check(L.pk_chrom_find_candidates(self._h, int(ra), int(rb), None))
         self._ncand = None
         self._cand = None
         self.M = None

@@ -82,9 +82,35 @@ def gather_to_rank0(obj, rank, world):
     return out
 
 
-def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_prob):
-    """Score this rank's units. Returns {chrom: [tile dict, ...]}."""
+def _fetch_tile(X, a, b, n, ncand=None):
+    """Collect the records of the scoring pass in flight on handle ``X``."""
     import ctypes as C
+
+    from . import _lib
+    L = _lib.lib()
+    nrec, nc = C.c_int64(), C.c_int64()
+    _lib.check(L.pk_chrom_result_count(X._h, C.byref(nrec), C.byref(nc), None))
+    m = nrec.value
+    x, y, bt = (np.empty(m, np.int32) for _ in range(3))
+    p, v = np.empty(m, np.float64), np.empty(m, np.float64)
+    _lib.check(L.pk_chrom_fetch_results(X._h, _lib.ptr(x), _lib.ptr(y), _lib.ptr(p), _lib.ptr(v),
+                                        _lib.ptr(bt), m, _lib.PK_MEM_HOST))
+    nb = C.c_int64()
+    _lib.check(L.pk_chrom_batch_windows(X._h, None, 0, C.byref(nb)))
+    bw = np.zeros(max(nb.value, 1), np.int64)
+    _lib.check(L.pk_chrom_batch_windows(X._h, _lib.ptr(bw, _lib.c_i64p), bw.size, C.byref(nb)))
+    return dict(row_begin=a, whole=(a == 0 and b == n), x=x, y=y, p=p, v=v, batch=bt,
+                batch_windows=bw[:nb.value], n_candidates=int(nc.value))
+
+
+def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_prob, depth=3):
+    """Score this rank's units. Returns {chrom: [tile dict, ...]}.
+
+    Chromosomes are pipelined over ``depth`` streams: while one chromosome's kernels
+    run, the next one's pixel columns are already crossing the bus. Every call of the
+    library up to the record count is asynchronous, so submitting is cheap."""
+    import ctypes as C
+    from collections import deque
 
     from . import _lib
     from .scoreUtils import Chromosome, DeviceForest
@@ -95,32 +121,45 @@ def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_pro
     by_chrom = {}
     for k, a, b in units:
         by_chrom.setdefault(k, []).append((a, b))
-    for key, tiles in by_chrom.items():
-        b1, b2, cnt = Lib.upper_pixels(key)
-        weights = Lib.weights(key, correct) if correct else None
-        n = Lib.nbins(key)
-        X = Chromosome.from_pixels(b1, b2, cnt, weights, n, forest, lower=lower, upper=upper,
-                                   cname="chr" + key.lstrip("chr"), res=res, width=flat.width, device=device,
-                                   sorted_pixels=True)
-        for a, b in tiles:
-            ncand = C.c_int64()
-            _lib.check(L.pk_chrom_find_candidates(X._h, a, b, C.byref(ncand)))
+    streams = []
+    for _ in range(max(1, depth)):
+        st = C.c_void_p()
+        _lib.check(L.pk_stream_create(device, C.byref(st)))
+        streams.append(st)
+    inflight = deque()
+
+    def finish(job):
+        key, X, tiles, n = job
+        a, b = tiles[0]
+        res_tiles = [_fetch_tile(X, a, b, n)]              # first tile was launched at submit time
+        for a, b in tiles[1:]:
+            _lib.check(L.pk_chrom_find_candidates(X._h, a, b, None))
             _lib.check(L.pk_chrom_score(X._h, forest.handle, float(min_prob)))
-            nrec = C.c_int64()
-            _lib.check(L.pk_chrom_result_count(X._h, C.byref(nrec), None, None))
-            m = nrec.value
-            x, y, bt = (np.empty(m, np.int32) for _ in range(3))
-            p, v = np.empty(m, np.float64), np.empty(m, np.float64)
-            _lib.check(L.pk_chrom_fetch_results(X._h, _lib.ptr(x), _lib.ptr(y), _lib.ptr(p), _lib.ptr(v),
-                                                _lib.ptr(bt), m, _lib.PK_MEM_HOST))
-            nb = C.c_int64()
-            _lib.check(L.pk_chrom_batch_windows(X._h, None, 0, C.byref(nb)))
-            bw = np.zeros(max(nb.value, 1), np.int64)
-            _lib.check(L.pk_chrom_batch_windows(X._h, _lib.ptr(bw, _lib.c_i64p), bw.size, C.byref(nb)))
-            out.setdefault(key, []).append(dict(row_begin=a, whole=(a == 0 and b == n), x=x, y=y, p=p, v=v,
-                                                batch=bt, batch_windows=bw[:nb.value],
-                                                n_candidates=int(ncand.value)))
+            res_tiles.append(_fetch_tile(X, a, b, n))
         X.close()
+        out[key] = res_tiles
+
+    try:
+        for i, (key, tiles) in enumerate(by_chrom.items()):
+            if len(inflight) == len(streams):
+                finish(inflight.popleft())
+            weights = Lib.weights(key, correct) if correct else None
+            n = Lib.nbins(key)
+            kw = dict(lower=lower, upper=upper, cname="chr" + key.lstrip("chr"), res=res, width=flat.width,
+                      device=device, stream=streams[i % len(streams)].value, first_tile=tiles[0])
+            if hasattr(Lib, "upper_pixels_csr"):
+                rp, b2, cnt = Lib.upper_pixels_csr(key)
+                X = Chromosome.from_csr(rp, b2, cnt, weights, n, forest, **kw)
+            else:
+                b1, b2, cnt = Lib.upper_pixels(key)
+                X = Chromosome.from_pixels(b1, b2, cnt, weights, n, forest, sorted_pixels=True, **kw)
+            _lib.check(L.pk_chrom_score(X._h, forest.handle, float(min_prob)))
+            inflight.append((key, X, tiles, n))
+        while inflight:
+            finish(inflight.popleft())
+    finally:
+        for st in streams:
+            L.pk_stream_destroy(device, st)
     return out
 
 
