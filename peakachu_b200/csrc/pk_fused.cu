@@ -88,6 +88,19 @@ __device__ __forceinline__ double pk_div_r(double a, double b, double r) {
 }
 __device__ __forceinline__ bool pk_div_safe(double v) { return v >= 1e-100 && v <= 1e100; }   // false for NaN
 
+// explicit shared-space accesses on 32-bit addresses: [reg + immediate], no generic-pointer arithmetic
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ void lds_node(uint32_t addr, uint2& nd) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nd.x), "=r"(nd.y) : "r"(addr));
 }
@@ -186,8 +199,9 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
     if (G > 1) { issue(1); issued = 2; }
     bool first_batch = true;
 
-    double* V0 = s_V + (size_t)(wib * 2) * F;       // both windows of this warp
-    double* myV = V0 + (size_t)half * F;
+    const uint32_t V0_addr = smem_u32(s_V) + (uint32_t)(wib * 2 * F) * 8u;    // both windows of this warp
+    const uint32_t myV_addr = V0_addr + (uint32_t)(half * F) * 8u;
+    const uint32_t exp_addr = smem_u32(s_exp), rexp_addr = smem_u32(s_rexp), fea_addr = smem_u32(s_fea);
 
     // ---- gather of one window pair: issue the band loads (registers), consume later ----
     struct Pair { int x, d; bool ok; int cnt[NS]; };
@@ -261,7 +275,7 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                             if (cnt != 0)
                                 v = pk_value(cnt, prm.balanced ? __ldg(prm.w + r) : 0.0,
                                              prm.balanced ? __ldg(prm.w + c) : 0.0, prm.balanced);
-                            V0[(size_t)k * F + a * S + b] = v;
+                            sts_f64(V0_addr + (uint32_t)(k * F + a * S + b) * 8u, v);
                             nzf = v != 0.0;
                             odd |= nzf && !pk_div_safe(v);
                         }
@@ -281,9 +295,9 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
 #pragma unroll
                     for (int a = 0; a < W; ++a)
 #pragma unroll
-                        for (int b = 0; b < W; ++b) s = __dadd_rn(s, myV[a * S + b]);
+                        for (int b = 0; b < W; ++b) s = __dadd_rn(s, lds_f64(myV_addr + (uint32_t)(a * S + b) * 8u));
                     const double ll = __ddiv_rn(s, (double)(W * W));
-                    ok = (ll > 0.0) && (__ddiv_rn(myV[W * S + W], ll) > 0.1);  // utils.py:229-232
+                    ok = (ll > 0.0) && (__ddiv_rn(lds_f64(myV_addr + (uint32_t)(W * S + W) * 8u), ll) > 0.1);  // utils.py:229-232
                 }
                 const bool kept = ok;                                          // uniform within the half
                 const bool actk = kept && (h < S);
@@ -293,16 +307,33 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                 double mn = CUDART_INF, mx = -CUDART_INF;
                 bool has_nan = false;
                 double g[S];
+                const uint32_t col_addr = myV_addr + (uint32_t)h * 8u;          // V[a][h] = col_addr + a*S*8
+                const uint32_t row_addr = myV_addr + (uint32_t)(h * S) * 8u;    // V[h][b] = row_addr + b*8
                 if (actk) {
-                    // distance normalisation (utils.py:187-200) + vertical pass in registers (column h)
+                    // distance normalisation (utils.py:187-200): V[a][h] / exp[|d + h - a|]
                     double v[S];
+                    if (fastdiv && d + h >= S - 1) {
+                        // common case: d + h - a >= 0 for every a, so exp is read at fixed offsets
+                        const uint32_t e0 = exp_addr + (uint32_t)(d + h) * 8u, r0 = rexp_addr + (uint32_t)(d + h) * 8u;
 #pragma unroll
-                    for (int a = 0; a < S; ++a) {
-                        int dd = d + h - a;
-                        dd = dd < 0 ? -dd : dd;
-                        v[a] = fastdiv ? pk_div_r(myV[a * S + h], s_exp[dd], s_rexp[dd])
-                                       : __ddiv_rn(myV[a * S + h], s_exp[dd]);
+                        for (int a = 0; a < S; ++a)
+                            v[a] = pk_div_r(lds_f64(col_addr + a * S * 8), lds_f64(e0 - a * 8), lds_f64(r0 - a * 8));
+                    } else if (fastdiv) {
+#pragma unroll
+                        for (int a = 0; a < S; ++a) {
+                            int dd = d + h - a;
+                            dd = dd < 0 ? -dd : dd;
+                            v[a] = pk_div_r(lds_f64(col_addr + a * S * 8), lds_f64(exp_addr + dd * 8), lds_f64(rexp_addr + dd * 8));
+                        }
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < S; ++a) {
+                            int dd = d + h - a;
+                            dd = dd < 0 ? -dd : dd;
+                            v[a] = __ddiv_rn(lds_f64(col_addr + a * S * 8), lds_f64(exp_addr + dd * 8));
+                        }
                     }
+                    // vertical pass in registers (column h)
 #pragma unroll
                     for (int a = 0; a < S; ++a) {
                         double t = __dmul_rn(v[a], PK_GK[4]);
@@ -315,14 +346,14 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                 __syncwarp();                    // every lane has read its column (and the ll corner)
                 if (actk) {
 #pragma unroll
-                    for (int a = 0; a < S; ++a) myV[a * S + h] = g[a];
+                    for (int a = 0; a < S; ++a) sts_f64(col_addr + a * S * 8, g[a]);
                 }
                 __syncwarp();
                 if (actk) {
                     // horizontal pass in registers (row h)
                     double t[S];
 #pragma unroll
-                    for (int b = 0; b < S; ++b) t[b] = myV[h * S + b];
+                    for (int b = 0; b < S; ++b) t[b] = lds_f64(row_addr + b * 8);
 #pragma unroll
                     for (int b = 0; b < S; ++b) {
                         double q = __dmul_rn(t[b], PK_GK[4]);
@@ -345,14 +376,19 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                     if (has_nan) { mn = CUDART_NAN; mx = CUDART_NAN; }          // numba min/max propagate NaN
                     const double range = __dsub_rn(mx, mn);
                     const bool fr = pk_div_safe(range) && mx <= 1e100;         // else: plain IEEE division
-                    const double rr = __ddiv_rn(1.0, range);
-                    float* frow = s_fea + (size_t)slot * F + h * S;
+                    const uint32_t frow = fea_addr + (uint32_t)(slot * F + h * S) * 4u;
+                    if (fr) {
+                        const double rr = __ddiv_rn(1.0, range);
 #pragma unroll
-                    for (int b = 0; b < S; ++b) {
-                        const double num = __dsub_rn(g[b], mn);
-                        const double q = fr ? pk_div_r(num, range, rr) : __ddiv_rn(num, range);   // utils.py:207
-                        fnan |= isnan(q);
-                        frow[b] = __double2float_rn(q);
+                        for (int b = 0; b < S; ++b)
+                            sts_f32(frow + b * 4, __double2float_rn(pk_div_r(__dsub_rn(g[b], mn), range, rr)));   // utils.py:207
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < S; ++b) {
+                            const double q = __ddiv_rn(__dsub_rn(g[b], mn), range);
+                            fnan |= isnan(q);
+                            sts_f32(frow + b * 4, __double2float_rn(q));
+                        }
                     }
                 }
                 // any NaN feature sends this pixel through the missing_go_to_left-aware walk
