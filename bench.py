@@ -342,7 +342,7 @@ def main():
                 "whole_step_frac": bytes_alg / (dev_ms / steps * 1e-3) / 1e9 / peak_gbs}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         model = load_sklearn_model(wl["forest"])
         cpu_pass(wl, 600, 5, model)
         dt, cpx, ccand, crows = cpu_pass(wl, 3 * args.cpu_bins, 100, model)

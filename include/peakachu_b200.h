@@ -150,6 +150,12 @@ int pk_fit_expected(const double* sum, const int64_t* cnt, int32_t len, double* 
  * division on n pseudo-random / adversarial operand pairs; *mismatches must come back 0 */
 int pk_selftest_divide(int device, int64_t n, uint64_t seed, int64_t* mismatches);
 
+/* Chromosome.writeBed (scoreUtils.py:127-135) for n records: tab-separated
+ * chrom, x*res, (x+1)*res, chrom, y*res, (y+1)*res, str(prob), str(value) with floats in
+ * Python's shortest round-trip repr. HOST buffers; *written = bytes produced (or needed). */
+int pk_format_bedpe(const char* chrom, int64_t res, const int32_t* x, const int32_t* y, const double* prob,
+                    const double* val, int64_t n, char* out, int64_t capacity, int64_t* written);
+
 /* a non-blocking CUDA stream for pk_chrom_create, for callers that do not bring their own
  * (two handles on two streams overlap one chromosome's upload with another's kernels) */
 int pk_stream_create(int device, void** out);

@@ -2,6 +2,9 @@
 // the expected-curve fit. Compiled with -ffp-contract=off: every float64 operation
 // below is one IEEE operation, in the order the reference's libraries perform it.
 #include <algorithm>
+#include <charconv>
+#include <cstring>
+#include <string>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -203,4 +206,84 @@ int pk_fit_expected_host(const double* sum, const long long* cnt, int32_t len, d
 extern "C" int pk_fit_expected(const double* sum, const int64_t* cnt, int32_t len, double* out_exp) {
     std::vector<long long> c(cnt, cnt + len);
     return pk_fit_expected_host(sum, c.data(), len, out_exp);
+}
+
+// ---------------------------------------------------------------------------
+// bedpe text (scoreUtils.py:127-135). The reference prints floats through
+// str(numpy.float64), which is the shortest round-trip representation in Python's repr
+// layout: fixed notation for 1e-4 <= |x| < 1e16 (with ".0" appended to integral values),
+// otherwise d.ddde+XX with at least two exponent digits.
+// ---------------------------------------------------------------------------
+static char* put_repr(char* p, double v) {
+    if (std::isnan(v)) { memcpy(p, "nan", 3); return p + 3; }
+    if (std::isinf(v)) { if (v < 0) *p++ = '-'; memcpy(p, "inf", 3); return p + 3; }
+    if (std::signbit(v)) { *p++ = '-'; v = -v; }
+    if (v == 0.0) { memcpy(p, "0.0", 3); return p + 3; }
+    char buf[64];
+    auto res = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);   // shortest digits
+    // buf = d[.ddd]e[+-]XX
+    char digits[32];
+    int nd = 0;
+    char* q = buf;
+    while (q < res.ptr && *q != 'e') { if (*q != '.') digits[nd++] = *q; ++q; }
+    int e10 = 0;
+    std::from_chars(q + 1 + (q[1] == '+'), res.ptr, e10);
+    const int decpt = e10 + 1;                       // value = 0.digits * 10^decpt
+    if (decpt > 16 || decpt < -3) {
+        *p++ = digits[0];
+        if (nd > 1) { *p++ = '.'; memcpy(p, digits + 1, nd - 1); p += nd - 1; }
+        *p++ = 'e';
+        int ex = decpt - 1;
+        *p++ = ex < 0 ? '-' : '+';
+        if (ex < 0) ex = -ex;
+        if (ex < 10) *p++ = '0';
+        p = std::to_chars(p, p + 8, ex).ptr;
+        return p;
+    }
+    if (decpt <= 0) {
+        *p++ = '0'; *p++ = '.';
+        for (int i = 0; i < -decpt; ++i) *p++ = '0';
+        memcpy(p, digits, nd); return p + nd;
+    }
+    if (nd <= decpt) {
+        memcpy(p, digits, nd); p += nd;
+        for (int i = nd; i < decpt; ++i) *p++ = '0';
+        *p++ = '.'; *p++ = '0';
+        return p;
+    }
+    memcpy(p, digits, decpt); p += decpt;
+    *p++ = '.';
+    memcpy(p, digits + decpt, nd - decpt);
+    return p + (nd - decpt);
+}
+
+extern "C" int pk_format_bedpe(const char* chrom, int64_t res, const int32_t* x, const int32_t* y, const double* prob,
+                               const double* val, int64_t n, char* out, int64_t capacity, int64_t* written) {
+    if (!chrom || !written || n < 0 || (n > 0 && (!x || !y || !prob || !val || !out))) {
+        pk_set_error("pk_format_bedpe: bad argument");
+        return PK_EINVAL;
+    }
+    const size_t cl = strlen(chrom);
+    const int64_t per_row = 2 * (int64_t)cl + 4 * 21 + 2 * 26 + 8;      // generous upper bound per line
+    if (capacity < n * per_row) {
+        *written = n * per_row;
+        pk_set_error("pk_format_bedpe: need %lld bytes", (long long)(n * per_row));
+        return PK_ECAPACITY;
+    }
+    char* p = out;
+    for (int64_t i = 0; i < n; ++i) {
+        // the reference multiplies numpy int32 bin indices by the resolution: int32 arithmetic
+        const int32_t a0 = (int32_t)((int64_t)x[i] * res), a1 = (int32_t)(((int64_t)x[i] + 1) * res);
+        const int32_t b0 = (int32_t)((int64_t)y[i] * res), b1 = (int32_t)(((int64_t)y[i] + 1) * res);
+        memcpy(p, chrom, cl); p += cl; *p++ = '\t';
+        p = std::to_chars(p, p + 12, a0).ptr; *p++ = '\t';
+        p = std::to_chars(p, p + 12, a1).ptr; *p++ = '\t';
+        memcpy(p, chrom, cl); p += cl; *p++ = '\t';
+        p = std::to_chars(p, p + 12, b0).ptr; *p++ = '\t';
+        p = std::to_chars(p, p + 12, b1).ptr; *p++ = '\t';
+        p = put_repr(p, prob[i]); *p++ = '\t';
+        p = put_repr(p, val[i]); *p++ = '\n';
+    }
+    *written = p - out;
+    return PK_OK;
 }

@@ -283,12 +283,18 @@ class Chromosome:
 
 def format_bedpe(chromname, res, r, c, prob, value) -> str:
     """Rows exactly as scoreUtils.py:131-135 prints them: ints from int32 bin index
-    times resolution, floats through str(numpy.float64) (shortest round-trip repr)."""
-    res = int(res)
-    lines = []
-    for i in range(len(r)):
-        a, b = int(r[i]), int(c[i])
-        lines.append("%s\t%d\t%d\t%s\t%d\t%d\t%s\t%s\n" % (
-            chromname, a * res, (a + 1) * res, chromname, b * res, (b + 1) * res,
-            repr(float(prob[i])), repr(float(value[i]))))
-    return "".join(lines)
+    times resolution, floats through str(numpy.float64) (shortest round-trip repr).
+    Formatted by the library (pk_format_bedpe); host-only code, no device needed."""
+    n = len(r)
+    if n == 0:
+        return ""
+    L = _lib.lib()
+    x, y = _lib.as_c(r, np.int32), _lib.as_c(c, np.int32)
+    p, v = _lib.as_c(prob, np.float64), _lib.as_c(value, np.float64)
+    name = chromname.encode()
+    cap = n * (2 * len(name) + 4 * 21 + 2 * 26 + 8)
+    buf = C.create_string_buffer(cap)
+    written = C.c_int64()
+    _lib.check(L.pk_format_bedpe(name, int(res), _lib.ptr(x, _lib.c_i32p), _lib.ptr(y, _lib.c_i32p),
+                                 _lib.ptr(p, _lib.c_f64p), _lib.ptr(v, _lib.c_f64p), n, buf, cap, C.byref(written)))
+    return buf.raw[:written.value].decode()

@@ -81,6 +81,18 @@ def test_bedpe_float_text_is_numpy_str():
                                      np.float64(vals[i]), np.float64(vals[::-1][i])]))
         assert rows[i] == want
     assert all(str(np.float64(v)) == repr(float(v)) for v in vals)
+    # every row, plus awkward magnitudes, against Python/numpy formatting
+    extra = np.array([1e15, 1e16, 9.999999999999999e15, 1e-4, 9.999e-5, 1.5e-7, 5e-324, 1.7976931348623157e308,
+                      123456.0, 0.0, 1.0, 100.0, 2.5e-5, 0.30000000000000004])
+    rng2 = np.random.default_rng(6)
+    wild = np.exp(rng2.uniform(-60, 60, 20000)) * rng2.choice([1.0, 0.5, 3.0], 20000)
+    allv = np.concatenate([vals, extra, wild])
+    txt = format_bedpe("chrX", 5000, np.arange(allv.size, dtype=np.int32), np.arange(allv.size, dtype=np.int32),
+                       allv, allv)
+    for i, row in enumerate(txt.splitlines()):
+        f = row.split("\t")
+        assert f[6] == str(np.float64(allv[i])) == f[7], (i, allv[i], f[6])
+        assert f[1] == str(np.int32(i) * 5000) and f[2] == str((np.int32(i) + 1) * 5000)
 
 
 def test_plan_covers_every_row_once_and_balances():
