@@ -38,6 +38,12 @@ WORKLOADS = {
     # name: (n_bins, res, lower, upper, w, forest, depth, band)
     "c2": dict(n=24900, res=10000, lower=6, upper=300, w=5, forest="c2", depth=300.0, band=330,
                desc="score_chromosome chr1-scale synthetic (24,900 bins, 10 kb, w=5, l=6, u=300, 100-tree RF)"),
+    "c4": dict(n=49850, res=5000, lower=6, upper=600, w=7, forest="c4", depth=300.0, band=640,
+               desc="score_chromosome chr1-scale synthetic at 5 kb (49,850 bins, w=7 / 15x15 windows, l=6, u=600, 200-tree RF)"),
+    # BASELINE configs[2]: score_genome on an hg19-shaped 10 kb genome, sharded over the ranks
+    # (chromosomes + band row tiles, greedy), records gathered on rank 0: strong scaling
+    "c3": dict(genome=True, res=10000, lower=6, upper=300, w=5, forest="c2", depth=300.0, band=330,
+               desc="score_genome hg19-shaped synthetic 10 kb (23 chromosomes, 303,641 bins, w=5, l=6, u=300, 100-tree RF)"),
     "c1": dict(n=2000, res=10000, lower=6, upper=300, w=5, forest="c2", depth=300.0, band=330,
                desc="score_chromosome 2,000-bin synthetic 10 kb (w=5, l=6, u=300, 100-tree RF)"),
 }
@@ -172,6 +178,82 @@ def run_reference_arm(args, wl):
 
 
 # ---------------------------------------------------------------------------
+# genome workload (extra, not the driver's default): score_genome end to end
+# ---------------------------------------------------------------------------
+def run_genome(args, wl, flat, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    from peakachu_b200 import shard, synth
+
+    sizes = synth.hg19_bins(wl["res"])
+    queue = list(sizes)
+    plan = shard.plan(sizes, world, wl["lower"], wl["upper"], wl["w"])
+    mine = plan[rank]
+    need = sorted({k for k, _, _ in mine}, key=queue.index)
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+
+    cols = {}
+    for k in need:
+        ch = synth.make_chromosome(k, sizes[k], seed=5000 + queue.index(k), depth=wl["depth"], band=wl["band"])
+        rp = np.searchsorted(ch.bin1, np.arange(ch.n + 1)).astype(np.int64)
+        cols[k] = tuple(pinned(a) for a in (rp, ch.bin2, ch.count, ch.weights))
+
+    class PinnedGenome:
+        def nbins(self, key): return sizes[key]
+        def weights(self, key, name): return cols[key][3].numpy()
+        def upper_pixels_csr(self, key): return tuple(t.numpy() for t in cols[key][:3])
+
+    def one_pass():
+        res = shard.score_units(PinnedGenome(), mine, flat, correct="weight", lower=wl["lower"], upper=wl["upper"],
+                                res=wl["res"], device=local, min_prob=0.5)
+        gathered = shard.gather_to_rank0(res, rank, world)
+        if rank == 0:
+            merged = {k: shard.merge_tiles(sorted([q for g in gathered for q in g.get(k, [])],
+                                                  key=lambda q: q["row_begin"])) for k in queue}
+            return sum(int(m[0].size) for m in merged.values())
+        return 0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 1)):
+        one_pass()
+    barrier()
+    t0 = time.perf_counter()
+    nrec = 0
+    for _ in range(args.steps):
+        nrec = one_pass()
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    px = sum(band_pixels(n, wl["lower"], wl["upper"], wl["w"]) for n in sizes.values())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "candidate pixels scored/sec (window features + RF proba)", "value": px * args.steps / dt,
+            "unit": "pixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "pixels": "band pixels, %d genome-wide" % px,
+                       "timed": "end to end: pinned host columns -> H2D -> kernels -> records D2H -> host gather on rank 0",
+                       "units_per_rank": [len(u) for u in plan], "records_per_step": nrec},
+            "e2e": {"value": px * args.steps / dt, "unit": "pixels/s",
+                    "h2d_bytes_per_step": int(sum(8 * cols[k][1].numel() + 16 * sizes[k] for k in need)),
+                    "d2h_bytes_per_step": 28 * nrec},
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
 def main():
@@ -210,6 +292,9 @@ def main():
 
     flat = FlatForest.load(os.path.join(ROOT, "bench_data", wl["forest"] + "_forest.npz"))
     forest = DeviceForest.of(flat, local)
+    if wl.get("genome"):
+        run_genome(args, wl, flat, rank, world, local)
+        return
     ch = make_map(wl, seed=1234 + rank)
     n, w = ch.n, wl["w"]
     px = band_pixels(n, wl["lower"], wl["upper"], w)

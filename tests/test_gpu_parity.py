@@ -264,3 +264,36 @@ def test_reciprocal_division_is_ieee_exact():
     bad = C.c_int64(-1)
     _lib.check(_lib.lib().pk_selftest_divide(0, 2_000_000_000, 12345, C.byref(bad)))
     assert bad.value == 0
+
+
+def test_c4_shape_matches_oracle(tmp_path):
+    """BASELINE config 4 shape at reduced length: 5 kb, upper=600, w=7 (15x15 windows),
+    the 200-tree bench forest; records bit-exact against the oracle."""
+    import io
+    from contextlib import redirect_stdout
+    import joblib
+    from oracle import peakachu_oracle as po
+    from peakachu_b200 import coolio, synth
+    from peakachu_b200.forest import FlatForest
+    from peakachu_b200.scoreUtils import Chromosome
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    flat = FlatForest.load(os.path.join(root, "bench_data", "c4_forest.npz"))
+    model = joblib.load(os.path.join(root, "bench_data", "c4.pkl"))
+    ch = synth.make_chromosome("chr1", 2200, seed=77, depth=300.0, band=640, n_loops=120, loop_max=550)
+    X = Chromosome.from_pixels(ch.bin1, ch.bin2, ch.count, ch.weights, ch.n, flat, lower=6, upper=600, cname="chr1",
+                               res=5000, width=7, sorted_pixels=True)
+    x, y, p, v = X.score_records(0.5)
+    path = os.path.join(str(tmp_path), "c4.pkcool")
+    coolio.PKCool.write(path, [ch], 5000)
+    lib = coolio.Cooler(path)
+    M = po.tocsr(lib.matrix(balance="weight", sparse=True).fetch("chr1"))
+    raw = po.tocsr(lib.matrix(balance=False, sparse=True).fetch("chr1"))
+    O = po.Chromosome(M, model=model, raw_M=raw, weights=ch.weights, lower=6, upper=600, cname="chr1", res=5000, width=7)
+    assert np.array_equal(X.exp_arr, O.exp_arr)
+    assert np.array_equal(X.ridx, O.ridx) and np.array_equal(X.cidx, O.cidx)
+    with redirect_stdout(io.StringIO()):
+        prob, val = O.score(0.5)
+    r, c = prob.nonzero()
+    assert np.array_equal(x, r) and np.array_equal(y, c)
+    assert np.array_equal(p, np.asarray(prob[r, c]).ravel()) and np.array_equal(v, np.asarray(val[r, c]).ravel())
+    X.close()
