@@ -469,11 +469,11 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         model = load_sklearn_model(wl["forest"])
         cpu_pass(wl, 600, 5, model)
-        dt, cpx, ccand, crows = cpu_pass(wl, 3 * args.cpu_bins, 100, model)
+        dt, cpx, ccand, crows = cpu_pass(wl, 6 * args.cpu_bins, 100, model)
         cpu = {"value": cpx / dt, "unit": "pixels/s", "cores": 1, "kind": "port",
                "sample": "one %d-bin chromosome of the same synthetic distribution (%d band px, %d candidates), "
                          "numpy oracle port of score_chromosome, 1 of %d host threads (the reference is "
-                         "single-threaded), %.1f s" % (3 * args.cpu_bins, cpx, ccand, os.cpu_count(), dt)}
+                         "single-threaded), %.1f s" % (6 * args.cpu_bins, cpx, ccand, os.cpu_count(), dt)}
 
     print(json.dumps({
         "metric": "candidate pixels scored/sec (window features + RF proba)",

@@ -675,9 +675,9 @@ static int settle_candidates(pk_chrom* c) {
             return PK_EUNSUPPORTED;
         }
         if (cand_small) PK_CHECK(reserve_candidates(c, c->n_cand + c->n_cand / 8 + 1024));
-        const int32_t keep1 = flags[1];
-        PK_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int32_t), c->stream));
-        PK_CUDA(cudaMemcpyAsync(c->d_flags + 1, &keep1, sizeof keep1, cudaMemcpyHostToDevice, c->stream));
+        // clear the two capacity flags, keep the rest (largest count, weight-range bit)
+        const int32_t keep[4] = {0, flags[1], flags[2], flags[3] & ~2};
+        PK_CUDA(cudaMemcpyAsync(c->d_flags, keep, sizeof keep, cudaMemcpyHostToDevice, c->stream));
         PK_CHECK(run_candidates(c, table_small ? flags[1] : 0));
     }
     pk_set_error("candidate scan did not settle");

@@ -80,7 +80,8 @@ struct pk_chrom {
     double* d_exp = nullptr;         // [ND]
     double* d_bg = nullptr;          // [ND]
     // [4]: 0 = a count exceeded the Poisson table, 1 = largest in-band count,
-    //      2 = expected fit failed, 3 = bit0 pixels not sorted / bit1 candidate buffer too small
+    //      2 = bit0 expected fit failed / bit1 diagonal too long / bit2 a weight outside [1e-45, 1e45],
+    //      3 = bit0 pixels not sorted / bit1 candidate buffer too small
     int32_t* d_flags = nullptr;
     // upload staging
     int32_t *d_b1 = nullptr, *d_b2 = nullptr, *d_cnt = nullptr;

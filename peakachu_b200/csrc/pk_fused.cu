@@ -31,6 +31,7 @@ struct FusedParams {
     int n_groups; int n_trees;
     uint8_t* keep; double* prob; int32_t* batch_win; unsigned long long* counters;
     unsigned long long* next;      // global work counter (candidates handed out)
+    const int32_t* flags;          // handle's device flags
 };
 
 // ---- mbarrier / bulk-copy PTX ------------------------------------------------
@@ -60,15 +61,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-template <int W, int P, int TPP, int TBN>
+template <int W, int P, int TPP, int TBN, int CH>
 struct FusedCfg {
     static constexpr int S = 2 * W + 1, F = S * S, NT = P * TPP, NW = NT / 32;
     static constexpr int NS = (2 * F + 31) / 32;              // gather slots per lane for a window pair
-    static constexpr int CHUNK = 4 * TPP;                     // trees walked per pixel per pass
+    static constexpr int CHUNK = CH * TPP;                    // trees walked per pixel per pass
     static constexpr size_t node_bytes = 2 * (size_t)TBN * 8;
     static constexpr size_t fea_bytes = (size_t)P * F * 4;
     static constexpr size_t scratch_bytes = (size_t)NW * 2 * F * 8;   // window scratch; reused for leaf hand-over
-    static_assert(TPP == 1 || scratch_bytes >= 2 * 4 * (size_t)P * 8, "leaf hand-over does not fit the window scratch");
+    static_assert(TPP == 1 || scratch_bytes >= 2 * CH * (size_t)P * 8, "leaf hand-over does not fit the window scratch");
     static size_t total(int ND, int n_trees) {
         return node_bytes + fea_bytes + 2 * (size_t)((ND + 1) & ~1) * 8 + scratch_bytes + (size_t)P * 4 +
                (size_t)n_trees * 4 + (size_t)((n_trees + 3) & ~3) + (size_t)((F + 1) & ~1) * 2 + (size_t)P + 64;
@@ -132,9 +133,9 @@ __device__ __forceinline__ void pk_step(uint32_t xrow_addr, uint32_t& addr, uint
         : "r"(xrow_addr));
 }
 
-template <int W, int P, int TPP, int TBN>
-__global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams prm) {
-    using Cfg = FusedCfg<W, P, TPP, TBN>;
+template <int W, int P, int TPP, int TBN, int CH, int OCC>
+__global__ void __launch_bounds__(P * TPP, OCC) k_score_fused(const FusedParams prm) {
+    using Cfg = FusedCfg<W, P, TPP, TBN, CH>;
     constexpr int S = Cfg::S, F = Cfg::F, NT = Cfg::NT, NW = Cfg::NW, NS = Cfg::NS, CHUNK = Cfg::CHUNK;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: node buffers (16 B aligned) | features | exp | per-warp window scratch | slot->candidate |
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
     uint16_t* s_lut = reinterpret_cast<uint16_t*>(s_depth + ((prm.n_trees + 3) & ~3));   // [F] cell order
     uint8_t* s_nan = reinterpret_cast<uint8_t*>(s_lut + ((F + 1) & ~1));     // [P]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_nan + P) + 15) & ~(uintptr_t)15);
-    double* s_lv = s_V;                                           // [2][4][P] leaf hand-over (phase B only)
+    double* s_lv = s_V;                                           // [2][CH][P] leaf hand-over (phase B only)
     __shared__ int s_nkept, s_take, s_done, s_expbad;
     __shared__ long long s_start;
 
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
     const bool resident = (G <= 2);
 
     // ---- one-time setup -----------------------------------------------------
-    if (tid == 0) s_expbad = 0;
+    if (tid == 0) s_expbad = prm.balanced ? (prm.flags[2] & 4) : 0;     // bit 2: a weight outside [1e-45, 1e45]
     __syncthreads();
     for (int i = tid; i < ND; i += NT) {
         const double e = prm.expv[i];
@@ -255,7 +256,6 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                 bool ok = cur.ok;
                 // balance the gathered counts and stage both windows in shared memory
                 int nz0 = 0, nz1 = 0;
-                bool odd = false;            // a value outside the range where pk_div_r is proven
                 {
                     const int x0 = __shfl_sync(0xffffffffu, x, 0), d0 = __shfl_sync(0xffffffffu, d, 0);
                     const int x1 = __shfl_sync(0xffffffffu, x, 16), d1 = __shfl_sync(0xffffffffu, d, 16);
@@ -277,7 +277,6 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                                              prm.balanced ? __ldg(prm.w + c) : 0.0, prm.balanced);
                             sts_f64(V0_addr + (uint32_t)(k * F + a * S + b) * 8u, v);
                             nzf = v != 0.0;
-                            odd |= nzf && !pk_div_safe(v);
                         }
                         const unsigned bal = __ballot_sync(0xffffffffu, nzf);
                         const unsigned m1 = __ballot_sync(0xffffffffu, k != 0);
@@ -288,7 +287,7 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                 // issue the next pair's loads now; they land while this pair is filtered
                 if (j0 + NW * 2 < take) pair_load(start, take, j0 + NW * 2, nxt);
                 __syncwarp();
-                const bool fastdiv = !__any_sync(0xffffffffu, odd) && !s_expbad;
+                const bool fastdiv = !s_expbad;      // weights and expected values inside pk_div_r's proven range
                 if (ok && (double)(half ? nz1 : nz0) < (double)F * 0.1) ok = false;   // utils.py:225
                 if (ok) {
                     double s = 0.0;                                            // utils.py:228 (numba order)
@@ -361,8 +360,9 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                         for (int jj = 4; jj >= 1; --jj)
                             q = __dadd_rn(q, __dmul_rn(__dadd_rn(t[pk_reflect(b - jj, S)], t[pk_reflect(b + jj, S)]), PK_GK[4 - jj]));
                         g[b] = q;
-                        has_nan |= isnan(q);
-                        mn = fmin(mn, q); mx = fmax(mx, q);
+                        has_nan |= (q != q);
+                        mn = (q < mn) ? q : mn;          // a NaN never wins a comparison; has_nan carries it
+                        mx = (q > mx) ? q : mx;
                     }
                 }
 #pragma unroll
@@ -437,38 +437,37 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                 const uint32_t buf_addr = smem_u32(buf);
                 const int t_end = grp.x + grp.y;
                 for (int tc = grp.x; tc < t_end; tc += CHUNK) {
-                    const int t = tc + 4 * sub;                // this thread's four trees
-                    double lv0 = 0.0, lv1 = 0.0, lv2 = 0.0, lv3 = 0.0;
-                    const bool e0 = t < t_end, e1 = t + 1 < t_end, e2 = t + 2 < t_end, e3 = t + 3 < t_end;
-                    if (mine && e0) {
+                    const int t = tc + CH * sub;               // this thread's CH trees
+                    double lv[CH];
+                    bool ex[CH];
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) { lv[k] = 0.0; ex[k] = t + k < t_end; }
+                    if (mine && ex[0]) {
                         if (fits && !warp_nan) {
                             // chains past the end of the group re-walk tree t and are dropped
-                            uint32_t a0 = buf_addr + (s_root[t] - gbase) * 8u;
-                            uint32_t a1 = buf_addr + (s_root[e1 ? t + 1 : t] - gbase) * 8u;
-                            uint32_t a2 = buf_addr + (s_root[e2 ? t + 2 : t] - gbase) * 8u;
-                            uint32_t a3 = buf_addr + (s_root[e3 ? t + 3 : t] - gbase) * 8u;
-                            int maxd = s_depth[t];
-                            if (e1) maxd = max(maxd, (int)s_depth[t + 1]);
-                            if (e2) maxd = max(maxd, (int)s_depth[t + 2]);
-                            if (e3) maxd = max(maxd, (int)s_depth[t + 3]);
-                            uint2 n0, n1, n2, n3;
-                            lds_node(a0, n0); lds_node(a1, n1); lds_node(a2, n2); lds_node(a3, n3);
-                            for (int lvl = 0; lvl < maxd; ++lvl) {
-                                pk_step(xrow_addr, a0, n0);
-                                pk_step(xrow_addr, a1, n1);
-                                pk_step(xrow_addr, a2, n2);
-                                pk_step(xrow_addr, a3, n3);
+                            uint32_t addr[CH];
+                            uint2 nd[CH];
+                            int maxd = 0;
+#pragma unroll
+                            for (int k = 0; k < CH; ++k) {
+                                const int tk = ex[k] ? t + k : t;
+                                addr[k] = buf_addr + (s_root[tk] - gbase) * 8u;
+                                maxd = max(maxd, (int)s_depth[tk]);
                             }
-                            lv0 = __hiloint2double((int)n0.y, (int)n0.x);
-                            lv1 = __hiloint2double((int)n1.y, (int)n1.x);
-                            lv2 = __hiloint2double((int)n2.y, (int)n2.x);
-                            lv3 = __hiloint2double((int)n3.y, (int)n3.x);
+#pragma unroll
+                            for (int k = 0; k < CH; ++k) lds_node(addr[k], nd[k]);
+                            for (int lvl = 0; lvl < maxd; ++lvl) {
+#pragma unroll
+                                for (int k = 0; k < CH; ++k) pk_step(xrow_addr, addr[k], nd[k]);
+                            }
+#pragma unroll
+                            for (int k = 0; k < CH; ++k) lv[k] = __hiloint2double((int)nd[k].y, (int)nd[k].x);
                         } else {
                             // general walk: NaN features follow missing_go_to_left; the tail of a tree
                             // larger than the staging buffer is read from global memory (L2)
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (t + k >= t_end) break;
+                            for (int k = 0; k < CH; ++k) {
+                                if (!ex[k]) continue;
                                 uint32_t p = s_root[t + k] - gbase;
                                 uint2 nd = p < staged ? buf[p] : __ldg(prm.nodes + gbase + p);
                                 while (PK_NODE_INTERNAL(nd.y)) {
@@ -477,16 +476,18 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                                     p += left ? 1u : PK_NODE_ROFF(nd.y);
                                     nd = p < staged ? buf[p] : __ldg(prm.nodes + gbase + p);
                                 }
-                                const double lv = __hiloint2double((int)nd.y, (int)nd.x);
-                                if (k == 0) lv0 = lv; else if (k == 1) lv1 = lv; else if (k == 2) lv2 = lv; else lv3 = lv;
+                                lv[k] = __hiloint2double((int)nd.y, (int)nd.x);
                             }
                         }
                     }
                     // After the last chunk of a group the buffer is handed back: one barrier covers
                     // "everyone is done with it", "the next group has landed" and the leaf hand-over.
                     const bool rotate = !resident && (tc + CHUNK >= t_end);
-                    double* lvb = s_lv + (size_t)lvpar * 4 * P;
-                    if (TPP == 2 && sub == 1 && mine) { lvb[pix] = lv0; lvb[P + pix] = lv1; lvb[2 * P + pix] = lv2; lvb[3 * P + pix] = lv3; }
+                    double* lvb = s_lv + (size_t)lvpar * CH * P;
+                    if (TPP == 2 && sub == 1 && mine) {
+#pragma unroll
+                        for (int k = 0; k < CH; ++k) lvb[k * P + pix] = lv[k];
+                    }
                     if (rotate && wib == 0) mbar_wait(&s_bar[(consumed + 1) & 1], ((consumed + 1) >> 1) & 1);
                     if (TPP == 2 || rotate) __syncthreads();
                     if (rotate) {
@@ -495,16 +496,13 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
                     }
                     // ordered accumulation: trees tc .. tc+CHUNK-1 in estimator order
                     if (mine && sub == 0) {
-                        acc = __dadd_rn(acc, lv0);
-                        if (e1) acc = __dadd_rn(acc, lv1);
-                        if (e2) acc = __dadd_rn(acc, lv2);
-                        if (e3) acc = __dadd_rn(acc, lv3);
+#pragma unroll
+                        for (int k = 0; k < CH; ++k)
+                            if (ex[k]) acc = __dadd_rn(acc, lv[k]);
                         if (TPP == 2) {
-                            const int t4 = tc + 4;
-                            if (t4 < t_end) acc = __dadd_rn(acc, lvb[pix]);
-                            if (t4 + 1 < t_end) acc = __dadd_rn(acc, lvb[P + pix]);
-                            if (t4 + 2 < t_end) acc = __dadd_rn(acc, lvb[2 * P + pix]);
-                            if (t4 + 3 < t_end) acc = __dadd_rn(acc, lvb[3 * P + pix]);
+#pragma unroll
+                            for (int k = 0; k < CH; ++k)
+                                if (tc + CH + k < t_end) acc = __dadd_rn(acc, lvb[k * P + pix]);
                         }
                     }
                     lvpar ^= 1;
@@ -525,19 +523,19 @@ __global__ void __launch_bounds__(P * TPP, 1) k_score_fused(const FusedParams pr
     }
 }
 
-template <int W, int P, int TPP, int TBN>
+template <int W, int P, int TPP, int TBN, int CH, int OCC>
 static int launch_fused_t(FusedParams prm, pk_forest* f, int ND, int sm_count, cudaStream_t stream) {
-    using Cfg = FusedCfg<W, P, TPP, TBN>;
+    using Cfg = FusedCfg<W, P, TPP, TBN, CH>;
     PK_CHECK(pk_forest_groups(f, TBN, Cfg::CHUNK, &prm.groups, &prm.n_groups));
     const size_t smem = Cfg::total(ND, prm.n_trees);
-    if (smem > 227 * 1024 - 64) { pk_set_error("fused kernel: %zu bytes of shared memory needed", smem); return PK_EUNSUPPORTED; }
+    if (OCC * (smem + 1024) > 228 * 1024) { pk_set_error("fused kernel: %zu bytes of shared memory needed (x%d per SM)", smem, OCC); return PK_EUNSUPPORTED; }
     static size_t attr_set = 0;      // largest dynamic size opted into so far
     if (smem > attr_set) {
-        PK_CUDA(cudaFuncSetAttribute(k_score_fused<W, P, TPP, TBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PK_CUDA(cudaFuncSetAttribute(k_score_fused<W, P, TPP, TBN, CH, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
-    unsigned grid = (unsigned)sm_count;        // persistent: CTAs without work exit at once
-    k_score_fused<W, P, TPP, TBN><<<grid, P * TPP, smem, stream>>>(prm);
+    unsigned grid = (unsigned)(sm_count * OCC);        // persistent: CTAs without work exit at once
+    k_score_fused<W, P, TPP, TBN, CH, OCC><<<grid, P * TPP, smem, stream>>>(prm);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
@@ -552,12 +550,15 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant) {
     prm.n_groups = 0; prm.n_trees = f->n_trees;
     prm.keep = c->d_keep; prm.prob = c->d_prob; prm.batch_win = c->d_batch_win; prm.counters = c->d_counters;
     prm.next = c->d_counters + 2;
+    prm.flags = c->d_flags;
     int sm = 148;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, c->device);
-    if (c->w == 5) return variant == 1 ? launch_fused_t<5, 256, 1, 4224>(prm, f, c->ND, sm, c->stream)
-                                       : launch_fused_t<5, 256, 2, 4224>(prm, f, c->ND, sm, c->stream);
-    if (c->w == 7) return variant == 1 ? launch_fused_t<7, 128, 1, 4224>(prm, f, c->ND, sm, c->stream)
-                                       : launch_fused_t<7, 128, 2, 4224>(prm, f, c->ND, sm, c->stream);
+    // variant 0: one CTA per SM, 256 pixels x 2 threads, 8-tree chunks (default)
+    // variant 1: two CTAs per SM out of phase (features of one overlap the forest of the other)
+    if (c->w == 5) return variant == 1 ? launch_fused_t<5, 112, 2, 2240, 2, 2>(prm, f, c->ND, sm, c->stream)
+                                       : launch_fused_t<5, 256, 2, 4224, 4, 1>(prm, f, c->ND, sm, c->stream);
+    if (c->w == 7) return variant == 1 ? launch_fused_t<7, 128, 1, 4224, 4, 1>(prm, f, c->ND, sm, c->stream)
+                                       : launch_fused_t<7, 128, 2, 4224, 4, 1>(prm, f, c->ND, sm, c->stream);
     return PK_EUNSUPPORTED;
 }
 

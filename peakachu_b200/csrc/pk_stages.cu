@@ -93,16 +93,25 @@ __global__ void __launch_bounds__(256) k_check_sorted(const int32_t* __restrict_
 }
 
 // valid[] bytes -> one bit per bin (word i covers bins 32i .. 32i+31); two padding words of 0
-__global__ void __launch_bounds__(256) k_valid_bits(const uint8_t* __restrict__ valid, int n, uint32_t* __restrict__ vbits,
-                                                    int n_words) {
+// Also raises flags[2] bit 2 when a finite non-zero weight lies outside [1e-45, 1e45]: balanced
+// values then stay inside the range where the feature kernel's reciprocal division is exact.
+__global__ void __launch_bounds__(256) k_valid_bits(const uint8_t* __restrict__ valid, const double* __restrict__ w,
+                                                    int balanced, int n, uint32_t* __restrict__ vbits, int n_words,
+                                                    int32_t* __restrict__ flags) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n_words) return;
     uint32_t m = 0;
+    bool wild = false;
     for (int b = 0; b < 32; ++b) {
         const int x = i * 32 + b;
         if (x < n && valid[x]) m |= 1u << b;
+        if (balanced && x < n) {
+            const double a = fabs(w[x]);
+            wild |= isfinite(a) && a != 0.0 && !(a >= 1e-45 && a <= 1e45);
+        }
     }
     vbits[i] = m;
+    if (wild) atomicOr(&flags[2], 4);
 }
 
 // ---------------------------------------------------------------------------
@@ -639,7 +648,8 @@ static int launch_diag_sums_t(pk_chrom* c, int n_words) {
 
 int pk_launch_diag_sums(pk_chrom* c) {
     const int n_words = (c->n + 31) / 32;
-    k_valid_bits<<<(n_words + 255) / 256, 256, 0, c->stream>>>(c->d_valid, c->n, c->d_vbits, n_words);
+    k_valid_bits<<<(n_words + 255) / 256, 256, 0, c->stream>>>(c->d_valid, c->d_w, c->balanced, c->n, c->d_vbits, n_words,
+                                                                c->d_flags);
     PK_CUDA(cudaGetLastError());
     // leaves of numpy's tree hold at least 57 elements
     if (c->n <= 57 * 1024) return launch_diag_sums_t<1024>(c, n_words);

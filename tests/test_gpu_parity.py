@@ -297,3 +297,27 @@ def test_c4_shape_matches_oracle(tmp_path):
     assert np.array_equal(x, r) and np.array_equal(y, c)
     assert np.array_equal(p, np.asarray(prob[r, c]).ravel()) and np.array_equal(v, np.asarray(val[r, c]).ravel())
     X.close()
+
+
+def test_forest_nan_features_follow_missing_go_to_left():
+    """sklearn routes NaN features by missing_go_to_left; the forest tap must
+    give the same leaves and probabilities on rows with NaNs."""
+    import torch
+    from peakachu_b200 import _lib
+    from peakachu_b200.scoreUtils import DeviceForest
+    case = Case("lowdepth")
+    model = case.model()
+    rng = np.random.default_rng(9)
+    X = rng.random((500, case.forest.n_features)).astype(np.float32)
+    X[rng.random(X.shape) < 0.15] = np.nan
+    X[:5] = np.nan
+    df = DeviceForest.of(case.forest, 0)
+    xs = torch.from_numpy(X).cuda()
+    leaves = torch.empty((X.shape[0], case.forest.n_trees), dtype=torch.int32, device="cuda")
+    proba = torch.empty(X.shape[0], dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().pk_forest_apply(df.handle, C.c_void_p(xs.data_ptr()), X.shape[0],
+                                          C.c_void_p(leaves.data_ptr()), C.c_void_p(proba.data_ptr()), None))
+    torch.cuda.synchronize()
+    want_leaves = np.stack([e.apply(X) for e in model.estimators_], axis=1)
+    assert np.array_equal(leaves.cpu().numpy(), want_leaves)
+    assert np.array_equal(proba.cpu().numpy(), model.predict_proba(X)[:, 1])
