@@ -321,3 +321,35 @@ def test_forest_nan_features_follow_missing_go_to_left():
     want_leaves = np.stack([e.apply(X) for e in model.estimators_], axis=1)
     assert np.array_equal(leaves.cpu().numpy(), want_leaves)
     assert np.array_equal(proba.cpu().numpy(), model.predict_proba(X)[:, 1])
+
+
+def test_edge_cases_empty_and_tiny():
+    """No pixels -> the reference raises in IsotonicRegression.fit, we raise PKError; an upper
+    bound below the lower bound -> no candidates, empty output; min_prob 1.0 -> no records."""
+    from peakachu_b200 import _lib
+    from peakachu_b200.scoreUtils import Chromosome
+    case = Case("tiny")
+    ch = case.chroms[0]
+    e = np.zeros(0, np.int32)
+    with pytest.raises(_lib.PKError, match="positive mean"):
+        X = Chromosome.from_pixels(e, e, e, np.ones(100), 100, case.forest, lower=6, upper=60, width=5,
+                                   sorted_pixels=True)
+        X.exp_arr
+    with pytest.raises(_lib.PKError, match="positive mean"):      # 4 bins: every diagonal has <= 10 entries
+        one = np.array([1], np.int32)
+        X = Chromosome.from_pixels(one * 0, one, one, np.ones(4), 4, case.forest, lower=6, upper=2, width=5,
+                                   sorted_pixels=True)
+        X.score_records(0.5)
+    # upper (clamped to n - 2w) below lower: nothing to scan
+    X = Chromosome.from_pixels(ch.bin1, ch.bin2, ch.count, ch.weights, ch.n, case.forest, lower=50, upper=20,
+                               width=5, sorted_pixels=True)
+    assert X.n_candidates == 0
+    x, y, p, v = X.score_records(0.5)
+    assert x.size == 0
+    X.close()
+    X = Chromosome.from_pixels(ch.bin1, ch.bin2, ch.count, ch.weights, ch.n, case.forest, lower=6, upper=60,
+                               width=5, sorted_pixels=True)
+    assert X.score_records(1.0)[0].size == 0          # probabilities never exceed 1
+    prob, val = X.score(thre=1.0)
+    assert prob.nnz == 0
+    X.close()
