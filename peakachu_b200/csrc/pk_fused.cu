@@ -61,9 +61,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-template <int W, int P, int TPP, int TBN, int CH>
+template <int W, int P, int TPP, int TBN, int CH, int NTH>
 struct FusedCfg {
-    static constexpr int S = 2 * W + 1, F = S * S, NT = P * TPP, NW = NT / 32;
+    static constexpr int S = 2 * W + 1, F = S * S, NT = NTH, NW = NT / 32;      // NTH >= P*TPP: extra warps only build features
+    static_assert(NTH >= P * TPP && NTH % 32 == 0, "thread count");
     static constexpr int NS = (2 * F + 31) / 32;              // gather slots per lane for a window pair
     static constexpr int CHUNK = CH * TPP;                    // trees walked per pixel per pass
     static constexpr size_t node_bytes = 2 * (size_t)TBN * 8;
@@ -133,9 +134,9 @@ __device__ __forceinline__ void pk_step(uint32_t xrow_addr, uint32_t& addr, uint
         : "r"(xrow_addr));
 }
 
-template <int W, int P, int TPP, int TBN, int CH, int OCC>
-__global__ void __launch_bounds__(P * TPP, OCC) k_score_fused(const FusedParams prm) {
-    using Cfg = FusedCfg<W, P, TPP, TBN, CH>;
+template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH>
+__global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm) {
+    using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH>;
     constexpr int S = Cfg::S, F = Cfg::F, NT = Cfg::NT, NW = Cfg::NW, NS = Cfg::NS, CHUNK = Cfg::CHUNK;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: node buffers (16 B aligned) | features | exp | per-warp window scratch | slot->candidate |
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(P * TPP, OCC) k_score_fused(const FusedParams 
         // ================= phase B: forest =================
         if (nkept > 0) {
             const int pix = tid % P, sub = tid / P;        // sub-thread `sub` walks trees [4*sub, 4*sub+4) of a chunk
-            const bool mine = pix < nkept;
+            const bool mine = tid < P * TPP && pix < nkept;
             const float* xrow = s_fea + (size_t)pix * F;
             const uint32_t xrow_addr = smem_u32(xrow);
             const bool warp_nan = __any_sync(0xffffffffu, mine && s_nan[pix]);
@@ -523,19 +524,19 @@ __global__ void __launch_bounds__(P * TPP, OCC) k_score_fused(const FusedParams 
     }
 }
 
-template <int W, int P, int TPP, int TBN, int CH, int OCC>
+template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH = P * TPP>
 static int launch_fused_t(FusedParams prm, pk_forest* f, int ND, int sm_count, cudaStream_t stream) {
-    using Cfg = FusedCfg<W, P, TPP, TBN, CH>;
+    using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH>;
     PK_CHECK(pk_forest_groups(f, TBN, Cfg::CHUNK, &prm.groups, &prm.n_groups));
     const size_t smem = Cfg::total(ND, prm.n_trees);
     if (OCC * (smem + 1024) > 228 * 1024) { pk_set_error("fused kernel: %zu bytes of shared memory needed (x%d per SM)", smem, OCC); return PK_EUNSUPPORTED; }
     static size_t attr_set = 0;      // largest dynamic size opted into so far
     if (smem > attr_set) {
-        PK_CUDA(cudaFuncSetAttribute(k_score_fused<W, P, TPP, TBN, CH, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PK_CUDA(cudaFuncSetAttribute(k_score_fused<W, P, TPP, TBN, CH, OCC, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
     unsigned grid = (unsigned)(sm_count * OCC);        // persistent: CTAs without work exit at once
-    k_score_fused<W, P, TPP, TBN, CH, OCC><<<grid, P * TPP, smem, stream>>>(prm);
+    k_score_fused<W, P, TPP, TBN, CH, OCC, NTH><<<grid, NTH, smem, stream>>>(prm);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
@@ -554,8 +555,8 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant) {
     int sm = 148;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, c->device);
     // variant 0: one CTA per SM, 256 pixels x 2 threads, 8-tree chunks (default)
-    // variant 1: two CTAs per SM out of phase (features of one overlap the forest of the other)
-    if (c->w == 5) return variant == 1 ? launch_fused_t<5, 112, 2, 2240, 2, 2>(prm, f, c->ND, sm, c->stream)
+    // variant 1: 24 warps (768 threads, <= 80 registers): 192 pixels, the extra warps only build features
+    if (c->w == 5) return variant == 1 ? launch_fused_t<5, 192, 2, 4224, 4, 1, 768>(prm, f, c->ND, sm, c->stream)
                                        : launch_fused_t<5, 256, 2, 4224, 4, 1>(prm, f, c->ND, sm, c->stream);
     if (c->w == 7) return variant == 1 ? launch_fused_t<7, 128, 1, 4224, 4, 1>(prm, f, c->ND, sm, c->stream)
                                        : launch_fused_t<7, 128, 2, 4224, 4, 1>(prm, f, c->ND, sm, c->stream);
