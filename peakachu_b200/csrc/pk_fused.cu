@@ -555,11 +555,11 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant) {
     int sm = 148;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, c->device);
     // variant 0: one CTA per SM, 256 pixels x 2 threads, 8-tree chunks (default)
-    // variant 1: 24 warps (768 threads, <= 80 registers): 192 pixels, the extra warps only build features
-    if (c->w == 5) return variant == 1 ? launch_fused_t<5, 192, 2, 4224, 4, 1, 768>(prm, f, c->ND, sm, c->stream)
+    // variant 1: experiments with other warp counts (extra warps only build features)
+    if (c->w == 5) return variant == 1 ? launch_fused_t<5, 224, 2, 4224, 4, 1, 640>(prm, f, c->ND, sm, c->stream)
                                        : launch_fused_t<5, 256, 2, 4224, 4, 1>(prm, f, c->ND, sm, c->stream);
-    if (c->w == 7) return variant == 1 ? launch_fused_t<7, 128, 1, 4224, 4, 1>(prm, f, c->ND, sm, c->stream)
-                                       : launch_fused_t<7, 128, 2, 4224, 4, 1>(prm, f, c->ND, sm, c->stream);
+    if (c->w == 7) return variant == 1 ? launch_fused_t<7, 128, 2, 4224, 4, 1, 256>(prm, f, c->ND, sm, c->stream)
+                                       : launch_fused_t<7, 128, 2, 3200, 2, 1, 384>(prm, f, c->ND, sm, c->stream);
     return PK_EUNSUPPORTED;
 }
 
