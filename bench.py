@@ -267,6 +267,7 @@ def main():
     ap.add_argument("--cpu-workers", type=int, default=32, help="processes of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused", type=int, default=-1, help="pk_set_tuning('fused'): -1 auto, 0 off, 1, 2")
+    ap.add_argument("--prune", type=int, default=1, help="pk_set_tuning('prune'): retire pixels that cannot exceed min_prob")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -288,6 +289,7 @@ def main():
     L = _lib.lib()
     _lib.require_device()
     _lib.check(L.pk_set_tuning(b"fused", args.fused))
+    _lib.check(L.pk_set_tuning(b"prune", args.prune))
     args.warmup = max(args.warmup, 3)
 
     flat = FlatForest.load(os.path.join(ROOT, "bench_data", wl["forest"] + "_forest.npz"))

@@ -165,7 +165,9 @@ int pk_stream_destroy(int device, void* stream);
 int pk_release_memory(void);
 
 /* process-wide tuning knob, for benchmarking: key "fused" = -1 auto (default),
- * 0 separate feature + forest kernels, 1 / 2 the two fused-kernel tile sizes */
+ * 0 separate feature + forest kernels, 1 / 2 the two fused-kernel tile sizes;
+ * key "prune" = 1 (default) lets the fused kernel stop walking trees for pixels whose
+ * probability can no longer exceed min_prob (emitted records are unaffected), 0 walks all */
 int pk_set_tuning(const char* key, int value);
 
 /* time spent (ms, CUDA events) in each stage of the last upload/fit/find/score of

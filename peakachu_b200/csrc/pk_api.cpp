@@ -25,7 +25,7 @@ int pk_launch_features(pk_chrom* c, double* d_fea64);
 int pk_launch_forest(const pk_forest* f, const float* X, const uint8_t* keep, int64_t n_rows, int32_t* leaves,
                      double* proba, cudaStream_t stream);
 int pk_launch_emit(pk_chrom* c, double thre);
-int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant);
+int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre);
 size_t pk_sort_temp_bytes(long long n);
 int pk_launch_sort_records(pk_chrom* c, long long n, unsigned long long* keys_in, unsigned long long* keys_out,
                            uint32_t* idx_in, uint32_t* idx_out, void* temp, size_t temp_bytes, unsigned char* packed,
@@ -45,9 +45,11 @@ extern "C" int pk_selftest_divide(int device, int64_t n, uint64_t seed, int64_t*
 
 // tuning knobs (pk_set_tuning): fused = -1 auto, 0 unfused kernels, 1 / 2 fused variants
 static int g_tune_fused = -1;
+static int g_tune_prune = 1;     // retire pixels that cannot exceed min_prob (exact for every emitted record)
 
 extern "C" int pk_set_tuning(const char* key, int value) {
     if (key && !strcmp(key, "fused")) { g_tune_fused = value; return PK_OK; }
+    if (key && !strcmp(key, "prune")) { g_tune_prune = value; return PK_OK; }
     pk_set_error("pk_set_tuning: unknown key %s", key ? key : "(null)");
     return PK_EINVAL;
 }
@@ -781,7 +783,7 @@ static int run_score(pk_chrom* c, pk_forest* f, double min_prob) {
     const bool fused = g_tune_fused != 0 && pk_fused_supported(c->w, f->n_trees);
     if (fused) {
         // features stay in shared memory; stage [4] reports the fused kernel, [5] is 0
-        PK_CHECK(pk_launch_fused(c, f, g_tune_fused == 2 ? 1 : 0));
+        PK_CHECK(pk_launch_fused(c, f, g_tune_fused == 2 ? 1 : 0, g_tune_prune ? min_prob : -1.0));
         PK_CUDA(cudaEventRecord(c->ev[8], s));
     } else {
         if (!c->n_cand_known) PK_CHECK(settle_candidates(c));

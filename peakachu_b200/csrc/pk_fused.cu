@@ -32,6 +32,7 @@ struct FusedParams {
     uint8_t* keep; double* prob; int32_t* batch_win; unsigned long long* counters;
     unsigned long long* next;      // global work counter (candidates handed out)
     const int32_t* flags;          // handle's device flags
+    double thre;                   // --minimum-prob: pixels that can no longer exceed it stop walking trees
 };
 
 // ---- mbarrier / bulk-copy PTX ------------------------------------------------
@@ -70,7 +71,7 @@ struct FusedCfg {
     static constexpr size_t node_bytes = 2 * (size_t)TBN * 8;
     static constexpr size_t fea_bytes = (size_t)P * F * 4;
     static constexpr size_t scratch_bytes = (size_t)NW * 2 * F * 8;   // window scratch; reused for leaf hand-over
-    static_assert(TPP == 1 || scratch_bytes >= 2 * CH * (size_t)P * 8, "leaf hand-over does not fit the window scratch");
+    static_assert(scratch_bytes >= ((TPP == 2 ? 2 * CH : 0) + 1) * (size_t)P * 8 + 4 * (size_t)P, "leaf hand-over does not fit the window scratch");
     static size_t total(int ND, int n_trees) {
         return node_bytes + fea_bytes + 2 * (size_t)((ND + 1) & ~1) * 8 + scratch_bytes + (size_t)P * 4 +
                (size_t)n_trees * 4 + (size_t)((n_trees + 3) & ~3) + (size_t)((F + 1) & ~1) * 2 + (size_t)P + 64;
@@ -153,8 +154,11 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
     uint16_t* s_lut = reinterpret_cast<uint16_t*>(s_depth + ((prm.n_trees + 3) & ~3));   // [F] cell order
     uint8_t* s_nan = reinterpret_cast<uint8_t*>(s_lut + ((F + 1) & ~1));     // [P]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_nan + P) + 15) & ~(uintptr_t)15);
-    double* s_lv = s_V;                                           // [2][CH][P] leaf hand-over (phase B only)
-    __shared__ int s_nkept, s_take, s_done, s_expbad;
+    // phase B reuses the window scratch: leaf hand-over, running sums, list of pixels still walking
+    double* s_lv = s_V;                                           // [2][CH][P] (TPP == 2)
+    double* s_acc = s_V + (TPP == 2 ? 2 * CH * P : 0);            // [P]
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_acc + P);    // [2][P]
+    __shared__ int s_nkept, s_take, s_done, s_expbad, s_wc[32];
     __shared__ long long s_start;
 
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -413,13 +417,17 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
 
         // ================= phase B: forest =================
         if (nkept > 0) {
-            const int pix = tid % P, sub = tid / P;        // sub-thread `sub` walks trees [4*sub, 4*sub+4) of a chunk
-            const bool mine = tid < P * TPP && pix < nkept;
-            const float* xrow = s_fea + (size_t)pix * F;
-            const uint32_t xrow_addr = smem_u32(xrow);
-            const bool warp_nan = __any_sync(0xffffffffu, mine && s_nan[pix]);
-            double acc = 0.0;
+            // A pixel whose running sum can no longer exceed min_prob (every leaf value is <= 1) stops
+            // walking trees: only pixels with prob > min_prob are ever emitted, and theirs stay exact.
+            // The survivors are re-packed onto the low threads after each tree group, so whole warps retire.
+            const int slot = tid % P, sub = tid / P;       // sub-thread `sub` walks trees [CH*sub, CH*sub+CH) of a chunk
+            const double T = (double)prm.n_trees;
+            const double die_below = prm.thre * T - 1e-9 * T;              // margin >> rounding of the sums
+            const bool prune = prm.thre > 0.0;
+            for (int i = tid; i < nkept; i += NT) { s_list[i] = (uint16_t)i; s_acc[i] = 0.0; }
+            int na = nkept, cur = 0;
             int lvpar = 0;
+            __syncthreads();
             // one warp polls the mbarrier, the others wait at the CTA barrier (no spinning warps)
             if (!resident || first_batch) {
                 if (wib == 0) {
@@ -439,6 +447,11 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                 const int t_end = grp.x + grp.y;
                 for (int tc = grp.x; tc < t_end; tc += CHUNK) {
                     const int t = tc + CH * sub;               // this thread's CH trees
+                    const bool mine = tid < P * TPP && slot < na;
+                    const int pix = mine ? s_list[cur * P + slot] : 0;
+                    const float* xrow = s_fea + (size_t)pix * F;
+                    const uint32_t xrow_addr = fea_addr + (uint32_t)(pix * F) * 4u;
+                    const bool warp_nan = __any_sync(0xffffffffu, mine && s_nan[pix]);
                     double lv[CH];
                     bool ex[CH];
 #pragma unroll
@@ -487,7 +500,7 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                     double* lvb = s_lv + (size_t)lvpar * CH * P;
                     if (TPP == 2 && sub == 1 && mine) {
 #pragma unroll
-                        for (int k = 0; k < CH; ++k) lvb[k * P + pix] = lv[k];
+                        for (int k = 0; k < CH; ++k) lvb[k * P + slot] = lv[k];
                     }
                     if (rotate && wib == 0) mbar_wait(&s_bar[(consumed + 1) & 1], ((consumed + 1) >> 1) & 1);
                     if (TPP == 2 || rotate) __syncthreads();
@@ -497,19 +510,42 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                     }
                     // ordered accumulation: trees tc .. tc+CHUNK-1 in estimator order
                     if (mine && sub == 0) {
+                        double acc = s_acc[pix];
 #pragma unroll
                         for (int k = 0; k < CH; ++k)
                             if (ex[k]) acc = __dadd_rn(acc, lv[k]);
                         if (TPP == 2) {
 #pragma unroll
                             for (int k = 0; k < CH; ++k)
-                                if (tc + CH + k < t_end) acc = __dadd_rn(acc, lvb[k * P + pix]);
+                                if (tc + CH + k < t_end) acc = __dadd_rn(acc, lvb[k * P + slot]);
                         }
+                        s_acc[pix] = acc;
                     }
                     lvpar ^= 1;
                 }
+                // re-pack the pixels that can still exceed min_prob (possible once done > (1 - thre) T)
+                if (prune && gi + 1 < G && (double)t_end > T - prm.thre * T) {
+                    __syncthreads();                               // sums of this group are in s_acc
+                    const double remaining = T - (double)t_end;
+                    bool alive = false;
+                    int px = 0;
+                    if (tid < na) {
+                        px = s_list[cur * P + tid];
+                        alive = !(s_acc[px] + remaining < die_below);
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, alive);
+                    if (lane == 0) s_wc[wib] = __popc(bal);
+                    __syncthreads();
+                    int pre = 0, tot = 0;
+                    for (int k = 0; k < NW; ++k) { const int c = s_wc[k]; if (k < wib) pre += c; tot += c; }
+                    if (alive) s_list[(cur ^ 1) * P + pre + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)px;
+                    __syncthreads();
+                    na = tot;
+                    cur ^= 1;
+                }
             }
-            if (mine && sub == 0) prm.prob[s_idx[pix]] = __ddiv_rn(acc, (double)prm.n_trees);
+            __syncthreads();
+            if (tid < nkept) prm.prob[s_idx[tid]] = __ddiv_rn(s_acc[tid], T);      // partial (< min_prob) for retired pixels
             if (tid == 0) atomicAdd(&prm.counters[1], (unsigned long long)nkept);
             first_batch = false;
         }
@@ -541,7 +577,7 @@ static int launch_fused_t(FusedParams prm, pk_forest* f, int ND, int sm_count, c
     return PK_OK;
 }
 
-int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant) {
+int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre) {
     FusedParams prm;
     prm.band = c->d_band; prm.w = c->d_w; prm.expv = c->d_exp;
     prm.n = c->n; prm.pitch = c->pitch; prm.balanced = c->balanced; prm.ND = c->ND;
@@ -552,6 +588,7 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant) {
     prm.keep = c->d_keep; prm.prob = c->d_prob; prm.batch_win = c->d_batch_win; prm.counters = c->d_counters;
     prm.next = c->d_counters + 2;
     prm.flags = c->d_flags;
+    prm.thre = thre;
     int sm = 148;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, c->device);
     // variant 0: one CTA per SM, 256 pixels x 2 threads, 8-tree chunks (default)
