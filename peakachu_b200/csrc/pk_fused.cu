@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
             const double die_below = prm.thre * T - 1e-9 * T;              // margin >> rounding of the sums
             const bool prune = prm.thre > 0.0;
             for (int i = tid; i < nkept; i += NT) { s_list[i] = (uint16_t)i; s_acc[i] = 0.0; }
-            int na = nkept, cur = 0;
+            int na = nkept, cur = 0, last_pack = 0;
             int lvpar = 0;
             __syncthreads();
             // one warp polls the mbarrier, the others wait at the CTA barrier (no spinning warps)
@@ -524,7 +524,8 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                     lvpar ^= 1;
                 }
                 // re-pack the pixels that can still exceed min_prob (possible once done > (1 - thre) T)
-                if (prune && gi + 1 < G && (double)t_end > T - prm.thre * T) {
+                if (prune && gi + 1 < G && (double)t_end > T - prm.thre * T && t_end - last_pack >= 12) {
+                    last_pack = t_end;
                     __syncthreads();                               // sums of this group are in s_acc
                     const double remaining = T - (double)t_end;
                     bool alive = false;
