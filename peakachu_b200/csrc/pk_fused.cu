@@ -67,14 +67,22 @@ struct FusedCfg {
     static constexpr int S = 2 * W + 1, F = S * S, NT = NTH, NW = NT / 32;      // NTH >= P*TPP: extra warps only build features
     static_assert(NTH >= P * TPP && NTH % 32 == 0, "thread count");
     static constexpr int NS = (2 * F + 31) / 32;              // gather slots per lane for a window pair
+    static constexpr int NM = (F + 31) / 32;                  // cells per lane for one window
     static constexpr int CHUNK = CH * TPP;                    // trees walked per pixel per pass
     static constexpr size_t node_bytes = 2 * (size_t)TBN * 8;
+    // phase B hand-over area: leaf values of the second sub-thread, running sums, list of pixels still walking
+    static constexpr size_t hand_bytes = ((((TPP == 2 ? 2 * CH : 0) + 1) * (size_t)P * 8 + 4 * (size_t)P) + 15) & ~(size_t)15;
+    // The tree buffers and the hand-over area are dead during phase A: the float64 windows are staged there.
+    static constexpr size_t stage_bytes = node_bytes + hand_bytes;
+    static constexpr int PB_raw = (int)(stage_bytes / ((size_t)F * 8)) & ~1;
+    static constexpr int PB = PB_raw < P ? PB_raw : P;        // windows staged per take (even)
     static constexpr size_t fea_bytes = (size_t)P * F * 4;
-    static constexpr size_t scratch_bytes = (size_t)NW * 2 * F * 8;   // window scratch; reused for leaf hand-over
-    static_assert(scratch_bytes >= ((TPP == 2 ? 2 * CH : 0) + 1) * (size_t)P * 8 + 4 * (size_t)P, "leaf hand-over does not fit the window scratch");
+    static_assert(F * 4 >= S * 16, "row extrema do not fit a feature row");
+    static constexpr int NPW = (PB / 2 + NW - 1) / NW;        // window pairs per warp per take
     static size_t total(int ND, int n_trees) {
-        return node_bytes + fea_bytes + 2 * (size_t)((ND + 1) & ~1) * 8 + scratch_bytes + (size_t)P * 4 +
-               (size_t)n_trees * 4 + (size_t)((n_trees + 3) & ~3) + (size_t)((F + 1) & ~1) * 2 + (size_t)P + 64;
+        return stage_bytes + fea_bytes + 2 * (size_t)((ND + 1) & ~1) * 8 + (size_t)PB * 4 + 2 * (size_t)F * 8 +
+               (size_t)P * 4 + 2 * (size_t)PB * 4 + (size_t)n_trees * 4 + (size_t)((n_trees + 3) & ~3) + (size_t)PB * 2 +
+               (size_t)P + 64;
     }
 };
 
@@ -91,6 +99,15 @@ __device__ __forceinline__ double pk_div_r(double a, double b, double r) {
 }
 __device__ __forceinline__ bool pk_div_safe(double v) { return v >= 1e-100 && v <= 1e100; }   // false for NaN
 
+// order-preserving map double -> uint64 (integer min / max reductions) and back
+__device__ __forceinline__ unsigned long long pk_key(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
+}
+__device__ __forceinline__ double pk_unkey(unsigned long long k) {
+    return __longlong_as_double((long long)(k ^ ((k >> 63) ? 0x8000000000000000ull : ~0ull)));
+}
+
 // explicit shared-space accesses on 32-bit addresses: [reg + immediate], no generic-pointer arithmetic
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
     double v;
@@ -102,6 +119,15 @@ __device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
 }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
 }
 
 __device__ __forceinline__ void lds_node(uint32_t addr, uint2& nd) {
@@ -135,37 +161,49 @@ __device__ __forceinline__ void pk_step(uint32_t xrow_addr, uint32_t& addr, uint
         : "r"(xrow_addr));
 }
 
+#ifdef PK_FUSED_CLOCK
+#define PK_TICK(k) do { if (tid == 0) { const long long t_ = clock64(); clk[k] += t_ - t0; t0 = t_; } } while (0)
+#else
+#define PK_TICK(k) do { } while (0)
+#endif
+
 template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH>
 __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm) {
     using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH>;
-    constexpr int S = Cfg::S, F = Cfg::F, NT = Cfg::NT, NW = Cfg::NW, NS = Cfg::NS, CHUNK = Cfg::CHUNK;
+    constexpr int S = Cfg::S, F = Cfg::F, NT = Cfg::NT, NW = Cfg::NW, NS = Cfg::NS, NM = Cfg::NM, CHUNK = Cfg::CHUNK;
+    constexpr int PB = Cfg::PB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: node buffers (16 B aligned) | features | exp | per-warp window scratch | slot->candidate |
-    //         tree roots | tree depths | cell order | nan flags | barriers
+    // layout: [tree buffers | hand-over]  (= window staging during phase A) | features | exp | 1/exp |
+    //         candidate rank | gather order | slot->candidate | window distance |
+    //         window nonzeros | tree roots | tree depths | kept windows of a take | nan flags | barriers
     uint2* s_nodes = reinterpret_cast<uint2*>(smem_raw);
-    float* s_fea = reinterpret_cast<float*>(smem_raw + Cfg::node_bytes);
-    double* s_exp = reinterpret_cast<double*>(smem_raw + Cfg::node_bytes + Cfg::fea_bytes);
+    double* s_hand = reinterpret_cast<double*>(smem_raw + Cfg::node_bytes);
+    double* s_V = reinterpret_cast<double*>(smem_raw);            // [PB][F] float64, phase A only
+    float* s_fea = reinterpret_cast<float*>(smem_raw + Cfg::stage_bytes);
+    double* s_exp = reinterpret_cast<double*>(smem_raw + Cfg::stage_bytes + Cfg::fea_bytes);
     const int ND = prm.ND, NDp = (ND + 1) & ~1;
     double* s_rexp = s_exp + NDp;                                 // RN(1 / exp)
-    double* s_V = s_rexp + NDp;                                   // [NW][2][F] float64
-    int32_t* s_idx = reinterpret_cast<int32_t*>(s_V + (size_t)NW * 2 * F);   // [P]
-    uint32_t* s_root = reinterpret_cast<uint32_t*>(s_idx + P);    // [n_trees]
+    int32_t* s_rank = reinterpret_cast<int32_t*>(s_rexp + NDp);   // [PB] candidate rank (PB even)
+    int2* s_cell = reinterpret_cast<int2*>(s_rank + PB);          // [2F] gather order of a window pair
+    int32_t* s_idx = reinterpret_cast<int32_t*>(s_cell + 2 * F);  // [P]
+    int32_t* s_cd = s_idx + P;                                    // [PB]
+    int32_t* s_nz = s_cd + PB;                                    // [PB]
+    uint32_t* s_root = reinterpret_cast<uint32_t*>(s_nz + PB);    // [n_trees]
     uint8_t* s_depth = reinterpret_cast<uint8_t*>(s_root + prm.n_trees);     // [n_trees] (padded to 4)
-    uint16_t* s_lut = reinterpret_cast<uint16_t*>(s_depth + ((prm.n_trees + 3) & ~3));   // [F] cell order
-    uint8_t* s_nan = reinterpret_cast<uint8_t*>(s_lut + ((F + 1) & ~1));     // [P]
+    uint16_t* s_kl = reinterpret_cast<uint16_t*>(s_depth + ((prm.n_trees + 3) & ~3));    // [PB]
+    uint8_t* s_nan = reinterpret_cast<uint8_t*>(s_kl + PB);       // [P]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_nan + P) + 15) & ~(uintptr_t)15);
-    // phase B reuses the window scratch: leaf hand-over, running sums, list of pixels still walking
-    double* s_lv = s_V;                                           // [2][CH][P] (TPP == 2)
-    double* s_acc = s_V + (TPP == 2 ? 2 * CH * P : 0);            // [P]
+    // phase B: leaf hand-over, running sums, list of pixels still walking
+    double* s_lv = s_hand;                                        // [2][CH][P] (TPP == 2)
+    double* s_acc = s_hand + (TPP == 2 ? 2 * CH * P : 0);         // [P]
     uint16_t* s_list = reinterpret_cast<uint16_t*>(s_acc + P);    // [2][P]
-    __shared__ int s_nkept, s_take, s_done, s_expbad, s_wc[32];
+    __shared__ int s_nkt, s_take, s_done, s_expbad, s_wc[32];
     __shared__ long long s_start;
 
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const int half = lane >> 4, h = lane & 15;
     const int G = prm.n_groups;
     const long long n_cand = min(prm.ncand_dev[0], prm.cand_cap);
-    const bool resident = (G <= 2);
 
     // ---- one-time setup -----------------------------------------------------
     if (tid == 0) s_expbad = prm.balanced ? (prm.flags[2] & 4) : 0;     // bit 2: a weight outside [1e-45, 1e45]
@@ -177,21 +215,28 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
         if (!pk_div_safe(e)) s_expbad = 1;
     }
     for (int i = tid; i < prm.n_trees; i += NT) { s_root[i] = prm.roots[i]; s_depth[i] = prm.depth[i]; }
+    // Gather order of a window pair: cells by window diagonal (b - a), then along it -- contiguous
+    // in the band. Entry idx of [0, 2F): .x = band offset of the cell relative to (d * pitch + x - W),
+    // .y = byte offset in the pair's staging area | a << 16 | b << 20 | window << 24.
+    for (int idx = tid; idx < 2 * F; idx += NT) {
+        const int k = idx >= F, kk = idx - k * F;
+        int a = 0, b = 0, run = 0;
+        for (int df = -(S - 1); df <= S - 1; ++df) {
+            const int len = S - (df < 0 ? -df : df);
+            if (kk < run + len) { a = (df < 0 ? -df : 0) + (kk - run); b = a + df; break; }
+            run += len;
+        }
+        s_cell[idx] = make_int2((int)((long long)(b - a) * prm.pitch + a), ((k * F + a * S + b) * 8) | (a << 16) | (b << 20) | (k << 24));
+    }
     if (tid == 0) {
-        // cells ordered by window diagonal (b - a), then along it: contiguous in the band
-        int k = 0;
-        for (int df = -(S - 1); df <= S - 1; ++df)
-            for (int a = 0; a < S; ++a) {
-                int b = a + df;
-                if (b >= 0 && b < S) s_lut[k++] = (uint16_t)((a << 8) | b);
-            }
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
         mbar_fence_init();
-        s_done = 0;
     }
     __syncthreads();
-    uint32_t issued = 0, consumed = 0;     // stream positions of tree-group loads (uniform across threads)
+    // Tree groups are streamed through the two buffers; positions count group loads since the
+    // start of the kernel (uniform across threads). No load is in flight during phase A.
+    uint32_t issued = 0, consumed = 0;
     auto issue = [&](uint32_t pos) {
         if (tid == 0) {
             const int4 g = prm.groups[pos % G];
@@ -201,219 +246,306 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
             bulk_g2s(s_nodes + (size_t)(pos & 1) * TBN, prm.nodes + g.z, bytes, bar);
         }
     };
-    issue(0); issued = 1;
-    if (G > 1) { issue(1); issued = 2; }
-    bool first_batch = true;
 
-    const uint32_t V0_addr = smem_u32(s_V) + (uint32_t)(wib * 2 * F) * 8u;    // both windows of this warp
-    const uint32_t myV_addr = V0_addr + (uint32_t)(half * F) * 8u;
+    const uint32_t V_addr = smem_u32(s_V);
     const uint32_t exp_addr = smem_u32(s_exp), rexp_addr = smem_u32(s_rexp), fea_addr = smem_u32(s_fea);
 
-    // ---- gather of one window pair: issue the band loads (registers), consume later ----
-    struct Pair { int x, d; bool ok; int cnt[NS]; };
-    auto pair_load = [&](long long start, int take, int j0, Pair& pr) {
-        const int j = j0 + half;
-        const bool have = j < take;
-        pr.x = 0; pr.d = 0;
-        if (have) { pr.x = prm.cx[start + j]; pr.d = prm.cd[start + j]; }
-        pr.ok = have && (pr.x - W >= 0) && (pr.x + pr.d + W + 1 <= prm.n);      // scoreUtils.py:75
-        const int x0 = __shfl_sync(0xffffffffu, pr.x, 0), d0 = __shfl_sync(0xffffffffu, pr.d, 0);
-        const int x1 = __shfl_sync(0xffffffffu, pr.x, 16), d1 = __shfl_sync(0xffffffffu, pr.d, 16);
-        const bool ok0 = __shfl_sync(0xffffffffu, (int)pr.ok, 0), ok1 = __shfl_sync(0xffffffffu, (int)pr.ok, 16);
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            const int idx = s * 32 + lane;
-            const int k = idx >= F;
-            pr.cnt[s] = 0;
-            if (idx < 2 * F && (k ? ok1 : ok0)) {
-                const int cell = s_lut[idx - k * F];
-                const int a = cell >> 8, b = cell & 255;
-                const int xx = k ? x1 : x0, dd0 = k ? d1 : d0;
-                const int r = xx - W + a, c = xx + dd0 - W + b;
-                const int dd = c - r, ad = dd < 0 ? -dd : dd, lo = dd < 0 ? c : r;
-                if (ad < ND - 1) pr.cnt[s] = __ldg(prm.band + (long long)ad * prm.pitch + lo);   // scoreUtils.py:31
-            }
-        }
-    };
-
+    bool last = false;
+#ifdef PK_FUSED_CLOCK
+    long long clk[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t0 = clock64();
+#endif
     for (;;) {
         // ================= phase A: features =================
-        if (tid == 0) s_nkept = 0;
-        __syncthreads();
+        // Windows are staged PB at a time ("a take") in the shared memory the tree buffers use
+        // during phase B; every step below runs over the whole take with all threads.
+        int nkept = 0;
         for (;;) {
             if (tid == 0) {
-                int free_slots = P - s_nkept;
+                const int free_slots = min(P - nkept, PB);
                 long long st = (long long)atomicAdd(prm.next, (unsigned long long)free_slots);
                 long long rem = n_cand - st;
                 s_start = st;
                 s_take = rem <= 0 ? 0 : (int)(rem < free_slots ? rem : free_slots);
-                if (rem <= free_slots) s_done = 1;
+                s_done = rem <= free_slots;
+                s_nkt = 0;
             }
             __syncthreads();
+            PK_TICK(0);
             const int take = s_take;
             const long long start = s_start;
-            Pair cur, nxt;
-            if (wib * 2 < take) pair_load(start, take, wib * 2, cur);
-            for (int j0 = wib * 2; j0 < take; j0 += NW * 2) {
-                // ---- two candidates per warp, one per half ----
-                const long long ci = start + j0 + half;
-                const int x = cur.x, d = cur.d;
-                bool ok = cur.ok;
-                // balance the gathered counts and stage both windows in shared memory
-                int nz0 = 0, nz1 = 0;
-                {
-                    const int x0 = __shfl_sync(0xffffffffu, x, 0), d0 = __shfl_sync(0xffffffffu, d, 0);
-                    const int x1 = __shfl_sync(0xffffffffu, x, 16), d1 = __shfl_sync(0xffffffffu, d, 16);
-                    const bool ok0 = __shfl_sync(0xffffffffu, (int)ok, 0), ok1 = __shfl_sync(0xffffffffu, (int)ok, 16);
+            last = s_done != 0;
+            // ---- A1: gather + balance. A warp owns NPW window pairs of the take; all 32 lanes share the
+            //      2*F cells of a pair. Every band load of the take is issued before the first is used.
+            {
+                constexpr int NPW = Cfg::NPW;
+                int myx = 0, myd = 0;
+                bool myok = false;
+                if (lane < 2 * NPW) {
+                    const int i = 2 * (wib + (lane >> 1) * NW) + (lane & 1);
+                    if (i < take) {
+                        myx = prm.cx[start + i];
+                        myd = prm.cd[start + i];
+                        myok = (myx - W >= 0) && (myx + myd + W + 1 <= prm.n);         // scoreUtils.py:75
+                        s_rank[i] = __ldg(prm.crank + start + i);
+                    }
+                }
+#ifdef PK_FUSED_CLOCK
+                if (__shfl_sync(0xffffffffu, myx, 0) == -12345) clk[11] = 1;
+                PK_TICK(8);
+#endif
+                int cnt[NPW][NS];
+                double wr[NPW], wc[NPW];
+#pragma unroll
+                for (int q = 0; q < NPW; ++q) {
+                    const int x0 = __shfl_sync(0xffffffffu, myx, 2 * q), d0 = __shfl_sync(0xffffffffu, myd, 2 * q);
+                    const int x1 = __shfl_sync(0xffffffffu, myx, 2 * q + 1), d1 = __shfl_sync(0xffffffffu, myd, 2 * q + 1);
+                    const bool ok0 = __shfl_sync(0xffffffffu, (int)myok, 2 * q), ok1 = __shfl_sync(0xffffffffu, (int)myok, 2 * q + 1);
+                    // every cell of the window lies on a stored diagonal d + (b - a) in [0, ND - 2]
+                    const bool fa0 = d0 >= S - 1 && d0 + S - 1 < ND - 1, fa1 = d1 >= S - 1 && d1 + S - 1 < ND - 1;
+                    const long long base0 = (long long)d0 * prm.pitch + (x0 - W), base1 = (long long)d1 * prm.pitch + (x1 - W);
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
                         const int idx = s * 32 + lane;
-                        const int k = idx >= F;
-                        bool nzf = false;
-                        if (idx < 2 * F && (k ? ok1 : ok0)) {
-                            const int cell = s_lut[idx - k * F];
-                            const int a = cell >> 8, b = cell & 255;
-                            const int xx = k ? x1 : x0, dd0 = k ? d1 : d0;
-                            const int r = xx - W + a, c = xx + dd0 - W + b;
-                            double v = 0.0;
-                            const int cnt = cur.cnt[s];
-                            if (cnt != 0)
-                                v = pk_value(cnt, prm.balanced ? __ldg(prm.w + r) : 0.0,
-                                             prm.balanced ? __ldg(prm.w + c) : 0.0, prm.balanced);
-                            sts_f64(V0_addr + (uint32_t)(k * F + a * S + b) * 8u, v);
-                            nzf = v != 0.0;
+                        cnt[q][s] = 0;
+                        if (idx < 2 * F) {
+                            const int2 cell = s_cell[idx];
+                            const int k = cell.y >> 24;
+                            if (k ? ok1 : ok0) {
+                                if (k ? fa1 : fa0) {
+                                    cnt[q][s] = __ldg(prm.band + ((k ? base1 : base0) + cell.x));           // scoreUtils.py:31
+                                } else {
+                                    const int a = (cell.y >> 16) & 15, b = (cell.y >> 20) & 15;
+                                    const int xx = k ? x1 : x0, dd0 = k ? d1 : d0;
+                                    const int r = xx - W + a, c = xx + dd0 - W + b;
+                                    const int dd = c - r, ad = dd < 0 ? -dd : dd, lo = dd < 0 ? c : r;
+                                    if (ad < ND - 1) cnt[q][s] = __ldg(prm.band + (long long)ad * prm.pitch + lo);
+                                }
+                            }
                         }
-                        const unsigned bal = __ballot_sync(0xffffffffu, nzf);
-                        const unsigned m1 = __ballot_sync(0xffffffffu, k != 0);
+                    }
+                    // lane h of a half holds the row weight w[x - W + h] and the column weight w[x + d - W + h]
+                    wr[q] = 0.0; wc[q] = 0.0;
+                    const bool okh = half ? ok1 : ok0;
+                    if (prm.balanced && okh && h < S) {
+                        const int xh = half ? x1 : x0, dh = half ? d1 : d0;
+                        wr[q] = __ldg(prm.w + (xh - W + h));
+                        wc[q] = __ldg(prm.w + (xh + dh - W + h));
+                    }
+                }
+                PK_TICK(9);
+#pragma unroll
+                for (int q = 0; q < NPW; ++q) {
+                    const int j0 = 2 * (wib + q * NW);
+                    if (j0 >= take) break;                                    // uniform in the warp
+                    const uint32_t V0_addr = V_addr + (uint32_t)(j0 * F) * 8u;
+                    int nz0 = 0, nz1 = 0;
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        const int idx = s * 32 + lane;
+                        const bool valid = idx < 2 * F;
+                        const int celly = s_cell[valid ? idx : 0].y;
+                        const int k = celly >> 24;
+                        double v = (double)cnt[q][s];
+                        if (prm.balanced) {
+                            const double wa = __shfl_sync(0xffffffffu, wr[q], k * 16 + ((celly >> 16) & 15));
+                            const double wb = __shfl_sync(0xffffffffu, wc[q], k * 16 + ((celly >> 20) & 15));
+                            v = __dmul_rn(__dmul_rn(wa, wb), v);              // pk_value
+                            v = isfinite(v) ? v : 0.0;
+                        }
+                        if (cnt[q][s] == 0) v = 0.0;
+                        // windows that fail the border test are dropped in A2; their cells are not read
+                        if (valid) sts_f64(V0_addr + (uint32_t)(celly & 0xFFFF), v);
+                        const unsigned bal = __ballot_sync(0xffffffffu, valid && v != 0.0);
+                        // lanes of slot s that belong to the second window
+                        const unsigned m1 = (s * 32 >= F) ? 0xffffffffu : ((s + 1) * 32 <= F ? 0u : (0xffffffffu << (F - s * 32)));
                         nz0 += __popc(bal & ~m1);
                         nz1 += __popc(bal & m1);
                     }
-                }
-                // issue the next pair's loads now; they land while this pair is filtered
-                if (j0 + NW * 2 < take) pair_load(start, take, j0 + NW * 2, nxt);
-                __syncwarp();
-                const bool fastdiv = !s_expbad;      // weights and expected values inside pk_div_r's proven range
-                if (ok && (double)(half ? nz1 : nz0) < (double)F * 0.1) ok = false;   // utils.py:225
-                if (ok) {
-                    double s = 0.0;                                            // utils.py:228 (numba order)
-#pragma unroll
-                    for (int a = 0; a < W; ++a)
-#pragma unroll
-                        for (int b = 0; b < W; ++b) s = __dadd_rn(s, lds_f64(myV_addr + (uint32_t)(a * S + b) * 8u));
-                    const double ll = __ddiv_rn(s, (double)(W * W));
-                    ok = (ll > 0.0) && (__ddiv_rn(lds_f64(myV_addr + (uint32_t)(W * S + W) * 8u), ll) > 0.1);  // utils.py:229-232
-                }
-                const bool kept = ok;                                          // uniform within the half
-                const bool actk = kept && (h < S);
-                int slot = 0;
-                if (kept && h == 0) slot = atomicAdd(&s_nkept, 1);
-                slot = __shfl_sync(0xffffffffu, slot, half * 16);
-                double mn = CUDART_INF, mx = -CUDART_INF;
-                bool has_nan = false;
-                double g[S];
-                const uint32_t col_addr = myV_addr + (uint32_t)h * 8u;          // V[a][h] = col_addr + a*S*8
-                const uint32_t row_addr = myV_addr + (uint32_t)(h * S) * 8u;    // V[h][b] = row_addr + b*8
-                if (actk) {
-                    // distance normalisation (utils.py:187-200): V[a][h] / exp[|d + h - a|]
-                    double v[S];
-                    if (fastdiv && d + h >= S - 1) {
-                        // common case: d + h - a >= 0 for every a, so exp is read at fixed offsets
-                        const uint32_t e0 = exp_addr + (uint32_t)(d + h) * 8u, r0 = rexp_addr + (uint32_t)(d + h) * 8u;
-#pragma unroll
-                        for (int a = 0; a < S; ++a)
-                            v[a] = pk_div_r(lds_f64(col_addr + a * S * 8), lds_f64(e0 - a * 8), lds_f64(r0 - a * 8));
-                    } else if (fastdiv) {
-#pragma unroll
-                        for (int a = 0; a < S; ++a) {
-                            int dd = d + h - a;
-                            dd = dd < 0 ? -dd : dd;
-                            v[a] = pk_div_r(lds_f64(col_addr + a * S * 8), lds_f64(exp_addr + dd * 8), lds_f64(rexp_addr + dd * 8));
-                        }
-                    } else {
-#pragma unroll
-                        for (int a = 0; a < S; ++a) {
-                            int dd = d + h - a;
-                            dd = dd < 0 ? -dd : dd;
-                            v[a] = __ddiv_rn(lds_f64(col_addr + a * S * 8), lds_f64(exp_addr + dd * 8));
-                        }
-                    }
-                    // vertical pass in registers (column h)
-#pragma unroll
-                    for (int a = 0; a < S; ++a) {
-                        double t = __dmul_rn(v[a], PK_GK[4]);
-#pragma unroll
-                        for (int jj = 4; jj >= 1; --jj)
-                            t = __dadd_rn(t, __dmul_rn(__dadd_rn(v[pk_reflect(a - jj, S)], v[pk_reflect(a + jj, S)]), PK_GK[4 - jj]));
-                        g[a] = t;
+                    const bool okh = __shfl_sync(0xffffffffu, (int)myok, 2 * q + half) != 0;
+                    const int dh = __shfl_sync(0xffffffffu, myd, 2 * q + half);
+                    if (h == 0 && j0 + half < take) {
+                        s_nz[j0 + half] = okh ? (half ? nz1 : nz0) : -1;
+                        s_cd[j0 + half] = dh;
                     }
                 }
-                __syncwarp();                    // every lane has read its column (and the ll corner)
-                if (actk) {
-#pragma unroll
-                    for (int a = 0; a < S; ++a) sts_f64(col_addr + a * S * 8, g[a]);
-                }
-                __syncwarp();
-                if (actk) {
-                    // horizontal pass in registers (row h)
-                    double t[S];
-#pragma unroll
-                    for (int b = 0; b < S; ++b) t[b] = lds_f64(row_addr + b * 8);
-#pragma unroll
-                    for (int b = 0; b < S; ++b) {
-                        double q = __dmul_rn(t[b], PK_GK[4]);
-#pragma unroll
-                        for (int jj = 4; jj >= 1; --jj)
-                            q = __dadd_rn(q, __dmul_rn(__dadd_rn(t[pk_reflect(b - jj, S)], t[pk_reflect(b + jj, S)]), PK_GK[4 - jj]));
-                        g[b] = q;
-                        has_nan |= (q != q);
-                        mn = (q < mn) ? q : mn;          // a NaN never wins a comparison; has_nan carries it
-                        mx = (q > mx) ? q : mx;
-                    }
-                }
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) {
-                    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                    has_nan |= (bool)__shfl_xor_sync(0xffffffffu, (int)has_nan, o);
-                }
-                bool fnan = false;
-                if (actk) {
-                    if (has_nan) { mn = CUDART_NAN; mx = CUDART_NAN; }          // numba min/max propagate NaN
-                    const double range = __dsub_rn(mx, mn);
-                    const bool fr = pk_div_safe(range) && mx <= 1e100;         // else: plain IEEE division
-                    const uint32_t frow = fea_addr + (uint32_t)(slot * F + h * S) * 4u;
-                    if (fr) {
-                        const double rr = __ddiv_rn(1.0, range);
-#pragma unroll
-                        for (int b = 0; b < S; ++b)
-                            sts_f32(frow + b * 4, __double2float_rn(pk_div_r(__dsub_rn(g[b], mn), range, rr)));   // utils.py:207
-                    } else {
-#pragma unroll
-                        for (int b = 0; b < S; ++b) {
-                            const double q = __ddiv_rn(__dsub_rn(g[b], mn), range);
-                            fnan |= isnan(q);
-                            sts_f32(frow + b * 4, __double2float_rn(q));
-                        }
-                    }
-                }
-                // any NaN feature sends this pixel through the missing_go_to_left-aware walk
-                const unsigned nanbal = __ballot_sync(0xffffffffu, fnan);
-                if (kept && h == 0) {
-                    s_idx[slot] = (int)ci;
-                    s_nan[slot] = ((nanbal >> (half * 16)) & 0xffffu) ? 1 : 0;
-                    prm.keep[ci] = 1;
-                    atomicAdd(&prm.batch_win[prm.crank[ci] / PK_BATCH], 1);
-                }
-                __syncwarp();
-                cur = nxt;
+                PK_TICK(10);
             }
             __syncthreads();
-            const int nk_now = s_nkept, done_now = s_done;
-            __syncthreads();                       // everyone has read them before thread 0 grabs again
-            if (done_now || nk_now > P - P / 8) break;
+            PK_TICK(1);
+            // ---- A2: the reference's filters, one thread per window (spread over all warps)
+            {
+                const int i = lane * NW + wib;
+                if (i < take) {
+                    const int nz = s_nz[i];
+                    bool ok = nz >= 0 && !((double)nz < (double)F * 0.1);        // utils.py:225
+                    const uint32_t myV = V_addr + (uint32_t)(i * F) * 8u;
+                    if (ok) {
+                        double s = 0.0;                                            // utils.py:228 (numba order)
+#pragma unroll
+                        for (int a = 0; a < W; ++a)
+#pragma unroll
+                            for (int b = 0; b < W; ++b) s = __dadd_rn(s, lds_f64(myV + (uint32_t)(a * S + b) * 8u));
+                        const double ll = __ddiv_rn(s, (double)(W * W));
+                        ok = (ll > 0.0) && (__ddiv_rn(lds_f64(myV + (uint32_t)(W * S + W) * 8u), ll) > 0.1);  // utils.py:229-232
+                    }
+                    if (ok) {
+                        const int kl = atomicAdd(&s_nkt, 1);
+                        const long long ci = start + i;
+                        s_kl[kl] = (uint16_t)i;
+                        s_idx[nkept + kl] = (int)ci;
+                        prm.keep[ci] = 1;
+                        atomicAdd(&prm.batch_win[s_rank[i] / PK_BATCH], 1);
+                        s_nan[nkept + kl] = 0;
+                    }
+                }
+            }
+            __syncthreads();
+            PK_TICK(2);
+            const int nkt = s_nkt;
+            const bool fastdiv = !s_expbad;      // weights and expected values inside pk_div_r's proven range
+            // ---- A3: distance normalisation + vertical Gaussian pass, one thread per window column, in place
+            for (int item = tid; item < nkt * S; item += NT) {
+                const int kl = item / S, b = item - kl * S;
+                const int i = s_kl[kl];
+                const int d = s_cd[i];
+                const uint32_t col_addr = V_addr + (uint32_t)(i * F + b) * 8u;     // V[a][b] = col_addr + a*S*8
+                double v[S], g[S];
+                // utils.py:187-200: V[a][b] / exp[|d + b - a|]
+                if (fastdiv && d + b >= S - 1) {
+                    // common case: d + b - a >= 0 for every a, so exp is read at fixed offsets
+                    const uint32_t e0 = exp_addr + (uint32_t)(d + b) * 8u, r0 = rexp_addr + (uint32_t)(d + b) * 8u;
+#pragma unroll
+                    for (int a = 0; a < S; ++a)
+                        v[a] = pk_div_r(lds_f64(col_addr + a * S * 8), lds_f64(e0 - a * 8), lds_f64(r0 - a * 8));
+                } else if (fastdiv) {
+#pragma unroll
+                    for (int a = 0; a < S; ++a) {
+                        int dd = d + b - a;
+                        dd = dd < 0 ? -dd : dd;
+                        v[a] = pk_div_r(lds_f64(col_addr + a * S * 8), lds_f64(exp_addr + dd * 8), lds_f64(rexp_addr + dd * 8));
+                    }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < S; ++a) {
+                        int dd = d + b - a;
+                        dd = dd < 0 ? -dd : dd;
+                        v[a] = __ddiv_rn(lds_f64(col_addr + a * S * 8), lds_f64(exp_addr + dd * 8));
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < S; ++a) {
+                    double t = __dmul_rn(v[a], PK_GK[4]);
+#pragma unroll
+                    for (int jj = 4; jj >= 1; --jj)
+                        t = __dadd_rn(t, __dmul_rn(__dadd_rn(v[pk_reflect(a - jj, S)], v[pk_reflect(a + jj, S)]), PK_GK[4 - jj]));
+                    g[a] = t;
+                }
+#pragma unroll
+                for (int a = 0; a < S; ++a) sts_f64(col_addr + a * S * 8, g[a]);
+            }
+            __syncthreads();
+            PK_TICK(3);
+            // ---- A4: horizontal pass, one thread per window row, in place
+            for (int item = tid; item < nkt * S; item += NT) {
+                const int kl = item / S, a = item - kl * S;
+                const int i = s_kl[kl];
+                const uint32_t row_addr = V_addr + (uint32_t)(i * F + a * S) * 8u;
+                double t[S];
+#pragma unroll
+                for (int b = 0; b < S; ++b) t[b] = lds_f64(row_addr + b * 8);
+                double mn = CUDART_INF, mx = -CUDART_INF;
+                bool has_nan = false;
+#pragma unroll
+                for (int b = 0; b < S; ++b) {
+                    double q = __dmul_rn(t[b], PK_GK[4]);
+#pragma unroll
+                    for (int jj = 4; jj >= 1; --jj)
+                        q = __dadd_rn(q, __dmul_rn(__dadd_rn(t[pk_reflect(b - jj, S)], t[pk_reflect(b + jj, S)]), PK_GK[4 - jj]));
+                    sts_f64(row_addr + b * 8, q);
+                    has_nan |= (q != q);
+                    mn = (q < mn) ? q : mn;          // a NaN never wins a comparison; has_nan carries it
+                    mx = (q > mx) ? q : mx;
+                }
+                // row extrema as order-preserving keys, parked in the (still unused) feature row of the
+                // window's slot; all ones in the max: NaN seen (numba min/max propagate NaN)
+                const unsigned long long kmn = pk_key(mn), kmx = has_nan ? ~0ull : pk_key(mx);
+                const uint32_t tmp = fea_addr + (uint32_t)((nkept + kl) * F) * 4u + (uint32_t)a * 16u;
+                sts_u32(tmp, (uint32_t)kmn);
+                sts_u32(tmp + 4, (uint32_t)(kmn >> 32));
+                sts_u32(tmp + 8, (uint32_t)kmx);
+                sts_u32(tmp + 12, (uint32_t)(kmx >> 32));
+            }
+            __syncthreads();
+            PK_TICK(4);
+            // ---- A5: min-max scaling to float32 features (utils.py:202-207), one warp per window, two
+            //      windows interleaved
+            for (int kl0 = wib; kl0 < nkt; kl0 += 2 * NW) {
+                double mn[2], range[2], rr[2];
+                bool fr[2];
+                uint32_t win[2], frow[2];
+                bool have[2];
+                uint32_t klo[2][2], khi[2][2];          // [window][min, max]
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int kl = kl0 + u * NW;
+                    have[u] = kl < nkt;
+                    const int klc = have[u] ? kl : kl0;
+                    win[u] = V_addr + (uint32_t)(s_kl[klc] * F) * 8u + (uint32_t)lane * 8u;
+                    frow[u] = fea_addr + (uint32_t)((nkept + klc) * F) * 4u;
+                    klo[u][0] = 0xffffffffu; khi[u][0] = 0xffffffffu; klo[u][1] = 0u; khi[u][1] = 0u;
+                    if (lane < S) {
+                        const uint32_t tmp = frow[u] + (uint32_t)lane * 16u;
+                        klo[u][0] = lds_u32(tmp); khi[u][0] = lds_u32(tmp + 4);
+                        klo[u][1] = lds_u32(tmp + 8); khi[u][1] = lds_u32(tmp + 12);
+                    }
+                    frow[u] += (uint32_t)lane * 4u;
+                }
+                __syncwarp();                    // the parked extrema have been read; the rows are overwritten below
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    // 64-bit min / max over the warp: high words first, then low words among the ties
+                    const uint32_t hmin = __reduce_min_sync(0xffffffffu, khi[u][0]);
+                    const uint32_t lmin = __reduce_min_sync(0xffffffffu, khi[u][0] == hmin ? klo[u][0] : 0xffffffffu);
+                    const uint32_t hmax = __reduce_max_sync(0xffffffffu, khi[u][1]);
+                    const uint32_t lmax = __reduce_max_sync(0xffffffffu, khi[u][1] == hmax ? klo[u][1] : 0u);
+                    const unsigned long long kmin = ((unsigned long long)hmin << 32) | lmin, kmax = ((unsigned long long)hmax << 32) | lmax;
+                    double mx = pk_unkey(kmax);
+                    mn[u] = pk_unkey(kmin);
+                    if (kmax == ~0ull) { mn[u] = CUDART_NAN; mx = CUDART_NAN; }
+                    range[u] = __dsub_rn(mx, mn[u]);
+                    fr[u] = pk_div_safe(range[u]) && mx <= 1e100;              // else: plain IEEE division
+                    rr[u] = __ddiv_rn(1.0, range[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (!have[u]) continue;
+                    double gv[NM];
+#pragma unroll
+                    for (int m = 0; m < NM; ++m) gv[m] = (m * 32 + lane < F) ? lds_f64(win[u] + m * 256) : 0.0;
+                    if (fr[u]) {
+#pragma unroll
+                        for (int m = 0; m < NM; ++m)
+                            if (m * 32 + lane < F)
+                                sts_f32(frow[u] + m * 128, __double2float_rn(pk_div_r(__dsub_rn(gv[m], mn[u]), range[u], rr[u])));
+                    } else {
+                        bool fnan = false;
+#pragma unroll
+                        for (int m = 0; m < NM; ++m)
+                            if (m * 32 + lane < F) {
+                                const double q = __ddiv_rn(__dsub_rn(gv[m], mn[u]), range[u]);
+                                fnan |= isnan(q);
+                                sts_f32(frow[u] + m * 128, __double2float_rn(q));
+                            }
+                        // any NaN feature sends this pixel through the missing_go_to_left-aware walk
+                        if (fnan) s_nan[nkept + kl0 + u * NW] = 1;
+                    }
+                }
+            }
+            nkept += nkt;
+            __syncthreads();                     // the staging area and the grab variables are free again
+            PK_TICK(5);
+            if (last || nkept > P - P / 8) break;
         }
-        const int nkept = s_nkept;
-        const bool last = s_done != 0;
 
         // ================= phase B: forest =================
         if (nkept > 0) {
@@ -424,20 +556,20 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
             const double T = (double)prm.n_trees;
             const double die_below = prm.thre * T - 1e-9 * T;              // margin >> rounding of the sums
             const bool prune = prm.thre > 0.0;
+            // the staging area is dead: start streaming the forest into it (two groups ahead)
+            if (tid == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            {
+                const uint32_t target = consumed + (uint32_t)(G < 2 ? G : 2);
+                while (issued < target) { issue(issued); ++issued; }
+            }
             for (int i = tid; i < nkept; i += NT) { s_list[i] = (uint16_t)i; s_acc[i] = 0.0; }
             int na = nkept, cur = 0, last_pack = 0;
             int lvpar = 0;
-            __syncthreads();
             // one warp polls the mbarrier, the others wait at the CTA barrier (no spinning warps)
-            if (!resident || first_batch) {
-                if (wib == 0) {
-                    if (resident) { for (uint32_t q = 0; q < issued; ++q) mbar_wait(&s_bar[q & 1], 0); }
-                    else mbar_wait(&s_bar[consumed & 1], (consumed >> 1) & 1);
-                }
-                __syncthreads();
-            }
+            if (wib == 0) mbar_wait(&s_bar[consumed & 1], (consumed >> 1) & 1);
+            __syncthreads();
             for (int gi = 0; gi < G; ++gi) {
-                const uint32_t pos = resident ? (uint32_t)gi : consumed;
+                const uint32_t pos = consumed;
                 const int4 grp = prm.groups[gi];
                 const uint32_t gbase = (uint32_t)grp.z;
                 const bool fits = grp.w > 0;                   // every tree of the group is fully staged
@@ -496,17 +628,19 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                     }
                     // After the last chunk of a group the buffer is handed back: one barrier covers
                     // "everyone is done with it", "the next group has landed" and the leaf hand-over.
-                    const bool rotate = !resident && (tc + CHUNK >= t_end);
+                    const bool rotate = tc + CHUNK >= t_end;
                     double* lvb = s_lv + (size_t)lvpar * CH * P;
                     if (TPP == 2 && sub == 1 && mine) {
 #pragma unroll
                         for (int k = 0; k < CH; ++k) lvb[k * P + slot] = lv[k];
                     }
-                    if (rotate && wib == 0) mbar_wait(&s_bar[(consumed + 1) & 1], ((consumed + 1) >> 1) & 1);
+                    if (rotate && wib == 0 && consumed + 1 < issued) mbar_wait(&s_bar[(consumed + 1) & 1], ((consumed + 1) >> 1) & 1);
                     if (TPP == 2 || rotate) __syncthreads();
                     if (rotate) {
                         ++consumed;
-                        issue(issued); ++issued;     // refill the freed buffer with the group two positions ahead
+                        // refill the freed buffer with the group two positions ahead -- unless that group
+                        // belongs to the next batch, whose windows are staged here first
+                        if (gi + 2 < G) { issue(issued); ++issued; }
                     }
                     // ordered accumulation: trees tc .. tc+CHUNK-1 in estimator order
                     if (mine && sub == 0) {
@@ -548,17 +682,19 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
             __syncthreads();
             if (tid < nkept) prm.prob[s_idx[tid]] = __ddiv_rn(s_acc[tid], T);      // partial (< min_prob) for retired pixels
             if (tid == 0) atomicAdd(&prm.counters[1], (unsigned long long)nkept);
-            first_batch = false;
         }
+        PK_TICK(6);
         if (last) break;
         __syncthreads();
     }
-    // drain outstanding bulk copies before the CTA's shared memory is released
-    if (!resident) {
-        for (uint32_t pos = consumed; pos < issued; ++pos) mbar_wait(&s_bar[pos & 1], (pos >> 1) & 1);
-    } else if (first_batch) {
-        for (uint32_t pos = 0; pos < issued; ++pos) mbar_wait(&s_bar[pos & 1], 0);
+#ifdef PK_FUSED_CLOCK
+    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) {
+        printf("cta %d A1 detail: coords %lld issue %lld process %lld\n", blockIdx.x, clk[8], clk[9], clk[10]);
+        printf("cta %d cycles: grab %lld A1 %lld A2 %lld A3 %lld A4 %lld A5a %lld A5b %lld B %lld\n", blockIdx.x, clk[0], clk[1], clk[2],
+               clk[3], clk[4], clk[7], clk[5], clk[6]);
     }
+#endif
+    // every issued group has been waited for (issued == consumed after a batch): nothing to drain
 }
 
 template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH = P * TPP>
@@ -592,12 +728,12 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre) {
     prm.thre = thre;
     int sm = 148;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, c->device);
-    // variant 0: one CTA per SM, 256 pixels x 2 threads, 8-tree chunks (default)
-    // variant 1: experiments with other warp counts (extra warps only build features)
-    if (c->w == 5) return variant == 1 ? launch_fused_t<5, 224, 2, 4224, 4, 1, 640>(prm, f, c->ND, sm, c->stream)
+    // variant 0: one CTA per SM, 256 (w=5) / 128 (w=7) pixels per batch, 16 warps
+    // variant 1: other warp counts / staging sizes (tuning knob)
+    if (c->w == 5) return variant == 1 ? launch_fused_t<5, 256, 2, 4224, 4, 1, 768>(prm, f, c->ND, sm, c->stream)
                                        : launch_fused_t<5, 256, 2, 4224, 4, 1>(prm, f, c->ND, sm, c->stream);
-    if (c->w == 7) return variant == 1 ? launch_fused_t<7, 128, 2, 4224, 4, 1, 256>(prm, f, c->ND, sm, c->stream)
-                                       : launch_fused_t<7, 128, 2, 3200, 2, 1, 384>(prm, f, c->ND, sm, c->stream);
+    if (c->w == 7) return variant == 1 ? launch_fused_t<7, 128, 2, 3200, 2, 1, 384>(prm, f, c->ND, sm, c->stream)
+                                       : launch_fused_t<7, 128, 2, 4224, 4, 1, 512>(prm, f, c->ND, sm, c->stream);
     return PK_EUNSUPPORTED;
 }
 
