@@ -43,7 +43,7 @@ extern "C" int pk_selftest_divide(int device, int64_t n, uint64_t seed, int64_t*
     return PK_OK;
 }
 
-// tuning knobs (pk_set_tuning): fused = -1 auto, 0 unfused kernels, 1 / 2 fused variants
+// tuning knobs (pk_set_tuning): fused = -1 auto, 0 unfused kernels, 1 + v: fused kernel variant v
 static int g_tune_fused = -1;
 static int g_tune_prune = 1;     // retire pixels that cannot exceed min_prob (exact for every emitted record)
 
@@ -783,7 +783,7 @@ static int run_score(pk_chrom* c, pk_forest* f, double min_prob) {
     const bool fused = g_tune_fused != 0 && pk_fused_supported(c->w, f->n_trees);
     if (fused) {
         // features stay in shared memory; stage [4] reports the fused kernel, [5] is 0
-        PK_CHECK(pk_launch_fused(c, f, g_tune_fused == 2 ? 1 : 0, g_tune_prune ? min_prob : -1.0));
+        PK_CHECK(pk_launch_fused(c, f, g_tune_fused > 1 ? g_tune_fused - 1 : 0, g_tune_prune ? min_prob : -1.0));
         PK_CUDA(cudaEventRecord(c->ev[8], s));
     } else {
         if (!c->n_cand_known) PK_CHECK(settle_candidates(c));

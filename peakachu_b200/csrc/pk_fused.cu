@@ -62,7 +62,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-template <int W, int P, int TPP, int TBN, int CH, int NTH>
+template <int W, int P, int TPP, int TBN, int CH, int NTH, int NGR = 2, int XSTAGE = 0>
 struct FusedCfg {
     static constexpr int S = 2 * W + 1, F = S * S, NT = NTH, NW = NT / 32;      // NTH >= P*TPP: extra warps only build features
     static_assert(NTH >= P * TPP && NTH % 32 == 0, "thread count");
@@ -73,16 +73,20 @@ struct FusedCfg {
     // phase B hand-over area: leaf values of the second sub-thread, running sums, list of pixels still walking
     static constexpr size_t hand_bytes = ((((TPP == 2 ? 2 * CH : 0) + 1) * (size_t)P * 8 + 4 * (size_t)P) + 15) & ~(size_t)15;
     // The tree buffers and the hand-over area are dead during phase A: the float64 windows are staged there.
-    static constexpr size_t stage_bytes = node_bytes + hand_bytes;
-    static constexpr int PB_raw = (int)(stage_bytes / ((size_t)F * 8)) & ~1;
-    static constexpr int PB = PB_raw < P ? PB_raw : P;        // windows staged per take (even)
+    static constexpr size_t stage_bytes = node_bytes + hand_bytes + XSTAGE;   // XSTAGE: extra staging when shared memory is left
+    // NG groups of warps build features independently (own staging buffer, own named barrier), so one
+    // group's band gather overlaps the other's arithmetic
+    static constexpr int NG = NGR, NTG = NT / NG, NWG = NW / NG;
+    static_assert(NW % NG == 0, "warps per group");
+    static constexpr int PB_raw = (int)(stage_bytes / NG / ((size_t)F * 8)) & ~1;
+    static constexpr int PB = PB_raw < P ? PB_raw : P;        // windows staged per take and group (even)
     static constexpr size_t fea_bytes = (size_t)P * F * 4;
     static_assert(F * 4 >= S * 16, "row extrema do not fit a feature row");
-    static constexpr int NPW = (PB / 2 + NW - 1) / NW;        // window pairs per warp per take
+    static constexpr int NPW = (PB / 2 + NWG - 1) / NWG;      // window pairs per warp per take
     static size_t total(int ND, int n_trees) {
-        return stage_bytes + fea_bytes + 2 * (size_t)((ND + 1) & ~1) * 8 + (size_t)PB * 4 + 2 * (size_t)F * 8 +
-               (size_t)P * 4 + 2 * (size_t)PB * 4 + (size_t)n_trees * 4 + (size_t)((n_trees + 3) & ~3) + (size_t)PB * 2 +
-               (size_t)P + 64;
+        return stage_bytes + fea_bytes + 2 * (size_t)((ND + 1) & ~1) * 8 + (size_t)NG * PB * 4 + 2 * (size_t)F * 8 +
+               (size_t)P * 4 + 2 * (size_t)NG * PB * 4 + (size_t)n_trees * 4 + (size_t)((n_trees + 3) & ~3) +
+               2 * (size_t)NG * PB * 2 + (size_t)P + 64;
     }
 };
 
@@ -167,41 +171,47 @@ __device__ __forceinline__ void pk_step(uint32_t xrow_addr, uint32_t& addr, uint
 #define PK_TICK(k) do { } while (0)
 #endif
 
-template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH>
+template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH, int NGR, int XSTAGE>
 __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm) {
-    using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH>;
+    using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH, NGR, XSTAGE>;
     constexpr int S = Cfg::S, F = Cfg::F, NT = Cfg::NT, NW = Cfg::NW, NS = Cfg::NS, NM = Cfg::NM, CHUNK = Cfg::CHUNK;
-    constexpr int PB = Cfg::PB;
+    constexpr int PB = Cfg::PB, NG = Cfg::NG, NTG = Cfg::NTG, NWG = Cfg::NWG;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [tree buffers | hand-over]  (= window staging during phase A) | features | exp | 1/exp |
     //         candidate rank | gather order | slot->candidate | window distance |
     //         window nonzeros | tree roots | tree depths | kept windows of a take | nan flags | barriers
     uint2* s_nodes = reinterpret_cast<uint2*>(smem_raw);
     double* s_hand = reinterpret_cast<double*>(smem_raw + Cfg::node_bytes);
-    double* s_V = reinterpret_cast<double*>(smem_raw);            // [PB][F] float64, phase A only
+    double* s_V = reinterpret_cast<double*>(smem_raw);            // [NG][PB][F] float64, phase A only
     float* s_fea = reinterpret_cast<float*>(smem_raw + Cfg::stage_bytes);
     double* s_exp = reinterpret_cast<double*>(smem_raw + Cfg::stage_bytes + Cfg::fea_bytes);
     const int ND = prm.ND, NDp = (ND + 1) & ~1;
     double* s_rexp = s_exp + NDp;                                 // RN(1 / exp)
-    int32_t* s_rank = reinterpret_cast<int32_t*>(s_rexp + NDp);   // [PB] candidate rank (PB even)
-    int2* s_cell = reinterpret_cast<int2*>(s_rank + PB);          // [2F] gather order of a window pair
+    int32_t* s_rank = reinterpret_cast<int32_t*>(s_rexp + NDp);   // [NG][PB] candidate rank (PB even)
+    int2* s_cell = reinterpret_cast<int2*>(s_rank + NG * PB);     // [2F] gather order of a window pair
     int32_t* s_idx = reinterpret_cast<int32_t*>(s_cell + 2 * F);  // [P]
-    int32_t* s_cd = s_idx + P;                                    // [PB]
-    int32_t* s_nz = s_cd + PB;                                    // [PB]
-    uint32_t* s_root = reinterpret_cast<uint32_t*>(s_nz + PB);    // [n_trees]
+    int32_t* s_cd = s_idx + P;                                    // [NG][PB]
+    int32_t* s_nz = s_cd + NG * PB;                               // [NG][PB]
+    uint32_t* s_root = reinterpret_cast<uint32_t*>(s_nz + NG * PB);   // [n_trees]
     uint8_t* s_depth = reinterpret_cast<uint8_t*>(s_root + prm.n_trees);     // [n_trees] (padded to 4)
-    uint16_t* s_kl = reinterpret_cast<uint16_t*>(s_depth + ((prm.n_trees + 3) & ~3));    // [PB]
-    uint8_t* s_nan = reinterpret_cast<uint8_t*>(s_kl + PB);       // [P]
+    uint16_t* s_kl = reinterpret_cast<uint16_t*>(s_depth + ((prm.n_trees + 3) & ~3));    // [NG][PB] kept windows of a take
+    uint16_t* s_ks = s_kl + NG * PB;                              // [NG][PB] their feature slots
+    uint8_t* s_nan = reinterpret_cast<uint8_t*>(s_ks + NG * PB);  // [P]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_nan + P) + 15) & ~(uintptr_t)15);
     // phase B: leaf hand-over, running sums, list of pixels still walking
     double* s_lv = s_hand;                                        // [2][CH][P] (TPP == 2)
     double* s_acc = s_hand + (TPP == 2 ? 2 * CH * P : 0);         // [P]
     uint16_t* s_list = reinterpret_cast<uint16_t*>(s_acc + P);    // [2][P]
-    __shared__ int s_nkt, s_take, s_done, s_expbad, s_wc[32];
-    __shared__ long long s_start;
+    __shared__ int s_gnkt[NG], s_gtake[NG], s_gstop[NG], s_reserved, s_nkept, s_done, s_expbad, s_wc[32];
+    __shared__ long long s_gstart[NG];
 
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const int half = lane >> 4, h = lane & 15;
+    const int grp = tid / NTG, gtid = tid - grp * NTG, gw = gtid >> 5;      // feature-building group
+    auto gsync = [&]() {
+        if (NG == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(NTG) : "memory");
+    };
     const int G = prm.n_groups;
     const long long n_cand = min(prm.ncand_dev[0], prm.cand_cap);
 
@@ -217,7 +227,8 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
     for (int i = tid; i < prm.n_trees; i += NT) { s_root[i] = prm.roots[i]; s_depth[i] = prm.depth[i]; }
     // Gather order of a window pair: cells by window diagonal (b - a), then along it -- contiguous
     // in the band. Entry idx of [0, 2F): .x = band offset of the cell relative to (d * pitch + x - W),
-    // .y = byte offset in the pair's staging area | a << 16 | b << 20 | window << 24.
+    // .y = byte offset in the pair's staging area | lane holding the row weight << 16 |
+    //      lane holding the column weight << 21 | window << 26.
     for (int idx = tid; idx < 2 * F; idx += NT) {
         const int k = idx >= F, kk = idx - k * F;
         int a = 0, b = 0, run = 0;
@@ -226,12 +237,13 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
             if (kk < run + len) { a = (df < 0 ? -df : 0) + (kk - run); b = a + df; break; }
             run += len;
         }
-        s_cell[idx] = make_int2((int)((long long)(b - a) * prm.pitch + a), ((k * F + a * S + b) * 8) | (a << 16) | (b << 20) | (k << 24));
+        s_cell[idx] = make_int2((int)((long long)(b - a) * prm.pitch + a), ((k * F + a * S + b) * 8) | ((k * 16 + a) << 16) | ((k * 16 + b) << 21) | (k << 26));
     }
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
         mbar_fence_init();
+        s_done = 0;
     }
     __syncthreads();
     // Tree groups are streamed through the two buffers; positions count group loads since the
@@ -247,7 +259,12 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
         }
     };
 
-    const uint32_t V_addr = smem_u32(s_V);
+    const uint32_t V_addr = smem_u32(s_V) + (uint32_t)(grp * PB * F) * 8u;     // this group's staging buffer
+    int32_t* g_rank = s_rank + grp * PB;
+    int32_t* g_cd = s_cd + grp * PB;
+    int32_t* g_nz = s_nz + grp * PB;
+    uint16_t* g_kl = s_kl + grp * PB;
+    uint16_t* g_ks = s_ks + grp * PB;
     const uint32_t exp_addr = smem_u32(s_exp), rexp_addr = smem_u32(s_rexp), fea_addr = smem_u32(s_fea);
 
     bool last = false;
@@ -256,24 +273,36 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
 #endif
     for (;;) {
         // ================= phase A: features =================
-        // Windows are staged PB at a time ("a take") in the shared memory the tree buffers use
-        // during phase B; every step below runs over the whole take with all threads.
-        int nkept = 0;
+        // Windows are staged PB at a time ("a take") in the shared memory the tree buffers use during
+        // phase B. Each group of warps runs its own takes; every step below runs over the whole take
+        // with all threads of the group.
+        if (tid == 0) { s_reserved = 0; s_nkept = 0; }
+        __syncthreads();
         for (;;) {
-            if (tid == 0) {
-                const int free_slots = min(P - nkept, PB);
-                long long st = (long long)atomicAdd(prm.next, (unsigned long long)free_slots);
-                long long rem = n_cand - st;
-                s_start = st;
-                s_take = rem <= 0 ? 0 : (int)(rem < free_slots ? rem : free_slots);
-                s_done = rem <= free_slots;
-                s_nkt = 0;
+            if (gtid == 0) {
+                // reserve feature slots, then candidates
+                const int prev = atomicAdd(&s_reserved, PB);
+                const int sz = max(0, min(PB, P - prev));
+                int take = 0;
+                long long st = 0;
+                bool stop = true;
+                if (sz > 0) {
+                    st = (long long)atomicAdd(prm.next, (unsigned long long)sz);
+                    const long long rem = n_cand - st;
+                    take = rem <= 0 ? 0 : (int)(rem < sz ? rem : sz);
+                    stop = rem <= sz;                      // every candidate has been handed out
+                    if (stop) s_done = 1;
+                }
+                s_gstart[grp] = st;
+                s_gtake[grp] = take;
+                s_gstop[grp] = stop;
+                s_gnkt[grp] = 0;
             }
-            __syncthreads();
+            gsync();
             PK_TICK(0);
-            const int take = s_take;
-            const long long start = s_start;
-            last = s_done != 0;
+            const int take = s_gtake[grp];
+            const long long start = s_gstart[grp];
+            const bool stop = s_gstop[grp] != 0;
             // ---- A1: gather + balance. A warp owns NPW window pairs of the take; all 32 lanes share the
             //      2*F cells of a pair. Every band load of the take is issued before the first is used.
             {
@@ -281,18 +310,25 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                 int myx = 0, myd = 0;
                 bool myok = false;
                 if (lane < 2 * NPW) {
-                    const int i = 2 * (wib + (lane >> 1) * NW) + (lane & 1);
+                    const int i = 2 * (gw + (lane >> 1) * NWG) + (lane & 1);
                     if (i < take) {
                         myx = prm.cx[start + i];
                         myd = prm.cd[start + i];
                         myok = (myx - W >= 0) && (myx + myd + W + 1 <= prm.n);         // scoreUtils.py:75
-                        s_rank[i] = __ldg(prm.crank + start + i);
+                        g_rank[i] = __ldg(prm.crank + start + i);
                     }
                 }
 #ifdef PK_FUSED_CLOCK
                 if (__shfl_sync(0xffffffffu, myx, 0) == -12345) clk[11] = 1;
                 PK_TICK(8);
 #endif
+                // this lane's cells of a pair (the same for every pair)
+                int cellx[NS], celly[NS];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const int2 cell = s_cell[min(s * 32 + lane, 2 * F - 1)];
+                    cellx[s] = cell.x; celly[s] = cell.y;
+                }
                 int cnt[NPW][NS];
                 double wr[NPW], wc[NPW];
 #pragma unroll
@@ -302,24 +338,28 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                     const bool ok0 = __shfl_sync(0xffffffffu, (int)myok, 2 * q), ok1 = __shfl_sync(0xffffffffu, (int)myok, 2 * q + 1);
                     // every cell of the window lies on a stored diagonal d + (b - a) in [0, ND - 2]
                     const bool fa0 = d0 >= S - 1 && d0 + S - 1 < ND - 1, fa1 = d1 >= S - 1 && d1 + S - 1 < ND - 1;
-                    const long long base0 = (long long)d0 * prm.pitch + (x0 - W), base1 = (long long)d1 * prm.pitch + (x1 - W);
+                    const int base0 = d0 * (int)prm.pitch + (x0 - W), base1 = d1 * (int)prm.pitch + (x1 - W);
+                    if (ok0 && ok1 && fa0 && fa1) {                         // uniform in the warp: the common case
 #pragma unroll
-                    for (int s = 0; s < NS; ++s) {
-                        const int idx = s * 32 + lane;
-                        cnt[q][s] = 0;
-                        if (idx < 2 * F) {
-                            const int2 cell = s_cell[idx];
-                            const int k = cell.y >> 24;
-                            if (k ? ok1 : ok0) {
-                                if (k ? fa1 : fa0) {
-                                    cnt[q][s] = __ldg(prm.band + ((k ? base1 : base0) + cell.x));           // scoreUtils.py:31
-                                } else {
-                                    const int a = (cell.y >> 16) & 15, b = (cell.y >> 20) & 15;
-                                    const int xx = k ? x1 : x0, dd0 = k ? d1 : d0;
-                                    const int r = xx - W + a, c = xx + dd0 - W + b;
-                                    const int dd = c - r, ad = dd < 0 ? -dd : dd, lo = dd < 0 ? c : r;
-                                    if (ad < ND - 1) cnt[q][s] = __ldg(prm.band + (long long)ad * prm.pitch + lo);
-                                }
+                        for (int s = 0; s < NS; ++s) {
+                            // window of this lane's cell: known at compile time except in the slot that straddles F
+                            const bool k = (s * 32 + 31 < F) ? false : ((s * 32 >= F) ? true : (lane >= F - s * 32));
+                            cnt[q][s] = 0;
+                            if (s * 32 + 31 < 2 * F || s * 32 + lane < 2 * F)
+                                cnt[q][s] = __ldg(prm.band + ((k ? base1 : base0) + cellx[s]));             // scoreUtils.py:31
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) {
+                            const int idx = s * 32 + lane;
+                            cnt[q][s] = 0;
+                            const int k = (celly[s] >> 26) & 1;
+                            if (idx < 2 * F && (k ? ok1 : ok0)) {
+                                const int a = (celly[s] >> 16) & 15, b = (celly[s] >> 21) & 15;
+                                const int xx = k ? x1 : x0, dd0 = k ? d1 : d0;
+                                const int r = xx - W + a, c = xx + dd0 - W + b;
+                                const int dd = c - r, ad = dd < 0 ? -dd : dd, lo = dd < 0 ? c : r;
+                                if (ad < ND - 1) cnt[q][s] = __ldg(prm.band + (long long)ad * prm.pitch + lo);
                             }
                         }
                     }
@@ -335,48 +375,44 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                 PK_TICK(9);
 #pragma unroll
                 for (int q = 0; q < NPW; ++q) {
-                    const int j0 = 2 * (wib + q * NW);
+                    const int j0 = 2 * (gw + q * NWG);
                     if (j0 >= take) break;                                    // uniform in the warp
                     const uint32_t V0_addr = V_addr + (uint32_t)(j0 * F) * 8u;
-                    int nz0 = 0, nz1 = 0;
+                    int nzp = 0;                                              // nonzeros: window 0 | window 1 << 16
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
-                        const int idx = s * 32 + lane;
-                        const bool valid = idx < 2 * F;
-                        const int celly = s_cell[valid ? idx : 0].y;
-                        const int k = celly >> 24;
+                        const bool valid = s * 32 + 31 < 2 * F || s * 32 + lane < 2 * F;
                         double v = (double)cnt[q][s];
                         if (prm.balanced) {
-                            const double wa = __shfl_sync(0xffffffffu, wr[q], k * 16 + ((celly >> 16) & 15));
-                            const double wb = __shfl_sync(0xffffffffu, wc[q], k * 16 + ((celly >> 20) & 15));
+                            const double wa = __shfl_sync(0xffffffffu, wr[q], (celly[s] >> 16) & 31);
+                            const double wb = __shfl_sync(0xffffffffu, wc[q], (celly[s] >> 21) & 31);
                             v = __dmul_rn(__dmul_rn(wa, wb), v);              // pk_value
                             v = isfinite(v) ? v : 0.0;
                         }
                         if (cnt[q][s] == 0) v = 0.0;
-                        // windows that fail the border test are dropped in A2; their cells are not read
-                        if (valid) sts_f64(V0_addr + (uint32_t)(celly & 0xFFFF), v);
-                        const unsigned bal = __ballot_sync(0xffffffffu, valid && v != 0.0);
-                        // lanes of slot s that belong to the second window
-                        const unsigned m1 = (s * 32 >= F) ? 0xffffffffu : ((s + 1) * 32 <= F ? 0u : (0xffffffffu << (F - s * 32)));
-                        nz0 += __popc(bal & ~m1);
-                        nz1 += __popc(bal & m1);
+                        // windows that fail the border test are dropped in A2; their cells are all zero
+                        if (valid) {
+                            sts_f64(V0_addr + (uint32_t)(celly[s] & 0xFFFF), v);
+                            if (v != 0.0) nzp += 1 << ((celly[s] >> 22) & 16);
+                        }
                     }
+                    nzp = __reduce_add_sync(0xffffffffu, nzp);
                     const bool okh = __shfl_sync(0xffffffffu, (int)myok, 2 * q + half) != 0;
                     const int dh = __shfl_sync(0xffffffffu, myd, 2 * q + half);
                     if (h == 0 && j0 + half < take) {
-                        s_nz[j0 + half] = okh ? (half ? nz1 : nz0) : -1;
-                        s_cd[j0 + half] = dh;
+                        g_nz[j0 + half] = okh ? ((nzp >> (16 * half)) & 0xFFFF) : -1;
+                        g_cd[j0 + half] = dh;
                     }
                 }
                 PK_TICK(10);
             }
-            __syncthreads();
+            gsync();
             PK_TICK(1);
             // ---- A2: the reference's filters, one thread per window (spread over all warps)
             {
-                const int i = lane * NW + wib;
+                const int i = lane * NWG + gw;
                 if (i < take) {
-                    const int nz = s_nz[i];
+                    const int nz = g_nz[i];
                     bool ok = nz >= 0 && !((double)nz < (double)F * 0.1);        // utils.py:225
                     const uint32_t myV = V_addr + (uint32_t)(i * F) * 8u;
                     if (ok) {
@@ -389,25 +425,28 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                         ok = (ll > 0.0) && (__ddiv_rn(lds_f64(myV + (uint32_t)(W * S + W) * 8u), ll) > 0.1);  // utils.py:229-232
                     }
                     if (ok) {
-                        const int kl = atomicAdd(&s_nkt, 1);
+                        const int kl = atomicAdd(&s_gnkt[grp], 1);
+                        const int slot = atomicAdd(&s_nkept, 1);
                         const long long ci = start + i;
-                        s_kl[kl] = (uint16_t)i;
-                        s_idx[nkept + kl] = (int)ci;
+                        g_kl[kl] = (uint16_t)i;
+                        g_ks[kl] = (uint16_t)slot;
+                        s_idx[slot] = (int)ci;
                         prm.keep[ci] = 1;
-                        atomicAdd(&prm.batch_win[s_rank[i] / PK_BATCH], 1);
-                        s_nan[nkept + kl] = 0;
+                        atomicAdd(&prm.batch_win[g_rank[i] / PK_BATCH], 1);
+                        s_nan[slot] = 0;
                     }
                 }
             }
-            __syncthreads();
+            gsync();
             PK_TICK(2);
-            const int nkt = s_nkt;
+            const int nkt = s_gnkt[grp];
+            if (gtid == 0 && nkt < take) atomicSub(&s_reserved, take - nkt);    // rejected windows free their slots
             const bool fastdiv = !s_expbad;      // weights and expected values inside pk_div_r's proven range
             // ---- A3: distance normalisation + vertical Gaussian pass, one thread per window column, in place
-            for (int item = tid; item < nkt * S; item += NT) {
+            for (int item = gtid; item < nkt * S; item += NTG) {
                 const int kl = item / S, b = item - kl * S;
-                const int i = s_kl[kl];
-                const int d = s_cd[i];
+                const int i = g_kl[kl];
+                const int d = g_cd[i];
                 const uint32_t col_addr = V_addr + (uint32_t)(i * F + b) * 8u;     // V[a][b] = col_addr + a*S*8
                 double v[S], g[S];
                 // utils.py:187-200: V[a][b] / exp[|d + b - a|]
@@ -443,12 +482,12 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
 #pragma unroll
                 for (int a = 0; a < S; ++a) sts_f64(col_addr + a * S * 8, g[a]);
             }
-            __syncthreads();
+            gsync();
             PK_TICK(3);
             // ---- A4: horizontal pass, one thread per window row, in place
-            for (int item = tid; item < nkt * S; item += NT) {
+            for (int item = gtid; item < nkt * S; item += NTG) {
                 const int kl = item / S, a = item - kl * S;
-                const int i = s_kl[kl];
+                const int i = g_kl[kl];
                 const uint32_t row_addr = V_addr + (uint32_t)(i * F + a * S) * 8u;
                 double t[S];
 #pragma unroll
@@ -469,29 +508,31 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                 // row extrema as order-preserving keys, parked in the (still unused) feature row of the
                 // window's slot; all ones in the max: NaN seen (numba min/max propagate NaN)
                 const unsigned long long kmn = pk_key(mn), kmx = has_nan ? ~0ull : pk_key(mx);
-                const uint32_t tmp = fea_addr + (uint32_t)((nkept + kl) * F) * 4u + (uint32_t)a * 16u;
+                const uint32_t tmp = fea_addr + (uint32_t)(g_ks[kl] * F) * 4u + (uint32_t)a * 16u;
                 sts_u32(tmp, (uint32_t)kmn);
                 sts_u32(tmp + 4, (uint32_t)(kmn >> 32));
                 sts_u32(tmp + 8, (uint32_t)kmx);
                 sts_u32(tmp + 12, (uint32_t)(kmx >> 32));
             }
-            __syncthreads();
+            gsync();
             PK_TICK(4);
             // ---- A5: min-max scaling to float32 features (utils.py:202-207), one warp per window, two
             //      windows interleaved
-            for (int kl0 = wib; kl0 < nkt; kl0 += 2 * NW) {
+            for (int kl0 = gw; kl0 < nkt; kl0 += 2 * NWG) {
                 double mn[2], range[2], rr[2];
                 bool fr[2];
                 uint32_t win[2], frow[2];
+                int slot[2];
                 bool have[2];
                 uint32_t klo[2][2], khi[2][2];          // [window][min, max]
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    const int kl = kl0 + u * NW;
+                    const int kl = kl0 + u * NWG;
                     have[u] = kl < nkt;
                     const int klc = have[u] ? kl : kl0;
-                    win[u] = V_addr + (uint32_t)(s_kl[klc] * F) * 8u + (uint32_t)lane * 8u;
-                    frow[u] = fea_addr + (uint32_t)((nkept + klc) * F) * 4u;
+                    win[u] = V_addr + (uint32_t)(g_kl[klc] * F) * 8u + (uint32_t)lane * 8u;
+                    slot[u] = g_ks[klc];
+                    frow[u] = fea_addr + (uint32_t)(slot[u] * F) * 4u;
                     klo[u][0] = 0xffffffffu; khi[u][0] = 0xffffffffu; klo[u][1] = 0u; khi[u][1] = 0u;
                     if (lane < S) {
                         const uint32_t tmp = frow[u] + (uint32_t)lane * 16u;
@@ -537,15 +578,17 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                                 sts_f32(frow[u] + m * 128, __double2float_rn(q));
                             }
                         // any NaN feature sends this pixel through the missing_go_to_left-aware walk
-                        if (fnan) s_nan[nkept + kl0 + u * NW] = 1;
+                        if (fnan) s_nan[slot[u]] = 1;
                     }
                 }
             }
-            nkept += nkt;
-            __syncthreads();                     // the staging area and the grab variables are free again
+            if (stop) break;                     // uniform in the group
+            gsync();                             // the staging buffer and the grab variables are free again
             PK_TICK(5);
-            if (last || nkept > P - P / 8) break;
         }
+        __syncthreads();
+        const int nkept = s_nkept;
+        last = s_done != 0;
 
         // ================= phase B: forest =================
         if (nkept > 0) {
@@ -697,19 +740,19 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
     // every issued group has been waited for (issued == consumed after a batch): nothing to drain
 }
 
-template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH = P * TPP>
+template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH = P * TPP, int NGR = 2, int XSTAGE = 0>
 static int launch_fused_t(FusedParams prm, pk_forest* f, int ND, int sm_count, cudaStream_t stream) {
-    using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH>;
+    using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH, NGR, XSTAGE>;
     PK_CHECK(pk_forest_groups(f, TBN, Cfg::CHUNK, &prm.groups, &prm.n_groups));
     const size_t smem = Cfg::total(ND, prm.n_trees);
     if (OCC * (smem + 1024) > 228 * 1024) { pk_set_error("fused kernel: %zu bytes of shared memory needed (x%d per SM)", smem, OCC); return PK_EUNSUPPORTED; }
     static size_t attr_set = 0;      // largest dynamic size opted into so far
     if (smem > attr_set) {
-        PK_CUDA(cudaFuncSetAttribute(k_score_fused<W, P, TPP, TBN, CH, OCC, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PK_CUDA(cudaFuncSetAttribute(k_score_fused<W, P, TPP, TBN, CH, OCC, NTH, NGR, XSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
     unsigned grid = (unsigned)(sm_count * OCC);        // persistent: CTAs without work exit at once
-    k_score_fused<W, P, TPP, TBN, CH, OCC, NTH><<<grid, NTH, smem, stream>>>(prm);
+    k_score_fused<W, P, TPP, TBN, CH, OCC, NTH, NGR, XSTAGE><<<grid, NTH, smem, stream>>>(prm);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
@@ -726,14 +769,28 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre) {
     prm.next = c->d_counters + 2;
     prm.flags = c->d_flags;
     prm.thre = thre;
+    if ((long long)c->ND * c->pitch >= (1LL << 31)) {      // the gather indexes the band with 32-bit offsets
+        pk_set_error("fused kernel: band of %d x %lld cells exceeds 2^31", c->ND, (long long)c->pitch);
+        return PK_EUNSUPPORTED;
+    }
     int sm = 148;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, c->device);
-    // variant 0: one CTA per SM, 256 (w=5) / 128 (w=7) pixels per batch, 16 warps
-    // variant 1: other warp counts / staging sizes (tuning knob)
-    if (c->w == 5) return variant == 1 ? launch_fused_t<5, 256, 2, 4224, 4, 1, 768>(prm, f, c->ND, sm, c->stream)
-                                       : launch_fused_t<5, 256, 2, 4224, 4, 1>(prm, f, c->ND, sm, c->stream);
-    if (c->w == 7) return variant == 1 ? launch_fused_t<7, 128, 2, 3200, 2, 1, 384>(prm, f, c->ND, sm, c->stream)
-                                       : launch_fused_t<7, 128, 2, 4224, 4, 1, 512>(prm, f, c->ND, sm, c->stream);
+    // variant 0 is the default; the others are tuning experiments (pk_set_tuning("fused", 1 + variant))
+    cudaStream_t st = c->stream;
+    if (c->w == 5) {
+        switch (variant) {
+        case 1: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 2>(prm, f, c->ND, sm, st);
+        case 2: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 1>(prm, f, c->ND, sm, st);
+        default: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4>(prm, f, c->ND, sm, st);
+        }
+    }
+    if (c->w == 7) {
+        switch (variant) {
+        case 1: return launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 2, 32768>(prm, f, c->ND, sm, st);
+        case 2: return launch_fused_t<7, 128, 2, 3200, 2, 1, 512, 2, 32768>(prm, f, c->ND, sm, st);
+        default: return launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 1, 32768>(prm, f, c->ND, sm, st);
+        }
+    }
     return PK_EUNSUPPORTED;
 }
 
