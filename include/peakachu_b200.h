@@ -95,6 +95,13 @@ int pk_chrom_upload_pixels(pk_chrom* c, const int32_t* bin1, const int32_t* bin2
  * to the chromosome, rebased to 0) plus the bin2 / count columns of those pixels. */
 int pk_chrom_upload_csr(pk_chrom* c, const int64_t* bin1_offset, const int32_t* bin2, const int32_t* count,
                         int64_t nnz, const double* weights, int mem);
+/* Same with narrow columns: bin2_delta[p] = bin2 - bin1 and count[p], both uint16 -- 4 bytes per
+ * pixel cross the bus instead of 8. Every pixel of the chromosome must be representable
+ * (bin2 - bin1 <= 65535, count <= 65535); a caller that drops farther pixels instead must make
+ * sure no bin loses its last finite pixel, because the `valid` mask of utils.py:146-156 looks
+ * at the whole matrix. */
+int pk_chrom_upload_csr16(pk_chrom* c, const int64_t* bin1_offset, const uint16_t* bin2_delta, const uint16_t* count,
+                          int64_t nnz, const double* weights, int mem);
 /* per-diagonal (sum, n_valid) for d = 0..upper+2w, to HOST arrays of exp_len */
 int pk_chrom_diag_sums(pk_chrom* c, double* out_sum, int64_t* out_cnt);
 /* expected curve fitted by the library itself: mean where n_valid > 10, then the
@@ -160,6 +167,14 @@ int pk_format_bedpe(const char* chrom, int64_t res, const int32_t* x, const int3
  * (two handles on two streams overlap one chromosome's upload with another's kernels) */
 int pk_stream_create(int device, void** out);
 int pk_stream_destroy(int device, void* stream);
+/* priority > 0: kernels of this stream are scheduled ahead of those of ordinary streams */
+int pk_stream_create_priority(int device, int priority, void** out);
+/* Run the fused scoring kernel of this handle (pk_chrom_score) on `stream` instead of the
+ * handle's own; the handle's stream waits for it. With the handles' own streams at high
+ * priority and one ordinary stream shared by the scoring kernels, those run back to back and the
+ * short stages of the chromosomes queued behind slip in where one ends and the next starts.
+ * NULL: back to one stream. */
+int pk_chrom_set_score_stream(pk_chrom* c, void* stream);
 
 /* return the library's cached device blocks (of destroyed handles) to the driver */
 int pk_release_memory(void);

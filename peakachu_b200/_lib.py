@@ -38,11 +38,14 @@ SIGNATURES = {
     "pk_chrom_bounds": (C.c_int, [C.c_void_p, c_i32p, c_i32p, c_i32p]),
     "pk_chrom_upload_pixels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "pk_chrom_upload_csr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    "pk_chrom_upload_csr16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "pk_release_memory": (C.c_int, []),
     "pk_format_bedpe": (C.c_int, [C.c_char_p, C.c_int64, c_i32p, c_i32p, c_f64p, c_f64p, C.c_int64, C.c_char_p,
                                   C.c_int64, c_i64p]),
     "pk_stream_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "pk_stream_destroy": (C.c_int, [C.c_int, C.c_void_p]),
+    "pk_stream_create_priority": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "pk_chrom_set_score_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pk_selftest_divide": (C.c_int, [C.c_int, C.c_int64, C.c_uint64, c_i64p]),
     "pk_chrom_diag_sums": (C.c_int, [C.c_void_p, c_f64p, c_i64p]),
     "pk_chrom_fit_expected": (C.c_int, [C.c_void_p]),

@@ -51,6 +51,10 @@ class PKCool:
         self.bin1_id = z["bin1_id"]
         self.bin2_id = z["bin2_id"]
         self.count = z["count"]
+        # optional narrow pixel columns (bin2 - bin1 and count as uint16), written when every
+        # pixel is representable: half the bytes to move to the GPU
+        self.delta16 = z["delta16"] if "delta16" in z.files else None
+        self.count16 = z["count16"] if "count16" in z.files else None
         self.weight_columns = {k[len("bins_"):]: z[k] for k in z.files if k.startswith("bins_")}
         # pixel range of each chromosome (bin1 sorted, intra-chromosomal only)
         self._pix_lo = np.searchsorted(self.bin1_id, self.chrom_offset[:-1], side="left")
@@ -69,12 +73,15 @@ class PKCool:
         b2 = np.concatenate([c.bin2.astype(np.int64) + off[i] for i, c in enumerate(chroms)])
         cnt = np.concatenate([c.count for c in chroms]).astype(np.int32)
         w = np.concatenate([c.weights for c in chroms]).astype(np.float64)
+        extra = {}
+        if b1.size and int((b2 - b1).max()) <= 65535 and int(cnt.max()) <= 65535 and int(cnt.min()) >= 0:
+            extra = dict(delta16=(b2 - b1).astype(np.uint16), count16=cnt.astype(np.uint16))
         with open(path, "wb") as fh:
             np.savez(fh, binsize=np.int64(binsize), chrom_names=names,
                      chrom_lengths=nb * binsize, chrom_offset=off,
                      bin1_id=b1.astype(np.int32 if off[-1] < 2**31 else np.int64),
                      bin2_id=b2.astype(np.int32 if off[-1] < 2**31 else np.int64),
-                     count=cnt, **{"bins_" + weight_name: w})
+                     count=cnt, **extra, **{"bins_" + weight_name: w})
 
     # -- per-chromosome access -------------------------------------------------
     def _cid(self, chrom: str) -> int:
@@ -106,6 +113,18 @@ class PKCool:
         rp = np.searchsorted(self.bin1_id[lo:hi], np.arange(off, off + n + 1), side="left").astype(np.int64)
         b2 = (self.bin2_id[lo:hi] - off).astype(np.int32)
         return rp, b2, np.ascontiguousarray(self.count[lo:hi], dtype=np.int32)
+
+    def upper_pixels_csr16(self, chrom: str):
+        """(bin1_offset int64[n+1], bin2 - bin1 uint16, count uint16), or None when the
+        container has no narrow columns."""
+        if self.delta16 is None or self.count16 is None:
+            return None
+        i = self._cid(chrom)
+        lo, hi = self._pix_lo[i], self._pix_hi[i]
+        off = self.chrom_offset[i]
+        n = self.nbins(chrom)
+        rp = np.searchsorted(self.bin1_id[lo:hi], np.arange(off, off + n + 1), side="left").astype(np.int64)
+        return rp, np.ascontiguousarray(self.delta16[lo:hi]), np.ascontiguousarray(self.count16[lo:hi])
 
     def weights(self, chrom: str, name: str) -> np.ndarray:
         if name not in self.weight_columns:

@@ -15,7 +15,7 @@
 
 // launchers implemented in pk_kernels.cu / pk_stages.cu / pk_fused.cu
 int pk_launch_scatter(pk_chrom* c, const int32_t* b1, const int32_t* b2, const int32_t* cnt, int64_t nnz);
-int pk_launch_band_csr(pk_chrom* c, const long long* rowptr, const int32_t* b2, const int32_t* cnt);
+int pk_launch_band_csr(pk_chrom* c, const long long* rowptr, const void* b2, const void* cnt, int enc);
 int pk_launch_rowptr(pk_chrom* c, const int32_t* b1, const int32_t* b2, int64_t nnz, long long* rowptr);
 int pk_launch_diag_sums(pk_chrom* c);
 bool pk_fit_on_device_supported(int len);
@@ -25,8 +25,10 @@ int pk_launch_features(pk_chrom* c, double* d_fea64);
 int pk_launch_forest(const pk_forest* f, const float* X, const uint8_t* keep, int64_t n_rows, int32_t* leaves,
                      double* proba, cudaStream_t stream);
 int pk_launch_emit(pk_chrom* c, double thre);
-int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre);
+int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms);
 size_t pk_sort_temp_bytes(long long n);
+size_t pk_sort32_temp_bytes(long long n);
+int pk_launch_sort_records_eager(pk_chrom* c, long long M, int key_bits);
 int pk_launch_sort_records(pk_chrom* c, long long n, unsigned long long* keys_in, unsigned long long* keys_out,
                            uint32_t* idx_in, uint32_t* idx_out, void* temp, size_t temp_bytes, unsigned char* packed,
                            long long off_f64, int key_bits);
@@ -44,12 +46,15 @@ extern "C" int pk_selftest_divide(int device, int64_t n, uint64_t seed, int64_t*
 }
 
 // tuning knobs (pk_set_tuning): fused = -1 auto, 0 unfused kernels, 1 + v: fused kernel variant v
+static const int64_t PK_EAGER_RECORDS = 1 << 17;   // records sorted behind the scoring pass; more fall back to a sort at fetch time
 static int g_tune_fused = -1;
-static int g_tune_prune = 1;     // retire pixels that cannot exceed min_prob (exact for every emitted record)
+static int g_tune_prune = 1;
+static int g_tune_reserve = 0;   // SMs the fused kernel leaves to the short stages of other chromosomes (pipelined use)     // retire pixels that cannot exceed min_prob (exact for every emitted record)
 
 extern "C" int pk_set_tuning(const char* key, int value) {
     if (key && !strcmp(key, "fused")) { g_tune_fused = value; return PK_OK; }
     if (key && !strcmp(key, "prune")) { g_tune_prune = value; return PK_OK; }
+    if (key && !strcmp(key, "reserve_sms")) { g_tune_reserve = value < 0 ? 0 : value; return PK_OK; }
     pk_set_error("pk_set_tuning: unknown key %s", key ? key : "(null)");
     return PK_EINVAL;
 }
@@ -166,6 +171,18 @@ extern "C" int pk_stream_create(int device, void** out) {
     PK_CUDA(cudaSetDevice(device));
     cudaStream_t s = nullptr;
     PK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *out = (void*)s;
+    return PK_OK;
+}
+
+// priority > 0: the stream's kernels are scheduled ahead of those of ordinary streams
+extern "C" int pk_stream_create_priority(int device, int priority, void** out) {
+    if (!out) { pk_set_error("pk_stream_create_priority: out is NULL"); return PK_EINVAL; }
+    PK_CUDA(cudaSetDevice(device));
+    int lo = 0, hi = 0;                       // numerically lower = higher priority
+    PK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    cudaStream_t s = nullptr;
+    PK_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, priority > 0 ? hi : lo));
     *out = (void*)s;
     return PK_OK;
 }
@@ -442,6 +459,8 @@ extern "C" int pk_chrom_destroy(pk_chrom* c) {
     dev_free(c->d_cx); dev_free(c->d_cd); dev_free(c->d_crank);
     dev_free(c->d_keep); dev_free(c->d_fea32); dev_free(c->d_prob); dev_free(c->d_batch_win);
     dev_free(c->d_rx); dev_free(c->d_ry); dev_free(c->d_rb); dev_free(c->d_rp); dev_free(c->d_rv);
+    if (c->ev_x) cudaEventDestroy(c->ev_x);
+    dev_free(c->d_sk0); dev_free(c->d_sk1); dev_free(c->d_si0); dev_free(c->d_si1); dev_free(c->d_stemp); dev_free(c->d_packed);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     hstage_release(c->h_stage, c->h_stage_bytes);
     delete c;
@@ -514,7 +533,7 @@ extern "C" int pk_chrom_upload_pixels(pk_chrom* c, const int32_t* bin1, const in
     if (sorted) {
         // cooler order: derive row offsets on the device, then the tiled CSR build
         PK_CHECK(pk_launch_rowptr(c, p1, p2, nnz, c->d_rowptr));
-        PK_CHECK(pk_launch_band_csr(c, c->d_rowptr, p2, pc));
+        PK_CHECK(pk_launch_band_csr(c, c->d_rowptr, p2, pc, 0));
     } else {
         PK_CUDA(cudaMemsetAsync(c->d_band, 0, (size_t)c->ND * c->pitch * sizeof(int32_t), s));
         PK_CHECK(pk_launch_scatter(c, p1, p2, pc, nnz));
@@ -545,7 +564,37 @@ extern "C" int pk_chrom_upload_csr(pk_chrom* c, const int64_t* bin1_offset, cons
     PK_CUDA(cudaMemsetAsync(c->d_valid, 0, (size_t)c->n, s));
     PK_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int32_t), s));
     c->declared_sorted = false;      // row offsets given: nothing to verify
-    PK_CHECK(pk_launch_band_csr(c, rp, p2, pc));
+    PK_CHECK(pk_launch_band_csr(c, rp, p2, pc, 0));
+    return after_band(c);
+}
+
+extern "C" int pk_chrom_upload_csr16(pk_chrom* c, const int64_t* bin1_offset, const uint16_t* bin2_delta, const uint16_t* count,
+                                     int64_t nnz, const double* weights, int mem) {
+    if (!c || nnz < 0 || !bin1_offset || (nnz > 0 && (!bin2_delta || !count))) { pk_set_error("pk_chrom_upload_csr16: bad argument"); return PK_EINVAL; }
+    if (c->balanced && !weights) { pk_set_error("pk_chrom_upload_csr16: balanced mode needs weights"); return PK_EINVAL; }
+    mem &= ~PK_PIXELS_SORTED;
+    PK_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const void *p2 = bin2_delta, *pc = count;
+    const long long* rp = reinterpret_cast<const long long*>(bin1_offset);
+    if (mem == PK_MEM_HOST) {
+        PK_CHECK(reserve_staging(c, (nnz + 1) / 2, false));        // two 16-bit values per staged int32
+        if (nnz > 0) {
+            PK_CUDA(cudaMemcpyAsync(c->d_b2, bin2_delta, (size_t)nnz * 2, cudaMemcpyHostToDevice, s));
+            PK_CUDA(cudaMemcpyAsync(c->d_cnt, count, (size_t)nnz * 2, cudaMemcpyHostToDevice, s));
+        }
+        p2 = c->d_b2; pc = c->d_cnt;
+        PK_CUDA(cudaMemcpyAsync(c->d_rowptr, bin1_offset, ((size_t)c->n + 1) * 8, cudaMemcpyHostToDevice, s));
+        rp = c->d_rowptr;
+    }
+    if (c->balanced)
+        PK_CUDA(cudaMemcpyAsync(c->d_w, weights, (size_t)c->n * sizeof(double),
+                                mem == PK_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    PK_CUDA(cudaEventRecord(c->ev[0], s));
+    PK_CUDA(cudaMemsetAsync(c->d_valid, 0, (size_t)c->n, s));
+    PK_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int32_t), s));
+    c->declared_sorted = false;
+    PK_CHECK(pk_launch_band_csr(c, rp, p2, pc, 1));
     return after_band(c);
 }
 
@@ -783,7 +832,21 @@ static int run_score(pk_chrom* c, pk_forest* f, double min_prob) {
     const bool fused = g_tune_fused != 0 && pk_fused_supported(c->w, f->n_trees);
     if (fused) {
         // features stay in shared memory; stage [4] reports the fused kernel, [5] is 0
-        PK_CHECK(pk_launch_fused(c, f, g_tune_fused > 1 ? g_tune_fused - 1 : 0, g_tune_prune ? min_prob : -1.0));
+        if (c->use_score_stream) {
+            // The fused kernel may run on a second stream (pk_chrom_set_score_stream): the handle's
+            // own stream waits for it, so everything queued on the handle later is ordered behind it.
+            if (!c->ev_x) PK_CUDA(cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming));
+            PK_CUDA(cudaEventRecord(c->ev_x, s));
+            PK_CUDA(cudaStreamWaitEvent(c->score_stream, c->ev_x, 0));
+            c->stream = c->score_stream;
+            const int r = pk_launch_fused(c, f, g_tune_fused > 1 ? g_tune_fused - 1 : 0, g_tune_prune ? min_prob : -1.0, g_tune_reserve);
+            c->stream = s;
+            PK_CHECK(r);
+            PK_CUDA(cudaEventRecord(c->ev_x, c->score_stream));
+            PK_CUDA(cudaStreamWaitEvent(s, c->ev_x, 0));
+        } else {
+            PK_CHECK(pk_launch_fused(c, f, g_tune_fused > 1 ? g_tune_fused - 1 : 0, g_tune_prune ? min_prob : -1.0, 0));
+        }
         PK_CUDA(cudaEventRecord(c->ev[8], s));
     } else {
         if (!c->n_cand_known) PK_CHECK(settle_candidates(c));
@@ -794,7 +857,33 @@ static int run_score(pk_chrom* c, pk_forest* f, double min_prob) {
     }
     PK_CUDA(cudaEventRecord(c->ev[9], s));
     PK_CHECK(pk_launch_emit(c, min_prob));
+    // sort + pack the records now, behind the scoring pass: later the SMs belong to the next chromosome
+    c->eager_valid = false;
+    c->counts_valid = false;
+    const int64_t M = std::min<int64_t>(c->cand_cap, PK_EAGER_RECORDS);
+    if ((long long)c->n * c->ND < 0xFFFFFFFFLL && M > 0) {
+        if (c->eager_cap != M || !c->d_packed) {
+            dev_free(c->d_sk0); dev_free(c->d_sk1); dev_free(c->d_si0); dev_free(c->d_si1); dev_free(c->d_stemp); dev_free(c->d_packed);
+            c->stemp_bytes = pk_sort32_temp_bytes(M);
+            PK_CHECK(dev_alloc(&c->d_sk0, (size_t)M)); PK_CHECK(dev_alloc(&c->d_sk1, (size_t)M));
+            PK_CHECK(dev_alloc(&c->d_si0, (size_t)M)); PK_CHECK(dev_alloc(&c->d_si1, (size_t)M));
+            PK_CHECK(dev_alloc(&c->d_stemp, c->stemp_bytes));
+            PK_CHECK(dev_alloc(&c->d_packed, (size_t)M * 28 + 16));
+            c->eager_cap = M;
+        }
+        int key_bits = 0;
+        for (long long v = (long long)c->n * c->ND; v > 0; v >>= 1) ++key_bits;
+        PK_CHECK(pk_launch_sort_records_eager(c, M, std::min(key_bits + 1, 32)));
+        c->eager_valid = true;
+    }
     PK_CUDA(cudaEventRecord(c->ev[10], s));
+    return PK_OK;
+}
+
+extern "C" int pk_chrom_set_score_stream(pk_chrom* c, void* stream) {
+    if (!c) { pk_set_error("pk_chrom_set_score_stream: NULL handle"); return PK_EINVAL; }
+    c->score_stream = (cudaStream_t)stream;
+    c->use_score_stream = stream != nullptr;
     return PK_OK;
 }
 
@@ -823,12 +912,14 @@ extern "C" int pk_chrom_result_count(pk_chrom* c, int64_t* n_records, int64_t* n
         PK_CHECK(settle_candidates(c));
         if (overflow) PK_CHECK(run_score(c, c->last_forest, c->last_thre));
     }
-    unsigned long long h[4] = {0, 0, 0, 0};
-    PK_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-    PK_CUDA(cudaStreamSynchronize(c->stream));
-    if (n_records) *n_records = (int64_t)h[0];
+    if (!c->counts_valid) {
+        PK_CUDA(cudaMemcpyAsync(c->h_counts, c->d_counters, sizeof c->h_counts, cudaMemcpyDeviceToHost, c->stream));
+        PK_CUDA(cudaStreamSynchronize(c->stream));
+        c->counts_valid = true;
+    }
+    if (n_records) *n_records = (int64_t)c->h_counts[0];
     if (n_candidates) *n_candidates = c->n_cand;
-    if (n_windows) *n_windows = (int64_t)h[1];
+    if (n_windows) *n_windows = (int64_t)c->h_counts[1];
     return PK_OK;
 }
 
@@ -866,6 +957,24 @@ extern "C" int pk_chrom_fetch_results(pk_chrom* c, int32_t* out_x, int32_t* out_
     // sort by (x, y) on the device, pack, one copy into pinned staging, split on the host
     const long long off_f64 = ((12 * n + 7) / 8) * 8;
     const size_t packed_bytes = (size_t)off_f64 + 16 * (size_t)n;
+    if (c->eager_valid && n <= c->eager_cap) {
+        // already sorted and packed behind the scoring pass: only the copy is left
+        if (packed_bytes > c->h_stage_bytes) {
+            hstage_release(c->h_stage, c->h_stage_bytes);
+            c->h_stage = nullptr; c->h_stage_bytes = 0;
+            PK_CHECK(hstage_acquire(&c->h_stage, &c->h_stage_bytes, packed_bytes));
+        }
+        PK_CUDA(cudaMemcpyAsync(c->h_stage, c->d_packed, packed_bytes, cudaMemcpyDeviceToHost, s));
+        PK_CUDA(cudaStreamSynchronize(s));
+        const int32_t* hi = reinterpret_cast<const int32_t*>(c->h_stage);
+        const double* hd = reinterpret_cast<const double*>(c->h_stage + off_f64);
+        if (out_x) memcpy(out_x, hi, (size_t)n * 4);
+        if (out_y) memcpy(out_y, hi + n, (size_t)n * 4);
+        if (out_batch) memcpy(out_batch, hi + 2 * n, (size_t)n * 4);
+        if (out_prob) memcpy(out_prob, hd, (size_t)n * 8);
+        if (out_val) memcpy(out_val, hd + n, (size_t)n * 8);
+        return PK_OK;
+    }
     const size_t temp_bytes = pk_sort_temp_bytes(n);
     unsigned long long *k0 = nullptr, *k1 = nullptr;
     uint32_t *i0 = nullptr, *i1 = nullptr;

@@ -116,6 +116,17 @@ struct pk_chrom {
     double *d_rp = nullptr, *d_rv = nullptr;
     unsigned long long* d_counters = nullptr;   // [4]: 0 = n_records, 1 = n_windows
     int64_t rec_cap = 0;
+    // records sorted by (x, y) and packed right after the scoring pass (no kernel at fetch time)
+    uint32_t *d_sk0 = nullptr, *d_sk1 = nullptr, *d_si0 = nullptr, *d_si1 = nullptr;
+    unsigned char *d_stemp = nullptr, *d_packed = nullptr;
+    size_t stemp_bytes = 0;
+    int64_t eager_cap = 0;              // records the eager sort covers
+    bool eager_valid = false;           // d_packed belongs to the current scores
+    cudaStream_t score_stream = nullptr;   // optional second stream for the scoring pass
+    bool use_score_stream = false;
+    cudaEvent_t ev_x = nullptr;            // hand-over between the two streams
+    unsigned long long h_counts[4] = {0, 0, 0, 0};
+    bool counts_valid = false;          // h_counts read since the last scoring pass
     unsigned char* h_stage = nullptr;   // pinned staging for fetch_results
     size_t h_stage_bytes = 0;
     // timing

@@ -757,7 +757,7 @@ static int launch_fused_t(FusedParams prm, pk_forest* f, int ND, int sm_count, c
     return PK_OK;
 }
 
-int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre) {
+int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms) {
     FusedParams prm;
     prm.band = c->d_band; prm.w = c->d_w; prm.expv = c->d_exp;
     prm.n = c->n; prm.pitch = c->pitch; prm.balanced = c->balanced; prm.ND = c->ND;
@@ -775,6 +775,7 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre) {
     }
     int sm = 148;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, c->device);
+    sm = std::max(1, sm - reserve_sms);
     // variant 0 is the default; the others are tuning experiments (pk_set_tuning("fused", 1 + variant))
     cudaStream_t st = c->stream;
     if (c->w == 5) {

@@ -14,8 +14,11 @@
 //     zeros included -- the band needs no memset and no global atomics.
 //     Side products: valid[] (utils.py:146-156) and the largest in-band count.
 // ---------------------------------------------------------------------------
+// TY / TC: element types of the column and count arrays. DELTA: the column array holds
+// bin2 - bin1 (pk_chrom_upload_csr16) instead of bin2.
+template <typename TY, typename TC, bool DELTA>
 __global__ void __launch_bounds__(256) k_band_csr(
-    const long long* __restrict__ rowptr, const int32_t* __restrict__ b2, const int32_t* __restrict__ cnt,
+    const long long* __restrict__ rowptr, const TY* __restrict__ b2, const TC* __restrict__ cnt,
     const double* __restrict__ w, int n, int ND, long long pitch, int balanced,
     int32_t* __restrict__ band, uint8_t* __restrict__ valid, int32_t* __restrict__ flags) {
     extern __shared__ int32_t s_tile[];                 // [ND][33]
@@ -37,7 +40,7 @@ __global__ void __launch_bounds__(256) k_band_csr(
             for (int j = 0; j < 4; ++j) {
                 const long long p = pb + j * 32 + lane;
                 y[j] = -1; c[j] = 0;
-                if (p < p1) { y[j] = b2[p]; c[j] = cnt[p]; }
+                if (p < p1) { y[j] = DELTA ? x + (int)b2[p] : (int)b2[p]; c[j] = (int)cnt[p]; }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -606,19 +609,26 @@ __global__ void __launch_bounds__(256) k_cand_write(
 // ---------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------
-int pk_launch_band_csr(pk_chrom* c, const long long* rowptr, const int32_t* b2, const int32_t* cnt) {
+template <typename TY, typename TC, bool DELTA>
+static int launch_band_csr_t(pk_chrom* c, const long long* rowptr, const void* b2, const void* cnt) {
     const size_t smem = (size_t)c->ND * 33 * sizeof(int32_t);
     if (smem > 200 * 1024) { pk_set_error("band build: %d diagonals do not fit a shared-memory tile", c->ND); return PK_EUNSUPPORTED; }
     static size_t attr_set = 0;
     if (smem > 48 * 1024 && smem > attr_set) {
-        PK_CUDA(cudaFuncSetAttribute(k_band_csr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PK_CUDA(cudaFuncSetAttribute(k_band_csr<TY, TC, DELTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
     const unsigned grid = (unsigned)((c->n + 31) / 32);
-    k_band_csr<<<grid, 256, smem, c->stream>>>(rowptr, b2, cnt, c->d_w, c->n, c->ND, c->pitch, c->balanced, c->d_band,
-                                               c->d_valid, c->d_flags);
+    k_band_csr<TY, TC, DELTA><<<grid, 256, smem, c->stream>>>(rowptr, (const TY*)b2, (const TC*)cnt, c->d_w, c->n, c->ND, c->pitch,
+                                                              c->balanced, c->d_band, c->d_valid, c->d_flags);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
+}
+
+// enc 0: int32 bin2 + int32 count; enc 1: uint16 (bin2 - bin1) + uint16 count
+int pk_launch_band_csr(pk_chrom* c, const long long* rowptr, const void* b2, const void* cnt, int enc) {
+    if (enc == 1) return launch_band_csr_t<uint16_t, uint16_t, true>(c, rowptr, b2, cnt);
+    return launch_band_csr_t<int32_t, int32_t, false>(c, rowptr, b2, cnt);
 }
 
 int pk_launch_rowptr(pk_chrom* c, const int32_t* b1, const int32_t* b2, int64_t nnz, long long* rowptr) {

@@ -108,31 +108,43 @@ class Chromosome:
     @classmethod
     def from_pixels(cls, bin1, bin2, count, weights, n_bins, model, lower=6, upper=300,
                     cname="chrm", res=10000, width=5, device=0, stream=None, sorted_pixels=None,
-                    first_tile=None):
+                    first_tile=None, score_stream=None):
         """Build from cooler-style upper-triangle pixel columns (chromosome-local bin
         ids) and the weight column (None = raw mode). ``sorted_pixels=True`` promises
         cooler order (sorted by bin1, then bin2; the device verifies it), ``None``
         checks on the host, ``False`` takes the order-free scatter path."""
         self = cls.__new__(cls)
         self._init(bin1, bin2, count, weights, int(n_bins), model, lower, upper, cname, res, width, device, stream,
-                   sorted_pixels=sorted_pixels, first_tile=first_tile)
+                   sorted_pixels=sorted_pixels, first_tile=first_tile, score_stream=score_stream)
         return self
 
     @classmethod
     def from_csr(cls, bin1_offset, bin2, count, weights, n_bins, model, lower=6, upper=300,
-                 cname="chrm", res=10000, width=5, device=0, stream=None, first_tile=None):
+                 cname="chrm", res=10000, width=5, device=0, stream=None, first_tile=None, score_stream=None):
         """Build from cooler's CSR layout: ``indexes/bin1_offset`` of the chromosome
         (rebased to 0, int64[n_bins+1]) plus the ``bin2_id`` (chromosome-local) and
         ``count`` columns of its pixels. 8 bytes per pixel cross the bus instead of 12.
         Arrays may live in pinned host memory (e.g. views of pinned torch tensors)."""
         self = cls.__new__(cls)
         self._init(None, bin2, count, weights, int(n_bins), model, lower, upper, cname, res, width, device, stream,
-                   bin1_offset=bin1_offset, first_tile=first_tile)
+                   bin1_offset=bin1_offset, first_tile=first_tile, score_stream=score_stream)
+        return self
+
+    @classmethod
+    def from_csr16(cls, bin1_offset, bin2_delta, count, weights, n_bins, model, lower=6, upper=300,
+                   cname="chrm", res=10000, width=5, device=0, stream=None, first_tile=None, score_stream=None):
+        """``from_csr`` with narrow columns: ``bin2_delta = bin2 - bin1`` and ``count`` as uint16
+        arrays (4 bytes per pixel cross the bus). Every pixel of the chromosome must be
+        representable, see ``pk_chrom_upload_csr16`` in include/peakachu_b200.h;
+        ``coolio.PKCool`` stores such columns when they are."""
+        self = cls.__new__(cls)
+        self._init(None, bin2_delta, count, weights, int(n_bins), model, lower, upper, cname, res, width, device,
+                   stream, bin1_offset=bin1_offset, first_tile=first_tile, csr16=True, score_stream=score_stream)
         return self
 
     # -- construction = upload + band + expected + candidates (scoreUtils.py:13-34) --
     def _init(self, b1, b2, cnt, weights, n, model, lower, upper, cname, res, width, device, stream,
-              sorted_pixels=None, bin1_offset=None, first_tile=None):
+              sorted_pixels=None, bin1_offset=None, first_tile=None, csr16=False, score_stream=None):
         L = _lib.lib()
         _lib.require_device()
         self.chromname, self.r, self.w = cname, res, width
@@ -144,18 +156,26 @@ class Chromosome:
         self._h = C.c_void_p()
         _lib.check(L.pk_chrom_create(device, n, width, lower, upper, 0 if weights is None else 1,
                                      C.c_void_p(stream or 0), C.byref(self._h)))
+        if score_stream:
+            # the scoring pass goes to its own stream (shard.score_units shares one among the
+            # chromosomes in flight and gives `stream` a high priority)
+            _lib.check(L.pk_chrom_set_score_stream(self._h, C.c_void_p(score_stream)))
         lo, up, el = C.c_int32(), C.c_int32(), C.c_int32()
         _lib.check(L.pk_chrom_bounds(self._h, C.byref(lo), C.byref(up), C.byref(el)))
         self.lower, self.upper, self._exp_len = lo.value, up.value, el.value
-        b2, cnt = _lib.as_c(b2, np.int32), _lib.as_c(cnt, np.int32)
+        col_t = np.uint16 if csr16 else np.int32
+        if csr16 and (np.asarray(b2).dtype != np.uint16 or np.asarray(cnt).dtype != np.uint16):
+            raise TypeError("from_csr16 takes uint16 arrays (bin2 - bin1, count)")
+        b2, cnt = _lib.as_c(b2, col_t), _lib.as_c(cnt, col_t)
         self._keepalive = [b2, cnt]          # uploads are asynchronous when the source is pinned
         if bin1_offset is not None:
             rp = _lib.as_c(bin1_offset, np.int64)
             self._keepalive.append(rp)
             if rp.size != n + 1:
                 raise ValueError("bin1_offset must have n_bins + 1 entries")
-            _lib.check(L.pk_chrom_upload_csr(self._h, _lib.ptr(rp), _lib.ptr(b2), _lib.ptr(cnt), b2.size,
-                                             _lib.ptr(self.weights), _lib.PK_MEM_HOST))
+            upload = L.pk_chrom_upload_csr16 if csr16 else L.pk_chrom_upload_csr
+            _lib.check(upload(self._h, _lib.ptr(rp), _lib.ptr(b2), _lib.ptr(cnt), b2.size,
+                              _lib.ptr(self.weights), _lib.PK_MEM_HOST))
         else:
             b1 = _lib.as_c(b1, np.int32)
             self._keepalive.append(b1)

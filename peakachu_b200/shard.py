@@ -103,7 +103,7 @@ def _fetch_tile(X, a, b, n, ncand=None):
                 batch_windows=bw[:nb.value], n_candidates=int(nc.value))
 
 
-def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_prob, depth=3):
+def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_prob, depth=6):
     """Score this rank's units. Returns {chrom: [tile dict, ...]}.
 
     Chromosomes are pipelined over ``depth`` streams: while one chromosome's kernels
@@ -121,11 +121,17 @@ def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_pro
     by_chrom = {}
     for k, a, b in units:
         by_chrom.setdefault(k, []).append((a, b))
+    # `depth` high-priority streams carry the upload and the short stages of the chromosomes in
+    # flight; the scoring passes, which fill the GPU one at a time anyway, share one ordinary
+    # stream. Between two scoring passes the short stages of the chromosomes queued behind run
+    # first and overlap each other.
     streams = []
     for _ in range(max(1, depth)):
         st = C.c_void_p()
-        _lib.check(L.pk_stream_create(device, C.byref(st)))
+        _lib.check(L.pk_stream_create_priority(device, 1, C.byref(st)))
         streams.append(st)
+    score_stream = C.c_void_p()
+    _lib.check(L.pk_stream_create_priority(device, 0, C.byref(score_stream)))
     inflight = deque()
 
     def finish(job):
@@ -146,8 +152,12 @@ def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_pro
             weights = Lib.weights(key, correct) if correct else None
             n = Lib.nbins(key)
             kw = dict(lower=lower, upper=upper, cname="chr" + key.lstrip("chr"), res=res, width=flat.width,
-                      device=device, stream=streams[i % len(streams)].value, first_tile=tiles[0])
-            if hasattr(Lib, "upper_pixels_csr"):
+                      device=device, stream=streams[i % len(streams)].value, first_tile=tiles[0],
+                      score_stream=score_stream.value)
+            narrow = Lib.upper_pixels_csr16(key) if hasattr(Lib, "upper_pixels_csr16") else None
+            if narrow is not None:
+                X = Chromosome.from_csr16(*narrow, weights, n, forest, **kw)
+            elif hasattr(Lib, "upper_pixels_csr"):
                 rp, b2, cnt = Lib.upper_pixels_csr(key)
                 X = Chromosome.from_csr(rp, b2, cnt, weights, n, forest, **kw)
             else:
@@ -158,7 +168,7 @@ def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_pro
         while inflight:
             finish(inflight.popleft())
     finally:
-        for st in streams:
+        for st in streams + [score_stream]:
             L.pk_stream_destroy(device, st)
     return out
 

@@ -210,6 +210,24 @@ def test_upload_paths_agree():
     _lib.check(L.pk_chrom_get_expected(h, _lib.ptr(e, _lib.c_f64p)))
     assert np.array_equal(e, A.exp_arr)
     L.pk_chrom_destroy(h)
+    # narrow columns (uint16 bin2 - bin1, uint16 count): same band, same records
+    for name in ("tiny", "tiny_raw", "w7", "lowdepth"):
+        cs = Case(name)
+        c2, chx = cs.cfg, cs.chroms[0]
+        kw2 = dict(lower=c2["lower"], upper=c2["upper"], cname=chx.name, res=c2["res"], width=c2["w"])
+        rp = np.searchsorted(chx.bin1, np.arange(chx.n + 1)).astype(np.int64)
+        assert int((chx.bin2 - chx.bin1).max()) <= 65535 and int(chx.count.max()) <= 65535
+        wts = None if c2["weight"] == "raw" else chx.weights
+        N = Chromosome.from_csr16(rp, (chx.bin2 - chx.bin1).astype(np.uint16), chx.count.astype(np.uint16), wts,
+                                  chx.n, cs.forest, **kw2)
+        W = Chromosome.from_csr(rp, chx.bin2, chx.count, wts, chx.n, cs.forest, **kw2)
+        assert np.array_equal(N.exp_arr, W.exp_arr) and np.array_equal(N.exp_arr, cs.z[chx.name + "/exp_arr"])
+        assert np.array_equal(N.ridx, W.ridx) and np.array_equal(N.cidx, W.cidx)
+        rn, rw = N.score_records(c2["min_prob"]), W.score_records(c2["min_prob"])
+        assert all(np.array_equal(u, v) for u, v in zip(rn, rw))
+        N.close(); W.close()
+    with pytest.raises(TypeError):
+        Chromosome.from_csr16(rowptr, ch.bin2, ch.count, ch.weights, ch.n, case.forest, **kw)
     # a broken promise
     with pytest.raises(_lib.PKError, match="not sorted"):
         X = Chromosome.from_pixels(ch.bin1[perm], ch.bin2[perm], ch.count[perm], ch.weights, ch.n, case.forest,
