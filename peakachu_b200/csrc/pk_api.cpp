@@ -27,8 +27,7 @@ int pk_launch_forest(const pk_forest* f, const float* X, const uint8_t* keep, in
 int pk_launch_emit(pk_chrom* c, double thre);
 int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms);
 size_t pk_sort_temp_bytes(long long n);
-size_t pk_sort32_temp_bytes(long long n);
-int pk_launch_sort_records_eager(pk_chrom* c, long long M, int key_bits);
+int pk_launch_sort_records_eager(pk_chrom* c, long long M);
 int pk_launch_sort_records(pk_chrom* c, long long n, unsigned long long* keys_in, unsigned long long* keys_out,
                            uint32_t* idx_in, uint32_t* idx_out, void* temp, size_t temp_bytes, unsigned char* packed,
                            long long off_f64, int key_bits);
@@ -460,7 +459,7 @@ extern "C" int pk_chrom_destroy(pk_chrom* c) {
     dev_free(c->d_keep); dev_free(c->d_fea32); dev_free(c->d_prob); dev_free(c->d_batch_win);
     dev_free(c->d_rx); dev_free(c->d_ry); dev_free(c->d_rb); dev_free(c->d_rp); dev_free(c->d_rv);
     if (c->ev_x) cudaEventDestroy(c->ev_x);
-    dev_free(c->d_sk0); dev_free(c->d_sk1); dev_free(c->d_si0); dev_free(c->d_si1); dev_free(c->d_stemp); dev_free(c->d_packed);
+    dev_free(c->d_rowcnt); dev_free(c->d_rowoff); dev_free(c->d_rrank); dev_free(c->d_perm); dev_free(c->d_packed);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     hstage_release(c->h_stage, c->h_stage_bytes);
     delete c;
@@ -797,6 +796,24 @@ static int reset_score_state(pk_chrom* c) {
     PK_CUDA(cudaMemsetAsync(c->d_batch_win, 0, (size_t)c->batch_cap * 4, c->stream));
     PK_CUDA(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream));
     PK_CUDA(cudaMemsetAsync(c->d_keep, 0, (size_t)c->cand_cap, c->stream));
+    // buffers of the record ordering that follows the scoring pass
+    c->eager_valid = false;
+    const int64_t M = std::min<int64_t>(c->cand_cap, PK_EAGER_RECORDS);
+    if (!c->d_rowcnt) {
+        PK_CHECK(dev_alloc(&c->d_rowcnt, (size_t)c->n + 1)); PK_CHECK(dev_alloc(&c->d_rowoff, (size_t)c->n + 2));
+        PK_CUDA(cudaMemsetAsync(c->d_rowcnt, 0, ((size_t)c->n + 1) * 4, c->stream));     // k_record_place keeps it zero afterwards
+    }
+    if (c->rrank_cap != c->cand_cap || !c->d_rrank) {
+        dev_free(c->d_rrank);
+        PK_CHECK(dev_alloc(&c->d_rrank, (size_t)c->cand_cap));
+        c->rrank_cap = c->cand_cap;
+    }
+    if (c->eager_cap != M || !c->d_packed) {
+        dev_free(c->d_perm); dev_free(c->d_packed);
+        PK_CHECK(dev_alloc(&c->d_perm, (size_t)M));
+        PK_CHECK(dev_alloc(&c->d_packed, (size_t)M * 28 + 16));
+        c->eager_cap = M;
+    }
     return PK_OK;
 }
 
@@ -857,25 +874,10 @@ static int run_score(pk_chrom* c, pk_forest* f, double min_prob) {
     }
     PK_CUDA(cudaEventRecord(c->ev[9], s));
     PK_CHECK(pk_launch_emit(c, min_prob));
-    // sort + pack the records now, behind the scoring pass: later the SMs belong to the next chromosome
-    c->eager_valid = false;
+    // order + pack the records now, behind the scoring pass: later the SMs belong to the next chromosome
     c->counts_valid = false;
-    const int64_t M = std::min<int64_t>(c->cand_cap, PK_EAGER_RECORDS);
-    if ((long long)c->n * c->ND < 0xFFFFFFFFLL && M > 0) {
-        if (c->eager_cap != M || !c->d_packed) {
-            dev_free(c->d_sk0); dev_free(c->d_sk1); dev_free(c->d_si0); dev_free(c->d_si1); dev_free(c->d_stemp); dev_free(c->d_packed);
-            c->stemp_bytes = pk_sort32_temp_bytes(M);
-            PK_CHECK(dev_alloc(&c->d_sk0, (size_t)M)); PK_CHECK(dev_alloc(&c->d_sk1, (size_t)M));
-            PK_CHECK(dev_alloc(&c->d_si0, (size_t)M)); PK_CHECK(dev_alloc(&c->d_si1, (size_t)M));
-            PK_CHECK(dev_alloc(&c->d_stemp, c->stemp_bytes));
-            PK_CHECK(dev_alloc(&c->d_packed, (size_t)M * 28 + 16));
-            c->eager_cap = M;
-        }
-        int key_bits = 0;
-        for (long long v = (long long)c->n * c->ND; v > 0; v >>= 1) ++key_bits;
-        PK_CHECK(pk_launch_sort_records_eager(c, M, std::min(key_bits + 1, 32)));
-        c->eager_valid = true;
-    }
+    PK_CHECK(pk_launch_sort_records_eager(c, c->eager_cap));
+    c->eager_valid = true;
     PK_CUDA(cudaEventRecord(c->ev[10], s));
     return PK_OK;
 }

@@ -117,10 +117,11 @@ struct pk_chrom {
     unsigned long long* d_counters = nullptr;   // [4]: 0 = n_records, 1 = n_windows
     int64_t rec_cap = 0;
     // records sorted by (x, y) and packed right after the scoring pass (no kernel at fetch time)
-    uint32_t *d_sk0 = nullptr, *d_sk1 = nullptr, *d_si0 = nullptr, *d_si1 = nullptr;
-    unsigned char *d_stemp = nullptr, *d_packed = nullptr;
-    size_t stemp_bytes = 0;
-    int64_t eager_cap = 0;              // records the eager sort covers
+    int32_t *d_rowcnt = nullptr, *d_rowoff = nullptr, *d_rrank = nullptr;   // [n], [n+1], [cand_cap]
+    uint32_t* d_perm = nullptr;         // [eager_cap]
+    unsigned char* d_packed = nullptr;
+    int64_t eager_cap = 0;              // records the eager ordering covers
+    int64_t rrank_cap = 0;
     bool eager_valid = false;           // d_packed belongs to the current scores
     cudaStream_t score_stream = nullptr;   // optional second stream for the scoring pass
     bool use_score_stream = false;

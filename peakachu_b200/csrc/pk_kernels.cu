@@ -211,7 +211,8 @@ __global__ void __launch_bounds__(256) k_emit(
     long long cap, double thre, const int32_t* __restrict__ batch_win, int apply_rule,
     const int32_t* __restrict__ band, const double* __restrict__ w, long long pitch, int balanced,
     int32_t* __restrict__ rx, int32_t* __restrict__ ry, double* __restrict__ rp, double* __restrict__ rv,
-    int32_t* __restrict__ rb, unsigned long long* __restrict__ counters) {
+    int32_t* __restrict__ rb, int32_t* __restrict__ rowcnt, int32_t* __restrict__ rrank,
+    unsigned long long* __restrict__ counters) {
     const long long n_cand = min(ncand_dev[0], cap);
     const int lane = threadIdx.x & 31;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__(256) k_emit(
         if (out) {
             const unsigned long long o = base + __popc(bal & ((1u << lane) - 1u));
             rx[o] = x; ry[o] = x + d; rp[o] = p; rb[o] = b;
+            rrank[o] = atomicAdd(&rowcnt[x], 1);              // arrival number inside row x (pk_sort.cu)
             rv[o] = pk_value(band[(long long)d * pitch + x], balanced ? w[x] : 0.0, balanced ? w[x + d] : 0.0, balanced);
         }
     }
@@ -281,7 +283,7 @@ int pk_launch_forest(const pk_forest* f, const float* X, const uint8_t* keep, in
 int pk_launch_emit(pk_chrom* c, double thre) {
     k_emit<<<148 * 4, 256, 0, c->stream>>>(c->d_cx, c->d_cd, c->d_crank, c->d_keep, c->d_prob, c->d_ncand, c->cand_cap, thre,
                                            c->d_batch_win, c->whole ? 1 : 0, c->d_band, c->d_w, c->pitch, c->balanced,
-                                           c->d_rx, c->d_ry, c->d_rp, c->d_rv, c->d_rb, c->d_counters);
+                                           c->d_rx, c->d_ry, c->d_rp, c->d_rv, c->d_rb, c->d_rowcnt, c->d_rrank, c->d_counters);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }

@@ -52,51 +52,78 @@ int pk_launch_sort_records(pk_chrom* c, long long n, unsigned long long* keys_in
 }
 
 // ---------------------------------------------------------------------------
-// Eager variant, queued right behind the scoring pass: the record count is still on the
-// device, so the sort covers a fixed capacity M (unused slots carry the largest key) and
-// the pack reads the count itself. The host later copies packed_bytes(count) -- no kernel
-// has to be scheduled at fetch time, when other chromosomes' kernels own the SMs.
+// Eager variant, queued right behind the scoring pass, when the record count is still on the
+// device. k_emit has counted the records of every row x (rowcnt) and given each record its
+// arrival number within the row (rrank). Three short kernels then order the records by (x, y):
+//   k_row_offsets   exclusive scan of rowcnt (one CTA)
+//   k_record_place  perm[rowoff[x] + rrank] = record; clears rowcnt for the next pass
+//   k_record_pack   rank of a record inside its row = records of the row with a smaller y
+//                   (rows hold a handful of records); writes the packed layout
+// The host later copies packed_bytes(count): no kernel has to be scheduled at fetch time, when
+// other chromosomes' kernels own the SMs.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_record_keys32(const int32_t* __restrict__ rx, const int32_t* __restrict__ ry,
-                                                       const unsigned long long* __restrict__ counters, long long M,
-                                                       uint32_t nd, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= M) return;
-    const long long n = (long long)counters[0];
-    keys[i] = i < n ? (uint32_t)rx[i] * nd + (uint32_t)(ry[i] - rx[i]) : 0xFFFFFFFFu;
-    idx[i] = (uint32_t)i;
+__global__ void __launch_bounds__(1024) k_row_offsets(const int32_t* __restrict__ rowcnt, int n, int32_t* __restrict__ rowoff) {
+    __shared__ int s_part[1024];
+    const int t = threadIdx.x;
+    const int per = (n + 1023) / 1024;
+    const int lo = min(t * per, n), hi = min(lo + per, n);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += rowcnt[i];
+    s_part[t] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                    // Hillis-Steele inclusive scan
+        const int v = t >= o ? s_part[t - o] : 0;
+        __syncthreads();
+        s_part[t] += v;
+        __syncthreads();
+    }
+    int run = s_part[t] - sum;
+    for (int i = lo; i < hi; ++i) { rowoff[i] = run; run += rowcnt[i]; }
+    if (t == 1023) rowoff[n] = s_part[1023];
 }
 
-__global__ void __launch_bounds__(256) k_record_gather_dev(const uint32_t* __restrict__ order, const unsigned long long* __restrict__ counters,
-                                                           long long M, const int32_t* __restrict__ rx, const int32_t* __restrict__ ry,
-                                                           const int32_t* __restrict__ rb, const double* __restrict__ rp,
-                                                           const double* __restrict__ rv, unsigned char* __restrict__ packed) {
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+__global__ void __launch_bounds__(256) k_record_place(const unsigned long long* __restrict__ counters, long long M,
+                                                      const int32_t* __restrict__ rx, const int32_t* __restrict__ rrank,
+                                                      const int32_t* __restrict__ rowoff, int32_t* __restrict__ rowcnt,
+                                                      uint32_t* __restrict__ perm) {
     const long long n = (long long)counters[0];
-    if (i >= n || n > M) return;
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        const int x = rx[i], r = rrank[i];
+        if (r == 0) rowcnt[x] = 0;                          // the scan has consumed it
+        if (n <= M) perm[rowoff[x] + r] = (uint32_t)i;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_record_pack(const unsigned long long* __restrict__ counters, long long M,
+                                                     const uint32_t* __restrict__ perm, const int32_t* __restrict__ rowoff,
+                                                     const int32_t* __restrict__ rx, const int32_t* __restrict__ ry,
+                                                     const int32_t* __restrict__ rb, const double* __restrict__ rp,
+                                                     const double* __restrict__ rv, unsigned char* __restrict__ packed) {
+    const long long n = (long long)counters[0];
+    if (n > M) return;
     const long long off_f64 = ((12 * n + 7) / 8) * 8;
-    const uint32_t j = order[i];
     int32_t* pi = reinterpret_cast<int32_t*>(packed);
     double* pd = reinterpret_cast<double*>(packed + off_f64);
-    pi[i] = rx[j]; pi[n + i] = ry[j]; pi[2 * n + i] = rb[j];
-    pd[i] = rp[j]; pd[n + i] = rv[j];
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        const int x = rx[i], y = ry[i];
+        const int a = rowoff[x], b = rowoff[x + 1];
+        int rank = 0;
+        for (int j = a; j < b; ++j) rank += ry[perm[j]] < y;
+        const long long o = a + rank;
+        pi[o] = x; pi[n + o] = y; pi[2 * n + o] = rb[i];
+        pd[o] = rp[i]; pd[n + o] = rv[i];
+    }
 }
 
-size_t pk_sort32_temp_bytes(long long n) {
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
-                                    (uint32_t*)nullptr, (int)n);
-    return bytes;
-}
-
-int pk_launch_sort_records_eager(pk_chrom* c, long long M, int key_bits) {
-    const unsigned grid = (unsigned)((M + 255) / 256);
-    k_record_keys32<<<grid, 256, 0, c->stream>>>(c->d_rx, c->d_ry, c->d_counters, M, (uint32_t)c->ND, c->d_sk0, c->d_si0);
+int pk_launch_sort_records_eager(pk_chrom* c, long long M) {
+    k_row_offsets<<<1, 1024, 0, c->stream>>>(c->d_rowcnt, c->n, c->d_rowoff);
     PK_CUDA(cudaGetLastError());
-    size_t tb = c->stemp_bytes;
-    PK_CUDA(cub::DeviceRadixSort::SortPairs(c->d_stemp, tb, c->d_sk0, c->d_sk1, c->d_si0, c->d_si1, (int)M, 0, key_bits, c->stream));
-    k_record_gather_dev<<<grid, 256, 0, c->stream>>>(c->d_si1, c->d_counters, M, c->d_rx, c->d_ry, c->d_rb, c->d_rp, c->d_rv,
-                                                     c->d_packed);
+    k_record_place<<<148, 256, 0, c->stream>>>(c->d_counters, M, c->d_rx, c->d_rrank, c->d_rowoff, c->d_rowcnt, c->d_perm);
+    PK_CUDA(cudaGetLastError());
+    k_record_pack<<<148, 256, 0, c->stream>>>(c->d_counters, M, c->d_perm, c->d_rowoff, c->d_rx, c->d_ry, c->d_rb, c->d_rp,
+                                              c->d_rv, c->d_packed);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
