@@ -47,7 +47,7 @@ WORKLOADS = {
     "c1": dict(n=2000, res=10000, lower=6, upper=300, w=5, forest="c2", depth=300.0, band=330,
                desc="score_chromosome 2,000-bin synthetic 10 kb (w=5, l=6, u=300, 100-tree RF)"),
 }
-KERNELS_PER_STEP = 8   # band_csr, diag_sums, fit_expected, cand_mark, scan2, cand_write, score_fused, emit
+KERNELS_PER_STEP = 12  # band_csr, valid_bits, diag_sums, fit_expected, cand_mark, scan2, cand_write, score_fused, emit, row_offsets, record_place, record_pack
 
 
 def band_pixels(n, lower, upper, w):

@@ -846,9 +846,12 @@ static int run_score(pk_chrom* c, pk_forest* f, double min_prob) {
     cudaStream_t s = c->stream;
     PK_CHECK(reset_score_state(c));
     PK_CUDA(cudaEventRecord(c->ev[7], s));
-    const bool fused = g_tune_fused != 0 && pk_fused_supported(c->w, f->n_trees);
+    bool fused = g_tune_fused != 0 && pk_fused_supported(c->w, f->n_trees);
     if (fused) {
         // features stay in shared memory; stage [4] reports the fused kernel, [5] is 0
+        const int variant = g_tune_fused > 1 ? g_tune_fused - 1 : 0;
+        const double thre = g_tune_prune ? min_prob : -1.0;
+        int r;
         if (c->use_score_stream) {
             // The fused kernel may run on a second stream (pk_chrom_set_score_stream): the handle's
             // own stream waits for it, so everything queued on the handle later is ordered behind it.
@@ -856,14 +859,17 @@ static int run_score(pk_chrom* c, pk_forest* f, double min_prob) {
             PK_CUDA(cudaEventRecord(c->ev_x, s));
             PK_CUDA(cudaStreamWaitEvent(c->score_stream, c->ev_x, 0));
             c->stream = c->score_stream;
-            const int r = pk_launch_fused(c, f, g_tune_fused > 1 ? g_tune_fused - 1 : 0, g_tune_prune ? min_prob : -1.0, g_tune_reserve);
+            r = pk_launch_fused(c, f, variant, thre, g_tune_reserve);
             c->stream = s;
-            PK_CHECK(r);
             PK_CUDA(cudaEventRecord(c->ev_x, c->score_stream));
             PK_CUDA(cudaStreamWaitEvent(s, c->ev_x, 0));
         } else {
-            PK_CHECK(pk_launch_fused(c, f, g_tune_fused > 1 ? g_tune_fused - 1 : 0, g_tune_prune ? min_prob : -1.0, 0));
+            r = pk_launch_fused(c, f, variant, thre, 0);
         }
+        if (r == PK_EUNSUPPORTED) fused = false;     // shapes the fused kernel has no room for: the two-kernel path below
+        else PK_CHECK(r);
+    }
+    if (fused) {
         PK_CUDA(cudaEventRecord(c->ev[8], s));
     } else {
         if (!c->n_cand_known) PK_CHECK(settle_candidates(c));

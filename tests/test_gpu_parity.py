@@ -317,6 +317,37 @@ def test_c4_shape_matches_oracle(tmp_path):
     X.close()
 
 
+def test_wide_band_takes_the_two_kernel_path(tmp_path):
+    """upper = 1500 needs more shared memory for the expected curve than the fused kernel has
+    left: the library must fall back to its separate feature and forest kernels, with the same
+    records as the oracle."""
+    import io
+    from contextlib import redirect_stdout
+    from oracle import peakachu_oracle as po
+    from peakachu_b200 import coolio, synth
+    from peakachu_b200.scoreUtils import Chromosome
+    case = Case("tiny")
+    ch = synth.make_chromosome("chr1", 2000, seed=5, depth=120.0, band=1530, n_loops=60, loop_max=1400)
+    X = Chromosome.from_pixels(ch.bin1, ch.bin2, ch.count, ch.weights, ch.n, case.forest, lower=6, upper=1500,
+                               cname="chr1", res=10000, width=5, sorted_pixels=True)
+    x, y, p, v = X.score_records(0.5)
+    assert X.stage_ms()["forest"] > 0.005        # the separate forest kernel ran
+    path = os.path.join(str(tmp_path), "wide.pkcool")
+    coolio.PKCool.write(path, [ch], 10000)
+    lib = coolio.Cooler(path)
+    M = po.tocsr(lib.matrix(balance="weight", sparse=True).fetch("chr1"))
+    raw = po.tocsr(lib.matrix(balance=False, sparse=True).fetch("chr1"))
+    O = po.Chromosome(M, model=case.model(), raw_M=raw, weights=ch.weights, lower=6, upper=1500, cname="chr1",
+                      res=10000, width=5)
+    assert np.array_equal(X.exp_arr, O.exp_arr)
+    with redirect_stdout(io.StringIO()):
+        prob, val = O.score(0.5)
+    r, c = prob.nonzero()
+    assert np.array_equal(x, r) and np.array_equal(y, c)
+    assert np.array_equal(p, np.asarray(prob[r, c]).ravel()) and np.array_equal(v, np.asarray(val[r, c]).ravel())
+    X.close()
+
+
 def test_forest_nan_features_follow_missing_go_to_left():
     """sklearn routes NaN features by missing_go_to_left; the forest tap must
     give the same leaves and probabilities on rows with NaNs."""
