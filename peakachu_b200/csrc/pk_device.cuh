@@ -26,3 +26,52 @@ __host__ __device__ constexpr int pk_reflect(int i, int S) { return i < 0 ? -i -
 #define PK_NODE_MGL(y) (((y) >> 30) & 1u)
 #define PK_NODE_ROFF(y) (((y) >> 12) & 0x3FFFFu)
 #define PK_NODE_ROFF8(y) (((y) >> 9) & 0x1FFFF8u)     /* right-child offset * 8 (byte offset) */
+
+// Exclusive scan of in[0..m) into out[0..m) by ONE CTA of 1024 threads, out[m] = total (returned to
+// every thread). Tiles of 1024 * VPT values: every thread loads its VPT consecutive values before
+// the first is used (one memory round trip per tile), scans them in registers, and a shuffle scan
+// of the per-thread sums supplies the offsets. `s_warp` is 33 words of shared memory.
+template <int VPT, typename T>
+__device__ __forceinline__ uint32_t pk_cta_scan_1024(const T* __restrict__ in, long long m, T* __restrict__ out,
+                                                    uint32_t* s_warp) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t carry = 0;
+    for (long long base = 0; base < m; base += 1024LL * VPT) {
+        const long long i0 = base + (long long)tid * VPT;
+        uint32_t v[VPT];
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) v[j] = (i0 + j < m) ? (uint32_t)in[i0 + j] : 0u;
+        uint32_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) sum += v[j];
+        uint32_t x = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += t;
+        }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = s_warp[lane], y = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, y, o);
+                if (lane >= o) y += t;
+            }
+            s_warp[lane] = y - w;                 // exclusive warp offsets
+            if (lane == 31) s_warp[32] = y;       // tile total
+        }
+        __syncthreads();
+        uint32_t run = carry + s_warp[wid] + x - sum;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            if (i0 + j < m) out[i0 + j] = (T)run;
+            run += v[j];
+        }
+        carry += s_warp[32];
+        __syncthreads();                          // s_warp is reused by the next tile
+    }
+    if (tid == 0) out[m] = (T)carry;
+    return carry;
+}

@@ -4,6 +4,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "pk_common.cuh"
+#include "pk_device.cuh"
 
 __global__ void __launch_bounds__(256) k_record_keys(const int32_t* __restrict__ rx, const int32_t* __restrict__ ry,
                                                      long long n, unsigned long long* __restrict__ keys,
@@ -63,23 +64,8 @@ int pk_launch_sort_records(pk_chrom* c, long long n, unsigned long long* keys_in
 // other chromosomes' kernels own the SMs.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_row_offsets(const int32_t* __restrict__ rowcnt, int n, int32_t* __restrict__ rowoff) {
-    __shared__ int s_part[1024];
-    const int t = threadIdx.x;
-    const int per = (n + 1023) / 1024;
-    const int lo = min(t * per, n), hi = min(lo + per, n);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += rowcnt[i];
-    s_part[t] = sum;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {                    // Hillis-Steele inclusive scan
-        const int v = t >= o ? s_part[t - o] : 0;
-        __syncthreads();
-        s_part[t] += v;
-        __syncthreads();
-    }
-    int run = s_part[t] - sum;
-    for (int i = lo; i < hi; ++i) { rowoff[i] = run; run += rowcnt[i]; }
-    if (t == 1023) rowoff[n] = s_part[1023];
+    __shared__ uint32_t s_warp[33];
+    pk_cta_scan_1024<8>(rowcnt, (long long)n, rowoff, s_warp);
 }
 
 __global__ void __launch_bounds__(256) k_record_place(const unsigned long long* __restrict__ counters, long long M,

@@ -101,19 +101,23 @@ __global__ void __launch_bounds__(256) k_check_sorted(const int32_t* __restrict_
 __global__ void __launch_bounds__(256) k_valid_bits(const uint8_t* __restrict__ valid, const double* __restrict__ w,
                                                     int balanced, int n, uint32_t* __restrict__ vbits, int n_words,
                                                     int32_t* __restrict__ flags) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n_words) return;
-    uint32_t m = 0;
+    // one warp per word, lane = bit: coalesced reads of valid[] and w[]
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * 256) >> 5;
     bool wild = false;
-    for (int b = 0; b < 32; ++b) {
-        const int x = i * 32 + b;
-        if (x < n && valid[x]) m |= 1u << b;
-        if (balanced && x < n) {
-            const double a = fabs(w[x]);
-            wild |= isfinite(a) && a != 0.0 && !(a >= 1e-45 && a <= 1e45);
+    for (int i = (blockIdx.x * 256 + threadIdx.x) >> 5; i < n_words; i += warps) {
+        const int x = i * 32 + lane;
+        bool v = false;
+        if (x < n) {
+            v = valid[x] != 0;
+            if (balanced) {
+                const double a = fabs(w[x]);
+                wild |= isfinite(a) && a != 0.0 && !(a >= 1e-45 && a <= 1e45);
+            }
         }
+        const uint32_t m = __ballot_sync(0xffffffffu, v);
+        if (lane == 0) vbits[i] = m;
     }
-    vbits[i] = m;
     if (wild) atomicOr(&flags[2], 4);
 }
 
@@ -533,31 +537,10 @@ __global__ void __launch_bounds__(256) k_cand_mark(
 __global__ void __launch_bounds__(1024) k_scan2(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
                                                 long long m, uint32_t* __restrict__ oa, uint32_t* __restrict__ ob,
                                                 long long* __restrict__ totals) {
-    __shared__ uint32_t sa[32], sb[32];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long per = (m + 1023) / 1024;
-    const long long i0 = (long long)tid * per, i1 = min(m, i0 + per);
-    uint32_t la = 0, lb = 0;
-    for (long long i = i0; i < i1; ++i) { la += a[i]; lb += b[i]; }
-    uint32_t xa = la, xb = lb;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t ta = __shfl_up_sync(0xffffffffu, xa, o), tb = __shfl_up_sync(0xffffffffu, xb, o);
-        if (lane >= o) { xa += ta; xb += tb; }
-    }
-    if (lane == 31) { sa[wid] = xa; sb[wid] = xb; }
-    __syncthreads();
-    uint32_t pa = 0, pb = 0, ta = 0, tb = 0;
-    for (int k = 0; k < 32; ++k) {
-        if (k < wid) { pa += sa[k]; pb += sb[k]; }
-        ta += sa[k]; tb += sb[k];
-    }
-    uint32_t ra = pa + xa - la, rb = pb + xb - lb;
-    for (long long i = i0; i < i1; ++i) {
-        oa[i] = ra; ob[i] = rb;
-        ra += a[i]; rb += b[i];
-    }
-    if (tid == 0) { oa[m] = ta; ob[m] = tb; totals[0] = tb; totals[1] = ta; }
+    __shared__ uint32_t s_warp[33];
+    const uint32_t ta = pk_cta_scan_1024<8>(a, m, oa, s_warp);
+    const uint32_t tb = pk_cta_scan_1024<8>(b, m, ob, s_warp);
+    if (threadIdx.x == 0) { totals[0] = tb; totals[1] = ta; }
 }
 
 __global__ void __launch_bounds__(256) k_cand_write(
@@ -658,7 +641,7 @@ static int launch_diag_sums_t(pk_chrom* c, int n_words) {
 
 int pk_launch_diag_sums(pk_chrom* c) {
     const int n_words = (c->n + 31) / 32;
-    k_valid_bits<<<(n_words + 255) / 256, 256, 0, c->stream>>>(c->d_valid, c->d_w, c->balanced, c->n, c->d_vbits, n_words,
+    k_valid_bits<<<std::min((n_words + 7) / 8, 148 * 4), 256, 0, c->stream>>>(c->d_valid, c->d_w, c->balanced, c->n, c->d_vbits, n_words,
                                                                 c->d_flags);
     PK_CUDA(cudaGetLastError());
     // leaves of numpy's tree hold at least 57 elements
