@@ -102,6 +102,9 @@ int pk_chrom_upload_csr(pk_chrom* c, const int64_t* bin1_offset, const int32_t* 
  * at the whole matrix. */
 int pk_chrom_upload_csr16(pk_chrom* c, const int64_t* bin1_offset, const uint16_t* bin2_delta, const uint16_t* count,
                           int64_t nnz, const double* weights, int mem);
+/* `peakachu depth` (calculate_depth.py:25-28): sum of the raw counts of the pixels of the last
+ * upload with bin2 - bin1 >= min_dis_bins. Columns passed as device pointers must still be alive. */
+int pk_chrom_depth(pk_chrom* c, int32_t min_dis_bins, int64_t* total);
 /* per-diagonal (sum, n_valid) for d = 0..upper+2w, to HOST arrays of exp_len */
 int pk_chrom_diag_sums(pk_chrom* c, double* out_sum, int64_t* out_cnt);
 /* expected curve fitted by the library itself: mean where n_valid > 10, then the
@@ -125,6 +128,13 @@ int pk_chrom_candidates(pk_chrom* c, int32_t* out_x, int32_t* out_y, int64_t cap
  * [n_candidates][(2w+1)^2] HOST arrays (either may be NULL), rows of rejected
  * candidates are left untouched. */
 int pk_chrom_features(pk_chrom* c, uint8_t* keep, float* fea32, double* fea64, int64_t capacity);
+/* The same windows at caller-supplied pixels (x[i], y[i]), x <= y, HOST int32 arrays: the
+ * training-set extraction of trainUtils.buildmatrix (trainUtils.py:12-44; the caller applies
+ * its coordinate mask, trainUtils.py:22). Needs pixels and an expected curve covering
+ * max(y - x) + 2w + 1 distances. The handle's candidate list is replaced: call
+ * pk_chrom_find_candidates again before scoring. keep / fea32 / fea64 as above, [n] rows. */
+int pk_chrom_features_at(pk_chrom* c, const int32_t* x, const int32_t* y, int64_t n, uint8_t* keep, float* fea32,
+                         double* fea64);
 
 /* Chromosome.score (scoreUtils.py:95-125): features -> forest -> keep prob > min_prob
  * (strict). The reference walks candidates in batches of 100,000 (in its own order,

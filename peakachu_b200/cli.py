@@ -1,7 +1,7 @@
-"""Command line with the reference's flags for the scoring sub-commands
-(scripts/peakachu:5-89): ``score_chromosome`` and ``score_genome``. ``train``,
-``depth`` and ``pool`` are host-side tools of the reference and are not part of
-this path; run the reference's own for those (``pool`` consumes our bedpe as is).
+"""Command line with the reference's flags (scripts/peakachu:5-89) for ``score_chromosome``,
+``score_genome`` and ``depth``. ``train`` and ``pool`` are host-side tools of the reference and
+are not part of this path; run the reference's own for those (``pool`` consumes our bedpe as
+is; ``peakachu_b200.trainUtils.buildmatrix`` provides the training features).
 """
 import argparse
 import sys
@@ -15,9 +15,16 @@ def getargs(argv=None):
                                      help="Calculate interaction probability per pixel for a chromosome")
     subgen = subparsers.add_parser("score_genome",
                                    help="Calculate interaction probability per pixel for the whole genome")
-    from . import score_chromosome, score_genome
+    subdepth = subparsers.add_parser("depth", help="Calculate the total number of intra-chromosomal chromatin "
+                                                   "contacts and select the most appropriate pre-trained model.")
+    from . import calculate_depth, score_chromosome, score_genome
     subchrom.set_defaults(func=score_chromosome.main)
     subgen.set_defaults(func=score_genome.main)
+    subdepth.set_defaults(func=calculate_depth.main)
+    subdepth.add_argument("-p", "--path", help="Path to a .cool URI string")
+    subdepth.add_argument("--min-dis", default=0, type=int,
+                          help="Only count reads with genomic distance (in base pairs) greater than this value.")
+    subdepth.add_argument("--device", type=int, default=None, help="CUDA device. Not a reference flag.")
     for i in (subchrom, subgen):
         i.add_argument("-r", "--resolution", help="Resolution in bp (default 10000)", type=int, default=10000)
         i.add_argument("-p", "--path", help="Path to a .cool URI string")
@@ -41,7 +48,7 @@ def getargs(argv=None):
         i.add_argument("--device", type=int, default=None,
                        help="CUDA device (default: LOCAL_RANK, else 0). Not a reference flag.")
     commands = list(sys.argv[1:] if argv is None else argv)
-    if (not commands) or (commands[0] in ("score_chromosome", "score_genome") and len(commands) == 1):
+    if (not commands) or (commands[0] in ("score_chromosome", "score_genome", "depth") and len(commands) == 1):
         commands.append("-h")
     return parser.parse_args(commands), commands
 

@@ -28,6 +28,7 @@ int pk_launch_emit(pk_chrom* c, double thre);
 int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms);
 size_t pk_sort_temp_bytes(long long n);
 int pk_launch_sort_records_eager(pk_chrom* c, long long M);
+int pk_launch_depth(pk_chrom* c, int32_t min_dis, unsigned long long* d_total);
 int pk_launch_sort_records(pk_chrom* c, long long n, unsigned long long* keys_in, unsigned long long* keys_out,
                            uint32_t* idx_in, uint32_t* idx_out, void* temp, size_t temp_bytes, unsigned char* packed,
                            long long off_f64, int key_bits);
@@ -529,6 +530,7 @@ extern "C" int pk_chrom_upload_pixels(pk_chrom* c, const int32_t* bin1, const in
     PK_CUDA(cudaMemsetAsync(c->d_valid, 0, (size_t)c->n, s));
     PK_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int32_t), s));
     c->declared_sorted = sorted;
+    c->up_kind = sorted ? 2 : 1; c->up_b1 = p1; c->up_b2 = p2; c->up_cnt = pc; c->up_rowptr = c->d_rowptr; c->up_nnz = nnz;
     if (sorted) {
         // cooler order: derive row offsets on the device, then the tiled CSR build
         PK_CHECK(pk_launch_rowptr(c, p1, p2, nnz, c->d_rowptr));
@@ -563,6 +565,7 @@ extern "C" int pk_chrom_upload_csr(pk_chrom* c, const int64_t* bin1_offset, cons
     PK_CUDA(cudaMemsetAsync(c->d_valid, 0, (size_t)c->n, s));
     PK_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int32_t), s));
     c->declared_sorted = false;      // row offsets given: nothing to verify
+    c->up_kind = 2; c->up_b1 = nullptr; c->up_b2 = p2; c->up_cnt = pc; c->up_rowptr = rp; c->up_nnz = nnz;
     PK_CHECK(pk_launch_band_csr(c, rp, p2, pc, 0));
     return after_band(c);
 }
@@ -593,8 +596,24 @@ extern "C" int pk_chrom_upload_csr16(pk_chrom* c, const int64_t* bin1_offset, co
     PK_CUDA(cudaMemsetAsync(c->d_valid, 0, (size_t)c->n, s));
     PK_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int32_t), s));
     c->declared_sorted = false;
+    c->up_kind = 3; c->up_b1 = nullptr; c->up_b2 = p2; c->up_cnt = pc; c->up_rowptr = rp; c->up_nnz = nnz;
     PK_CHECK(pk_launch_band_csr(c, rp, p2, pc, 1));
     return after_band(c);
+}
+
+// calculate_depth.py:25-28: sum of the raw counts of the uploaded pixels with bin2 - bin1 >= min_dis_bins
+extern "C" int pk_chrom_depth(pk_chrom* c, int32_t min_dis_bins, int64_t* total) {
+    if (!c || !total) { pk_set_error("pk_chrom_depth: bad argument"); return PK_EINVAL; }
+    if (!c->has_pixels || c->up_kind == 0) { pk_set_error("pk_chrom_depth: no pixels uploaded"); return PK_ESTATE; }
+    PK_CUDA(cudaSetDevice(c->device));
+    unsigned long long* d_total = c->d_counters + 3;          // spare counter slot
+    PK_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), c->stream));
+    PK_CHECK(pk_launch_depth(c, min_dis_bins, d_total));
+    unsigned long long h = 0;
+    PK_CUDA(cudaMemcpyAsync(&h, d_total, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    PK_CUDA(cudaStreamSynchronize(c->stream));
+    *total = (int64_t)h;
+    return PK_OK;
 }
 
 extern "C" int pk_chrom_diag_sums(pk_chrom* c, double* out_sum, int64_t* out_cnt) {
@@ -839,6 +858,49 @@ extern "C" int pk_chrom_features(pk_chrom* c, uint8_t* keep, float* fea32, doubl
     }
     dev_free(d64);
     c->has_scores = false;
+    return r;
+}
+
+// Window features at caller-supplied pixels: the training-set extraction of trainUtils.buildmatrix
+// (trainUtils.py:12-44). The pixels replace the handle's candidate list.
+extern "C" int pk_chrom_features_at(pk_chrom* c, const int32_t* x, const int32_t* y, int64_t n, uint8_t* keep, float* fea32,
+                                    double* fea64) {
+    if (!c || n < 0 || (n > 0 && (!x || !y))) { pk_set_error("pk_chrom_features_at: bad argument"); return PK_EINVAL; }
+    if (!c->has_pixels || !c->has_expected) { pk_set_error("pk_chrom_features_at: pixels and expected curve needed"); return PK_ESTATE; }
+    std::vector<int32_t> hx((size_t)n), hd((size_t)n), hr((size_t)n, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t d = y[i] - x[i];
+        if (x[i] < 0 || y[i] >= c->n || d < 0) { pk_set_error("pk_chrom_features_at: pixel %lld (%d, %d) is not in the upper triangle", (long long)i, x[i], y[i]); return PK_EINVAL; }
+        // every cell of the window must lie on a stored diagonal with an expected value
+        if (d + 2 * c->w >= c->ND - 1) { pk_set_error("pk_chrom_features_at: pixel %lld at distance %d needs upper >= %d", (long long)i, d, d + 1); return PK_EINVAL; }
+        hx[(size_t)i] = x[i]; hd[(size_t)i] = d;
+    }
+    PK_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    c->has_candidates = false; c->has_scores = false;
+    if (n == 0) return PK_OK;
+    PK_CHECK(reserve_candidates(c, n));
+    PK_CUDA(cudaMemcpyAsync(c->d_cx, hx.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    PK_CUDA(cudaMemcpyAsync(c->d_cd, hd.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    PK_CUDA(cudaMemcpyAsync(c->d_crank, hr.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    long long nc[2] = {(long long)n, (long long)n};
+    PK_CUDA(cudaMemcpyAsync(c->d_ncand, nc, sizeof nc, cudaMemcpyHostToDevice, s));
+    PK_CUDA(cudaStreamSynchronize(s));           // hx, hd, hr, nc are locals
+    c->n_cand = n; c->n_cand_all = n; c->n_cand_known = true;
+    PK_CHECK(reset_score_state(c));
+    PK_CHECK(ensure_feature_buffer(c));
+    double* d64 = nullptr;
+    if (fea64) PK_CHECK(dev_alloc(&d64, (size_t)n * c->F));
+    int r = pk_launch_features(c, d64);
+    if (r == PK_OK) {
+        cudaError_t e = cudaSuccess;
+        if (keep) e = cudaMemcpyAsync(keep, c->d_keep, (size_t)n, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && fea32) e = cudaMemcpyAsync(fea32, c->d_fea32, (size_t)n * c->F * 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && fea64) e = cudaMemcpyAsync(fea64, d64, (size_t)n * c->F * 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { pk_set_error("pk_chrom_features_at: %s", cudaGetErrorString(e)); r = PK_ECUDA; }
+    }
+    dev_free(d64);
     return r;
 }
 

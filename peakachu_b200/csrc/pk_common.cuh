@@ -123,6 +123,12 @@ struct pk_chrom {
     int64_t eager_cap = 0;              // records the eager ordering covers
     int64_t rrank_cap = 0;
     bool eager_valid = false;           // d_packed belongs to the current scores
+    // pixel columns of the last upload as they sit on the device (pk_chrom_depth): kind 0 none,
+    // 1 COO (b1, b2, cnt int32), 2 rows + int32 columns, 3 rows + uint16 (bin2 - bin1, count)
+    int up_kind = 0;
+    const void *up_b1 = nullptr, *up_b2 = nullptr, *up_cnt = nullptr;
+    const long long* up_rowptr = nullptr;
+    int64_t up_nnz = 0;
     cudaStream_t score_stream = nullptr;   // optional second stream for the scoring pass
     bool use_score_stream = false;
     cudaEvent_t ev_x = nullptr;            // hand-over between the two streams

@@ -614,6 +614,61 @@ int pk_launch_band_csr(pk_chrom* c, const long long* rowptr, const void* b2, con
     return launch_band_csr_t<int32_t, int32_t, false>(c, rowptr, b2, cnt);
 }
 
+// ---------------------------------------------------------------------------
+// depth (calculate_depth.py:25-28): sum of the raw counts with bin2 - bin1 >= min_dis over the
+// uploaded pixel columns. A warp per row for row-indexed columns, a thread per pixel for COO.
+// ---------------------------------------------------------------------------
+template <typename TY, typename TC, bool DELTA>
+__global__ void __launch_bounds__(256) k_depth_rows(const long long* __restrict__ rowptr, const TY* __restrict__ b2,
+                                                    const TC* __restrict__ cnt, int n, int min_dis,
+                                                    unsigned long long* __restrict__ total) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * 256) >> 5;
+    unsigned long long sum = 0;
+    for (int x = (blockIdx.x * 256 + threadIdx.x) >> 5; x < n; x += warps) {
+        const long long p0 = rowptr[x], p1 = rowptr[x + 1];
+        for (long long p = p0 + lane; p < p1; p += 32) {
+            const int d = DELTA ? (int)b2[p] : (int)b2[p] - x;
+            const long long c = (long long)cnt[p];
+            if (d >= min_dis && c > 0) sum += (unsigned long long)c;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0 && sum) atomicAdd(total, sum);
+}
+
+__global__ void __launch_bounds__(256) k_depth_coo(const int32_t* __restrict__ b1, const int32_t* __restrict__ b2,
+                                                   const int32_t* __restrict__ cnt, long long nnz, int min_dis,
+                                                   unsigned long long* __restrict__ total) {
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * 256;
+    unsigned long long sum = 0;
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < nnz; p += stride) {
+        const int d = b2[p] - b1[p];
+        if (d >= min_dis && cnt[p] > 0) sum += (unsigned long long)cnt[p];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0 && sum) atomicAdd(total, sum);
+}
+
+int pk_launch_depth(pk_chrom* c, int32_t min_dis, unsigned long long* d_total) {
+    if (c->up_nnz == 0) return PK_OK;
+    const unsigned grid = 148 * 4;
+    if (c->up_kind == 1)
+        k_depth_coo<<<grid, 256, 0, c->stream>>>((const int32_t*)c->up_b1, (const int32_t*)c->up_b2, (const int32_t*)c->up_cnt,
+                                                 c->up_nnz, min_dis, d_total);
+    else if (c->up_kind == 3)
+        k_depth_rows<uint16_t, uint16_t, true><<<grid, 256, 0, c->stream>>>(c->up_rowptr, (const uint16_t*)c->up_b2,
+                                                                            (const uint16_t*)c->up_cnt, c->n, min_dis, d_total);
+    else
+        k_depth_rows<int32_t, int32_t, false><<<grid, 256, 0, c->stream>>>(c->up_rowptr, (const int32_t*)c->up_b2,
+                                                                           (const int32_t*)c->up_cnt, c->n, min_dis, d_total);
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
 int pk_launch_rowptr(pk_chrom* c, const int32_t* b1, const int32_t* b2, int64_t nnz, long long* rowptr) {
     if (nnz > 0) {
         k_check_sorted<<<(unsigned)((nnz + 255) / 256), 256, 0, c->stream>>>(b1, b2, nnz, c->d_flags);

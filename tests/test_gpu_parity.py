@@ -402,3 +402,56 @@ def test_edge_cases_empty_and_tiny():
     prob, val = X.score(thre=1.0)
     assert prob.nnz == 0
     X.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["tiny", "tiny_raw", "w7"])
+def test_buildmatrix_matches_reference(name, tmp_path):
+    """Training-set features (trainUtils.buildmatrix) from the CUDA feature
+    kernel: float64 bit-exact against the reference's own output, through both the pixel-column
+    entry point and the drop-in signature with scipy matrices."""
+    from peakachu_b200 import coolio, trainUtils
+    case = Case(name)
+    cfg, ch = case.cfg, case.chroms[0]
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "buildmatrix.npz"))
+    coords = [tuple(p) for p in g[name + "/coords"].tolist()]
+    raw = cfg["weight"] == "raw"
+    fea = trainUtils.buildmatrix_from_pixels(ch.bin1, ch.bin2, ch.count, None if raw else ch.weights, ch.n, coords,
+                                             w=cfg["w"])
+    assert np.array_equal(np.array(fea), g[name + "/fea"])
+    lib = coolio.Cooler(case.write_cool(tmp_path))
+    raw_M = lib.matrix(balance=False, sparse=True).fetch(ch.name).tocsr()
+    if raw:
+        fea2 = trainUtils.buildmatrix(raw_M, coords, w=cfg["w"])
+    else:
+        M = lib.matrix(balance=cfg["weight"], sparse=True).fetch(ch.name).tocsr()
+        fea2 = trainUtils.buildmatrix(M, coords, w=cfg["w"], raw_M=raw_M, weights=ch.weights)
+    assert np.array_equal(np.array(fea2), g[name + "/fea"])
+    assert trainUtils.buildmatrix_from_pixels(ch.bin1, ch.bin2, ch.count, None, ch.n, coords[:5], w=cfg["w"]) is None
+
+
+@pytest.mark.gpu
+def test_depth_matches_dense_triu_sum(tmp_path, capsys):
+    """`depth` (calculate_depth.py:25-28): device reduction = np.triu(raw, k).sum() for every
+    upload path, and the sub-command prints the reference's three lines."""
+    from peakachu_b200 import calculate_depth, cli, coolio
+    case = Case("genome")
+    path = case.write_cool(tmp_path)
+    lib = coolio.PKCool(path)
+    for ch in case.chroms[:2]:
+        d = ch.bin2 - ch.bin1
+        rp = np.searchsorted(ch.bin1, np.arange(ch.n + 1)).astype(np.int64)
+        for k in (0, 3, 50):
+            want = int(ch.count[d >= k].sum())
+            assert calculate_depth.chromosome_depth((ch.bin1, ch.bin2, ch.count), ch.n, k) == want
+            assert calculate_depth.chromosome_depth((rp, ch.bin2, ch.count), ch.n, k) == want
+            assert calculate_depth.chromosome_depth(lib.upper_pixels_csr16(ch.name), ch.n, k) == want
+        perm = np.random.default_rng(1).permutation(ch.bin1.size)
+        got = calculate_depth.chromosome_depth((ch.bin1[perm], ch.bin2[perm], ch.count[perm]), ch.n, 3)
+        assert got == int(ch.count[d >= 3].sum())
+    cli.run(["depth", "-p", path, "--min-dis", str(2 * case.cfg["res"])])
+    out = capsys.readouterr().out.strip().splitlines()
+    total = sum(int(c.count[(c.bin2 - c.bin1) >= 2].sum()) for c in case.chroms)
+    assert out[-3] == "num of intra reads in your data: %d" % total
+    assert out[-1].startswith("suggested model: ")
+    assert out[:len(case.chroms)] == [c.name for c in case.chroms]

@@ -70,3 +70,17 @@ def test_oracle_bedpe_matches_reference(name, tmp_path):
     po.score_map(lib, case.model(), names, weight_name=cfg["weight"], lower=cfg["lower"],
                  upper=cfg["upper"], res=cfg["res"], min_prob=cfg["min_prob"], output=out)
     assert open(out).read() == case.bedpe                                    # tap (v)
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_raw", "w7"])
+def test_oracle_buildmatrix_matches_reference(name, tmp_path):
+    """trainUtils.buildmatrix (trainUtils.py:12-44): features of the reference itself
+    (tests/golden/make_buildmatrix_golden.py), float64 bit-exact."""
+    case = Case(name)
+    cfg, ch = case.cfg, case.chroms[0]
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "buildmatrix.npz"))
+    lib = coolio.Cooler(case.write_cool(tmp_path))
+    balance = False if cfg["weight"] == "raw" else cfg["weight"]
+    M = po.tocsr(lib.matrix(balance=balance, sparse=True).fetch(ch.name))
+    fea = po.buildmatrix(M, [tuple(p) for p in g[name + "/coords"].tolist()], w=cfg["w"])
+    assert np.array_equal(np.array(fea), g[name + "/fea"])
