@@ -455,3 +455,69 @@ def test_depth_matches_dense_triu_sum(tmp_path, capsys):
     assert out[-3] == "num of intra reads in your data: %d" % total
     assert out[-1].startswith("suggested model: ")
     assert out[:len(case.chroms)] == [c.name for c in case.chroms]
+
+
+@pytest.mark.gpu
+def test_full_size_c2_properties():
+    """BASELINE configs[1] at full size (24,900 bins, 7.3 M band pixels, the 100-tree bench
+    forest), where the oracle would take minutes: size-independent properties instead.
+    (1) fused kernel == separate feature + forest kernels, record for record, bit for bit;
+    (2) pruning (pixels that cannot exceed min_prob stop walking trees) changes nothing;
+    (3) uint16 columns == int32 columns == unordered COO upload;
+    (4) three band row tiles == the whole chromosome (the multi-GPU seam);
+    (5) every record obeys prob > min_prob, lower <= y - x <= upper, and value == (w_x w_y) count;
+    (6) a higher min_prob yields exactly the subset of the records above it."""
+    from peakachu_b200 import _lib, shard, synth
+    from peakachu_b200.forest import FlatForest
+    from peakachu_b200.scoreUtils import Chromosome
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    flat = FlatForest.load(os.path.join(root, "bench_data", "c2_forest.npz"))
+    ch = synth.make_chromosome("chr1", 24900, seed=1234, depth=300.0, band=330)
+    n = ch.n
+    rp = np.searchsorted(ch.bin1, np.arange(n + 1)).astype(np.int64)
+    kw = dict(lower=6, upper=300, cname="chr1", res=10000, width=5)
+    L = _lib.lib()
+    X = Chromosome.from_csr(rp, ch.bin2, ch.count, ch.weights, n, flat, **kw)
+    ref = X.score_records(0.5)
+    assert ref[0].size > 10000
+    try:
+        _lib.check(L.pk_set_tuning(b"fused", 0))                              # (1)
+        two = X.score_records(0.5)
+        _lib.check(L.pk_set_tuning(b"fused", -1))
+        _lib.check(L.pk_set_tuning(b"prune", 0))                              # (2)
+        full = X.score_records(0.5)
+    finally:
+        _lib.check(L.pk_set_tuning(b"fused", -1))
+        _lib.check(L.pk_set_tuning(b"prune", 1))
+    for other in (two, full):
+        assert all(np.array_equal(a, b) for a, b in zip(ref, other))
+    hi = X.score_records(0.9)                                                 # (6)
+    sel = ref[2] > 0.9
+    assert all(np.array_equal(a[sel], b) for a, b in zip(ref, hi))
+    X.close()
+    N = Chromosome.from_csr16(rp, (ch.bin2 - ch.bin1).astype(np.uint16), ch.count.astype(np.uint16), ch.weights,
+                              n, flat, **kw)                                  # (3)
+    perm = np.random.default_rng(3).permutation(ch.bin1.size)
+    U = Chromosome.from_pixels(ch.bin1[perm], ch.bin2[perm], ch.count[perm], ch.weights, n, flat,
+                               sorted_pixels=False, **kw)
+    for Y in (N, U):
+        got = Y.score_records(0.5)
+        assert all(np.array_equal(a, b) for a, b in zip(ref, got))
+        Y.close()
+
+    class OneChrom:                                                           # (4)
+        def upper_pixels_csr(self, k): return rp, ch.bin2, ch.count
+        def weights(self, k, name): return ch.weights
+        def nbins(self, k): return n
+    tiles = shard.score_units(OneChrom(), [("chr1", 0, 9000), ("chr1", 9000, 17001), ("chr1", 17001, n)], flat,
+                              correct="weight", lower=6, upper=300, res=10000, device=0, min_prob=0.5)
+    tx, ty, tp, tv = shard.merge_tiles(sorted(tiles["chr1"], key=lambda q: q["row_begin"]))
+    assert all(np.array_equal(a, b) for a, b in zip(ref, (tx, ty, tp, tv)))
+    x, y, p, v = ref                                                          # (5)
+    assert np.all(p > 0.5) and np.all(p <= 1.0)
+    assert np.all(y - x >= 6) and np.all(y - x <= 300)
+    assert np.all(np.lexsort((y, x)) == np.arange(x.size))
+    from scipy import sparse
+    C_ = sparse.csr_matrix((ch.count, (ch.bin1, ch.bin2)), shape=(n, n))
+    cnt = np.asarray(C_[x, y]).ravel()
+    assert np.array_equal(v, (ch.weights[x] * ch.weights[y]) * cnt)
