@@ -521,3 +521,44 @@ def test_full_size_c2_properties():
     C_ = sparse.csr_matrix((ch.count, (ch.bin1, ch.bin2)), shape=(n, n))
     cnt = np.asarray(C_[x, y]).ravel()
     assert np.array_equal(v, (ch.weights[x] * ch.weights[y]) * cnt)
+
+
+@pytest.mark.gpu
+def test_full_size_c4_properties():
+    """BASELINE configs[3] shape for one chromosome at full length (49,850 bins at 5 kb, upper=600,
+    w=7, the 200-tree bench forest): fused kernel == separate kernels, pruning changes nothing,
+    narrow columns == int32 columns, record invariants."""
+    from peakachu_b200 import _lib, synth
+    from peakachu_b200.forest import FlatForest
+    from peakachu_b200.scoreUtils import Chromosome
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    flat = FlatForest.load(os.path.join(root, "bench_data", "c4_forest.npz"))
+    ch = synth.make_chromosome("chr1", 49850, seed=1234, depth=300.0, band=640)
+    n = ch.n
+    rp = np.searchsorted(ch.bin1, np.arange(n + 1)).astype(np.int64)
+    kw = dict(lower=6, upper=600, cname="chr1", res=5000, width=7)
+    L = _lib.lib()
+    X = Chromosome.from_csr(rp, ch.bin2, ch.count, ch.weights, n, flat, **kw)
+    assert X.lower == 8                                     # max(lower, w + 1), scoreUtils.py:13
+    ref = X.score_records(0.5)
+    assert ref[0].size > 10000
+    try:
+        _lib.check(L.pk_set_tuning(b"fused", 0))
+        two = X.score_records(0.5)
+        _lib.check(L.pk_set_tuning(b"fused", -1))
+        _lib.check(L.pk_set_tuning(b"prune", 0))
+        full = X.score_records(0.5)
+    finally:
+        _lib.check(L.pk_set_tuning(b"fused", -1))
+        _lib.check(L.pk_set_tuning(b"prune", 1))
+    for other in (two, full):
+        assert all(np.array_equal(a, b) for a, b in zip(ref, other))
+    X.close()
+    N = Chromosome.from_csr16(rp, (ch.bin2 - ch.bin1).astype(np.uint16), ch.count.astype(np.uint16), ch.weights,
+                              n, flat, **kw)
+    got = N.score_records(0.5)
+    assert all(np.array_equal(a, b) for a, b in zip(ref, got))
+    N.close()
+    x, y, p, v = ref
+    assert np.all(p > 0.5) and np.all(y - x >= 8) and np.all(y - x <= 600)
+    assert np.all(np.lexsort((y, x)) == np.arange(x.size))
