@@ -562,3 +562,35 @@ def test_full_size_c4_properties():
     x, y, p, v = ref
     assert np.all(p > 0.5) and np.all(y - x >= 8) and np.all(y - x <= 600)
     assert np.all(np.lexsort((y, x)) == np.arange(x.size))
+
+
+@pytest.mark.gpu
+def test_long_chromosome_matches_oracle(tmp_path):
+    """70,000 bins (longer than 57 * 1024: the per-diagonal sums take their large-table variant,
+    numpy's pairwise tree is two levels deeper): expected curve, candidates and records bit-exact
+    against the oracle."""
+    import io
+    from contextlib import redirect_stdout
+    from oracle import peakachu_oracle as po
+    from peakachu_b200 import coolio, synth
+    from peakachu_b200.scoreUtils import Chromosome
+    case = Case("tiny")
+    ch = synth.make_chromosome("chr1", 70000, seed=9, depth=40.0, band=90, n_loops=200, loop_max=60)
+    X = Chromosome.from_pixels(ch.bin1, ch.bin2, ch.count, ch.weights, ch.n, case.forest, lower=6, upper=60,
+                               cname="chr1", res=10000, width=5, sorted_pixels=True)
+    x, y, p, v = X.score_records(0.5)
+    path = os.path.join(str(tmp_path), "long.pkcool")
+    coolio.PKCool.write(path, [ch], 10000)
+    lib = coolio.Cooler(path)
+    M = po.tocsr(lib.matrix(balance="weight", sparse=True).fetch("chr1"))
+    raw = po.tocsr(lib.matrix(balance=False, sparse=True).fetch("chr1"))
+    O = po.Chromosome(M, model=case.model(), raw_M=raw, weights=ch.weights, lower=6, upper=60, cname="chr1",
+                      res=10000, width=5)
+    assert np.array_equal(X.exp_arr, O.exp_arr)
+    assert np.array_equal(X.ridx, O.ridx) and np.array_equal(X.cidx, O.cidx)
+    with redirect_stdout(io.StringIO()):
+        prob, val = O.score(0.5)
+    r, c = prob.nonzero()
+    assert np.array_equal(x, r) and np.array_equal(y, c)
+    assert np.array_equal(p, np.asarray(prob[r, c]).ravel()) and np.array_equal(v, np.asarray(val[r, c]).ravel())
+    X.close()
