@@ -28,22 +28,33 @@ __host__ __device__ constexpr int pk_reflect(int i, int S) { return i < 0 ? -i -
 #define PK_NODE_ROFF8(y) (((y) >> 9) & 0x1FFFF8u)     /* right-child offset * 8 (byte offset) */
 
 // Exclusive scan of in[0..m) into out[0..m) by ONE CTA of 1024 threads, out[m] = total (returned to
-// every thread). Tiles of 1024 * VPT values: every thread loads its VPT consecutive values before
-// the first is used (one memory round trip per tile), scans them in registers, and a shuffle scan
-// of the per-thread sums supplies the offsets. `s_warp` is 33 words of shared memory.
-template <int VPT, typename T>
+// every thread). `in` and `out` are 16-byte aligned 32-bit arrays. Tiles of 4096 values: a thread
+// moves its four consecutive values with one 128-bit load / store (coalesced -- a single SM's
+// load/store unit is the bottleneck of a one-CTA kernel), the next tile's load is issued before
+// the current tile is scanned, and a shuffle scan of the per-thread sums supplies the offsets.
+// `s_warp` is 33 words of shared memory.
+template <typename T>
 __device__ __forceinline__ uint32_t pk_cta_scan_1024(const T* __restrict__ in, long long m, T* __restrict__ out,
                                                     uint32_t* s_warp) {
+    static_assert(sizeof(T) == 4, "32-bit elements");
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    auto load4 = [&](long long i0) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (i0 + 3 < m) v = *reinterpret_cast<const uint4*>(in + i0);
+        else {
+            if (i0 < m) v.x = (uint32_t)in[i0];
+            if (i0 + 1 < m) v.y = (uint32_t)in[i0 + 1];
+            if (i0 + 2 < m) v.z = (uint32_t)in[i0 + 2];
+        }
+        return v;
+    };
     uint32_t carry = 0;
-    for (long long base = 0; base < m; base += 1024LL * VPT) {
-        const long long i0 = base + (long long)tid * VPT;
-        uint32_t v[VPT];
-#pragma unroll
-        for (int j = 0; j < VPT; ++j) v[j] = (i0 + j < m) ? (uint32_t)in[i0 + j] : 0u;
-        uint32_t sum = 0;
-#pragma unroll
-        for (int j = 0; j < VPT; ++j) sum += v[j];
+    uint4 nxt = load4((long long)tid * 4);
+    for (long long base = 0; base < m; base += 4096) {
+        const long long i0 = base + (long long)tid * 4;
+        const uint4 v = nxt;
+        if (base + 4096 < m) nxt = load4(i0 + 4096);
+        const uint32_t sum = v.x + v.y + v.z + v.w;
         uint32_t x = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -63,11 +74,14 @@ __device__ __forceinline__ uint32_t pk_cta_scan_1024(const T* __restrict__ in, l
             if (lane == 31) s_warp[32] = y;       // tile total
         }
         __syncthreads();
-        uint32_t run = carry + s_warp[wid] + x - sum;
-#pragma unroll
-        for (int j = 0; j < VPT; ++j) {
-            if (i0 + j < m) out[i0 + j] = (T)run;
-            run += v[j];
+        uint4 r;
+        r.x = carry + s_warp[wid] + x - sum;
+        r.y = r.x + v.x; r.z = r.y + v.y; r.w = r.z + v.z;
+        if (i0 + 3 < m) *reinterpret_cast<uint4*>(out + i0) = r;
+        else {
+            if (i0 < m) out[i0] = (T)r.x;
+            if (i0 + 1 < m) out[i0 + 1] = (T)r.y;
+            if (i0 + 2 < m) out[i0 + 2] = (T)r.z;
         }
         carry += s_warp[32];
         __syncthreads();                          // s_warp is reused by the next tile

@@ -65,7 +65,7 @@ int pk_launch_sort_records(pk_chrom* c, long long n, unsigned long long* keys_in
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_row_offsets(const int32_t* __restrict__ rowcnt, int n, int32_t* __restrict__ rowoff) {
     __shared__ uint32_t s_warp[33];
-    pk_cta_scan_1024<8>(rowcnt, (long long)n, rowoff, s_warp);
+    pk_cta_scan_1024(rowcnt, (long long)n, rowoff, s_warp);
 }
 
 __global__ void __launch_bounds__(256) k_record_place(const unsigned long long* __restrict__ counters, long long M,

@@ -538,8 +538,8 @@ __global__ void __launch_bounds__(1024) k_scan2(const uint32_t* __restrict__ a, 
                                                 long long m, uint32_t* __restrict__ oa, uint32_t* __restrict__ ob,
                                                 long long* __restrict__ totals) {
     __shared__ uint32_t s_warp[33];
-    const uint32_t ta = pk_cta_scan_1024<8>(a, m, oa, s_warp);
-    const uint32_t tb = pk_cta_scan_1024<8>(b, m, ob, s_warp);
+    const uint32_t ta = pk_cta_scan_1024(a, m, oa, s_warp);
+    const uint32_t tb = pk_cta_scan_1024(b, m, ob, s_warp);
     if (threadIdx.x == 0) { totals[0] = tb; totals[1] = ta; }
 }
 
