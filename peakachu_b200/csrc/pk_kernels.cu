@@ -221,11 +221,17 @@ __global__ void __launch_bounds__(256) k_emit(
         bool out = false;
         int x = 0, d = 0, b = 0;
         double p = 0.0;
-        if (i < n_cand && keep[i]) {
-            p = prob[i];
-            b = crank[i] / PK_BATCH;
-            out = (p > thre) && (!apply_rule || batch_win[b] > 1);
+        if (i < n_cand) {
+            // independent loads first: one memory round trip for the five columns
+            const uint8_t kp = keep[i];
+            const double pv = prob[i];
+            const int rk = crank[i];
             x = cx[i]; d = cd[i];
+            if (kp) {
+                p = pv;
+                b = rk / PK_BATCH;
+                out = (p > thre) && (!apply_rule || batch_win[b] > 1);
+            }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, out);
         if (bal == 0) continue;

@@ -19,15 +19,16 @@
 template <typename TY, typename TC, bool DELTA>
 __global__ void __launch_bounds__(256) k_band_csr(
     const long long* __restrict__ rowptr, const TY* __restrict__ b2, const TC* __restrict__ cnt,
-    const double* __restrict__ w, int n, int ND, long long pitch, int balanced,
+    const double* __restrict__ w, int n, int ND, long long pitch, int balanced, int R,
     int32_t* __restrict__ band, uint8_t* __restrict__ valid, int32_t* __restrict__ flags) {
-    extern __shared__ int32_t s_tile[];                 // [ND][33]
-    const int x0 = blockIdx.x * 32;
+    extern __shared__ int32_t s_tile[];                 // [ND][R + 1], R rows per CTA
+    const int TP = R + 1;
+    const int x0 = blockIdx.x * R;
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-    for (int i = tid; i < ND * 33; i += 256) s_tile[i] = 0;
+    for (int i = tid; i < ND * TP; i += 256) s_tile[i] = 0;
     __syncthreads();
     int cmax = 0;
-    for (int xl = wib; xl < 32; xl += 8) {
+    for (int xl = wib; xl < R; xl += 8) {
         const int x = x0 + xl;
         if (x >= n) break;
         const long long p0 = rowptr[x], p1 = rowptr[x + 1];
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(256) k_band_csr(
                 if (fin) { any = true; valid[y[j]] = 1; }
                 const int d = y[j] - x;
                 if (d < ND) {
-                    atomicAdd(&s_tile[d * 33 + xl], c[j]);     // duplicates are summed like utils.tocsr
+                    atomicAdd(&s_tile[d * TP + xl], c[j]);     // duplicates are summed like utils.tocsr
                     cmax = max(cmax, c[j]);
                 }
             }
@@ -67,9 +68,8 @@ __global__ void __launch_bounds__(256) k_band_csr(
     for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
     if (lane == 0 && cmax > 0) atomicMax(&flags[1], cmax);
     __syncthreads();
-    const int x = x0 + lane;
-    if (x < n)
-        for (int d = wib; d < ND; d += 8) band[(long long)d * pitch + x] = s_tile[d * 33 + lane];
+    for (int d = wib; d < ND; d += 8)
+        for (int xl = lane; xl < R && x0 + xl < n; xl += 32) band[(long long)d * pitch + x0 + xl] = s_tile[d * TP + xl];
 }
 
 // rowptr for pixels sorted by (bin1, bin2): rowptr[x] = first pixel with bin1 >= x
@@ -491,20 +491,20 @@ __global__ void __launch_bounds__(256) k_cand_mark(
     const int32_t* row = band + (long long)d * pitch;
     const long long slot = (long long)di * n_chunks + chunk;
     __shared__ int s_a[8], s_t[8];
+    // counts and weights are loaded side by side with bg[d] (one memory round trip, not three)
     int k[4];
     double wx[4], wy[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int x = chunk * PK_CHUNK + j * 256 + tid;
-        k[j] = (d_ok && x < len) ? row[x] : 0;
+        const bool in = x < len;
+        k[j] = in ? row[x] : 0;
+        wx[j] = (balanced && in) ? w[x] : 1.0;
+        wy[j] = (balanced && in) ? w[x + d] : 1.0;
     }
-    if (balanced) {
+    if (!d_ok) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int x = chunk * PK_CHUNK + j * 256 + tid;
-            wx[j] = k[j] > 0 ? w[x] : 1.0;
-            wy[j] = k[j] > 0 ? w[x + d] : 1.0;
-        }
+        for (int j = 0; j < 4; ++j) k[j] = 0;
     }
     int tot_a = 0, tot_t = 0;
 #pragma unroll
@@ -594,16 +594,27 @@ __global__ void __launch_bounds__(256) k_cand_write(
 // ---------------------------------------------------------------------------
 template <typename TY, typename TC, bool DELTA>
 static int launch_band_csr_t(pk_chrom* c, const long long* rowptr, const void* b2, const void* cnt) {
-    const size_t smem = (size_t)c->ND * 33 * sizeof(int32_t);
+    // Rows per CTA: 32, or a few more when that lets every CTA be resident at once. The band
+    // barely fits the GPU's shared memory, so with 32 rows a chr1-scale chromosome needs 779
+    // CTAs for 740 slots -- a second wave for 5 % of the work.
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    auto tile_bytes = [&](int R) { return (size_t)c->ND * (R + 1) * sizeof(int32_t); };
+    auto slots = [&](int R) { return (long long)sms * std::min<long long>(8, (long long)((227 * 1024) / (tile_bytes(R) + 1024))); };
+    int R = 32;
+    if ((c->n + 31) / 32 > slots(32))
+        for (int r = 34; r <= 64; r += 2)
+            if ((c->n + r - 1) / r <= slots(r)) { R = r; break; }
+    const size_t smem = tile_bytes(R);
     if (smem > 200 * 1024) { pk_set_error("band build: %d diagonals do not fit a shared-memory tile", c->ND); return PK_EUNSUPPORTED; }
     static size_t attr_set = 0;
     if (smem > 48 * 1024 && smem > attr_set) {
         PK_CUDA(cudaFuncSetAttribute(k_band_csr<TY, TC, DELTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
-    const unsigned grid = (unsigned)((c->n + 31) / 32);
+    const unsigned grid = (unsigned)((c->n + R - 1) / R);
     k_band_csr<TY, TC, DELTA><<<grid, 256, smem, c->stream>>>(rowptr, (const TY*)b2, (const TC*)cnt, c->d_w, c->n, c->ND, c->pitch,
-                                                              c->balanced, c->d_band, c->d_valid, c->d_flags);
+                                                              c->balanced, R, c->d_band, c->d_valid, c->d_flags);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
