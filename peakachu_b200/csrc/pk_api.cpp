@@ -92,10 +92,9 @@ extern "C" int pk_device_count(int* out) {
 // blocks are kept per device and reused for requests of up to twice their size.
 // ---------------------------------------------------------------------------
 namespace {
-struct Block { void* p; size_t bytes; };
 std::mutex g_pool_mu;
-std::map<int, std::vector<Block>> g_pool_free;         // device -> cached blocks
-std::map<void*, std::pair<int, size_t>> g_pool_live;   // pointer -> (device, bytes)
+std::map<int, std::multimap<size_t, void*>> g_pool_free;   // device -> cached blocks by size
+std::map<void*, std::pair<int, size_t>> g_pool_live;       // pointer -> (device, bytes)
 }  // namespace
 
 static int pool_alloc(void** out, size_t bytes) {
@@ -107,13 +106,11 @@ static int pool_alloc(void** out, size_t bytes) {
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
         auto& fl = g_pool_free[dev];
-        int best = -1;
-        for (int i = 0; i < (int)fl.size(); ++i)
-            if (fl[i].bytes >= bytes && fl[i].bytes <= 2 * bytes + 4096 && (best < 0 || fl[i].bytes < fl[best].bytes)) best = i;
-        if (best >= 0) {
-            *out = fl[best].p;
-            g_pool_live[*out] = {dev, fl[best].bytes};
-            fl.erase(fl.begin() + best);
+        auto it = fl.lower_bound(bytes);                 // smallest cached block that is large enough
+        if (it != fl.end() && it->first <= 2 * bytes + 4096) {
+            *out = it->second;
+            g_pool_live[*out] = {dev, it->first};
+            fl.erase(it);
             return PK_OK;
         }
     }
@@ -132,7 +129,7 @@ static void pool_free(void* p) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     auto it = g_pool_live.find(p);
     if (it == g_pool_live.end()) { cudaFree(p); return; }
-    g_pool_free[it->second.first].push_back({p, it->second.second});
+    g_pool_free[it->second.first].emplace(it->second.second, p);
     g_pool_live.erase(it);
 }
 
@@ -200,7 +197,7 @@ extern "C" int pk_release_memory(void) {
     for (auto& kv : g_pool_free) {
         cudaSetDevice(kv.first);
         cudaDeviceSynchronize();
-        for (auto& b : kv.second) cudaFree(b.p);
+        for (auto& b : kv.second) cudaFree(b.second);
         kv.second.clear();
     }
     std::lock_guard<std::mutex> lk2(g_hstage_mu);

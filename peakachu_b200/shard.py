@@ -103,7 +103,7 @@ def _fetch_tile(X, a, b, n, ncand=None):
                 batch_windows=bw[:nb.value], n_candidates=int(nc.value))
 
 
-def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_prob, depth=6):
+def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_prob, depth=6, shared_score_stream=True):
     """Score this rank's units. Returns {chrom: [tile dict, ...]}.
 
     Chromosomes are pipelined over ``depth`` streams: while one chromosome's kernels
@@ -153,7 +153,7 @@ def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_pro
             n = Lib.nbins(key)
             kw = dict(lower=lower, upper=upper, cname="chr" + key.lstrip("chr"), res=res, width=flat.width,
                       device=device, stream=streams[i % len(streams)].value, first_tile=tiles[0],
-                      score_stream=score_stream.value)
+                      score_stream=score_stream.value if shared_score_stream else None)
             narrow = Lib.upper_pixels_csr16(key) if hasattr(Lib, "upper_pixels_csr16") else None
             if narrow is not None:
                 X = Chromosome.from_csr16(*narrow, weights, n, forest, **kw)
