@@ -10,6 +10,8 @@ The reference reads a ``.cool`` through four ``cooler`` calls
 
 ``cooler``/``h5py`` are not installed in this image, so this module provides
 
+* ``H5Cool`` -- a reader of real cooler files over the built-in HDF5 subset reader
+  (``h5mini``), with PKCool's surface,
 * ``PKCool`` -- an on-disk container (``.pkcool`` = numpy ``.npz``) holding the
   same columns a cooler file holds (``pixels/{bin1_id,bin2_id,count}`` with
   genome-wide bin ids, ``bins/<weight>``, ``chroms/{name,length}``,
@@ -25,8 +27,7 @@ cooler itself is absent, so this definition is the boundary's contract
 
 ``open_map`` is what the product path calls: it returns the upper-triangle pixel
 triplets and the weight vector per chromosome (what the CUDA band build
-consumes), from a ``.pkcool`` or -- when the real ``cooler`` package exists --
-from a real ``.cool`` URI.
+consumes), from a ``.pkcool`` or from a real ``.cool`` / ``.mcool::group`` URI.
 """
 from __future__ import annotations
 
@@ -228,18 +229,150 @@ class _RealCoolAdapter:
         return np.ascontiguousarray(self._c.bins().fetch(chrom)[name].values, dtype=np.float64)
 
 
+class H5Cool:
+    """Same surface as PKCool over a real cooler file (``.cool`` / ``.mcool::/resolutions/N``),
+    read with the built-in HDF5 subset reader (``h5mini``) -- no h5py / cooler needed.
+
+    cooler's schema: ``pixels/{bin1_id,bin2_id,count}`` sorted by (bin1, bin2), upper triangle
+    (``storage-mode = symmetric-upper``), genome-wide bin ids, inter-chromosomal pixels included;
+    ``indexes/bin1_offset`` is the CSR row pointer of that table and ``indexes/chrom_offset`` the
+    first bin of each chromosome. ``matrix(...).fetch(chrom)`` of the reference
+    (``score_chromosome.py:42-43``) is the intra-chromosomal block: pixels of the chromosome's
+    rows whose ``bin2`` also lies in the chromosome."""
+
+    def __init__(self, uri: str):
+        from . import h5mini
+        path, _, group = uri.partition("::")
+        self.path = path
+        self._f = h5mini.File(path)
+        g = self._f[group] if group.strip("/") else self._f.root
+        for need in ("chroms/name", "indexes/chrom_offset", "indexes/bin1_offset", "pixels/bin2_id", "pixels/count"):
+            if need not in g:
+                raise KeyError("%s: not a cooler (no %s); multi-resolution files need "
+                               "'file.mcool::/resolutions/<binsize>'" % (uri, need))
+        self._g = g
+        self.chromnames = [s.split(b"\0")[0].decode() for s in g["chroms/name"].read()]
+        self.chrom_offset = g["indexes/chrom_offset"].read().astype(np.int64)
+        self.chrom_lengths = g["chroms/length"].read().astype(np.int64) if "chroms/length" in g else None
+        bs = g.attrs.get("bin-size")
+        if bs is None and "bins/start" in g:
+            se = g["bins/start"].read(0, 1), g["bins/end"].read(0, 1)
+            bs = int(se[1][0] - se[0][0])
+        self.binsize = int(bs) if bs is not None else None
+        self._bin1_offset = g["indexes/bin1_offset"]
+        self._bin2 = g["pixels/bin2_id"]
+        self._count = g["pixels/count"]
+        self._cache = (None, None)
+
+    def close(self):
+        self._f.close()
+
+    def _cid(self, chrom: str) -> int:
+        try:
+            return self.chromnames.index(chrom)
+        except ValueError:
+            raise KeyError("chromosome %r not in %s" % (chrom, self.path)) from None
+
+    def nbins(self, chrom: str) -> int:
+        i = self._cid(chrom)
+        return int(self.chrom_offset[i + 1] - self.chrom_offset[i])
+
+    def _fetch(self, chrom: str):
+        """(row pointer int64[n+1], bin2 int32 local, count int32) of the intra-chromosomal block."""
+        if self._cache[0] == chrom:
+            return self._cache[1]
+        i = self._cid(chrom)
+        lo, hi = int(self.chrom_offset[i]), int(self.chrom_offset[i + 1])
+        n = hi - lo
+        rp = self._bin1_offset.read(lo, hi + 1).astype(np.int64)
+        p0, p1 = int(rp[0]), int(rp[-1])
+        b2 = self._bin2.read(p0, p1).astype(np.int64)
+        cnt = self._count.read(p0, p1)
+        if cnt.dtype.kind == "f":
+            if not np.all(cnt == np.rint(cnt)):
+                raise ValueError("%s: non-integer pixel counts; the Poisson filter "
+                                 "(scoreUtils.py:59-60) needs raw counts" % self.path)
+        if cnt.size and (cnt.min() < 0 or cnt.max() > np.iinfo(np.int32).max):
+            raise ValueError("%s: pixel counts outside int32" % self.path)
+        cnt = cnt.astype(np.int32)
+        rp -= p0
+        cis = b2 < hi
+        if b2.size and b2.min() < lo:
+            raise ValueError("%s: pixels below the diagonal (storage-mode is not symmetric-upper)" % self.path)
+        if not cis.all():                                    # drop inter-chromosomal pixels, rebuild the row pointer
+            rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+            rp = np.concatenate([[0], np.cumsum(np.bincount(rows[cis], minlength=n))]).astype(np.int64)
+            b2, cnt = b2[cis], cnt[cis]
+        out = (rp, (b2 - lo).astype(np.int32), np.ascontiguousarray(cnt))
+        self._cache = (chrom, out)
+        return out
+
+    def upper_pixels_csr(self, chrom: str):
+        return self._fetch(chrom)
+
+    def upper_pixels(self, chrom: str):
+        rp, b2, cnt = self._fetch(chrom)
+        b1 = np.repeat(np.arange(rp.size - 1, dtype=np.int32), np.diff(rp))
+        return b1, b2, cnt
+
+    def upper_pixels_csr16(self, chrom: str):
+        rp, b2, cnt = self._fetch(chrom)
+        if not b2.size:
+            return None
+        delta = b2 - np.repeat(np.arange(rp.size - 1, dtype=np.int32), np.diff(rp))
+        if int(delta.max()) > 65535 or int(delta.min()) < 0 or int(cnt.max()) > 65535:
+            return None
+        return rp, delta.astype(np.uint16), cnt.astype(np.uint16)
+
+    def weights(self, chrom: str, name: str) -> np.ndarray:
+        key = "bins/" + name
+        if key not in self._g:
+            raise KeyError("no weight column %r in %s" % (name, self.path))
+        i = self._cid(chrom)
+        return np.ascontiguousarray(self._g[key].read(int(self.chrom_offset[i]), int(self.chrom_offset[i + 1])),
+                                    dtype=np.float64)
+
+
+def _is_hdf5(path: str) -> bool:
+    from .h5mini import SIGNATURE
+    try:
+        with open(path, "rb") as fh:
+            pos = 0
+            while True:
+                fh.seek(pos)
+                head = fh.read(8)
+                if len(head) < 8:
+                    return False
+                if head == SIGNATURE:
+                    return True
+                pos = 512 if pos == 0 else pos * 2
+    except OSError:
+        return False
+
+
 def open_map(uri: str):
-    """Open a contact map for the CUDA path: ``.pkcool`` container, or a real
-    ``.cool`` URI when the ``cooler`` package is importable."""
+    """Open a contact map for the CUDA path: a ``.pkcool`` container or a real cooler file
+    (``.cool``, ``.mcool::/resolutions/N``). Cooler files are read by the built-in HDF5 subset
+    reader; a file that uses HDF5 features outside that subset falls back to the ``cooler``
+    package when it is importable."""
     path = uri.split("::")[0]
     if path.endswith(".pkcool") or path.endswith(".npz"):
         return PKCool(path)
     try:
-        import cooler  # noqa: F401
-    except ImportError as e:
-        raise RuntimeError(
-            "%s is not a .pkcool container and the `cooler` package (HDF5) is not "
-            "installed in this environment" % uri) from e
-    if getattr(cooler, "Cooler", None) is Cooler:   # stand-in injected by a test
+        import cooler
+    except ImportError:
+        cooler = None
+    if cooler is not None and getattr(cooler, "Cooler", None) is Cooler:   # stand-in injected by a test
         return PKCool(path)
-    return _RealCoolAdapter(uri)
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    if _is_hdf5(path):
+        from .h5mini import H5Unsupported
+        try:
+            return H5Cool(uri)
+        except H5Unsupported as e:
+            if cooler is None:
+                raise RuntimeError("%s: %s is outside the built-in HDF5 reader's subset and the `cooler` "
+                                   "package is not installed" % (uri, e)) from e
+            return _RealCoolAdapter(uri)
+    raise RuntimeError("%s is neither a .pkcool container nor an HDF5 (.cool) file" % uri)

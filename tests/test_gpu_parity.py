@@ -109,6 +109,32 @@ def test_bedpe_identical_to_reference(name, fused, tuning, tmp_path):
     assert open(out).read() == case.bedpe                                        # (v)
 
 
+@pytest.mark.parametrize("name,group", [("tiny", ""), ("tiny_raw", ""), ("genome", "resolutions/10000")])
+def test_bedpe_from_a_real_cool_file(name, group, tmp_path):
+    """SURVEY.md 8(f) row 1: the same CLI on an HDF5 cooler file (.cool / .mcool::group, read by
+    h5mini) writes the reference's bedpe; inter-chromosomal pixels in the file are ignored."""
+    from peakachu_b200 import score_chromosome, score_genome
+    from tests import h5write
+    case = Case(name)
+    cfg = case.cfg
+    nb = np.array([c.n for c in case.chroms])
+    off = np.concatenate([[0], np.cumsum(nb)])
+    trans = [(off[0] + 3, off[1] + 5, 7), (off[0] + nb[0] - 1, off[-1] - 1, 2)] if len(nb) > 1 else None
+    cool = os.path.join(str(tmp_path), name + (".mcool" if group else ".cool"))
+    h5write.write_cool(cool, case.chroms, cfg["res"], trans=trans, group=group, chunk=5000)
+    out = os.path.join(str(tmp_path), "gpu.bedpe")
+    ns = argparse.Namespace(path=cool + ("::/" + group if group else ""), model=case.pkl, output=out,
+                            resolution=cfg["res"], lower=cfg["lower"], upper=cfg["upper"],
+                            minimum_prob=cfg["min_prob"], clr_weight_name=cfg["weight"])
+    if cfg.get("genome"):
+        ns.chroms = ["#", "X"]
+        score_genome.main(ns)
+    else:
+        ns.chrom = case.chroms[0].name
+        score_chromosome.main(ns)
+    assert open(out).read() == case.bedpe
+
+
 def test_forest_npz_and_pkl_give_same_tables():
     from peakachu_b200.forest import load_model
     case = Case("tiny")

@@ -1,0 +1,155 @@
+"""Real `.cool` ingestion: the HDF5 subset reader and the cooler
+adapter, on CPU. The reference's entry is `cooler.Cooler(uri)` + `matrix(...).fetch(chrom)` +
+`bins().fetch(chrom)[weight]` (score_chromosome.py:33-44)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from peakachu_b200 import coolio, h5mini, synth
+from tests import h5write
+
+
+def _genome(seed=3):
+    return synth.make_genome({"chr1": 900, "chr2": 640, "chrX": 410}, seed=seed, depth=60.0)
+
+
+def _trans(chroms, rng, k=500):
+    nb = np.array([c.n for c in chroms])
+    off = np.concatenate([[0], np.cumsum(nb)])
+    out = []
+    for _ in range(k):
+        i = rng.integers(0, len(chroms) - 1)
+        j = rng.integers(i + 1, len(chroms))
+        out.append((off[i] + rng.integers(0, nb[i]), off[j] + rng.integers(0, nb[j]), rng.integers(1, 5)))
+    return np.unique(np.array(out, dtype=np.int64), axis=0)
+
+
+def test_reader_on_a_libhdf5_written_file():
+    """The one HDF5 file in the image that libhdf5 itself wrote (MATLAB 7.3, 512-byte user block,
+    symbol-table root group, version-1 object header, fixed-string attribute)."""
+    import scipy.io
+    hits = glob.glob(os.path.join(os.path.dirname(scipy.io.__file__), "matlab", "tests", "data", "testhdf5_7.4_GLNX86.mat"))
+    if not hits:
+        pytest.skip("scipy test data not installed")
+    with h5mini.File(hits[0]) as f:
+        assert f.root.keys() == ["testdouble"]
+        d = f["testdouble"]
+        assert d.shape == (9, 1) and d.dtype == np.dtype("<f8")
+        np.testing.assert_array_equal(d.read().ravel(), np.arange(9) * (np.pi / 4))     # scipy's test_mio: 0 .. 2 pi
+        assert d.attrs["MATLAB_class"] == b"double"
+
+
+@pytest.mark.parametrize("userblock,group,chunk", [(0, "", 4096), (512, "resolutions/10000", 1000), (0, "", 37)])
+def test_cool_round_trip(tmp_path, userblock, group, chunk):
+    chroms = _genome()
+    rng = np.random.default_rng(0)
+    path = str(tmp_path / "t.cool")
+    ref = h5write.write_cool(path, chroms, 10000, trans=_trans(chroms, rng), group=group, chunk=chunk,
+                             userblock=userblock, extra_bins={"KR": np.arange(sum(c.n for c in chroms), dtype=np.float64)})
+    uri = path + ("::/" + group if group else "")
+    lib = coolio.open_map(uri)
+    assert isinstance(lib, coolio.H5Cool)
+    assert lib.chromnames == [c.name for c in chroms]
+    assert lib.binsize == 10000
+    off = 0
+    for c in chroms:
+        assert lib.nbins(c.name) == c.n
+        b1, b2, cnt = lib.upper_pixels(c.name)
+        order = np.lexsort((c.bin2, c.bin1))
+        np.testing.assert_array_equal(b1, c.bin1[order])
+        np.testing.assert_array_equal(b2, c.bin2[order])
+        np.testing.assert_array_equal(cnt, c.count[order])
+        assert b1.dtype == np.int32 and cnt.dtype == np.int32
+        rp, b2c, cntc = lib.upper_pixels_csr(c.name)
+        assert rp.dtype == np.int64 and rp.size == c.n + 1 and rp[0] == 0 and rp[-1] == b2c.size
+        np.testing.assert_array_equal(np.repeat(np.arange(c.n), np.diff(rp)), b1)
+        narrow = lib.upper_pixels_csr16(c.name)
+        assert narrow is not None
+        np.testing.assert_array_equal(narrow[1].astype(np.int64) + b1, b2)
+        np.testing.assert_array_equal(narrow[2], cnt)
+        w = lib.weights(c.name, "weight")
+        np.testing.assert_array_equal(w, c.weights)           # NaN positions included
+        np.testing.assert_array_equal(lib.weights(c.name, "KR"), np.arange(off, off + c.n, dtype=np.float64))
+        off += c.n
+    with pytest.raises(KeyError):
+        lib.weights("chr1", "VC")
+    with pytest.raises(KeyError):
+        lib.upper_pixels("chr9")
+    lib.close()
+    # the raw columns, chunk by chunk and in partial reads
+    with h5mini.File(path) as f:
+        g = f[group] if group else f.root
+        assert sorted(g.keys()) == ["bins", "chroms", "indexes", "pixels"]
+        assert g.attrs["nnz"] == ref["bin1"].size and g.attrs["format"] == b"HDF5::Cooler"
+        d = g["pixels/bin1_id"]
+        np.testing.assert_array_equal(d.read(), ref["bin1"])
+        for lo, hi in [(0, 1), (chunk - 1, chunk + 1), (5, 3 * chunk + 7), (ref["bin1"].size - 3, ref["bin1"].size + 10)]:
+            np.testing.assert_array_equal(d.read(lo, hi), ref["bin1"][lo:hi])
+            np.testing.assert_array_equal(d[lo:hi], ref["bin1"][lo:hi])
+        np.testing.assert_array_equal(g["pixels/count"].read(), ref["count"])     # fletcher32 + shuffle + deflate
+        np.testing.assert_array_equal(g["bins/weight"].read(), ref["weights"])   # one chunk with deflate masked out
+        assert g["bins/weight"].attrs["ignore_diags"] == 2
+        np.testing.assert_array_equal(g["indexes/chrom_offset"].read(), ref["chrom_offset"])  # contiguous
+        np.testing.assert_array_equal(g["bins/chrom"].read(), np.repeat(np.arange(3), [c.n for c in chroms]))  # enum
+
+
+def test_same_pixels_as_the_pkcool_container(tmp_path):
+    """A .cool and a .pkcool of the same map hand the scoring path identical columns."""
+    chroms = _genome(seed=5)
+    p1, p2 = str(tmp_path / "a.cool"), str(tmp_path / "a.pkcool")
+    h5write.write_cool(p1, chroms, 10000)
+    coolio.PKCool.write(p2, chroms, 10000)
+    a, b = coolio.open_map(p1), coolio.open_map(p2)
+    assert type(a) is coolio.H5Cool and type(b) is coolio.PKCool
+    for c in chroms:
+        for fa, fb in [(a.upper_pixels, b.upper_pixels), (a.upper_pixels_csr, b.upper_pixels_csr), (a.upper_pixels_csr16, b.upper_pixels_csr16)]:
+            for x, y in zip(fa(c.name), fb(c.name)):
+                np.testing.assert_array_equal(x, y)
+                assert x.dtype == y.dtype
+        np.testing.assert_array_equal(a.weights(c.name, "weight"), b.weights(c.name, "weight"))
+
+
+def test_layout_and_type_variants(tmp_path):
+    """Compact and contiguous layouts, big-endian and narrow integer columns, float32, empty datasets,
+    groups wider than one symbol-table node, multi-level chunk B-trees."""
+    W = h5write.Writer()
+    rng = np.random.default_rng(1)
+    big = rng.integers(-2**40, 2**40, 70000)
+    kids = {
+        "compact": W.dataset(np.arange(7, dtype=np.int16), compact=True),
+        "be": W.dataset(np.arange(11, dtype=">i4")),
+        "f4": W.dataset(np.linspace(0, 1, 33, dtype=np.float32), chunk=8, gzip=1),
+        "u1": W.dataset(np.arange(200, dtype=np.uint8), chunk=64, shuffle=True),
+        "empty": W.dataset(np.zeros(0, dtype=np.int64), chunk=16, gzip=6),
+        "deep": W.dataset(big, chunk=100, gzip=1, shuffle=True),          # 700 chunks: three B-tree levels at K=32... two here
+    }
+    for i in range(20):                                                    # > 8 links: several SNODs
+        kids["col%02d" % i] = W.dataset(np.full(3, i, dtype=np.int32))
+    root = W.group(kids, attrs={"k": np.float64(2.5)})
+    path = str(tmp_path / "v.h5")
+    W.finish(root, path)
+    with h5mini.File(path) as f:
+        assert len(f.root.keys()) == 26 and f.root.attrs["k"] == 2.5
+        np.testing.assert_array_equal(f["compact"].read(), np.arange(7))
+        assert f["be"].read().dtype == np.dtype("=i4")
+        np.testing.assert_array_equal(f["be"].read(), np.arange(11))
+        np.testing.assert_array_equal(f["f4"].read(), np.linspace(0, 1, 33, dtype=np.float32))
+        np.testing.assert_array_equal(f["u1"][10:150], np.arange(10, 150))
+        assert f["empty"].read().size == 0
+        np.testing.assert_array_equal(f["deep"].read(), big)
+        np.testing.assert_array_equal(f["deep"].read(12345, 54321), big[12345:54321])
+        for i in range(20):
+            np.testing.assert_array_equal(f["col%02d" % i].read(), np.full(3, i))
+        with pytest.raises(KeyError):
+            f["nope"]
+
+
+def test_not_hdf5(tmp_path):
+    p = tmp_path / "x.cool"
+    p.write_bytes(b"not an hdf5 file" * 100)
+    with pytest.raises(RuntimeError):
+        coolio.open_map(str(p))
+    with pytest.raises(FileNotFoundError):
+        coolio.open_map(str(tmp_path / "missing.cool"))
