@@ -22,6 +22,19 @@ void pk_set_error(const char* fmt, ...);
         }                                                                                  \
     } while (0)
 
+// Opt a kernel into `smem` bytes of dynamic shared memory. The attribute belongs to the (kernel,
+// device) pair, so the high-water mark is kept per device: a process may hold handles on several GPUs.
+#define PK_MAX_DEVICES 64
+#define PK_OPT_IN_SMEM(kernel, smem, device)                                               \
+    do {                                                                                   \
+        static size_t hw__[PK_MAX_DEVICES] = {0};                                          \
+        const int d__ = ((device) >= 0 && (device) < PK_MAX_DEVICES) ? (device) : 0;       \
+        if ((size_t)(smem) > 48 * 1024 && (size_t)(smem) > hw__[d__]) {                    \
+            PK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
+            hw__[d__] = (size_t)(smem);                                                    \
+        }                                                                                  \
+    } while (0)
+
 #define PK_CHECK(call)             \
     do {                           \
         int r__ = (call);          \

@@ -746,11 +746,7 @@ static int launch_fused_t(FusedParams prm, pk_forest* f, int ND, int sm_count, c
     PK_CHECK(pk_forest_groups(f, TBN, Cfg::CHUNK, &prm.groups, &prm.n_groups));
     const size_t smem = Cfg::total(ND, prm.n_trees);
     if (OCC * (smem + 1024) > 228 * 1024) { pk_set_error("fused kernel: %zu bytes of shared memory needed (x%d per SM)", smem, OCC); return PK_EUNSUPPORTED; }
-    static size_t attr_set = 0;      // largest dynamic size opted into so far
-    if (smem > attr_set) {
-        PK_CUDA(cudaFuncSetAttribute(k_score_fused<W, P, TPP, TBN, CH, OCC, NTH, NGR, XSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
-    }
+    PK_OPT_IN_SMEM((k_score_fused<W, P, TPP, TBN, CH, OCC, NTH, NGR, XSTAGE>), smem, f->device);
     unsigned grid = (unsigned)(sm_count * OCC);        // persistent: CTAs without work exit at once
     k_score_fused<W, P, TPP, TBN, CH, OCC, NTH, NGR, XSTAGE><<<grid, NTH, smem, stream>>>(prm);
     PK_CUDA(cudaGetLastError());

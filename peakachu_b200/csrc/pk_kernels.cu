@@ -262,11 +262,7 @@ int pk_launch_scatter(pk_chrom* c, const int32_t* b1, const int32_t* b2, const i
 int pk_launch_features(pk_chrom* c, double* d_fea64) {
     if (c->n_cand == 0) return PK_OK;
     size_t smem = (size_t)PK_FEAT_WARPS * 2 * c->F * sizeof(double);
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
-        PK_CUDA(cudaFuncSetAttribute(k_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    PK_OPT_IN_SMEM(k_features, smem, c->device);
     long long want = (c->n_cand + PK_FEAT_WARPS - 1) / PK_FEAT_WARPS;
     unsigned grid = (unsigned)std::min<long long>(want, 148LL * 16);
     k_features<<<grid, PK_FEAT_WARPS * 32, smem, c->stream>>>(c->d_band, c->d_w, c->d_exp, c->n, c->pitch, c->balanced, c->w,

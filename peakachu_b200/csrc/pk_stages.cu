@@ -607,11 +607,7 @@ static int launch_band_csr_t(pk_chrom* c, const long long* rowptr, const void* b
             if ((c->n + r - 1) / r <= slots(r)) { R = r; break; }
     const size_t smem = tile_bytes(R);
     if (smem > 200 * 1024) { pk_set_error("band build: %d diagonals do not fit a shared-memory tile", c->ND); return PK_EUNSUPPORTED; }
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) {
-        PK_CUDA(cudaFuncSetAttribute(k_band_csr<TY, TC, DELTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
-    }
+    PK_OPT_IN_SMEM((k_band_csr<TY, TC, DELTA>), smem, c->device);
     const unsigned grid = (unsigned)((c->n + R - 1) / R);
     k_band_csr<TY, TC, DELTA><<<grid, 256, smem, c->stream>>>(rowptr, (const TY*)b2, (const TC*)cnt, c->d_w, c->n, c->ND, c->pitch,
                                                               c->balanced, R, c->d_band, c->d_valid, c->d_flags);
@@ -693,11 +689,7 @@ int pk_launch_rowptr(pk_chrom* c, const int32_t* b1, const int32_t* b2, int64_t 
 template <int CAP>
 static int launch_diag_sums_t(pk_chrom* c, int n_words) {
     const size_t smem = sizeof(DiagSmem<CAP>) + ((size_t)n_words + 2) * 4;
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
-        PK_CUDA(cudaFuncSetAttribute(k_diag_sums<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
-    }
+    PK_OPT_IN_SMEM(k_diag_sums<CAP>, smem, c->device);
     k_diag_sums<CAP><<<c->ND, PK_DS_THREADS, smem, c->stream>>>(c->d_band, c->d_w, c->d_vbits, n_words, c->n, c->pitch,
                                                                 c->balanced, c->d_scratch, c->d_diag_sum, c->d_diag_cnt,
                                                                 c->d_flags);

@@ -42,3 +42,23 @@ def test_score_genome_two_ranks(name, chroms, tmp_path):
                       "-l", str(cfg["lower"]), "-u", str(cfg["upper"]), "--minimum-prob", str(cfg["min_prob"]),
                       "--clr-weight-name", cfg["weight"], "-C"] + chroms, tmp_path)
     assert open(out).read() == case.bedpe
+
+
+def test_two_devices_in_one_process(tmp_path):
+    """Handles on different GPUs in one process (the C ABI takes a device per handle): per-device
+    kernel attributes, allocator caches and streams; the second device gives the same bedpe."""
+    import argparse
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from peakachu_b200 import score_chromosome
+    case = Case("c1")
+    cfg = case.cfg
+    cool = case.write_cool(tmp_path)
+    for dev in (0, 1, 0):
+        out = os.path.join(str(tmp_path), "dev%d.bedpe" % dev)
+        score_chromosome.main(argparse.Namespace(path=cool, model=case.pkl, output=out, resolution=cfg["res"],
+                                                 lower=cfg["lower"], upper=cfg["upper"], minimum_prob=cfg["min_prob"],
+                                                 clr_weight_name=cfg["weight"], chrom=case.chroms[0].name, device=dev))
+        assert open(out).read() == case.bedpe
