@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpeakachu_b200.so")
+# PEAKACHU_B200_LIB points at another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("PEAKACHU_B200_LIB") or os.path.join(_HERE, "libpeakachu_b200.so")
 
 PK_MEM_HOST, PK_MEM_DEVICE = 0, 1
 PK_PIXELS_SORTED = 0x100

@@ -138,7 +138,8 @@ __device__ __forceinline__ void lds_node(uint32_t addr, uint2& nd) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nd.x), "=r"(nd.y) : "r"(addr));
 }
 // one level of one chain. `nd` is the node at shared address `addr`; an internal node
-// moves to a child and loads it, a leaf stays (its 8 bytes are the leaf value).
+// moves to a child and loads it, a leaf stays (its 8 bytes are the leaf value; `addr` keeps
+// moving by garbage after a leaf, but every later load is predicated off, so it is never used).
 // No branch: the loads are predicated on "internal", the step is selected. NaN features
 // are handled by the caller on a separate path (NaN compares false: always right).
 //   feature byte offset = y & 0xFFC, right-child byte offset = (y >> 9) & 0x1FFFF8
@@ -157,7 +158,6 @@ __device__ __forceinline__ void pk_step(uint32_t xrow_addr, uint32_t& addr, uint
         "shr.u32 s, %2, 9;\n"
         "and.b32 s, s, 0x1FFFF8;\n"
         "selp.u32 s, 8, s, le;\n"
-        "selp.u32 s, s, 0, q;\n"
         "add.u32 %0, %0, s;\n"
         "@q ld.shared.v2.u32 {%1, %2}, [%0];\n"
         "}"
