@@ -268,6 +268,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused", type=int, default=-1, help="pk_set_tuning('fused'): -1 auto, 0 off, 1, 2")
     ap.add_argument("--prune", type=int, default=1, help="pk_set_tuning('prune'): retire pixels that cannot exceed min_prob")
+    ap.add_argument("--child-features", type=int, default=-1, help="pk_set_tuning('child_features'): forest walk on the child-feature node encoding (-1 auto, 0 off, 1 on)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -290,6 +291,8 @@ def main():
     _lib.require_device()
     _lib.check(L.pk_set_tuning(b"fused", args.fused))
     _lib.check(L.pk_set_tuning(b"prune", args.prune))
+    if L.pk_set_tuning(b"child_features", args.child_features) != 0 and args.child_features != -1:
+        raise SystemExit("this build of the library has no child_features switch")     # older builds (tools/ab_libs.sh)
     args.warmup = max(args.warmup, 3)
 
     flat = FlatForest.load(os.path.join(ROOT, "bench_data", wl["forest"] + "_forest.npz"))

@@ -25,7 +25,7 @@ int pk_launch_features(pk_chrom* c, double* d_fea64);
 int pk_launch_forest(const pk_forest* f, const float* X, const uint8_t* keep, int64_t n_rows, int32_t* leaves,
                      double* proba, cudaStream_t stream);
 int pk_launch_emit(pk_chrom* c, double thre);
-int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms);
+int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms, int child_features);
 size_t pk_sort_temp_bytes(long long n);
 int pk_launch_sort_records_eager(pk_chrom* c, long long M);
 int pk_launch_depth(pk_chrom* c, int32_t min_dis, unsigned long long* d_total);
@@ -49,11 +49,13 @@ extern "C" int pk_selftest_divide(int device, int64_t n, uint64_t seed, int64_t*
 static const int64_t PK_EAGER_RECORDS = 1 << 17;   // records sorted behind the scoring pass; more fall back to a sort at fetch time
 static int g_tune_fused = -1;
 static int g_tune_prune = 1;
+static int g_tune_cf = -1;       // fused forest walk on the child-feature node encoding: -1 where measured faster (w = 7), 0 off, 1 on
 static int g_tune_reserve = 0;   // SMs the fused kernel leaves to the short stages of other chromosomes (pipelined use)     // retire pixels that cannot exceed min_prob (exact for every emitted record)
 
 extern "C" int pk_set_tuning(const char* key, int value) {
     if (key && !strcmp(key, "fused")) { g_tune_fused = value; return PK_OK; }
     if (key && !strcmp(key, "prune")) { g_tune_prune = value; return PK_OK; }
+    if (key && !strcmp(key, "child_features")) { g_tune_cf = value; return PK_OK; }
     if (key && !strcmp(key, "reserve_sms")) { g_tune_reserve = value < 0 ? 0 : value; return PK_OK; }
     pk_set_error("pk_set_tuning: unknown key %s", key ? key : "(null)");
     return PK_EINVAL;
@@ -274,6 +276,9 @@ extern "C" int pk_forest_create(int device, int32_t n_trees, int32_t n_features,
     std::vector<int32_t> orig((size_t)total);
     std::vector<uint32_t> roots((size_t)n_trees);
     std::vector<uint8_t> tdepth((size_t)n_trees);
+    std::vector<uint2> nodes_cf((size_t)total);
+    std::vector<uint8_t> rootfeat((size_t)n_trees);
+    bool cf_ok = n_features <= 256;
     int32_t max_depth = 0;
     std::vector<int32_t> newid, stack, depth;
     for (int32_t t = 0; t < n_trees; ++t) {
@@ -319,8 +324,15 @@ extern "C" int pk_forest_create(int device, int32_t n_trees, int32_t n_features,
                 uint32_t tb;
                 memcpy(&tb, &thr, 4);
                 nodes[(size_t)p] = make_uint2(tb, meta);
+                const uint32_t fl = left[o + l] != -1 ? (uint32_t)feature[o + l] : 0u;
+                const uint32_t fr = left[o + r] != -1 ? (uint32_t)feature[o + r] : 0u;
+                if (roff >= (1u << 14) || fl > 255u || fr > 255u) cf_ok = false;
+                nodes_cf[(size_t)p] = make_uint2(tb, (meta & 0xC0000000u) | ((roff & 0x3FFFu) << 16) | ((fr & 255u) << 8) | (fl & 255u));
             }
         }
+        for (int32_t v = 0; v < cnt; ++v)
+            if (left[o + v] == -1) nodes_cf[(size_t)(o + newid[v])] = nodes[(size_t)(o + newid[v])];
+        rootfeat[(size_t)t] = left[o] != -1 ? (uint8_t)(feature[o] & 255) : 0;
         roots[(size_t)t] = (uint32_t)o;
         if (this_depth > 255) { pk_set_error("pk_forest_create: tree %d deeper than 255", t); return PK_EUNSUPPORTED; }
         tdepth[(size_t)t] = (uint8_t)this_depth;
@@ -340,6 +352,16 @@ extern "C" int pk_forest_create(int device, int32_t n_trees, int32_t n_features,
     PK_CUDA(cudaMemcpy(f->d_orig, orig.data(), (size_t)total * sizeof(int32_t), cudaMemcpyHostToDevice));
     PK_CUDA(cudaMemset(f->d_nodes + total, 0, 4 * sizeof(uint2)));
     PK_CUDA(cudaMemcpy(f->d_depth, tdepth.data(), (size_t)n_trees, cudaMemcpyHostToDevice));
+    f->cf_ok = cf_ok;
+    if (cf_ok) {
+        if ((r = dev_alloc(&f->d_nodes_cf, (size_t)total + 4)) || (r = dev_alloc(&f->d_rootfeat, (size_t)n_trees))) {
+            pk_forest_destroy(f);
+            return r;
+        }
+        PK_CUDA(cudaMemcpy(f->d_nodes_cf, nodes_cf.data(), (size_t)total * sizeof(uint2), cudaMemcpyHostToDevice));
+        PK_CUDA(cudaMemset(f->d_nodes_cf + total, 0, 4 * sizeof(uint2)));
+        PK_CUDA(cudaMemcpy(f->d_rootfeat, rootfeat.data(), (size_t)n_trees, cudaMemcpyHostToDevice));
+    }
     *out = f;
     return PK_OK;
 }
@@ -375,6 +397,7 @@ extern "C" int pk_forest_destroy(pk_forest* f) {
     if (!f) return PK_OK;
     cudaSetDevice(f->device);
     dev_free(f->d_nodes); dev_free(f->d_root); dev_free(f->d_orig); dev_free(f->d_depth);
+    dev_free(f->d_nodes_cf); dev_free(f->d_rootfeat);
     for (auto& g : f->group_tables) dev_free(g.d);
     delete f;
     return PK_OK;
@@ -918,12 +941,12 @@ static int run_score(pk_chrom* c, pk_forest* f, double min_prob) {
             PK_CUDA(cudaEventRecord(c->ev_x, s));
             PK_CUDA(cudaStreamWaitEvent(c->score_stream, c->ev_x, 0));
             c->stream = c->score_stream;
-            r = pk_launch_fused(c, f, variant, thre, g_tune_reserve);
+            r = pk_launch_fused(c, f, variant, thre, g_tune_reserve, g_tune_cf);
             c->stream = s;
             PK_CUDA(cudaEventRecord(c->ev_x, c->score_stream));
             PK_CUDA(cudaStreamWaitEvent(s, c->ev_x, 0));
         } else {
-            r = pk_launch_fused(c, f, variant, thre, 0);
+            r = pk_launch_fused(c, f, variant, thre, 0, g_tune_cf);
         }
         if (r == PK_EUNSUPPORTED) fused = false;     // shapes the fused kernel has no room for: the two-kernel path below
         else PK_CHECK(r);

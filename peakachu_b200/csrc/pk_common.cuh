@@ -55,6 +55,15 @@ struct pk_forest {
     uint32_t* d_root = nullptr;      // [n_trees] packed index of the root
     int32_t* d_orig = nullptr;       // [n_nodes] tree-local sklearn node id (apply tap)
     uint8_t* d_depth = nullptr;      // [n_trees] depth of the deepest leaf
+    // Second encoding for the fused kernel ("child features"): an internal node names the features its two
+    // children test instead of its own, so a walk can fetch the next node and the next feature value at the
+    // same time (one shared-memory round trip per level instead of two).
+    //   internal .y = 1<<31 | missing_go_left<<30 | (right - self)<<16 [14 bits] | feature(right)<<8 | feature(left)
+    //   (a leaf child counts as feature 0); .x and leaves as above. Only when n_features <= 256 and every
+    //   right offset < 2^14 (cf_ok).
+    uint2* d_nodes_cf = nullptr;     // [n_nodes]
+    uint8_t* d_rootfeat = nullptr;   // [n_trees] feature tested by the root (0 for a single-leaf tree)
+    bool cf_ok = false;
     int32_t max_depth = 0;
     std::vector<int64_t> h_node_offset;   // host copy, for building group tables
     // tree groups staged into shared memory by the fused kernel, one table per

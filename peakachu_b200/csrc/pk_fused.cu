@@ -1,20 +1,23 @@
 // peakachu_b200: fused window-features + forest kernel (the dominant stage).
 //
-// One persistent CTA of P*TPP threads per SM, scoring P pixels per batch. It repeats:
-//   phase A  (scoreUtils.py:70-93)  fill a shared-memory feature buffer with up to P
-//            windows that pass the reference's filters. A warp works on two candidates
-//            at a time, one per 16-lane half. All 32 lanes gather the 2*(2W+1)^2 band
-//            cells in band-contiguous (window-diagonal) order -- the loads of the next
-//            pair are issued before the current pair is processed -- and balance them;
-//            then lane h of a half owns column h of its window for the vertical Gaussian
-//            pass and row h for the horizontal pass, so both passes run in registers
-//            with one shared-memory transpose in between.
-//   phase B  (scoreUtils.py:109)    TPP threads per pixel walk the forest. Trees are
-//            staged group by group into two shared-memory buffers with TMA bulk copies
-//            (cp.async.bulk + mbarrier), so node fetches are LDS instead of divergent
-//            global loads. Each thread walks four trees at once, branch-free; leaf
-//            values are added in estimator order in float64 (with TPP = 2 the second
-//            thread hands its four leaf values over through shared memory).
+// One persistent CTA of NTH threads per SM, scoring up to P pixels per batch. It repeats:
+//   phase A  (scoreUtils.py:70-93, utils.py:180-237)  fill the shared-memory feature buffer
+//            (float32 [P][F]) with windows that pass the reference's filters. The CTA's warps form
+//            NG independent groups (own staging buffer, own named barrier); a group takes PB
+//            candidates at a time and runs five steps over the take: A1 gather + balance (a warp
+//            owns window pairs, its 32 lanes share the 2*(2W+1)^2 band cells in band-contiguous
+//            order, every load of the take issued before the first use), A2 the reference's
+//            filters (one thread per window), A3 distance normalisation + vertical Gaussian pass
+//            (one thread per window column), A4 horizontal pass + row extrema (one thread per
+//            window row), A5 min-max scaling to float32 (a warp per window).
+//   phase B  (scoreUtils.py:109)    TPP threads per pixel walk the forest. Trees are staged
+//            group by group into two shared-memory buffers with TMA bulk copies
+//            (cp.async.bulk + mbarrier) -- the same memory that held the float64 windows during
+//            phase A -- so node fetches are LDS instead of divergent global loads. Each thread
+//            walks CH trees at once, branch-free; leaf values are added in estimator order in
+//            float64 (with TPP = 2 the second thread hands its leaf values over through shared
+//            memory). Pixels that can no longer exceed --minimum-prob stop walking trees and the
+//            survivors are re-packed onto the low threads.
 // Features never leave the SM: HBM traffic is the band cells of the windows, the
 // candidate list and one (keep, prob) pair per candidate.
 #include "pk_common.cuh"
@@ -28,6 +31,7 @@ struct FusedParams {
     const int32_t* cx; const int32_t* cd; const int32_t* crank;
     const long long* ncand_dev; long long cand_cap;   // candidate count lives on the device
     const uint2* nodes; const uint32_t* roots; const uint8_t* depth; const int4* groups;
+    const uint8_t* rootfeat;       // child-feature encoding only (template parameter CF)
     int n_groups; int n_trees;
     uint8_t* keep; double* prob; int32_t* batch_win; unsigned long long* counters;
     unsigned long long* next;      // global work counter (candidates handed out)
@@ -62,7 +66,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-template <int W, int P, int TPP, int TBN, int CH, int NTH, int NGR = 2, int XSTAGE = 0>
+template <int W, int P, int TPP, int TBN, int CH, int NTH, int NGR = 2, int XSTAGE = 0, int CF = 0>
 struct FusedCfg {
     static constexpr int S = 2 * W + 1, F = S * S, NT = NTH, NW = NT / 32;      // NTH >= P*TPP: extra warps only build features
     static_assert(NTH >= P * TPP && NTH % 32 == 0, "thread count");
@@ -86,7 +90,7 @@ struct FusedCfg {
     static size_t total(int ND, int n_trees) {
         return stage_bytes + fea_bytes + 2 * (size_t)((ND + 1) & ~1) * 8 + (size_t)NG * PB * 4 + 2 * (size_t)F * 8 +
                (size_t)P * 4 + 2 * (size_t)NG * PB * 4 + (size_t)n_trees * 4 + (size_t)((n_trees + 3) & ~3) +
-               2 * (size_t)NG * PB * 2 + (size_t)P + 64;
+               2 * (size_t)NG * PB * 2 + (size_t)P + 64 + (CF ? (size_t)((n_trees + 3) & ~3) : 0);
     }
 };
 
@@ -165,15 +169,44 @@ __device__ __forceinline__ void pk_step(uint32_t xrow_addr, uint32_t& addr, uint
         : "r"(xrow_addr));
 }
 
+// The same step on the child-feature encoding (pk_common.cuh): the thread holds the node AND the
+// value `xv` of the feature that node tests, so the compare needs no load; the node names the
+// features of both children, so the child's node and the child's feature value are fetched together:
+// one shared-memory round trip per level instead of two.
+//   left feature = y & 0xFF, right feature = (y >> 8) & 0xFF, right-child byte offset = (y >> 13) & 0x1FFF8
+__device__ __forceinline__ void pk_step_cf(uint32_t xrow_addr, uint32_t& addr, uint2& nd, uint32_t& xv) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q, le;\n"
+        ".reg .u32 t, s, sel;\n"
+        ".reg .f32 x, thr;\n"
+        "setp.lt.s32 q, %2, 0;\n"
+        "mov.b32 thr, %1;\n"
+        "mov.b32 x, %3;\n"
+        "setp.le.f32 le, x, thr;\n"
+        "selp.b32 sel, 0x4440, 0x4441, le;\n"
+        "prmt.b32 t, %2, 0, sel;\n"
+        "mad.lo.u32 t, t, 4, %4;\n"
+        "shr.u32 s, %2, 13;\n"
+        "and.b32 s, s, 0x1FFF8;\n"
+        "selp.u32 s, 8, s, le;\n"
+        "add.u32 %0, %0, s;\n"
+        "@q ld.shared.v2.u32 {%1, %2}, [%0];\n"
+        "@q ld.shared.u32 %3, [t];\n"
+        "}"
+        : "+r"(addr), "+r"(nd.x), "+r"(nd.y), "+r"(xv)
+        : "r"(xrow_addr));
+}
+
 #ifdef PK_FUSED_CLOCK
 #define PK_TICK(k) do { if (tid == 0) { const long long t_ = clock64(); clk[k] += t_ - t0; t0 = t_; } } while (0)
 #else
 #define PK_TICK(k) do { } while (0)
 #endif
 
-template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH, int NGR, int XSTAGE>
+template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH, int NGR, int XSTAGE, int CF>
 __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm) {
-    using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH, NGR, XSTAGE>;
+    using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH, NGR, XSTAGE, CF>;
     constexpr int S = Cfg::S, F = Cfg::F, NT = Cfg::NT, NW = Cfg::NW, NS = Cfg::NS, NM = Cfg::NM, CHUNK = Cfg::CHUNK;
     constexpr int PB = Cfg::PB, NG = Cfg::NG, NTG = Cfg::NTG, NWG = Cfg::NWG;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -198,12 +231,15 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
     uint16_t* s_ks = s_kl + NG * PB;                              // [NG][PB] their feature slots
     uint8_t* s_nan = reinterpret_cast<uint8_t*>(s_ks + NG * PB);  // [P]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_nan + P) + 15) & ~(uintptr_t)15);
+    uint8_t* s_rootfeat = reinterpret_cast<uint8_t*>(s_bar + 4);  // [n_trees] (CF only)
     // phase B: leaf hand-over, running sums, list of pixels still walking
     double* s_lv = s_hand;                                        // [2][CH][P] (TPP == 2)
     double* s_acc = s_hand + (TPP == 2 ? 2 * CH * P : 0);         // [P]
     uint16_t* s_list = reinterpret_cast<uint16_t*>(s_acc + P);    // [2][P]
     __shared__ int s_gnkt[NG], s_gtake[NG], s_gstop[NG], s_reserved, s_nkept, s_done, s_expbad, s_wc[32];
     __shared__ long long s_gstart[NG];
+    constexpr int GCACHE = 64;                   // tree-group table kept in shared memory when it fits
+    __shared__ int4 s_grp[GCACHE];
 
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const int half = lane >> 4, h = lane & 15;
@@ -225,6 +261,10 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
         if (!pk_div_safe(e)) s_expbad = 1;
     }
     for (int i = tid; i < prm.n_trees; i += NT) { s_root[i] = prm.roots[i]; s_depth[i] = prm.depth[i]; }
+    for (int i = tid; i < G && i < GCACHE; i += NT) s_grp[i] = prm.groups[i];
+    if (CF)
+        for (int i = tid; i < prm.n_trees; i += NT) s_rootfeat[i] = prm.rootfeat[i];
+    auto group_of = [&](int gi) -> int4 { return (G <= GCACHE) ? s_grp[gi] : prm.groups[gi]; };
     // Gather order of a window pair: cells by window diagonal (b - a), then along it -- contiguous
     // in the band. Entry idx of [0, 2F): .x = band offset of the cell relative to (d * pitch + x - W),
     // .y = byte offset in the pair's staging area | lane holding the row weight << 16 |
@@ -249,9 +289,12 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
     // Tree groups are streamed through the two buffers; positions count group loads since the
     // start of the kernel (uniform across threads). No load is in flight during phase A.
     uint32_t issued = 0, consumed = 0;
+    // Issued by the first lane of the last warp: that warp never accumulates (it belongs to the last
+    // sub-thread) and is idle once pixels retire, so refills stay off the CTA's critical path.
+    constexpr int ISSUER = NT - 32;
     auto issue = [&](uint32_t pos) {
-        if (tid == 0) {
-            const int4 g = prm.groups[pos % G];
+        if (tid == ISSUER) {
+            const int4 g = group_of((int)(pos % G));
             const uint32_t bytes = (uint32_t)(g.w < 0 ? -g.w : g.w) * 8u;
             uint64_t* bar = &s_bar[pos & 1];
             mbar_expect_tx(bar, bytes);
@@ -270,6 +313,8 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
     bool last = false;
 #ifdef PK_FUSED_CLOCK
     long long clk[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t0 = clock64();
+    long long clkq[6] = {0, 0, 0, 0, 0, 0};      // inside a forest chunk (thread 0): setup | walk | hand-over + mbarrier | CTA barrier | refill | accumulate
+    long long clkg[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};      // forest phase, per tree group (re-pack time lands in the next group)
 #endif
     for (;;) {
         // ================= phase A: features =================
@@ -600,7 +645,7 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
             const double die_below = prm.thre * T - 1e-9 * T;              // margin >> rounding of the sums
             const bool prune = prm.thre > 0.0;
             // the staging area is dead: start streaming the forest into it (two groups ahead)
-            if (tid == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (tid == ISSUER) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             {
                 const uint32_t target = consumed + (uint32_t)(G < 2 ? G : 2);
                 while (issued < target) { issue(issued); ++issued; }
@@ -611,9 +656,12 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
             // one warp polls the mbarrier, the others wait at the CTA barrier (no spinning warps)
             if (wib == 0) mbar_wait(&s_bar[consumed & 1], (consumed >> 1) & 1);
             __syncthreads();
+#ifdef PK_FUSED_CLOCK
+            long long tg0 = clock64();
+#endif
             for (int gi = 0; gi < G; ++gi) {
                 const uint32_t pos = consumed;
-                const int4 grp = prm.groups[gi];
+                const int4 grp = group_of(gi);
                 const uint32_t gbase = (uint32_t)grp.z;
                 const bool fits = grp.w > 0;                   // every tree of the group is fully staged
                 const uint32_t staged = (uint32_t)(fits ? grp.w : -grp.w);
@@ -621,6 +669,12 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                 const uint32_t buf_addr = smem_u32(buf);
                 const int t_end = grp.x + grp.y;
                 for (int tc = grp.x; tc < t_end; tc += CHUNK) {
+#ifdef PK_FUSED_CLOCK
+                    long long tq0 = clock64();
+#define PK_TICKQ(k) do { if (tid == 0) { const long long t_ = clock64(); clkq[k] += t_ - tq0; tq0 = t_; } } while (0)
+#else
+#define PK_TICKQ(k) do { } while (0)
+#endif
                     const int t = tc + CH * sub;               // this thread's CH trees
                     const bool mine = tid < P * TPP && slot < na;
                     const int pix = mine ? s_list[cur * P + slot] : 0;
@@ -636,18 +690,27 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                             // chains past the end of the group re-walk tree t and are dropped
                             uint32_t addr[CH];
                             uint2 nd[CH];
+                            uint32_t xv[CH];                 // CF: value of the feature the current node tests
                             int maxd = 0;
 #pragma unroll
                             for (int k = 0; k < CH; ++k) {
                                 const int tk = ex[k] ? t + k : t;
                                 addr[k] = buf_addr + (s_root[tk] - gbase) * 8u;
                                 maxd = max(maxd, (int)s_depth[tk]);
+                                xv[k] = CF ? xrow_addr + 4u * s_rootfeat[tk] : 0u;
                             }
 #pragma unroll
-                            for (int k = 0; k < CH; ++k) lds_node(addr[k], nd[k]);
+                            for (int k = 0; k < CH; ++k) {
+                                lds_node(addr[k], nd[k]);
+                                if (CF) xv[k] = lds_u32(xv[k]);
+                            }
+                            PK_TICKQ(0);
                             for (int lvl = 0; lvl < maxd; ++lvl) {
 #pragma unroll
-                                for (int k = 0; k < CH; ++k) pk_step(xrow_addr, addr[k], nd[k]);
+                                for (int k = 0; k < CH; ++k) {
+                                    if (CF) pk_step_cf(xrow_addr, addr[k], nd[k], xv[k]);
+                                    else pk_step(xrow_addr, addr[k], nd[k]);
+                                }
                             }
 #pragma unroll
                             for (int k = 0; k < CH; ++k) lv[k] = __hiloint2double((int)nd[k].y, (int)nd[k].x);
@@ -659,10 +722,16 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                                 if (!ex[k]) continue;
                                 uint32_t p = s_root[t + k] - gbase;
                                 uint2 nd = p < staged ? buf[p] : __ldg(prm.nodes + gbase + p);
+                                uint32_t ft = CF ? s_rootfeat[t + k] : 0u;        // CF: feature of the current node
                                 while (PK_NODE_INTERNAL(nd.y)) {
-                                    const float xv = xrow[PK_NODE_FEAT(nd.y)];
+                                    const float xv = xrow[CF ? ft : PK_NODE_FEAT(nd.y)];
                                     const bool left = isnan(xv) ? (PK_NODE_MGL(nd.y) != 0u) : (xv <= __uint_as_float(nd.x));
-                                    p += left ? 1u : PK_NODE_ROFF(nd.y);
+                                    if (CF) {
+                                        ft = left ? (nd.y & 0xFFu) : ((nd.y >> 8) & 0xFFu);
+                                        p += left ? 1u : ((nd.y >> 16) & 0x3FFFu);
+                                    } else {
+                                        p += left ? 1u : PK_NODE_ROFF(nd.y);
+                                    }
                                     nd = p < staged ? buf[p] : __ldg(prm.nodes + gbase + p);
                                 }
                                 lv[k] = __hiloint2double((int)nd.y, (int)nd.x);
@@ -671,6 +740,7 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                     }
                     // After the last chunk of a group the buffer is handed back: one barrier covers
                     // "everyone is done with it", "the next group has landed" and the leaf hand-over.
+                    PK_TICKQ(1);
                     const bool rotate = tc + CHUNK >= t_end;
                     double* lvb = s_lv + (size_t)lvpar * CH * P;
                     if (TPP == 2 && sub == 1 && mine) {
@@ -678,13 +748,16 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                         for (int k = 0; k < CH; ++k) lvb[k * P + slot] = lv[k];
                     }
                     if (rotate && wib == 0 && consumed + 1 < issued) mbar_wait(&s_bar[(consumed + 1) & 1], ((consumed + 1) >> 1) & 1);
+                    PK_TICKQ(2);
                     if (TPP == 2 || rotate) __syncthreads();
+                    PK_TICKQ(3);
                     if (rotate) {
                         ++consumed;
                         // refill the freed buffer with the group two positions ahead -- unless that group
                         // belongs to the next batch, whose windows are staged here first
                         if (gi + 2 < G) { issue(issued); ++issued; }
                     }
+                    PK_TICKQ(4);
                     // ordered accumulation: trees tc .. tc+CHUNK-1 in estimator order
                     if (mine && sub == 0) {
                         double acc = s_acc[pix];
@@ -699,7 +772,11 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                         s_acc[pix] = acc;
                     }
                     lvpar ^= 1;
+                    PK_TICKQ(5);
                 }
+#ifdef PK_FUSED_CLOCK
+                if (tid == 0 && gi < 16) { const long long t_ = clock64(); clkg[gi] += t_ - tg0; tg0 = t_; }
+#endif
                 // re-pack the pixels that can still exceed min_prob (possible once done > (1 - thre) T)
                 if (prune && gi + 1 < G && (double)t_end > T - prm.thre * T && t_end - last_pack >= 12) {
                     last_pack = t_end;
@@ -733,6 +810,9 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
 #ifdef PK_FUSED_CLOCK
     if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) {
         printf("cta %d A1 detail: coords %lld issue %lld process %lld\n", blockIdx.x, clk[8], clk[9], clk[10]);
+        printf("cta %d forest cycles per tree group: %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", blockIdx.x, clkg[0], clkg[1],
+               clkg[2], clkg[3], clkg[4], clkg[5], clkg[6], clkg[7], clkg[8], clkg[9], clkg[10], clkg[11], clkg[12], clkg[13], clkg[14], clkg[15]);
+        printf("cta %d forest chunk (thread 0): setup %lld walk %lld handover+mbar %lld barrier %lld refill %lld accumulate %lld\n", blockIdx.x, clkq[0], clkq[1], clkq[2], clkq[3], clkq[4], clkq[5]);
         printf("cta %d cycles: grab %lld A1 %lld A2 %lld A3 %lld A4 %lld A5a %lld A5b %lld B %lld\n", blockIdx.x, clk[0], clk[1], clk[2],
                clk[3], clk[4], clk[7], clk[5], clk[6]);
     }
@@ -740,27 +820,32 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
     // every issued group has been waited for (issued == consumed after a batch): nothing to drain
 }
 
-template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH = P * TPP, int NGR = 2, int XSTAGE = 0>
+template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH = P * TPP, int NGR = 2, int XSTAGE = 0, int CF = 0>
 static int launch_fused_t(FusedParams prm, pk_forest* f, int ND, int sm_count, cudaStream_t stream) {
-    using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH, NGR, XSTAGE>;
+    using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH, NGR, XSTAGE, CF>;
+    if (CF) { prm.nodes = f->d_nodes_cf; prm.rootfeat = f->d_rootfeat; }
     PK_CHECK(pk_forest_groups(f, TBN, Cfg::CHUNK, &prm.groups, &prm.n_groups));
     const size_t smem = Cfg::total(ND, prm.n_trees);
     if (OCC * (smem + 1024) > 228 * 1024) { pk_set_error("fused kernel: %zu bytes of shared memory needed (x%d per SM)", smem, OCC); return PK_EUNSUPPORTED; }
-    PK_OPT_IN_SMEM((k_score_fused<W, P, TPP, TBN, CH, OCC, NTH, NGR, XSTAGE>), smem, f->device);
+    PK_OPT_IN_SMEM((k_score_fused<W, P, TPP, TBN, CH, OCC, NTH, NGR, XSTAGE, CF>), smem, f->device);
     unsigned grid = (unsigned)(sm_count * OCC);        // persistent: CTAs without work exit at once
-    k_score_fused<W, P, TPP, TBN, CH, OCC, NTH, NGR, XSTAGE><<<grid, NTH, smem, stream>>>(prm);
+    k_score_fused<W, P, TPP, TBN, CH, OCC, NTH, NGR, XSTAGE, CF><<<grid, NTH, smem, stream>>>(prm);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
 
-int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms) {
+int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms, int child_features) {
     FusedParams prm;
     prm.band = c->d_band; prm.w = c->d_w; prm.expv = c->d_exp;
     prm.n = c->n; prm.pitch = c->pitch; prm.balanced = c->balanced; prm.ND = c->ND;
     prm.cx = c->d_cx; prm.cd = c->d_cd; prm.crank = c->d_crank;
     prm.ncand_dev = c->d_ncand; prm.cand_cap = c->cand_cap;
     prm.nodes = f->d_nodes; prm.roots = f->d_root; prm.depth = f->d_depth; prm.groups = nullptr;
-    prm.n_groups = 0; prm.n_trees = f->n_trees;
+    prm.n_groups = 0; prm.n_trees = f->n_trees; prm.rootfeat = nullptr;
+    // Child-feature encoding (default variants only): one shared-memory round trip per level instead of two,
+    // one instruction more per level. Measured (profiles/r1_summary.md): -6 % on the w = 7 kernel (two chains
+    // per thread, latency-bound), +3 % on the w = 5 kernel (four chains per thread, closer to issue-bound).
+    const bool cf = f->cf_ok && (child_features < 0 ? c->w == 7 : child_features != 0);
     prm.keep = c->d_keep; prm.prob = c->d_prob; prm.batch_win = c->d_batch_win; prm.counters = c->d_counters;
     prm.next = c->d_counters + 2;
     prm.flags = c->d_flags;
@@ -778,14 +863,16 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int res
         switch (variant) {
         case 1: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 2>(prm, f, c->ND, sm, st);
         case 2: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 1>(prm, f, c->ND, sm, st);
-        default: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4>(prm, f, c->ND, sm, st);
+        default: return cf ? launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4, 0, 1>(prm, f, c->ND, sm, st)
+                           : launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4>(prm, f, c->ND, sm, st);
         }
     }
     if (c->w == 7) {
         switch (variant) {
         case 1: return launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 2, 32768>(prm, f, c->ND, sm, st);
         case 2: return launch_fused_t<7, 128, 2, 3200, 2, 1, 512, 2, 32768>(prm, f, c->ND, sm, st);
-        default: return launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 1, 32768>(prm, f, c->ND, sm, st);
+        default: return cf ? launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 1, 32768, 1>(prm, f, c->ND, sm, st)
+                           : launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 1, 32768>(prm, f, c->ND, sm, st);
         }
     }
     return PK_EUNSUPPORTED;

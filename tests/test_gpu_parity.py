@@ -89,6 +89,35 @@ def test_all_window_probabilities_bit_exact(name, fused, tuning):
         X.close()
 
 
+@pytest.mark.parametrize("cf", [0, 1])
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_both_forest_encodings_are_exact(name, cf):
+    """The fused kernel walks the forest on either node encoding (own feature per node, or the
+    children's features per node: pk_set_tuning("child_features")); both give the reference's
+    probabilities bit for bit, with and without pruning."""
+    from peakachu_b200 import _lib
+    L = _lib.lib()
+    case = Case(name)
+    try:
+        _lib.check(L.pk_set_tuning(b"child_features", cf))
+        for thre in (-1.0, case.cfg["min_prob"]):
+            for ch in case.chroms:
+                k = ch.name + "/"
+                X = _gpu_chromosome(case, ch)
+                x, y, p, v = X.score_records(thre)
+                clist, proba = case.z[k + "clist"], case.z[k + "proba"]
+                order = np.lexsort((clist[:, 1], clist[:, 0]))
+                if thre < 0:
+                    assert np.array_equal(x, clist[order, 0]) and np.array_equal(y, clist[order, 1])
+                    assert np.array_equal(p, proba[order])
+                else:               # a subset of the windows (the 100,000-candidate batch rule may drop more)
+                    ref = {(int(a), int(b)): float(c) for a, b, c in zip(clist[:, 0], clist[:, 1], proba)}
+                    assert all(ref[(int(a), int(b))] == float(c) and c > thre for a, b, c in zip(x, y, p))
+                X.close()
+    finally:
+        _lib.check(L.pk_set_tuning(b"child_features", -1))
+
+
 @pytest.mark.parametrize("fused", [0, 1, 2])
 @pytest.mark.parametrize("name", ALL_CASES)
 def test_bedpe_identical_to_reference(name, fused, tuning, tmp_path):
@@ -372,6 +401,57 @@ def test_wide_band_takes_the_two_kernel_path(tmp_path):
     assert np.array_equal(x, r) and np.array_equal(y, c)
     assert np.array_equal(p, np.asarray(prob[r, c]).ravel()) and np.array_equal(v, np.asarray(val[r, c]).ravel())
     X.close()
+
+
+def _random_forest_tables(sizes, n_features, seed):
+    """FlatForest of randomly grown trees with the given node counts (odd)."""
+    from peakachu_b200.forest import FlatForest
+    rng = np.random.default_rng(seed)
+    feats, thrs, lefts, rights, p1s, offs = [], [], [], [], [], [0]
+    for n_nodes in sizes:
+        left = np.full(n_nodes, -1, np.int32)
+        right = np.full(n_nodes, -1, np.int32)
+        leaves, used = [0], 1
+        while used + 2 <= n_nodes:
+            v = leaves.pop(int(rng.integers(0, len(leaves))))
+            left[v], right[v] = used, used + 1
+            leaves += [used, used + 1]
+            used += 2
+        internal = left >= 0
+        feats.append(np.where(internal, rng.integers(0, n_features, n_nodes), -2).astype(np.int32))
+        thrs.append(np.where(internal, rng.random(n_nodes), -2.0))
+        lefts.append(left); rights.append(right)
+        p1s.append(rng.integers(0, 8, n_nodes) / 7.0)
+        offs.append(offs[-1] + n_nodes)
+    n = offs[-1]
+    return FlatForest(n_trees=len(sizes), n_features=n_features, node_offset=np.asarray(offs, np.int64),
+                      feature=np.concatenate(feats), threshold=np.concatenate(thrs), left=np.concatenate(lefts),
+                      right=np.concatenate(rights), missing_left=np.zeros(n, np.uint8), leaf_p1=np.concatenate(p1s))
+
+
+@pytest.mark.parametrize("sizes", [[301, 9001, 5, 1, 4301, 77, 1201, 3, 2001, 601, 15, 4223],     # trees larger than a staging buffer
+                                   [101, 60001, 33, 501]])                                         # right offsets beyond 2^14: own-feature encoding only
+def test_fused_walk_on_odd_forests(sizes, tuning):
+    """Trees that do not fit the fused kernel's staging buffer (their tail is read from L2), single-leaf
+    trees, groups of uneven size: the fused kernel on both node encodings equals the separate kernels."""
+    from peakachu_b200 import _lib
+    L = _lib.lib()
+    case = Case("tiny")
+    forest = _random_forest_tables(sizes, case.forest.n_features, seed=len(sizes))
+    got = {}
+    try:
+        for key, fused, cf in (("separate", 0, 1), ("own", -1, 0), ("child", -1, 1)):
+            tuning(fused)
+            _lib.check(L.pk_set_tuning(b"child_features", cf))
+            X = _gpu_chromosome(case, case.chroms[0], forest=forest)
+            got[key] = X.score_records(-1.0)
+            X.close()
+    finally:
+        _lib.check(L.pk_set_tuning(b"child_features", -1))
+    assert got["separate"][0].size > 500
+    for key in ("own", "child"):
+        for a, b in zip(got["separate"], got[key]):
+            assert np.array_equal(a, b), key
 
 
 def test_forest_nan_features_follow_missing_go_to_left():
