@@ -276,9 +276,9 @@ extern "C" int pk_forest_create(int device, int32_t n_trees, int32_t n_features,
     std::vector<int32_t> orig((size_t)total);
     std::vector<uint32_t> roots((size_t)n_trees);
     std::vector<uint8_t> tdepth((size_t)n_trees);
-    std::vector<uint2> nodes_cf((size_t)total);
+    std::vector<uint2> nodes_f0((size_t)total), nodes_f1((size_t)total);     // fused-kernel encodings (pk_common.cuh)
     std::vector<uint8_t> rootfeat((size_t)n_trees);
-    bool cf_ok = n_features <= 256;
+    bool fused_ok = true, cf_ok = n_features <= 256;
     int32_t max_depth = 0;
     std::vector<int32_t> newid, stack, depth;
     for (int32_t t = 0; t < n_trees; ++t) {
@@ -326,12 +326,14 @@ extern "C" int pk_forest_create(int device, int32_t n_trees, int32_t n_features,
                 nodes[(size_t)p] = make_uint2(tb, meta);
                 const uint32_t fl = left[o + l] != -1 ? (uint32_t)feature[o + l] : 0u;
                 const uint32_t fr = left[o + r] != -1 ? (uint32_t)feature[o + r] : 0u;
-                if (roff >= (1u << 14) || fl > 255u || fr > 255u) cf_ok = false;
-                nodes_cf[(size_t)p] = make_uint2(tb, (meta & 0xC0000000u) | ((roff & 0x3FFFu) << 16) | ((fr & 255u) << 8) | (fl & 255u));
+                if (roff >= 4096u) fused_ok = false;
+                const uint32_t top = 0x80000000u | ((roff & 4095u) << 19);
+                nodes_f0[(size_t)p] = make_uint2(tb, top | ((meta >> 30) & 1u) << 15 | ((uint32_t)ft << 2));
+                nodes_f1[(size_t)p] = make_uint2(tb, top | ((fr & 255u) << 8) | (fl & 255u));
             }
         }
         for (int32_t v = 0; v < cnt; ++v)
-            if (left[o + v] == -1) nodes_cf[(size_t)(o + newid[v])] = nodes[(size_t)(o + newid[v])];
+            if (left[o + v] == -1) nodes_f0[(size_t)(o + newid[v])] = nodes_f1[(size_t)(o + newid[v])] = nodes[(size_t)(o + newid[v])];
         rootfeat[(size_t)t] = left[o] != -1 ? (uint8_t)(feature[o] & 255) : 0;
         roots[(size_t)t] = (uint32_t)o;
         if (this_depth > 255) { pk_set_error("pk_forest_create: tree %d deeper than 255", t); return PK_EUNSUPPORTED; }
@@ -352,14 +354,18 @@ extern "C" int pk_forest_create(int device, int32_t n_trees, int32_t n_features,
     PK_CUDA(cudaMemcpy(f->d_orig, orig.data(), (size_t)total * sizeof(int32_t), cudaMemcpyHostToDevice));
     PK_CUDA(cudaMemset(f->d_nodes + total, 0, 4 * sizeof(uint2)));
     PK_CUDA(cudaMemcpy(f->d_depth, tdepth.data(), (size_t)n_trees, cudaMemcpyHostToDevice));
-    f->cf_ok = cf_ok;
-    if (cf_ok) {
-        if ((r = dev_alloc(&f->d_nodes_cf, (size_t)total + 4)) || (r = dev_alloc(&f->d_rootfeat, (size_t)n_trees))) {
+    f->fused_ok = fused_ok;
+    f->cf_ok = fused_ok && cf_ok;
+    if (fused_ok) {
+        if ((r = dev_alloc(&f->d_nodes_f0, (size_t)total + 4)) || (r = dev_alloc(&f->d_nodes_f1, (size_t)total + 4)) ||
+            (r = dev_alloc(&f->d_rootfeat, (size_t)n_trees))) {
             pk_forest_destroy(f);
             return r;
         }
-        PK_CUDA(cudaMemcpy(f->d_nodes_cf, nodes_cf.data(), (size_t)total * sizeof(uint2), cudaMemcpyHostToDevice));
-        PK_CUDA(cudaMemset(f->d_nodes_cf + total, 0, 4 * sizeof(uint2)));
+        PK_CUDA(cudaMemcpy(f->d_nodes_f0, nodes_f0.data(), (size_t)total * sizeof(uint2), cudaMemcpyHostToDevice));
+        PK_CUDA(cudaMemset(f->d_nodes_f0 + total, 0, 4 * sizeof(uint2)));
+        PK_CUDA(cudaMemcpy(f->d_nodes_f1, nodes_f1.data(), (size_t)total * sizeof(uint2), cudaMemcpyHostToDevice));
+        PK_CUDA(cudaMemset(f->d_nodes_f1 + total, 0, 4 * sizeof(uint2)));
         PK_CUDA(cudaMemcpy(f->d_rootfeat, rootfeat.data(), (size_t)n_trees, cudaMemcpyHostToDevice));
     }
     *out = f;
@@ -397,7 +403,7 @@ extern "C" int pk_forest_destroy(pk_forest* f) {
     if (!f) return PK_OK;
     cudaSetDevice(f->device);
     dev_free(f->d_nodes); dev_free(f->d_root); dev_free(f->d_orig); dev_free(f->d_depth);
-    dev_free(f->d_nodes_cf); dev_free(f->d_rootfeat);
+    dev_free(f->d_nodes_f0); dev_free(f->d_nodes_f1); dev_free(f->d_rootfeat);
     for (auto& g : f->group_tables) dev_free(g.d);
     delete f;
     return PK_OK;

@@ -55,15 +55,20 @@ struct pk_forest {
     uint32_t* d_root = nullptr;      // [n_trees] packed index of the root
     int32_t* d_orig = nullptr;       // [n_nodes] tree-local sklearn node id (apply tap)
     uint8_t* d_depth = nullptr;      // [n_trees] depth of the deepest leaf
-    // Second encoding for the fused kernel ("child features"): an internal node names the features its two
-    // children test instead of its own, so a walk can fetch the next node and the next feature value at the
-    // same time (one shared-memory round trip per level instead of two).
-    //   internal .y = 1<<31 | missing_go_left<<30 | (right - self)<<16 [14 bits] | feature(right)<<8 | feature(left)
-    //   (a leaf child counts as feature 0); .x and leaves as above. Only when n_features <= 256 and every
-    //   right offset < 2^14 (cf_ok).
-    uint2* d_nodes_cf = nullptr;     // [n_nodes]
+    // Node arrays of the fused kernel (same numbering, leaves and .x as d_nodes). The right-child byte
+    // offset sits in bits 16..30 under the "internal" bit, so `y >> 16` is that offset + 0x8000 and the
+    // walk's address update is one three-input add (addr + step - 0x8000). Needs every right offset
+    // < 4096 nodes (fused_ok); other forests take the separate feature / forest kernels.
+    //   own-feature:    .y = 1<<31 | (right - self)*8 << 16 | missing_go_left << 15 | feature*4
+    //   child-feature:  .y = 1<<31 | (right - self)*8 << 16 | feature(right) << 8 | feature(left)
+    //     An internal node names the features its two children test instead of its own (a leaf child
+    //     counts as feature 0), so a walk fetches the next node and the next feature value at the same
+    //     time: one shared-memory round trip per level instead of two. Needs n_features <= 256 (cf_ok);
+    //     missing_go_left is read from d_nodes on the (rare) NaN path.
+    uint2* d_nodes_f0 = nullptr;     // [n_nodes] own-feature
+    uint2* d_nodes_f1 = nullptr;     // [n_nodes] child-feature
     uint8_t* d_rootfeat = nullptr;   // [n_trees] feature tested by the root (0 for a single-leaf tree)
-    bool cf_ok = false;
+    bool fused_ok = false, cf_ok = false;
     int32_t max_depth = 0;
     std::vector<int64_t> h_node_offset;   // host copy, for building group tables
     // tree groups staged into shared memory by the fused kernel, one table per

@@ -32,6 +32,7 @@ struct FusedParams {
     const long long* ncand_dev; long long cand_cap;   // candidate count lives on the device
     const uint2* nodes; const uint32_t* roots; const uint8_t* depth; const int4* groups;
     const uint8_t* rootfeat;       // child-feature encoding only (template parameter CF)
+    const uint2* nodes_classic;    // pk_forest.d_nodes: missing_go_left of the child-feature encoding's NaN walk
     int n_groups; int n_trees;
     uint8_t* keep; double* prob; int32_t* batch_win; unsigned long long* counters;
     unsigned long long* next;      // global work counter (candidates handed out)
@@ -146,7 +147,7 @@ __device__ __forceinline__ void lds_node(uint32_t addr, uint2& nd) {
 // moving by garbage after a leaf, but every later load is predicated off, so it is never used).
 // No branch: the loads are predicated on "internal", the step is selected. NaN features
 // are handled by the caller on a separate path (NaN compares false: always right).
-//   feature byte offset = y & 0xFFC, right-child byte offset = (y >> 9) & 0x1FFFF8
+//   feature byte offset = y & 0xFFC, right-child byte offset = (y >> 16) - 0x8000 (pk_common.cuh)
 __device__ __forceinline__ void pk_step(uint32_t xrow_addr, uint32_t& addr, uint2& nd) {
     asm volatile(
         "{\n"
@@ -159,10 +160,10 @@ __device__ __forceinline__ void pk_step(uint32_t xrow_addr, uint32_t& addr, uint
         "@q ld.shared.f32 x, [t];\n"
         "mov.b32 thr, %1;\n"
         "setp.le.f32 le, x, thr;\n"
-        "shr.u32 s, %2, 9;\n"
-        "and.b32 s, s, 0x1FFFF8;\n"
-        "selp.u32 s, 8, s, le;\n"
-        "add.u32 %0, %0, s;\n"
+        "shr.u32 s, %2, 16;\n"
+        "selp.u32 s, 0x8008, s, le;\n"
+        "add.u32 s, s, %0;\n"
+        "add.u32 %0, s, 0xFFFF8000;\n"
         "@q ld.shared.v2.u32 {%1, %2}, [%0];\n"
         "}"
         : "+r"(addr), "+r"(nd.x), "+r"(nd.y)
@@ -173,7 +174,7 @@ __device__ __forceinline__ void pk_step(uint32_t xrow_addr, uint32_t& addr, uint
 // value `xv` of the feature that node tests, so the compare needs no load; the node names the
 // features of both children, so the child's node and the child's feature value are fetched together:
 // one shared-memory round trip per level instead of two.
-//   left feature = y & 0xFF, right feature = (y >> 8) & 0xFF, right-child byte offset = (y >> 13) & 0x1FFF8
+//   left feature = y & 0xFF, right feature = (y >> 8) & 0xFF, right-child byte offset = (y >> 16) - 0x8000
 __device__ __forceinline__ void pk_step_cf(uint32_t xrow_addr, uint32_t& addr, uint2& nd, uint32_t& xv) {
     asm volatile(
         "{\n"
@@ -187,10 +188,10 @@ __device__ __forceinline__ void pk_step_cf(uint32_t xrow_addr, uint32_t& addr, u
         "selp.b32 sel, 0x4440, 0x4441, le;\n"
         "prmt.b32 t, %2, 0, sel;\n"
         "mad.lo.u32 t, t, 4, %4;\n"
-        "shr.u32 s, %2, 13;\n"
-        "and.b32 s, s, 0x1FFF8;\n"
-        "selp.u32 s, 8, s, le;\n"
-        "add.u32 %0, %0, s;\n"
+        "shr.u32 s, %2, 16;\n"
+        "selp.u32 s, 0x8008, s, le;\n"
+        "add.u32 s, s, %0;\n"
+        "add.u32 %0, s, 0xFFFF8000;\n"
         "@q ld.shared.v2.u32 {%1, %2}, [%0];\n"
         "@q ld.shared.u32 %3, [t];\n"
         "}"
@@ -723,15 +724,12 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                                 uint32_t p = s_root[t + k] - gbase;
                                 uint2 nd = p < staged ? buf[p] : __ldg(prm.nodes + gbase + p);
                                 uint32_t ft = CF ? s_rootfeat[t + k] : 0u;        // CF: feature of the current node
-                                while (PK_NODE_INTERNAL(nd.y)) {
-                                    const float xv = xrow[CF ? ft : PK_NODE_FEAT(nd.y)];
-                                    const bool left = isnan(xv) ? (PK_NODE_MGL(nd.y) != 0u) : (xv <= __uint_as_float(nd.x));
-                                    if (CF) {
-                                        ft = left ? (nd.y & 0xFFu) : ((nd.y >> 8) & 0xFFu);
-                                        p += left ? 1u : ((nd.y >> 16) & 0x3FFFu);
-                                    } else {
-                                        p += left ? 1u : PK_NODE_ROFF(nd.y);
-                                    }
+                                while ((int)nd.y < 0) {                            // fused-kernel encodings (pk_common.cuh)
+                                    const float xv = xrow[CF ? ft : ((nd.y & 0xFFCu) >> 2)];
+                                    bool left = xv <= __uint_as_float(nd.x);
+                                    if (isnan(xv)) left = CF ? (PK_NODE_MGL(__ldg(&prm.nodes_classic[gbase + p].y)) != 0u) : ((nd.y >> 15) & 1u) != 0u;
+                                    if (CF) ft = left ? (nd.y & 0xFFu) : ((nd.y >> 8) & 0xFFu);
+                                    p += left ? 1u : ((nd.y >> 19) & 4095u);
                                     nd = p < staged ? buf[p] : __ldg(prm.nodes + gbase + p);
                                 }
                                 lv[k] = __hiloint2double((int)nd.y, (int)nd.x);
@@ -823,7 +821,9 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
 template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH = P * TPP, int NGR = 2, int XSTAGE = 0, int CF = 0>
 static int launch_fused_t(FusedParams prm, pk_forest* f, int ND, int sm_count, cudaStream_t stream) {
     using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH, NGR, XSTAGE, CF>;
-    if (CF) { prm.nodes = f->d_nodes_cf; prm.rootfeat = f->d_rootfeat; }
+    prm.nodes = CF ? f->d_nodes_f1 : f->d_nodes_f0;
+    prm.rootfeat = f->d_rootfeat;
+    prm.nodes_classic = f->d_nodes;
     PK_CHECK(pk_forest_groups(f, TBN, Cfg::CHUNK, &prm.groups, &prm.n_groups));
     const size_t smem = Cfg::total(ND, prm.n_trees);
     if (OCC * (smem + 1024) > 228 * 1024) { pk_set_error("fused kernel: %zu bytes of shared memory needed (x%d per SM)", smem, OCC); return PK_EUNSUPPORTED; }
@@ -850,6 +850,10 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int res
     prm.next = c->d_counters + 2;
     prm.flags = c->d_flags;
     prm.thre = thre;
+    if (!f->fused_ok) {         // a right child 4096 or more nodes away: the fused kernel's node encodings cannot hold it
+        pk_set_error("fused kernel: a tree of this forest is too large for its node encoding");
+        return PK_EUNSUPPORTED;
+    }
     if ((long long)c->ND * c->pitch >= (1LL << 31)) {      // the gather indexes the band with 32-bit offsets
         pk_set_error("fused kernel: band of %d x %lld cells exceeds 2^31", c->ND, (long long)c->pitch);
         return PK_EUNSUPPORTED;

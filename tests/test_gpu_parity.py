@@ -429,8 +429,8 @@ def _random_forest_tables(sizes, n_features, seed):
                       right=np.concatenate(rights), missing_left=np.zeros(n, np.uint8), leaf_p1=np.concatenate(p1s))
 
 
-@pytest.mark.parametrize("sizes", [[301, 9001, 5, 1, 4301, 77, 1201, 3, 2001, 601, 15, 4223],     # trees larger than a staging buffer
-                                   [101, 60001, 33, 501]])                                         # right offsets beyond 2^14: own-feature encoding only
+@pytest.mark.parametrize("sizes", [[301, 4401, 5, 1, 4301, 77, 1201, 3, 2001, 601, 15, 4223],     # trees larger than a staging buffer
+                                   [101, 60001, 33, 501]])                                         # right offsets beyond the fused encodings: separate kernels
 def test_fused_walk_on_odd_forests(sizes, tuning):
     """Trees that do not fit the fused kernel's staging buffer (their tail is read from L2), single-leaf
     trees, groups of uneven size: the fused kernel on both node encodings equals the separate kernels."""
@@ -449,6 +449,47 @@ def test_fused_walk_on_odd_forests(sizes, tuning):
     finally:
         _lib.check(L.pk_set_tuning(b"child_features", -1))
     assert got["separate"][0].size > 500
+    for key in ("own", "child"):
+        for a, b in zip(got["separate"], got[key]):
+            assert np.array_equal(a, b), key
+
+
+def test_fused_walk_with_nan_windows():
+    """Constant windows scale to 0/0 = NaN features (utils.py:204-209) and sklearn routes those by
+    missing_go_to_left. Half of this raw-mode chromosome is a constant plateau (with the expected curve
+    set to 1 every window there is constant), the other half is noise, so warps mix NaN and ordinary
+    pixels; the fused kernel on both encodings must equal the separate kernels, whose forest walk is
+    pinned against sklearn on NaN rows (test_forest_nan_features_follow_missing_go_to_left)."""
+    from peakachu_b200 import _lib
+    from peakachu_b200.scoreUtils import Chromosome
+    L = _lib.lib()
+    case = Case("lowdepth")          # its forest was fitted with missing_go_to_left set on some nodes
+    n, w, lower, upper = 400, 5, 6, 60
+    rng = np.random.default_rng(4)
+    b1, b2 = np.nonzero(np.triu(np.ones((n, n), bool)) & ~np.triu(np.ones((n, n), bool), upper + 2 * w + 1))
+    cnt = np.where(b2 < n // 2, 3, rng.integers(1, 9, b1.size)).astype(np.int32)
+    got = {}
+    try:
+        for key, fused, cf in (("separate", 0, -1), ("own", -1, 0), ("child", -1, 1)):
+            _lib.check(L.pk_set_tuning(b"fused", fused))
+            _lib.check(L.pk_set_tuning(b"child_features", cf))
+            X = Chromosome.from_pixels(b1.astype(np.int32), b2.astype(np.int32), cnt, None, n, case.forest, lower=lower,
+                                       upper=upper, cname="chr1", res=10000, width=w)
+            el = X._exp_len
+            exp, bg = np.ones(el), np.full(el, 0.01)
+            _lib.check(L.pk_chrom_set_expected(X._h, exp.ctypes.data_as(_lib.c_f64p), bg.ctypes.data_as(_lib.c_f64p)))
+            _lib.check(L.pk_chrom_find_candidates(X._h, 0, n, None))
+            X._ncand = X._cand = None
+            got[key] = X.score_records(-1.0)
+            X.close()
+    finally:
+        _lib.check(L.pk_set_tuning(b"fused", -1))
+        _lib.check(L.pk_set_tuning(b"child_features", -1))
+    x, y, p, v = got["separate"]
+    # (at distance `upper` the window's far corner lies on the first diagonal the band trim drops, scoreUtils.py:31)
+    plateau = (y < n // 2 - w) & (y - x < upper)
+    assert plateau.sum() > 1000 and (~plateau).sum() > 1000
+    assert np.unique(p[plateau]).size == 1           # every constant window takes the all-NaN route
     for key in ("own", "child"):
         for a, b in zip(got["separate"], got[key]):
             assert np.array_equal(a, b), key
