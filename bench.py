@@ -483,8 +483,9 @@ def main():
                 "unit": "GB/s", "frac": bytes_alg / (dom_ms * 1e-3) / 1e9 / peak_gbs, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
                 "bytes_alg_per_launch": bytes_alg, "kernel_ms": dom_ms,
-                "note": "the dominant kernel is bound by instruction issue and shared-memory wavefronts, not HBM "
-                        "(DESIGN.md section 4); frac is algorithmic bytes of the chromosome over its duration",
+                "note": "the dominant kernel is bound by shared-memory load throughput and round-trip latency of the forest "
+                        "walk plus issue/FP64 in the feature phase, not HBM (DESIGN.md section 4); frac is algorithmic "
+                        "bytes of the chromosome over its duration",
                 "whole_step_frac": bytes_alg / (dev_ms / steps * 1e-3) / 1e9 / peak_gbs,
                 "serial_step_ms": serial_ms}
 
