@@ -196,26 +196,44 @@ def run_genome(args, wl, flat, rank, world, local):
         t.numpy()[...] = a
         return t
 
-    cols = {}
+    cols, narrow = {}, {}
     for k in need:
         ch = synth.make_chromosome(k, sizes[k], seed=5000 + queue.index(k), depth=wl["depth"], band=wl["band"])
         rp = np.searchsorted(ch.bin1, np.arange(ch.n + 1)).astype(np.int64)
         cols[k] = tuple(pinned(a) for a in (rp, ch.bin2, ch.count, ch.weights))
+        # narrow columns (bin2 - bin1 and count as uint16), what a .pkcool container / coolio.H5Cool hand over
+        # when every pixel is representable: half the bytes that cross the bus
+        if ch.count.size and int((ch.bin2 - ch.bin1).max()) <= 65535 and int(ch.count.max()) <= 65535:
+            narrow[k] = (pinned((ch.bin2 - ch.bin1).astype(np.uint16).view(np.uint8)),
+                         pinned(ch.count.astype(np.uint16).view(np.uint8)))
 
     class PinnedGenome:
         def nbins(self, key): return sizes[key]
         def weights(self, key, name): return cols[key][3].numpy()
         def upper_pixels_csr(self, key): return tuple(t.numpy() for t in cols[key][:3])
+        def upper_pixels_csr16(self, key):
+            if key not in narrow:
+                return None
+            d16, c16 = narrow[key]
+            return cols[key][0].numpy(), d16.numpy().view(np.uint16), c16.numpy().view(np.uint16)
+
+    phase_s = [0.0, 0.0, 0.0]          # score_units | gather | merge (this rank, all passes)
 
     def one_pass():
+        t_a = time.perf_counter()
         res = shard.score_units(PinnedGenome(), mine, flat, correct="weight", lower=wl["lower"], upper=wl["upper"],
                                 res=wl["res"], device=local, min_prob=0.5)
+        t_b = time.perf_counter()
         gathered = shard.gather_to_rank0(res, rank, world)
+        t_c = time.perf_counter()
+        n_out = 0
         if rank == 0:
             merged = {k: shard.merge_tiles(sorted([q for g in gathered for q in g.get(k, [])],
                                                   key=lambda q: q["row_begin"])) for k in queue}
-            return sum(int(m[0].size) for m in merged.values())
-        return 0
+            n_out = sum(int(m[0].size) for m in merged.values())
+        t_d = time.perf_counter()
+        phase_s[0] += t_b - t_a; phase_s[1] += t_c - t_b; phase_s[2] += t_d - t_c
+        return n_out
 
     def barrier():
         torch.cuda.synchronize()
@@ -225,12 +243,15 @@ def run_genome(args, wl, flat, rank, world, local):
     for _ in range(max(args.warmup, 1)):
         one_pass()
     barrier()
+    phase_s[:] = [0.0, 0.0, 0.0]
     t0 = time.perf_counter()
     nrec = 0
     for _ in range(args.steps):
         nrec = one_pass()
     barrier()
     dt = time.perf_counter() - t0
+    print("rank %d: ms per pass: score_units %.2f, gather %.2f, merge %.2f (%d units)" % (
+        rank, *(1e3 * v / args.steps for v in phase_s), len(mine)), file=sys.stderr)
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -246,7 +267,8 @@ def run_genome(args, wl, flat, rank, world, local):
                        "timed": "end to end: pinned host columns -> H2D -> kernels -> records D2H -> host gather on rank 0",
                        "units_per_rank": [len(u) for u in plan], "records_per_step": nrec},
             "e2e": {"value": px * args.steps / dt, "unit": "pixels/s",
-                    "h2d_bytes_per_step": int(sum(8 * cols[k][1].numel() + 16 * sizes[k] for k in need)),
+                    "h2d_bytes_per_step": int(sum((4 if k in narrow else 8) * cols[k][1].numel() + 16 * sizes[k] for k in need)),
+                    "columns": "bin1_offset int64 + (bin2 - bin1) uint16 + count uint16 + weights f64 where representable, else int32 columns",
                     "d2h_bytes_per_step": 28 * nrec},
         }))
     if world > 1:

@@ -71,12 +71,127 @@ def _host_group():
     return _GROUP
 
 
+# -- host-side gather ---------------------------------------------------------------
+# Records are numpy columns. Pickling them through gloo's gather_object costs milliseconds per pass
+# (serialise, TCP loopback, deserialise), as much as a rank's share of an hg19-sized genome takes to
+# score on eight GPUs. On one node (the deployment SURVEY.md 8(e) describes) the columns go through a
+# POSIX shared-memory segment per rank instead: each rank copies its arrays into its segment, a small
+# gather_object carries the layout, rank 0 copies the arrays out, a barrier releases the segments.
+_SHM = {"seg": None, "cap": 0, "same_host": None, "peers": {}}
+
+
+def _strip_arrays(obj, arrays):
+    """Replace every ndarray in a nest of dicts / lists / tuples by a placeholder."""
+    if isinstance(obj, np.ndarray):
+        arrays.append(np.ascontiguousarray(obj))
+        return ("__nd__", len(arrays) - 1)
+    if isinstance(obj, dict):
+        return {k: _strip_arrays(v, arrays) for k, v in obj.items()}
+    if isinstance(obj, list):
+        return [_strip_arrays(v, arrays) for v in obj]
+    return obj
+
+
+def _restore_arrays(obj, arrays):
+    if isinstance(obj, tuple) and len(obj) == 2 and obj[0] == "__nd__":
+        return arrays[obj[1]]
+    if isinstance(obj, dict):
+        return {k: _restore_arrays(v, arrays) for k, v in obj.items()}
+    if isinstance(obj, list):
+        return [_restore_arrays(v, arrays) for v in obj]
+    return obj
+
+
+def _release_shm():
+    seg = _SHM["seg"]
+    _SHM["seg"] = None
+    for peer in _SHM["peers"].values():
+        try:
+            peer.close()
+        except Exception:
+            pass
+    _SHM["peers"].clear()
+    if seg is not None:
+        try:
+            seg.close()
+            seg.unlink()
+        except Exception:
+            pass
+
+
+def _segment(nbytes):
+    from multiprocessing import shared_memory
+    if _SHM["seg"] is None or _SHM["cap"] < nbytes:
+        if _SHM["seg"] is not None:
+            _SHM["seg"].close()
+            _SHM["seg"].unlink()
+        else:
+            import atexit
+            atexit.register(_release_shm)
+        cap = max(1 << 20, int(nbytes * 1.5))
+        _SHM["seg"] = shared_memory.SharedMemory(create=True, size=cap)
+        _SHM["cap"] = cap
+    return _SHM["seg"]
+
+
+def _attach(name):
+    """Map another rank's segment (cached by name; the owner unlinks it)."""
+    from multiprocessing import resource_tracker, shared_memory
+    seg = _SHM["peers"].get(name)
+    if seg is None:
+        seg = shared_memory.SharedMemory(name=name)
+        try:        # Python < 3.13 registers attached segments too; the owner is responsible for this one
+            resource_tracker.unregister(seg._name, "shared_memory")
+        except Exception:
+            pass
+        _SHM["peers"][name] = seg
+    return seg
+
+
+def _gather_shm(obj, rank, world, group):
+    import torch.distributed as dist
+    arrays = []
+    meta = _strip_arrays(obj, arrays)
+    layout, off = [], 0
+    for a in arrays:
+        layout.append((a.dtype.str, a.shape, off))
+        off += (a.nbytes + 63) & ~63
+    name = None
+    if rank != 0:
+        seg = _segment(off)
+        name = seg.name
+        for a, (_, _, o) in zip(arrays, layout):
+            if a.nbytes:
+                np.frombuffer(seg.buf, dtype=np.uint8, count=a.nbytes, offset=o)[:] = a.reshape(-1).view(np.uint8)
+    out = [None] * world if rank == 0 else None
+    dist.gather_object((name, meta, layout), out, dst=0, group=group)
+    result = None
+    if rank == 0:
+        result = [obj]
+        for r in range(1, world):
+            rname, rmeta, rlayout = out[r]
+            seg = _attach(rname)
+            got = [np.frombuffer(seg.buf, dtype=np.dtype(dt), count=int(np.prod(shape, dtype=np.int64)), offset=o)
+                   .reshape(shape).copy() for dt, shape, o in rlayout]
+            result.append(_restore_arrays(rmeta, got))
+    dist.barrier(group=group)           # rank 0 has copied: the segments may be overwritten by the next pass
+    return result
+
+
 def gather_to_rank0(obj, rank, world):
-    """Host-side gather of python objects to rank 0 (gloo group)."""
+    """Host-side gather of the ranks' records to rank 0 (gloo group): numpy columns through shared
+    memory when every rank runs on the same host, else pickled through gather_object."""
     if world == 1:
         return [obj]
     import torch.distributed as dist
     group = _host_group()
+    if _SHM["same_host"] is None:
+        import socket
+        names = [None] * world
+        dist.all_gather_object(names, socket.gethostname(), group=group)
+        _SHM["same_host"] = len(set(names)) == 1 and os.environ.get("PEAKACHU_B200_GATHER", "shm") == "shm"
+    if _SHM["same_host"]:
+        return _gather_shm(obj, rank, world, group)
     out = [None] * world if rank == 0 else None
     dist.gather_object(obj, out, dst=0, group=group)
     return out

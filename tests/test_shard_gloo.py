@@ -44,8 +44,11 @@ def _worker(rank, world, port, tmp):
     asg = shard.plan(SIZES, world, 6, 80, 5)
     assert any(len({k for k, _, _ in u}) for u in asg)
     mine = _fake_units(asg[rank], rec)
-    gathered = shard.gather_to_rank0(mine, rank, world)
+    for _ in range(3):                 # the shared-memory segments are reused from pass to pass
+        gathered = shard.gather_to_rank0(mine, rank, world)
+    assert shard._SHM["same_host"] is (os.environ.get("PEAKACHU_B200_GATHER", "shm") == "shm")
     if rank == 0:
+        assert len(gathered) == world
         text = shard.assemble_text(queue, gathered, 10000)
         with open(os.path.join(tmp, "out.bedpe"), "w") as fh:
             for k in queue:
@@ -54,8 +57,11 @@ def _worker(rank, world, port, tmp):
     dist.destroy_process_group()
 
 
-def test_two_rank_gather_reproduces_bedpe(tmp_path):
+@pytest.mark.parametrize("how", ["shm", "pickle"])
+def test_two_rank_gather_reproduces_bedpe(tmp_path, how, monkeypatch):
+    """Both host gathers: numpy columns through shared memory (one node) and pickled objects."""
     import torch.multiprocessing as mp
+    monkeypatch.setenv("PEAKACHU_B200_GATHER", how)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
