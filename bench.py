@@ -288,6 +288,7 @@ def main():
     ap.add_argument("--cpu-bins", type=int, default=4000, help="chromosome size of the bounded CPU sample")
     ap.add_argument("--cpu-workers", type=int, default=32, help="processes of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--numa", type=int, default=1, help="N > 1: run each rank on the NUMA node of its GPU (0: leave the affinity alone)")
     ap.add_argument("--fused", type=int, default=-1, help="pk_set_tuning('fused'): -1 auto, 0 off, 1, 2")
     ap.add_argument("--prune", type=int, default=1, help="pk_set_tuning('prune'): retire pixels that cannot exceed min_prob")
     ap.add_argument("--child-features", type=int, default=-1, help="pk_set_tuning('child_features'): forest walk on the child-feature node encoding (-1 auto, 0 off, 1 on)")
@@ -311,6 +312,11 @@ def main():
     torch.cuda.set_device(local)
     L = _lib.lib()
     _lib.require_device()
+    numa_node = None
+    if world > 1 and args.numa:
+        from peakachu_b200 import shard as _shard
+        numa_node = _shard.bind_to_device_node(local)       # before any pinned allocation
+    print("rank %d: device %d, NUMA node %s" % (rank, local, numa_node), file=sys.stderr)
     _lib.check(L.pk_set_tuning(b"fused", args.fused))
     _lib.check(L.pk_set_tuning(b"prune", args.prune))
     if L.pk_set_tuning(b"child_features", args.child_features) != 0 and args.child_features != -1:

@@ -50,6 +50,10 @@ const char* pk_last_error(void);
 int pk_abi_version(void);
 /* number of visible CUDA devices; fails with PK_ECUDA when there is none */
 int pk_device_count(int* out);
+/* PCI bus id of a device ("0000:1b:00.0"), NUL-terminated into buf[len]. The host side uses it to run each
+ * rank of score_genome (score_genome.py:46-84, one process per GPU here) on the NUMA node its GPU hangs off,
+ * so that the pinned pixel columns are local to the DMA engine. */
+int pk_device_pci_bus_id(int device, char* buf, int len);
 
 /* ---- forest: replaces model.predict_proba(fea)[:, 1] (scoreUtils.py:109) on the
  * joblib-loaded sklearn RandomForestClassifier (score_chromosome.py:14). Arrays are

@@ -28,6 +28,7 @@ SIGNATURES = {
     "pk_last_error": (C.c_char_p, []),
     "pk_abi_version": (C.c_int, []),
     "pk_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "pk_device_pci_bus_id": (C.c_int, [C.c_int, C.c_char_p, C.c_int]),
     "pk_forest_create": (C.c_int, [C.c_int, C.c_int32, C.c_int32, c_i64p, c_i32p, c_f64p, c_i32p, c_i32p,
                                    c_u8p, c_f64p, C.POINTER(C.c_void_p)]),
     "pk_forest_destroy": (C.c_int, [C.c_void_p]),

@@ -87,6 +87,12 @@ extern "C" int pk_device_count(int* out) {
     return PK_OK;
 }
 
+extern "C" int pk_device_pci_bus_id(int device, char* buf, int len) {
+    if (!buf || len < 13) { pk_set_error("pk_device_pci_bus_id: buffer of at least 13 bytes needed"); return PK_EINVAL; }
+    PK_CUDA(cudaDeviceGetPCIBusId(buf, len, device));
+    return PK_OK;
+}
+
 // ---------------------------------------------------------------------------
 // device memory: a small caching allocator. Handles are created and destroyed per
 // chromosome (as the reference builds one Chromosome object per chromosome), so

@@ -54,6 +54,45 @@ def plan(sizes: dict, world: int, lower: int, upper: int, w: int, split: bool = 
     return out
 
 
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        elif part:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_to_device_node(device, sysfs="/sys"):
+    """Run this process on the CPUs of the NUMA node its GPU is attached to, so that host buffers
+    allocated (and pinned) from now on are local to the GPU's DMA engine. With one process per GPU on
+    a two-socket box the ranks otherwise land on either socket and half of the uploads cross the
+    socket interconnect. Returns the node, or None when the topology is not exposed (containers,
+    single-node hosts) or PEAKACHU_B200_NUMA=0."""
+    import ctypes as C
+
+    from . import _lib
+    if os.environ.get("PEAKACHU_B200_NUMA", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None
+    buf = C.create_string_buffer(32)
+    _lib.check(_lib.lib().pk_device_pci_bus_id(int(device), buf, 32))
+    bus = buf.value.decode().lower()
+    try:
+        node = int(open(os.path.join(sysfs, "bus/pci/devices", bus, "numa_node")).read())
+        if node < 0:
+            return None
+        cpus = _cpulist(open(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % node)).read())
+        cpus &= os.sched_getaffinity(0)          # stay inside a cgroup / taskset restriction
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError):
+        return None
+
+
 _GROUP = None
 
 
@@ -334,6 +373,8 @@ def score_chromosomes(Lib, queue, flat, *, correct, lower, upper, res, min_prob,
     rank, world = rank_world()
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        bind_to_device_node(device)
     sizes = {k: Lib.nbins(k) for k in queue}
     assignment = plan(sizes, world, lower, upper, flat.width)
     mine = score_units(Lib, assignment[rank], flat, correct=correct, lower=lower, upper=upper, res=res,

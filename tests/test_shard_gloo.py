@@ -74,3 +74,33 @@ def test_plan_splits_large_chromosome_into_row_tiles():
     tiles = sorted((a, b) for u in asg for k, a, b in u if k == "1")
     assert len(tiles) == 4 and tiles[0][0] == 0 and tiles[-1][1] == 24926
     assert all(t0[1] == t1[0] for t0, t1 in zip(tiles, tiles[1:]))
+
+
+def test_bind_to_device_node_reads_sysfs(tmp_path, monkeypatch):
+    """NUMA binding of a rank: PCI bus id of the device -> numa_node -> cpulist -> sched_setaffinity
+    (sysfs faked; the affinity call recorded, not applied)."""
+    from peakachu_b200 import _lib
+
+    class Stub:
+        @staticmethod
+        def pk_device_pci_bus_id(device, buf, n):
+            buf.value = b"0000:1B:00.0"
+            return 0
+    monkeypatch.setattr(_lib, "lib", lambda: Stub)
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    node = tmp_path / "devices/system/node/node1"
+    node.mkdir(parents=True)
+    have = sorted(os.sched_getaffinity(0))
+    (node / "cpulist").write_text("%d-%d,9999\n" % (have[0], have[-1]))
+    calls = []
+    monkeypatch.setattr(os, "sched_setaffinity", lambda pid, cpus: calls.append((pid, set(cpus))))
+    assert shard.bind_to_device_node(0, sysfs=str(tmp_path)) == 1
+    assert calls == [(0, set(have))]                      # intersected with the current affinity
+    (dev / "numa_node").write_text("-1\n")                # topology not exposed
+    assert shard.bind_to_device_node(0, sysfs=str(tmp_path)) is None
+    monkeypatch.setenv("PEAKACHU_B200_NUMA", "0")
+    (dev / "numa_node").write_text("1\n")
+    assert shard.bind_to_device_node(0, sysfs=str(tmp_path)) is None
+    assert len(calls) == 1
