@@ -112,15 +112,22 @@ def _host_group():
 
 # -- host-side gather ---------------------------------------------------------------
 # Records are numpy columns. Pickling them through gloo's gather_object costs milliseconds per pass
-# (serialise, TCP loopback, deserialise), as much as a rank's share of an hg19-sized genome takes to
-# score on eight GPUs. On one node (the deployment SURVEY.md 8(e) describes) the columns go through a
-# POSIX shared-memory segment per rank instead: each rank copies its arrays into its segment, a small
-# gather_object carries the layout, rank 0 copies the arrays out, a barrier releases the segments.
-_SHM = {"seg": None, "cap": 0, "same_host": None, "peers": {}}
+# (serialise, TCP loopback, deserialise; 6 ms at two ranks), as much as a rank's share of an hg19-sized
+# genome takes to score on eight GPUs, and even a metadata-only gather_object + barrier costs 2-3 ms at
+# eight ranks. On one node (the deployment SURVEY.md 8(e) describes) nothing goes through a collective
+# after the first call: every rank owns a small control segment and a data segment in POSIX shared
+# memory. A rank copies its columns into its data segment and publishes the pass number in its control
+# segment; rank 0 polls for it, copies the columns out and acknowledges in its own control segment,
+# which the rank checks before it overwrites the data in the next pass.
+#   control segment: [0:8] last published pass, [8:16] bytes of the data block, [16:80] name of the data
+#   segment, [128 + 8 r] rank 0 only: last pass of rank r it has finished reading
+_CTL_BYTES = 4096
+_SHM = {"mode": None, "pass": 0, "ctl": None, "seg": None, "cap": 0, "ctl_peers": {}, "peers": {}, "peer_names": {},
+        "fence": None}
 
 
 def _strip_arrays(obj, arrays):
-    """Replace every ndarray in a nest of dicts / lists / tuples by a placeholder."""
+    """Replace every ndarray in a nest of dicts / lists by a placeholder."""
     if isinstance(obj, np.ndarray):
         arrays.append(np.ascontiguousarray(obj))
         return ("__nd__", len(arrays) - 1)
@@ -142,97 +149,164 @@ def _restore_arrays(obj, arrays):
 
 
 def _release_shm():
-    seg = _SHM["seg"]
-    _SHM["seg"] = None
-    for peer in _SHM["peers"].values():
-        try:
-            peer.close()
-        except Exception:
-            pass
-    _SHM["peers"].clear()
-    if seg is not None:
-        try:
-            seg.close()
-            seg.unlink()
-        except Exception:
-            pass
+    for d in (_SHM["peers"], _SHM["ctl_peers"]):
+        for peer in d.values():
+            try:
+                peer.close()
+            except Exception:
+                pass
+        d.clear()
+    for key in ("seg", "ctl"):
+        seg, _SHM[key] = _SHM[key], None
+        if seg is not None:
+            try:
+                seg.close()
+                seg.unlink()
+            except Exception:
+                pass
 
 
-def _segment(nbytes):
-    from multiprocessing import shared_memory
-    if _SHM["seg"] is None or _SHM["cap"] < nbytes:
-        if _SHM["seg"] is not None:
-            _SHM["seg"].close()
-            _SHM["seg"].unlink()
-        else:
-            import atexit
-            atexit.register(_release_shm)
-        cap = max(1 << 20, int(nbytes * 1.5))
-        _SHM["seg"] = shared_memory.SharedMemory(create=True, size=cap)
-        _SHM["cap"] = cap
-    return _SHM["seg"]
-
-
-def _attach(name):
-    """Map another rank's segment (cached by name; the owner unlinks it)."""
+def _attach(name, cache):
+    """Map another rank's segment (the owner unlinks it)."""
     from multiprocessing import resource_tracker, shared_memory
-    seg = _SHM["peers"].get(name)
-    if seg is None:
-        seg = shared_memory.SharedMemory(name=name)
-        try:        # Python < 3.13 registers attached segments too; the owner is responsible for this one
-            resource_tracker.unregister(seg._name, "shared_memory")
-        except Exception:
-            pass
-        _SHM["peers"][name] = seg
+    seg = shared_memory.SharedMemory(name=name)
+    try:        # Python < 3.13 registers attached segments too; the owner is responsible for this one
+        resource_tracker.unregister(seg._name, "shared_memory")
+    except Exception:
+        pass
+    cache[name] = seg
     return seg
 
 
-def _gather_shm(obj, rank, world, group):
+def _fence():
+    """Full memory barrier between writing a block and publishing its sequence number (and between
+    seeing the number and reading the block): a mutex round trip."""
+    lock = _SHM["fence"]
+    lock.acquire()
+    lock.release()
+
+
+def _wait_for(buf, offset, value, what, timeout=600.0):
+    import struct
+    import time
+    t0, spins = time.monotonic(), 0
+    while struct.unpack_from("<Q", buf, offset)[0] < value:
+        spins += 1
+        time.sleep(0 if spins < 20000 else 1e-4)
+        if (spins & 1023) == 0 and time.monotonic() - t0 > timeout:
+            raise RuntimeError("host gather: timed out waiting for %s" % what)
+
+
+def _setup_shm(rank, world, group):
+    """First call: decide the mode, create the control segments, exchange their names once."""
+    import atexit
+    import socket
+    import threading
+    from multiprocessing import shared_memory
+
     import torch.distributed as dist
-    arrays = []
-    meta = _strip_arrays(obj, arrays)
-    layout, off = [], 0
-    for a in arrays:
-        layout.append((a.dtype.str, a.shape, off))
-        off += (a.nbytes + 63) & ~63
-    name = None
+    want = os.environ.get("PEAKACHU_B200_GATHER", "shm")
+    ctl = None
+    if want == "shm":
+        try:
+            ctl = shared_memory.SharedMemory(create=True, size=_CTL_BYTES)
+            ctl.buf[:_CTL_BYTES] = bytes(_CTL_BYTES)
+        except OSError:
+            ctl = None
+    info = [None] * world
+    dist.all_gather_object(info, (socket.gethostname(), ctl.name if ctl is not None else None), group=group)
+    ok = want == "shm" and len({h for h, _ in info}) == 1 and all(n is not None for _, n in info)
+    if not ok:
+        if ctl is not None:
+            ctl.close()
+            ctl.unlink()
+        _SHM["mode"] = "pickle"
+        return
+    _SHM.update(mode="shm", ctl=ctl, fence=threading.Lock())
+    atexit.register(_release_shm)
+    if rank == 0:
+        for r in range(1, world):
+            _attach(info[r][1], _SHM["ctl_peers"])
+        _SHM["ctl_names"] = [n for _, n in info]
+    else:
+        _attach(info[0][1], _SHM["ctl_peers"])
+        _SHM["root_ctl"] = info[0][1]
+
+
+def _gather_shm(obj, rank, world):
+    import pickle
+    import struct
+    from multiprocessing import shared_memory
+    p = _SHM["pass"] = _SHM["pass"] + 1
     if rank != 0:
-        seg = _segment(off)
-        name = seg.name
+        arrays = []
+        meta = _strip_arrays(obj, arrays)
+        layout, off = [], 0
+        for a in arrays:
+            layout.append((a.dtype.str, a.shape, off))
+            off += (a.nbytes + 63) & ~63
+        head = pickle.dumps((meta, layout), protocol=pickle.HIGHEST_PROTOCOL)
+        base = (16 + len(head) + 63) & ~63
+        total = base + off
+        # rank 0 must have finished with the previous pass before its block is overwritten
+        root = _SHM["ctl_peers"][_SHM["root_ctl"]]
+        _wait_for(root.buf, 128 + 8 * rank, p - 1, "rank 0 to read pass %d" % (p - 1))
+        if _SHM["seg"] is None or _SHM["cap"] < total:
+            if _SHM["seg"] is not None:
+                _SHM["seg"].close()
+                _SHM["seg"].unlink()
+            _SHM["cap"] = max(1 << 20, int(total * 1.5))
+            _SHM["seg"] = shared_memory.SharedMemory(create=True, size=_SHM["cap"])
+        buf = _SHM["seg"].buf
+        struct.pack_into("<QQ", buf, 0, len(head), base)
+        buf[16:16 + len(head)] = head
         for a, (_, _, o) in zip(arrays, layout):
             if a.nbytes:
-                np.frombuffer(seg.buf, dtype=np.uint8, count=a.nbytes, offset=o)[:] = a.reshape(-1).view(np.uint8)
-    out = [None] * world if rank == 0 else None
-    dist.gather_object((name, meta, layout), out, dst=0, group=group)
-    result = None
-    if rank == 0:
-        result = [obj]
-        for r in range(1, world):
-            rname, rmeta, rlayout = out[r]
-            seg = _attach(rname)
-            got = [np.frombuffer(seg.buf, dtype=np.dtype(dt), count=int(np.prod(shape, dtype=np.int64)), offset=o)
-                   .reshape(shape).copy() for dt, shape, o in rlayout]
-            result.append(_restore_arrays(rmeta, got))
-    dist.barrier(group=group)           # rank 0 has copied: the segments may be overwritten by the next pass
+                np.frombuffer(buf, dtype=np.uint8, count=a.nbytes, offset=base + o)[:] = a.reshape(-1).view(np.uint8)
+        ctl = _SHM["ctl"].buf
+        name = _SHM["seg"].name.encode()
+        struct.pack_into("<Q64s", ctl, 8, total, name)
+        _fence()
+        struct.pack_into("<Q", ctl, 0, p)                 # publish
+        return None
+    result = [obj]
+    mine = _SHM["ctl"].buf
+    for r in range(1, world):
+        ctl = _SHM["ctl_peers"][_SHM["ctl_names"][r]].buf
+        _wait_for(ctl, 0, p, "rank %d to publish pass %d" % (r, p))
+        _fence()
+        total, name = struct.unpack_from("<Q64s", ctl, 8)
+        name = name.rstrip(b"\0").decode()
+        seg = _SHM["peers"].get(r)
+        if seg is None or _SHM["peer_names"].get(r) != name:      # first pass, or rank r grew its segment
+            if seg is not None:
+                seg.close()
+            seg = _attach(name, {})
+            _SHM["peers"][r] = seg
+            _SHM["peer_names"][r] = name
+        hlen, base = struct.unpack_from("<QQ", seg.buf, 0)
+        meta, layout = pickle.loads(bytes(seg.buf[16:16 + hlen]))
+        got = [np.frombuffer(seg.buf, dtype=np.dtype(dt), count=int(np.prod(shape, dtype=np.int64)), offset=base + o)
+               .reshape(shape).copy() for dt, shape, o in layout]
+        result.append(_restore_arrays(meta, got))
+        _fence()
+        struct.pack_into("<Q", mine, 128 + 8 * r, p)      # acknowledge: rank r may overwrite its block
     return result
 
 
 def gather_to_rank0(obj, rank, world):
-    """Host-side gather of the ranks' records to rank 0 (gloo group): numpy columns through shared
-    memory when every rank runs on the same host, else pickled through gather_object."""
+    """Host-side gather of the ranks' records to rank 0: numpy columns through shared memory when every
+    rank runs on the same host (PEAKACHU_B200_GATHER=shm, the default), else pickled through gloo's
+    gather_object. Returns the list of per-rank objects on rank 0, None elsewhere."""
     if world == 1:
         return [obj]
     import torch.distributed as dist
-    group = _host_group()
-    if _SHM["same_host"] is None:
-        import socket
-        names = [None] * world
-        dist.all_gather_object(names, socket.gethostname(), group=group)
-        _SHM["same_host"] = len(set(names)) == 1 and os.environ.get("PEAKACHU_B200_GATHER", "shm") == "shm"
-    if _SHM["same_host"]:
-        return _gather_shm(obj, rank, world, group)
+    if _SHM["mode"] is None:
+        _setup_shm(rank, world, _host_group())
+    if _SHM["mode"] == "shm":
+        return _gather_shm(obj, rank, world)
     out = [None] * world if rank == 0 else None
-    dist.gather_object(obj, out, dst=0, group=group)
+    dist.gather_object(obj, out, dst=0, group=_host_group())
     return out
 
 

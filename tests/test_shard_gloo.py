@@ -44,9 +44,13 @@ def _worker(rank, world, port, tmp):
     asg = shard.plan(SIZES, world, 6, 80, 5)
     assert any(len({k for k, _, _ in u}) for u in asg)
     mine = _fake_units(asg[rank], rec)
-    for _ in range(3):                 # the shared-memory segments are reused from pass to pass
-        gathered = shard.gather_to_rank0(mine, rank, world)
-    assert shard._SHM["same_host"] is (os.environ.get("PEAKACHU_B200_GATHER", "shm") == "shm")
+    for i in range(4):                 # the shared-memory segments are reused from pass to pass, and regrown
+        big = dict(mine, pad=[dict(row_begin=0, junk=np.arange((i % 2) * 400000 + rank, dtype=np.int64))]) if i < 3 else mine
+        gathered = shard.gather_to_rank0(big, rank, world)
+        if rank == 0 and i < 3:
+            for r in range(world):
+                assert np.array_equal(gathered[r]["pad"][0]["junk"], np.arange((i % 2) * 400000 + r))
+    assert shard._SHM["mode"] == os.environ.get("PEAKACHU_B200_GATHER", "shm")
     if rank == 0:
         assert len(gathered) == world
         text = shard.assemble_text(queue, gathered, 10000)
