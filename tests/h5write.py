@@ -219,7 +219,7 @@ class Writer:
 
 
 def write_cool(path: str, chroms, binsize: int, weight_name: str = "weight", trans=None, group: str = "",
-               chunk: int = 4096, userblock: int = 0, extra_bins: dict | None = None):
+               chunk: int = 4096, userblock: int = 0, extra_bins: dict | None = None, latest: bool = False):
     """Write synth.SynthChrom-like objects (name, n, bin1, bin2, count, weights) as a cooler file:
     cooler's schema version 3 columns and dtypes (int64 bin ids, int32 counts and coordinates, float64
     weights, enum chromosome ids, fixed-length ASCII names), gzip level 6 + shuffle like cooler's
@@ -245,7 +245,7 @@ def write_cool(path: str, chroms, binsize: int, weight_name: str = "weight", tra
     chrom_id = np.repeat(np.arange(len(chroms), dtype=np.int32), nb)
     names = np.array([c.name.encode() for c in chroms], dtype="S%d" % max(len(c.name) for c in chroms))
 
-    W = Writer(userblock=userblock)
+    W = (Writer2 if latest else Writer)(userblock=userblock)      # Writer2 is defined below (resolved at call time)
     z = dict(chunk=chunk, gzip=6, shuffle=True, unlimited=True)
     g_chroms = W.group({"name": W.dataset(names, chunk=max(1, len(chroms)), gzip=6, shuffle=True),
                         "length": W.dataset(lengths, chunk=max(1, len(chroms)), gzip=6, shuffle=True)})
@@ -265,3 +265,131 @@ def write_cool(path: str, chroms, binsize: int, weight_name: str = "weight", tra
         top = W.group({part: top})
     W.finish(top, path)
     return dict(bin1=b1, bin2=b2, count=cnt, chrom_offset=off, bin1_offset=bin1_offset, weights=w)
+
+
+class Writer2(Writer):
+    """The same objects in HDF5's "latest" file format (what h5py writes with libver='latest'):
+    superblock version 2, version-2 object headers (OHDR / OCHK), groups as link messages,
+    version-2 dataspaces and filter pipelines, version-3 attributes, version-4 data layouts with
+    single-chunk, implicit and fixed-array chunk indexes. Checksum fields are written as zero (the
+    reader under test does not verify them)."""
+
+    def __init__(self, userblock: int = 0):
+        super().__init__(userblock)
+        del self.buf[self.base + 48:]                  # the version-2 superblock is 48 bytes
+
+    @staticmethod
+    def space_msg(shape, unlimited=False) -> bytes:
+        m = struct.pack("<BBBB", 2, len(shape), 1 if unlimited else 0, 1 if len(shape) else 0)
+        m += b"".join(struct.pack("<Q", s) for s in shape)
+        if unlimited:
+            m += b"".join(struct.pack("<Q", UNDEF) for _ in shape)
+        return m
+
+    @staticmethod
+    def attr_msg(name: str, value) -> bytes:
+        v = np.asarray(value)
+        nm = name.encode() + b"\0"
+        dtm = Writer.dtype_msg(v.dtype)
+        spm = Writer2.space_msg(v.shape)
+        return struct.pack("<BBHHHB", 3, 0, len(nm), len(dtm), len(spm), 0) + nm + dtm + spm + v.tobytes()
+
+    def object_header(self, messages, split_after=None) -> int:
+        def pack(msgs):
+            return b"".join(struct.pack("<BHB", t, len(data), 0) + data for t, data in msgs)
+        if split_after is not None and split_after < len(messages):
+            tail = b"OCHK" + pack(messages[split_after:]) + b"\0" * 4
+            tail_addr = self.alloc(tail)
+            head = pack(list(messages[:split_after]) + [(0x10, struct.pack("<QQ", tail_addr, len(tail)))])
+        else:
+            head = pack(messages)
+        # flags 0x22: chunk-0 size in 4 bytes, times stored
+        return self.alloc(b"OHDR" + struct.pack("<BB", 2, 0x22) + b"\0" * 16 + struct.pack("<I", len(head)) + head + b"\0" * 4)
+
+    def dataset(self, arr, chunk=None, gzip=None, shuffle=False, fletcher=False, unlimited=False,
+                enum=None, attrs=None, compact=False, skip_filter_on=None) -> int:
+        arr = np.ascontiguousarray(arr)
+        msgs = [(0x01, self.space_msg(arr.shape, unlimited)), (0x03, self.dtype_msg(arr.dtype, enum)),
+                (0x05, struct.pack("<BB", 3, 0x09))]
+        es = arr.dtype.itemsize
+        if chunk is None:
+            if compact:
+                raw = arr.tobytes()
+                msgs.append((0x08, struct.pack("<BBH", 4, 0, len(raw)) + raw))
+            else:
+                addr = self.alloc(arr.tobytes()) if arr.size else UNDEF
+                msgs.append((0x08, struct.pack("<BBQQ", 4, 1, addr, arr.nbytes)))
+        else:
+            c = chunk if isinstance(chunk, int) else chunk[0]
+            assert arr.ndim == 1
+            filters = ([(2, [es])] if shuffle else []) + ([(1, [gzip])] if gzip is not None else []) + ([(3, [])] if fletcher else [])
+            if filters:
+                fm = struct.pack("<BB", 2, len(filters))
+                for fid, vals in filters:
+                    fm += struct.pack("<HHH", fid, 1, len(vals)) + b"".join(struct.pack("<I", v) for v in vals)
+                msgs.append((0x0B, fm))
+            records = []
+            for k, o in enumerate(range(0, arr.shape[0], c)):
+                blk = np.zeros(c, dtype=arr.dtype)
+                part = arr[o:o + c]
+                blk[:part.size] = part
+                raw = blk.tobytes()
+                mask = 0
+                for i, (fid, vals) in enumerate(filters):
+                    if skip_filter_on is not None and k == skip_filter_on and fid == 1:
+                        mask |= 1 << i
+                        continue
+                    if fid == 2:
+                        raw = np.frombuffer(raw, dtype=np.uint8).reshape(c, es).T.tobytes()
+                    elif fid == 1:
+                        raw = zlib.compress(raw, vals[0])
+                    elif fid == 3:
+                        raw = raw + b"\0" * 4
+                records.append((self.alloc(raw), len(raw), mask))
+            head = struct.pack("<BBBBB", 4, 2, 0x02 if (filters and len(records) == 1) else 0, 2, 4) + struct.pack("<II", c, es)
+            if len(records) <= 1:                      # single-chunk index
+                addr, size, mask = records[0] if records else (UNDEF, 0, 0)
+                lay = head + struct.pack("<B", 1) + (struct.pack("<QI", size, mask) if filters and records else b"") + struct.pack("<Q", addr)
+                if not records:
+                    lay = struct.pack("<BBBBB", 4, 2, 0, 2, 4) + struct.pack("<II", c, es) + struct.pack("<BQ", 1, UNDEF)
+            elif not filters:                          # implicit index: the chunks lie back to back
+                first = self.alloc(b"".join(bytes(self.buf[self.base + a: self.base + a + n]) for a, n, _ in records))
+                lay = head + struct.pack("<BQ", 2, first)
+            else:                                      # fixed array of (address, size, mask) entries
+                esize = 8 + 4 + 4
+                fahd = self.alloc(b"\0" * (4 + 4 + 8 + 8 + 4))
+                body = b"FADB" + struct.pack("<BBQ", 0, 1, fahd)
+                body += b"".join(struct.pack("<QII", a, n, m) for a, n, m in records) + b"\0" * 4
+                fadb = self.alloc(body)
+                self.buf[self.base + fahd: self.base + fahd + 28] = b"FAHD" + struct.pack("<BBBBQQ", 0, 1, esize, 10, len(records), fadb) + b"\0" * 4
+                lay = head + struct.pack("<BBQ", 3, 10, fahd)
+            msgs.append((0x08, lay))
+        split = None
+        if attrs:
+            split = len(msgs)
+            for k, v in attrs.items():
+                msgs.append((0x0C, self.attr_msg(k, v)))
+        return self.object_header(msgs, split_after=split)
+
+    def group(self, children: dict, attrs=None, leaf_k: int = 4) -> int:
+        msgs = [(0x02, struct.pack("<BBQQ", 0, 0, UNDEF, UNDEF)), (0x0A, struct.pack("<BB", 0, 0))]
+        for i, nm in enumerate(sorted(children)):
+            name = nm.encode()
+            if i % 2:                                  # alternate the optional fields of a link message
+                msgs.append((0x06, struct.pack("<BBBQBB", 1, 0x1C, 0, i, 0, len(name)) + name + struct.pack("<Q", children[nm])))
+            else:
+                msgs.append((0x06, struct.pack("<BBH", 1, 0x01, len(name)) + name + struct.pack("<Q", children[nm])))
+        split = None
+        if attrs:
+            split = len(msgs)
+            for k, v in attrs.items():
+                msgs.append((0x0C, self.attr_msg(k, v)))
+        return self.object_header(msgs, split_after=split)
+
+    def finish(self, root_addr: int, path: str):
+        sb = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBB", 2, 8, 8, 0)
+        sb += struct.pack("<QQQQ", self.base, UNDEF, len(self.buf) - self.base, root_addr) + b"\0" * 4
+        assert len(sb) == 48
+        self.buf[self.base:self.base + 48] = sb
+        with open(path, "wb") as fh:
+            fh.write(self.buf)

@@ -41,16 +41,24 @@ def test_reader_on_a_libhdf5_written_file():
         assert d.attrs["MATLAB_class"] == b"double"
 
 
+@pytest.mark.parametrize("latest", [False, True])
 @pytest.mark.parametrize("userblock,group,chunk", [(0, "", 4096), (512, "resolutions/10000", 1000), (0, "", 37)])
-def test_cool_round_trip(tmp_path, userblock, group, chunk):
+def test_cool_round_trip(tmp_path, userblock, group, chunk, latest):
+    """`latest`: the same cooler in HDF5's newer on-disk structures (superblock 2, OHDR object headers,
+    link-message groups, version-4 layouts with fixed-array / single-chunk indexes; h5py libver='latest')."""
     chroms = _genome()
     rng = np.random.default_rng(0)
     path = str(tmp_path / "t.cool")
-    ref = h5write.write_cool(path, chroms, 10000, trans=_trans(chroms, rng), group=group, chunk=chunk,
+    ref = h5write.write_cool(path, chroms, 10000, trans=_trans(chroms, rng), group=group, chunk=chunk, latest=latest,
                              userblock=userblock, extra_bins={"KR": np.arange(sum(c.n for c in chroms), dtype=np.float64)})
     uri = path + ("::/" + group if group else "")
     lib = coolio.open_map(uri)
     assert isinstance(lib, coolio.H5Cool)
+    if latest and chunk == 37:
+        # more than 1024 chunks: libhdf5 pages the fixed-array index, which the subset reader refuses loudly
+        with pytest.raises(h5mini.H5Unsupported, match="paged fixed array"):
+            lib.upper_pixels(chroms[0].name)
+        return
     assert lib.chromnames == [c.name for c in chroms]
     assert lib.binsize == 10000
     off = 0
@@ -111,10 +119,12 @@ def test_same_pixels_as_the_pkcool_container(tmp_path):
         np.testing.assert_array_equal(a.weights(c.name, "weight"), b.weights(c.name, "weight"))
 
 
-def test_layout_and_type_variants(tmp_path):
+@pytest.mark.parametrize("latest", [False, True])
+def test_layout_and_type_variants(tmp_path, latest):
     """Compact and contiguous layouts, big-endian and narrow integer columns, float32, empty datasets,
-    groups wider than one symbol-table node, multi-level chunk B-trees."""
-    W = h5write.Writer()
+    groups wider than one symbol-table node, multi-level chunk B-trees; in the newer format: implicit
+    (unfiltered), single-chunk and fixed-array chunk indexes."""
+    W = (h5write.Writer2 if latest else h5write.Writer)()
     rng = np.random.default_rng(1)
     big = rng.integers(-2**40, 2**40, 70000)
     kids = {
@@ -123,7 +133,10 @@ def test_layout_and_type_variants(tmp_path):
         "f4": W.dataset(np.linspace(0, 1, 33, dtype=np.float32), chunk=8, gzip=1),
         "u1": W.dataset(np.arange(200, dtype=np.uint8), chunk=64, shuffle=True),
         "empty": W.dataset(np.zeros(0, dtype=np.int64), chunk=16, gzip=6),
-        "deep": W.dataset(big, chunk=100, gzip=1, shuffle=True),          # 700 chunks: three B-tree levels at K=32... two here
+        "deep": W.dataset(big, chunk=100, gzip=1, shuffle=True),          # 700 chunks: two B-tree levels / a fixed array
+        "plain": W.dataset(np.arange(1000, dtype=np.int32), chunk=128),    # chunked, no filter (implicit index when latest)
+        "one": W.dataset(np.arange(50, dtype=np.int64), chunk=64, gzip=4, shuffle=True),   # a single, partial chunk
+        "one_plain": W.dataset(np.arange(50, dtype=np.int64), chunk=64),
     }
     for i in range(20):                                                    # > 8 links: several SNODs
         kids["col%02d" % i] = W.dataset(np.full(3, i, dtype=np.int32))
@@ -131,7 +144,13 @@ def test_layout_and_type_variants(tmp_path):
     path = str(tmp_path / "v.h5")
     W.finish(root, path)
     with h5mini.File(path) as f:
-        assert len(f.root.keys()) == 26 and f.root.attrs["k"] == 2.5
+        assert len(f.root.keys()) == 29 and f.root.attrs["k"] == 2.5
+        np.testing.assert_array_equal(f["plain"].read(), np.arange(1000))
+        np.testing.assert_array_equal(f["plain"].read(120, 300), np.arange(120, 300))
+        np.testing.assert_array_equal(f["one"].read(), np.arange(50))
+        np.testing.assert_array_equal(f["one_plain"][3:40], np.arange(3, 40))
+        if latest:
+            assert [f[k]._layout[0] for k in ("deep", "plain", "one", "one_plain")] == ["farray", "implicit", "single", "single"]
         np.testing.assert_array_equal(f["compact"].read(), np.arange(7))
         assert f["be"].read().dtype == np.dtype("=i4")
         np.testing.assert_array_equal(f["be"].read(), np.arange(11))
