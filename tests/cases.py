@@ -53,5 +53,5 @@ class Case:
         return joblib.load(self.pkl)
 
 
-ALL_CASES = ["tiny", "tiny_raw", "w7", "lowdepth", "c1", "genome"]
+ALL_CASES = ["tiny", "tiny_raw", "w7", "lowdepth", "c1", "genome", "c5"]
 FULL_TAP_CASES = ["tiny", "tiny_raw", "w7", "lowdepth"]

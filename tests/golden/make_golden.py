@@ -96,6 +96,16 @@ CASES = {
         lower=6, upper=80, res=10000, w=5, weight="weight", min_prob=0.5,
         forest=dict(n_estimators=40, max_depth=12, seed=4), store_inputs=False, full_taps=False,
         genome=True),
+    # BASELINE.json configs[4]: score_genome on a low-depth map with a forest fitted at the matching depth
+    # (what the reference's `depth` step selects), --minimum-prob 0.6, then `pool` at 0.6 and at the default 0.9
+    "c5": dict(
+        chroms=[dict(name="1", n=800, seed=51, depth=8.0, band=110, n_loops=60, loop_max=70),
+                dict(name="5", n=550, seed=52, depth=8.0, band=110, n_loops=40, loop_max=70),
+                dict(name="X", n=480, seed=53, depth=8.0, band=110, n_loops=30, loop_max=70)],
+        train=dict(name="chrT", n=3000, seed=54, depth=8.0, band=110, n_loops=800, loop_max=70),
+        lower=6, upper=60, res=10000, w=5, weight="weight", min_prob=0.6,
+        forest=dict(n_estimators=60, max_depth=14, seed=5), store_inputs=False, full_taps=False,
+        genome=True),
 }
 
 
