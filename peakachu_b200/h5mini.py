@@ -34,6 +34,23 @@ SIGNATURE = b"\x89HDF\r\n\x1a\n"
 UNDEF = 0xFFFFFFFFFFFFFFFF
 
 
+_POOL = None
+
+
+def _pool():
+    """Threads that inflate chunks (shared by every file of the process)."""
+    global _POOL
+    if _POOL is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except AttributeError:
+            ncpu = os.cpu_count() or 1
+        _POOL = ThreadPoolExecutor(max_workers=max(1, min(16, ncpu)), thread_name_prefix="h5mini")
+    return _POOL
+
+
 class H5Error(Exception):
     pass
 
@@ -580,12 +597,19 @@ class Dataset:
                 continue
             fid, vals = self.filters[i]
             if fid == 1:
-                raw = zlib.decompress(raw)
+                # sized output buffer: one inflate call, all of it outside the GIL (the chunks of a large
+                # read are inflated on a thread pool)
+                raw = zlib.decompress(raw, 15, int(np.prod(self._layout[2])) * self.dtype.itemsize + 16)
             elif fid == 2:
+                # byte planes back to elements: one strided store per plane (a transposed copy through
+                # .T.tobytes() is ten times slower and dominated the read)
                 es = vals[0] if vals else self.dtype.itemsize
                 n = len(raw) // es
-                body = np.frombuffer(raw, dtype=np.uint8, count=n * es).reshape(es, n).T.tobytes()
-                raw = body + raw[n * es:]
+                planes = np.frombuffer(raw, dtype=np.uint8, count=n * es).reshape(es, n)
+                body = np.empty((n, es), dtype=np.uint8)
+                for j in range(es):
+                    body[:, j] = planes[j]
+                raw = body.reshape(-1).data if n * es == len(raw) else body.tobytes() + bytes(raw[n * es:])
             elif fid == 3:
                 raw = raw[:-4]
             else:
@@ -618,11 +642,15 @@ class Dataset:
             return np.frombuffer(buf, dtype=self.dtype).reshape(out_shape).astype(native, copy=True)
         out = np.zeros(out_shape, dtype=native)
         cdims = self._layout[2]
-        for offs, addr, csize, fmask in self._chunk_list():
+        hits = [rec for rec in self._chunk_list() if rec[0][0] + cdims[0] > lo and rec[0][0] < hi]
+        # zlib releases the GIL: inflate the chunks of a large read on a few threads (a chromosome of a
+        # genome-wide cooler is hundreds of megabytes of pixel columns)
+        if len(hits) >= 4 and sum(rec[2] for rec in hits) >= (1 << 20) and self.filters:
+            decoded = _pool().map(lambda rec: self._decode_chunk(rec[1], rec[2], rec[3]), hits)
+        else:
+            decoded = (self._decode_chunk(rec[1], rec[2], rec[3]) for rec in hits)
+        for (offs, addr, csize, fmask), chunk in zip(hits, decoded):
             c_lo, c_hi = offs[0], offs[0] + cdims[0]
-            if c_hi <= lo or c_lo >= hi:
-                continue
-            chunk = self._decode_chunk(addr, csize, fmask)
             src = [slice(max(lo, c_lo) - c_lo, min(hi, c_hi) - c_lo)]
             dst = [slice(max(lo, c_lo) - lo, min(hi, c_hi) - lo)]
             for ax in range(1, len(shape)):
