@@ -108,3 +108,36 @@ def test_bind_to_device_node_reads_sysfs(tmp_path, monkeypatch):
     (dev / "numa_node").write_text("1\n")
     assert shard.bind_to_device_node(0, sysfs=str(tmp_path)) is None
     assert len(calls) == 1
+
+
+def test_plan_covers_every_row_once_and_balances():
+    """Property test of the greedy plan: every band row of every chromosome is assigned
+    exactly once, tiles of a chromosome are contiguous, and no rank carries more than the even share plus
+    the largest unit (the bound of greedy largest-first)."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(min_value=1, max_value=30000), min_size=1, max_size=30),
+           st.integers(min_value=1, max_value=8), st.sampled_from([(6, 300, 5), (6, 600, 7), (6, 60, 5)]))
+    def check(sizes, world, lu):
+        lower, upper, w = lu
+        named = {"c%d" % i: n for i, n in enumerate(sizes)}
+        asg = shard.plan(named, world, lower, upper, w)
+        assert len(asg) == world
+        seen = {}
+        for units in asg:
+            for k, a, b in units:
+                assert 0 <= a <= b <= named[k]
+                seen.setdefault(k, []).append((a, b))
+        assert set(seen) == set(named)
+        for k, tiles in seen.items():
+            tiles.sort()
+            assert tiles[0][0] == 0 and tiles[-1][1] == named[k]
+            assert all(t0[1] == t1[0] for t0, t1 in zip(tiles, tiles[1:]))
+        cost = {k: shard.band_pixels(n, lower, upper, w) for k, n in named.items()}
+        unit_cost = [cost[k] / len(seen[k]) for units in asg for k, _, _ in units]
+        loads = [sum(cost[k] / len(seen[k]) for k, _, _ in units) for units in asg]
+        assert max(loads) <= sum(cost.values()) / world + max(unit_cost) + 1e-6
+
+    check()
