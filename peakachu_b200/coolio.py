@@ -296,11 +296,13 @@ class H5Cool:
             raise ValueError("%s: pixel counts outside int32" % self.path)
         cnt = cnt.astype(np.int32)
         rp -= p0
-        cis = b2 < hi
-        if b2.size and b2.min() < lo:
+        if rp.size != n + 1 or np.any(np.diff(rp) < 0):
+            raise ValueError("%s: indexes/bin1_offset is not a row pointer of the pixel table" % self.path)
+        rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+        if b2.size and np.any(b2 - lo < rows):
             raise ValueError("%s: pixels below the diagonal (storage-mode is not symmetric-upper)" % self.path)
+        cis = b2 < hi
         if not cis.all():                                    # drop inter-chromosomal pixels, rebuild the row pointer
-            rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
             rp = np.concatenate([[0], np.cumsum(np.bincount(rows[cis], minlength=n))]).astype(np.int64)
             b2, cnt = b2[cis], cnt[cis]
         out = (rp, (b2 - lo).astype(np.int32), np.ascontiguousarray(cnt))

@@ -172,3 +172,44 @@ def test_not_hdf5(tmp_path):
         coolio.open_map(str(p))
     with pytest.raises(FileNotFoundError):
         coolio.open_map(str(tmp_path / "missing.cool"))
+
+
+def _mini_cool(path, b1, b2, cnt, n=50):
+    """A one-chromosome cooler built column by column (lets a test plant odd columns)."""
+    W = h5write.Writer()
+    off = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
+    z = dict(chunk=64, gzip=6, shuffle=True)
+    g = W.group({
+        "chroms": W.group({"name": W.dataset(np.array([b"chrZ"])), "length": W.dataset(np.array([n * 1000], np.int32))}),
+        "bins": W.group({"start": W.dataset(np.arange(n, dtype=np.int32) * 1000, **z),
+                         "end": W.dataset(np.arange(1, n + 1, dtype=np.int32) * 1000, **z),
+                         "weight": W.dataset(np.ones(n), **z)}),
+        "pixels": W.group({"bin1_id": W.dataset(np.asarray(b1, np.int64), **z), "bin2_id": W.dataset(np.asarray(b2, np.int64), **z),
+                           "count": W.dataset(np.asarray(cnt), **z)}),
+        "indexes": W.group({"chrom_offset": W.dataset(np.array([0, n], np.int64)), "bin1_offset": W.dataset(off, **z)})})
+    W.finish(g, path)
+
+
+def test_odd_pixel_columns_fail_loudly(tmp_path):
+    """Float counts are accepted when they are whole numbers (some coolers store them so); fractional
+    counts (a balanced or normalised matrix in place of raw counts) and pixels below the diagonal are
+    refused: the Poisson filter of scoreUtils.py:59-60 needs raw upper-triangle counts."""
+    b1 = np.repeat(np.arange(40), 3)
+    b2 = b1 + np.tile(np.arange(3), 40)
+    p = str(tmp_path / "f.cool")
+    _mini_cool(p, b1, b2, np.arange(1, 121, dtype=np.float64))
+    lib = coolio.open_map(p)
+    assert lib.binsize == 1000                       # no bin-size attribute: taken from bins/start, bins/end
+    r1, r2, cnt = lib.upper_pixels("chrZ")
+    assert cnt.dtype == np.int32 and np.array_equal(cnt, np.arange(1, 121)) and np.array_equal(r2, b2)
+    _mini_cool(p, b1, b2, np.arange(1, 121) + 0.5)
+    with pytest.raises(ValueError, match="non-integer"):
+        coolio.open_map(p).upper_pixels("chrZ")
+    b2l = b2.copy()
+    b2l[30] = b1[30] - 2
+    _mini_cool(p, b1, b2l, np.ones(120, np.int32))
+    with pytest.raises(ValueError, match="below the diagonal"):
+        coolio.open_map(p).upper_pixels("chrZ")
+    _mini_cool(p, b1, b2, np.full(120, 2**31 + 5, np.int64))
+    with pytest.raises(ValueError, match="outside int32"):
+        coolio.open_map(p).upper_pixels("chrZ")
