@@ -132,6 +132,12 @@ int pk_chrom_candidates(pk_chrom* c, int32_t* out_x, int32_t* out_y, int64_t cap
  * [n_candidates][(2w+1)^2] HOST arrays (either may be NULL), rows of rejected
  * candidates are left untouched. */
 int pk_chrom_features(pk_chrom* c, uint8_t* keep, float* fea32, double* fea64, int64_t capacity);
+/* The same tap taken INSIDE the product kernel: pk_chrom_score's fused kernel builds the float32
+ * feature rows in shared memory and normally never writes them out; here it also spills them to
+ * global memory (what sklearn's predict_proba would be handed, scoreUtils.py:109). keep / fea32 are
+ * HOST arrays as above; rows of rejected candidates come back zero. PK_EUNSUPPORTED for shapes the
+ * fused kernel does not cover. Scores of an earlier pk_chrom_score are invalidated. */
+int pk_chrom_fused_features(pk_chrom* c, pk_forest* f, uint8_t* keep, float* fea32, int64_t capacity);
 /* The same windows at caller-supplied pixels (x[i], y[i]), x <= y, HOST int32 arrays: the
  * training-set extraction of trainUtils.buildmatrix (trainUtils.py:12-44; the caller applies
  * its coordinate mask, trainUtils.py:22). Needs pixels and an expected curve covering

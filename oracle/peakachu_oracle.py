@@ -468,16 +468,21 @@ class Chromosome:
 
 
 def score_map(lib, model, chrom_names, *, weight_name="weight", lower=6, upper=300,
-              res=10000, min_prob=0.5, output=None):
+              res=10000, min_prob=0.5, output=None, genome=False):
     """Body of score_chromosome.main / score_genome.main (score_chromosome.py:14-71,
-    score_genome.py:46-84) on an already-open cooler-like ``lib``."""
+    score_genome.py:46-84) on an already-open cooler-like ``lib``. The two drivers label the
+    records differently: score_chromosome.py:37-38 strips leading 'c', 'h', 'r' characters and
+    prepends 'chr'; score_genome.py:48-51 (``genome=True``) prepends 'chr' unless the name starts with it."""
     import io
     from contextlib import redirect_stdout
     width = int((np.sqrt(model.feature_importances_.size) - 1) / 2)
     correct = False if weight_name.lower() == "raw" else weight_name
     stats_out = []
     for key in chrom_names:
-        cname = "chr" + key.lstrip("chr")
+        if genome:
+            cname = key if key.startswith("chr") else "chr" + key      # score_genome.py:48-51
+        else:
+            cname = "chr" + key.lstrip("chr")                          # score_chromosome.py:37-38
         if correct:
             M = tocsr(lib.matrix(balance=correct, sparse=True).fetch(key))
             raw_M = tocsr(lib.matrix(balance=False, sparse=True).fetch(key))

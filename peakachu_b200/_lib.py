@@ -57,6 +57,7 @@ SIGNATURES = {
     "pk_chrom_find_candidates": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_i64p]),
     "pk_chrom_candidates": (C.c_int, [C.c_void_p, c_i32p, c_i32p, C.c_int64, c_i64p]),
     "pk_chrom_features": (C.c_int, [C.c_void_p, c_u8p, c_f32p, c_f64p, C.c_int64]),
+    "pk_chrom_fused_features": (C.c_int, [C.c_void_p, C.c_void_p, c_u8p, c_f32p, C.c_int64]),
     "pk_chrom_features_at": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, c_u8p, c_f32p, c_f64p]),
     "pk_chrom_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double]),
     "pk_chrom_result_count": (C.c_int, [C.c_void_p, c_i64p, c_i64p, c_i64p]),

@@ -50,6 +50,9 @@ def match_pretrained_models(v, platform="Hi-C"):
 def main(args):
     Lib = coolio.open_map(args.path)
     device = getattr(args, "device", None) or 0
+    if getattr(Lib, "chrom_lengths", None) is None:
+        raise ValueError("%s has no chroms/length column: `depth` scales by the genome size "
+                         "(calculate_depth.py:46)" % args.path)
     genome_size = int(np.sum(Lib.chrom_lengths))
     mindis = args.min_dis // Lib.binsize                                   # calculate_depth.py:22
     totals = 0

@@ -213,6 +213,7 @@ class _RealCoolAdapter:
         self._c = cooler.Cooler(uri)
         self.chromnames = list(self._c.chromnames)
         self.binsize = int(self._c.binsize)
+        self.chrom_lengths = np.asarray(self._c.chromsizes.values, dtype=np.int64)     # `depth` (calculate_depth.py:46)
 
     def nbins(self, chrom):
         lo, hi = self._c.extent(chrom)
@@ -224,6 +225,11 @@ class _RealCoolAdapter:
         return ((df["bin1_id"].values - lo).astype(np.int32),
                 (df["bin2_id"].values - lo).astype(np.int32),
                 df["count"].values.astype(np.int32))
+
+    def upper_pixels_csr(self, chrom):
+        b1, b2, cnt = self.upper_pixels(chrom)
+        rp = np.searchsorted(b1, np.arange(self.nbins(chrom) + 1)).astype(np.int64)
+        return rp, b2, cnt
 
     def weights(self, chrom, name):
         return np.ascontiguousarray(self._c.bins().fetch(chrom)[name].values, dtype=np.float64)
@@ -285,27 +291,41 @@ class H5Cool:
         lo, hi = int(self.chrom_offset[i]), int(self.chrom_offset[i + 1])
         n = hi - lo
         rp = self._bin1_offset.read(lo, hi + 1).astype(np.int64)
-        p0, p1 = int(rp[0]), int(rp[-1])
-        b2 = self._bin2.read(p0, p1).astype(np.int64)
-        cnt = self._count.read(p0, p1)
-        if cnt.dtype.kind == "f":
-            if not np.all(cnt == np.rint(cnt)):
-                raise ValueError("%s: non-integer pixel counts; the Poisson filter "
-                                 "(scoreUtils.py:59-60) needs raw counts" % self.path)
-        if cnt.size and (cnt.min() < 0 or cnt.max() > np.iinfo(np.int32).max):
-            raise ValueError("%s: pixel counts outside int32" % self.path)
-        cnt = cnt.astype(np.int32)
+        p0 = int(rp[0])
         rp -= p0
         if rp.size != n + 1 or np.any(np.diff(rp) < 0):
             raise ValueError("%s: indexes/bin1_offset is not a row pointer of the pixel table" % self.path)
-        rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
-        if b2.size and np.any(b2 - lo < rows):
-            raise ValueError("%s: pixels below the diagonal (storage-mode is not symmetric-upper)" % self.path)
-        cis = b2 < hi
-        if not cis.all():                                    # drop inter-chromosomal pixels, rebuild the row pointer
-            rp = np.concatenate([[0], np.cumsum(np.bincount(rows[cis], minlength=n))]).astype(np.int64)
-            b2, cnt = b2[cis], cnt[cis]
-        out = (rp, (b2 - lo).astype(np.int32), np.ascontiguousarray(cnt))
+        # The rows of a chromosome also hold its inter-chromosomal pixels (several GB per chromosome in a
+        # genome-wide 10 kb file): read bin2 / count in blocks of rows and keep the intra-chromosomal
+        # pixels of each block only.
+        BLOCK = 1 << 24                                       # pixels per block
+        kept_b2, kept_cnt, row_counts = [], [], np.zeros(n, dtype=np.int64)
+        r0 = 0
+        while r0 < n:
+            r1 = int(np.searchsorted(rp, rp[r0] + BLOCK, side="right")) - 1
+            r1 = min(n, max(r1, r0 + 1))
+            a, b = p0 + int(rp[r0]), p0 + int(rp[r1])
+            b2 = self._bin2.read(a, b).astype(np.int64)
+            cnt = self._count.read(a, b)
+            if cnt.dtype.kind == "f" and not np.all(cnt == np.rint(cnt)):
+                raise ValueError("%s: non-integer pixel counts; the Poisson filter "
+                                 "(scoreUtils.py:59-60) needs raw counts" % self.path)
+            if cnt.size and (cnt.min() < 0 or cnt.max() > np.iinfo(np.int32).max):
+                raise ValueError("%s: pixel counts outside int32" % self.path)
+            rows = np.repeat(np.arange(r0, r1, dtype=np.int64), np.diff(rp[r0:r1 + 1]))
+            if b2.size and np.any(b2 - lo < rows):
+                raise ValueError("%s: pixels below the diagonal (storage-mode is not symmetric-upper)" % self.path)
+            cis = b2 < hi
+            if not cis.all():                                # drop inter-chromosomal pixels
+                rows, b2, cnt = rows[cis], b2[cis], cnt[cis]
+            row_counts[r0:r1] = np.bincount(rows - r0, minlength=r1 - r0)
+            kept_b2.append((b2 - lo).astype(np.int32))
+            kept_cnt.append(cnt.astype(np.int32))
+            r0 = r1
+        rp = np.concatenate([[0], np.cumsum(row_counts)]).astype(np.int64)
+        b2l = np.concatenate(kept_b2) if kept_b2 else np.zeros(0, np.int32)
+        cnt = np.concatenate(kept_cnt) if kept_cnt else np.zeros(0, np.int32)
+        out = (rp, np.ascontiguousarray(b2l), np.ascontiguousarray(cnt))
         self._cache = (chrom, out)
         return out
 

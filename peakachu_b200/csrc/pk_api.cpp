@@ -25,7 +25,7 @@ int pk_launch_features(pk_chrom* c, double* d_fea64);
 int pk_launch_forest(const pk_forest* f, const float* X, const uint8_t* keep, int64_t n_rows, int32_t* leaves,
                      double* proba, cudaStream_t stream);
 int pk_launch_emit(pk_chrom* c, double thre);
-int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms, int child_features);
+int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms, int child_features, float* fea_tap);
 size_t pk_sort_temp_bytes(long long n);
 int pk_launch_sort_records_eager(pk_chrom* c, long long M);
 int pk_launch_depth(pk_chrom* c, int32_t min_dis, unsigned long long* d_total);
@@ -132,6 +132,10 @@ static int pool_alloc(void** out, size_t bytes) {
     return PK_OK;
 }
 
+// INVARIANT: a block is freed only after the stream that used it has been synchronised
+// (pk_chrom_destroy, settle_candidates / read_flags before a regrow, pk_chrom_fetch_results): a cached
+// block carries no stream ordering and may be handed to a handle on another stream at once. Buffers
+// that grow while work may still be queued call quiesce() first.
 static void pool_free(void* p) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(g_pool_mu);
@@ -521,8 +525,17 @@ static int stage_pixels(pk_chrom* c, const int32_t** p, int32_t** d_stage, int64
     return PK_OK;
 }
 
+// Wait for everything queued on the handle's streams: called before a buffer that queued work may
+// still read is returned to the block cache (growth of a reused handle's buffers; rare).
+static int quiesce(pk_chrom* c) {
+    PK_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->score_stream) PK_CUDA(cudaStreamSynchronize(c->score_stream));
+    return PK_OK;
+}
+
 static int reserve_staging(pk_chrom* c, int64_t nnz, bool need_b1) {
     if (nnz > c->pix_cap || !c->d_b2 || (need_b1 && !c->d_b1)) {
+        if (c->d_b2) PK_CHECK(quiesce(c));
         dev_free(c->d_b1); dev_free(c->d_b2); dev_free(c->d_cnt);
         int64_t cap = std::max<int64_t>(nnz, 1024);
         PK_CHECK(dev_alloc(&c->d_b1, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_b2, (size_t)cap)); PK_CHECK(dev_alloc(&c->d_cnt, (size_t)cap));
@@ -723,6 +736,7 @@ extern "C" int pk_chrom_get_expected(pk_chrom* c, double* out_exp) {
 
 static int reserve_candidates(pk_chrom* c, int64_t want) {
     if (want > c->cand_cap || !c->d_cx) {
+        if (c->d_cx) PK_CHECK(quiesce(c));
         dev_free(c->d_cx); dev_free(c->d_cd); dev_free(c->d_crank);
         dev_free(c->d_keep); dev_free(c->d_prob);
         dev_free(c->d_rx); dev_free(c->d_ry); dev_free(c->d_rb); dev_free(c->d_rp); dev_free(c->d_rv);
@@ -746,6 +760,7 @@ static int run_candidates(pk_chrom* c, int32_t kmin) {
         c->n_chunks = (c->n + 1023) / 1024;
         const int64_t m = (int64_t)nd * c->n_chunks;
         if (m + 1 > c->cnt_cap) {
+            if (c->d_cnt_all) PK_CHECK(quiesce(c));
             dev_free(c->d_cnt_all); dev_free(c->d_cnt_tile); dev_free(c->d_off_all); dev_free(c->d_off_tile); dev_free(c->d_bits);
             PK_CHECK(dev_alloc(&c->d_cnt_all, (size_t)m + 1)); PK_CHECK(dev_alloc(&c->d_cnt_tile, (size_t)m + 1));
             PK_CHECK(dev_alloc(&c->d_off_all, (size_t)m + 1)); PK_CHECK(dev_alloc(&c->d_off_tile, (size_t)m + 1));
@@ -828,6 +843,7 @@ extern "C" int pk_chrom_candidates(pk_chrom* c, int32_t* out_x, int32_t* out_y, 
 
 static int ensure_feature_buffer(pk_chrom* c) {
     if (c->n_cand > c->fea_cap || !c->d_fea32) {
+        if (c->d_fea32) PK_CHECK(quiesce(c));
         dev_free(c->d_fea32);
         int64_t cap = std::max<int64_t>(c->n_cand + c->n_cand / 8, 1024);
         PK_CHECK(dev_alloc(&c->d_fea32, (size_t)cap * c->F));
@@ -840,6 +856,7 @@ static int reset_score_state(pk_chrom* c) {
     // batches are numbered over the whole chromosome's candidates (at most the band pixels)
     const int64_t nb = band_pixels_of(c) / PK_BATCH + 2;
     if (nb > c->batch_cap || !c->d_batch_win) {
+        if (c->d_batch_win) PK_CHECK(quiesce(c));
         dev_free(c->d_batch_win);
         PK_CHECK(dev_alloc(&c->d_batch_win, (size_t)nb));
         c->batch_cap = nb;
@@ -855,11 +872,13 @@ static int reset_score_state(pk_chrom* c) {
         PK_CUDA(cudaMemsetAsync(c->d_rowcnt, 0, ((size_t)c->n + 1) * 4, c->stream));     // k_record_place keeps it zero afterwards
     }
     if (c->rrank_cap != c->cand_cap || !c->d_rrank) {
+        if (c->d_rrank) PK_CHECK(quiesce(c));
         dev_free(c->d_rrank);
         PK_CHECK(dev_alloc(&c->d_rrank, (size_t)c->cand_cap));
         c->rrank_cap = c->cand_cap;
     }
     if (c->eager_cap != M || !c->d_packed) {
+        if (c->d_packed) PK_CHECK(quiesce(c));
         dev_free(c->d_perm); dev_free(c->d_packed);
         PK_CHECK(dev_alloc(&c->d_perm, (size_t)M));
         PK_CHECK(dev_alloc(&c->d_packed, (size_t)M * 28 + 16));
@@ -936,6 +955,31 @@ extern "C" int pk_chrom_features_at(pk_chrom* c, const int32_t* x, const int32_t
     return r;
 }
 
+// Parity tap of the product kernel: the float32 feature rows k_score_fused builds in shared memory
+// (scoreUtils.py:70-93 -> what predict_proba reads), spilled to global memory by the kernel itself.
+// Rows of rejected candidates are zero. The separate feature kernel (pk_chrom_features) is a
+// different code path (plain IEEE divisions); this one is what pk_chrom_score runs.
+extern "C" int pk_chrom_fused_features(pk_chrom* c, pk_forest* f, uint8_t* keep, float* fea32, int64_t capacity) {
+    if (!c || !f) { pk_set_error("pk_chrom_fused_features: NULL handle"); return PK_EINVAL; }
+    if (!c->has_candidates) { pk_set_error("pk_chrom_fused_features: find_candidates not called"); return PK_ESTATE; }
+    if (f->device != c->device || f->n_features != c->F) { pk_set_error("pk_chrom_fused_features: forest does not match the handle"); return PK_EINVAL; }
+    if (!pk_fused_supported(c->w, f->n_trees)) { pk_set_error("pk_chrom_fused_features: no fused kernel for width %d", c->w); return PK_EUNSUPPORTED; }
+    PK_CUDA(cudaSetDevice(c->device));
+    if (!c->n_cand_known) PK_CHECK(settle_candidates(c));
+    if (capacity < c->n_cand) { pk_set_error("pk_chrom_fused_features: capacity too small"); return PK_ECAPACITY; }
+    c->has_scores = false;
+    if (c->n_cand == 0) return PK_OK;
+    PK_CHECK(reset_score_state(c));
+    PK_CHECK(ensure_feature_buffer(c));
+    PK_CUDA(cudaMemsetAsync(c->d_fea32, 0, (size_t)c->n_cand * c->F * sizeof(float), c->stream));
+    const int variant = g_tune_fused > 1 ? g_tune_fused - 1 : 0;
+    PK_CHECK(pk_launch_fused(c, f, variant, -1.0, 0, g_tune_cf, c->d_fea32));
+    if (keep) PK_CUDA(cudaMemcpyAsync(keep, c->d_keep, (size_t)c->n_cand, cudaMemcpyDeviceToHost, c->stream));
+    if (fea32) PK_CUDA(cudaMemcpyAsync(fea32, c->d_fea32, (size_t)c->n_cand * c->F * 4, cudaMemcpyDeviceToHost, c->stream));
+    PK_CUDA(cudaStreamSynchronize(c->stream));
+    return PK_OK;
+}
+
 static int run_score(pk_chrom* c, pk_forest* f, double min_prob) {
     cudaStream_t s = c->stream;
     PK_CHECK(reset_score_state(c));
@@ -953,12 +997,12 @@ static int run_score(pk_chrom* c, pk_forest* f, double min_prob) {
             PK_CUDA(cudaEventRecord(c->ev_x, s));
             PK_CUDA(cudaStreamWaitEvent(c->score_stream, c->ev_x, 0));
             c->stream = c->score_stream;
-            r = pk_launch_fused(c, f, variant, thre, g_tune_reserve, g_tune_cf);
+            r = pk_launch_fused(c, f, variant, thre, g_tune_reserve, g_tune_cf, nullptr);
             c->stream = s;
             PK_CUDA(cudaEventRecord(c->ev_x, c->score_stream));
             PK_CUDA(cudaStreamWaitEvent(s, c->ev_x, 0));
         } else {
-            r = pk_launch_fused(c, f, variant, thre, 0, g_tune_cf);
+            r = pk_launch_fused(c, f, variant, thre, 0, g_tune_cf, nullptr);
         }
         if (r == PK_EUNSUPPORTED) fused = false;     // shapes the fused kernel has no room for: the two-kernel path below
         else PK_CHECK(r);

@@ -38,6 +38,7 @@ struct FusedParams {
     unsigned long long* next;      // global work counter (candidates handed out)
     const int32_t* flags;          // handle's device flags
     double thre;                   // --minimum-prob: pixels that can no longer exceed it stop walking trees
+    float* fea_tap;                // parity tap (pk_chrom_fused_features): [n_cand][F] copy of the shared-memory feature rows, else NULL
 };
 
 // ---- mbarrier / bulk-copy PTX ------------------------------------------------
@@ -635,6 +636,13 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
         __syncthreads();
         const int nkept = s_nkept;
         last = s_done != 0;
+        if (prm.fea_tap != nullptr) {
+            // parity tap: the float32 feature rows the forest is about to read, spilled per candidate
+            for (int i = tid; i < nkept * F; i += NT) {
+                const int sl = i / F;
+                prm.fea_tap[(size_t)s_idx[sl] * F + (i - sl * F)] = s_fea[i];
+            }
+        }
 
         // ================= phase B: forest =================
         if (nkept > 0) {
@@ -834,8 +842,9 @@ static int launch_fused_t(FusedParams prm, pk_forest* f, int ND, int sm_count, c
     return PK_OK;
 }
 
-int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms, int child_features) {
+int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms, int child_features, float* fea_tap) {
     FusedParams prm;
+    prm.fea_tap = fea_tap;
     prm.band = c->d_band; prm.w = c->d_w; prm.expv = c->d_exp;
     prm.n = c->n; prm.pitch = c->pitch; prm.balanced = c->balanced; prm.ND = c->ND;
     prm.cx = c->d_cx; prm.cd = c->d_cd; prm.crank = c->d_crank;

@@ -255,6 +255,18 @@ class Chromosome:
                                                 _lib.ptr(f64, _lib.c_f64p) if want64 else None, n))
         return (keep.astype(bool), f32, f64) if want64 else (keep.astype(bool), f32)
 
+    def fused_window_features(self):
+        """(keep mask, float32 features) as the product kernel (k_score_fused) builds them in
+        shared memory: the parity tap inside the kernel ``score`` runs (pk_chrom_fused_features)."""
+        if self._forest is None:
+            self._forest = DeviceForest.of(self.model, self.device)
+        n, F = self.n_candidates, (2 * self.w + 1) ** 2
+        keep = np.zeros(n, dtype=np.uint8)
+        f32 = np.zeros((n, F), dtype=np.float32)
+        _lib.check(_lib.lib().pk_chrom_fused_features(self._h, self._forest.handle, _lib.ptr(keep, _lib.c_u8p),
+                                                      _lib.ptr(f32, _lib.c_f32p), n))
+        return keep.astype(bool), f32
+
     # -- scoring (scoreUtils.py:95-125) -----------------------------------------------
     def score_records(self, thre=0.5):
         """(x, y, prob, value) numpy arrays sorted by (x, y)."""

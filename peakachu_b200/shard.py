@@ -16,6 +16,13 @@ import os
 import numpy as np
 
 
+def genome_cname(key):
+    """Chromosome label of ``score_genome`` records (score_genome.py:48-51): the name itself when it
+    starts with 'chr', else 'chr' + name. ``score_chromosome`` has a different rule
+    (score_chromosome.py:37-38, ``'chr' + name.lstrip('chr')``), kept in score_chromosome.py."""
+    return key if key.startswith("chr") else "chr" + key
+
+
 def rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -149,6 +156,18 @@ def _restore_arrays(obj, arrays):
 
 
 def _release_shm():
+    # A rank other than 0 must not unlink its data segment before rank 0 has read the last pass it
+    # published: rank 0 attaches a peer's data segment lazily, at its first read, and usually finishes
+    # last (the greedy plan gives it the largest unit). Wait for its acknowledgement first.
+    root_name = _SHM.get("root_ctl")
+    if _SHM["mode"] == "shm" and root_name is not None and _SHM["pass"] > 0 and _SHM.get("rank", 0) != 0:
+        root = _SHM["ctl_peers"].get(root_name)
+        if root is not None:
+            try:
+                _wait_for(root.buf, 128 + 8 * _SHM["rank"], _SHM["pass"],
+                          "rank 0 to read pass %d before exit" % _SHM["pass"], timeout=120.0)
+            except Exception:
+                pass                      # rank 0 died or never gathered: nothing left to protect
     for d in (_SHM["peers"], _SHM["ctl_peers"]):
         for peer in d.values():
             try:
@@ -222,7 +241,7 @@ def _setup_shm(rank, world, group):
             ctl.unlink()
         _SHM["mode"] = "pickle"
         return
-    _SHM.update(mode="shm", ctl=ctl, fence=threading.Lock())
+    _SHM.update(mode="shm", ctl=ctl, fence=threading.Lock(), rank=rank)
     atexit.register(_release_shm)
     if rank == 0:
         for r in range(1, world):
@@ -379,7 +398,7 @@ def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_pro
                 finish(inflight.popleft())
             weights = Lib.weights(key, correct) if correct else None
             n = Lib.nbins(key)
-            kw = dict(lower=lower, upper=upper, cname="chr" + key.lstrip("chr"), res=res, width=flat.width,
+            kw = dict(lower=lower, upper=upper, cname=genome_cname(key), res=res, width=flat.width,
                       device=device, stream=streams[i % len(streams)].value, first_tile=tiles[0],
                       score_stream=score_stream.value if shared_score_stream else None)
             narrow = Lib.upper_pixels_csr16(key) if hasattr(Lib, "upper_pixels_csr16") else None
@@ -432,7 +451,7 @@ def assemble_text(queue, gathered, res, verbose=False):
         for g in gathered:
             parts.extend(g.get(key, []))
         parts.sort(key=lambda q: q["row_begin"])
-        cname = "chr" + key.lstrip("chr")
+        cname = genome_cname(key)
         if verbose:                                           # scoreUtils.py:97-98
             print("scoring matrix {}".format(cname))
             print("number of candidates {}".format(sum(q["n_candidates"] for q in parts)))

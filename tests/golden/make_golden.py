@@ -106,10 +106,39 @@ CASES = {
         lower=6, upper=60, res=10000, w=5, weight="weight", min_prob=0.6,
         forest=dict(n_estimators=60, max_depth=14, seed=5), store_inputs=False, full_taps=False,
         genome=True),
+    # score_genome's labels (score_genome.py:48-51 prepends 'chr' unless the name starts with it; it does
+    # not strip characters the way score_chromosome.py:37-38 does) on contig names that tell the two rules
+    # apart; an empty --chroms list scores every chromosome (score_genome.py:43)
+    "gnames": dict(
+        chroms=[dict(name="chr1", n=420, seed=61, depth=300.0, band=110, n_loops=25, loop_max=70),
+                dict(name="hs37d5", n=380, seed=62, depth=300.0, band=110, n_loops=20, loop_max=70),
+                dict(name="contig1", n=350, seed=63, depth=300.0, band=110, n_loops=20, loop_max=70),
+                dict(name="chrrDNA", n=330, seed=64, depth=300.0, band=110, n_loops=20, loop_max=70)],
+        train=dict(name="chrT", n=2000, seed=65, depth=300.0, band=110, n_loops=500, loop_max=70),
+        lower=6, upper=60, res=10000, w=5, weight="weight", min_prob=0.5,
+        forest=dict(n_estimators=20, max_depth=8, seed=6), store_inputs=False, full_taps=False,
+        genome=True, chroms_arg=[]),
+    # the 100,000-candidate batch rule (scoreUtils.py:104-108): ~340,000 candidates in four batches that keep
+    # 2 / 1 / 0 / 3 windows (tests/cases.py make_batchrule_chromosome); the reference drops the second batch's
+    # only window
+    "batchrule": dict(
+        chroms=[dict(name="chr7", n=14000, builder="batchrule")],
+        train=dict(name="chrT", n=2000, seed=12, depth=300.0, band=110, n_loops=500, loop_max=70),
+        lower=6, upper=300, res=10000, w=5, weight="weight", min_prob=0.5,
+        forest=dict(n_estimators=20, max_depth=8, seed=1), store_inputs=False, full_taps=False),
+    # BASELINE.json configs[1] at full size: the benchmark's chromosome (bench.py workload c2, seed 1234) and
+    # the benchmark's forest (bench_data/c2.pkl). Only checksums of the large taps are stored.
+    "c2": dict(
+        chroms=[dict(name="chr1", n=24900, seed=1234, depth=300.0, band=330)],
+        lower=6, upper=300, res=10000, w=5, weight="weight", min_prob=0.5,
+        forest=dict(pretrained="bench_data/c2"), store_inputs=False, full_taps=False, compact=True),
 }
 
 
 def build_chrom(spec):
+    if spec.get("builder") == "batchrule":
+        from tests.cases import make_batchrule_chromosome
+        return make_batchrule_chromosome(spec["name"], spec["n"])
     kw = {k: v for k, v in spec.items() if k not in ("name", "n")}
     return synth.make_chromosome(spec["name"], spec["n"], **kw)
 
@@ -168,12 +197,19 @@ def run_case(name):
     cool = os.path.join(tmp, name + ".pkcool")
     coolio.PKCool.write(cool, chroms, case["res"])
 
-    model, tshape = train_forest(case)
-    pkl = os.path.join(HERE, name + ".pkl")
-    joblib.dump(model, pkl, compress=("xz", 3))
-    ff = flatten_forest(model)
-    ff.save(os.path.join(HERE, name + "_forest.npz"))
-    print("   forest: trained on", tshape, "nodes", ff.n_nodes)
+    if "pretrained" in case["forest"]:
+        pkl = os.path.join(ROOT, case["forest"]["pretrained"] + ".pkl")
+        model = joblib.load(pkl)
+        ff = flatten_forest(model)
+        print("   forest: %s, nodes %d" % (case["forest"]["pretrained"], ff.n_nodes))
+    else:
+        model, tshape = train_forest(case)
+        pkl = os.path.join(HERE, name + ".pkl")
+        joblib.dump(model, pkl, compress=("xz", 3))
+        ff = flatten_forest(model)
+        ff.save(os.path.join(HERE, name + "_forest.npz"))
+        print("   forest: trained on", tshape, "nodes", ff.n_nodes)
+    compact = bool(case.get("compact"))
 
     out = {}
     meta = dict(case=case, checksums={c.name: c.checksum() for c in chroms},
@@ -195,8 +231,9 @@ def run_case(name):
         k = ch.name + "/"
         out[k + "exp_arr"] = np.asarray(X.exp_arr, dtype=np.float64)
         out[k + "background"] = np.asarray(X.background, dtype=np.float64)
-        out[k + "ridx"] = X.ridx.astype(np.int32)
-        out[k + "cidx"] = X.cidx.astype(np.int32)
+        if not compact:
+            out[k + "ridx"] = X.ridx.astype(np.int32)
+            out[k + "cidx"] = X.cidx.astype(np.int32)
         coords = [(r, c) for r, c in zip(X.ridx, X.cidx)]
         # taps (iii)/(iv) over ALL candidates in one call (no batching quirk here)
         fea, clist = X.getwindow(coords) if coords else (np.zeros((0, (2 * w + 1) ** 2)), np.zeros((0, 2)))
@@ -206,10 +243,13 @@ def run_case(name):
         proba = model.predict_proba(fea)[:, 1] if fea.shape[0] else np.zeros(0)
         leaves = np.stack([e.apply(fea32) for e in model.estimators_], axis=1).astype(np.int32) \
             if fea.shape[0] else np.zeros((0, len(model.estimators_)), np.int32)
-        out[k + "clist"] = clist.astype(np.int32)
-        out[k + "proba"] = proba
+        if not compact:
+            out[k + "clist"] = clist.astype(np.int32)
+            out[k + "proba"] = proba
         meta.setdefault("sha", {})[ch.name] = dict(fea64=sha(fea), fea32=sha(fea32), leaves=sha(leaves),
-                                                  n_windows=int(fea.shape[0]))
+                                                  n_windows=int(fea.shape[0]), n_candidates=int(X.ridx.size),
+                                                  ridx=sha(X.ridx.astype(np.int32)), cidx=sha(X.cidx.astype(np.int32)),
+                                                  clist=sha(clist.astype(np.int32)), proba=sha(proba))
         if case["full_taps"]:
             out[k + "fea64_head"] = fea[:128]      # float64 for the first 128 windows
             out[k + "fea32"] = fea32               # float32 (what the forest sees) for all
@@ -227,7 +267,7 @@ def run_case(name):
     buf = io.StringIO()
     with redirect_stdout(buf):
         if case.get("genome"):
-            ns.chroms = ["#", "X"]
+            ns.chroms = case.get("chroms_arg", ["#", "X"])
             score_genome.main(ns)
         else:
             ns.chrom = chroms[0].name
@@ -235,8 +275,18 @@ def run_case(name):
     meta["stdout"] = buf.getvalue()
     with open(bed) as fh:
         bedtxt = fh.read()
-    with open(os.path.join(HERE, name + ".bedpe"), "w") as fh:
-        fh.write(bedtxt)
+    meta["bedpe_sha"] = hashlib.sha256(bedtxt.encode()).hexdigest()
+    meta["bedpe_rows"] = bedtxt.count("\n")
+    if compact:
+        # the text is large: keep its checksum and the records (columns 2, 5 / res, 7, 8 of the text) instead
+        rows = [ln.split("\t") for ln in bedtxt.splitlines()]
+        out["records/x"] = np.array([int(r[1]) // case["res"] for r in rows], dtype=np.int32)
+        out["records/y"] = np.array([int(r[4]) // case["res"] for r in rows], dtype=np.int32)
+        out["records/prob"] = np.array([float(r[6]) for r in rows], dtype=np.float64)
+        out["records/value"] = np.array([float(r[7]) for r in rows], dtype=np.float64)
+    else:
+        with open(os.path.join(HERE, name + ".bedpe"), "w") as fh:
+            fh.write(bedtxt)
     print("   bedpe rows:", bedtxt.count("\n"))
 
     # tap (vi): pool
@@ -249,8 +299,12 @@ def run_case(name):
                 ptxt = fh.read()
         except Exception as e:  # the reference's clustering can fail on tiny inputs
             ptxt = "ERROR " + type(e).__name__
-        with open(os.path.join(HERE, "%s.pool_t%s.bedpe" % (name, thr)), "w") as fh:
-            fh.write(ptxt)
+        if compact:
+            meta.setdefault("pool_sha", {})[str(thr)] = hashlib.sha256(ptxt.encode()).hexdigest()
+            meta.setdefault("pool_rows", {})[str(thr)] = ptxt.count("\n")
+        else:
+            with open(os.path.join(HERE, "%s.pool_t%s.bedpe" % (name, thr)), "w") as fh:
+                fh.write(ptxt)
         print("   pool t=%s rows: %s" % (thr, ptxt.count("\n")))
 
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)

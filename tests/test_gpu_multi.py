@@ -29,18 +29,36 @@ def _run_torchrun(nproc, argv, tmp):
     return r
 
 
+def _score_genome_args(case, cool, out, chroms):
+    cfg = case.cfg
+    return ["score_genome", "-p", cool, "-m", case.pkl, "-O", out, "-r", str(cfg["res"]),
+            "-l", str(cfg["lower"]), "-u", str(cfg["upper"]), "--minimum-prob", str(cfg["min_prob"]),
+            "--clr-weight-name", cfg["weight"], "-C"] + chroms
+
+
 @pytest.mark.parametrize("name,chroms", [("genome", ["#", "X"]), ("c1", ["1"])])
 def test_score_genome_two_ranks(name, chroms, tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     case = Case(name)
-    cfg = case.cfg
     cool = case.write_cool(tmp_path)
     out = os.path.join(str(tmp_path), "multi.bedpe")
-    _run_torchrun(2, ["score_genome", "-p", cool, "-m", case.pkl, "-O", out, "-r", str(cfg["res"]),
-                      "-l", str(cfg["lower"]), "-u", str(cfg["upper"]), "--minimum-prob", str(cfg["min_prob"]),
-                      "--clr-weight-name", cfg["weight"], "-C"] + chroms, tmp_path)
+    _run_torchrun(2, _score_genome_args(case, cool, out, chroms), tmp_path)
+    assert open(out).read() == case.bedpe
+
+
+@pytest.mark.parametrize("name,chroms,world", [("genome", ["#", "X"], 2), ("c1", ["1"], 2), ("gnames", [], 3),
+                                               ("batchrule", [], 2), ("batchrule", [], 3)])
+def test_score_genome_ranks_sharing_one_device(name, chroms, world, tmp_path):
+    """The N-rank path of score_genome (plan, chromosome shards, band row tiles of a chromosome larger
+    than an even share, shared-memory gather, per-batch window sums over the tiles) with every rank on
+    device 0 (--device 0), so that it runs on a one-GPU box too. `batchrule` is a single chromosome: its
+    rows are tiled over the ranks and the 100,000-candidate batch rule is decided on the gathered counts."""
+    case = Case(name)
+    cool = case.write_cool(tmp_path)
+    out = os.path.join(str(tmp_path), "multi.bedpe")
+    _run_torchrun(world, _score_genome_args(case, cool, out, chroms) + ["--device", "0"], tmp_path)
     assert open(out).read() == case.bedpe
 
 

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.cases import ALL_CASES, FULL_TAP_CASES, Case
+from tests.cases import ALL_CASES, BIG_CASES, FULL_TAP_CASES, Case
 
 pytestmark = pytest.mark.gpu
 
@@ -46,6 +46,13 @@ def test_taps_match_reference_golden(name):
         sh = case.meta["sha"][ch.name]
         assert hashlib.sha256(np.ascontiguousarray(f64[keep]).tobytes()).hexdigest() == sh["fea64"]
         assert hashlib.sha256(np.ascontiguousarray(f32[keep]).tobytes()).hexdigest() == sh["fea32"]
+        # (iii) again, tapped INSIDE the product kernel: the float32 rows k_score_fused hands its forest walk
+        keep_f, f32_f = X.fused_window_features()
+        assert np.array_equal(keep_f, keep)
+        assert hashlib.sha256(np.ascontiguousarray(f32_f[keep_f]).tobytes()).hexdigest() == sh["fea32"]
+        assert not f32_f[~keep_f].any()
+        if name in FULL_TAP_CASES:
+            assert np.array_equal(f32_f[keep_f], case.z[k + "fea32"])
         # (iv) leaves + probabilities from the device forest on those rows
         xs = torch.from_numpy(np.ascontiguousarray(f32[keep])).cuda()
         leaves = torch.empty((xs.shape[0], case.forest.n_trees), dtype=torch.int32, device="cuda")
@@ -130,12 +137,22 @@ def test_bedpe_identical_to_reference(name, fused, tuning, tmp_path):
     ns = argparse.Namespace(path=cool, model=case.pkl, output=out, resolution=cfg["res"], lower=cfg["lower"],
                             upper=cfg["upper"], minimum_prob=cfg["min_prob"], clr_weight_name=cfg["weight"])
     if cfg.get("genome"):
-        ns.chroms = ["#", "X"]
+        ns.chroms = case.chroms_arg()
         score_genome.main(ns)
     else:
         ns.chrom = case.chroms[0].name
         score_chromosome.main(ns)
-    assert open(out).read() == case.bedpe                                        # (v)
+    txt = open(out).read()
+    assert txt == case.bedpe                                                     # (v)
+    # (vi) `peakachu pool` stays on the host and reads this text; the reference's pooled loops of the
+    # golden bedpe are rows of OUR output, field for field (peakacluster re-prints prob and value)
+    rows = {tuple(ln.split("\t")[i] for i in (0, 1, 4)): ln.split("\t")[6:8] for ln in txt.splitlines()}
+    for thr in (0.9, cfg["min_prob"]):
+        for ln in case.pool(thr).splitlines():
+            if ln.startswith("ERROR"):
+                continue
+            f = ln.split("\t")
+            assert rows[(f[0], f[1], f[4])] == f[6:8]
 
 
 @pytest.mark.parametrize("name,group", [("tiny", ""), ("tiny_raw", ""), ("genome", "resolutions/10000")])
@@ -668,6 +685,82 @@ def test_full_size_c2_properties():
     C_ = sparse.csr_matrix((ch.count, (ch.bin1, ch.bin2)), shape=(n, n))
     cnt = np.asarray(C_[x, y]).ravel()
     assert np.array_equal(v, (ch.weights[x] * ch.weights[y]) * cnt)
+
+
+@pytest.mark.parametrize("name", BIG_CASES)
+def test_full_size_matches_reference(name, tmp_path):
+    """BASELINE configs[1] at full size against the REFERENCE's own run on the same map and forest
+    (tests/golden/c2.*, made by make_golden.py): expected curve bit for bit; candidate list, kept windows,
+    float32 features (separate kernel and the tap inside the fused kernel), probabilities of every window
+    and the bedpe text by checksum; the records column by column."""
+    import hashlib
+    from peakachu_b200 import score_chromosome
+    from peakachu_b200.scoreUtils import DeviceForest
+
+    def sha(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    case = Case(name)
+    cfg, ch = case.cfg, case.chroms[0]
+    sh = case.meta["sha"][ch.name]
+    X = _gpu_chromosome(case, ch, DeviceForest.of(case.forest, 0))
+    assert np.array_equal(X.exp_arr, case.z[ch.name + "/exp_arr"])
+    assert X.ridx.size == sh["n_candidates"]
+    assert sha(X.ridx.astype(np.int32)) == sh["ridx"] and sha(X.cidx.astype(np.int32)) == sh["cidx"]
+    keep, f32 = X.window_features()
+    assert int(keep.sum()) == sh["n_windows"]
+    clist = np.stack([X.ridx[keep], X.cidx[keep]], axis=1).astype(np.int32)
+    assert sha(clist) == sh["clist"]
+    assert sha(f32[keep]) == sh["fea32"]
+    keep_f, f32_f = X.fused_window_features()
+    assert np.array_equal(keep_f, keep) and sha(f32_f[keep_f]) == sh["fea32"]
+    del f32, f32_f
+    x, y, p, v = X.score_records(-1.0)                 # every window's probability, (x, y) order
+    order = np.lexsort((clist[:, 1], clist[:, 0]))
+    assert np.array_equal(x, clist[order, 0]) and np.array_equal(y, clist[order, 1])
+    back = np.empty_like(p)
+    back[order] = p                                    # back to the reference's window order
+    assert sha(back) == sh["proba"]
+    x, y, p, v = X.score_records(cfg["min_prob"])
+    assert np.array_equal(x, case.z["records/x"]) and np.array_equal(y, case.z["records/y"])
+    assert np.array_equal(p, case.z["records/prob"]) and np.array_equal(v, case.z["records/value"])
+    X.close()
+    out = os.path.join(str(tmp_path), "gpu.bedpe")
+    score_chromosome.main(argparse.Namespace(path=case.write_cool(tmp_path), model=case.pkl, output=out,
+                                             resolution=cfg["res"], lower=cfg["lower"], upper=cfg["upper"],
+                                             minimum_prob=cfg["min_prob"], clr_weight_name=cfg["weight"],
+                                             chrom=ch.name))
+    txt = open(out).read()
+    assert hashlib.sha256(txt.encode()).hexdigest() == case.meta["bedpe_sha"]
+
+
+def test_batch_rule_whole_chromosome_and_row_tiles():
+    """scoreUtils.py:104-108 on the fixture made for it (> 340,000 candidates; four reference batches keep
+    2 / 1 / 0 / 3 windows): the whole-chromosome pass drops the lone window of the second batch on the
+    device; with three row tiles the two windows of the first batch fall into different tiles, so each tile
+    alone sees one -- only the per-batch sum over the tiles keeps them. Both give the reference's bedpe."""
+    from peakachu_b200 import shard
+
+    class OneChrom:
+        def __init__(self, ch): self.ch = ch
+        def upper_pixels(self, k): return self.ch.bin1, self.ch.bin2, self.ch.count
+        def weights(self, k, name): return self.ch.weights
+        def nbins(self, k): return self.ch.n
+
+    case = Case("batchrule")
+    cfg, ch = case.cfg, case.chroms[0]
+    lib = OneChrom(ch)
+    kw = dict(correct="weight", lower=cfg["lower"], upper=cfg["upper"], res=cfg["res"], device=0,
+              min_prob=cfg["min_prob"])
+    whole = shard.score_units(lib, [(ch.name, 0, ch.n)], case.forest, **kw)
+    assert whole[ch.name][0]["batch_windows"].tolist() == [2, 1, 0, 3]
+    assert whole[ch.name][0]["x"].size == 5                        # rule applied on the device
+    edges = [0, 4666, 9333, ch.n]
+    tiles = shard.score_units(lib, [(ch.name, a, b) for a, b in zip(edges[:-1], edges[1:])], case.forest, **kw)
+    per_tile = [q["batch_windows"].tolist() for q in sorted(tiles[ch.name], key=lambda q: q["row_begin"])]
+    assert per_tile == [[1, 0, 0, 1], [0, 1, 0, 1], [1, 0, 0, 1]]
+    assert sum(q["x"].size for q in tiles[ch.name]) == 6           # a tile cannot apply the rule alone
+    for res_ in (whole, tiles):
+        assert shard.assemble_text([ch.name], [res_], cfg["res"])[ch.name] == case.bedpe
 
 
 @pytest.mark.gpu

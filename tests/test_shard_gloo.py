@@ -61,6 +61,37 @@ def _worker(rank, world, port, tmp):
     dist.destroy_process_group()
 
 
+def _worker_early_exit(rank, world, port, tmp):
+    """Rank 1 publishes one pass and leaves at once (no barrier, as the torchrun CLI path does); rank 0
+    turns up a second later. Rank 1's exit hook must keep its data segment alive until rank 0 has read it."""
+    import time
+
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shard._setup_shm(rank, world, shard._host_group())          # the one collective of the gather
+    assert shard._SHM["mode"] == "shm"
+    payload = dict(c=[dict(row_begin=0, junk=np.arange(300000, dtype=np.int64) + rank)])
+    if rank == 0:
+        time.sleep(1.0)
+    gathered = shard.gather_to_rank0(payload, rank, world)
+    if rank == 0:
+        assert np.array_equal(gathered[1]["c"][0]["junk"], np.arange(300000, dtype=np.int64) + 1)
+        open(os.path.join(tmp, "ok"), "w").write("ok")
+    # no barrier: a non-zero rank returns immediately and its atexit hook runs
+    if rank != 0:
+        shard._release_shm()
+
+
+def test_rank_that_exits_right_after_the_gather_keeps_its_segment(tmp_path):
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker_early_exit, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(os.path.join(str(tmp_path), "ok"))
+
+
 @pytest.mark.parametrize("how", ["shm", "pickle"])
 def test_two_rank_gather_reproduces_bedpe(tmp_path, how, monkeypatch):
     """Both host gathers: numpy columns through shared memory (one node) and pickled objects."""
