@@ -106,6 +106,22 @@ int pk_chrom_upload_csr(pk_chrom* c, const int64_t* bin1_offset, const int32_t* 
  * at the whole matrix. */
 int pk_chrom_upload_csr16(pk_chrom* c, const int64_t* bin1_offset, const uint16_t* bin2_delta, const uint16_t* count,
                           int64_t nnz, const double* weights, int mem);
+/* Packed pixel rows: the whole chromosome in ONE contiguous blob, about 1.3 bytes per band pixel
+ * on a dense map (peakachu_b200/rowpack.py writes and reads it; coolio.PKCool stores it). Little
+ * endian, every section 16-byte aligned, offsets from the start of the blob:
+ *   header  int64[16]: PK_ROWS_MAGIC, n_bins, nd_enc, words_per_row = ceil(nd_enc / 32), nnz_band, n_esc,
+ *                      n_far, off_bits, off_cnt_off, off_cnt8, off_esc, off_far_off, off_far_b2,
+ *                      off_far_cnt, total_bytes, 0
+ *   bits    uint32[n_bins][words_per_row]  bit d of row x: pixel (x, x + d) is present (d < nd_enc)
+ *   cnt_off uint32[n_bins + 1]             first count byte of each row
+ *   cnt8    uint8[nnz_band]                counts in (row, distance) order; 255 = see `esc`
+ *   esc     int32[3][n_esc]                x | d | count of the pixels with count >= 255
+ *   far_off int64[n_bins + 1], far_b2 int32[n_far], far_cnt int32[n_far]
+ *                                          pixels with d >= nd_enc as CSR columns: they never enter the
+ *                                          band but decide the `valid` mask (utils.py:146-156) and `depth`
+ * nd_enc must cover the band: nd_enc >= upper + 2w + 1 (effective upper). No duplicates by construction. */
+#define PK_ROWS_MAGIC 0x31524B50LL
+int pk_chrom_upload_rows(pk_chrom* c, const void* blob, int64_t bytes, const double* weights, int mem);
 /* `peakachu depth` (calculate_depth.py:25-28): sum of the raw counts of the pixels of the last
  * upload with bin2 - bin1 >= min_dis_bins. Columns passed as device pointers must still be alive. */
 int pk_chrom_depth(pk_chrom* c, int32_t min_dis_bins, int64_t* total);
@@ -163,6 +179,44 @@ int pk_chrom_batch_windows(pk_chrom* c, int64_t* out, int64_t capacity, int64_t*
  * mem = PK_MEM_DEVICE: device-to-device copy in emission order (unsorted). */
 int pk_chrom_fetch_results(pk_chrom* c, int32_t* out_x, int32_t* out_y, double* out_prob,
                            double* out_val, int32_t* out_batch, int64_t capacity, int mem);
+
+/* ---- engine: the chromosome loop of score_genome.main (score_genome.py:46-84) as a persistent
+ * per-device pipeline. Streams, chromosome handles and pinned staging are created once and reused;
+ * pk_engine_submit queues one unit -- a chromosome, or rows [row_begin, row_end) of one (the
+ * multi-GPU row-tile seam) -- and never waits for the device; pk_engine_collect waits for all queued
+ * units, in submission order, and exposes their records. One host thread per engine.
+ * Unit columns are HOST arrays (pinned memory makes the uploads asynchronous); they must stay alive
+ * until pk_engine_collect returns. */
+typedef struct pk_engine pk_engine;
+#define PK_ENC_COO   0   /* a = bin1 int32[size], b = bin2 int32[size], c = count int32[size], cooler order */
+#define PK_ENC_CSR32 1   /* a = bin1_offset int64[n_bins+1], b = bin2 int32[size], c = count int32[size] */
+#define PK_ENC_CSR16 2   /* a = bin1_offset int64[n_bins+1], b = (bin2 - bin1) uint16[size], c = count uint16[size] */
+#define PK_ENC_ROWS  3   /* a = packed rows blob (pk_chrom_upload_rows), size = its bytes */
+typedef struct pk_unit {
+    int64_t tag;                 /* returned with the results */
+    int32_t n_bins, row_begin, row_end, encoding;
+    const void *a, *b, *c;
+    int64_t size;
+    const double* weights;       /* NULL: raw mode */
+    double min_prob;
+} pk_unit;
+typedef struct pk_unit_result {
+    int64_t tag;
+    int32_t n_bins, row_begin, row_end, whole;
+    int64_t n_records, n_candidates, n_windows, n_batches;
+    /* records ordered by (x, y); pinned memory owned by the engine, valid until the next pk_engine_submit */
+    const int32_t *x, *y, *batch;
+    const double *prob, *value;
+    const int32_t* batch_windows;   /* [n_batches] surviving windows per reference batch (see pk_chrom_score) */
+} pk_unit_result;
+/* depth: chromosomes in flight (uploads of the next ones overlap the kernels of the current one) */
+int pk_engine_create(int device, pk_forest* f, int32_t width, int32_t lower, int32_t upper, int depth, pk_engine** out);
+int pk_engine_destroy(pk_engine* e);
+int pk_engine_submit(pk_engine* e, const pk_unit* u);
+/* out == NULL: only the number of queued units. */
+int pk_engine_collect(pk_engine* e, pk_unit_result* out, int64_t capacity, int64_t* n_units);
+/* after a failed submit / collect: wait for the device and drop the queued units */
+int pk_engine_reset(pk_engine* e);
 
 /* ---- Poisson decision table: crit[k] = smallest float64 mu with
  * Pr[Poisson(mu) > k] >= 0.01, so that `p < 0.01` <=> `mu < crit[k]`

@@ -16,12 +16,30 @@ LIB_PATH = os.environ.get("PEAKACHU_B200_LIB") or os.path.join(_HERE, "libpeakac
 
 PK_MEM_HOST, PK_MEM_DEVICE = 0, 1
 PK_PIXELS_SORTED = 0x100
+PK_ENC_COO, PK_ENC_CSR32, PK_ENC_CSR16, PK_ENC_ROWS = 0, 1, 2, 3
 
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
 c_f64p = C.POINTER(C.c_double)
 c_f32p = C.POINTER(C.c_float)
 c_u8p = C.POINTER(C.c_uint8)
+
+
+
+class Unit(C.Structure):
+    """pk_unit (include/peakachu_b200.h)."""
+    _fields_ = [("tag", C.c_int64), ("n_bins", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32),
+                ("encoding", C.c_int32), ("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p),
+                ("size", C.c_int64), ("weights", C.c_void_p), ("min_prob", C.c_double)]
+
+
+class UnitResult(C.Structure):
+    """pk_unit_result (include/peakachu_b200.h)."""
+    _fields_ = [("tag", C.c_int64), ("n_bins", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32),
+                ("whole", C.c_int32), ("n_records", C.c_int64), ("n_candidates", C.c_int64),
+                ("n_windows", C.c_int64), ("n_batches", C.c_int64), ("x", C.c_void_p), ("y", C.c_void_p),
+                ("batch", C.c_void_p), ("prob", C.c_void_p), ("value", C.c_void_p), ("batch_windows", C.c_void_p)]
+
 
 # name -> (restype, argtypes); every symbol declared in include/peakachu_b200.h
 SIGNATURES = {
@@ -41,6 +59,12 @@ SIGNATURES = {
     "pk_chrom_upload_pixels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "pk_chrom_upload_csr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "pk_chrom_upload_csr16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    "pk_chrom_upload_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    "pk_engine_create": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int, C.POINTER(C.c_void_p)]),
+    "pk_engine_destroy": (C.c_int, [C.c_void_p]),
+    "pk_engine_submit": (C.c_int, [C.c_void_p, C.POINTER(Unit)]),
+    "pk_engine_collect": (C.c_int, [C.c_void_p, C.POINTER(UnitResult), C.c_int64, c_i64p]),
+    "pk_engine_reset": (C.c_int, [C.c_void_p]),
     "pk_release_memory": (C.c_int, []),
     "pk_format_bedpe": (C.c_int, [C.c_char_p, C.c_int64, c_i32p, c_i32p, c_f64p, c_f64p, C.c_int64, C.c_char_p,
                                   C.c_int64, c_i64p]),

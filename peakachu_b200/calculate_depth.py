@@ -11,13 +11,19 @@ from . import _lib, coolio
 
 def chromosome_depth(pixels, n_bins, min_dis_bins=0, device=0):
     """Sum of the counts of one chromosome's upper-triangle pixels with bin2 - bin1 >= min_dis_bins.
-    ``pixels``: (bin1_offset, bin2 - bin1 uint16, count uint16), (bin1_offset, bin2, count) or
-    (bin1, bin2, count) as the ``coolio`` readers return them."""
+    ``pixels``: a packed-rows blob, (bin1_offset, bin2 - bin1 uint16, count uint16), (bin1_offset, bin2,
+    count) or (bin1, bin2, count) as the ``coolio`` readers return them."""
     L = _lib.lib()
     _lib.require_device()
     h = C.c_void_p()
     _lib.check(L.pk_chrom_create(device, int(n_bins), 5, 6, 1, 0, None, C.byref(h)))
     try:
+        if isinstance(pixels, np.ndarray):                     # packed pixel rows (rowpack)
+            blob = _lib.as_c(pixels, np.uint8)
+            _lib.check(L.pk_chrom_upload_rows(h, _lib.ptr(blob), blob.size, None, _lib.PK_MEM_HOST))
+            tot = C.c_int64()
+            _lib.check(L.pk_chrom_depth(h, int(min_dis_bins), C.byref(tot)))
+            return int(tot.value)
         a, b, c = pixels
         if np.asarray(b).dtype == np.uint16:
             a, b, c = _lib.as_c(a, np.int64), _lib.as_c(b, np.uint16), _lib.as_c(c, np.uint16)
@@ -58,8 +64,11 @@ def main(args):
     totals = 0
     for k in Lib.chromnames:
         print(k)
-        narrow = Lib.upper_pixels_csr16(k) if hasattr(Lib, "upper_pixels_csr16") else None
-        pixels = narrow if narrow is not None else Lib.upper_pixels(k)
+        pixels = Lib.upper_pixels_rows(k, 0) if hasattr(Lib, "upper_pixels_rows") else None
+        if pixels is None:
+            pixels = Lib.upper_pixels_csr16(k) if hasattr(Lib, "upper_pixels_csr16") else None
+        if pixels is None:
+            pixels = Lib.upper_pixels(k)
         totals += chromosome_depth(pixels, Lib.nbins(k), mindis, device)
     print("num of intra reads in your data:", totals)
     matched_read_num = 3031042417 / genome_size * totals                   # calculate_depth.py:42

@@ -56,6 +56,9 @@ class PKCool:
         # pixel is representable: half the bytes to move to the GPU
         self.delta16 = z["delta16"] if "delta16" in z.files else None
         self.count16 = z["count16"] if "count16" in z.files else None
+        # optional packed pixel rows, one blob per chromosome (peakachu_b200.rowpack): what crosses the bus
+        self.rows_nd = int(z["rows_nd"]) if "rows_nd" in z.files else 0
+        self._rows = {int(k[len("rows_"):]): z[k] for k in z.files if k.startswith("rows_") and k != "rows_nd"}
         self.weight_columns = {k[len("bins_"):]: z[k] for k in z.files if k.startswith("bins_")}
         # pixel range of each chromosome (bin1 sorted, intra-chromosomal only)
         self._pix_lo = np.searchsorted(self.bin1_id, self.chrom_offset[:-1], side="left")
@@ -63,9 +66,12 @@ class PKCool:
 
     # -- writer -----------------------------------------------------------
     @staticmethod
-    def write(path: str, chroms, binsize: int, weight_name: str = "weight") -> None:
+    def write(path: str, chroms, binsize: int, weight_name: str = "weight", rows_nd: int = 352) -> None:
         """chroms: iterable of synth.SynthChrom-like objects
-        (name, n, bin1, bin2, count, weights)."""
+        (name, n, bin1, bin2, count, weights). ``rows_nd`` > 0 also stores every chromosome as packed
+        pixel rows covering that many distances (enough for ``--upper 300`` with windows up to 25 x 25;
+        a run that needs more distances falls back to the plain columns)."""
+        from . import rowpack
         chroms = list(chroms)
         names = np.array([c.name for c in chroms])
         nb = np.array([c.n for c in chroms], dtype=np.int64)
@@ -77,6 +83,14 @@ class PKCool:
         extra = {}
         if b1.size and int((b2 - b1).max()) <= 65535 and int(cnt.max()) <= 65535 and int(cnt.min()) >= 0:
             extra = dict(delta16=(b2 - b1).astype(np.uint16), count16=cnt.astype(np.uint16))
+        if rows_nd and rows_nd > 0:
+            extra["rows_nd"] = np.int64(rows_nd)
+            for i, c in enumerate(chroms):
+                order = np.lexsort((c.bin2, c.bin1))
+                cb1 = np.asarray(c.bin1)[order]
+                rp = np.searchsorted(cb1, np.arange(c.n + 1), side="left").astype(np.int64)
+                extra["rows_%d" % i] = rowpack.pack_rows(rp, np.asarray(c.bin2)[order], np.asarray(c.count)[order],
+                                                         c.n, rows_nd)
         with open(path, "wb") as fh:
             np.savez(fh, binsize=np.int64(binsize), chrom_names=names,
                      chrom_lengths=nb * binsize, chrom_offset=off,
@@ -126,6 +140,13 @@ class PKCool:
         n = self.nbins(chrom)
         rp = np.searchsorted(self.bin1_id[lo:hi], np.arange(off, off + n + 1), side="left").astype(np.int64)
         return rp, np.ascontiguousarray(self.delta16[lo:hi]), np.ascontiguousarray(self.count16[lo:hi])
+
+    def upper_pixels_rows(self, chrom: str, nd_min: int):
+        """Packed pixel rows of the chromosome (uint8 blob for ``pk_chrom_upload_rows``) when the
+        container holds them and they cover ``nd_min`` distances, else None."""
+        if self.rows_nd < nd_min:
+            return None
+        return self._rows.get(self._cid(chrom))
 
     def weights(self, chrom: str, name: str) -> np.ndarray:
         if name not in self.weight_columns:

@@ -16,6 +16,7 @@
 // launchers implemented in pk_kernels.cu / pk_stages.cu / pk_fused.cu
 int pk_launch_scatter(pk_chrom* c, const int32_t* b1, const int32_t* b2, const int32_t* cnt, int64_t nnz);
 int pk_launch_band_csr(pk_chrom* c, const long long* rowptr, const void* b2, const void* cnt, int enc);
+int pk_launch_band_rows(pk_chrom* c);
 int pk_launch_rowptr(pk_chrom* c, const int32_t* b1, const int32_t* b2, int64_t nnz, long long* rowptr);
 int pk_launch_diag_sums(pk_chrom* c);
 bool pk_fit_on_device_supported(int len);
@@ -26,12 +27,8 @@ int pk_launch_forest(const pk_forest* f, const float* X, const uint8_t* keep, in
                      double* proba, cudaStream_t stream);
 int pk_launch_emit(pk_chrom* c, double thre);
 int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms, int child_features, float* fea_tap);
-size_t pk_sort_temp_bytes(long long n);
 int pk_launch_sort_records_eager(pk_chrom* c, long long M);
 int pk_launch_depth(pk_chrom* c, int32_t min_dis, unsigned long long* d_total);
-int pk_launch_sort_records(pk_chrom* c, long long n, unsigned long long* keys_in, unsigned long long* keys_out,
-                           uint32_t* idx_in, uint32_t* idx_out, void* temp, size_t temp_bytes, unsigned char* packed,
-                           long long off_f64, int key_bits);
 bool pk_fused_supported(int w, int n_trees);
 
 int pk_run_selftest_divide(long long n, unsigned long long seed, long long* mismatches);
@@ -46,7 +43,6 @@ extern "C" int pk_selftest_divide(int device, int64_t n, uint64_t seed, int64_t*
 }
 
 // tuning knobs (pk_set_tuning): fused = -1 auto, 0 unfused kernels, 1 + v: fused kernel variant v
-static const int64_t PK_EAGER_RECORDS = 1 << 17;   // records sorted behind the scoring pass; more fall back to a sort at fetch time
 static int g_tune_fused = -1;
 static int g_tune_prune = 1;
 static int g_tune_cf = -1;       // fused forest walk on the child-feature node encoding: -1 where measured faster (w = 7), 0 off, 1 on
@@ -470,11 +466,20 @@ extern "C" int pk_chrom_create(int device, int32_t n_bins, int32_t width, int32_
         (r = dev_alloc(&c->d_scratch, bandsz)) ||
         (r = dev_alloc(&c->d_diag_sum, (size_t)c->ND)) || (r = dev_alloc(&c->d_diag_cnt, (size_t)c->ND)) ||
         (r = dev_alloc(&c->d_exp, (size_t)c->ND)) || (r = dev_alloc(&c->d_bg, (size_t)c->ND)) ||
-        (r = dev_alloc(&c->d_flags, 4)) || (r = dev_alloc(&c->d_counters, 4)) || (r = dev_alloc(&c->d_ncand, 2)) ||
         (r = dev_alloc(&c->d_rowptr, (size_t)n_bins + 1))) {
         pk_chrom_destroy(c);
         return r;
     }
+    // Everything the host reads back after a scoring pass sits in one block, so that one copy fetches it:
+    // flags int32[4] | candidate totals int64[2] | counters uint64[4] | surviving windows per reference batch int32[nb]
+    // (batches are numbered over the whole chromosome's candidates: at most the band pixels)
+    c->batch_cap = band_pixels_of(c) / PK_BATCH + 2;
+    c->head_bytes = 64 + 4 * (size_t)c->batch_cap;
+    if ((r = dev_alloc(&c->d_head, c->head_bytes))) { pk_chrom_destroy(c); return r; }
+    c->d_flags = reinterpret_cast<int32_t*>(c->d_head);
+    c->d_ncand = reinterpret_cast<long long*>(c->d_head + 16);
+    c->d_counters = reinterpret_cast<unsigned long long*>(c->d_head + 32);
+    c->d_batch_win = reinterpret_cast<int32_t*>(c->d_head + 64);
     for (auto& e : c->ev) {
         if (cudaEventCreate(&e) != cudaSuccess) { pk_set_error("cudaEventCreate failed"); pk_chrom_destroy(c); return PK_ECUDA; }
     }
@@ -488,12 +493,13 @@ extern "C" int pk_chrom_destroy(pk_chrom* c) {
     if (c->stream) cudaStreamSynchronize(c->stream); else cudaDeviceSynchronize();
     dev_free(c->d_band); dev_free(c->d_w); dev_free(c->d_valid); dev_free(c->d_vbits); dev_free(c->d_scratch);
     dev_free(c->d_diag_sum); dev_free(c->d_diag_cnt);
-    dev_free(c->d_exp); dev_free(c->d_bg); dev_free(c->d_flags); dev_free(c->d_counters); dev_free(c->d_ncand);
+    dev_free(c->d_exp); dev_free(c->d_bg); dev_free(c->d_head);
+    c->d_flags = nullptr; c->d_counters = nullptr; c->d_ncand = nullptr; c->d_batch_win = nullptr;
     dev_free(c->d_rowptr);
-    dev_free(c->d_b1); dev_free(c->d_b2); dev_free(c->d_cnt);
+    dev_free(c->d_b1); dev_free(c->d_b2); dev_free(c->d_cnt); dev_free(c->d_blob_own);
     dev_free(c->d_cnt_all); dev_free(c->d_cnt_tile); dev_free(c->d_off_all); dev_free(c->d_off_tile); dev_free(c->d_bits);
     dev_free(c->d_cx); dev_free(c->d_cd); dev_free(c->d_crank);
-    dev_free(c->d_keep); dev_free(c->d_fea32); dev_free(c->d_prob); dev_free(c->d_batch_win);
+    dev_free(c->d_keep); dev_free(c->d_fea32); dev_free(c->d_prob);
     dev_free(c->d_rx); dev_free(c->d_ry); dev_free(c->d_rb); dev_free(c->d_rp); dev_free(c->d_rv);
     if (c->ev_x) cudaEventDestroy(c->ev_x);
     dev_free(c->d_rowcnt); dev_free(c->d_rowoff); dev_free(c->d_rrank); dev_free(c->d_perm); dev_free(c->d_packed);
@@ -546,9 +552,9 @@ static int reserve_staging(pk_chrom* c, int64_t nnz, bool need_b1) {
 
 static int after_band(pk_chrom* c) {
     cudaStream_t s = c->stream;
-    PK_CUDA(cudaEventRecord(c->ev[1], s));
+    if (c->timing) PK_CUDA(cudaEventRecord(c->ev[1], s));
     PK_CHECK(pk_launch_diag_sums(c));
-    PK_CUDA(cudaEventRecord(c->ev[2], s));
+    if (c->timing) PK_CUDA(cudaEventRecord(c->ev[2], s));
     c->has_pixels = true; c->has_expected = false; c->has_candidates = false; c->has_scores = false;
     return PK_OK;
 }
@@ -571,7 +577,7 @@ extern "C" int pk_chrom_upload_pixels(pk_chrom* c, const int32_t* bin1, const in
     if (c->balanced)
         PK_CUDA(cudaMemcpyAsync(c->d_w, weights, (size_t)c->n * sizeof(double),
                                 mem == PK_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
-    PK_CUDA(cudaEventRecord(c->ev[0], s));
+    if (c->timing) PK_CUDA(cudaEventRecord(c->ev[0], s));
     PK_CUDA(cudaMemsetAsync(c->d_valid, 0, (size_t)c->n, s));
     PK_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int32_t), s));
     c->declared_sorted = sorted;
@@ -606,7 +612,7 @@ extern "C" int pk_chrom_upload_csr(pk_chrom* c, const int64_t* bin1_offset, cons
     if (c->balanced)
         PK_CUDA(cudaMemcpyAsync(c->d_w, weights, (size_t)c->n * sizeof(double),
                                 mem == PK_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
-    PK_CUDA(cudaEventRecord(c->ev[0], s));
+    if (c->timing) PK_CUDA(cudaEventRecord(c->ev[0], s));
     PK_CUDA(cudaMemsetAsync(c->d_valid, 0, (size_t)c->n, s));
     PK_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int32_t), s));
     c->declared_sorted = false;      // row offsets given: nothing to verify
@@ -637,12 +643,60 @@ extern "C" int pk_chrom_upload_csr16(pk_chrom* c, const int64_t* bin1_offset, co
     if (c->balanced)
         PK_CUDA(cudaMemcpyAsync(c->d_w, weights, (size_t)c->n * sizeof(double),
                                 mem == PK_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
-    PK_CUDA(cudaEventRecord(c->ev[0], s));
+    if (c->timing) PK_CUDA(cudaEventRecord(c->ev[0], s));
     PK_CUDA(cudaMemsetAsync(c->d_valid, 0, (size_t)c->n, s));
     PK_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int32_t), s));
     c->declared_sorted = false;
     c->up_kind = 3; c->up_b1 = nullptr; c->up_b2 = p2; c->up_cnt = pc; c->up_rowptr = rp; c->up_nnz = nnz;
     PK_CHECK(pk_launch_band_csr(c, rp, p2, pc, 1));
+    return after_band(c);
+}
+
+// Packed pixel rows (one contiguous blob, layout in the header file): a chromosome crosses the bus in one copy.
+extern "C" int pk_chrom_upload_rows(pk_chrom* c, const void* blob, int64_t bytes, const double* weights, int mem) {
+    if (!c || !blob || bytes < 128) { pk_set_error("pk_chrom_upload_rows: bad argument"); return PK_EINVAL; }
+    if (c->balanced && !weights) { pk_set_error("pk_chrom_upload_rows: balanced mode needs weights"); return PK_EINVAL; }
+    mem &= ~PK_PIXELS_SORTED;
+    PK_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    long long* h = c->rows_hdr;
+    if (mem == PK_MEM_HOST) memcpy(h, blob, 128);
+    else PK_CUDA(cudaMemcpy(h, blob, 128, cudaMemcpyDeviceToHost));
+    if (h[0] != PK_ROWS_MAGIC) { pk_set_error("pk_chrom_upload_rows: not a packed-rows blob"); return PK_EINVAL; }
+    if (h[1] != c->n) { pk_set_error("pk_chrom_upload_rows: blob holds %lld bins, the handle %d", h[1], c->n); return PK_EINVAL; }
+    if (h[2] < c->ND) {
+        pk_set_error("pk_chrom_upload_rows: blob packs %lld distances, the band needs upper + 2w + 1 = %d", h[2], c->ND);
+        return PK_EINVAL;
+    }
+    if (h[14] > bytes || h[3] != (h[2] + 31) / 32 || h[4] < 0 || h[5] < 0 || h[6] < 0) {
+        pk_set_error("pk_chrom_upload_rows: inconsistent header"); return PK_EINVAL;
+    }
+    const long long n1 = (long long)c->n + 1;
+    const long long need[7] = {h[7] + 4 * h[3] * c->n, h[8] + 4 * n1, h[9] + h[4], h[10] + 12 * h[5], h[11] + 8 * n1,
+                               h[12] + 4 * h[6], h[13] + 4 * h[6]};
+    for (int i = 0; i < 7; ++i)
+        if (h[7 + i] < 128 || (h[7 + i] & 15) || need[i] > h[14]) { pk_set_error("pk_chrom_upload_rows: section %d out of bounds", i); return PK_EINVAL; }
+    if (mem == PK_MEM_HOST) {
+        if (h[14] > c->blob_cap || !c->d_blob_own) {
+            if (c->d_blob_own) PK_CHECK(quiesce(c));
+            dev_free(c->d_blob_own);
+            PK_CHECK(dev_alloc(&c->d_blob_own, (size_t)h[14] + (size_t)h[14] / 8));
+            c->blob_cap = h[14] + h[14] / 8;
+        }
+        PK_CUDA(cudaMemcpyAsync(c->d_blob_own, blob, (size_t)h[14], cudaMemcpyHostToDevice, s));
+        c->d_blob = c->d_blob_own;
+    } else {
+        c->d_blob = (unsigned char*)blob;
+    }
+    if (c->balanced)
+        PK_CUDA(cudaMemcpyAsync(c->d_w, weights, (size_t)c->n * sizeof(double),
+                                mem == PK_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    if (c->timing) PK_CUDA(cudaEventRecord(c->ev[0], s));
+    PK_CUDA(cudaMemsetAsync(c->d_valid, 0, (size_t)c->n, s));
+    PK_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int32_t), s));
+    c->declared_sorted = false;
+    c->up_kind = 4; c->up_b1 = nullptr; c->up_b2 = nullptr; c->up_cnt = nullptr; c->up_rowptr = nullptr; c->up_nnz = h[4] + h[6];
+    PK_CHECK(pk_launch_band_rows(c));
     return after_band(c);
 }
 
@@ -685,7 +739,7 @@ extern "C" int pk_chrom_fit_expected(pk_chrom* c) {
     if (!c) { pk_set_error("pk_chrom_fit_expected: NULL handle"); return PK_EINVAL; }
     if (!c->has_pixels) { pk_set_error("pk_chrom_fit_expected: no pixels uploaded"); return PK_ESTATE; }
     PK_CUDA(cudaSetDevice(c->device));
-    PK_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    if (c->timing) PK_CUDA(cudaEventRecord(c->ev[3], c->stream));
     if (pk_fit_on_device_supported(c->ND)) {
         PK_CHECK(pk_launch_fit_expected(c));      // stays on the stream; a failed fit raises flags[2]
     } else {
@@ -699,7 +753,7 @@ extern "C" int pk_chrom_fit_expected(pk_chrom* c) {
         PK_CUDA(cudaMemcpyAsync(c->d_bg, e.data(), (size_t)c->ND * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         PK_CUDA(cudaStreamSynchronize(c->stream));
     }
-    PK_CUDA(cudaEventRecord(c->ev[4], c->stream));
+    if (c->timing) PK_CUDA(cudaEventRecord(c->ev[4], c->stream));
     c->has_expected = true; c->has_candidates = false; c->has_scores = false;
     return PK_OK;
 }
@@ -754,7 +808,7 @@ static int reserve_candidates(pk_chrom* c, int64_t want) {
 static int run_candidates(pk_chrom* c, int32_t kmin) {
     cudaStream_t s = c->stream;
     const int nd = c->upper - c->lower + 1;
-    PK_CUDA(cudaEventRecord(c->ev[5], s));
+    if (c->timing) PK_CUDA(cudaEventRecord(c->ev[5], s));
     PK_CUDA(cudaMemsetAsync(c->d_ncand, 0, 2 * sizeof(long long), s));
     if (nd > 0) {
         c->n_chunks = (c->n + 1023) / 1024;
@@ -772,7 +826,7 @@ static int run_candidates(pk_chrom* c, int32_t kmin) {
         PK_CHECK(pk_poisson_table_device(c->device, kmin, &d_crit, &kmax));
         PK_CHECK(pk_launch_candidates(c, d_crit, kmax));
     }
-    PK_CUDA(cudaEventRecord(c->ev[6], s));
+    if (c->timing) PK_CUDA(cudaEventRecord(c->ev[6], s));
     return PK_OK;
 }
 
@@ -853,20 +907,12 @@ static int ensure_feature_buffer(pk_chrom* c) {
 }
 
 static int reset_score_state(pk_chrom* c) {
-    // batches are numbered over the whole chromosome's candidates (at most the band pixels)
-    const int64_t nb = band_pixels_of(c) / PK_BATCH + 2;
-    if (nb > c->batch_cap || !c->d_batch_win) {
-        if (c->d_batch_win) PK_CHECK(quiesce(c));
-        dev_free(c->d_batch_win);
-        PK_CHECK(dev_alloc(&c->d_batch_win, (size_t)nb));
-        c->batch_cap = nb;
-    }
-    PK_CUDA(cudaMemsetAsync(c->d_batch_win, 0, (size_t)c->batch_cap * 4, c->stream));
-    PK_CUDA(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream));
+    // counters and the per-batch window counts are neighbours in the head block: one memset
+    PK_CUDA(cudaMemsetAsync(c->d_counters, 0, 32 + (size_t)c->batch_cap * 4, c->stream));
     PK_CUDA(cudaMemsetAsync(c->d_keep, 0, (size_t)c->cand_cap, c->stream));
     // buffers of the record ordering that follows the scoring pass
     c->eager_valid = false;
-    const int64_t M = std::min<int64_t>(c->cand_cap, PK_EAGER_RECORDS);
+    const int64_t M = c->cand_cap;              // every record is a candidate: the ordering buffers cover them all
     if (!c->d_rowcnt) {
         PK_CHECK(dev_alloc(&c->d_rowcnt, (size_t)c->n + 1)); PK_CHECK(dev_alloc(&c->d_rowoff, (size_t)c->n + 2));
         PK_CUDA(cudaMemsetAsync(c->d_rowcnt, 0, ((size_t)c->n + 1) * 4, c->stream));     // k_record_place keeps it zero afterwards
@@ -983,7 +1029,7 @@ extern "C" int pk_chrom_fused_features(pk_chrom* c, pk_forest* f, uint8_t* keep,
 static int run_score(pk_chrom* c, pk_forest* f, double min_prob) {
     cudaStream_t s = c->stream;
     PK_CHECK(reset_score_state(c));
-    PK_CUDA(cudaEventRecord(c->ev[7], s));
+    if (c->timing) PK_CUDA(cudaEventRecord(c->ev[7], s));
     bool fused = g_tune_fused != 0 && pk_fused_supported(c->w, f->n_trees);
     if (fused) {
         // features stay in shared memory; stage [4] reports the fused kernel, [5] is 0
@@ -1008,21 +1054,21 @@ static int run_score(pk_chrom* c, pk_forest* f, double min_prob) {
         else PK_CHECK(r);
     }
     if (fused) {
-        PK_CUDA(cudaEventRecord(c->ev[8], s));
+        if (c->timing) PK_CUDA(cudaEventRecord(c->ev[8], s));
     } else {
         if (!c->n_cand_known) PK_CHECK(settle_candidates(c));
         PK_CHECK(ensure_feature_buffer(c));
         PK_CHECK(pk_launch_features(c, nullptr));
-        PK_CUDA(cudaEventRecord(c->ev[8], s));
+        if (c->timing) PK_CUDA(cudaEventRecord(c->ev[8], s));
         PK_CHECK(pk_launch_forest(f, c->d_fea32, c->d_keep, c->n_cand, nullptr, c->d_prob, s));
     }
-    PK_CUDA(cudaEventRecord(c->ev[9], s));
+    if (c->timing) PK_CUDA(cudaEventRecord(c->ev[9], s));
     PK_CHECK(pk_launch_emit(c, min_prob));
     // order + pack the records now, behind the scoring pass: later the SMs belong to the next chromosome
     c->counts_valid = false;
     PK_CHECK(pk_launch_sort_records_eager(c, c->eager_cap));
     c->eager_valid = true;
-    PK_CUDA(cudaEventRecord(c->ev[10], s));
+    if (c->timing) PK_CUDA(cudaEventRecord(c->ev[10], s));
     return PK_OK;
 }
 
@@ -1121,39 +1167,9 @@ extern "C" int pk_chrom_fetch_results(pk_chrom* c, int32_t* out_x, int32_t* out_
         if (out_val) memcpy(out_val, hd + n, (size_t)n * 8);
         return PK_OK;
     }
-    const size_t temp_bytes = pk_sort_temp_bytes(n);
-    unsigned long long *k0 = nullptr, *k1 = nullptr;
-    uint32_t *i0 = nullptr, *i1 = nullptr;
-    unsigned char *temp = nullptr, *packed = nullptr;
-    int r = PK_OK;
-    if ((r = dev_alloc(&k0, (size_t)n)) || (r = dev_alloc(&k1, (size_t)n)) || (r = dev_alloc(&i0, (size_t)n)) ||
-        (r = dev_alloc(&i1, (size_t)n)) || (r = dev_alloc(&temp, temp_bytes)) || (r = dev_alloc(&packed, packed_bytes))) {
-        dev_free(k0); dev_free(k1); dev_free(i0); dev_free(i1); dev_free(temp); dev_free(packed);
-        return r;
-    }
-    if (packed_bytes > c->h_stage_bytes) {
-        hstage_release(c->h_stage, c->h_stage_bytes);
-        c->h_stage = nullptr; c->h_stage_bytes = 0;
-        r = hstage_acquire(&c->h_stage, &c->h_stage_bytes, packed_bytes);
-    }
-    int key_bits = 32;
-    for (int nb = c->n; nb > 0; nb >>= 1) ++key_bits;      // x needs bits(n) bits above the 32 bits of y
-    if (r == PK_OK) r = pk_launch_sort_records(c, n, k0, k1, i0, i1, temp, temp_bytes, packed, off_f64, std::min(key_bits, 64));
-    if (r == PK_OK) {
-        cudaError_t e = cudaMemcpyAsync(c->h_stage, packed, packed_bytes, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) { pk_set_error("pk_chrom_fetch_results: %s", cudaGetErrorString(e)); r = PK_ECUDA; }
-    }
-    dev_free(k0); dev_free(k1); dev_free(i0); dev_free(i1); dev_free(temp); dev_free(packed);
-    PK_CHECK(r);
-    const int32_t* hi = reinterpret_cast<const int32_t*>(c->h_stage);
-    const double* hd = reinterpret_cast<const double*>(c->h_stage + off_f64);
-    if (out_x) memcpy(out_x, hi, (size_t)n * 4);
-    if (out_y) memcpy(out_y, hi + n, (size_t)n * 4);
-    if (out_batch) memcpy(out_batch, hi + 2 * n, (size_t)n * 4);
-    if (out_prob) memcpy(out_prob, hd, (size_t)n * 8);
-    if (out_val) memcpy(out_val, hd + n, (size_t)n * 8);
-    return PK_OK;
+    // every record is a candidate and the ordering buffers cover cand_cap records: not reachable
+    pk_set_error("pk_chrom_fetch_results: %lld records exceed the ordering buffers (%lld)", (long long)n, (long long)c->eager_cap);
+    return PK_ECAPACITY;
 }
 
 extern "C" int pk_chrom_stage_ms(pk_chrom* c, float* out_ms) {
@@ -1170,5 +1186,245 @@ extern "C" int pk_chrom_stage_ms(pk_chrom* c, float* out_ms) {
         out_ms[5] = ev_ms(c, 8, 9);
         out_ms[6] = ev_ms(c, 9, 10);
     }
+    return PK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// engine: score_genome's loop (score_genome.py:46-84) as a persistent per-device pipeline.
+// Streams, chromosome handles and pinned staging are created once and reused from pass to pass;
+// pk_engine_submit queues a unit (a chromosome, or a band row tile of one) without ever waiting
+// for the device; pk_engine_collect waits for the units in order and moves every unit's records
+// with one copy each into one pinned block. Uploads and the short stages of the units run on a
+// ring of high-priority streams, the scoring kernels back to back on one ordinary stream.
+// ---------------------------------------------------------------------------
+struct pk_engine_slot {
+    pk_chrom* c = nullptr;
+    int64_t tag = 0;
+    int32_t row_begin = 0, row_end = 0;
+    cudaEvent_t done = nullptr;         // recorded behind the copy of the head block
+    size_t head_off = 0;                // in h_head
+    int64_t n_rec = 0;
+    size_t res_off = 0;                 // in h_res
+};
+
+struct pk_engine {
+    int device = 0;
+    pk_forest* forest = nullptr;
+    int32_t w = 0, lower = 0, upper = 0;
+    std::vector<cudaStream_t> streams;
+    cudaStream_t score_stream = nullptr;
+    std::vector<pk_engine_slot> units;  // queued since the last collect
+    std::vector<pk_chrom*> idle;        // handles kept for reuse
+    std::vector<cudaEvent_t> events;    // one per slot index, created on demand
+    unsigned char* h_head = nullptr; size_t h_head_bytes = 0, h_head_used = 0;
+    unsigned char* h_res = nullptr; size_t h_res_bytes = 0;
+    int64_t submitted = 0;
+    bool collected = true;              // results of the last collect are still exposed
+};
+
+static const size_t PK_ENGINE_HEAD_BYTES = 4 << 20;
+static const size_t PK_ENGINE_IDLE_MAX = 64;
+
+extern "C" int pk_engine_create(int device, pk_forest* f, int32_t width, int32_t lower, int32_t upper, int depth,
+                                pk_engine** out) {
+    if (!out || !f || depth < 1 || depth > 32) { pk_set_error("pk_engine_create: bad argument"); return PK_EINVAL; }
+    if (f->device != device) { pk_set_error("pk_engine_create: forest lives on device %d", f->device); return PK_EINVAL; }
+    if ((2 * width + 1) * (2 * width + 1) != f->n_features) {
+        pk_set_error("pk_engine_create: forest has %d features, width %d needs %d", f->n_features, width, (2 * width + 1) * (2 * width + 1));
+        return PK_EINVAL;
+    }
+    PK_CUDA(cudaSetDevice(device));
+    pk_engine* e = new pk_engine();
+    e->device = device; e->forest = f; e->w = width; e->lower = lower; e->upper = upper;
+    int lo = 0, hi = 0;                       // numerically lower = higher priority
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    for (int i = 0; i < depth; ++i) {
+        cudaStream_t s = nullptr;
+        if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) != cudaSuccess) { pk_engine_destroy(e); pk_set_error("pk_engine_create: stream"); return PK_ECUDA; }
+        e->streams.push_back(s);
+    }
+    if (cudaStreamCreateWithPriority(&e->score_stream, cudaStreamNonBlocking, lo) != cudaSuccess) { pk_engine_destroy(e); pk_set_error("pk_engine_create: stream"); return PK_ECUDA; }
+    if (cudaMallocHost((void**)&e->h_head, PK_ENGINE_HEAD_BYTES) != cudaSuccess) { pk_engine_destroy(e); pk_set_error("pk_engine_create: pinned memory"); return PK_ENOMEM; }
+    e->h_head_bytes = PK_ENGINE_HEAD_BYTES;
+    *out = e;
+    return PK_OK;
+}
+
+static void engine_drain(pk_engine* e) {
+    for (auto s : e->streams) cudaStreamSynchronize(s);
+    if (e->score_stream) cudaStreamSynchronize(e->score_stream);
+}
+
+// forget the queued units (after an error): wait for the device, keep the handles
+extern "C" int pk_engine_reset(pk_engine* e) {
+    if (!e) return PK_OK;
+    cudaSetDevice(e->device);
+    engine_drain(e);
+    for (auto& u : e->units)
+        if (u.c) pk_chrom_destroy(u.c);        // their state is unknown: do not reuse
+    e->units.clear();
+    e->h_head_used = 0;
+    e->collected = true;
+    cudaGetLastError();
+    return PK_OK;
+}
+
+extern "C" int pk_engine_destroy(pk_engine* e) {
+    if (!e) return PK_OK;
+    cudaSetDevice(e->device);
+    pk_engine_reset(e);
+    for (auto c : e->idle) pk_chrom_destroy(c);
+    for (auto ev : e->events) if (ev) cudaEventDestroy(ev);
+    for (auto s : e->streams) if (s) cudaStreamDestroy(s);
+    if (e->score_stream) cudaStreamDestroy(e->score_stream);
+    if (e->h_head) cudaFreeHost(e->h_head);
+    if (e->h_res) cudaFreeHost(e->h_res);
+    delete e;
+    return PK_OK;
+}
+
+extern "C" int pk_engine_submit(pk_engine* e, const pk_unit* u) {
+    if (!e || !u) { pk_set_error("pk_engine_submit: NULL argument"); return PK_EINVAL; }
+    if (u->n_bins <= 0 || u->row_begin < 0 || u->row_end > u->n_bins || u->row_begin > u->row_end) {
+        pk_set_error("pk_engine_submit: bad unit (n_bins %d, rows [%d, %d))", u->n_bins, u->row_begin, u->row_end);
+        return PK_EINVAL;
+    }
+    PK_CUDA(cudaSetDevice(e->device));
+    if (e->collected) {                      // first unit of a new pass: the previous results are released
+        e->collected = false;
+        e->h_head_used = 0;
+    }
+    const int balanced = u->weights != nullptr;
+    pk_chrom* c = nullptr;
+    for (size_t i = 0; i < e->idle.size(); ++i)
+        if (e->idle[i]->n == u->n_bins && e->idle[i]->balanced == balanced) {
+            c = e->idle[i];
+            e->idle.erase(e->idle.begin() + (long)i);
+            break;
+        }
+    cudaStream_t s = e->streams[(size_t)(e->submitted++ % (int64_t)e->streams.size())];
+    if (!c) {
+        PK_CHECK(pk_chrom_create(e->device, u->n_bins, e->w, e->lower, e->upper, balanced, (void*)s, &c));
+        c->timing = false;
+        c->score_stream = e->score_stream;
+        c->use_score_stream = true;
+    }
+    c->stream = s;
+    const size_t hb = (c->head_bytes + 63) & ~(size_t)63;
+    int r = PK_OK;
+    if (e->h_head_used + hb > e->h_head_bytes) { pk_set_error("pk_engine_submit: too many units queued; collect first"); r = PK_ECAPACITY; }
+    if (r == PK_OK) {
+        switch (u->encoding) {
+        case PK_ENC_COO: r = pk_chrom_upload_pixels(c, (const int32_t*)u->a, (const int32_t*)u->b, (const int32_t*)u->c, u->size, u->weights, PK_MEM_HOST | PK_PIXELS_SORTED); break;
+        case PK_ENC_CSR32: r = pk_chrom_upload_csr(c, (const int64_t*)u->a, (const int32_t*)u->b, (const int32_t*)u->c, u->size, u->weights, PK_MEM_HOST); break;
+        case PK_ENC_CSR16: r = pk_chrom_upload_csr16(c, (const int64_t*)u->a, (const uint16_t*)u->b, (const uint16_t*)u->c, u->size, u->weights, PK_MEM_HOST); break;
+        case PK_ENC_ROWS: r = pk_chrom_upload_rows(c, u->a, u->size, u->weights, PK_MEM_HOST); break;
+        default: pk_set_error("pk_engine_submit: unknown encoding %d", u->encoding); r = PK_EINVAL;
+        }
+    }
+    if (r == PK_OK) r = pk_chrom_fit_expected(c);
+    if (r == PK_OK) r = pk_chrom_find_candidates(c, u->row_begin, u->row_end, nullptr);
+    if (r == PK_OK) r = pk_chrom_score(c, e->forest, u->min_prob);
+    pk_engine_slot slot;
+    if (r == PK_OK) {
+        const size_t idx = e->units.size();
+        while (e->events.size() <= idx) {
+            cudaEvent_t ev = nullptr;
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { pk_set_error("pk_engine_submit: event"); r = PK_ECUDA; break; }
+            e->events.push_back(ev);
+        }
+        if (r == PK_OK) {
+            slot.c = c; slot.tag = u->tag; slot.row_begin = u->row_begin; slot.row_end = u->row_end;
+            slot.done = e->events[idx];
+            slot.head_off = e->h_head_used;
+            cudaError_t ce = cudaMemcpyAsync(e->h_head + slot.head_off, c->d_head, c->head_bytes, cudaMemcpyDeviceToHost, s);
+            if (ce == cudaSuccess) ce = cudaEventRecord(slot.done, s);
+            if (ce != cudaSuccess) { pk_set_error("pk_engine_submit: %s", cudaGetErrorString(ce)); r = PK_ECUDA; }
+        }
+    }
+    if (r != PK_OK) {
+        cudaStreamSynchronize(s);
+        if (c->score_stream) cudaStreamSynchronize(c->score_stream);
+        pk_chrom_destroy(c);
+        return r;
+    }
+    e->h_head_used += hb;
+    e->units.push_back(slot);
+    return PK_OK;
+}
+
+static int engine_grow_results(pk_engine* e, size_t need) {
+    if (need <= e->h_res_bytes) return PK_OK;
+    engine_drain(e);                          // earlier record copies land in the old block first
+    size_t want = std::max<size_t>(need + need / 2, 4 << 20);
+    unsigned char* nb = nullptr;
+    if (cudaMallocHost((void**)&nb, want) != cudaSuccess) { pk_set_error("pk_engine_collect: %zu bytes of pinned memory", want); cudaGetLastError(); return PK_ENOMEM; }
+    if (e->h_res) { memcpy(nb, e->h_res, e->h_res_bytes); cudaFreeHost(e->h_res); }
+    e->h_res = nb; e->h_res_bytes = want;
+    return PK_OK;
+}
+
+extern "C" int pk_engine_collect(pk_engine* e, pk_unit_result* out, int64_t capacity, int64_t* n_units) {
+    if (!e || !n_units) { pk_set_error("pk_engine_collect: NULL argument"); return PK_EINVAL; }
+    *n_units = (int64_t)e->units.size();
+    if (!out) return PK_OK;
+    if (capacity < (int64_t)e->units.size()) { pk_set_error("pk_engine_collect: capacity %lld < %zu units", (long long)capacity, e->units.size()); return PK_ECAPACITY; }
+    PK_CUDA(cudaSetDevice(e->device));
+    size_t used = 0;
+    for (auto& u : e->units) {
+        pk_chrom* c = u.c;
+        PK_CUDA(cudaEventSynchronize(u.done));
+        unsigned char* hd = e->h_head + u.head_off;
+        const int32_t* flags = reinterpret_cast<const int32_t*>(hd);
+        const long long* nc = reinterpret_cast<const long long*>(hd + 16);
+        const unsigned long long* cnt = reinterpret_cast<const unsigned long long*>(hd + 32);
+        const bool overflow = flags[0] != 0 || (flags[3] & 2) != 0 || nc[0] > c->cand_cap;
+        const bool trouble = overflow || (flags[2] & 3) != 0 || (c->declared_sorted && (flags[3] & 1));
+        if (trouble) {
+            // a device-side capacity was exceeded (the scan and the scoring are replayed) or the pass failed:
+            // the step-by-step entry points sort it out, then the head block is read again
+            PK_CHECK(pk_chrom_result_count(c, nullptr, nullptr, nullptr));
+            PK_CUDA(cudaMemcpyAsync(hd, c->d_head, c->head_bytes, cudaMemcpyDeviceToHost, c->stream));
+            PK_CUDA(cudaStreamSynchronize(c->stream));
+        } else {
+            c->n_cand = nc[0]; c->n_cand_all = nc[1]; c->n_cand_known = true;
+            memcpy(c->h_counts, cnt, sizeof c->h_counts);
+            c->counts_valid = true;
+        }
+        u.n_rec = (int64_t)c->h_counts[0];
+        if (u.n_rec > c->eager_cap) { pk_set_error("pk_engine_collect: %lld records exceed the ordering buffers", (long long)u.n_rec); return PK_ECAPACITY; }
+        const size_t off_f64 = (size_t)((12 * u.n_rec + 7) / 8) * 8;
+        const size_t bytes = off_f64 + 16 * (size_t)u.n_rec;
+        u.res_off = used;
+        used = (used + bytes + 63) & ~(size_t)63;
+        PK_CHECK(engine_grow_results(e, used));
+        if (u.n_rec > 0)
+            PK_CUDA(cudaMemcpyAsync(e->h_res + u.res_off, c->d_packed, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    engine_drain(e);
+    PK_CUDA(cudaGetLastError());
+    int64_t i = 0;
+    for (auto& u : e->units) {
+        pk_chrom* c = u.c;
+        pk_unit_result& r = out[i++];
+        const unsigned char* hd = e->h_head + u.head_off;
+        const unsigned char* base = e->h_res + u.res_off;
+        const size_t off_f64 = (size_t)((12 * u.n_rec + 7) / 8) * 8;
+        r.tag = u.tag; r.n_bins = c->n; r.row_begin = u.row_begin; r.row_end = u.row_end;
+        r.whole = (u.row_begin == 0 && u.row_end == c->n) ? 1 : 0;
+        r.n_records = u.n_rec; r.n_candidates = c->n_cand; r.n_windows = (int64_t)c->h_counts[1];
+        r.n_batches = (c->n_cand_all + PK_BATCH - 1) / PK_BATCH;
+        r.x = reinterpret_cast<const int32_t*>(base);
+        r.y = r.x + u.n_rec;
+        r.batch = r.x + 2 * u.n_rec;
+        r.prob = reinterpret_cast<const double*>(base + off_f64);
+        r.value = r.prob + u.n_rec;
+        r.batch_windows = reinterpret_cast<const int32_t*>(hd + 64);
+        if (e->idle.size() < PK_ENGINE_IDLE_MAX) e->idle.push_back(c);
+        else pk_chrom_destroy(c);
+        u.c = nullptr;
+    }
+    e->units.clear();
+    e->collected = true;
     return PK_OK;
 }

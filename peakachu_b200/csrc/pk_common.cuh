@@ -110,11 +110,17 @@ struct pk_chrom {
     //      2 = bit0 expected fit failed / bit1 diagonal too long / bit2 a weight outside [1e-45, 1e45],
     //      3 = bit0 pixels not sorted / bit1 candidate buffer too small
     int32_t* d_flags = nullptr;
+    unsigned char* d_head = nullptr; // flags | d_ncand | d_counters | d_batch_win in one block (one copy reads them all)
+    size_t head_bytes = 0;
     // upload staging
     int32_t *d_b1 = nullptr, *d_b2 = nullptr, *d_cnt = nullptr;
     int64_t pix_cap = 0;
     long long* d_rowptr = nullptr;   // [n+1]
     bool declared_sorted = false;
+    unsigned char* d_blob = nullptr; // packed pixel rows (pk_chrom_upload_rows), or the caller's device blob
+    unsigned char* d_blob_own = nullptr;   // the staging block this handle owns
+    int64_t blob_cap = 0;
+    long long rows_hdr[16] = {};     // host copy of the blob's header
     // candidates
     int32_t n_chunks = 0;
     uint32_t* d_cnt_all = nullptr;   // [nd_cand * n_chunks] whole-chromosome counts
@@ -151,7 +157,7 @@ struct pk_chrom {
     int64_t rrank_cap = 0;
     bool eager_valid = false;           // d_packed belongs to the current scores
     // pixel columns of the last upload as they sit on the device (pk_chrom_depth): kind 0 none,
-    // 1 COO (b1, b2, cnt int32), 2 rows + int32 columns, 3 rows + uint16 (bin2 - bin1, count)
+    // 1 COO (b1, b2, cnt int32), 2 rows + int32 columns, 3 rows + uint16 (bin2 - bin1, count), 4 packed rows (d_blob)
     int up_kind = 0;
     const void *up_b1 = nullptr, *up_b2 = nullptr, *up_cnt = nullptr;
     const long long* up_rowptr = nullptr;
@@ -166,6 +172,7 @@ struct pk_chrom {
     // timing
     cudaEvent_t ev[16] = {};
     float stage_ms[8] = {};
+    bool timing = true;                 // record the per-stage events (pk_chrom_stage_ms); the engine turns it off
 };
 
 // Poisson decision table (host long double -> float64), per device copy

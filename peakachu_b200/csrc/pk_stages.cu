@@ -72,6 +72,151 @@ __global__ void __launch_bounds__(256) k_band_csr(
         for (int xl = lane; xl < R && x0 + xl < n; xl += 32) band[(long long)d * pitch + x0 + xl] = s_tile[d * TP + xl];
 }
 
+// ---------------------------------------------------------------------------
+// S1'  band build from packed pixel rows (pk_chrom_upload_rows; layout in include/peakachu_b200.h and
+//      peakachu_b200/rowpack.py): per row a presence bitmap over the first nd_enc distances, one count
+//      byte per present pixel (255 = escaped to a side list), far pixels (d >= nd_enc) as CSR columns.
+//      Same tiling as k_band_csr: a CTA owns R rows, a warp walks a row -- lane l decodes bitmap word l,
+//      i.e. distances 32 l .. 32 l + 31 -- and the CTA writes the tile as full lines. The bitmap makes
+//      duplicates impossible, so the tile is filled with plain stores. Far pixels only mark `valid`.
+// ---------------------------------------------------------------------------
+struct PkRowsView {
+    const uint32_t* bits; const uint32_t* cnt_off; const uint8_t* cnt8;
+    const int32_t* esc;            // [3][n_esc]: x | d | count
+    long long n_esc;
+    const long long* far_off; const int32_t* far_b2; const int32_t* far_cnt;
+    int nd_enc, W;
+};
+
+__global__ void __launch_bounds__(256) k_band_rows(
+    const PkRowsView v, const double* __restrict__ w, int n, int ND, long long pitch, int balanced, int R,
+    int32_t* __restrict__ band, uint8_t* __restrict__ valid, int32_t* __restrict__ flags) {
+    extern __shared__ int32_t s_tile[];                 // [ND][R + 1]
+    const int TP = R + 1;
+    const int x0 = blockIdx.x * R;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    for (int i = tid; i < ND * TP; i += 256) s_tile[i] = 0;
+    __syncthreads();
+    int cmax = 0;
+    for (int xl = wib; xl < R; xl += 8) {
+        const int x = x0 + xl;
+        if (x >= n) break;
+        const double wx = balanced ? w[x] : 0.0;
+        bool any = false;
+        const uint8_t* cb = v.cnt8 + v.cnt_off[x];
+        int carry = 0;
+        for (int w0 = 0; w0 < v.W; w0 += 32) {
+            const int wi = w0 + lane;
+            uint32_t b = wi < v.W ? v.bits[(size_t)x * v.W + wi] : 0u;
+            const int pc = __popc(b);
+            int pre = pc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+            const uint8_t* mine = cb + carry + pre - pc;               // this lane's count bytes
+            carry += __shfl_sync(0xffffffffu, pre, 31);
+            const int ybase = x + wi * 32;
+            // four pixels per round: every load of a round is issued before the first use
+            for (int k = 0; k < pc; k += 4) {
+                int bit[4], c[4];
+                double wy[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    bit[j] = -1; c[j] = 0; wy[j] = 0.0;
+                    if (b) {
+                        bit[j] = __ffs(b) - 1;
+                        b &= b - 1;
+                        c[j] = mine[k + j];
+                        const int y = ybase + bit[j];
+                        if (y >= n) c[j] = 0;                            // past the end of the chromosome: ignored
+                        else if (balanced) wy[j] = w[y];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (c[j] == 0 || c[j] == 255) continue;             // 255: an escaped count (k_band_escapes)
+                    bool fin;
+                    if (balanced) fin = isfinite(__dmul_rn(__dmul_rn(wx, wy[j]), (double)c[j]));
+                    else fin = true;
+                    const int d = wi * 32 + bit[j];
+                    if (fin) { any = true; valid[x + d] = 1; }
+                    if (d < ND) { s_tile[d * TP + xl] = c[j]; cmax = max(cmax, c[j]); }
+                }
+            }
+        }
+        // far pixels: never in the band, but they make their bins valid (utils.py:146-156)
+        for (long long p = v.far_off[x] + lane; p < v.far_off[x + 1]; p += 32) {
+            const int y = v.far_b2[p], c = v.far_cnt[p];
+            if (c <= 0 || y < x || y >= n) continue;
+            bool fin = true;
+            if (balanced) fin = isfinite(__dmul_rn(__dmul_rn(wx, w[y]), (double)c));
+            if (fin) { any = true; valid[y] = 1; }
+        }
+        if (__any_sync(0xffffffffu, any) && lane == 0) valid[x] = 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+    if (lane == 0 && cmax > 0) atomicMax(&flags[1], cmax);
+    __syncthreads();
+    for (int d = wib; d < ND; d += 8)
+        for (int xl = lane; xl < R && x0 + xl < n; xl += 32) band[(long long)d * pitch + x0 + xl] = s_tile[d * TP + xl];
+}
+
+// escaped counts (>= 255) of the packed rows: a few per row at most, written after the tiles
+__global__ void __launch_bounds__(256) k_band_escapes(const PkRowsView v, const double* __restrict__ w, int n, int ND,
+                                                      long long pitch, int balanced, int32_t* __restrict__ band,
+                                                      uint8_t* __restrict__ valid, int32_t* __restrict__ flags) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= v.n_esc) return;
+    const int x = v.esc[i], d = v.esc[v.n_esc + i], c = v.esc[2 * v.n_esc + i];
+    if (x < 0 || d < 0 || x + d >= n || c <= 0) return;
+    bool fin = true;
+    if (balanced) fin = isfinite(__dmul_rn(__dmul_rn(w[x], w[x + d]), (double)c));
+    if (fin) { valid[x] = 1; valid[x + d] = 1; }
+    if (d < ND) {
+        band[(long long)d * pitch + x] = c;
+        if (c > flags[1]) atomicMax(&flags[1], c);
+    }
+}
+
+// depth over packed rows: band part (a warp per row, lane per bitmap word), escapes, far pixels
+__global__ void __launch_bounds__(256) k_depth_packed(const PkRowsView v, int n, int min_dis,
+                                                      unsigned long long* __restrict__ total) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * 256) >> 5, warp = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    unsigned long long sum = 0;
+    for (int x = warp; x < n; x += warps) {
+        const uint8_t* cb = v.cnt8 + v.cnt_off[x];
+        int carry = 0;
+        for (int w0 = 0; w0 < v.W; w0 += 32) {
+            const int wi = w0 + lane;
+            uint32_t b = wi < v.W ? v.bits[(size_t)x * v.W + wi] : 0u;
+            const int pc = __popc(b);
+            int pre = pc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+            const uint8_t* mine = cb + carry + pre - pc;
+            carry += __shfl_sync(0xffffffffu, pre, 31);
+            for (int k = 0; b; ++k) {
+                const int bit = __ffs(b) - 1;
+                b &= b - 1;
+                const int c = mine[k], d = wi * 32 + bit;
+                if (c != 255 && d >= min_dis && x + d < n) sum += (unsigned long long)c;
+            }
+        }
+        for (long long p = v.far_off[x] + lane; p < v.far_off[x + 1]; p += 32) {
+            const int y = v.far_b2[p], c = v.far_cnt[p];
+            if (c > 0 && y - x >= min_dis && y < n) sum += (unsigned long long)c;
+        }
+    }
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < v.n_esc; i += (long long)gridDim.x * 256) {
+        const int x = v.esc[i], d = v.esc[v.n_esc + i], c = v.esc[2 * v.n_esc + i];
+        if (c > 0 && d >= min_dis && x >= 0 && x + d < n) sum += (unsigned long long)c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0 && sum) atomicAdd(total, sum);
+}
+
 // rowptr for pixels sorted by (bin1, bin2): rowptr[x] = first pixel with bin1 >= x
 __global__ void __launch_bounds__(256) k_rowptr(const int32_t* __restrict__ b1, long long nnz, int n,
                                                 long long* __restrict__ rowptr) {
@@ -615,6 +760,51 @@ static int launch_band_csr_t(pk_chrom* c, const long long* rowptr, const void* b
     return PK_OK;
 }
 
+static PkRowsView rows_view(const pk_chrom* c) {
+    const unsigned char* base = c->d_blob;
+    const long long* h = c->rows_hdr;
+    PkRowsView v;
+    v.nd_enc = (int)h[2]; v.W = (int)h[3]; v.n_esc = h[5];
+    v.bits = reinterpret_cast<const uint32_t*>(base + h[7]);
+    v.cnt_off = reinterpret_cast<const uint32_t*>(base + h[8]);
+    v.cnt8 = base + h[9];
+    v.esc = reinterpret_cast<const int32_t*>(base + h[10]);
+    v.far_off = reinterpret_cast<const long long*>(base + h[11]);
+    v.far_b2 = reinterpret_cast<const int32_t*>(base + h[12]);
+    v.far_cnt = reinterpret_cast<const int32_t*>(base + h[13]);
+    return v;
+}
+
+// rows per CTA of the tiled band builds: 32, or a few more when that lets every CTA be resident at once
+static int band_rows_per_cta(const pk_chrom* c) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    auto tile_bytes = [&](int R) { return (size_t)c->ND * (R + 1) * sizeof(int32_t); };
+    auto slots = [&](int R) { return (long long)sms * std::min<long long>(8, (long long)((227 * 1024) / (tile_bytes(R) + 1024))); };
+    int R = 32;
+    if ((c->n + 31) / 32 > slots(32))
+        for (int r = 34; r <= 64; r += 2)
+            if ((c->n + r - 1) / r <= slots(r)) { R = r; break; }
+    return R;
+}
+
+int pk_launch_band_rows(pk_chrom* c) {
+    const PkRowsView v = rows_view(c);
+    const int R = band_rows_per_cta(c);
+    const size_t smem = (size_t)c->ND * (R + 1) * sizeof(int32_t);
+    if (smem > 200 * 1024) { pk_set_error("band build: %d diagonals do not fit a shared-memory tile", c->ND); return PK_EUNSUPPORTED; }
+    PK_OPT_IN_SMEM(k_band_rows, smem, c->device);
+    k_band_rows<<<(unsigned)((c->n + R - 1) / R), 256, smem, c->stream>>>(v, c->d_w, c->n, c->ND, c->pitch, c->balanced, R,
+                                                                       c->d_band, c->d_valid, c->d_flags);
+    PK_CUDA(cudaGetLastError());
+    if (v.n_esc > 0) {
+        k_band_escapes<<<(unsigned)((v.n_esc + 255) / 256), 256, 0, c->stream>>>(v, c->d_w, c->n, c->ND, c->pitch, c->balanced,
+                                                                              c->d_band, c->d_valid, c->d_flags);
+        PK_CUDA(cudaGetLastError());
+    }
+    return PK_OK;
+}
+
 // enc 0: int32 bin2 + int32 count; enc 1: uint16 (bin2 - bin1) + uint16 count
 int pk_launch_band_csr(pk_chrom* c, const long long* rowptr, const void* b2, const void* cnt, int enc) {
     if (enc == 1) return launch_band_csr_t<uint16_t, uint16_t, true>(c, rowptr, b2, cnt);
@@ -661,8 +851,13 @@ __global__ void __launch_bounds__(256) k_depth_coo(const int32_t* __restrict__ b
 }
 
 int pk_launch_depth(pk_chrom* c, int32_t min_dis, unsigned long long* d_total) {
-    if (c->up_nnz == 0) return PK_OK;
     const unsigned grid = 148 * 4;
+    if (c->up_kind == 4) {
+        k_depth_packed<<<grid, 256, 0, c->stream>>>(rows_view(c), c->n, min_dis, d_total);
+        PK_CUDA(cudaGetLastError());
+        return PK_OK;
+    }
+    if (c->up_nnz == 0) return PK_OK;
     if (c->up_kind == 1)
         k_depth_coo<<<grid, 256, 0, c->stream>>>((const int32_t*)c->up_b1, (const int32_t*)c->up_b2, (const int32_t*)c->up_cnt,
                                                  c->up_nnz, min_dis, d_total);

@@ -142,9 +142,37 @@ class Chromosome:
                    stream, bin1_offset=bin1_offset, first_tile=first_tile, csr16=True, score_stream=score_stream)
         return self
 
+    @classmethod
+    def from_rows(cls, blob, weights, n_bins, model, lower=6, upper=300,
+                  cname="chrm", res=10000, width=5, device=0, stream=None, first_tile=None, score_stream=None):
+        """Build from packed pixel rows (``peakachu_b200.rowpack``; ``pk_chrom_upload_rows``): the
+        chromosome crosses the bus in one copy of about 1.3 bytes per band pixel."""
+        self = cls.__new__(cls)
+        self._init(None, None, None, weights, int(n_bins), model, lower, upper, cname, res, width, device,
+                   stream, first_tile=first_tile, score_stream=score_stream, rows=blob)
+        return self
+
+    @classmethod
+    def from_map(cls, Lib, key, weights, model, lower=6, upper=300, cname="chrm", res=10000, width=5, device=0,
+                 encoding=None):
+        """Build from an opened map (``coolio.open_map``), taking the chromosome's pixels in the most
+        compact column format the reader offers: packed rows, uint16 columns, cooler's CSR columns."""
+        from . import shard
+        n = Lib.nbins(key)
+        nd_need = min(upper, n - 2 * width) + 2 * width + 1
+        enc, a, b, c, _ = shard._unit_columns(Lib, key, nd_need, encoding)
+        kw = dict(lower=lower, upper=upper, cname=cname, res=res, width=width, device=device)
+        if enc == _lib.PK_ENC_ROWS:
+            return cls.from_rows(a, weights, n, model, **kw)
+        if enc == _lib.PK_ENC_CSR16:
+            return cls.from_csr16(a, b, c, weights, n, model, **kw)
+        if enc == _lib.PK_ENC_CSR32:
+            return cls.from_csr(a, b, c, weights, n, model, **kw)
+        return cls.from_pixels(a, b, c, weights, n, model, sorted_pixels=True, **kw)
+
     # -- construction = upload + band + expected + candidates (scoreUtils.py:13-34) --
     def _init(self, b1, b2, cnt, weights, n, model, lower, upper, cname, res, width, device, stream,
-              sorted_pixels=None, bin1_offset=None, first_tile=None, csr16=False, score_stream=None):
+              sorted_pixels=None, bin1_offset=None, first_tile=None, csr16=False, score_stream=None, rows=None):
         L = _lib.lib()
         _lib.require_device()
         self.chromname, self.r, self.w = cname, res, width
@@ -163,6 +191,13 @@ class Chromosome:
         lo, up, el = C.c_int32(), C.c_int32(), C.c_int32()
         _lib.check(L.pk_chrom_bounds(self._h, C.byref(lo), C.byref(up), C.byref(el)))
         self.lower, self.upper, self._exp_len = lo.value, up.value, el.value
+        if rows is not None:
+            blob = _lib.as_c(rows, np.uint8)
+            self._keepalive = [blob]
+            _lib.check(L.pk_chrom_upload_rows(self._h, _lib.ptr(blob), blob.size, _lib.ptr(self.weights),
+                                              _lib.PK_MEM_HOST))
+            self._after_upload(L, first_tile, n)
+            return
         col_t = np.uint16 if csr16 else np.int32
         if csr16 and (np.asarray(b2).dtype != np.uint16 or np.asarray(cnt).dtype != np.uint16):
             raise TypeError("from_csr16 takes uint16 arrays (bin2 - bin1, count)")
@@ -184,6 +219,9 @@ class Chromosome:
             mem = _lib.PK_MEM_HOST | (_lib.PK_PIXELS_SORTED if sorted_pixels else 0)
             _lib.check(L.pk_chrom_upload_pixels(self._h, _lib.ptr(b1), _lib.ptr(b2), _lib.ptr(cnt), b1.size,
                                                 _lib.ptr(self.weights), mem))
+        self._after_upload(L, first_tile, n)
+
+    def _after_upload(self, L, first_tile, n):
         _lib.check(L.pk_chrom_fit_expected(self._h))
         self._exp = None
         # asynchronous: the candidate count is read back only when somebody asks for it

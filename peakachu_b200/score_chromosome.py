@@ -24,12 +24,11 @@ def main(args):
     ccname = args.chrom
     cikada = "chr" + ccname.lstrip("chr")                 # :37-38
 
-    b1, b2, cnt = Lib.upper_pixels(ccname)                # replaces :42-43 (matrix fetch + tocsr)
     weights = Lib.weights(ccname, correct) if correct else None   # :44
     forest = DeviceForest.of(flat, device)
-    X = Chromosome.from_pixels(b1, b2, cnt, weights, Lib.nbins(ccname), forest, lower=args.lower,
-                               upper=args.upper, cname=cikada, res=args.resolution, width=width,
-                               device=device, sorted_pixels=True)
+    # replaces :42-43 (matrix fetch + tocsr): the chromosome's pixel columns as the reader stores them
+    X = Chromosome.from_map(Lib, ccname, weights, forest, lower=args.lower, upper=args.upper, cname=cikada,
+                            res=args.resolution, width=width, device=device)
     result, R = X.score(thre=args.minimum_prob)           # :70
     X.writeBed(args.output, result, R)                    # :71
     X.close()

@@ -329,94 +329,155 @@ def gather_to_rank0(obj, rank, world):
     return out
 
 
-def _fetch_tile(X, a, b, n, ncand=None):
-    """Collect the records of the scoring pass in flight on handle ``X``."""
-    import ctypes as C
+class Engine:
+    """The library's persistent scoring pipeline of one device (``pk_engine_*``): streams, chromosome
+    handles and pinned staging live as long as the object; ``submit`` queues a unit without waiting for
+    the device, ``collect`` returns the records of everything queued."""
 
+    _cache: dict = {}
+
+    def __init__(self, forest, lower, upper, device, depth=6):
+        import ctypes as C
+
+        from . import _lib
+        self._L = _lib.lib()
+        self.forest, self.device = forest, device
+        self._h = C.c_void_p()
+        _lib.check(self._L.pk_engine_create(device, forest.handle, forest.width, int(lower), int(upper), int(depth),
+                                            C.byref(self._h)))
+        self._keep = []
+
+    @classmethod
+    def of(cls, forest, lower, upper, device, depth=6):
+        key = (id(forest), int(lower), int(upper), int(device), int(depth))
+        hit = cls._cache.get(key)
+        if hit is None or hit.forest is not forest or not hit._h:
+            hit = cls._cache[key] = cls(forest, lower, upper, device, depth)
+        return hit
+
+    def submit(self, tag, n_bins, row_begin, row_end, encoding, a, b, c, size, weights, min_prob):
+        import ctypes as C
+
+        from . import _lib
+        arrays = [v for v in (a, b, c, weights) if v is not None]
+        self._keep.extend(arrays)                        # uploads are asynchronous when the source is pinned
+        u = _lib.Unit(int(tag), int(n_bins), int(row_begin), int(row_end), int(encoding),
+                      a.ctypes.data if a is not None else None, b.ctypes.data if b is not None else None,
+                      c.ctypes.data if c is not None else None, int(size),
+                      weights.ctypes.data if weights is not None else None, float(min_prob))
+        rc = self._L.pk_engine_submit(self._h, C.byref(u))
+        if rc != 0:
+            msg = self._L.pk_last_error().decode("utf-8", "replace")
+            self.reset()
+            raise _lib.PKError(rc, msg)
+
+    def collect(self, copy=True):
+        """List of result dicts in submission order. With ``copy=False`` the record columns are views of
+        the engine's pinned block, valid until the next ``submit``."""
+        import ctypes as C
+
+        from . import _lib
+        n = C.c_int64()
+        _lib.check(self._L.pk_engine_collect(self._h, None, 0, C.byref(n)))
+        res = (_lib.UnitResult * max(n.value, 1))()
+        rc = self._L.pk_engine_collect(self._h, res, n.value, C.byref(n))
+        self._keep = []
+        if rc != 0:
+            msg = self._L.pk_last_error().decode("utf-8", "replace")
+            self.reset()
+            raise _lib.PKError(rc, msg)
+
+        def col(ptr, count, dtype):
+            if count == 0:
+                return np.zeros(0, dtype)
+            buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+            v = np.frombuffer(buf, dtype=dtype, count=count)
+            return v.copy() if copy else v
+        out = []
+        for r in res[:n.value]:
+            m = r.n_records
+            out.append(dict(tag=r.tag, row_begin=r.row_begin, whole=bool(r.whole), x=col(r.x, m, np.int32),
+                            y=col(r.y, m, np.int32), p=col(r.prob, m, np.float64), v=col(r.value, m, np.float64),
+                            batch=col(r.batch, m, np.int32),
+                            batch_windows=col(r.batch_windows, r.n_batches, np.int32).astype(np.int64),
+                            n_candidates=int(r.n_candidates), n_windows=int(r.n_windows)))
+        return out
+
+    def reset(self):
+        self._keep = []
+        self._L.pk_engine_reset(self._h)
+
+    def close(self):
+        if self._h:
+            self._L.pk_engine_destroy(self._h)
+            self._h = None
+
+
+def _unit_columns(Lib, key, nd_need, encoding):
+    """The pixel columns of one chromosome in the most compact form the reader offers (or the one asked
+    for): (PK_ENC_*, a, b, c, size)."""
     from . import _lib
-    L = _lib.lib()
-    nrec, nc = C.c_int64(), C.c_int64()
-    _lib.check(L.pk_chrom_result_count(X._h, C.byref(nrec), C.byref(nc), None))
-    m = nrec.value
-    x, y, bt = (np.empty(m, np.int32) for _ in range(3))
-    p, v = np.empty(m, np.float64), np.empty(m, np.float64)
-    _lib.check(L.pk_chrom_fetch_results(X._h, _lib.ptr(x), _lib.ptr(y), _lib.ptr(p), _lib.ptr(v),
-                                        _lib.ptr(bt), m, _lib.PK_MEM_HOST))
-    nb = C.c_int64()
-    _lib.check(L.pk_chrom_batch_windows(X._h, None, 0, C.byref(nb)))
-    bw = np.zeros(max(nb.value, 1), np.int64)
-    _lib.check(L.pk_chrom_batch_windows(X._h, _lib.ptr(bw, _lib.c_i64p), bw.size, C.byref(nb)))
-    return dict(row_begin=a, whole=(a == 0 and b == n), x=x, y=y, p=p, v=v, batch=bt,
-                batch_windows=bw[:nb.value], n_candidates=int(nc.value))
+    n = Lib.nbins(key)
+    if encoding in (None, "rows") and hasattr(Lib, "upper_pixels_rows"):
+        blob = Lib.upper_pixels_rows(key, nd_need)
+        if blob is not None:
+            blob = _lib.as_c(blob, np.uint8)
+            return _lib.PK_ENC_ROWS, blob, None, None, blob.size
+    if encoding == "rows":
+        raise ValueError("no packed rows covering %d distances for chromosome %s" % (nd_need, key))
+    if encoding in (None, "csr16") and hasattr(Lib, "upper_pixels_csr16"):
+        narrow = Lib.upper_pixels_csr16(key)
+        if narrow is not None:
+            rp, d16, c16 = narrow
+            if np.asarray(d16).dtype != np.uint16 or np.asarray(c16).dtype != np.uint16:
+                raise TypeError("upper_pixels_csr16 must return uint16 columns")
+            rp, d16, c16 = _lib.as_c(rp, np.int64), _lib.as_c(d16, np.uint16), _lib.as_c(c16, np.uint16)
+            return _lib.PK_ENC_CSR16, rp, d16, c16, d16.size
+    if encoding == "csr16":
+        raise ValueError("chromosome %s has pixels that uint16 columns cannot hold" % key)
+    if encoding in (None, "csr32") and hasattr(Lib, "upper_pixels_csr"):
+        rp, b2, cnt = Lib.upper_pixels_csr(key)
+        rp, b2, cnt = _lib.as_c(rp, np.int64), _lib.as_c(b2, np.int32), _lib.as_c(cnt, np.int32)
+        if rp.size != n + 1:
+            raise ValueError("bin1_offset must have n_bins + 1 entries")
+        return _lib.PK_ENC_CSR32, rp, b2, cnt, b2.size
+    b1, b2, cnt = Lib.upper_pixels(key)
+    b1, b2, cnt = (_lib.as_c(v, np.int32) for v in (b1, b2, cnt))
+    return _lib.PK_ENC_COO, b1, b2, cnt, b1.size
 
 
-def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_prob, depth=6, shared_score_stream=True):
-    """Score this rank's units. Returns {chrom: [tile dict, ...]}.
+def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_prob, depth=6, copy=True,
+                encoding=None):
+    """Score this rank's units ``(chrom, row_begin, row_end)``. Returns {chrom: [tile dict, ...]}.
 
-    Chromosomes are pipelined over ``depth`` streams: while one chromosome's kernels
-    run, the next one's pixel columns are already crossing the bus. Every call of the
-    library up to the record count is asynchronous, so submitting is cheap."""
-    import ctypes as C
-    from collections import deque
-
+    Everything runs in the library's engine (``pk_engine_*``): the units are queued back to back --
+    while one chromosome's kernels run, the next one's pixel columns are already crossing the bus --
+    and collected with one wait at the end. ``encoding`` forces a column format (``"rows"``,
+    ``"csr16"``, ``"csr32"``, ``"coo"``); by default the most compact one the reader offers is used."""
     from . import _lib
-    from .scoreUtils import Chromosome, DeviceForest
-
+    from .scoreUtils import DeviceForest
+    _lib.require_device()
     forest = DeviceForest.of(flat, device)
-    L = _lib.lib()
-    out = {}
-    by_chrom = {}
-    for k, a, b in units:
-        by_chrom.setdefault(k, []).append((a, b))
-    # `depth` high-priority streams carry the upload and the short stages of the chromosomes in
-    # flight; the scoring passes, which fill the GPU one at a time anyway, share one ordinary
-    # stream. Between two scoring passes the short stages of the chromosomes queued behind run
-    # first and overlap each other.
-    streams = []
-    for _ in range(max(1, depth)):
-        st = C.c_void_p()
-        _lib.check(L.pk_stream_create_priority(device, 1, C.byref(st)))
-        streams.append(st)
-    score_stream = C.c_void_p()
-    _lib.check(L.pk_stream_create_priority(device, 0, C.byref(score_stream)))
-    inflight = deque()
-
-    def finish(job):
-        key, X, tiles, n = job
-        a, b = tiles[0]
-        res_tiles = [_fetch_tile(X, a, b, n)]              # first tile was launched at submit time
-        for a, b in tiles[1:]:
-            _lib.check(L.pk_chrom_find_candidates(X._h, a, b, None))
-            _lib.check(L.pk_chrom_score(X._h, forest.handle, float(min_prob)))
-            res_tiles.append(_fetch_tile(X, a, b, n))
-        X.close()
-        out[key] = res_tiles
-
+    eng = Engine.of(forest, lower, upper, device, depth)
+    w = forest.width
+    keys = []
     try:
-        for i, (key, tiles) in enumerate(by_chrom.items()):
-            if len(inflight) == len(streams):
-                finish(inflight.popleft())
-            weights = Lib.weights(key, correct) if correct else None
+        for key, a, b in units:
             n = Lib.nbins(key)
-            kw = dict(lower=lower, upper=upper, cname=genome_cname(key), res=res, width=flat.width,
-                      device=device, stream=streams[i % len(streams)].value, first_tile=tiles[0],
-                      score_stream=score_stream.value if shared_score_stream else None)
-            narrow = Lib.upper_pixels_csr16(key) if hasattr(Lib, "upper_pixels_csr16") else None
-            if narrow is not None:
-                X = Chromosome.from_csr16(*narrow, weights, n, forest, **kw)
-            elif hasattr(Lib, "upper_pixels_csr"):
-                rp, b2, cnt = Lib.upper_pixels_csr(key)
-                X = Chromosome.from_csr(rp, b2, cnt, weights, n, forest, **kw)
-            else:
-                b1, b2, cnt = Lib.upper_pixels(key)
-                X = Chromosome.from_pixels(b1, b2, cnt, weights, n, forest, sorted_pixels=True, **kw)
-            _lib.check(L.pk_chrom_score(X._h, forest.handle, float(min_prob)))
-            inflight.append((key, X, tiles, n))
-        while inflight:
-            finish(inflight.popleft())
-    finally:
-        for st in streams + [score_stream]:
-            L.pk_stream_destroy(device, st)
+            nd_need = min(upper, n - 2 * w) + 2 * w + 1              # stored distances (scoreUtils.py:14,31)
+            enc, ca, cb, cc, size = _unit_columns(Lib, key, nd_need, encoding)
+            weights = _lib.as_c(Lib.weights(key, correct), np.float64) if correct else None
+            if weights is not None and weights.size != n:
+                raise ValueError("weight column of %s has %d entries for %d bins" % (key, weights.size, n))
+            eng.submit(len(keys), n, a, b, enc, ca, cb, cc, size, weights, min_prob)
+            keys.append(key)
+        results = eng.collect(copy=copy)
+    except BaseException:
+        eng.reset()
+        raise
+    out = {}
+    for key, r in zip(keys, results):
+        out.setdefault(key, []).append(r)
     return out
 
 

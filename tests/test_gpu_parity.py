@@ -67,6 +67,16 @@ def test_taps_match_reference_golden(name):
         X.close()
 
 
+def _windows_after_batch_rule(case, k):
+    """(clist, proba) of the golden windows that survive scoreUtils.py:104-108: windows of a
+    100,000-candidate batch that keeps at most one window are dropped by Chromosome.score."""
+    clist, proba = case.z[k + "clist"], case.z[k + "proba"]
+    rank = {(int(x), int(y)): i for i, (x, y) in enumerate(zip(case.z[k + "ridx"], case.z[k + "cidx"]))}
+    batch = np.array([rank[(int(x), int(y))] // 100000 for x, y in clist], dtype=np.int64)
+    ok = np.bincount(batch, minlength=1)[batch] > 1 if batch.size else np.zeros(0, bool)
+    return clist[ok], proba[ok], int(clist.shape[0])
+
+
 @pytest.fixture
 def tuning():
     from peakachu_b200 import _lib
@@ -88,11 +98,11 @@ def test_all_window_probabilities_bit_exact(name, fused, tuning):
         k = ch.name + "/"
         X = _gpu_chromosome(case, ch)
         x, y, p, v = X.score_records(-1.0)
-        clist, proba = case.z[k + "clist"], case.z[k + "proba"]
+        clist, proba, n_windows = _windows_after_batch_rule(case, k)
         order = np.lexsort((clist[:, 1], clist[:, 0]))
         assert np.array_equal(x, clist[order, 0]) and np.array_equal(y, clist[order, 1])
         assert np.array_equal(p, proba[order])
-        assert X.n_windows == clist.shape[0]
+        assert X.n_windows == n_windows
         X.close()
 
 
@@ -112,7 +122,7 @@ def test_both_forest_encodings_are_exact(name, cf):
                 k = ch.name + "/"
                 X = _gpu_chromosome(case, ch)
                 x, y, p, v = X.score_records(thre)
-                clist, proba = case.z[k + "clist"], case.z[k + "proba"]
+                clist, proba, _ = _windows_after_batch_rule(case, k)
                 order = np.lexsort((clist[:, 1], clist[:, 0]))
                 if thre < 0:
                     assert np.array_equal(x, clist[order, 0]) and np.array_equal(y, clist[order, 1])
@@ -297,6 +307,18 @@ def test_upload_paths_agree():
         assert np.array_equal(N.ridx, W.ridx) and np.array_equal(N.cidx, W.cidx)
         rn, rw = N.score_records(c2["min_prob"]), W.score_records(c2["min_prob"])
         assert all(np.array_equal(u, v) for u, v in zip(rn, rw))
+        # packed pixel rows (pk_chrom_upload_rows): exactly the band's distances, and far more than needed
+        from peakachu_b200 import rowpack
+        for nd_enc in (N._exp_len, N._exp_len + 70):
+            P = Chromosome.from_rows(rowpack.pack_rows(rp, chx.bin2, chx.count, chx.n, nd_enc), wts, chx.n,
+                                     cs.forest, **kw2)
+            assert np.array_equal(P.exp_arr, W.exp_arr)
+            assert np.array_equal(P.ridx, W.ridx) and np.array_equal(P.cidx, W.cidx)
+            assert all(np.array_equal(u, v) for u, v in zip(P.score_records(c2["min_prob"]), rw))
+            P.close()
+        with pytest.raises(_lib.PKError, match="distances"):
+            Chromosome.from_rows(rowpack.pack_rows(rp, chx.bin2, chx.count, chx.n, N._exp_len - 1), wts, chx.n,
+                                 cs.forest, **kw2)
         N.close(); W.close()
     with pytest.raises(TypeError):
         Chromosome.from_csr16(rowptr, ch.bin2, ch.count, ch.weights, ch.n, case.forest, **kw)
@@ -599,6 +621,7 @@ def test_depth_matches_dense_triu_sum(tmp_path, capsys):
     """`depth` (calculate_depth.py:25-28): device reduction = np.triu(raw, k).sum() for every
     upload path, and the sub-command prints the reference's three lines."""
     from peakachu_b200 import calculate_depth, cli, coolio
+    from peakachu_b200 import rowpack
     case = Case("genome")
     path = case.write_cool(tmp_path)
     lib = coolio.PKCool(path)
@@ -610,6 +633,8 @@ def test_depth_matches_dense_triu_sum(tmp_path, capsys):
             assert calculate_depth.chromosome_depth((ch.bin1, ch.bin2, ch.count), ch.n, k) == want
             assert calculate_depth.chromosome_depth((rp, ch.bin2, ch.count), ch.n, k) == want
             assert calculate_depth.chromosome_depth(lib.upper_pixels_csr16(ch.name), ch.n, k) == want
+            assert calculate_depth.chromosome_depth(lib.upper_pixels_rows(ch.name, 0), ch.n, k) == want
+            assert calculate_depth.chromosome_depth(rowpack.pack_rows(rp, ch.bin2, ch.count, ch.n, 40), ch.n, k) == want
         perm = np.random.default_rng(1).permutation(ch.bin1.size)
         got = calculate_depth.chromosome_depth((ch.bin1[perm], ch.bin2[perm], ch.count[perm]), ch.n, 3)
         assert got == int(ch.count[d >= 3].sum())
@@ -627,7 +652,7 @@ def test_full_size_c2_properties():
     forest), where the oracle would take minutes: size-independent properties instead.
     (1) fused kernel == separate feature + forest kernels, record for record, bit for bit;
     (2) pruning (pixels that cannot exceed min_prob stop walking trees) changes nothing;
-    (3) uint16 columns == int32 columns == unordered COO upload;
+    (3) uint16 columns == int32 columns == unordered COO upload == packed pixel rows;
     (4) three band row tiles == the whole chromosome (the multi-GPU seam);
     (5) every record obeys prob > min_prob, lower <= y - x <= upper, and value == (w_x w_y) count;
     (6) a higher min_prob yields exactly the subset of the records above it."""
@@ -664,7 +689,9 @@ def test_full_size_c2_properties():
     perm = np.random.default_rng(3).permutation(ch.bin1.size)
     U = Chromosome.from_pixels(ch.bin1[perm], ch.bin2[perm], ch.count[perm], ch.weights, n, flat,
                                sorted_pixels=False, **kw)
-    for Y in (N, U):
+    from peakachu_b200 import rowpack
+    P = Chromosome.from_rows(rowpack.pack_rows(rp, ch.bin2, ch.count, n, 320), ch.weights, n, flat, **kw)
+    for Y in (N, U, P):
         got = Y.score_records(0.5)
         assert all(np.array_equal(a, b) for a, b in zip(ref, got))
         Y.close()
