@@ -40,12 +40,18 @@ WORKLOADS = {
                desc="score_chromosome chr1-scale synthetic (24,900 bins, 10 kb, w=5, l=6, u=300, 100-tree RF)"),
     "c4": dict(n=49850, res=5000, lower=6, upper=600, w=7, forest="c4", depth=300.0, band=640,
                desc="score_chromosome chr1-scale synthetic at 5 kb (49,850 bins, w=7 / 15x15 windows, l=6, u=600, 200-tree RF)"),
-    # BASELINE configs[2]: score_genome on an hg19-shaped 10 kb genome, sharded over the ranks
-    # (chromosomes + band row tiles, greedy), records gathered on rank 0: strong scaling
-    "c3": dict(genome=True, res=10000, lower=6, upper=300, w=5, forest="c2", depth=300.0, band=330,
-               desc="score_genome hg19-shaped synthetic 10 kb (23 chromosomes, 303,641 bins, w=5, l=6, u=300, 100-tree RF)"),
     "c1": dict(n=2000, res=10000, lower=6, upper=300, w=5, forest="c2", depth=300.0, band=330,
                desc="score_chromosome 2,000-bin synthetic 10 kb (w=5, l=6, u=300, 100-tree RF)"),
+}
+# score_genome workloads (the `genome` block of the JSON line): hg19-shaped genomes sharded over the ranks
+# (chromosomes + band row tiles, greedy), records gathered on rank 0 -- strong scaling
+GENOMES = {
+    # BASELINE configs[2]
+    "c3": dict(res=10000, lower=6, upper=300, w=5, forest="c2", depth=300.0, band=330,
+               desc="score_genome hg19-shaped synthetic 10 kb (23 chromosomes, 303,641 bins, w=5, l=6, u=300, 100-tree RF)"),
+    # BASELINE configs[3]
+    "c4": dict(res=5000, lower=6, upper=600, w=7, forest="c4", depth=300.0, band=640,
+               desc="score_genome hg19-shaped synthetic 5 kb (23 chromosomes, 607,271 bins, w=7 / 15x15 windows, l=6, u=600, 200-tree RF)"),
 }
 KERNELS_PER_STEP = 12  # band_csr, valid_bits, diag_sums, fit_expected, cand_mark, scan2, cand_write, score_fused, emit, row_offsets, record_place, record_pack
 
@@ -107,6 +113,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_config(wl, args):
+    """The `config` object of the JSON line: identical in the GPU arm and the --impl reference arm."""
+    px = band_pixels(wl["n"], wl["lower"], wl["upper"], wl["w"]) if "n" in wl else None
+    return {"workload": wl["desc"],
+            "pixels": "band pixels sum_{d=l..u}(n-d)" + (" = %d per chromosome" % px if px else ""),
+            "per_rank": "one chromosome of the workload per rank per step (weak scaling); the `genome` block of the "
+                        "GPU arm is score_genome on the hg19-shaped map sharded over the ranks (strong scaling)",
+            "forest": "bench_data/%s.pkl" % wl["forest"],
+            "l2": "value: three chromosomes in flight, 3 x ~150 MB of working set > 126 MB L2; stage_ms / roofline: "
+                  "one chromosome at a time with a 256 MiB L2 flush between steps; e2e: every step uploads its "
+                  "inputs from pinned host memory (the host is the cold side)"}
+
+
 # ---------------------------------------------------------------------------
 # CPU arm: the oracle port on host cores (the only place bench.py runs oracle/)
 # ---------------------------------------------------------------------------
@@ -118,7 +137,7 @@ def cpu_pass(wl, n_bins, seed, model):
     from peakachu_b200 import coolio, synth
     ch = synth.make_chromosome("chr1", n_bins, seed=seed, depth=wl["depth"], band=wl["band"])
     path = os.path.join(tempfile.mkdtemp(), "cpu.pkcool")
-    coolio.PKCool.write(path, [ch], wl["res"])
+    coolio.PKCool.write(path, [ch], wl["res"], rows_nd=0)
     lib = coolio.Cooler(path)
     t0 = time.perf_counter()
     st = po.score_map(lib, model, ["chr1"], weight_name="weight", lower=wl["lower"], upper=wl["upper"],
@@ -143,151 +162,201 @@ def _cpu_worker(job):
 
 
 def run_reference_arm(args, wl):
-    """The reference path on the host cores: the reference itself is single-threaded
-    (forest n_jobs=1, sequential chromosome loop), so "all host threads" means one
-    process per chromosome, the only parallelism its design admits."""
+    """The reference path on the host cores, SAME configuration as the GPU arm: every step scores
+    full-size chromosomes of the workload (24,900 bins for c2). The reference is single-threaded
+    (forest n_jobs=1, sequential chromosome loop), so "all host threads" means one process per
+    chromosome, the only parallelism its design admits."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     from concurrent.futures import ProcessPoolExecutor
     workers = max(1, min(os.cpu_count() or 1, args.cpu_workers))
-    n_sample = args.cpu_bins
+    n_sample = args.cpu_bins or wl["n"]
     with ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("fork")) as ex:
         for _ in range(max(args.warmup, 1)):
             list(ex.map(_cpu_worker, [(wl, 600, 5)] * workers))          # imports, model load
         tot_t, tot_px = 0.0, 0
         for s in range(args.steps):
             t0 = time.perf_counter()
-            res = list(ex.map(_cpu_worker, [(wl, n_sample, 100 + s * workers + i) for i in range(workers)]))
+            res = list(ex.map(_cpu_worker, [(wl, n_sample, 1234 + s * workers + i) for i in range(workers)]))
             tot_t += time.perf_counter() - t0
             tot_px += sum(r[1] for r in res)
     val = tot_px / tot_t
-    sample = ("per step: %d chromosomes of %d bins from the c2 synthetic distribution (%d band px each), one "
-              "process each, numpy oracle port of score_chromosome" % (
-                  workers, n_sample, band_pixels(n_sample, wl["lower"], wl["upper"], wl["w"])))
+    sample = ("per step: %d chromosomes of %d bins from the workload's synthetic distribution (%d band px each; the "
+              "GPU arm's chromosome is seed 1234), one process each on %d of %d host threads, numpy oracle port of "
+              "score_chromosome (oracle/peakachu_oracle.py, pinned to the reference's own outputs at this size: "
+              "tests/golden/c2.json)" % (workers, n_sample, band_pixels(n_sample, wl["lower"], wl["upper"], wl["w"]),
+                                         workers, os.cpu_count() or 1))
     print(json.dumps({
-        "impl": "reference", "metric": "candidate pixels scored/sec (window features + RF proba)",
+        "impl": "reference", "metric": METRIC,
         "value": val, "unit": "pixels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "pixels": "band pixels sum_{d=l..u}(n-d)"},
+        "config": workload_config(wl, args),
+        "same_config": n_sample == wl.get("n"),
         "cpu_baseline": {"value": val, "unit": "pixels/s", "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # ---------------------------------------------------------------------------
-# genome workload (extra, not the driver's default): score_genome end to end
+# pinned host maps (what a reader hands to the scoring API, minus the file)
 # ---------------------------------------------------------------------------
-def run_genome(args, wl, flat, rank, world, local):
+def _pinned(a):
+    import torch
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.uint16:                       # torch has no pinned uint16 on every build: pin the bytes
+        return _pinned(a.view(np.uint8)).view(np.uint16)
+    t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
+    v = t.numpy()
+    v[...] = a
+    _PIN_KEEP.append(t)
+    return v
+
+
+_PIN_KEEP = []
+
+
+class PinnedMap:
+    """Chromosomes in pinned host memory in every column format of the C ABI. `alias` maps the
+    names the bench scores (chr1, chr2, ... of identical content) to the stored chromosome."""
+
+    def __init__(self, nd_enc):
+        self.nd_enc, self.ch, self.alias = nd_enc, {}, {}
+
+    def add(self, key, ch, formats=("rows", "csr16", "csr32")):
+        from peakachu_b200 import rowpack
+        rp = np.searchsorted(ch.bin1, np.arange(ch.n + 1)).astype(np.int64)
+        e = dict(n=ch.n, w=_pinned(ch.weights), rp=_pinned(rp), nnz=int(ch.bin1.size))
+        if "csr32" in formats:
+            e["b2"], e["cnt"] = _pinned(ch.bin2), _pinned(ch.count)
+        delta = ch.bin2 - ch.bin1
+        if "csr16" in formats and ch.count.size and int(delta.max()) <= 65535 and int(ch.count.max()) <= 65535:
+            e["d16"], e["c16"] = _pinned(delta.astype(np.uint16)), _pinned(ch.count.astype(np.uint16))
+        if "rows" in formats:
+            e["rows"] = _pinned(rowpack.pack_rows(rp, ch.bin2, ch.count, ch.n, self.nd_enc))
+        self.ch[key] = e
+
+    def _e(self, key): return self.ch[self.alias.get(key, key)]
+    def nbins(self, key): return self._e(key)["n"]
+    def weights(self, key, name): return self._e(key)["w"]
+    def upper_pixels_csr(self, key): e = self._e(key); return e["rp"], e["b2"], e["cnt"]
+    def upper_pixels_csr16(self, key): e = self._e(key); return (e["rp"], e["d16"], e["c16"]) if "d16" in e else None
+    def upper_pixels_rows(self, key, nd_min): e = self._e(key); return e.get("rows") if self.nd_enc >= nd_min else None
+
+    def h2d_bytes(self, key, encoding):
+        e = self._e(key)
+        if encoding == "rows":
+            return int(e["rows"].nbytes) + 8 * e["n"]
+        return (4 if encoding == "csr16" else 8) * e["nnz"] + 8 * (e["n"] + 1) + 8 * e["n"]
+
+
+COLUMNS = {"rows": "packed pixel rows (pk_chrom_upload_rows: presence bitmap + 1 byte per count, one blob per chromosome; "
+                   "what a .pkcool container stores) + weights f64",
+           "csr16": "bin1_offset int64 + (bin2 - bin1) uint16 + count uint16 + weights f64 (pk_chrom_upload_csr16)",
+           "csr32": "cooler's own columns: bin1_offset int64 + bin2 int32 + count int32 + weights f64 (pk_chrom_upload_csr)"}
+
+
+# ---------------------------------------------------------------------------
+# score_genome (BASELINE configs[2], [3]): the whole multi-rank path, strong scaling
+# ---------------------------------------------------------------------------
+def run_genome(args, name, flat, rank, world, local, steps, encodings):
     import torch
     import torch.distributed as dist
     from peakachu_b200 import shard, synth
-
+    wl = GENOMES[name]
     sizes = synth.hg19_bins(wl["res"])
     queue = list(sizes)
     plan = shard.plan(sizes, world, wl["lower"], wl["upper"], wl["w"])
     mine = plan[rank]
     need = sorted({k for k, _, _ in mine}, key=queue.index)
-
-    def pinned(a):
-        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
-        t.numpy()[...] = a
-        return t
-
-    cols, narrow = {}, {}
+    pm = PinnedMap(nd_enc=(wl["upper"] + 2 * wl["w"] + 1 + 31) // 32 * 32)
+    t_gen = time.perf_counter()
     for k in need:
-        ch = synth.make_chromosome(k, sizes[k], seed=5000 + queue.index(k), depth=wl["depth"], band=wl["band"])
-        rp = np.searchsorted(ch.bin1, np.arange(ch.n + 1)).astype(np.int64)
-        cols[k] = tuple(pinned(a) for a in (rp, ch.bin2, ch.count, ch.weights))
-        # narrow columns (bin2 - bin1 and count as uint16), what a .pkcool container / coolio.H5Cool hand over
-        # when every pixel is representable: half the bytes that cross the bus
-        if ch.count.size and int((ch.bin2 - ch.bin1).max()) <= 65535 and int(ch.count.max()) <= 65535:
-            narrow[k] = (pinned((ch.bin2 - ch.bin1).astype(np.uint16).view(np.uint8)),
-                         pinned(ch.count.astype(np.uint16).view(np.uint8)))
-
-    class PinnedGenome:
-        def nbins(self, key): return sizes[key]
-        def weights(self, key, name): return cols[key][3].numpy()
-        def upper_pixels_csr(self, key): return tuple(t.numpy() for t in cols[key][:3])
-        def upper_pixels_csr16(self, key):
-            if key not in narrow:
-                return None
-            d16, c16 = narrow[key]
-            return cols[key][0].numpy(), d16.numpy().view(np.uint16), c16.numpy().view(np.uint16)
-
-    phase_s = [0.0, 0.0, 0.0]          # score_units | gather | merge (this rank, all passes)
-
-    def one_pass():
-        t_a = time.perf_counter()
-        res = shard.score_units(PinnedGenome(), mine, flat, correct="weight", lower=wl["lower"], upper=wl["upper"],
-                                res=wl["res"], device=local, min_prob=0.5)
-        t_b = time.perf_counter()
-        gathered = shard.gather_to_rank0(res, rank, world)
-        t_c = time.perf_counter()
-        n_out = 0
-        if rank == 0:
-            merged = {k: shard.merge_tiles(sorted([q for g in gathered for q in g.get(k, [])],
-                                                  key=lambda q: q["row_begin"])) for k in queue}
-            n_out = sum(int(m[0].size) for m in merged.values())
-        t_d = time.perf_counter()
-        phase_s[0] += t_b - t_a; phase_s[1] += t_c - t_b; phase_s[2] += t_d - t_c
-        return n_out
+        pm.add(k, synth.make_chromosome(k, sizes[k], seed=5000 + queue.index(k), depth=wl["depth"], band=wl["band"]),
+               formats=encodings)
+    t_gen = time.perf_counter() - t_gen
+    px = sum(band_pixels(n, wl["lower"], wl["upper"], wl["w"]) for n in sizes.values())
+    my_px = sum(band_pixels(sizes[k], wl["lower"], wl["upper"], wl["w"]) * (b - a) / sizes[k] for k, a, b in mine)
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
-    for _ in range(max(args.warmup, 1)):
-        one_pass()
-    barrier()
-    phase_s[:] = [0.0, 0.0, 0.0]
-    t0 = time.perf_counter()
-    nrec = 0
-    for _ in range(args.steps):
-        nrec = one_pass()
-    barrier()
-    dt = time.perf_counter() - t0
-    print("rank %d: ms per pass: score_units %.2f, gather %.2f, merge %.2f (%d units)" % (
-        rank, *(1e3 * v / args.steps for v in phase_s), len(mine)), file=sys.stderr)
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
-    px = sum(band_pixels(n, wl["lower"], wl["upper"], wl["w"]) for n in sizes.values())
-    if rank == 0:
-        print(json.dumps({
-            "metric": "candidate pixels scored/sec (window features + RF proba)", "value": px * args.steps / dt,
-            "unit": "pixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "pixels": "band pixels, %d genome-wide" % px,
-                       "timed": "end to end: pinned host columns -> H2D -> kernels -> records D2H -> host gather on rank 0",
-                       "units_per_rank": [len(u) for u in plan], "records_per_step": nrec},
-            "e2e": {"value": px * args.steps / dt, "unit": "pixels/s",
-                    "h2d_bytes_per_step": int(sum((4 if k in narrow else 8) * cols[k][1].numel() + 16 * sizes[k] for k in need)),
-                    "columns": "bin1_offset int64 + (bin2 - bin1) uint16 + count uint16 + weights f64 where representable, else int32 columns",
-                    "d2h_bytes_per_step": 28 * nrec},
-        }))
-    if world > 1:
-        dist.destroy_process_group()
+    out = {}
+    for enc in encodings:
+        phase = np.zeros(3)          # score_units | gather | merge (this rank, all timed passes)
+
+        def one_pass():
+            t_a = time.perf_counter()
+            res = shard.score_units(pm, mine, flat, correct="weight", lower=wl["lower"], upper=wl["upper"],
+                                    res=wl["res"], device=local, min_prob=0.5, copy=False, encoding=enc)
+            t_b = time.perf_counter()
+            gathered = shard.gather_to_rank0(res, rank, world)
+            t_c = time.perf_counter()
+            n_out = 0
+            if rank == 0:
+                merged = {k: shard.merge_tiles(sorted([q for g in gathered for q in g.get(k, [])],
+                                                      key=lambda q: q["row_begin"])) for k in queue}
+                n_out = sum(int(m[0].size) for m in merged.values())
+            t_d = time.perf_counter()
+            phase[:] += (t_b - t_a, t_c - t_b, t_d - t_c)
+            return n_out
+
+        for _ in range(3):
+            one_pass()
+        barrier()
+        phase[:] = 0
+        t0 = time.perf_counter()
+        nrec = 0
+        for _ in range(steps):
+            nrec = one_pass()
+        barrier()
+        dt = time.perf_counter() - t0
+        h2d = sum(pm.h2d_bytes(k, enc) for k, _, _ in mine)
+        t = torch.tensor([dt] + (phase / steps).tolist() + [h2d], dtype=torch.float64, device="cuda")
+        tmax = t.clone()
+        if world > 1:
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dt = float(tmax[0].item())
+        out[enc] = {"ms_per_pass": 1e3 * dt / steps, "pixels_per_s": px * steps / dt,
+                    "pixels_per_s_per_gpu": px * steps / dt / world, "records_per_pass": nrec,
+                    "phase_ms_max_over_ranks": {"score_units": 1e3 * float(tmax[1]), "gather": 1e3 * float(tmax[2]),
+                                                "merge_rank0": 1e3 * float(tmax[3])},
+                    "h2d_bytes_per_pass_all_ranks": int(float(t[4]) + 0.5),
+                    "h2d_bytes_per_pass_max_rank": int(float(tmax[4]) + 0.5),
+                    "pcie_gbs_busiest_rank": float(tmax[4]) / (dt / steps) / 1e9, "columns": COLUMNS[enc]}
+    return {"workload": wl["desc"], "band_pixels": px, "scaling": "strong", "steps": steps,
+            "timed": "whole passes back to back: pinned host columns -> H2D -> kernels -> records D2H -> host gather "
+                     "to rank 0 -> records of every chromosome in the reference's order (bedpe text not formatted)",
+            "units_per_rank": [len(u) for u in plan],
+            "share_of_busiest_rank": max(sum(band_pixels(sizes[k], wl["lower"], wl["upper"], wl["w"]) * (b - a) / sizes[k]
+                                             for k, a, b in u) for u in plan) / px,
+            "synth_s_this_rank": t_gen, "by_columns": out}
 
 
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+METRIC = "candidate pixels scored/sec (window features + RF proba)"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-bins", type=int, default=4000, help="chromosome size of the bounded CPU sample")
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4"])
+    ap.add_argument("--cpu-bins", type=int, default=0, help="chromosome size of the CPU arms (0: the workload's own, 24,900 for c2)")
     ap.add_argument("--cpu-workers", type=int, default=32, help="processes of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--genome", default="auto", help="score_genome blocks in the JSON line: auto (c3 at every N, c4 too at N = 8), "
+                                                     "none, or a comma list of c3,c4")
+    ap.add_argument("--genome-steps", type=int, default=0, help="timed passes of a genome block (0: min(steps, 10))")
     ap.add_argument("--numa", type=int, default=1, help="N > 1: run each rank on the NUMA node of its GPU (0: leave the affinity alone)")
     ap.add_argument("--fused", type=int, default=-1, help="pk_set_tuning('fused'): -1 auto, 0 off, 1, 2")
     ap.add_argument("--prune", type=int, default=1, help="pk_set_tuning('prune'): retire pixels that cannot exceed min_prob")
@@ -299,9 +368,9 @@ def main():
         return
 
     import torch
-    from peakachu_b200 import _lib
+    from peakachu_b200 import _lib, shard
     from peakachu_b200.forest import FlatForest
-    from peakachu_b200.scoreUtils import Chromosome, DeviceForest
+    from peakachu_b200.scoreUtils import DeviceForest
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -314,20 +383,15 @@ def main():
     _lib.require_device()
     numa_node = None
     if world > 1 and args.numa:
-        from peakachu_b200 import shard as _shard
-        numa_node = _shard.bind_to_device_node(local)       # before any pinned allocation
+        numa_node = shard.bind_to_device_node(local)       # before any pinned allocation
     print("rank %d: device %d, NUMA node %s" % (rank, local, numa_node), file=sys.stderr)
     _lib.check(L.pk_set_tuning(b"fused", args.fused))
     _lib.check(L.pk_set_tuning(b"prune", args.prune))
-    if L.pk_set_tuning(b"child_features", args.child_features) != 0 and args.child_features != -1:
-        raise SystemExit("this build of the library has no child_features switch")     # older builds (tools/ab_libs.sh)
+    _lib.check(L.pk_set_tuning(b"child_features", args.child_features))
     args.warmup = max(args.warmup, 3)
 
     flat = FlatForest.load(os.path.join(ROOT, "bench_data", wl["forest"] + "_forest.npz"))
     forest = DeviceForest.of(flat, local)
-    if wl.get("genome"):
-        run_genome(args, wl, flat, rank, world, local)
-        return
     ch = make_map(wl, seed=1234 + rank)
     n, w = ch.n, wl["w"]
     px = band_pixels(n, wl["lower"], wl["upper"], w)
@@ -342,13 +406,13 @@ def main():
     h = C.c_void_p()
     _lib.check(L.pk_chrom_create(local, n, w, wl["lower"], wl["upper"], 1, C.c_void_p(stream.cuda_stream), C.byref(h)))
 
-    def device_step():
-        _lib.check(L.pk_chrom_upload_csr(h, C.c_void_p(d_rp.data_ptr()), C.c_void_p(d_b2.data_ptr()),
+    def device_step(hh):
+        _lib.check(L.pk_chrom_upload_csr(hh, C.c_void_p(d_rp.data_ptr()), C.c_void_p(d_b2.data_ptr()),
                                          C.c_void_p(d_cnt.data_ptr()), nnz, C.c_void_p(d_w.data_ptr()),
                                          _lib.PK_MEM_DEVICE))
-        _lib.check(L.pk_chrom_fit_expected(h))
-        _lib.check(L.pk_chrom_find_candidates(h, 0, n, None))
-        _lib.check(L.pk_chrom_score(h, forest.handle, 0.5))
+        _lib.check(L.pk_chrom_fit_expected(hh))
+        _lib.check(L.pk_chrom_find_candidates(hh, 0, n, None))
+        _lib.check(L.pk_chrom_score(hh, forest.handle, 0.5))
 
     def barrier():
         torch.cuda.synchronize()
@@ -360,7 +424,7 @@ def main():
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
-        device_step()
+        device_step(h)
     barrier()
     # ---- pass 1: one chromosome at a time, L2 flushed between steps: per-kernel times ----
     k1 = min(args.steps, 10)
@@ -371,7 +435,7 @@ def main():
         torch.cuda.synchronize()
         with torch.cuda.stream(stream):
             a.record(stream)
-            device_step()
+            device_step(h)
             b.record(stream)
         stream.synchronize()
         ms = np.zeros(8, dtype=np.float32)
@@ -390,17 +454,8 @@ def main():
         hh = C.c_void_p()
         _lib.check(L.pk_chrom_create(local, n, w, wl["lower"], wl["upper"], 1, C.c_void_p(st.cuda_stream), C.byref(hh)))
         handles.append(hh)
-
-    def flight_step(hh):
-        _lib.check(L.pk_chrom_upload_csr(hh, C.c_void_p(d_rp.data_ptr()), C.c_void_p(d_b2.data_ptr()),
-                                         C.c_void_p(d_cnt.data_ptr()), nnz, C.c_void_p(d_w.data_ptr()),
-                                         _lib.PK_MEM_DEVICE))
-        _lib.check(L.pk_chrom_fit_expected(hh))
-        _lib.check(L.pk_chrom_find_candidates(hh, 0, n, None))
-        _lib.check(L.pk_chrom_score(hh, forest.handle, 0.5))
-
     for i in range(2 * NFLIGHT):
-        flight_step(handles[i % NFLIGHT])
+        device_step(handles[i % NFLIGHT])
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = [torch.cuda.Event(enable_timing=True) for _ in range(NFLIGHT)]
@@ -408,7 +463,7 @@ def main():
     for st in streams:
         st.wait_event(e0)
     for i in range(args.steps):
-        flight_step(handles[i % NFLIGHT])
+        device_step(handles[i % NFLIGHT])
     for st, e in zip(streams, e1):
         e.record(st)
     barrier()
@@ -418,65 +473,53 @@ def main():
         _lib.check(L.pk_chrom_result_count(hh, C.byref(nr2), None, None))   # also checks the device flags
         assert nr2.value == nrec.value
         _lib.check(L.pk_chrom_destroy(hh))
+    _lib.check(L.pk_chrom_destroy(h))
+    del d_rp, d_b2, d_cnt, d_w
 
-    # ---- end to end through the public API with host buffers (pinned, as a reader would fill them) ----
-    def pinned(a):
-        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
-        t.numpy()[...] = a
-        return t
-    p_rp, p_b2, p_cnt, p_w = pinned(rowptr), pinned(ch.bin2), pinned(ch.count), pinned(ch.weights)
-    # narrow columns (bin2 - bin1 and count as uint16: what a .pkcool container stores when every
-    # pixel is representable) halve the bytes that cross the bus
-    narrow_ok = nnz > 0 and int((ch.bin2 - ch.bin1).max()) <= 65535 and int(ch.count.max()) <= 65535
-    if narrow_ok:
-        # torch has no pinned uint16 on every build: pin the bytes and view them
-        p_d16 = pinned((ch.bin2 - ch.bin1).astype(np.uint16).view(np.uint8))
-        p_c16 = pinned(ch.count.astype(np.uint16).view(np.uint8))
+    # ---- end to end through the public API (shard.score_units, the engine of score_genome) with HOST buffers:
+    # per chromosome an H2D of its columns from pinned memory, the kernels, a D2H of its records ----
+    pm = PinnedMap(nd_enc=(wl["upper"] + 2 * w + 1 + 31) // 32 * 32)
+    pm.add("chr1", ch)
+    encs = [e for e in ("rows", "csr16", "csr32") if e != "csr16" or "d16" in pm.ch["chr1"]]
 
-    class PinnedMap:
-        """K chromosomes of the workload shape backed by the pinned columns above: what
-        coolio.open_map hands to the scoring API, minus the file."""
-        def __init__(self, narrow): self.narrow = narrow
-        def nbins(self, key): return n
-        def weights(self, key, name): return p_w.numpy()
-        def upper_pixels_csr(self, key): return p_rp.numpy(), p_b2.numpy(), p_cnt.numpy()
-        def upper_pixels_csr16(self, key):
-            if not self.narrow:
-                return None
-            return p_rp.numpy(), p_d16.numpy().view(np.uint16), p_c16.numpy().view(np.uint16)
+    def e2e_run(k, enc):
+        units = []
+        for i in range(k):
+            pm.alias["c%d" % i] = "chr1"
+            units.append(("c%d" % i, 0, n))
+        return shard.score_units(pm, units, flat, correct="weight", lower=wl["lower"], upper=wl["upper"],
+                                 res=wl["res"], device=local, min_prob=0.5, copy=False, encoding=enc)
 
-    from peakachu_b200 import shard
-
-    def e2e_run(k, narrow):
-        # the public multi-chromosome entry point (score_genome's engine): per chromosome an
-        # H2D of its columns, the kernels, a D2H of its records; chromosomes are pipelined
-        units = [("chr%d" % (i + 1), 0, n) for i in range(k)]
-        return shard.score_units(PinnedMap(narrow), units, flat, correct="weight", lower=wl["lower"],
-                                 upper=wl["upper"], res=wl["res"], device=local, min_prob=0.5)
-
-    def e2e_time(narrow):
-        e2e_run(12, narrow)     # warm the library's block cache for the handles in flight
+    e2e_ms, rec_x = {}, {}
+    for enc in encs:
+        e2e_run(12, enc)                 # warm the engine's handles and staging
         barrier()
         t0 = time.perf_counter()
-        res = e2e_run(args.steps, narrow)
+        res = e2e_run(args.steps, enc)
         torch.cuda.synchronize()
-        return time.perf_counter() - t0, res
-
-    e2e32_s, res32 = e2e_time(False)
-    e2e_s, res_e2e = e2e_time(True) if narrow_ok else (e2e32_s, res32)
-    rec = [res_e2e["chr1"][0]["x"]]
-    assert np.array_equal(rec[0], res32["chr1"][0]["x"])
+        e2e_ms[enc] = 1e3 * (time.perf_counter() - t0)
+        rec_x[enc] = res["c0"][0]["x"].copy()
+        assert all(np.array_equal(rec_x[enc], res["c%d" % i][0]["x"]) for i in range(args.steps))
+    assert all(np.array_equal(rec_x[encs[0]], v) for v in rec_x.values()) and rec_x[encs[0]].size == nrec.value
     clocks = sampler.stop() if rank == 0 else None
-    h2d32 = 8 * nnz + 8 * (n + 1) + 8 * n
-    h2d = (4 * nnz + 8 * (n + 1) + 8 * n) if narrow_ok else h2d32
-    d2h = 28 * int(rec[0].size)
+    d2h = 28 * int(nrec.value) + 64 + 4 * (px // 100000 + 2)
 
     # max over ranks
-    t = torch.tensor([dev_ms, e2e_s * 1e3, e2e32_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms] + [e2e_ms[e] for e in encs], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, e2e32_ms = t.tolist()
-    _lib.check(L.pk_chrom_destroy(h))
+    dev_ms = float(t[0])
+    e2e_ms = {e: float(v) for e, v in zip(encs, t[1:].tolist())}
+
+    # ---- score_genome blocks (strong scaling of BASELINE configs[2] / [3]) ----
+    want = args.genome
+    if want == "auto":
+        want = "c3,c4" if world >= 8 else "c3"
+    genome = {}
+    gsteps = args.genome_steps or min(args.steps, 10)
+    for name in [g for g in want.split(",") if g and g != "none"]:
+        gflat = FlatForest.load(os.path.join(ROOT, "bench_data", GENOMES[name]["forest"] + "_forest.npz"))
+        genome[name] = run_genome(args, name, gflat, rank, world, local, gsteps, ("rows", "csr32"))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -484,7 +527,6 @@ def main():
 
     steps = args.steps
     value = world * px * steps / (dev_ms * 1e-3)
-    e2e_val = world * px * steps / (e2e_ms * 1e-3)
     stage = dict(zip(("band_build", "diag_sums", "expected_fit", "candidate_scan", "features", "forest", "emit"),
                      (stage_acc[:7] / k1).tolist()))
     peaks = {}
@@ -521,38 +563,39 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         model = load_sklearn_model(wl["forest"])
         cpu_pass(wl, 600, 5, model)
-        dt, cpx, ccand, crows = cpu_pass(wl, 6 * args.cpu_bins, 100, model)
+        nb = args.cpu_bins or n
+        dt, cpx, ccand, crows = cpu_pass(wl, nb, 1234, model)
         cpu = {"value": cpx / dt, "unit": "pixels/s", "cores": 1, "kind": "port",
-               "sample": "one %d-bin chromosome of the same synthetic distribution (%d band px, %d candidates), "
+               "sample": "the workload's own chromosome (%d bins, seed 1234: %d band px, %d candidates, %d records), "
                          "numpy oracle port of score_chromosome, 1 of %d host threads (the reference is "
-                         "single-threaded), %.1f s" % (6 * args.cpu_bins, cpx, ccand, os.cpu_count(), dt)}
+                         "single-threaded), %.1f s" % (nb, cpx, ccand, crows, os.cpu_count(), dt)}
+        if nb == n:
+            assert ccand == ncand.value and crows == nrec.value, "CPU oracle and GPU disagree on the bench map"
 
-    print(json.dumps({
-        "metric": "candidate pixels scored/sec (window features + RF proba)",
-        "value": value, "unit": "pixels/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
+    def e2e_block(enc):
+        ms = e2e_ms[enc] / steps
+        hb = pm.h2d_bytes("chr1", enc)
+        return {"value": world * px / (ms * 1e-3), "unit": "pixels/s", "ms_per_step": ms, "h2d_bytes_per_step": hb,
+                "d2h_bytes_per_step": d2h, "pcie_gbs_per_gpu": (hb + d2h) / (ms * 1e-3) / 1e9, "columns": COLUMNS[enc]}
+    head = e2e_block(encs[0])
+    head["api"] = ("peakachu_b200.shard.score_units (the engine of score_genome: pk_engine_submit / pk_engine_collect), "
+                   "pinned host buffers, six chromosomes in flight")
+    line = {
+        "metric": METRIC, "value": value, "unit": "pixels/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "pixels": "band pixels sum_{d=l..u}(n-d) = %d per chromosome" % px,
-                   "per_rank": "one chromosome per rank per step", "candidates_per_step": int(ncand.value),
-                   "windows_per_step": int(nwin.value), "records_per_step": int(nrec.value),
-                   "forest": "%d trees, %d nodes" % (flat.n_trees, flat.n_nodes),
-                   "timed": "%d chromosomes, three in flight on three streams (device-resident CSR columns)" % steps,
-                   "l2": "three working sets in flight (3 x ~150 MB) exceed the 126 MB L2; the per-kernel pass "
-                         "(stage_ms, roofline) runs one chromosome at a time with an L2 flush between steps"},
+        "dtype": "f64", "data": "synthetic", "config": workload_config(wl, args),
+        "run": {"candidates_per_step": int(ncand.value), "windows_per_step": int(nwin.value),
+                "records_per_step": int(nrec.value), "forest": "%d trees, %d nodes" % (flat.n_trees, flat.n_nodes),
+                "timed": "%d chromosomes, three in flight on three streams (device-resident CSR columns)" % steps},
         "candidates_per_s": world * int(ncand.value) * steps / (dev_ms * 1e-3),
-        "stage_ms": stage, "roofline": roofline, "cpu_baseline": cpu,
-        "e2e": {"value": e2e_val, "unit": "pixels/s", "ms_per_step": e2e_ms / steps,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "columns": ("bin1_offset int64 + (bin2 - bin1) uint16 + count uint16 + weights f64 "
-                            "(pk_chrom_upload_csr16, 4 B/pixel)") if narrow_ok else
-                           "bin1_offset int64 + bin2 int32 + count int32 + weights f64 (pk_chrom_upload_csr, 8 B/pixel)",
-                "api": "peakachu_b200.shard.score_units (engine of score_genome), pinned host columns, "
-                       "six chromosomes in flight (uploads and short stages on high-priority streams, "
-                       "the fused kernels back to back on one stream)"},
-        "e2e_int32_columns": {"value": world * px * steps / (e2e32_ms * 1e-3), "unit": "pixels/s",
-                              "ms_per_step": e2e32_ms / steps, "h2d_bytes_per_step": h2d32, "d2h_bytes_per_step": d2h},
-        "gpu_launches": KERNELS_PER_STEP * steps, "clocks": clocks,
-    }))
+        "stage_ms": stage, "roofline": roofline, "cpu_baseline": cpu, "e2e": head,
+    }
+    for enc in encs[1:]:
+        line["e2e_%s_columns" % ("uint16" if enc == "csr16" else "int32")] = e2e_block(enc)
+    line["genome"] = genome
+    line["gpu_launches"] = KERNELS_PER_STEP * steps
+    line["clocks"] = clocks
+    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

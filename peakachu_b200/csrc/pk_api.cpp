@@ -1056,7 +1056,13 @@ static int run_score(pk_chrom* c, pk_forest* f, double min_prob) {
     if (fused) {
         if (c->timing) PK_CUDA(cudaEventRecord(c->ev[8], s));
     } else {
-        if (!c->n_cand_known) PK_CHECK(settle_candidates(c));
+        if (!c->n_cand_known) {
+            // the separate kernels size their launch from the host's candidate count; if the scan had
+            // to be redone with larger buffers, the scoring state is sized again as well
+            const int64_t cap0 = c->cand_cap;
+            PK_CHECK(settle_candidates(c));
+            if (c->cand_cap != cap0) PK_CHECK(reset_score_state(c));
+        }
         PK_CHECK(ensure_feature_buffer(c));
         PK_CHECK(pk_launch_features(c, nullptr));
         if (c->timing) PK_CUDA(cudaEventRecord(c->ev[8], s));
@@ -1203,7 +1209,8 @@ struct pk_engine_slot {
     int32_t row_begin = 0, row_end = 0;
     cudaEvent_t done = nullptr;         // recorded behind the copy of the head block
     size_t head_off = 0;                // in h_head
-    int64_t n_rec = 0;
+    int64_t n_rec = 0, n_cand = 0, n_cand_all = 0, n_win = 0;
+    int32_t n_bins = 0;
     size_t res_off = 0;                 // in h_res
 };
 
@@ -1217,8 +1224,9 @@ struct pk_engine {
     std::vector<pk_chrom*> idle;        // handles kept for reuse
     std::vector<cudaEvent_t> events;    // one per slot index, created on demand
     unsigned char* h_head = nullptr; size_t h_head_bytes = 0, h_head_used = 0;
-    unsigned char* h_res = nullptr; size_t h_res_bytes = 0;
+    unsigned char* h_res = nullptr; size_t h_res_bytes = 0, h_res_used = 0;
     int64_t submitted = 0;
+    int in_flight = 0, max_in_flight = 0;   // units holding a chromosome handle; more than that and the oldest is retired first
     bool collected = true;              // results of the last collect are still exposed
 };
 
@@ -1236,6 +1244,7 @@ extern "C" int pk_engine_create(int device, pk_forest* f, int32_t width, int32_t
     PK_CUDA(cudaSetDevice(device));
     pk_engine* e = new pk_engine();
     e->device = device; e->forest = f; e->w = width; e->lower = lower; e->upper = upper;
+    e->max_in_flight = 2 * depth;
     int lo = 0, hi = 0;                       // numerically lower = higher priority
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     for (int i = 0; i < depth; ++i) {
@@ -1263,7 +1272,7 @@ extern "C" int pk_engine_reset(pk_engine* e) {
     for (auto& u : e->units)
         if (u.c) pk_chrom_destroy(u.c);        // their state is unknown: do not reuse
     e->units.clear();
-    e->h_head_used = 0;
+    e->h_head_used = 0; e->h_res_used = 0; e->in_flight = 0;
     e->collected = true;
     cudaGetLastError();
     return PK_OK;
@@ -1283,6 +1292,8 @@ extern "C" int pk_engine_destroy(pk_engine* e) {
     return PK_OK;
 }
 
+static int engine_retire(pk_engine* e, pk_engine_slot& u);
+
 extern "C" int pk_engine_submit(pk_engine* e, const pk_unit* u) {
     if (!e || !u) { pk_set_error("pk_engine_submit: NULL argument"); return PK_EINVAL; }
     if (u->n_bins <= 0 || u->row_begin < 0 || u->row_end > u->n_bins || u->row_begin > u->row_end) {
@@ -1293,6 +1304,12 @@ extern "C" int pk_engine_submit(pk_engine* e, const pk_unit* u) {
     if (e->collected) {                      // first unit of a new pass: the previous results are released
         e->collected = false;
         e->h_head_used = 0;
+        e->h_res_used = 0;
+    }
+    // bound the device memory of a long queue: beyond max_in_flight the oldest unit is finished first
+    for (auto& q : e->units) {
+        if (e->in_flight < e->max_in_flight) break;
+        if (q.c) PK_CHECK(engine_retire(e, q));
     }
     const int balanced = u->weights != nullptr;
     pk_chrom* c = nullptr;
@@ -1310,6 +1327,10 @@ extern "C" int pk_engine_submit(pk_engine* e, const pk_unit* u) {
         c->use_score_stream = true;
     }
     c->stream = s;
+    if (c->reuse_pending) {                  // the previous unit's record copy may still be on its old stream
+        PK_CUDA(cudaStreamWaitEvent(s, c->ev_x, 0));
+        c->reuse_pending = false;
+    }
     const size_t hb = (c->head_bytes + 63) & ~(size_t)63;
     int r = PK_OK;
     if (e->h_head_used + hb > e->h_head_bytes) { pk_set_error("pk_engine_submit: too many units queued; collect first"); r = PK_ECAPACITY; }
@@ -1350,6 +1371,7 @@ extern "C" int pk_engine_submit(pk_engine* e, const pk_unit* u) {
     }
     e->h_head_used += hb;
     e->units.push_back(slot);
+    ++e->in_flight;
     return PK_OK;
 }
 
@@ -1364,65 +1386,74 @@ static int engine_grow_results(pk_engine* e, size_t need) {
     return PK_OK;
 }
 
+// Finish the oldest unit still in flight: wait for its head block, queue the copy of its records into the
+// pinned result block, hand its chromosome handle back for reuse (the next user's stream waits for that copy).
+static int engine_retire(pk_engine* e, pk_engine_slot& u) {
+    pk_chrom* c = u.c;
+    PK_CUDA(cudaEventSynchronize(u.done));
+    unsigned char* hd = e->h_head + u.head_off;
+    const int32_t* flags = reinterpret_cast<const int32_t*>(hd);
+    const long long* nc = reinterpret_cast<const long long*>(hd + 16);
+    const unsigned long long* cnt = reinterpret_cast<const unsigned long long*>(hd + 32);
+    const bool overflow = flags[0] != 0 || (flags[3] & 2) != 0 || nc[0] > c->cand_cap;
+    const bool trouble = overflow || (flags[2] & 3) != 0 || (c->declared_sorted && (flags[3] & 1));
+    if (trouble) {
+        // a device-side capacity was exceeded (the scan and the scoring are replayed) or the pass failed:
+        // the step-by-step entry points sort it out, then the head block is read again
+        PK_CHECK(pk_chrom_result_count(c, nullptr, nullptr, nullptr));
+        PK_CUDA(cudaMemcpyAsync(hd, c->d_head, c->head_bytes, cudaMemcpyDeviceToHost, c->stream));
+        PK_CUDA(cudaStreamSynchronize(c->stream));
+    } else {
+        c->n_cand = nc[0]; c->n_cand_all = nc[1]; c->n_cand_known = true;
+        memcpy(c->h_counts, cnt, sizeof c->h_counts);
+        c->counts_valid = true;
+    }
+    u.n_rec = (int64_t)c->h_counts[0];
+    u.n_cand = c->n_cand; u.n_cand_all = c->n_cand_all; u.n_win = (int64_t)c->h_counts[1]; u.n_bins = c->n;
+    if (u.n_rec > c->eager_cap) { pk_set_error("pk_engine: %lld records exceed the ordering buffers", (long long)u.n_rec); return PK_ECAPACITY; }
+    const size_t off_f64 = (size_t)((12 * u.n_rec + 7) / 8) * 8;
+    const size_t bytes = off_f64 + 16 * (size_t)u.n_rec;
+    u.res_off = e->h_res_used;
+    e->h_res_used = (e->h_res_used + bytes + 63) & ~(size_t)63;
+    PK_CHECK(engine_grow_results(e, e->h_res_used));
+    if (u.n_rec > 0)
+        PK_CUDA(cudaMemcpyAsync(e->h_res + u.res_off, c->d_packed, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (!c->ev_x) PK_CUDA(cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming));
+    PK_CUDA(cudaEventRecord(c->ev_x, c->stream));        // the next unit on this handle starts behind the copy
+    c->reuse_pending = true;
+    if (e->idle.size() < PK_ENGINE_IDLE_MAX) e->idle.push_back(c);
+    else { pk_chrom_destroy(c); }
+    u.c = nullptr;
+    --e->in_flight;
+    return PK_OK;
+}
+
 extern "C" int pk_engine_collect(pk_engine* e, pk_unit_result* out, int64_t capacity, int64_t* n_units) {
     if (!e || !n_units) { pk_set_error("pk_engine_collect: NULL argument"); return PK_EINVAL; }
     *n_units = (int64_t)e->units.size();
     if (!out) return PK_OK;
     if (capacity < (int64_t)e->units.size()) { pk_set_error("pk_engine_collect: capacity %lld < %zu units", (long long)capacity, e->units.size()); return PK_ECAPACITY; }
     PK_CUDA(cudaSetDevice(e->device));
-    size_t used = 0;
-    for (auto& u : e->units) {
-        pk_chrom* c = u.c;
-        PK_CUDA(cudaEventSynchronize(u.done));
-        unsigned char* hd = e->h_head + u.head_off;
-        const int32_t* flags = reinterpret_cast<const int32_t*>(hd);
-        const long long* nc = reinterpret_cast<const long long*>(hd + 16);
-        const unsigned long long* cnt = reinterpret_cast<const unsigned long long*>(hd + 32);
-        const bool overflow = flags[0] != 0 || (flags[3] & 2) != 0 || nc[0] > c->cand_cap;
-        const bool trouble = overflow || (flags[2] & 3) != 0 || (c->declared_sorted && (flags[3] & 1));
-        if (trouble) {
-            // a device-side capacity was exceeded (the scan and the scoring are replayed) or the pass failed:
-            // the step-by-step entry points sort it out, then the head block is read again
-            PK_CHECK(pk_chrom_result_count(c, nullptr, nullptr, nullptr));
-            PK_CUDA(cudaMemcpyAsync(hd, c->d_head, c->head_bytes, cudaMemcpyDeviceToHost, c->stream));
-            PK_CUDA(cudaStreamSynchronize(c->stream));
-        } else {
-            c->n_cand = nc[0]; c->n_cand_all = nc[1]; c->n_cand_known = true;
-            memcpy(c->h_counts, cnt, sizeof c->h_counts);
-            c->counts_valid = true;
-        }
-        u.n_rec = (int64_t)c->h_counts[0];
-        if (u.n_rec > c->eager_cap) { pk_set_error("pk_engine_collect: %lld records exceed the ordering buffers", (long long)u.n_rec); return PK_ECAPACITY; }
-        const size_t off_f64 = (size_t)((12 * u.n_rec + 7) / 8) * 8;
-        const size_t bytes = off_f64 + 16 * (size_t)u.n_rec;
-        u.res_off = used;
-        used = (used + bytes + 63) & ~(size_t)63;
-        PK_CHECK(engine_grow_results(e, used));
-        if (u.n_rec > 0)
-            PK_CUDA(cudaMemcpyAsync(e->h_res + u.res_off, c->d_packed, bytes, cudaMemcpyDeviceToHost, c->stream));
-    }
+    for (auto& u : e->units)
+        if (u.c) PK_CHECK(engine_retire(e, u));
     engine_drain(e);
     PK_CUDA(cudaGetLastError());
     int64_t i = 0;
     for (auto& u : e->units) {
-        pk_chrom* c = u.c;
         pk_unit_result& r = out[i++];
         const unsigned char* hd = e->h_head + u.head_off;
         const unsigned char* base = e->h_res + u.res_off;
         const size_t off_f64 = (size_t)((12 * u.n_rec + 7) / 8) * 8;
-        r.tag = u.tag; r.n_bins = c->n; r.row_begin = u.row_begin; r.row_end = u.row_end;
-        r.whole = (u.row_begin == 0 && u.row_end == c->n) ? 1 : 0;
-        r.n_records = u.n_rec; r.n_candidates = c->n_cand; r.n_windows = (int64_t)c->h_counts[1];
-        r.n_batches = (c->n_cand_all + PK_BATCH - 1) / PK_BATCH;
+        r.tag = u.tag; r.n_bins = u.n_bins; r.row_begin = u.row_begin; r.row_end = u.row_end;
+        r.whole = (u.row_begin == 0 && u.row_end == u.n_bins) ? 1 : 0;
+        r.n_records = u.n_rec; r.n_candidates = u.n_cand; r.n_windows = u.n_win;
+        r.n_batches = (u.n_cand_all + PK_BATCH - 1) / PK_BATCH;
         r.x = reinterpret_cast<const int32_t*>(base);
         r.y = r.x + u.n_rec;
         r.batch = r.x + 2 * u.n_rec;
         r.prob = reinterpret_cast<const double*>(base + off_f64);
         r.value = r.prob + u.n_rec;
         r.batch_windows = reinterpret_cast<const int32_t*>(hd + 64);
-        if (e->idle.size() < PK_ENGINE_IDLE_MAX) e->idle.push_back(c);
-        else pk_chrom_destroy(c);
-        u.c = nullptr;
     }
     e->units.clear();
     e->collected = true;

@@ -165,6 +165,7 @@ struct pk_chrom {
     cudaStream_t score_stream = nullptr;   // optional second stream for the scoring pass
     bool use_score_stream = false;
     cudaEvent_t ev_x = nullptr;            // hand-over between the two streams
+    bool reuse_pending = false;            // engine: ev_x marks the end of the previous unit's record copy
     unsigned long long h_counts[4] = {0, 0, 0, 0};
     bool counts_valid = false;          // h_counts read since the last scoring pass
     unsigned char* h_stage = nullptr;   // pinned staging for fetch_results

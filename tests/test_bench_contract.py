@@ -24,3 +24,10 @@ def test_reference_arm_prints_one_contract_line():
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["sample"]
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0 and j["e2e"]["value"] == j["value"]
     assert "workload" in j["config"] and j["vs_baseline"] is None
+    assert j["same_config"] is False                       # a 700-bin sample here; the default is the workload's own size
+    # the GPU arm prints the very same config object (the driver compares the two arms)
+    sys.path.insert(0, ROOT)
+    import argparse
+
+    import bench
+    assert j["config"] == bench.workload_config(bench.WORKLOADS["c2"], argparse.Namespace())

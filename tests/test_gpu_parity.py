@@ -784,7 +784,7 @@ def test_batch_rule_whole_chromosome_and_row_tiles():
     edges = [0, 4666, 9333, ch.n]
     tiles = shard.score_units(lib, [(ch.name, a, b) for a, b in zip(edges[:-1], edges[1:])], case.forest, **kw)
     per_tile = [q["batch_windows"].tolist() for q in sorted(tiles[ch.name], key=lambda q: q["row_begin"])]
-    assert per_tile == [[1, 0, 0, 1], [0, 1, 0, 1], [1, 0, 0, 1]]
+    assert per_tile == [[1, 0, 0, 1], [0, 1, 0, 2], [1, 0, 0, 0]]
     assert sum(q["x"].size for q in tiles[ch.name]) == 6           # a tile cannot apply the rule alone
     for res_ in (whole, tiles):
         assert shard.assemble_text([ch.name], [res_], cfg["res"])[ch.name] == case.bedpe
