@@ -269,7 +269,8 @@ def run_genome(args, name, flat, rank, world, local, steps, encodings):
     sizes = synth.hg19_bins(wl["res"])
     queue = list(sizes)
     plan = shard.plan(sizes, world, wl["lower"], wl["upper"], wl["w"])
-    mine = plan[rank]
+    # smallest unit first, as shard.score_chromosomes orders them
+    mine = sorted(plan[rank], key=lambda u: band_pixels(sizes[u[0]], wl["lower"], wl["upper"], wl["w"]) * (u[2] - u[1]) / sizes[u[0]])
     need = sorted({k for k, _, _ in mine}, key=queue.index)
     pm = PinnedMap(nd_enc=(wl["upper"] + 2 * wl["w"] + 1 + 31) // 32 * 32)
     t_gen = time.perf_counter()
@@ -492,7 +493,7 @@ def main():
 
     e2e_ms, rec_x = {}, {}
     for enc in encs:
-        e2e_run(12, enc)                 # warm the engine's handles and staging
+        e2e_run(max(12, args.steps), enc)      # warm the engine's handles and its pinned staging
         barrier()
         t0 = time.perf_counter()
         res = e2e_run(args.steps, enc)

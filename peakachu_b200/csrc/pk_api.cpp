@@ -497,7 +497,7 @@ extern "C" int pk_chrom_destroy(pk_chrom* c) {
     c->d_flags = nullptr; c->d_counters = nullptr; c->d_ncand = nullptr; c->d_batch_win = nullptr;
     dev_free(c->d_rowptr);
     dev_free(c->d_b1); dev_free(c->d_b2); dev_free(c->d_cnt); dev_free(c->d_blob_own);
-    dev_free(c->d_cnt_all); dev_free(c->d_cnt_tile); dev_free(c->d_off_all); dev_free(c->d_off_tile); dev_free(c->d_bits);
+    dev_free(c->d_cstate);
     dev_free(c->d_cx); dev_free(c->d_cd); dev_free(c->d_crank);
     dev_free(c->d_keep); dev_free(c->d_fea32); dev_free(c->d_prob);
     dev_free(c->d_rx); dev_free(c->d_ry); dev_free(c->d_rb); dev_free(c->d_rp); dev_free(c->d_rv);
@@ -813,12 +813,11 @@ static int run_candidates(pk_chrom* c, int32_t kmin) {
     if (nd > 0) {
         c->n_chunks = (c->n + 1023) / 1024;
         const int64_t m = (int64_t)nd * c->n_chunks;
+        if (m >= (1LL << 31)) { pk_set_error("candidate scan: %lld tiles", (long long)m); return PK_EUNSUPPORTED; }
         if (m + 1 > c->cnt_cap) {
-            if (c->d_cnt_all) PK_CHECK(quiesce(c));
-            dev_free(c->d_cnt_all); dev_free(c->d_cnt_tile); dev_free(c->d_off_all); dev_free(c->d_off_tile); dev_free(c->d_bits);
-            PK_CHECK(dev_alloc(&c->d_cnt_all, (size_t)m + 1)); PK_CHECK(dev_alloc(&c->d_cnt_tile, (size_t)m + 1));
-            PK_CHECK(dev_alloc(&c->d_off_all, (size_t)m + 1)); PK_CHECK(dev_alloc(&c->d_off_tile, (size_t)m + 1));
-            PK_CHECK(dev_alloc(&c->d_bits, (size_t)m * 32));
+            if (c->d_cstate) PK_CHECK(quiesce(c));
+            dev_free(c->d_cstate);
+            PK_CHECK(dev_alloc(&c->d_cstate, (size_t)m + 1));
             c->cnt_cap = m + 1;
         }
         const double* d_crit = nullptr;
@@ -1378,7 +1377,7 @@ extern "C" int pk_engine_submit(pk_engine* e, const pk_unit* u) {
 static int engine_grow_results(pk_engine* e, size_t need) {
     if (need <= e->h_res_bytes) return PK_OK;
     engine_drain(e);                          // earlier record copies land in the old block first
-    size_t want = std::max<size_t>(need + need / 2, 4 << 20);
+    size_t want = std::max<size_t>(2 * need, 16 << 20);
     unsigned char* nb = nullptr;
     if (cudaMallocHost((void**)&nb, want) != cudaSuccess) { pk_set_error("pk_engine_collect: %zu bytes of pinned memory", want); cudaGetLastError(); return PK_ENOMEM; }
     if (e->h_res) { memcpy(nb, e->h_res, e->h_res_bytes); cudaFreeHost(e->h_res); }

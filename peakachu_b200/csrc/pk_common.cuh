@@ -123,12 +123,8 @@ struct pk_chrom {
     long long rows_hdr[16] = {};     // host copy of the blob's header
     // candidates
     int32_t n_chunks = 0;
-    uint32_t* d_cnt_all = nullptr;   // [nd_cand * n_chunks] whole-chromosome counts
-    uint32_t* d_cnt_tile = nullptr;  // same, restricted to the row tile
-    uint32_t* d_off_all = nullptr;   // exclusive scans (+1 total)
-    uint32_t* d_off_tile = nullptr;
+    unsigned long long* d_cstate = nullptr;   // [nd_cand * n_chunks + 1] look-back states of the candidate scan + tile ticket
     int64_t cnt_cap = 0;
-    uint32_t* d_bits = nullptr;      // [nd_cand * n_chunks * 32] one bit per band slot
     long long* d_ncand = nullptr;    // [2]: candidates in the row tile, in the whole chromosome
     int64_t n_cand = 0, n_cand_all = 0;   // host copies, valid when n_cand_known
     bool n_cand_known = false;

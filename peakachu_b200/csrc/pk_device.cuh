@@ -19,6 +19,19 @@ __device__ constexpr double PK_GK[5] = {0x1.18a9c4fd536c6p-13, 0x1.22724cb7eb269
 // scipy mode='reflect' (d c b a | a b c d | d c b a)
 __host__ __device__ constexpr int pk_reflect(int i, int S) { return i < 0 ? -i - 1 : (i >= S ? 2 * S - i - 1 : i); }
 
+// a / b, correctly rounded, from a correctly rounded reciprocal r = RN(1/b): two
+// residual corrections (q' = q + (a - b q) r with exact FMA residuals). The first makes q
+// faithful, the second is then correctly rounded (Markstein). Valid away from
+// overflow/underflow; callers take __ddiv_rn otherwise. Checked against __ddiv_rn on the
+// device by pk_selftest_divide.
+__device__ __forceinline__ double pk_div_r(double a, double b, double r) {
+    double q = __dmul_rn(a, r);
+    q = __fma_rn(__fma_rn(-b, q, a), r, q);
+    q = __fma_rn(__fma_rn(-b, q, a), r, q);
+    return q;
+}
+__device__ __forceinline__ bool pk_div_safe(double v) { return v >= 1e-100 && v <= 1e100; }   // false for NaN
+
 // packed forest node (see pk_common.cuh): leaf <=> sign bit of .y clear
 #define PK_NODE_INTERNAL(y) ((int)(y) < 0)
 #define PK_NODE_FEAT4(y) ((y) & 0xFFCu)               /* feature index * 4 (byte offset into a float row) */

@@ -96,19 +96,6 @@ struct FusedCfg {
     }
 };
 
-// a / b, correctly rounded, from a correctly rounded reciprocal r = RN(1/b): two
-// residual corrections (q' = q + (a - b q) r with exact FMA residuals). The first makes q
-// faithful, the second is then correctly rounded (Markstein). Valid away from
-// overflow/underflow; callers take __ddiv_rn otherwise. Checked against __ddiv_rn on the
-// device by pk_selftest_divide.
-__device__ __forceinline__ double pk_div_r(double a, double b, double r) {
-    double q = __dmul_rn(a, r);
-    q = __fma_rn(__fma_rn(-b, q, a), r, q);
-    q = __fma_rn(__fma_rn(-b, q, a), r, q);
-    return q;
-}
-__device__ __forceinline__ bool pk_div_safe(double v) { return v >= 1e-100 && v <= 1e100; }   // false for NaN
-
 // order-preserving map double -> uint64 (integer min / max reductions) and back
 __device__ __forceinline__ unsigned long long pk_key(double v) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(v);

@@ -329,60 +329,89 @@ __device__ __forceinline__ uint32_t pk_pair_word(const uint32_t* __restrict__ vb
     return vb[x0 >> 5] & __funnelshift_r(lo, hi, y0 & 31);
 }
 
-template <int CAP>
-__global__ void __launch_bounds__(PK_DS_THREADS) k_diag_sums(
+// Compaction, wide: CTA (slice, d) owns PK_DC_SLICE consecutive x of diagonal d. Its output offset is the
+// number of valid pairs before its slice, counted straight from the bit vector (at most n / 32 words), so
+// no scan kernel and no ordering between CTAs is needed. Slice 0 also writes the diagonal's total.
+#define PK_DC_SLICE 2048
+__global__ void __launch_bounds__(256) k_diag_compact(
     const int32_t* __restrict__ band, const double* __restrict__ w, const uint32_t* __restrict__ vbits, int n_words,
-    int n, long long pitch, int balanced, double* __restrict__ scratch,
-    double* __restrict__ out_sum, long long* __restrict__ out_cnt, int32_t* __restrict__ flags) {
-    constexpr int NWARP = PK_DS_THREADS / 32;
-    extern __shared__ __align__(16) unsigned char ds_raw[];
-    DiagSmem<CAP>& sm = *reinterpret_cast<DiagSmem<CAP>*>(ds_raw);
-    uint32_t* s_vb = reinterpret_cast<uint32_t*>(ds_raw + sizeof(DiagSmem<CAP>));     // [n_words + 2]
-    const int d = blockIdx.x;
-    const int len = n - d;
+    int n, long long pitch, int balanced, double* __restrict__ scratch, long long* __restrict__ out_cnt) {
+    extern __shared__ uint32_t s_vbc[];                 // [n_words + 2]
+    __shared__ int s_part[8];
+    const int d = blockIdx.y, len = n - d;
+    const int xs = blockIdx.x * PK_DC_SLICE;
+    if (xs >= len && blockIdx.x != 0) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    double* sc = scratch + (long long)d * pitch;
-    const int32_t* row = band + (long long)d * pitch;
-    for (int i = tid; i < n_words + 2; i += PK_DS_THREADS) s_vb[i] = i < n_words ? vbits[i] : 0u;
+    for (int i = tid; i < n_words + 2; i += 256) s_vbc[i] = i < n_words ? vbits[i] : 0u;
     __syncthreads();
-    // ---- compaction: slice of this warp, a multiple of 256 elements ----
-    const int per = len > 0 ? (((len + NWARP - 1) / NWARP + 255) & ~255) : 0;
-    const int xb = wid * per, xe = min(len, xb + per);
+    // valid pairs in the words before this slice (slice 0: in the whole diagonal, for out_cnt)
+    const int w_end = blockIdx.x == 0 ? (len + 31) / 32 : xs / 32;
     int cntw = 0;
-    for (int x0 = xb + lane * 32; x0 < xe; x0 += 1024) {
-        uint32_t m = pk_pair_word(s_vb, x0, d);
-        if (x0 + 32 > xe) m &= (1u << (xe - x0)) - 1u;       // xe - x0 in [1, 31]
+    for (int wi = tid; wi < w_end; wi += 256) {
+        uint32_t m = pk_pair_word(s_vbc, wi * 32, d);
+        if (wi * 32 + 32 > len) m &= (len - wi * 32 > 0) ? ((1u << (len - wi * 32)) - 1u) : 0u;
         cntw += __popc(m);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cntw += __shfl_xor_sync(0xffffffffu, cntw, o);
-    if (lane == 0) sm.wcnt[wid] = cntw;
+    if (lane == 0) s_part[wid] = cntw;
     __syncthreads();
-    int base = 0, nd = 0;
+    int before = 0;
 #pragma unroll
-    for (int k = 0; k < NWARP; ++k) {
-        const int t = sm.wcnt[k];
-        if (k < wid) base += t;
-        nd += t;
+    for (int k = 0; k < 8; ++k) before += s_part[k];
+    if (blockIdx.x == 0) {
+        if (tid == 0) out_cnt[d] = before;
+        before = 0;
     }
-    for (int x0 = xb; x0 < xe; x0 += 256) {
-        uint32_t m[8]; int c[8]; double wa[8], wb[8];
+    if (xs >= len) return;
+    // this warp's 256 elements: valid pairs before them inside the slice
+    const int xe = min(len, xs + PK_DC_SLICE);
+    const int xw0 = xs + wid * 256;
+    uint32_t m[8];
+    int mine = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int xw = x0 + j * 32, x = xw + lane;
-            m[j] = xw < xe ? pk_pair_word(s_vb, xw, d) : 0u;
-            if (xw < xe && xw + 32 > xe) m[j] &= (1u << (xe - xw)) - 1u;
-            const bool f = (m[j] >> lane) & 1u;
-            c[j] = f ? __ldg(row + x) : 0;
-            wa[j] = (f && balanced) ? __ldg(w + x) : 0.0;
-            wb[j] = (f && balanced) ? __ldg(w + x + d) : 0.0;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if ((m[j] >> lane) & 1u) sc[base + __popc(m[j] & ((1u << lane) - 1u))] = pk_value(c[j], wa[j], wb[j], balanced);
-            base += __popc(m[j]);
-        }
+    for (int j = 0; j < 8; ++j) {
+        const int xw = xw0 + j * 32;
+        m[j] = xw < xe ? pk_pair_word(s_vbc, xw, d) : 0u;
+        if (xw < xe && xw + 32 > xe) m[j] &= (1u << (xe - xw)) - 1u;
+        mine += __popc(m[j]);
     }
+    __syncthreads();
+    if (lane == 0) s_part[wid] = mine;
+    __syncthreads();
+    int base = before;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (k < wid) base += s_part[k];
+    double* sc = scratch + (long long)d * pitch;
+    const int32_t* row = band + (long long)d * pitch;
+    int c[8]; double wa[8], wb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int x = xw0 + j * 32 + lane;
+        const bool f = (m[j] >> lane) & 1u;
+        c[j] = f ? __ldg(row + x) : 0;
+        wa[j] = (f && balanced) ? __ldg(w + x) : 0.0;
+        wb[j] = (f && balanced) ? __ldg(w + x + d) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if ((m[j] >> lane) & 1u) sc[base + __popc(m[j] & ((1u << lane) - 1u))] = pk_value(c[j], wa[j], wb[j], balanced);
+        base += __popc(m[j]);
+    }
+}
+
+// Sums: one CTA per distance over the compacted row (k_diag_compact): numpy's pairwise tree built level by
+// level in shared memory, leaf sums by lane octets, combined back up the same tree.
+template <int CAP>
+__global__ void __launch_bounds__(PK_DS_THREADS) k_diag_sums(
+    long long pitch, const double* __restrict__ scratch,
+    double* __restrict__ out_sum, const long long* __restrict__ out_cnt, int32_t* __restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char ds_raw[];
+    DiagSmem<CAP>& sm = *reinterpret_cast<DiagSmem<CAP>*>(ds_raw);
+    const int d = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double* sc = scratch + (long long)d * pitch;
+    const int nd = (int)out_cnt[d];
     // ---- leaf table, level by level ----
     if (tid == 0) { sm.seg_s[0][0] = 0; sm.seg_m[0][0] = nd; sm.nseg[0] = 1; }
     __syncthreads();                       // also: scratch row complete (block-scope visibility)
@@ -433,7 +462,7 @@ __global__ void __launch_bounds__(PK_DS_THREADS) k_diag_sums(
         cur ^= 1;
     }
     if (overflow) {                         // diagonal longer than the shared-memory tables: refuse loudly
-        if (tid == 0) { atomicOr(&flags[2], 2); out_sum[d] = CUDART_NAN; out_cnt[d] = nd; }
+        if (tid == 0) { atomicOr(&flags[2], 2); out_sum[d] = CUDART_NAN; }
         return;
     }
     // ---- leaf sums (8 strided accumulators + tail), one leaf per thread ----
@@ -459,10 +488,7 @@ __global__ void __launch_bounds__(PK_DS_THREADS) k_diag_sums(
         __syncthreads();
         vc ^= 1;
     }
-    if (tid == 0) {
-        out_sum[d] = sm.val[vc][0];
-        out_cnt[d] = nd;
-    }
+    if (tid == 0) out_sum[d] = sm.val[vc][0];
 }
 
 // ---------------------------------------------------------------------------
@@ -525,7 +551,20 @@ __global__ void __launch_bounds__(PK_FIT_THREADS) k_fit_expected(
     }
     for (int i = tid; i < n; i += PK_FIT_THREADS) { s_e[i] = s_ky[n - 1 - i]; s_w[i] = 1.0; }
     __syncthreads();
+    // s_ky is dead until the knots: it holds RN(1 / k), k = 1..PK_FIT_MAX, during PAVA, which divides by
+    // block weights (sums of unit weights: small integers)
+    double* s_rcp = s_ky;
+    for (int k = tid; k < PK_FIT_MAX; k += PK_FIT_THREADS) s_rcp[k] = __ddiv_rn(1.0, (double)(k + 1));
+    __syncthreads();
     // ---- PAVA on the reversed values (sequential; the block top lives in registers) ----
+    // The chain of dependent float64 divisions is what this kernel waits for. Block weights are sums of unit
+    // weights, i.e. exact integers <= n: sb / wb goes through the tabulated reciprocal with two residual
+    // corrections (pk_div_r: bit-identical to IEEE division inside its guarded range, else __ddiv_rn).
+    auto div_w = [&](double sb, double wb) -> double {
+        const int k = (int)wb;
+        if (pk_div_safe(sb) && k >= 1 && k <= PK_FIT_MAX && (double)k == wb) return pk_div_r(sb, wb, s_rcp[k - 1]);
+        return __ddiv_rn(sb, wb);
+    };
     if (tid == 0) {
         s_r[0] = 0;
         s_r[1] = 1;
@@ -538,18 +577,18 @@ __global__ void __launch_bounds__(PK_FIT_THREADS) k_fit_expected(
                 b--;
                 double sb = __dadd_rn(__dmul_rn(wb_prev, xb_prev), __dmul_rn(wb, xb));
                 wb = __dadd_rn(wb, wb_prev);
-                xb = __ddiv_rn(sb, wb);
+                xb = div_w(sb, wb);
                 while (i < n - 1 && xb >= s_e[i + 1]) {
                     i++;
                     sb = __dadd_rn(sb, __dmul_rn(1.0, s_e[i]));
                     wb = __dadd_rn(wb, 1.0);
-                    xb = __ddiv_rn(sb, wb);
+                    xb = div_w(sb, wb);
                 }
                 while (b > 0 && s_e[b - 1] >= xb) {
                     b--;
                     sb = __dadd_rn(sb, __dmul_rn(s_w[b], s_e[b]));
                     wb = __dadd_rn(wb, s_w[b]);
-                    xb = __ddiv_rn(sb, wb);
+                    xb = div_w(sb, wb);
                 }
             }
             s_e[b] = xb_prev = xb;
@@ -614,28 +653,41 @@ __global__ void __launch_bounds__(PK_FIT_THREADS) k_fit_expected(
 }
 
 // ---------------------------------------------------------------------------
-// S4  Poisson candidate scan (scoreUtils.py:40-68).
+// S4  Poisson candidate scan (scoreUtils.py:40-68), one pass over the band.
 //     candidate <=> count > 0 and mu = bg[d] / (w_x * w_y) satisfies 0 <= mu < crit[count].
-//     Reference order is distance asc, row asc. Pass 1 evaluates every band slot
-//     once (4 slots per thread, loads first), keeps one bit per slot and counts per
-//     (distance, 1024-row chunk); a scan gives offsets; pass 2 expands the bits into
-//     the ordered candidate list. Nothing is returned to the host.
+//     Reference order is distance asc, row asc, and every candidate needs its rank in that order over
+//     the whole chromosome (the 100,000-candidate batches of scoreUtils.py:104) and its position in the
+//     list of this row tile. Tiles of 1024 band slots are taken in that order (an atomic ticket), each
+//     tile evaluates its slots (4 per thread, loads first), publishes its two counts in one 64-bit word and
+//     obtains the counts of all earlier tiles by decoupled look-back (aggregate / inclusive-prefix states,
+//     a warp inspecting 32 predecessors at a time), then writes its candidates straight to their final
+//     positions. No bit array, no scan kernel, no second pass over the slots.
+//     state word: [63:62] 0 empty, 1 aggregate, 2 inclusive prefix | [61:31] count over all rows | [30:0] count in the row tile
 // ---------------------------------------------------------------------------
 #define PK_CHUNK 1024
 
-__global__ void __launch_bounds__(256) k_cand_mark(
+__device__ __forceinline__ unsigned long long pk_cs_pack(unsigned status, unsigned a, unsigned t) {
+    return ((unsigned long long)status << 62) | ((unsigned long long)a << 31) | (unsigned long long)t;
+}
+
+__global__ void __launch_bounds__(256) k_cand_scan(
     const int32_t* __restrict__ band, const double* __restrict__ w, const double* __restrict__ bg,
     int n, long long pitch, int balanced, int lower, const double* __restrict__ crit, int kmax,
-    int row_begin, int row_end, int n_chunks, uint32_t* __restrict__ bits,
-    uint32_t* __restrict__ cnt_all, uint32_t* __restrict__ cnt_tile, int32_t* __restrict__ flags) {
-    const int chunk = blockIdx.x, di = blockIdx.y, d = lower + di;
+    int row_begin, int row_end, int n_chunks, unsigned n_tiles, unsigned long long* __restrict__ state,
+    unsigned* __restrict__ ticket, long long cap, int32_t* __restrict__ cx, int32_t* __restrict__ cd,
+    int32_t* __restrict__ crank, long long* __restrict__ ncand, int32_t* __restrict__ flags) {
+    __shared__ unsigned s_tile;
+    __shared__ int s_ca[4][8], s_ct[4][8];
+    __shared__ unsigned s_ea, s_et;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned t = s_tile;
+    const int di = (int)(t / (unsigned)n_chunks), chunk = (int)(t - (unsigned)di * (unsigned)n_chunks), d = lower + di;
     const int len = n - d;
     const double e = bg[d];
     const bool d_ok = (len > 0) && (e > 0.0);
     const int32_t* row = band + (long long)d * pitch;
-    const long long slot = (long long)di * n_chunks + chunk;
-    __shared__ int s_a[8], s_t[8];
     // counts and weights are loaded side by side with bg[d] (one memory round trip, not three)
     int k[4];
     double wx[4], wy[4];
@@ -651,7 +703,7 @@ __global__ void __launch_bounds__(256) k_cand_mark(
 #pragma unroll
         for (int j = 0; j < 4; ++j) k[j] = 0;
     }
-    int tot_a = 0, tot_t = 0;
+    unsigned ba[4], bt[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int x = chunk * PK_CHUNK + j * 256 + tid;
@@ -662,74 +714,71 @@ __global__ void __launch_bounds__(256) k_cand_mark(
             if (k[j] > kmax) atomicOr(&flags[0], 1);
             else c = (mu >= 0.0) && (mu < crit[k[j]]);
         }
-        const unsigned ba = __ballot_sync(0xffffffffu, c);
-        const unsigned bt = __ballot_sync(0xffffffffu, c && x >= row_begin && x < row_end);
-        if (lane == 0) bits[slot * 32 + j * 8 + wid] = ba;
-        tot_a += __popc(ba);
-        tot_t += __popc(bt);
+        ba[j] = __ballot_sync(0xffffffffu, c);
+        bt[j] = __ballot_sync(0xffffffffu, c && x >= row_begin && x < row_end);
+        if (lane == 0) { s_ca[j][wid] = __popc(ba[j]); s_ct[j][wid] = __popc(bt[j]); }
     }
-    if (lane == 0) { s_a[wid] = tot_a; s_t[wid] = tot_t; }
     __syncthreads();
-    if (tid == 0) {
-        int a = 0, t = 0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { a += s_a[q]; t += s_t[q]; }
-        cnt_all[slot] = a; cnt_tile[slot] = t;
-    }
-}
-
-// exclusive scan of two uint32 arrays of length m; totals -> totals[0..1] (as int64) and at [m]
-__global__ void __launch_bounds__(1024) k_scan2(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
-                                                long long m, uint32_t* __restrict__ oa, uint32_t* __restrict__ ob,
-                                                long long* __restrict__ totals) {
-    __shared__ uint32_t s_warp[33];
-    const uint32_t ta = pk_cta_scan_1024(a, m, oa, s_warp);
-    const uint32_t tb = pk_cta_scan_1024(b, m, ob, s_warp);
-    if (threadIdx.x == 0) { totals[0] = tb; totals[1] = ta; }
-}
-
-__global__ void __launch_bounds__(256) k_cand_write(
-    const uint32_t* __restrict__ bits, const uint32_t* __restrict__ off_all, const uint32_t* __restrict__ off_tile,
-    int lower, int row_begin, int row_end, int n_chunks, long long cap,
-    int32_t* __restrict__ cx, int32_t* __restrict__ cd, int32_t* __restrict__ crank, int32_t* __restrict__ flags) {
-    const int chunk = blockIdx.x, di = blockIdx.y, d = lower + di;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long slot = (long long)di * n_chunks + chunk;
-    if (off_all[slot + 1] == off_all[slot]) return;           // no candidate in this chunk
-    __shared__ uint32_t s_pa[32], s_pt[32], s_word[32];
     if (wid == 0) {
-        // word q covers rows chunk*1024 + (q/8)*256 + (q%8)*32 .. +31, i.e. rows ascend with q
-        const uint32_t word = bits[slot * 32 + lane];
-        const int xw = chunk * PK_CHUNK + (lane >> 3) * 256 + (lane & 7) * 32;
-        uint32_t inr = 0;
-        for (int b = 0; b < 32; ++b)
-            if (xw + b >= row_begin && xw + b < row_end) inr |= 1u << b;
-        uint32_t ca = __popc(word), ct = __popc(word & inr);
-        uint32_t xa = ca, xt = ct;
+        // tile totals (32 partial counts, one per lane)
+        unsigned agg_a = (unsigned)s_ca[lane >> 3][lane & 7], agg_t = (unsigned)s_ct[lane >> 3][lane & 7];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t ta = __shfl_up_sync(0xffffffffu, xa, o), tt = __shfl_up_sync(0xffffffffu, xt, o);
-            if (lane >= o) { xa += ta; xt += tt; }
+        for (int o = 16; o > 0; o >>= 1) {
+            agg_a += __shfl_xor_sync(0xffffffffu, agg_a, o);
+            agg_t += __shfl_xor_sync(0xffffffffu, agg_t, o);
         }
-        s_pa[lane] = off_all[slot] + xa - ca;
-        s_pt[lane] = off_tile[slot] + xt - ct;
-        s_word[lane] = word;
+        volatile unsigned long long* vstate = state;
+        if (lane == 0) vstate[t] = pk_cs_pack(t == 0 ? 2u : 1u, agg_a, agg_t);
+        unsigned ea = 0, et = 0;
+        if (t > 0) {
+            long long look = (long long)t - 1;
+            for (;;) {
+                const long long i = look - lane;
+                unsigned long long v = pk_cs_pack(2u, 0u, 0u);              // before the first tile: prefix 0
+                if (i >= 0) v = vstate[i];
+                const unsigned st = (unsigned)(v >> 62);
+                if (__any_sync(0xffffffffu, st == 0u)) continue;             // a predecessor has not published yet
+                const unsigned pm = __ballot_sync(0xffffffffu, st == 2u);
+                const int first = pm ? __ffs(pm) - 1 : 32;                    // nearest predecessor holding a prefix
+                unsigned va = lane <= first ? (unsigned)((v >> 31) & 0x7FFFFFFFull) : 0u;
+                unsigned vt = lane <= first ? (unsigned)(v & 0x7FFFFFFFull) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    va += __shfl_xor_sync(0xffffffffu, va, o);
+                    vt += __shfl_xor_sync(0xffffffffu, vt, o);
+                }
+                ea += va; et += vt;
+                if (pm) break;
+                look -= 32;
+            }
+            if (lane == 0) vstate[t] = pk_cs_pack(2u, ea + agg_a, et + agg_t);
+        }
+        if (lane == 0) {
+            s_ea = ea; s_et = et;
+            if (t == n_tiles - 1) { ncand[0] = (long long)(et + agg_t); ncand[1] = (long long)(ea + agg_a); }
+        }
     }
     __syncthreads();
+    // candidates of this tile, in slot order (j, warp, lane), to their final positions
+    unsigned pa = s_ea, pt = s_et;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int q = j * 8 + wid;
-        const uint32_t word = s_word[q];
-        const int x = chunk * PK_CHUNK + j * 256 + tid;
-        const bool c = (word >> lane) & 1u;
-        const bool t = c && x >= row_begin && x < row_end;
-        const unsigned bt = __ballot_sync(0xffffffffu, t);
-        if (t) {
-            const unsigned lm = (1u << lane) - 1u;
-            const long long rt = (long long)s_pt[q] + __popc(bt & lm);
-            const uint32_t ra = s_pa[q] + __popc(word & lm);
-            if (rt < cap) { cx[rt] = x; cd[rt] = d; crank[rt] = (int32_t)ra; }
-            else atomicOr(&flags[3], 2);                       // candidate buffer too small
+        unsigned ja = pa, jt = pt;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (q < wid) { ja += (unsigned)s_ca[j][q]; jt += (unsigned)s_ct[j][q]; }
+            pa += (unsigned)s_ca[j][q]; pt += (unsigned)s_ct[j][q];
+        }
+        const unsigned lm = (1u << lane) - 1u;
+        if ((bt[j] >> lane) & 1u) {
+            const long long rt = (long long)jt + __popc(bt[j] & lm);
+            if (rt < cap) {
+                cx[rt] = chunk * PK_CHUNK + j * 256 + tid;
+                cd[rt] = d;
+                crank[rt] = (int32_t)(ja + __popc(ba[j] & lm));
+            } else {
+                atomicOr(&flags[3], 2);                                   // candidate buffer too small
+            }
         }
     }
 }
@@ -882,12 +931,10 @@ int pk_launch_rowptr(pk_chrom* c, const int32_t* b1, const int32_t* b2, int64_t 
 }
 
 template <int CAP>
-static int launch_diag_sums_t(pk_chrom* c, int n_words) {
-    const size_t smem = sizeof(DiagSmem<CAP>) + ((size_t)n_words + 2) * 4;
+static int launch_diag_sums_t(pk_chrom* c) {
+    const size_t smem = sizeof(DiagSmem<CAP>);
     PK_OPT_IN_SMEM(k_diag_sums<CAP>, smem, c->device);
-    k_diag_sums<CAP><<<c->ND, PK_DS_THREADS, smem, c->stream>>>(c->d_band, c->d_w, c->d_vbits, n_words, c->n, c->pitch,
-                                                                c->balanced, c->d_scratch, c->d_diag_sum, c->d_diag_cnt,
-                                                                c->d_flags);
+    k_diag_sums<CAP><<<c->ND, PK_DS_THREADS, smem, c->stream>>>(c->pitch, c->d_scratch, c->d_diag_sum, c->d_diag_cnt, c->d_flags);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
@@ -897,9 +944,16 @@ int pk_launch_diag_sums(pk_chrom* c) {
     k_valid_bits<<<std::min((n_words + 7) / 8, 148 * 4), 256, 0, c->stream>>>(c->d_valid, c->d_w, c->balanced, c->n, c->d_vbits, n_words,
                                                                 c->d_flags);
     PK_CUDA(cudaGetLastError());
+    const size_t smem_c = ((size_t)n_words + 2) * 4;
+    if (smem_c > 200 * 1024) { pk_set_error("chromosome of %d bins: valid mask does not fit shared memory", c->n); return PK_EUNSUPPORTED; }
+    PK_OPT_IN_SMEM(k_diag_compact, smem_c, c->device);
+    dim3 grid((unsigned)((c->n + PK_DC_SLICE - 1) / PK_DC_SLICE), (unsigned)c->ND);
+    k_diag_compact<<<grid, 256, smem_c, c->stream>>>(c->d_band, c->d_w, c->d_vbits, n_words, c->n, c->pitch, c->balanced,
+                                                    c->d_scratch, c->d_diag_cnt);
+    PK_CUDA(cudaGetLastError());
     // leaves of numpy's tree hold at least 57 elements
-    if (c->n <= 57 * 1024) return launch_diag_sums_t<1024>(c, n_words);
-    return launch_diag_sums_t<4096>(c, n_words);
+    if (c->n <= 57 * 1024) return launch_diag_sums_t<1024>(c);
+    return launch_diag_sums_t<4096>(c);
 }
 
 bool pk_fit_on_device_supported(int len) { return len <= PK_FIT_MAX; }
@@ -914,15 +968,12 @@ int pk_launch_candidates(pk_chrom* c, const double* d_crit, int kmax) {
     const int nd = c->upper - c->lower + 1;
     if (nd <= 0) return PK_OK;
     const long long m = (long long)nd * c->n_chunks;
-    dim3 grid(c->n_chunks, nd);
-    k_cand_mark<<<grid, 256, 0, c->stream>>>(c->d_band, c->d_w, c->d_bg, c->n, c->pitch, c->balanced, c->lower, d_crit, kmax,
-                                            c->row_begin, c->row_end, c->n_chunks, c->d_bits, c->d_cnt_all, c->d_cnt_tile,
-                                            c->d_flags);
-    PK_CUDA(cudaGetLastError());
-    k_scan2<<<1, 1024, 0, c->stream>>>(c->d_cnt_all, c->d_cnt_tile, m, c->d_off_all, c->d_off_tile, c->d_ncand);
-    PK_CUDA(cudaGetLastError());
-    k_cand_write<<<grid, 256, 0, c->stream>>>(c->d_bits, c->d_off_all, c->d_off_tile, c->lower, c->row_begin, c->row_end,
-                                             c->n_chunks, c->cand_cap, c->d_cx, c->d_cd, c->d_crank, c->d_flags);
+    // look-back states + the tile ticket, cleared together
+    PK_CUDA(cudaMemsetAsync(c->d_cstate, 0, ((size_t)m + 1) * sizeof(unsigned long long), c->stream));
+    k_cand_scan<<<(unsigned)m, 256, 0, c->stream>>>(c->d_band, c->d_w, c->d_bg, c->n, c->pitch, c->balanced, c->lower, d_crit, kmax,
+                                                   c->row_begin, c->row_end, c->n_chunks, (unsigned)m, c->d_cstate,
+                                                   reinterpret_cast<unsigned*>(c->d_cstate + m), c->cand_cap, c->d_cx, c->d_cd,
+                                                   c->d_crank, c->d_ncand, c->d_flags);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }

@@ -531,7 +531,10 @@ def score_chromosomes(Lib, queue, flat, *, correct, lower, upper, res, min_prob,
         bind_to_device_node(device)
     sizes = {k: Lib.nbins(k) for k in queue}
     assignment = plan(sizes, world, lower, upper, flat.width)
-    mine = score_units(Lib, assignment[rank], flat, correct=correct, lower=lower, upper=upper, res=res,
+    # smallest unit first: the pass starts computing after a short upload, and the large uploads that
+    # follow hide behind kernels
+    order = sorted(assignment[rank], key=lambda u: band_pixels(sizes[u[0]], lower, upper, flat.width) * (u[2] - u[1]) / max(sizes[u[0]], 1))
+    mine = score_units(Lib, order, flat, correct=correct, lower=lower, upper=upper, res=res,
                        device=device, min_prob=min_prob)
     gathered = gather_to_rank0(mine, rank, world)
     if rank != 0:
