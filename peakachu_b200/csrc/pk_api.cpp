@@ -497,7 +497,7 @@ extern "C" int pk_chrom_destroy(pk_chrom* c) {
     c->d_flags = nullptr; c->d_counters = nullptr; c->d_ncand = nullptr; c->d_batch_win = nullptr;
     dev_free(c->d_rowptr);
     dev_free(c->d_b1); dev_free(c->d_b2); dev_free(c->d_cnt); dev_free(c->d_blob_own);
-    dev_free(c->d_cstate);
+    dev_free(c->d_cstate); dev_free(c->d_bits);
     dev_free(c->d_cx); dev_free(c->d_cd); dev_free(c->d_crank);
     dev_free(c->d_keep); dev_free(c->d_fea32); dev_free(c->d_prob);
     dev_free(c->d_rx); dev_free(c->d_ry); dev_free(c->d_rb); dev_free(c->d_rp); dev_free(c->d_rv);
@@ -811,13 +811,14 @@ static int run_candidates(pk_chrom* c, int32_t kmin) {
     if (c->timing) PK_CUDA(cudaEventRecord(c->ev[5], s));
     PK_CUDA(cudaMemsetAsync(c->d_ncand, 0, 2 * sizeof(long long), s));
     if (nd > 0) {
-        c->n_chunks = (c->n + 1023) / 1024;
+        c->n_chunks = (c->n + 4095) / 4096;               // PK_CTILE slots per scan tile
         const int64_t m = (int64_t)nd * c->n_chunks;
         if (m >= (1LL << 31)) { pk_set_error("candidate scan: %lld tiles", (long long)m); return PK_EUNSUPPORTED; }
         if (m + 1 > c->cnt_cap) {
             if (c->d_cstate) PK_CHECK(quiesce(c));
-            dev_free(c->d_cstate);
+            dev_free(c->d_cstate); dev_free(c->d_bits);
             PK_CHECK(dev_alloc(&c->d_cstate, (size_t)m + 1));
+            PK_CHECK(dev_alloc(&c->d_bits, (size_t)m * 128));
             c->cnt_cap = m + 1;
         }
         const double* d_crit = nullptr;

@@ -123,7 +123,8 @@ struct pk_chrom {
     long long rows_hdr[16] = {};     // host copy of the blob's header
     // candidates
     int32_t n_chunks = 0;
-    unsigned long long* d_cstate = nullptr;   // [nd_cand * n_chunks + 1] look-back states of the candidate scan + tile ticket
+    unsigned long long* d_cstate = nullptr;   // [nd_cand * n_chunks] candidate counts per scan tile (all rows, row tile) as uint2
+    uint32_t* d_bits = nullptr;               // [nd_cand * n_chunks * PK_CTILE / 32] one bit per band slot
     int64_t cnt_cap = 0;
     long long* d_ncand = nullptr;    // [2]: candidates in the row tile, in the whole chromosome
     int64_t n_cand = 0, n_cand_all = 0;   // host copies, valid when n_cand_known

@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(256) k_band_rows(
     for (int i = tid; i < ND * TP; i += 256) s_tile[i] = 0;
     __syncthreads();
     int cmax = 0;
+    const unsigned lt = (1u << lane) - 1u;
     for (int xl = wib; xl < R; xl += 8) {
         const int x = x0 + xl;
         if (x >= n) break;
@@ -106,38 +107,36 @@ __global__ void __launch_bounds__(256) k_band_rows(
         const uint8_t* cb = v.cnt8 + v.cnt_off[x];
         int carry = 0;
         for (int w0 = 0; w0 < v.W; w0 += 32) {
-            const int wi = w0 + lane;
-            uint32_t b = wi < v.W ? v.bits[(size_t)x * v.W + wi] : 0u;
-            const int pc = __popc(b);
+            // lane l holds bitmap word w0 + l and the number of pixels in the words before it
+            const uint32_t mine = (w0 + lane < v.W) ? v.bits[(size_t)x * v.W + w0 + lane] : 0u;
+            const int pc = __popc(mine);
             int pre = pc;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
-            const uint8_t* mine = cb + carry + pre - pc;               // this lane's count bytes
-            carry += __shfl_sync(0xffffffffu, pre, 31);
-            const int ybase = x + wi * 32;
-            // four pixels per round: every load of a round is issued before the first use
-            for (int k = 0; k < pc; k += 4) {
-                int bit[4], c[4];
-                double wy[4];
+            pre += carry - pc;                                             // exclusive, from the start of the row
+            carry = __shfl_sync(0xffffffffu, pre + pc, 31);
+            const int nw = min(32, v.W - w0);
+            // one word per step: lane = distance inside the word, so count bytes and weights are read
+            // coalesced; eight words per round, every load of a round issued before the first use
+            for (int q0 = 0; q0 < nw; q0 += 8) {
+                int c[8];
+                double wy[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    bit[j] = -1; c[j] = 0; wy[j] = 0.0;
-                    if (b) {
-                        bit[j] = __ffs(b) - 1;
-                        b &= b - 1;
-                        c[j] = mine[k + j];
-                        const int y = ybase + bit[j];
-                        if (y >= n) c[j] = 0;                            // past the end of the chromosome: ignored
-                        else if (balanced) wy[j] = w[y];
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    const int q = min(q0 + j, 31);
+                    const uint32_t b = __shfl_sync(0xffffffffu, mine, q);
+                    const int base = __shfl_sync(0xffffffffu, pre, q);
+                    const int y = x + (w0 + q) * 32 + lane;
+                    const bool have = q0 + j < nw && ((b >> lane) & 1u) && y < n;
+                    c[j] = have ? (int)cb[base + __popc(b & lt)] : 0;
+                    wy[j] = (have && balanced) ? w[y] : 0.0;
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (c[j] == 0 || c[j] == 255) continue;             // 255: an escaped count (k_band_escapes)
-                    bool fin;
+                for (int j = 0; j < 8; ++j) {
+                    if (c[j] == 0 || c[j] == 255) continue;                 // 255: an escaped count (k_band_escapes)
+                    const int d = (w0 + q0 + j) * 32 + lane;
+                    bool fin = true;
                     if (balanced) fin = isfinite(__dmul_rn(__dmul_rn(wx, wy[j]), (double)c[j]));
-                    else fin = true;
-                    const int d = wi * 32 + bit[j];
                     if (fin) { any = true; valid[x + d] = 1; }
                     if (d < ND) { s_tile[d * TP + xl] = c[j]; cmax = max(cmax, c[j]); }
                 }
@@ -307,6 +306,38 @@ __device__ __forceinline__ double pk_leaf_sum8(const double* __restrict__ a, int
     return r;                                         // valid in lane j == 0
 }
 
+// Two leaves at once (the loads of both are issued before the first add): same arithmetic per leaf.
+__device__ __forceinline__ void pk_leaf_sum8x2(const double* __restrict__ a, int na, const double* __restrict__ b, int nb_,
+                                               int j, double& ra, double& rb) {
+    const int ca = na < 8 ? 0 : (na - (na % 8)), cb = nb_ < 8 ? 0 : (nb_ - (nb_ % 8));
+    double va[16], vb[16], ta[7], tb[7];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) va[i] = (j + 8 * i < ca) ? a[j + 8 * i] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) vb[i] = (j + 8 * i < cb) ? b[j + 8 * i] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) ta[i] = (j == 0 && ca + i < na) ? a[ca + i] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) tb[i] = (j == 0 && cb + i < nb_) ? b[cb + i] : 0.0;
+    double r = va[0], q = vb[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) {
+        if (j + 8 * i < ca) r = __dadd_rn(r, va[i]);
+        if (j + 8 * i < cb) q = __dadd_rn(q, vb[i]);
+    }
+    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1)); q = __dadd_rn(q, __shfl_xor_sync(0xffffffffu, q, 1));
+    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2)); q = __dadd_rn(q, __shfl_xor_sync(0xffffffffu, q, 2));
+    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4)); q = __dadd_rn(q, __shfl_xor_sync(0xffffffffu, q, 4));
+    if (na < 8) r = 0.0;
+    if (nb_ < 8) q = 0.0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        if (ca + i < na) r = __dadd_rn(r, ta[i]);
+        if (cb + i < nb_) q = __dadd_rn(q, tb[i]);
+    }
+    ra = r; rb = q;                                   // valid in lane j == 0
+}
+
 // numpy's recursion, one level at a time, all threads: segments (start, size) of level l
 // become those of level l+1 (a segment of more than 128 elements splits into
 // n2 = m/2 - (m/2)%8 and the rest, others are carried over), order preserved. The split
@@ -400,95 +431,101 @@ __global__ void __launch_bounds__(256) k_diag_compact(
     }
 }
 
-// Sums: one CTA per distance over the compacted row (k_diag_compact): numpy's pairwise tree built level by
-// level in shared memory, leaf sums by lane octets, combined back up the same tree.
+// Sums: one CTA per distance over the compacted row (k_diag_compact). numpy's pairwise tree is built level by
+// level in shared memory by ONE warp (warp barriers only: the table is a few hundred segments, block-wide
+// barriers would cost more than the work), the leaf sums are taken by all threads -- an octet of lanes per
+// leaf, two leaves per octet and round so that two leaves' loads are in flight together -- and the same warp
+// combines them back up the tree.
 template <int CAP>
 __global__ void __launch_bounds__(PK_DS_THREADS) k_diag_sums(
     long long pitch, const double* __restrict__ scratch,
     double* __restrict__ out_sum, const long long* __restrict__ out_cnt, int32_t* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char ds_raw[];
     DiagSmem<CAP>& sm = *reinterpret_cast<DiagSmem<CAP>*>(ds_raw);
+    __shared__ int s_L, s_cur, s_overflow;
     const int d = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const double* sc = scratch + (long long)d * pitch;
     const int nd = (int)out_cnt[d];
-    // ---- leaf table, level by level ----
-    if (tid == 0) { sm.seg_s[0][0] = 0; sm.seg_m[0][0] = nd; sm.nseg[0] = 1; }
-    __syncthreads();                       // also: scratch row complete (block-scope visibility)
-    int cur = 0, L = 0;
-    bool overflow = false;
-    for (;; ++L) {
-        const int ns = sm.nseg[L];
-        const int nw = (ns + 31) / 32;
-        // split mask of this level
-        for (int i0 = wid * 32; i0 < nw * 32; i0 += PK_DS_THREADS) {
-            const int i = i0 + lane;
-            const bool sp = (i < ns) && sm.seg_m[cur][i] > 128;
-            const unsigned bal = __ballot_sync(0xffffffffu, sp);
-            if (lane == 0) sm.split[L][i0 >> 5] = bal;
-        }
-        __syncthreads();
-        if (wid == 0) {                     // exclusive prefix of the per-word split counts
+    // ---- leaf table, level by level (warp 0) ----
+    if (wid == 0) {
+        if (lane == 0) { sm.seg_s[0][0] = 0; sm.seg_m[0][0] = nd; sm.nseg[0] = 1; }
+        __syncwarp();
+        int cur = 0, L = 0;
+        bool overflow = false;
+        for (;; ++L) {
+            const int ns = sm.nseg[L];
+            const int nw = (ns + 31) / 32;
             int carry = 0;
-            for (int w0 = 0; w0 < nw; w0 += 32) {
-                const int wi = w0 + lane;
-                const int cnt = wi < nw ? __popc(sm.split[L][wi]) : 0;
-                int x = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
-                if (wi < nw) sm.wpre[L][wi] = (uint16_t)(carry + x - cnt);
-                carry += __shfl_sync(0xffffffffu, x, 31);
+            for (int w0 = 0; w0 < nw; ++w0) {               // split mask of this level, word by word, with its prefix
+                const int i = w0 * 32 + lane;
+                const bool sp = (i < ns) && sm.seg_m[cur][i] > 128;
+                const unsigned bal = __ballot_sync(0xffffffffu, sp);
+                if (lane == 0) { sm.split[L][w0] = bal; sm.wpre[L][w0] = (uint16_t)carry; }
+                carry += __popc(bal);
             }
-            if (lane == 0) sm.nseg[L + 1] = ns + carry;
-        }
-        __syncthreads();
-        const int ns_next = sm.nseg[L + 1];
-        if (ns_next == ns) break;           // nothing split: level L holds the leaves
-        if (ns_next > CAP || L + 1 >= PK_DS_LEVELS) { overflow = true; break; }
-        for (int i = tid; i < ns; i += PK_DS_THREADS) {
-            const uint32_t word = sm.split[L][i >> 5];
-            const int pos = i + sm.wpre[L][i >> 5] + __popc(word & ((1u << (i & 31)) - 1u));
-            const int s0 = sm.seg_s[cur][i], m = sm.seg_m[cur][i];
-            if ((word >> (i & 31)) & 1u) {
-                int n2 = m / 2;
-                n2 -= n2 % 8;
-                sm.seg_s[cur ^ 1][pos] = s0;          sm.seg_m[cur ^ 1][pos] = n2;
-                sm.seg_s[cur ^ 1][pos + 1] = s0 + n2; sm.seg_m[cur ^ 1][pos + 1] = m - n2;
-            } else {
-                sm.seg_s[cur ^ 1][pos] = s0; sm.seg_m[cur ^ 1][pos] = m;
+            const int ns_next = ns + carry;
+            if (lane == 0) sm.nseg[L + 1] = ns_next;
+            __syncwarp();
+            if (ns_next == ns) break;                        // nothing split: level L holds the leaves
+            if (ns_next > CAP || L + 1 >= PK_DS_LEVELS) { overflow = true; break; }
+            for (int i = lane; i < ns; i += 32) {
+                const uint32_t word = sm.split[L][i >> 5];
+                const int pos = i + sm.wpre[L][i >> 5] + __popc(word & ((1u << (i & 31)) - 1u));
+                const int s0 = sm.seg_s[cur][i], m = sm.seg_m[cur][i];
+                if ((word >> (i & 31)) & 1u) {
+                    int n2 = m / 2;
+                    n2 -= n2 % 8;
+                    sm.seg_s[cur ^ 1][pos] = s0;          sm.seg_m[cur ^ 1][pos] = n2;
+                    sm.seg_s[cur ^ 1][pos + 1] = s0 + n2; sm.seg_m[cur ^ 1][pos + 1] = m - n2;
+                } else {
+                    sm.seg_s[cur ^ 1][pos] = s0; sm.seg_m[cur ^ 1][pos] = m;
+                }
             }
+            __syncwarp();
+            cur ^= 1;
         }
-        __syncthreads();
-        cur ^= 1;
+        if (lane == 0) { s_L = L; s_cur = cur; s_overflow = overflow ? 1 : 0; }
     }
-    if (overflow) {                         // diagonal longer than the shared-memory tables: refuse loudly
+    __syncthreads();
+    if (s_overflow) {                       // diagonal longer than the shared-memory tables: refuse loudly
         if (tid == 0) { atomicOr(&flags[2], 2); out_sum[d] = CUDART_NAN; }
         return;
     }
-    // ---- leaf sums (8 strided accumulators + tail), one leaf per thread ----
+    const int L = s_L, cur = s_cur;
+    // ---- leaf sums (8 strided accumulators + tail): an octet per leaf, two leaves per octet and round ----
     const int nl = sm.nseg[L];
-    int vc = 0;
-    for (int l0 = 0; l0 < nl; l0 += PK_DS_THREADS / 8) {          // uniform trip count: shuffles inside
-        const int l = l0 + (tid >> 3);
-        const bool have = l < nl;
-        const double r = pk_leaf_sum8(sc + (have ? sm.seg_s[cur][l] : 0), have ? sm.seg_m[cur][l] : 0, tid & 7);
-        if (have && (tid & 7) == 0) sm.val[vc][l] = r;
+    constexpr int OCT = PK_DS_THREADS / 8;
+    for (int l0 = 0; l0 < nl; l0 += 2 * OCT) {                    // uniform trip count: shuffles inside
+        const int la = l0 + (tid >> 3), lb = la + OCT;
+        const bool ha = la < nl, hb = lb < nl;
+        const double* pa = sc + (ha ? sm.seg_s[cur][la] : 0);
+        const double* pb = sc + (hb ? sm.seg_s[cur][lb] : 0);
+        double ra, rb;
+        pk_leaf_sum8x2(pa, ha ? sm.seg_m[cur][la] : 0, pb, hb ? sm.seg_m[cur][lb] : 0, tid & 7, ra, rb);
+        if ((tid & 7) == 0) {
+            if (ha) sm.val[0][la] = ra;
+            if (hb) sm.val[0][lb] = rb;
+        }
     }
     __syncthreads();
-    // ---- combine back up: left + right wherever a segment was split ----
-    for (int lv = L - 1; lv >= 0; --lv) {
-        const int ns = sm.nseg[lv];
-        for (int i = tid; i < ns; i += PK_DS_THREADS) {
-            const uint32_t word = sm.split[lv][i >> 5];
-            const int pos = i + sm.wpre[lv][i >> 5] + __popc(word & ((1u << (i & 31)) - 1u));
-            double v = sm.val[vc][pos];
-            if ((word >> (i & 31)) & 1u) v = __dadd_rn(v, sm.val[vc][pos + 1]);
-            sm.val[vc ^ 1][i] = v;
+    // ---- combine back up: left + right wherever a segment was split (warp 0) ----
+    if (wid == 0) {
+        int vc = 0;
+        for (int lv = L - 1; lv >= 0; --lv) {
+            const int ns = sm.nseg[lv];
+            for (int i = lane; i < ns; i += 32) {
+                const uint32_t word = sm.split[lv][i >> 5];
+                const int pos = i + sm.wpre[lv][i >> 5] + __popc(word & ((1u << (i & 31)) - 1u));
+                double v = sm.val[vc][pos];
+                if ((word >> (i & 31)) & 1u) v = __dadd_rn(v, sm.val[vc][pos + 1]);
+                sm.val[vc ^ 1][i] = v;
+            }
+            __syncwarp();
+            vc ^= 1;
         }
-        __syncthreads();
-        vc ^= 1;
+        if (lane == 0) out_sum[d] = sm.val[vc][0];
     }
-    if (tid == 0) out_sum[d] = sm.val[vc][0];
 }
 
 // ---------------------------------------------------------------------------
@@ -525,7 +562,7 @@ __global__ void __launch_bounds__(PK_FIT_THREADS) k_fit_expected(
     __shared__ double s_w[PK_FIT_MAX];
     __shared__ double s_kx[PK_FIT_MAX], s_ky[PK_FIT_MAX];
     __shared__ int s_xs[PK_FIT_MAX], s_r[PK_FIT_MAX + 1];
-    __shared__ int s_warp[PK_FIT_THREADS / 32], s_nblk;
+    __shared__ int s_warp[PK_FIT_THREADS / 32];
     const int tid = threadIdx.x;
     constexpr int PER = PK_FIT_MAX / PK_FIT_THREADS;       // consecutive distances per thread
     // ---- means and ordered compaction of the positive ones ----
@@ -556,53 +593,79 @@ __global__ void __launch_bounds__(PK_FIT_THREADS) k_fit_expected(
     double* s_rcp = s_ky;
     for (int k = tid; k < PK_FIT_MAX; k += PK_FIT_THREADS) s_rcp[k] = __ddiv_rn(1.0, (double)(k + 1));
     __syncthreads();
-    // ---- PAVA on the reversed values (sequential; the block top lives in registers) ----
-    // The chain of dependent float64 divisions is what this kernel waits for. Block weights are sums of unit
-    // weights, i.e. exact integers <= n: sb / wb goes through the tabulated reciprocal with two residual
+    // ---- PAVA on the reversed values ----
+    // scipy's loop (Busing 2022, Alg. 1) visits every point, but a point only costs anything where the
+    // sequence is out of order. Blocks are kept in place, at the index of their last point -- value s_e[p],
+    // weight s_w[p], first point s_r[p]; every point starts as its own block, set up by all threads -- and
+    // s_nv[p] is the next index >= p whose raw predecessor is not smaller (found by a warp with ballots).
+    // The sequential part then jumps from one violation to the next and performs exactly the reference's
+    // additions, multiplications and divisions there, in the reference's order. Block weights are sums of
+    // unit weights, i.e. exact integers <= n: sb / wb goes through a tabulated reciprocal with two residual
     // corrections (pk_div_r: bit-identical to IEEE division inside its guarded range, else __ddiv_rn).
+    int* s_nv = reinterpret_cast<int*>(s_kx);               // [n + 1]; s_kx is not needed before the expansion
+    __shared__ unsigned char s_end[PK_FIT_MAX];
+    for (int i = tid; i < n; i += PK_FIT_THREADS) { s_r[i] = i; s_end[i] = 1; }
+    if (tid < 32) {
+        int carry = n;                                      // next violation at or after the chunk to the right
+        for (int c0 = ((n - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
+            const int p = c0 + tid;
+            const bool f = p >= 1 && p < n && s_e[p - 1] >= s_e[p];
+            const unsigned bal = __ballot_sync(0xffffffffu, f);
+            const unsigned at_or_after = bal >> tid;
+            if (p <= n) s_nv[p] = at_or_after ? p + __ffs(at_or_after) - 1 : carry;
+            if (bal) carry = c0 + __ffs(bal) - 1;
+        }
+        if (tid == 0) s_nv[n] = n;
+    }
+    __syncthreads();
     auto div_w = [&](double sb, double wb) -> double {
         const int k = (int)wb;
         if (pk_div_safe(sb) && k >= 1 && k <= PK_FIT_MAX && (double)k == wb) return pk_div_r(sb, wb, s_rcp[k - 1]);
         return __ddiv_rn(sb, wb);
     };
     if (tid == 0) {
-        s_r[0] = 0;
-        s_r[1] = 1;
-        int b = 0;
-        double xb_prev = s_e[0], wb_prev = 1.0;
-        for (int i = 1; i < n; ++i) {
-            b++;
-            double xb = s_e[i], wb = 1.0;
-            if (xb_prev >= xb) {
-                b--;
-                double sb = __dadd_rn(__dmul_rn(wb_prev, xb_prev), __dmul_rn(wb, xb));
-                wb = __dadd_rn(wb, wb_prev);
+        int i = s_nv[1];
+        while (i < n) {
+            const int q = i - 1;                            // the block that ends just before point i
+            if (!(s_e[q] >= s_e[i])) { i = s_nv[i + 1]; continue; }      // in order: on to the next raw violation
+            double sb = __dadd_rn(__dmul_rn(s_w[q], s_e[q]), __dmul_rn(1.0, s_e[i]));
+            double wb = __dadd_rn(1.0, s_w[q]);
+            double xb = div_w(sb, wb);
+            int st = s_r[q];
+            s_end[q] = 0;
+            while (i < n - 1 && xb >= s_e[i + 1]) {
+                s_end[i] = 0;
+                i++;
+                sb = __dadd_rn(sb, __dmul_rn(1.0, s_e[i]));
+                wb = __dadd_rn(wb, 1.0);
                 xb = div_w(sb, wb);
-                while (i < n - 1 && xb >= s_e[i + 1]) {
-                    i++;
-                    sb = __dadd_rn(sb, __dmul_rn(1.0, s_e[i]));
-                    wb = __dadd_rn(wb, 1.0);
-                    xb = div_w(sb, wb);
-                }
-                while (b > 0 && s_e[b - 1] >= xb) {
-                    b--;
-                    sb = __dadd_rn(sb, __dmul_rn(s_w[b], s_e[b]));
-                    wb = __dadd_rn(wb, s_w[b]);
-                    xb = div_w(sb, wb);
-                }
             }
-            s_e[b] = xb_prev = xb;
-            s_w[b] = wb_prev = wb;
-            s_r[b + 1] = i + 1;
+            while (st > 0 && s_e[st - 1] >= xb) {
+                const int q2 = st - 1;
+                sb = __dadd_rn(sb, __dmul_rn(s_w[q2], s_e[q2]));
+                wb = __dadd_rn(wb, s_w[q2]);
+                xb = div_w(sb, wb);
+                s_end[q2] = 0;
+                st = s_r[q2];
+            }
+            s_e[i] = xb; s_w[i] = wb; s_r[i] = st;
+            i++;
         }
-        s_nblk = b + 1;
     }
     __syncthreads();
-    // ---- expand the blocks into the forward-ordered fit (s_kx borrowed as yf[]) ----
-    const int nblk = s_nblk;
-    for (int k = tid; k < nblk; k += PK_FIT_THREADS) {
-        const double xk = s_e[k];
-        for (int i = s_r[k]; i < s_r[k + 1]; ++i) s_kx[n - 1 - i] = xk;
+    // ---- expand the blocks into the forward-ordered fit (s_kx as yf[]; s_nv is dead) ----
+    {
+        double xk[PER]; int lo[PER], hi[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int p = tid * PER + j;
+            hi[j] = -1; lo[j] = 0; xk[j] = 0.0;
+            if (p < n && s_end[p]) { hi[j] = p; lo[j] = s_r[p]; xk[j] = s_e[p]; }
+        }
+        __syncthreads();                                    // every read of s_nv's memory precedes the writes below
+#pragma unroll
+        for (int j = 0; j < PER; ++j)
+            for (int i = lo[j]; i <= hi[j]; ++i) s_kx[n - 1 - i] = xk[j];
     }
     __syncthreads();
     // ---- knots: first, last, and every point that differs from a neighbour ----
@@ -653,131 +716,127 @@ __global__ void __launch_bounds__(PK_FIT_THREADS) k_fit_expected(
 }
 
 // ---------------------------------------------------------------------------
-// S4  Poisson candidate scan (scoreUtils.py:40-68), one pass over the band.
+// S4  Poisson candidate scan (scoreUtils.py:40-68).
 //     candidate <=> count > 0 and mu = bg[d] / (w_x * w_y) satisfies 0 <= mu < crit[count].
 //     Reference order is distance asc, row asc, and every candidate needs its rank in that order over
 //     the whole chromosome (the 100,000-candidate batches of scoreUtils.py:104) and its position in the
-//     list of this row tile. Tiles of 1024 band slots are taken in that order (an atomic ticket), each
-//     tile evaluates its slots (4 per thread, loads first), publishes its two counts in one 64-bit word and
-//     obtains the counts of all earlier tiles by decoupled look-back (aggregate / inclusive-prefix states,
-//     a warp inspecting 32 predecessors at a time), then writes its candidates straight to their final
-//     positions. No bit array, no scan kernel, no second pass over the slots.
-//     state word: [63:62] 0 empty, 1 aggregate, 2 inclusive prefix | [61:31] count over all rows | [30:0] count in the row tile
+//     list of this row tile. Two kernels over tiles of PK_CTILE band slots (distance-major):
+//       k_cand_mark   evaluates every slot once (8 per thread and round, loads first), keeps one bit per
+//                     slot and the tile's two counts;
+//       k_cand_write  gets the counts of all earlier tiles by summing them directly (a few thousand values
+//                     from L2 -- no scan kernel, no waiting on other CTAs) and expands its bits into the
+//                     ordered candidate list; the last tile leaves the totals.
 // ---------------------------------------------------------------------------
-#define PK_CHUNK 1024
+#define PK_CTILE 4096
 
-__device__ __forceinline__ unsigned long long pk_cs_pack(unsigned status, unsigned a, unsigned t) {
-    return ((unsigned long long)status << 62) | ((unsigned long long)a << 31) | (unsigned long long)t;
-}
-
-__global__ void __launch_bounds__(256) k_cand_scan(
+__global__ void __launch_bounds__(256) k_cand_mark(
     const int32_t* __restrict__ band, const double* __restrict__ w, const double* __restrict__ bg,
     int n, long long pitch, int balanced, int lower, const double* __restrict__ crit, int kmax,
-    int row_begin, int row_end, int n_chunks, unsigned n_tiles, unsigned long long* __restrict__ state,
-    unsigned* __restrict__ ticket, long long cap, int32_t* __restrict__ cx, int32_t* __restrict__ cd,
-    int32_t* __restrict__ crank, long long* __restrict__ ncand, int32_t* __restrict__ flags) {
-    __shared__ unsigned s_tile;
-    __shared__ int s_ca[4][8], s_ct[4][8];
-    __shared__ unsigned s_ea, s_et;
+    int row_begin, int row_end, int n_chunks, uint32_t* __restrict__ bits,
+    uint2* __restrict__ counts, int32_t* __restrict__ flags) {
+    const int chunk = blockIdx.x, di = blockIdx.y, d = lower + di;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const unsigned t = s_tile;
-    const int di = (int)(t / (unsigned)n_chunks), chunk = (int)(t - (unsigned)di * (unsigned)n_chunks), d = lower + di;
     const int len = n - d;
     const double e = bg[d];
     const bool d_ok = (len > 0) && (e > 0.0);
     const int32_t* row = band + (long long)d * pitch;
-    // counts and weights are loaded side by side with bg[d] (one memory round trip, not three)
-    int k[4];
-    double wx[4], wy[4];
+    const long long tile = (long long)di * n_chunks + chunk;
+    __shared__ int s_a[8], s_t[8];
+    int tot_a = 0, tot_t = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int x = chunk * PK_CHUNK + j * 256 + tid;
-        const bool in = x < len;
-        k[j] = in ? row[x] : 0;
-        wx[j] = (balanced && in) ? w[x] : 1.0;
-        wy[j] = (balanced && in) ? w[x + d] : 1.0;
-    }
-    if (!d_ok) {
+    for (int r = 0; r < PK_CTILE / 2048; ++r) {
+        // counts and weights of 8 slots are loaded side by side (one memory round trip)
+        int k[8];
+        double wx[8], wy[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) k[j] = 0;
-    }
-    unsigned ba[4], bt[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int x = chunk * PK_CHUNK + j * 256 + tid;
-        bool c = false;
-        if (k[j] > 0) {
-            double mu = e;
-            if (balanced) mu = __ddiv_rn(e, __dmul_rn(wx[j], wy[j]));
-            if (k[j] > kmax) atomicOr(&flags[0], 1);
-            else c = (mu >= 0.0) && (mu < crit[k[j]]);
+        for (int j = 0; j < 8; ++j) {
+            const int x = chunk * PK_CTILE + (r * 8 + j) * 256 + tid;
+            const bool in = d_ok && x < len;
+            k[j] = in ? row[x] : 0;
+            wx[j] = (balanced && in) ? w[x] : 1.0;
+            wy[j] = (balanced && in) ? w[x + d] : 1.0;
         }
-        ba[j] = __ballot_sync(0xffffffffu, c);
-        bt[j] = __ballot_sync(0xffffffffu, c && x >= row_begin && x < row_end);
-        if (lane == 0) { s_ca[j][wid] = __popc(ba[j]); s_ct[j][wid] = __popc(bt[j]); }
-    }
-    __syncthreads();
-    if (wid == 0) {
-        // tile totals (32 partial counts, one per lane)
-        unsigned agg_a = (unsigned)s_ca[lane >> 3][lane & 7], agg_t = (unsigned)s_ct[lane >> 3][lane & 7];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            agg_a += __shfl_xor_sync(0xffffffffu, agg_a, o);
-            agg_t += __shfl_xor_sync(0xffffffffu, agg_t, o);
-        }
-        volatile unsigned long long* vstate = state;
-        if (lane == 0) vstate[t] = pk_cs_pack(t == 0 ? 2u : 1u, agg_a, agg_t);
-        unsigned ea = 0, et = 0;
-        if (t > 0) {
-            long long look = (long long)t - 1;
-            for (;;) {
-                const long long i = look - lane;
-                unsigned long long v = pk_cs_pack(2u, 0u, 0u);              // before the first tile: prefix 0
-                if (i >= 0) v = vstate[i];
-                const unsigned st = (unsigned)(v >> 62);
-                if (__any_sync(0xffffffffu, st == 0u)) continue;             // a predecessor has not published yet
-                const unsigned pm = __ballot_sync(0xffffffffu, st == 2u);
-                const int first = pm ? __ffs(pm) - 1 : 32;                    // nearest predecessor holding a prefix
-                unsigned va = lane <= first ? (unsigned)((v >> 31) & 0x7FFFFFFFull) : 0u;
-                unsigned vt = lane <= first ? (unsigned)(v & 0x7FFFFFFFull) : 0u;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    va += __shfl_xor_sync(0xffffffffu, va, o);
-                    vt += __shfl_xor_sync(0xffffffffu, vt, o);
-                }
-                ea += va; et += vt;
-                if (pm) break;
-                look -= 32;
+        for (int j = 0; j < 8; ++j) {
+            const int x = chunk * PK_CTILE + (r * 8 + j) * 256 + tid;
+            bool c = false;
+            if (k[j] > 0) {
+                double mu = e;
+                if (balanced) mu = __ddiv_rn(e, __dmul_rn(wx[j], wy[j]));
+                if (k[j] > kmax) atomicOr(&flags[0], 1);
+                else c = (mu >= 0.0) && (mu < crit[k[j]]);
             }
-            if (lane == 0) vstate[t] = pk_cs_pack(2u, ea + agg_a, et + agg_t);
-        }
-        if (lane == 0) {
-            s_ea = ea; s_et = et;
-            if (t == n_tiles - 1) { ncand[0] = (long long)(et + agg_t); ncand[1] = (long long)(ea + agg_a); }
+            const unsigned ba = __ballot_sync(0xffffffffu, c);
+            const unsigned bt = __ballot_sync(0xffffffffu, c && x >= row_begin && x < row_end);
+            // word q of the tile covers slots 32 q .. 32 q + 31
+            if (lane == 0) bits[tile * (PK_CTILE / 32) + (r * 8 + j) * 8 + wid] = ba;
+            tot_a += __popc(ba);
+            tot_t += __popc(bt);
         }
     }
+    if (lane == 0) { s_a[wid] = tot_a; s_t[wid] = tot_t; }
     __syncthreads();
-    // candidates of this tile, in slot order (j, warp, lane), to their final positions
-    unsigned pa = s_ea, pt = s_et;
+    if (tid == 0) {
+        int a = 0, t = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        unsigned ja = pa, jt = pt;
+        for (int q = 0; q < 8; ++q) { a += s_a[q]; t += s_t[q]; }
+        counts[tile] = make_uint2((unsigned)a, (unsigned)t);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cand_write(
+    const uint32_t* __restrict__ bits, const uint2* __restrict__ counts, int lower, int row_begin, int row_end,
+    int n_chunks, long long n_tiles, long long cap, int32_t* __restrict__ cx, int32_t* __restrict__ cd,
+    int32_t* __restrict__ crank, long long* __restrict__ ncand, int32_t* __restrict__ flags) {
+    const int chunk = blockIdx.x, di = blockIdx.y, d = lower + di;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long tile = (long long)di * n_chunks + chunk;
+    const uint2 mine = counts[tile];
+    const bool is_last = tile == n_tiles - 1;
+    if (mine.x == 0 && !is_last) return;                       // no candidate in this tile
+    // candidates in all earlier tiles (distance-major order): a direct sum
+    unsigned long long pa = 0, pt = 0;
+    for (long long i = tid; i < tile; i += 256) { const uint2 c = counts[i]; pa += c.x; pt += c.y; }
+    __shared__ unsigned long long s_pa[8], s_pt[8];
+    __shared__ uint32_t s_wa[PK_CTILE / 32], s_wt[PK_CTILE / 32];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            if (q < wid) { ja += (unsigned)s_ca[j][q]; jt += (unsigned)s_ct[j][q]; }
-            pa += (unsigned)s_ca[j][q]; pt += (unsigned)s_ct[j][q];
-        }
-        const unsigned lm = (1u << lane) - 1u;
-        if ((bt[j] >> lane) & 1u) {
-            const long long rt = (long long)jt + __popc(bt[j] & lm);
+    for (int o = 16; o > 0; o >>= 1) { pa += __shfl_xor_sync(0xffffffffu, pa, o); pt += __shfl_xor_sync(0xffffffffu, pt, o); }
+    if (lane == 0) { s_pa[wid] = pa; s_pt[wid] = pt; }
+    // per-word candidate counts of this tile (all rows / rows of the row tile), then their exclusive prefix
+    constexpr int NWORD = PK_CTILE / 32;                       // 128 words, one per thread of the first four warps
+    uint32_t word = 0, inr = 0;
+    if (tid < NWORD) {
+        word = bits[tile * NWORD + tid];
+        // word q = (round j) * 8 + warp covers slots x = chunk * PK_CTILE + j * 256 + warp * 32 + bit
+        const int xw = chunk * PK_CTILE + (tid >> 3) * 256 + (tid & 7) * 32;
+        const int lo = max(row_begin - xw, 0), hi = min(row_end - xw, 32);
+        if (hi > lo) inr = (hi - lo >= 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+        s_wa[tid] = __popc(word);
+        s_wt[tid] = __popc(word & inr);
+    }
+    __syncthreads();
+    pa = 0; pt = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { pa += s_pa[q]; pt += s_pt[q]; }
+    if (is_last && tid == 0) { ncand[0] = (long long)(pt + mine.y); ncand[1] = (long long)(pa + mine.x); }
+    if (mine.x == 0) return;
+    if (tid < NWORD) {
+        // exclusive prefix over the 128 words: slot order is word order
+        unsigned ea = 0, et = 0;
+        for (int q = 0; q < tid; ++q) { ea += s_wa[q]; et += s_wt[q]; }
+        const int j = tid >> 3, wq = tid & 7;
+        uint32_t rem = word & inr;
+        while (rem) {
+            const int bit = __ffs(rem) - 1;
+            rem &= rem - 1;
+            const unsigned lm = (1u << bit) - 1u;
+            const long long rt = (long long)pt + et + __popc(word & inr & lm);
             if (rt < cap) {
-                cx[rt] = chunk * PK_CHUNK + j * 256 + tid;
+                cx[rt] = chunk * PK_CTILE + j * 256 + wq * 32 + bit;
                 cd[rt] = d;
-                crank[rt] = (int32_t)(ja + __popc(ba[j] & lm));
+                crank[rt] = (int32_t)(pa + ea + __popc(word & lm));
             } else {
-                atomicOr(&flags[3], 2);                                   // candidate buffer too small
+                atomicOr(&flags[3], 2);                        // candidate buffer too small
             }
         }
     }
@@ -968,12 +1027,13 @@ int pk_launch_candidates(pk_chrom* c, const double* d_crit, int kmax) {
     const int nd = c->upper - c->lower + 1;
     if (nd <= 0) return PK_OK;
     const long long m = (long long)nd * c->n_chunks;
-    // look-back states + the tile ticket, cleared together
-    PK_CUDA(cudaMemsetAsync(c->d_cstate, 0, ((size_t)m + 1) * sizeof(unsigned long long), c->stream));
-    k_cand_scan<<<(unsigned)m, 256, 0, c->stream>>>(c->d_band, c->d_w, c->d_bg, c->n, c->pitch, c->balanced, c->lower, d_crit, kmax,
-                                                   c->row_begin, c->row_end, c->n_chunks, (unsigned)m, c->d_cstate,
-                                                   reinterpret_cast<unsigned*>(c->d_cstate + m), c->cand_cap, c->d_cx, c->d_cd,
-                                                   c->d_crank, c->d_ncand, c->d_flags);
+    dim3 grid(c->n_chunks, nd);
+    uint2* counts = reinterpret_cast<uint2*>(c->d_cstate);
+    k_cand_mark<<<grid, 256, 0, c->stream>>>(c->d_band, c->d_w, c->d_bg, c->n, c->pitch, c->balanced, c->lower, d_crit, kmax,
+                                            c->row_begin, c->row_end, c->n_chunks, c->d_bits, counts, c->d_flags);
+    PK_CUDA(cudaGetLastError());
+    k_cand_write<<<grid, 256, 0, c->stream>>>(c->d_bits, counts, c->lower, c->row_begin, c->row_end, c->n_chunks, m, c->cand_cap,
+                                             c->d_cx, c->d_cd, c->d_crank, c->d_ncand, c->d_flags);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }

@@ -9,6 +9,7 @@ import sys
 
 sass_csv, dis, kname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+sort_key = sys.argv[5] if len(sys.argv) > 5 else "Instructions Executed"   # or "# Samples"
 # address -> line from nvdisasm
 addr2line = {}
 cur = None
@@ -35,6 +36,8 @@ base = None
 agg = collections.defaultdict(lambda: collections.Counter())
 tot = collections.Counter()
 for r in rows[hi + 1:]:
+    if r and r[0] == "Address":          # a second launch of the same kernel in the report: the first one is enough
+        break
     if len(r) < len(hdr):
         continue
     a = int(r[ci["Address"]], 16)
@@ -51,7 +54,7 @@ for r in rows[hi + 1:]:
         tot[k] += v
 print("total warp-instructions %d, samples %d, smem wavefronts %d" % (tot["Instructions Executed"], tot["# Samples"], tot["L1 Wavefronts Shared"]))
 print("%-22s %12s %6s %8s %10s %8s %8s %8s %8s" % ("line", "warp-inst", "%", "samples", "smem-wf", "wait", "long_sb", "short_sb", "barrier"))
-for key, c in sorted(agg.items(), key=lambda kv: -kv[1]["Instructions Executed"])[:top]:
+for key, c in sorted(agg.items(), key=lambda kv: -kv[1][sort_key])[:top]:
     print("%-22s %12d %6.2f %8d %10d %8d %8d %8d %8d" % ("%s:%d" % key, c["Instructions Executed"],
           100.0 * c["Instructions Executed"] / max(tot["Instructions Executed"], 1), c["# Samples"], c["L1 Wavefronts Shared"],
           c["stall_wait"], c["stall_long_sb"], c["stall_short_sb"], c["stall_barrier"]))
