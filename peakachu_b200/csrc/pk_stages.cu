@@ -16,6 +16,29 @@
 // ---------------------------------------------------------------------------
 // TY / TC: element types of the column and count arrays. DELTA: the column array holds
 // bin2 - bin1 (pk_chrom_upload_csr16) instead of bin2.
+// Write a CTA's tile T[d][0..R) (R <= 64 rows, pitch TP) to the diagonal-major band: a warp per distance,
+// lanes along the rows, pointers advanced by addition (no 64-bit multiply per store).
+__device__ __forceinline__ void pk_tile_writeout(const int32_t* __restrict__ s_tile, int TP, int R, int32_t* __restrict__ band,
+                                                 long long pitch, int x0, int n, int ND, int lane, int wib) {
+    const bool a = lane < R && x0 + lane < n, b = lane + 32 < R && x0 + lane + 32 < n;
+    int32_t* dst = band + (long long)wib * pitch + x0 + lane;
+    const int32_t* src = s_tile + wib * TP + lane;
+    const long long dstep = 8 * pitch;
+    const int sstep = 8 * TP;
+    for (int d = wib; d < ND; d += 8) {
+        if (a) dst[0] = src[0];
+        if (b) dst[32] = src[32];
+        dst += dstep; src += sstep;
+    }
+}
+
+// exponent of a weight inside [2^-150, 2^150] (false for 0, denormals, inf, NaN): products of two such
+// weights and a 31-bit count are finite, so the finiteness test of a balanced pixel needs no arithmetic
+__device__ __forceinline__ bool pk_weight_tame(double w) {
+    const unsigned e = ((unsigned)__double2hiint(w) >> 20) & 0x7FFu;
+    return e >= 1023u - 150u && e <= 1023u + 150u;
+}
+
 template <typename TY, typename TC, bool DELTA>
 __global__ void __launch_bounds__(256) k_band_csr(
     const long long* __restrict__ rowptr, const TY* __restrict__ b2, const TC* __restrict__ cnt,
@@ -33,6 +56,7 @@ __global__ void __launch_bounds__(256) k_band_csr(
         if (x >= n) break;
         const long long p0 = rowptr[x], p1 = rowptr[x + 1];
         const double wx = balanced ? w[x] : 0.0;
+        const bool tame_x = !balanced || pk_weight_tame(wx);
         bool any = false;
         for (long long pb = p0; pb < p1; pb += 128) {
             int y[4], c[4];
@@ -52,8 +76,9 @@ __global__ void __launch_bounds__(256) k_band_csr(
             for (int j = 0; j < 4; ++j) {
                 if (c[j] == 0) continue;
                 bool fin;
-                if (balanced) fin = isfinite(__dmul_rn(__dmul_rn(wx, wy[j]), (double)c[j]));
-                else fin = c[j] > 0;
+                if (!balanced) fin = c[j] > 0;
+                else if (tame_x && pk_weight_tame(wy[j])) fin = true;
+                else fin = isfinite(__dmul_rn(__dmul_rn(wx, wy[j]), (double)c[j]));
                 if (fin) { any = true; valid[y[j]] = 1; }
                 const int d = y[j] - x;
                 if (d < ND) {
@@ -68,8 +93,7 @@ __global__ void __launch_bounds__(256) k_band_csr(
     for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
     if (lane == 0 && cmax > 0) atomicMax(&flags[1], cmax);
     __syncthreads();
-    for (int d = wib; d < ND; d += 8)
-        for (int xl = lane; xl < R && x0 + xl < n; xl += 32) band[(long long)d * pitch + x0 + xl] = s_tile[d * TP + xl];
+    pk_tile_writeout(s_tile, TP, R, band, pitch, x0, n, ND, lane, wib);
 }
 
 // ---------------------------------------------------------------------------
@@ -103,6 +127,7 @@ __global__ void __launch_bounds__(256) k_band_rows(
         const int x = x0 + xl;
         if (x >= n) break;
         const double wx = balanced ? w[x] : 0.0;
+        const bool tame_x = !balanced || pk_weight_tame(wx);
         bool any = false;
         const uint8_t* cb = v.cnt8 + v.cnt_off[x];
         int carry = 0;
@@ -136,7 +161,7 @@ __global__ void __launch_bounds__(256) k_band_rows(
                     if (c[j] == 0 || c[j] == 255) continue;                 // 255: an escaped count (k_band_escapes)
                     const int d = (w0 + q0 + j) * 32 + lane;
                     bool fin = true;
-                    if (balanced) fin = isfinite(__dmul_rn(__dmul_rn(wx, wy[j]), (double)c[j]));
+                    if (balanced && !(tame_x && pk_weight_tame(wy[j]))) fin = isfinite(__dmul_rn(__dmul_rn(wx, wy[j]), (double)c[j]));
                     if (fin) { any = true; valid[x + d] = 1; }
                     if (d < ND) { s_tile[d * TP + xl] = c[j]; cmax = max(cmax, c[j]); }
                 }
@@ -156,8 +181,7 @@ __global__ void __launch_bounds__(256) k_band_rows(
     for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
     if (lane == 0 && cmax > 0) atomicMax(&flags[1], cmax);
     __syncthreads();
-    for (int d = wib; d < ND; d += 8)
-        for (int xl = lane; xl < R && x0 + xl < n; xl += 32) band[(long long)d * pitch + x0 + xl] = s_tile[d * TP + xl];
+    pk_tile_writeout(s_tile, TP, R, band, pitch, x0, n, ND, lane, wib);
 }
 
 // escaped counts (>= 255) of the packed rows: a few per row at most, written after the tiles
@@ -275,7 +299,7 @@ __global__ void __launch_bounds__(256) k_valid_bits(const uint8_t* __restrict__ 
 //     elements with 8 strided accumulators combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)),
 //     then a sequential tail) is evaluated leaf-parallel, combined by one thread.
 // ---------------------------------------------------------------------------
-#define PK_DS_THREADS 512
+#define PK_DS_THREADS 256
 #define PK_DS_LEVELS 14
 
 // numpy's leaf: eight strided accumulators r_j = a[j] + a[j+8] + ..., combined as
@@ -304,38 +328,6 @@ __device__ __forceinline__ double pk_leaf_sum8(const double* __restrict__ a, int
     for (int i = 0; i < 7; ++i)
         if (nb + i < n) r = __dadd_rn(r, tail[i]);
     return r;                                         // valid in lane j == 0
-}
-
-// Two leaves at once (the loads of both are issued before the first add): same arithmetic per leaf.
-__device__ __forceinline__ void pk_leaf_sum8x2(const double* __restrict__ a, int na, const double* __restrict__ b, int nb_,
-                                               int j, double& ra, double& rb) {
-    const int ca = na < 8 ? 0 : (na - (na % 8)), cb = nb_ < 8 ? 0 : (nb_ - (nb_ % 8));
-    double va[16], vb[16], ta[7], tb[7];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) va[i] = (j + 8 * i < ca) ? a[j + 8 * i] : 0.0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) vb[i] = (j + 8 * i < cb) ? b[j + 8 * i] : 0.0;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) ta[i] = (j == 0 && ca + i < na) ? a[ca + i] : 0.0;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) tb[i] = (j == 0 && cb + i < nb_) ? b[cb + i] : 0.0;
-    double r = va[0], q = vb[0];
-#pragma unroll
-    for (int i = 1; i < 16; ++i) {
-        if (j + 8 * i < ca) r = __dadd_rn(r, va[i]);
-        if (j + 8 * i < cb) q = __dadd_rn(q, vb[i]);
-    }
-    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1)); q = __dadd_rn(q, __shfl_xor_sync(0xffffffffu, q, 1));
-    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2)); q = __dadd_rn(q, __shfl_xor_sync(0xffffffffu, q, 2));
-    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4)); q = __dadd_rn(q, __shfl_xor_sync(0xffffffffu, q, 4));
-    if (na < 8) r = 0.0;
-    if (nb_ < 8) q = 0.0;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) {
-        if (ca + i < na) r = __dadd_rn(r, ta[i]);
-        if (cb + i < nb_) q = __dadd_rn(q, tb[i]);
-    }
-    ra = r; rb = q;                                   // valid in lane j == 0
 }
 
 // numpy's recursion, one level at a time, all threads: segments (start, size) of level l
@@ -426,16 +418,25 @@ __global__ void __launch_bounds__(256) k_diag_compact(
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        if ((m[j] >> lane) & 1u) sc[base + __popc(m[j] & ((1u << lane) - 1u))] = pk_value(c[j], wa[j], wb[j], balanced);
+        if ((m[j] >> lane) & 1u) {
+            double val;
+            if (c[j] == 0) val = 0.0;
+            else if (!balanced) val = (double)c[j];
+            else {
+                val = __dmul_rn(__dmul_rn(wa[j], wb[j]), (double)c[j]);            // pk_value
+                if (!(pk_weight_tame(wa[j]) && pk_weight_tame(wb[j])) && !isfinite(val)) val = 0.0;
+            }
+            sc[base + __popc(m[j] & ((1u << lane) - 1u))] = val;
+        }
         base += __popc(m[j]);
     }
 }
 
 // Sums: one CTA per distance over the compacted row (k_diag_compact). numpy's pairwise tree is built level by
 // level in shared memory by ONE warp (warp barriers only: the table is a few hundred segments, block-wide
-// barriers would cost more than the work), the leaf sums are taken by all threads -- an octet of lanes per
-// leaf, two leaves per octet and round so that two leaves' loads are in flight together -- and the same warp
-// combines them back up the tree.
+// barriers would cost more than the work), the leaf sums are taken by all threads, an octet of lanes per
+// leaf, and the same warp combines them back up the tree. 256 threads and few registers: every distance's
+// CTA is resident at once (the kernel is bound by the latency of its dependent steps, not by bandwidth).
 template <int CAP>
 __global__ void __launch_bounds__(PK_DS_THREADS) k_diag_sums(
     long long pitch, const double* __restrict__ scratch,
@@ -493,20 +494,14 @@ __global__ void __launch_bounds__(PK_DS_THREADS) k_diag_sums(
         return;
     }
     const int L = s_L, cur = s_cur;
-    // ---- leaf sums (8 strided accumulators + tail): an octet per leaf, two leaves per octet and round ----
+    // ---- leaf sums (8 strided accumulators + tail): an octet of lanes per leaf ----
     const int nl = sm.nseg[L];
     constexpr int OCT = PK_DS_THREADS / 8;
-    for (int l0 = 0; l0 < nl; l0 += 2 * OCT) {                    // uniform trip count: shuffles inside
-        const int la = l0 + (tid >> 3), lb = la + OCT;
-        const bool ha = la < nl, hb = lb < nl;
-        const double* pa = sc + (ha ? sm.seg_s[cur][la] : 0);
-        const double* pb = sc + (hb ? sm.seg_s[cur][lb] : 0);
-        double ra, rb;
-        pk_leaf_sum8x2(pa, ha ? sm.seg_m[cur][la] : 0, pb, hb ? sm.seg_m[cur][lb] : 0, tid & 7, ra, rb);
-        if ((tid & 7) == 0) {
-            if (ha) sm.val[0][la] = ra;
-            if (hb) sm.val[0][lb] = rb;
-        }
+    for (int l0 = 0; l0 < nl; l0 += OCT) {                        // uniform trip count: shuffles inside
+        const int l = l0 + (tid >> 3);
+        const bool have = l < nl;
+        const double r = pk_leaf_sum8(sc + (have ? sm.seg_s[cur][l] : 0), have ? sm.seg_m[cur][l] : 0, tid & 7);
+        if (have && (tid & 7) == 0) sm.val[0][l] = r;
     }
     __syncthreads();
     // ---- combine back up: left + right wherever a segment was split (warp 0) ----
