@@ -122,6 +122,12 @@ int pk_chrom_upload_csr16(pk_chrom* c, const int64_t* bin1_offset, const uint16_
  * nd_enc must cover the band: nd_enc >= upper + 2w + 1 (effective upper). No duplicates by construction. */
 #define PK_ROWS_MAGIC 0x31524B50LL
 int pk_chrom_upload_rows(pk_chrom* c, const void* blob, int64_t bytes, const double* weights, int mem);
+/* Balancing weights of the Poisson filter (scoreUtils.py:55-57) when they differ from the ones the pixel
+ * values were balanced with. cooler inverts a weight column whose `divisive_weights` attribute is set
+ * (hic2cool's KR / VC columns) inside matrix(balance=name), whereas the reference passes the column's raw
+ * values to Chromosome (score_chromosome.py:44): such a map is uploaded with 1 / w and gets the raw column
+ * here. Call after the upload, before pk_chrom_find_candidates. */
+int pk_chrom_set_poisson_weights(pk_chrom* c, const double* weights, int mem);
 /* `peakachu depth` (calculate_depth.py:25-28): sum of the raw counts of the pixels of the last
  * upload with bin2 - bin1 >= min_dis_bins. Columns passed as device pointers must still be alive. */
 int pk_chrom_depth(pk_chrom* c, int32_t min_dis_bins, int64_t* total);
@@ -198,6 +204,7 @@ typedef struct pk_unit {
     const void *a, *b, *c;
     int64_t size;
     const double* weights;       /* NULL: raw mode */
+    const double* poisson_weights;   /* NULL: the same as `weights` (see pk_chrom_set_poisson_weights) */
     double min_prob;
 } pk_unit;
 typedef struct pk_unit_result {

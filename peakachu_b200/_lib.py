@@ -30,7 +30,7 @@ class Unit(C.Structure):
     """pk_unit (include/peakachu_b200.h)."""
     _fields_ = [("tag", C.c_int64), ("n_bins", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32),
                 ("encoding", C.c_int32), ("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p),
-                ("size", C.c_int64), ("weights", C.c_void_p), ("min_prob", C.c_double)]
+                ("size", C.c_int64), ("weights", C.c_void_p), ("poisson_weights", C.c_void_p), ("min_prob", C.c_double)]
 
 
 class UnitResult(C.Structure):
@@ -59,6 +59,7 @@ SIGNATURES = {
     "pk_chrom_upload_pixels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "pk_chrom_upload_csr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "pk_chrom_upload_csr16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    "pk_chrom_set_poisson_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pk_chrom_upload_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "pk_engine_create": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int, C.POINTER(C.c_void_p)]),
     "pk_engine_destroy": (C.c_int, [C.c_void_p]),

@@ -60,13 +60,16 @@ class PKCool:
         self.rows_nd = int(z["rows_nd"]) if "rows_nd" in z.files else 0
         self._rows = {int(k[len("rows_"):]): z[k] for k in z.files if k.startswith("rows_") and k != "rows_nd"}
         self.weight_columns = {k[len("bins_"):]: z[k] for k in z.files if k.startswith("bins_")}
+        # weight columns cooler would invert (column attribute `divisive_weights`, e.g. hic2cool's KR / VC)
+        self.divisive = {str(s) for s in z["divisive_columns"]} if "divisive_columns" in z.files else set()
         # pixel range of each chromosome (bin1 sorted, intra-chromosomal only)
         self._pix_lo = np.searchsorted(self.bin1_id, self.chrom_offset[:-1], side="left")
         self._pix_hi = np.searchsorted(self.bin1_id, self.chrom_offset[1:], side="left")
 
     # -- writer -----------------------------------------------------------
     @staticmethod
-    def write(path: str, chroms, binsize: int, weight_name: str = "weight", rows_nd: int = 352) -> None:
+    def write(path: str, chroms, binsize: int, weight_name: str = "weight", rows_nd: int = 352,
+              divisive: bool = False) -> None:
         """chroms: iterable of synth.SynthChrom-like objects
         (name, n, bin1, bin2, count, weights). ``rows_nd`` > 0 also stores every chromosome as packed
         pixel rows covering that many distances (enough for ``--upper 300`` with windows up to 25 x 25;
@@ -83,6 +86,8 @@ class PKCool:
         extra = {}
         if b1.size and int((b2 - b1).max()) <= 65535 and int(cnt.max()) <= 65535 and int(cnt.min()) >= 0:
             extra = dict(delta16=(b2 - b1).astype(np.uint16), count16=cnt.astype(np.uint16))
+        if divisive:
+            extra["divisive_columns"] = np.array([weight_name])
         if rows_nd and rows_nd > 0:
             extra["rows_nd"] = np.int64(rows_nd)
             for i, c in enumerate(chroms):
@@ -141,6 +146,9 @@ class PKCool:
         rp = np.searchsorted(self.bin1_id[lo:hi], np.arange(off, off + n + 1), side="left").astype(np.int64)
         return rp, np.ascontiguousarray(self.delta16[lo:hi]), np.ascontiguousarray(self.count16[lo:hi])
 
+    def weights_divisive(self, name: str) -> bool:
+        return name in self.divisive
+
     def upper_pixels_rows(self, chrom: str, nd_min: int):
         """Packed pixel rows of the chromosome (uint8 blob for ``pk_chrom_upload_rows``) when the
         container holds them and they cover ``nd_min`` distances, else None."""
@@ -175,6 +183,9 @@ class _MatrixSelector:
         if self._balance:
             name = "weight" if self._balance is True else self._balance
             w = self._s.weights(chrom, name)
+            if self._s.weights_divisive(name):             # cooler: bias = 1 / bias for divisive_weights columns
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    w = 1.0 / w
             data = w[row] * w[col] * data
         mat = sp.coo_matrix((data, (row, col)), shape=(n, n))
         return mat if self._sparse else mat.toarray()
@@ -251,6 +262,12 @@ class _RealCoolAdapter:
         b1, b2, cnt = self.upper_pixels(chrom)
         rp = np.searchsorted(b1, np.arange(self.nbins(chrom) + 1)).astype(np.int64)
         return rp, b2, cnt
+
+    def weights_divisive(self, name):
+        try:
+            return bool(self._c.open("r")["bins"][name].attrs.get("divisive_weights", False))
+        except Exception:
+            return False
 
     def weights(self, chrom, name):
         return np.ascontiguousarray(self._c.bins().fetch(chrom)[name].values, dtype=np.float64)
@@ -366,6 +383,18 @@ class H5Cool:
         if int(delta.max()) > 65535 or int(delta.min()) < 0 or int(cnt.max()) > 65535:
             return None
         return rp, delta.astype(np.uint16), cnt.astype(np.uint16)
+
+    def weights_divisive(self, name: str) -> bool:
+        """cooler's column attribute `divisive_weights` (set by hic2cool for KR / VC columns): the balanced
+        value divides by the weights instead of multiplying."""
+        key = "bins/" + name
+        if key not in self._g:
+            raise KeyError("no weight column %r in %s" % (name, self.path))
+        v = self._g[key].attrs.get("divisive_weights")
+        try:
+            return bool(np.asarray(v).ravel()[0]) if v is not None else False
+        except (IndexError, ValueError):
+            return False
 
     def weights(self, chrom: str, name: str) -> np.ndarray:
         key = "bins/" + name

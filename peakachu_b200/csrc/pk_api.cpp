@@ -491,7 +491,7 @@ extern "C" int pk_chrom_destroy(pk_chrom* c) {
     if (!c) return PK_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream); else cudaDeviceSynchronize();
-    dev_free(c->d_band); dev_free(c->d_w); dev_free(c->d_valid); dev_free(c->d_vbits); dev_free(c->d_scratch);
+    dev_free(c->d_band); dev_free(c->d_w); dev_free(c->d_wp); dev_free(c->d_valid); dev_free(c->d_vbits); dev_free(c->d_scratch);
     dev_free(c->d_diag_sum); dev_free(c->d_diag_cnt);
     dev_free(c->d_exp); dev_free(c->d_bg); dev_free(c->d_head);
     c->d_flags = nullptr; c->d_counters = nullptr; c->d_ncand = nullptr; c->d_batch_win = nullptr;
@@ -556,6 +556,22 @@ static int after_band(pk_chrom* c) {
     PK_CHECK(pk_launch_diag_sums(c));
     if (c->timing) PK_CUDA(cudaEventRecord(c->ev[2], s));
     c->has_pixels = true; c->has_expected = false; c->has_candidates = false; c->has_scores = false;
+    c->use_wp = false;
+    return PK_OK;
+}
+
+// Weights of the Poisson filter alone (scoreUtils.py:55-57) when they are not the ones that balance the
+// pixel values: cooler inverts a weight column flagged `divisive_weights` inside matrix(balance=...), while
+// the reference hands the column's raw values to Chromosome (score_chromosome.py:44).
+extern "C" int pk_chrom_set_poisson_weights(pk_chrom* c, const double* weights, int mem) {
+    if (!c || !weights) { pk_set_error("pk_chrom_set_poisson_weights: bad argument"); return PK_EINVAL; }
+    if (!c->balanced) { pk_set_error("pk_chrom_set_poisson_weights: raw mode has no weights"); return PK_ESTATE; }
+    if (!c->has_pixels) { pk_set_error("pk_chrom_set_poisson_weights: upload the pixels first"); return PK_ESTATE; }
+    PK_CUDA(cudaSetDevice(c->device));
+    if (!c->d_wp) PK_CHECK(dev_alloc(&c->d_wp, (size_t)c->n));
+    PK_CUDA(cudaMemcpyAsync(c->d_wp, weights, (size_t)c->n * sizeof(double),
+                            (mem & ~PK_PIXELS_SORTED) == PK_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
+    c->use_wp = true; c->has_candidates = false; c->has_scores = false;
     return PK_OK;
 }
 
@@ -1343,6 +1359,7 @@ extern "C" int pk_engine_submit(pk_engine* e, const pk_unit* u) {
         default: pk_set_error("pk_engine_submit: unknown encoding %d", u->encoding); r = PK_EINVAL;
         }
     }
+    if (r == PK_OK && u->poisson_weights) r = pk_chrom_set_poisson_weights(c, u->poisson_weights, PK_MEM_HOST);
     if (r == PK_OK) r = pk_chrom_fit_expected(c);
     if (r == PK_OK) r = pk_chrom_find_candidates(c, u->row_begin, u->row_end, nullptr);
     if (r == PK_OK) r = pk_chrom_score(c, e->forest, u->min_prob);

@@ -99,6 +99,8 @@ struct pk_chrom {
     // device buffers
     int32_t* d_band = nullptr;       // [ND][pitch] raw counts, diagonal-major
     double* d_w = nullptr;           // [n]
+    double* d_wp = nullptr;          // [n] weights of the Poisson filter when they differ from d_w (pk_chrom_set_poisson_weights)
+    bool use_wp = false;
     uint8_t* d_valid = nullptr;      // [n]
     uint32_t* d_vbits = nullptr;     // [ceil(n/32)] the same, one bit per bin
     double* d_scratch = nullptr;     // [ND][pitch] compacted diagonal values

@@ -863,6 +863,8 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int res
         switch (variant) {
         case 1: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 2>(prm, f, c->ND, sm, st);
         case 2: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 1>(prm, f, c->ND, sm, st);
+        case 3: return launch_fused_t<5, 128, 2, 2112, 2, 2, 256, 2>(prm, f, c->ND, sm, st);      // two CTAs per SM: their phases drift apart and overlap
+        case 4: return launch_fused_t<5, 128, 2, 2112, 4, 2, 256, 2>(prm, f, c->ND, sm, st);
         default: return cf ? launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4, 0, 1>(prm, f, c->ND, sm, st)
                            : launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4>(prm, f, c->ND, sm, st);
         }

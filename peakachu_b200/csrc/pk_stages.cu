@@ -1024,7 +1024,7 @@ int pk_launch_candidates(pk_chrom* c, const double* d_crit, int kmax) {
     const long long m = (long long)nd * c->n_chunks;
     dim3 grid(c->n_chunks, nd);
     uint2* counts = reinterpret_cast<uint2*>(c->d_cstate);
-    k_cand_mark<<<grid, 256, 0, c->stream>>>(c->d_band, c->d_w, c->d_bg, c->n, c->pitch, c->balanced, c->lower, d_crit, kmax,
+    k_cand_mark<<<grid, 256, 0, c->stream>>>(c->d_band, c->use_wp ? c->d_wp : c->d_w, c->d_bg, c->n, c->pitch, c->balanced, c->lower, d_crit, kmax,
                                             c->row_begin, c->row_end, c->n_chunks, c->d_bits, counts, c->d_flags);
     PK_CUDA(cudaGetLastError());
     k_cand_write<<<grid, 256, 0, c->stream>>>(c->d_bits, counts, c->lower, c->row_begin, c->row_end, c->n_chunks, m, c->cand_cap,

@@ -221,6 +221,18 @@ class Chromosome:
                                                 _lib.ptr(self.weights), mem))
         self._after_upload(L, first_tile, n)
 
+    def set_poisson_weights(self, weights):
+        """Weights of the Poisson filter alone (``pk_chrom_set_poisson_weights``): the raw values of a
+        ``divisive_weights`` column, whose reciprocals balanced the pixels. Re-runs the candidate scan."""
+        wp = _lib.as_c(weights, np.float64)
+        if wp.size != self.n:
+            raise ValueError("poisson weights must have n_bins entries")
+        self._keepalive.append(wp)
+        L = _lib.lib()
+        _lib.check(L.pk_chrom_set_poisson_weights(self._h, _lib.ptr(wp), _lib.PK_MEM_HOST))
+        _lib.check(L.pk_chrom_find_candidates(self._h, 0, self.n, None))
+        self._ncand = self._cand = None
+
     def _after_upload(self, L, first_tile, n):
         _lib.check(L.pk_chrom_fit_expected(self._h))
         self._exp = None

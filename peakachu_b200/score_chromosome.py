@@ -24,11 +24,14 @@ def main(args):
     ccname = args.chrom
     cikada = "chr" + ccname.lstrip("chr")                 # :37-38
 
-    weights = Lib.weights(ccname, correct) if correct else None   # :44
+    from .shard import map_weights
+    weights, pweights = map_weights(Lib, ccname, correct)         # :44 (a divisive_weights column is inverted for the values)
     forest = DeviceForest.of(flat, device)
     # replaces :42-43 (matrix fetch + tocsr): the chromosome's pixel columns as the reader stores them
     X = Chromosome.from_map(Lib, ccname, weights, forest, lower=args.lower, upper=args.upper, cname=cikada,
                             res=args.resolution, width=width, device=device)
+    if pweights is not None:
+        X.set_poisson_weights(pweights)
     result, R = X.score(thre=args.minimum_prob)           # :70
     X.writeBed(args.output, result, R)                    # :71
     X.close()

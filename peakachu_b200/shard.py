@@ -355,16 +355,17 @@ class Engine:
             hit = cls._cache[key] = cls(forest, lower, upper, device, depth)
         return hit
 
-    def submit(self, tag, n_bins, row_begin, row_end, encoding, a, b, c, size, weights, min_prob):
+    def submit(self, tag, n_bins, row_begin, row_end, encoding, a, b, c, size, weights, min_prob, poisson_weights=None):
         import ctypes as C
 
         from . import _lib
-        arrays = [v for v in (a, b, c, weights) if v is not None]
+        arrays = [v for v in (a, b, c, weights, poisson_weights) if v is not None]
         self._keep.extend(arrays)                        # uploads are asynchronous when the source is pinned
         u = _lib.Unit(int(tag), int(n_bins), int(row_begin), int(row_end), int(encoding),
                       a.ctypes.data if a is not None else None, b.ctypes.data if b is not None else None,
                       c.ctypes.data if c is not None else None, int(size),
-                      weights.ctypes.data if weights is not None else None, float(min_prob))
+                      weights.ctypes.data if weights is not None else None,
+                      poisson_weights.ctypes.data if poisson_weights is not None else None, float(min_prob))
         rc = self._L.pk_engine_submit(self._h, C.byref(u))
         if rc != 0:
             msg = self._L.pk_last_error().decode("utf-8", "replace")
@@ -411,6 +412,22 @@ class Engine:
         if self._h:
             self._L.pk_engine_destroy(self._h)
             self._h = None
+
+
+def map_weights(Lib, key, correct):
+    """(weights that balance the pixel values, weights of the Poisson filter or None when they are the same)
+    of one chromosome. cooler's ``matrix(balance=name)`` multiplies by the column -- or by its reciprocal
+    when the column carries ``divisive_weights`` (hic2cool's KR / VC columns) -- while the reference hands
+    the column's raw values to ``Chromosome`` (score_chromosome.py:42-44), which divides the expected value
+    by them in the Poisson filter (scoreUtils.py:55-57)."""
+    from . import _lib
+    if not correct:
+        return None, None
+    w = _lib.as_c(Lib.weights(key, correct), np.float64)
+    if getattr(Lib, "weights_divisive", None) is not None and Lib.weights_divisive(correct):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.ascontiguousarray(1.0 / w), w
+    return w, None
 
 
 def _unit_columns(Lib, key, nd_need, encoding):
@@ -466,10 +483,10 @@ def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_pro
             n = Lib.nbins(key)
             nd_need = min(upper, n - 2 * w) + 2 * w + 1              # stored distances (scoreUtils.py:14,31)
             enc, ca, cb, cc, size = _unit_columns(Lib, key, nd_need, encoding)
-            weights = _lib.as_c(Lib.weights(key, correct), np.float64) if correct else None
+            weights, pweights = map_weights(Lib, key, correct)
             if weights is not None and weights.size != n:
                 raise ValueError("weight column of %s has %d entries for %d bins" % (key, weights.size, n))
-            eng.submit(len(keys), n, a, b, enc, ca, cb, cc, size, weights, min_prob)
+            eng.submit(len(keys), n, a, b, enc, ca, cb, cc, size, weights, min_prob, pweights)
             keys.append(key)
         results = eng.collect(copy=copy)
     except BaseException:

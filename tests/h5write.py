@@ -253,7 +253,9 @@ def write_cool(path: str, chroms, binsize: int, weight_name: str = "weight", tra
             "start": W.dataset(start, **z), "end": W.dataset(end, **z),
             weight_name: W.dataset(w, attrs={"ignore_diags": np.int64(2), "converged": np.uint8(1)}, skip_filter_on=1, **z)}
     for k, v in (extra_bins or {}).items():
-        bins[k] = W.dataset(v, **z)
+        # a column named like hic2cool's KR / VC carries cooler's `divisive_weights` attribute
+        at = {"divisive_weights": np.uint8(1)} if k in ("KR", "VC", "VC_SQRT") else None
+        bins[k] = W.dataset(v, attrs=at, **z)
     g_bins = W.group(bins)
     g_pixels = W.group({"bin1_id": W.dataset(b1, **z), "bin2_id": W.dataset(b2, **z),
                         "count": W.dataset(cnt, fletcher=True, **z)})

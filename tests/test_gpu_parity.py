@@ -191,6 +191,42 @@ def test_bedpe_from_a_real_cool_file(name, group, tmp_path):
     assert open(out).read() == case.bedpe
 
 
+@pytest.mark.parametrize("container", ["pkcool", "cool"])
+def test_divisive_weight_column(container, tmp_path):
+    """A weight column flagged `divisive_weights` (hic2cool's KR / VC): cooler's matrix(balance=name) divides by
+    the weights, while the reference hands the raw column to Chromosome, which uses it in the Poisson filter
+    (score_chromosome.py:42-44, scoreUtils.py:55-57). The CLI reproduces the oracle run on such a map -- and
+    differs from a run that treats the column as multiplicative."""
+    import copy
+    from oracle import peakachu_oracle as po
+    from peakachu_b200 import coolio, score_chromosome
+    from tests import h5write
+    case = Case("tiny")
+    cfg = case.cfg
+    ch = copy.copy(case.chroms[0])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        kr = 1.0 / ch.weights                       # the column as hic2cool stores it: balanced = count / (kr_i kr_j)
+    ref_path = os.path.join(str(tmp_path), "ref.pkcool")
+    ch_kr = copy.copy(ch)
+    ch_kr.weights = kr
+    coolio.PKCool.write(ref_path, [ch_kr], cfg["res"], weight_name="KR", divisive=True)
+    lib = coolio.Cooler(ref_path)                  # the stand-in inverts a divisive column like cooler does
+    out_o = os.path.join(str(tmp_path), "oracle.bedpe")
+    po.score_map(lib, case.model(), [ch.name], weight_name="KR", lower=cfg["lower"], upper=cfg["upper"],
+                 res=cfg["res"], min_prob=cfg["min_prob"], output=out_o)
+    if container == "pkcool":
+        path = ref_path
+    else:
+        path = os.path.join(str(tmp_path), "kr.cool")
+        h5write.write_cool(path, [ch], cfg["res"], extra_bins={"KR": kr})
+    out = os.path.join(str(tmp_path), "gpu.bedpe")
+    ns = argparse.Namespace(path=path, model=case.pkl, output=out, resolution=cfg["res"], lower=cfg["lower"],
+                            upper=cfg["upper"], minimum_prob=cfg["min_prob"], clr_weight_name="KR", chrom=ch.name)
+    score_chromosome.main(ns)
+    assert open(out).read() == open(out_o).read()
+    assert open(out).read() != case.bedpe           # the Poisson filter saw the raw column, not its reciprocal
+
+
 def test_forest_npz_and_pkl_give_same_tables():
     from peakachu_b200.forest import load_model
     case = Case("tiny")

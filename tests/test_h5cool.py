@@ -77,6 +77,7 @@ def test_cool_round_trip(tmp_path, userblock, group, chunk, latest):
         assert narrow is not None
         np.testing.assert_array_equal(narrow[1].astype(np.int64) + b1, b2)
         np.testing.assert_array_equal(narrow[2], cnt)
+        assert lib.weights_divisive("KR") and not lib.weights_divisive("weight")      # cooler's column attribute
         w = lib.weights(c.name, "weight")
         np.testing.assert_array_equal(w, c.weights)           # NaN positions included
         np.testing.assert_array_equal(lib.weights(c.name, "KR"), np.arange(off, off + c.n, dtype=np.float64))
