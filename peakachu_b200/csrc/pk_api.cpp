@@ -463,6 +463,7 @@ extern "C" int pk_chrom_create(int device, int32_t n_bins, int32_t width, int32_
     const size_t bandsz = (size_t)c->ND * (size_t)c->pitch;
     if ((r = dev_alloc(&c->d_band, bandsz)) || (r = dev_alloc(&c->d_w, (size_t)n_bins)) ||
         (r = dev_alloc(&c->d_valid, (size_t)n_bins)) || (r = dev_alloc(&c->d_vbits, (size_t)n_bins / 32 + 4)) ||
+        (r = dev_alloc(&c->d_scratch, bandsz)) ||
         (r = dev_alloc(&c->d_diag_sum, (size_t)c->ND)) || (r = dev_alloc(&c->d_diag_cnt, (size_t)c->ND)) ||
         (r = dev_alloc(&c->d_exp, (size_t)c->ND)) || (r = dev_alloc(&c->d_bg, (size_t)c->ND)) ||
         (r = dev_alloc(&c->d_rowptr, (size_t)n_bins + 1))) {
@@ -490,7 +491,7 @@ extern "C" int pk_chrom_destroy(pk_chrom* c) {
     if (!c) return PK_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream); else cudaDeviceSynchronize();
-    dev_free(c->d_band); dev_free(c->d_w); dev_free(c->d_wp); dev_free(c->d_valid); dev_free(c->d_vbits);
+    dev_free(c->d_band); dev_free(c->d_w); dev_free(c->d_wp); dev_free(c->d_valid); dev_free(c->d_vbits); dev_free(c->d_scratch);
     dev_free(c->d_diag_sum); dev_free(c->d_diag_cnt);
     dev_free(c->d_exp); dev_free(c->d_bg); dev_free(c->d_head);
     c->d_flags = nullptr; c->d_counters = nullptr; c->d_ncand = nullptr; c->d_batch_win = nullptr;

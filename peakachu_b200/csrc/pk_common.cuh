@@ -103,6 +103,7 @@ struct pk_chrom {
     bool use_wp = false;
     uint8_t* d_valid = nullptr;      // [n]
     uint32_t* d_vbits = nullptr;     // [ceil(n/32)] the same, one bit per bin
+    double* d_scratch = nullptr;     // [ND][pitch] compacted diagonal values
     double* d_diag_sum = nullptr;    // [ND]
     long long* d_diag_cnt = nullptr; // [ND]
     double* d_exp = nullptr;         // [ND]

@@ -290,27 +290,59 @@ __global__ void __launch_bounds__(256) k_valid_bits(const uint8_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------
-// S2  per-diagonal sums in numpy's pairwise order (utils.py:160-170), one CTA per distance d, no scratch.
-//     The summed array is diag[valid]: the values (zeros included) of the pairs x with valid[x] & valid[x+d],
-//     in x order. numpy's pairwise tree over its nd elements (n > 128 -> n2 = n/2 - (n/2)%8 | rest; leaves of
-//     64..128 elements with 8 strided accumulators combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then a
-//     sequential tail) depends on nd alone, and the node sizes of one depth differ by at most 15. So:
-//       1. the pair mask of the diagonal and its running popcount go to shared memory (rank -> x);
-//       2. one warp tabulates, depth by depth, the few node sizes that occur and their leaf counts;
-//       3. every leaf is found by its index with a walk down those tables (no table of segments is built),
-//          and summed straight from the band by an octet of lanes, values computed on the fly;
-//       4. the leaf that starts the right half of a node adds its half onto the left one, deepest nodes first.
-//     Nothing is compacted or written back: the band is read once, in place.
+// S2  per-diagonal sums in numpy's pairwise order (utils.py:160-170).
+//     One CTA per distance d. Each warp owns a contiguous slice of the diagonal:
+//     it counts its valid pairs (valid[x] & valid[x+d]), a block scan turns the
+//     counts into offsets, and the warp writes value(x, d) of its valid pairs,
+//     zeros included and order kept, into the compacted scratch row. numpy's
+//     pairwise tree (n > 128 -> n2 = n/2 - (n/2)%8 | rest; leaves of <= 128
+//     elements with 8 strided accumulators combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)),
+//     then a sequential tail) is evaluated leaf-parallel, combined by one thread.
 // ---------------------------------------------------------------------------
 #define PK_DS_THREADS 256
-#define PK_DS_LEVELS 16
-#define PK_DS_WIDTH 32
+#define PK_DS_LEVELS 14
 
-struct DiagHdr {
-    int lo[PK_DS_LEVELS + 1], hi[PK_DS_LEVELS + 1];
-    int nlt[PK_DS_LEVELS + 1][PK_DS_WIDTH];     // leaves under a node of size lo[k] + i at depth k
-    int K, nd, nl, bad;
-    int wsum[PK_DS_THREADS / 32];
+// numpy's leaf: eight strided accumulators r_j = a[j] + a[j+8] + ..., combined as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the n%8 tail added one by one. Eight lanes
+// (an aligned octet of a warp) take one accumulator each: all of a lane's values are
+// loaded before the first add, so a leaf costs one memory latency, not sixteen.
+// Every lane of the warp must call it; lanes of an octet share (a, n); n <= 128.
+__device__ __forceinline__ double pk_leaf_sum8(const double* __restrict__ a, int n, int j /* lane & 7 */) {
+    const int nb = n < 8 ? 0 : (n - (n % 8));      // elements covered by the accumulators
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (j + 8 * i < nb) ? a[j + 8 * i] : 0.0;
+    double tail[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) tail[i] = (j == 0 && nb + i < n) ? a[nb + i] : 0.0;
+    double r = v[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i)
+        if (j + 8 * i < nb) r = __dadd_rn(r, v[i]);
+    // pairwise combine across the octet (addition is commutative, so the partner order is free)
+    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+    if (n < 8) r = 0.0;                              // numpy: plain loop from 0.0 for short arrays
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+        if (nb + i < n) r = __dadd_rn(r, tail[i]);
+    return r;                                         // valid in lane j == 0
+}
+
+// numpy's recursion, one level at a time, all threads: segments (start, size) of level l
+// become those of level l+1 (a segment of more than 128 elements splits into
+// n2 = m/2 - (m/2)%8 and the rest, others are carried over), order preserved. The split
+// bitmask of every level is kept so that the sums can be combined back up the same tree.
+template <int CAP>                 // leaves per diagonal handled in shared memory (n up to ~57 * CAP bins)
+struct DiagSmem {
+    int32_t seg_s[2][CAP];
+    int32_t seg_m[2][CAP];
+    double val[2][CAP];
+    uint32_t split[PK_DS_LEVELS][CAP / 32];
+    uint16_t wpre[PK_DS_LEVELS][CAP / 32];      // splits in the words before this one
+    int32_t nseg[PK_DS_LEVELS + 1];
+    int32_t wcnt[PK_DS_THREADS / 32];
 };
 
 // pair mask of bins x0..x0+31 on diagonal d: valid[x] & valid[x+d], from the bit vector
@@ -320,182 +352,175 @@ __device__ __forceinline__ uint32_t pk_pair_word(const uint32_t* __restrict__ vb
     return vb[x0 >> 5] & __funnelshift_r(lo, hi, y0 & 31);
 }
 
-// position of the k-th (0-based) set bit of m; k < popc(m)
-__device__ __forceinline__ int pk_select32(uint32_t m, int k) {
-    if (m == 0xffffffffu) return k;
-    int pos = 0, c;
-    c = __popc(m & 0xFFFFu); if (k >= c) { k -= c; pos += 16; m >>= 16; }
-    c = __popc(m & 0xFFu);   if (k >= c) { k -= c; pos += 8;  m >>= 8; }
-    c = __popc(m & 0xFu);    if (k >= c) { k -= c; pos += 4;  m >>= 4; }
-    c = __popc(m & 0x3u);    if (k >= c) { k -= c; pos += 2;  m >>= 2; }
-    c = (int)(m & 1u);       if (k >= c) pos += 1;
-    return pos;
-}
-
-__device__ __forceinline__ void pk_np_split(int m, int& left, int& right) {
-    int n2 = m / 2;
-    n2 -= n2 % 8;
-    left = n2; right = m - n2;
-}
-
-__global__ void __launch_bounds__(PK_DS_THREADS, 3) k_diag_sums(
+// Compaction, wide: CTA (slice, d) owns PK_DC_SLICE consecutive x of diagonal d. Its output offset is the
+// number of valid pairs before its slice, counted straight from the bit vector (at most n / 32 words), so
+// no scan kernel and no ordering between CTAs is needed. Slice 0 also writes the diagonal's total.
+#define PK_DC_SLICE 2048
+__global__ void __launch_bounds__(256) k_diag_compact(
     const int32_t* __restrict__ band, const double* __restrict__ w, const uint32_t* __restrict__ vbits, int n_words,
-    int n, long long pitch, int balanced, int cap_leaves, double* __restrict__ out_sum,
-    long long* __restrict__ out_cnt, int32_t* __restrict__ flags) {
-    extern __shared__ __align__(16) unsigned char ds_raw[];
-    const int d = blockIdx.x;
-    const int len = max(n - d, 0);
-    const int nwd = (len + 31) / 32;
-    // layout: header | leaf sums f64[cap] | vb u32[n_words + 2] | pw u32[nwd] | pp u32[nwd + 1] | own_c i32[cap] | own_k u8[cap]
-    DiagHdr& hd = *reinterpret_cast<DiagHdr*>(ds_raw);
-    double* s_res = reinterpret_cast<double*>(ds_raw + ((sizeof(DiagHdr) + 15) & ~(size_t)15));
-    uint32_t* s_vb = reinterpret_cast<uint32_t*>(s_res + cap_leaves);
-    uint32_t* s_pw = s_vb + n_words + 2;
-    uint32_t* s_pp = s_pw + (n_words + 1);
-    int32_t* s_ownc = reinterpret_cast<int32_t*>(s_pp + (n_words + 2));
-    uint8_t* s_ownk = reinterpret_cast<uint8_t*>(s_ownc + cap_leaves);
+    int n, long long pitch, int balanced, double* __restrict__ scratch, long long* __restrict__ out_cnt) {
+    extern __shared__ uint32_t s_vbc[];                 // [n_words + 2]
+    __shared__ int s_part[8];
+    const int d = blockIdx.y, len = n - d;
+    const int xs = blockIdx.x * PK_DC_SLICE;
+    if (xs >= len && blockIdx.x != 0) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int i = tid; i < n_words + 2; i += PK_DS_THREADS) s_vb[i] = i < n_words ? vbits[i] : 0u;
+    for (int i = tid; i < n_words + 2; i += 256) s_vbc[i] = i < n_words ? vbits[i] : 0u;
     __syncthreads();
-    // ---- 1. pair mask and its running popcount ----
-    const int per = (nwd + PK_DS_THREADS - 1) / PK_DS_THREADS;
-    const int i0 = min(tid * per, nwd), i1 = min(i0 + per, nwd);
+    // valid pairs in the words before this slice (slice 0: in the whole diagonal, for out_cnt)
+    const int w_end = blockIdx.x == 0 ? (len + 31) / 32 : xs / 32;
+    int cntw = 0;
+    for (int wi = tid; wi < w_end; wi += 256) {
+        uint32_t m = pk_pair_word(s_vbc, wi * 32, d);
+        if (wi * 32 + 32 > len) m &= (len - wi * 32 > 0) ? ((1u << (len - wi * 32)) - 1u) : 0u;
+        cntw += __popc(m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cntw += __shfl_xor_sync(0xffffffffu, cntw, o);
+    if (lane == 0) s_part[wid] = cntw;
+    __syncthreads();
+    int before = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) before += s_part[k];
+    if (blockIdx.x == 0) {
+        if (tid == 0) out_cnt[d] = before;
+        before = 0;
+    }
+    if (xs >= len) return;
+    // this warp's 256 elements: valid pairs before them inside the slice
+    const int xe = min(len, xs + PK_DC_SLICE);
+    const int xw0 = xs + wid * 256;
+    uint32_t m[8];
     int mine = 0;
-    for (int i = i0; i < i1; ++i) {
-        uint32_t m = pk_pair_word(s_vb, i * 32, d);
-        if (i * 32 + 32 > len) m &= (1u << (len - i * 32)) - 1u;          // len - 32 i in [1, 31]
-        s_pw[i] = m;
-        mine += __popc(m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int xw = xw0 + j * 32;
+        m[j] = xw < xe ? pk_pair_word(s_vbc, xw, d) : 0u;
+        if (xw < xe && xw + 32 > xe) m[j] &= (1u << (xe - xw)) - 1u;
+        mine += __popc(m[j]);
     }
-    int incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    if (lane == 31) hd.wsum[wid] = incl;
     __syncthreads();
-    int base = incl - mine, nd = 0;
+    if (lane == 0) s_part[wid] = mine;
+    __syncthreads();
+    int base = before;
 #pragma unroll
-    for (int k = 0; k < PK_DS_THREADS / 32; ++k) { const int t = hd.wsum[k]; if (k < wid) base += t; nd += t; }
-    for (int i = i0; i < i1; ++i) { s_pp[i] = (uint32_t)base; base += __popc(s_pw[i]); }
-    if (tid == 0) { s_pp[nwd] = (uint32_t)nd; out_cnt[d] = nd; }
-    // ---- 2. node sizes per depth and the leaves under them (one warp) ----
-    if (wid == 0) {
-        int lo = nd, hi = nd, K = 0, bad = 0;
-        if (lane == 0) { hd.lo[0] = nd; hd.hi[0] = nd; }
-        while (hi > 128) {
-            const int m = lo + lane;
-            int mn = 0x7fffffff, mx = 0;
-            if (m <= hi && m > 128) { int a, b; pk_np_split(m, a, b); mn = min(a, b); mx = max(a, b); }
+    for (int k = 0; k < 8; ++k) if (k < wid) base += s_part[k];
+    double* sc = scratch + (long long)d * pitch;
+    const int32_t* row = band + (long long)d * pitch;
+    int c[8]; double wa[8], wb[8];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
-            ++K;
-            if (mx - mn + 1 > PK_DS_WIDTH || K >= PK_DS_LEVELS) { bad = 1; break; }
-            lo = mn; hi = mx;
-            if (lane == 0) { hd.lo[K] = lo; hd.hi[K] = hi; }
-        }
-        __syncwarp();
-        if (!bad) {
-            hd.nlt[K][lane] = 1;
-            __syncwarp();
-            for (int k = K - 1; k >= 0; --k) {
-                const int m = hd.lo[k] + lane;
-                int v = 1;
-                if (m <= hd.hi[k] && m > 128) {
-                    int a, b;
-                    pk_np_split(m, a, b);
-                    v = hd.nlt[k + 1][a - hd.lo[k + 1]] + hd.nlt[k + 1][b - hd.lo[k + 1]];
-                }
-                hd.nlt[k][lane] = v;
-                __syncwarp();
+    for (int j = 0; j < 8; ++j) {
+        const int x = xw0 + j * 32 + lane;
+        const bool f = (m[j] >> lane) & 1u;
+        c[j] = f ? __ldg(row + x) : 0;
+        wa[j] = (f && balanced) ? __ldg(w + x) : 0.0;
+        wb[j] = (f && balanced) ? __ldg(w + x + d) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if ((m[j] >> lane) & 1u) {
+            double val;
+            if (c[j] == 0) val = 0.0;
+            else if (!balanced) val = (double)c[j];
+            else {
+                val = __dmul_rn(__dmul_rn(wa[j], wb[j]), (double)c[j]);            // pk_value
+                if (!(pk_weight_tame(wa[j]) && pk_weight_tame(wb[j])) && !isfinite(val)) val = 0.0;
             }
+            sc[base + __popc(m[j] & ((1u << lane) - 1u))] = val;
         }
-        if (lane == 0) { hd.K = K; hd.nd = nd; hd.nl = bad ? 0 : hd.nlt[0][0]; hd.bad = bad || (!bad && hd.nlt[0][0] > cap_leaves); }
+        base += __popc(m[j]);
+    }
+}
+
+// Sums: one CTA per distance over the compacted row (k_diag_compact). numpy's pairwise tree is built level by
+// level in shared memory by ONE warp (warp barriers only: the table is a few hundred segments, block-wide
+// barriers would cost more than the work), the leaf sums are taken by all threads, an octet of lanes per
+// leaf, and the same warp combines them back up the tree. 256 threads and few registers: every distance's
+// CTA is resident at once (the kernel is bound by the latency of its dependent steps, not by bandwidth).
+template <int CAP>
+__global__ void __launch_bounds__(PK_DS_THREADS) k_diag_sums(
+    long long pitch, const double* __restrict__ scratch,
+    double* __restrict__ out_sum, const long long* __restrict__ out_cnt, int32_t* __restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char ds_raw[];
+    DiagSmem<CAP>& sm = *reinterpret_cast<DiagSmem<CAP>*>(ds_raw);
+    __shared__ int s_L, s_cur, s_overflow;
+    const int d = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double* sc = scratch + (long long)d * pitch;
+    const int nd = (int)out_cnt[d];
+    // ---- leaf table, level by level (warp 0) ----
+    if (wid == 0) {
+        if (lane == 0) { sm.seg_s[0][0] = 0; sm.seg_m[0][0] = nd; sm.nseg[0] = 1; }
+        __syncwarp();
+        int cur = 0, L = 0;
+        bool overflow = false;
+        for (;; ++L) {
+            const int ns = sm.nseg[L];
+            const int nw = (ns + 31) / 32;
+            int carry = 0;
+            for (int w0 = 0; w0 < nw; ++w0) {               // split mask of this level, word by word, with its prefix
+                const int i = w0 * 32 + lane;
+                const bool sp = (i < ns) && sm.seg_m[cur][i] > 128;
+                const unsigned bal = __ballot_sync(0xffffffffu, sp);
+                if (lane == 0) { sm.split[L][w0] = bal; sm.wpre[L][w0] = (uint16_t)carry; }
+                carry += __popc(bal);
+            }
+            const int ns_next = ns + carry;
+            if (lane == 0) sm.nseg[L + 1] = ns_next;
+            __syncwarp();
+            if (ns_next == ns) break;                        // nothing split: level L holds the leaves
+            if (ns_next > CAP || L + 1 >= PK_DS_LEVELS) { overflow = true; break; }
+            for (int i = lane; i < ns; i += 32) {
+                const uint32_t word = sm.split[L][i >> 5];
+                const int pos = i + sm.wpre[L][i >> 5] + __popc(word & ((1u << (i & 31)) - 1u));
+                const int s0 = sm.seg_s[cur][i], m = sm.seg_m[cur][i];
+                if ((word >> (i & 31)) & 1u) {
+                    int n2 = m / 2;
+                    n2 -= n2 % 8;
+                    sm.seg_s[cur ^ 1][pos] = s0;          sm.seg_m[cur ^ 1][pos] = n2;
+                    sm.seg_s[cur ^ 1][pos + 1] = s0 + n2; sm.seg_m[cur ^ 1][pos + 1] = m - n2;
+                } else {
+                    sm.seg_s[cur ^ 1][pos] = s0; sm.seg_m[cur ^ 1][pos] = m;
+                }
+            }
+            __syncwarp();
+            cur ^= 1;
+        }
+        if (lane == 0) { s_L = L; s_cur = cur; s_overflow = overflow ? 1 : 0; }
     }
     __syncthreads();
-    if (hd.bad) {                           // diagonal longer than the shared-memory tables: refuse loudly
+    if (s_overflow) {                       // diagonal longer than the shared-memory tables: refuse loudly
         if (tid == 0) { atomicOr(&flags[2], 2); out_sum[d] = CUDART_NAN; }
         return;
     }
-    const int nl = hd.nl, K = hd.K;
-    const int32_t* row = band + (long long)d * pitch;
-    // ---- 3. leaves: an octet of lanes per leaf ----
-    const int j = tid & 7;
-    for (int l0 = 0; l0 < nl; l0 += PK_DS_THREADS / 8) {           // uniform trip count: shuffles inside
+    const int L = s_L, cur = s_cur;
+    // ---- leaf sums (8 strided accumulators + tail): an octet of lanes per leaf ----
+    const int nl = sm.nseg[L];
+    constexpr int OCT = PK_DS_THREADS / 8;
+    for (int l0 = 0; l0 < nl; l0 += OCT) {                        // uniform trip count: shuffles inside
         const int l = l0 + (tid >> 3);
         const bool have = l < nl;
-        // walk down to leaf l: start s and size m in the compacted order; the node it closes (see step 4)
-        int s = 0, m = have ? nd : 0, li = l, own_k = 255, own_c = 0;
-        for (int k = 0; m > 128; ++k) {
-            int a, b;
-            pk_np_split(m, a, b);
-            const int c = hd.nlt[k + 1][a - hd.lo[k + 1]];
-            if (li < c) { m = a; }
-            else {
-                li -= c; s += a; m = b;
-                if (li == 0) { own_k = k; own_c = c; } else own_k = 255;
-            }
-        }
-        if (have && j == 0) { s_ownk[l] = (uint8_t)own_k; s_ownc[l] = own_c; }
-        // numpy's leaf: accumulator j takes elements j, j + 8, ... of the first nb, the tail goes one by one
-        const int nb = m < 8 ? 0 : m - (m % 8);
-        double r = 0.0;
-        int wi = 0;
-        if (nb > 0 || m > 0) {                 // word holding rank s + j (or s for the tail-only case)
-            const uint32_t r0 = (uint32_t)(s + (nb > 0 ? j : 0));
-            int lo_ = 0, hi_ = nwd;            // largest wi with pp[wi] <= r0
-            while (hi_ - lo_ > 1) { const int mid = (lo_ + hi_) >> 1; if (s_pp[mid] <= r0) lo_ = mid; else hi_ = mid; }
-            wi = lo_;
-        }
-        const int wi_start = wi;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            int cnt[8];
-            double wa[8], wb[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int e = j + 8 * (h * 8 + i);
-                cnt[i] = 0; wa[i] = 0.0; wb[i] = 0.0;
-                if (e < nb) {
-                    const uint32_t rk = (uint32_t)(s + e);
-                    while (s_pp[wi + 1] <= rk) ++wi;
-                    const int x = wi * 32 + pk_select32(s_pw[wi], (int)(rk - s_pp[wi]));
-                    cnt[i] = __ldg(row + x);
-                    if (balanced) { wa[i] = __ldg(w + x); wb[i] = __ldg(w + x + d); }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int e = j + 8 * (h * 8 + i);
-                if (e < nb) {
-                    const double v = pk_value(cnt[i], wa[i], wb[i], balanced);
-                    r = (h == 0 && i == 0) ? v : __dadd_rn(r, v);
-                }
-            }
-        }
-        // pairwise combine across the octet (addition is commutative, so the partner order is free)
-        r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
-        r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
-        r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
-        if (m < 8) r = 0.0;                              // numpy: plain loop from 0.0 for short arrays
-        if (j == 0 && m > nb) {                          // the n % 8 tail (all of a short array), one by one
-            int wt = wi_start;
-            for (int e = nb; e < m; ++e) {
-                const uint32_t rk = (uint32_t)(s + e);
-                while (s_pp[wt + 1] <= rk) ++wt;
-                const int x = wt * 32 + pk_select32(s_pw[wt], (int)(rk - s_pp[wt]));
-                const double v = pk_value(__ldg(row + x), balanced ? __ldg(w + x) : 0.0, balanced ? __ldg(w + x + d) : 0.0, balanced);
-                r = __dadd_rn(r, v);
-            }
-        }
-        if (have && j == 0) s_res[l] = r;
+        const double r = pk_leaf_sum8(sc + (have ? sm.seg_s[cur][l] : 0), have ? sm.seg_m[cur][l] : 0, tid & 7);
+        if (have && (tid & 7) == 0) sm.val[0][l] = r;
     }
     __syncthreads();
-    // ---- 4. up the tree: the first leaf of a node's right half adds that half onto the left one ----
-    for (int k = K - 1; k >= 0; --k) {
-        for (int l = tid; l < nl; l += PK_DS_THREADS)
-            if (s_ownk[l] == k) s_res[l - s_ownc[l]] = __dadd_rn(s_res[l - s_ownc[l]], s_res[l]);
-        __syncthreads();
+    // ---- combine back up: left + right wherever a segment was split (warp 0) ----
+    if (wid == 0) {
+        int vc = 0;
+        for (int lv = L - 1; lv >= 0; --lv) {
+            const int ns = sm.nseg[lv];
+            for (int i = lane; i < ns; i += 32) {
+                const uint32_t word = sm.split[lv][i >> 5];
+                const int pos = i + sm.wpre[lv][i >> 5] + __popc(word & ((1u << (i & 31)) - 1u));
+                double v = sm.val[vc][pos];
+                if ((word >> (i & 31)) & 1u) v = __dadd_rn(v, sm.val[vc][pos + 1]);
+                sm.val[vc ^ 1][i] = v;
+            }
+            __syncwarp();
+            vc ^= 1;
+        }
+        if (lane == 0) out_sum[d] = sm.val[vc][0];
     }
-    if (tid == 0) out_sum[d] = nl > 0 ? s_res[0] : 0.0;
 }
 
 // ---------------------------------------------------------------------------
@@ -977,20 +1002,30 @@ int pk_launch_rowptr(pk_chrom* c, const int32_t* b1, const int32_t* b2, int64_t 
     return PK_OK;
 }
 
+template <int CAP>
+static int launch_diag_sums_t(pk_chrom* c) {
+    const size_t smem = sizeof(DiagSmem<CAP>);
+    PK_OPT_IN_SMEM(k_diag_sums<CAP>, smem, c->device);
+    k_diag_sums<CAP><<<c->ND, PK_DS_THREADS, smem, c->stream>>>(c->pitch, c->d_scratch, c->d_diag_sum, c->d_diag_cnt, c->d_flags);
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
 int pk_launch_diag_sums(pk_chrom* c) {
     const int n_words = (c->n + 31) / 32;
     k_valid_bits<<<std::min((n_words + 7) / 8, 148 * 4), 256, 0, c->stream>>>(c->d_valid, c->d_w, c->balanced, c->n, c->d_vbits, n_words,
                                                                 c->d_flags);
     PK_CUDA(cudaGetLastError());
-    const int cap_leaves = c->n / 64 + 8;               // numpy's leaves hold at least 64 elements (one leaf below 129)
-    const size_t smem = ((sizeof(DiagHdr) + 15) & ~(size_t)15) + (size_t)cap_leaves * 8 + ((size_t)n_words + 2) * 4 +
-                        ((size_t)n_words + 1) * 4 + ((size_t)n_words + 2) * 4 + (size_t)cap_leaves * 4 + (size_t)cap_leaves + 16;
-    if (smem > 200 * 1024) { pk_set_error("chromosome of %d bins is too long for the per-diagonal sum tables", c->n); return PK_EUNSUPPORTED; }
-    PK_OPT_IN_SMEM(k_diag_sums, smem, c->device);
-    k_diag_sums<<<c->ND, PK_DS_THREADS, smem, c->stream>>>(c->d_band, c->d_w, c->d_vbits, n_words, c->n, c->pitch, c->balanced,
-                                                          cap_leaves, c->d_diag_sum, c->d_diag_cnt, c->d_flags);
+    const size_t smem_c = ((size_t)n_words + 2) * 4;
+    if (smem_c > 200 * 1024) { pk_set_error("chromosome of %d bins: valid mask does not fit shared memory", c->n); return PK_EUNSUPPORTED; }
+    PK_OPT_IN_SMEM(k_diag_compact, smem_c, c->device);
+    dim3 grid((unsigned)((c->n + PK_DC_SLICE - 1) / PK_DC_SLICE), (unsigned)c->ND);
+    k_diag_compact<<<grid, 256, smem_c, c->stream>>>(c->d_band, c->d_w, c->d_vbits, n_words, c->n, c->pitch, c->balanced,
+                                                    c->d_scratch, c->d_diag_cnt);
     PK_CUDA(cudaGetLastError());
-    return PK_OK;
+    // leaves of numpy's tree hold at least 57 elements
+    if (c->n <= 57 * 1024) return launch_diag_sums_t<1024>(c);
+    return launch_diag_sums_t<4096>(c);
 }
 
 bool pk_fit_on_device_supported(int len) { return len <= PK_FIT_MAX; }
