@@ -17,6 +17,7 @@
 int pk_launch_scatter(pk_chrom* c, const int32_t* b1, const int32_t* b2, const int32_t* cnt, int64_t nnz);
 int pk_launch_band_csr(pk_chrom* c, const long long* rowptr, const void* b2, const void* cnt, int enc);
 int pk_launch_band_rows(pk_chrom* c);
+int pk_launch_band_rowmajor(pk_chrom* c);
 int pk_launch_rowptr(pk_chrom* c, const int32_t* b1, const int32_t* b2, int64_t nnz, long long* rowptr);
 int pk_launch_diag_sums(pk_chrom* c);
 bool pk_fit_on_device_supported(int len);
@@ -26,7 +27,7 @@ int pk_launch_features(pk_chrom* c, double* d_fea64);
 int pk_launch_forest(const pk_forest* f, const float* X, const uint8_t* keep, int64_t n_rows, int32_t* leaves,
                      double* proba, cudaStream_t stream);
 int pk_launch_emit(pk_chrom* c, double thre);
-int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms, int child_features, float* fea_tap);
+int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms, int child_features, int tma, float* fea_tap);
 int pk_launch_sort_records_eager(pk_chrom* c, long long M);
 int pk_launch_depth(pk_chrom* c, int32_t min_dis, unsigned long long* d_total);
 bool pk_fused_supported(int w, int n_trees);
@@ -46,12 +47,16 @@ extern "C" int pk_selftest_divide(int device, int64_t n, uint64_t seed, int64_t*
 static int g_tune_fused = -1;
 static int g_tune_prune = 1;
 static int g_tune_cf = -1;       // fused forest walk on the child-feature node encoding: -1 where measured faster (w = 7), 0 off, 1 on
+// fused kernel fetches windows as TMA boxes from a row-major copy of the band: 1 = where measured faster (w = 7: -8 %;
+// the w = 5 kernel is 6 % slower with it, profiles/r2_summary.md), 2 = always, 0 = never (per-cell gather)
+static int g_tune_tma = 1;
 static int g_tune_reserve = 0;   // SMs the fused kernel leaves to the short stages of other chromosomes (pipelined use)     // retire pixels that cannot exceed min_prob (exact for every emitted record)
 
 extern "C" int pk_set_tuning(const char* key, int value) {
     if (key && !strcmp(key, "fused")) { g_tune_fused = value; return PK_OK; }
     if (key && !strcmp(key, "prune")) { g_tune_prune = value; return PK_OK; }
     if (key && !strcmp(key, "child_features")) { g_tune_cf = value; return PK_OK; }
+    if (key && !strcmp(key, "tma")) { g_tune_tma = value; return PK_OK; }
     if (key && !strcmp(key, "reserve_sms")) { g_tune_reserve = value < 0 ? 0 : value; return PK_OK; }
     pk_set_error("pk_set_tuning: unknown key %s", key ? key : "(null)");
     return PK_EINVAL;
@@ -438,6 +443,36 @@ static int64_t band_pixels_of(const pk_chrom* c) {
     return k * c->n - ((int64_t)c->lower + c->upper) * k / 2;
 }
 
+// Skewed tensor map over the row-major band copy (pk_common.cuh): element (j, i) = band2[j * (P2 - 1) + i], the
+// dense matrix cell (row j, column i). The driver entry point is looked up at run time (no link against libcuda).
+typedef CUresult (*pk_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_band2_map(pk_chrom* c) {
+    static pk_encode_tiled_fn enc = nullptr;
+    if (!enc) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            pk_set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return PK_EUNSUPPORTED;
+        }
+        enc = (pk_encode_tiled_fn)fn;
+    }
+    const int S = c->S, BC = (S + 3 + 3) & ~3;        // box columns: the window plus the slack of a 16-byte aligned start
+    const cuuint64_t dims[2] = {(cuuint64_t)c->n + 8, (cuuint64_t)c->n};
+    const cuuint64_t strides[1] = {(cuuint64_t)(c->P2 - 1) * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)BC, (cuuint32_t)S}, estr[2] = {1, 1};
+    const CUresult r = enc(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, c->d_band2, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { pk_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return PK_ECUDA; }
+    c->tmap_ok = true;
+    return PK_OK;
+}
+
 extern "C" int pk_chrom_create(int device, int32_t n_bins, int32_t width, int32_t lower, int32_t upper, int balanced,
                                void* stream, pk_chrom** out) {
     if (!out) { pk_set_error("pk_chrom_create: out is NULL"); return PK_EINVAL; }
@@ -483,6 +518,16 @@ extern "C" int pk_chrom_create(int device, int32_t n_bins, int32_t width, int32_
     for (auto& e : c->ev) {
         if (cudaEventCreate(&e) != cudaSuccess) { pk_set_error("cudaEventCreate failed"); pk_chrom_destroy(c); return PK_ECUDA; }
     }
+    if ((g_tune_tma == 1 && width == 7) || (g_tune_tma > 1 && (width == 5 || width == 7))) {
+        // row-major band copy + tensor map for the fused kernel's window fetch; without them (an old driver)
+        // the kernel gathers cell by cell
+        c->P2 = ((int64_t)c->ND + 3) / 4 * 4 + 1;
+        if (dev_alloc(&c->d_band2, (size_t)c->n * (size_t)c->P2 + 64) == PK_OK) {
+            if (make_band2_map(c) != PK_OK) dev_free(c->d_band2);
+        } else {
+            cudaGetLastError();
+        }
+    }
     *out = c;
     return PK_OK;
 }
@@ -491,7 +536,7 @@ extern "C" int pk_chrom_destroy(pk_chrom* c) {
     if (!c) return PK_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream); else cudaDeviceSynchronize();
-    dev_free(c->d_band); dev_free(c->d_w); dev_free(c->d_wp); dev_free(c->d_valid); dev_free(c->d_vbits); dev_free(c->d_scratch);
+    dev_free(c->d_band); dev_free(c->d_band2); dev_free(c->d_w); dev_free(c->d_wp); dev_free(c->d_valid); dev_free(c->d_vbits); dev_free(c->d_scratch);
     dev_free(c->d_diag_sum); dev_free(c->d_diag_cnt);
     dev_free(c->d_exp); dev_free(c->d_bg); dev_free(c->d_head);
     c->d_flags = nullptr; c->d_counters = nullptr; c->d_ncand = nullptr; c->d_batch_win = nullptr;
@@ -552,6 +597,8 @@ static int reserve_staging(pk_chrom* c, int64_t nnz, bool need_b1) {
 
 static int after_band(pk_chrom* c) {
     cudaStream_t s = c->stream;
+    c->band2_valid = false;
+    if (c->d_band2 && c->tmap_ok && g_tune_tma) PK_CHECK(pk_launch_band_rowmajor(c));     // while the band is hot in L2
     if (c->timing) PK_CUDA(cudaEventRecord(c->ev[1], s));
     PK_CHECK(pk_launch_diag_sums(c));
     if (c->timing) PK_CUDA(cudaEventRecord(c->ev[2], s));
@@ -1035,7 +1082,7 @@ extern "C" int pk_chrom_fused_features(pk_chrom* c, pk_forest* f, uint8_t* keep,
     PK_CHECK(ensure_feature_buffer(c));
     PK_CUDA(cudaMemsetAsync(c->d_fea32, 0, (size_t)c->n_cand * c->F * sizeof(float), c->stream));
     const int variant = g_tune_fused > 1 ? g_tune_fused - 1 : 0;
-    PK_CHECK(pk_launch_fused(c, f, variant, -1.0, 0, g_tune_cf, c->d_fea32));
+    PK_CHECK(pk_launch_fused(c, f, variant, -1.0, 0, g_tune_cf, g_tune_tma, c->d_fea32));
     if (keep) PK_CUDA(cudaMemcpyAsync(keep, c->d_keep, (size_t)c->n_cand, cudaMemcpyDeviceToHost, c->stream));
     if (fea32) PK_CUDA(cudaMemcpyAsync(fea32, c->d_fea32, (size_t)c->n_cand * c->F * 4, cudaMemcpyDeviceToHost, c->stream));
     PK_CUDA(cudaStreamSynchronize(c->stream));
@@ -1059,12 +1106,12 @@ static int run_score(pk_chrom* c, pk_forest* f, double min_prob) {
             PK_CUDA(cudaEventRecord(c->ev_x, s));
             PK_CUDA(cudaStreamWaitEvent(c->score_stream, c->ev_x, 0));
             c->stream = c->score_stream;
-            r = pk_launch_fused(c, f, variant, thre, g_tune_reserve, g_tune_cf, nullptr);
+            r = pk_launch_fused(c, f, variant, thre, g_tune_reserve, g_tune_cf, g_tune_tma, nullptr);
             c->stream = s;
             PK_CUDA(cudaEventRecord(c->ev_x, c->score_stream));
             PK_CUDA(cudaStreamWaitEvent(s, c->ev_x, 0));
         } else {
-            r = pk_launch_fused(c, f, variant, thre, 0, g_tune_cf, nullptr);
+            r = pk_launch_fused(c, f, variant, thre, 0, g_tune_cf, g_tune_tma, nullptr);
         }
         if (r == PK_EUNSUPPORTED) fused = false;     // shapes the fused kernel has no room for: the two-kernel path below
         else PK_CHECK(r);

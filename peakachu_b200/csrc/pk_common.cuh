@@ -1,5 +1,6 @@
 // Shared declarations of the peakachu_b200 CUDA library (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -98,6 +99,15 @@ struct pk_chrom {
     bool whole = true;
     // device buffers
     int32_t* d_band = nullptr;       // [ND][pitch] raw counts, diagonal-major
+    // Row-major copy of the band for the fused kernel's window fetch: band2[r * P2 + o] = count of pixel (r, r + o),
+    // o < ND - 1 (the trimmed diagonal and the padding columns are zero). P2 = 4k + 1, so that the skewed tensor map
+    // T[j][i] = band2 + j * (P2 - 1) + i (row stride a multiple of 16 bytes) addresses the dense matrix cell
+    // (row j, column i) and a pixel's (2w+1)^2 window is one rectangular TMA box (pk_fused.cu, phase A).
+    int32_t* d_band2 = nullptr;      // [n][P2] (+ padding)
+    int64_t P2 = 0;
+    bool band2_valid = false;        // built from the current pixels
+    alignas(64) CUtensorMap tmap;    // the skewed view, box = (2w+1) rows x (2w+1 + slack) columns
+    bool tmap_ok = false;
     double* d_w = nullptr;           // [n]
     double* d_wp = nullptr;          // [n] weights of the Poisson filter when they differ from d_w (pk_chrom_set_poisson_weights)
     bool use_wp = false;

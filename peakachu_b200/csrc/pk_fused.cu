@@ -24,6 +24,7 @@
 #include "pk_device.cuh"
 
 #include <algorithm>
+#include <cstring>
 
 struct FusedParams {
     const int32_t* band; const double* w; const double* expv;
@@ -39,6 +40,8 @@ struct FusedParams {
     const int32_t* flags;          // handle's device flags
     double thre;                   // --minimum-prob: pixels that can no longer exceed it stop walking trees
     float* fea_tap;                // parity tap (pk_chrom_fused_features): [n_cand][F] copy of the shared-memory feature rows, else NULL
+    const int32_t* band2; long long P2;   // TM kernels: row-major band copy (pk_common.cuh) ...
+    alignas(64) CUtensorMap tmap;         // ... and the skewed tensor map whose boxes are windows
 };
 
 // ---- mbarrier / bulk-copy PTX ------------------------------------------------
@@ -68,7 +71,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-template <int W, int P, int TPP, int TBN, int CH, int NTH, int NGR = 2, int XSTAGE = 0, int CF = 0>
+// one window of the row-major band as a 2-D box (SASS UTMALDG.2D); c0 = first column (a multiple of 4), c1 = first row
+__device__ __forceinline__ void tma_box_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+template <int W, int P, int TPP, int TBN, int CH, int NTH, int NGR = 2, int XSTAGE = 0, int CF = 0, int TM = 0>
 struct FusedCfg {
     static constexpr int S = 2 * W + 1, F = S * S, NT = NTH, NW = NT / 32;      // NTH >= P*TPP: extra warps only build features
     static_assert(NTH >= P * TPP && NTH % 32 == 0, "thread count");
@@ -84,15 +93,34 @@ struct FusedCfg {
     // group's band gather overlaps the other's arithmetic
     static constexpr int NG = NGR, NTG = NT / NG, NWG = NW / NG;
     static_assert(NW % NG == 0, "warps per group");
-    static constexpr int PB_raw = (int)(stage_bytes / NG / ((size_t)F * 8)) & ~1;
+    // TM: a window's band cells arrive as one TMA box of S rows x BC columns (the window plus the slack of a
+    // 16-byte aligned start) in the window's staging slot; behind the box a scratch area holds the lower-left
+    // block for the filters; the float64 window later overwrites both in place.
+    static constexpr int BC = (S + 3 + 3) & ~3;
+    static constexpr int BOX_BYTES = S * BC * 4;
+    static constexpr int SCR_OFF = BOX_BYTES, SCR_BYTES = (W * W + 1) * 8;
+    static constexpr int SLOT_raw = F * 8 > SCR_OFF + SCR_BYTES ? F * 8 : SCR_OFF + SCR_BYTES;
+    // bytes between staged windows. TM: slots are 128-byte aligned (TMA destination), so the same cell of every
+    // window would fall into the same bank; the float64 window and the scratch block are therefore shifted
+    // inside the slot by a few words that depend on the window's index (VOFF / SOFF below)
+    static constexpr int WSTRIDE = TM ? ((SLOT_raw + 127) & ~127) : F * 8;
+    static constexpr int VSLACK = WSTRIDE - F * 8, SSLACK = WSTRIDE - SCR_OFF - SCR_BYTES;
+    static constexpr int VSTEP = !TM ? 0 : (VSLACK / 3 >= 40 ? ((VSLACK / 3) & ~7) : (VSLACK & ~7));
+    static constexpr int VMASK = VSLACK / 3 >= 40 ? 3 : 1;
+    static constexpr int SSTEP = !TM ? 0 : ((SSLACK / 3) & ~7);
+    static constexpr int PB_raw = (int)(stage_bytes / NG / (size_t)WSTRIDE) & ~1;
     static constexpr int PB = PB_raw < P ? PB_raw : P;        // windows staged per take and group (even)
+    static constexpr int NIT = (PB * S + NTG - 1) / NTG;      // TM: window columns per thread and take
+    static constexpr int NIW = (PB + 31) / 32;                // TM: warps of a group that request boxes
+    static_assert(!TM || NIW * 32 <= NTG, "issuing warps");
     static constexpr size_t fea_bytes = (size_t)P * F * 4;
     static_assert(F * 4 >= S * 16, "row extrema do not fit a feature row");
     static constexpr int NPW = (PB / 2 + NWG - 1) / NWG;      // window pairs per warp per take
     static size_t total(int ND, int n_trees) {
         return stage_bytes + fea_bytes + 2 * (size_t)((ND + 1) & ~1) * 8 + (size_t)NG * PB * 4 + 2 * (size_t)F * 8 +
                (size_t)P * 4 + 2 * (size_t)NG * PB * 4 + (size_t)n_trees * 4 + (size_t)((n_trees + 3) & ~3) +
-               2 * (size_t)NG * PB * 2 + (size_t)P + 64 + (CF ? (size_t)((n_trees + 3) & ~3) : 0);
+               2 * (size_t)NG * PB * 2 + (size_t)P + 64 + (CF ? (size_t)((n_trees + 3) & ~3) : 0) +
+               (TM ? (size_t)NG * PB * 6 + 16 : 0);
     }
 };
 
@@ -193,12 +221,12 @@ __device__ __forceinline__ void pk_step_cf(uint32_t xrow_addr, uint32_t& addr, u
 #define PK_TICK(k) do { } while (0)
 #endif
 
-template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH, int NGR, int XSTAGE, int CF>
-__global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm) {
-    using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH, NGR, XSTAGE, CF>;
+template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH, int NGR, int XSTAGE, int CF, int TM>
+__global__ void __launch_bounds__(NTH, OCC) k_score_fused(const __grid_constant__ FusedParams prm) {
+    using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH, NGR, XSTAGE, CF, TM>;
     constexpr int S = Cfg::S, F = Cfg::F, NT = Cfg::NT, NW = Cfg::NW, NS = Cfg::NS, NM = Cfg::NM, CHUNK = Cfg::CHUNK;
-    constexpr int PB = Cfg::PB, NG = Cfg::NG, NTG = Cfg::NTG, NWG = Cfg::NWG;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int PB = Cfg::PB, NG = Cfg::NG, NTG = Cfg::NTG, NWG = Cfg::NWG, WSTRIDE = Cfg::WSTRIDE;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [tree buffers | hand-over]  (= window staging during phase A) | features | exp | 1/exp |
     //         candidate rank | gather order | slot->candidate | window distance |
     //         window nonzeros | tree roots | tree depths | kept windows of a take | nan flags | barriers
@@ -221,6 +249,9 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
     uint8_t* s_nan = reinterpret_cast<uint8_t*>(s_ks + NG * PB);  // [P]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_nan + P) + 15) & ~(uintptr_t)15);
     uint8_t* s_rootfeat = reinterpret_cast<uint8_t*>(s_bar + 4);  // [n_trees] (CF only)
+    int32_t* s_cx = reinterpret_cast<int32_t*>(s_rootfeat + (CF ? ((prm.n_trees + 3) & ~3) : 0));   // [NG][PB] window row (TM only)
+    int16_t* s_slot = reinterpret_cast<int16_t*>(s_cx + NG * PB);  // [NG][PB] feature slot of a kept window, else -1 (TM only)
+    __shared__ uint64_t s_gbar[NG];                               // TM: a group's boxes have landed
     // phase B: leaf hand-over, running sums, list of pixels still walking
     double* s_lv = s_hand;                                        // [2][CH][P] (TPP == 2)
     double* s_acc = s_hand + (TPP == 2 ? 2 * CH * P : 0);         // [P]
@@ -235,6 +266,7 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
     const int grp = tid / NTG, gtid = tid - grp * NTG, gw = gtid >> 5;      // feature-building group
     auto gsync = [&]() {
         if (NG == 1) __syncthreads();
+        else if (NTG == 32) __syncwarp();
         else asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(NTG) : "memory");
     };
     const int G = prm.n_groups;
@@ -271,6 +303,8 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
+        if (TM)
+            for (int g = 0; g < NG; ++g) mbar_init(&s_gbar[g], Cfg::NIW);
         mbar_fence_init();
         s_done = 0;
     }
@@ -291,7 +325,16 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
         }
     };
 
-    const uint32_t V_addr = smem_u32(s_V) + (uint32_t)(grp * PB * F) * 8u;     // this group's staging buffer
+    const uint32_t V_addr = smem_u32(s_V) + (uint32_t)(grp * PB) * (uint32_t)WSTRIDE;     // this group's staging buffer
+    auto win_base = [&](int i) -> uint32_t {     // float64 window of the take's window i
+        return V_addr + (uint32_t)i * (uint32_t)WSTRIDE + (uint32_t)((i & Cfg::VMASK) * Cfg::VSTEP);
+    };
+    auto scr_base = [&](int i) -> uint32_t {     // TM: parked lower-left block + centre of window i
+        return V_addr + (uint32_t)i * (uint32_t)WSTRIDE + (uint32_t)(Cfg::SCR_OFF + ((i >> 2) & 3) * Cfg::SSTEP);
+    };
+    int32_t* g_cx = s_cx + grp * PB;
+    int16_t* g_slot = s_slot + grp * PB;
+    uint32_t gphase = 0;                         // TM: parity of the group's box barrier
     int32_t* g_rank = s_rank + grp * PB;
     int32_t* g_cd = s_cd + grp * PB;
     int32_t* g_nz = s_nz + grp * PB;
@@ -301,7 +344,7 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
 
     bool last = false;
 #ifdef PK_FUSED_CLOCK
-    long long clk[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t0 = clock64();
+    long long clk[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t0 = clock64();
     long long clkq[6] = {0, 0, 0, 0, 0, 0};      // inside a forest chunk (thread 0): setup | walk | hand-over + mbarrier | CTA barrier | refill | accumulate
     long long clkg[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};      // forest phase, per tree group (re-pack time lands in the next group)
 #endif
@@ -337,6 +380,183 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
             const int take = s_gtake[grp];
             const long long start = s_gstart[grp];
             const bool stop = s_gstop[grp] != 0;
+            if constexpr (TM) {
+            // ---- T1 (TM): one lane per window reads its coordinates and requests the window's band cells from the
+            //      TMA unit: rows x-W..x+W, columns from (y-W) & ~3 of the dense-matrix view of the row-major band
+            //      (one cp.async.bulk.tensor.2d per window, SASS UTMALDG.2D), completing on the group's mbarrier.
+            if (gtid < Cfg::NIW * 32) {
+                const int i = gtid;
+                int x = 0, d = 0;
+                bool ok = false;
+                if (i < take) {
+                    x = prm.cx[start + i];
+                    d = prm.cd[start + i];
+                    ok = (x - W >= 0) && (x + d + W + 1 <= prm.n);                         // scoreUtils.py:75
+                    g_rank[i] = __ldg(prm.crank + start + i);
+                    g_cd[i] = d; g_cx[i] = x; g_nz[i] = ok ? 0 : -1; g_slot[i] = -1;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                // the slots were last touched through the generic proxy (previous take, forest phase)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (lane == 0) mbar_expect_tx(&s_gbar[grp], (uint32_t)__popc(m) * (uint32_t)Cfg::BOX_BYTES);
+                __syncwarp();
+                if (ok) tma_box_2d(V_addr + (uint32_t)i * (uint32_t)WSTRIDE, &prm.tmap, (x + d - W) & ~3, x - W, smem_u32(&s_gbar[grp]));
+            }
+            gsync();
+            PK_TICK(8);
+            // ---- A3a (TM): one thread per window column: counts from the box, balanced values into registers,
+            //      non-zeros counted, the lower-left block and the centre parked for the filters
+            double v[Cfg::NIT][S];
+            {
+                bool waited = false;
+#pragma unroll
+                for (int k = 0; k < Cfg::NIT; ++k) {
+                    const int item = gtid + k * NTG;
+                    const int i = item / S, b = item - i * S;
+#pragma unroll
+                    for (int a = 0; a < S; ++a) v[k][a] = 0.0;
+                    const bool have = item < take * S && g_nz[i] >= 0;          // border windows were not requested
+                    int x = 0, d = 0;
+                    double wr[S], wcb = 1.0;
+#pragma unroll
+                    for (int a = 0; a < S; ++a) wr[a] = 1.0;
+                    if (have) {
+                        x = g_cx[i]; d = g_cd[i];
+                        if (prm.balanced) {
+                            wcb = __ldg(prm.w + (x + d - W + b));
+#pragma unroll
+                            for (int a = 0; a < S; ++a) wr[a] = __ldg(prm.w + (x - W + a));
+                        }
+                    }
+                    if (!waited) { PK_TICK(9); mbar_wait(&s_gbar[grp], gphase); waited = true; PK_TICK(10); }
+                    if (have) {
+                        const int y0 = x + d - W;
+                        const uint32_t cell0 = V_addr + (uint32_t)i * (uint32_t)WSTRIDE + (uint32_t)((y0 & 3) + b) * 4u;
+                        int nz = 0;
+                        // weight products w[r] * w[c] of the column; the largest high word (as unsigned) tells whether
+                        // every product is positive, finite and small enough that product * count cannot overflow
+                        double p[S];
+                        unsigned hmax = 0u;
+#pragma unroll
+                        for (int a = 0; a < S; ++a) {
+                            p[a] = __dmul_rn(wr[a], wcb);
+                            hmax = max(hmax, (unsigned)__double2hiint(p[a]));
+                        }
+                        if (hmax < 0x7DF00000u && d + b >= S - 1) {
+                            // common case: (w[r] w[c]) count needs no finiteness test (a zero count gives +0) and every
+                            // cell of the column lies on or above the main diagonal
+#pragma unroll
+                            for (int a = 0; a < S; ++a) {
+                                const double q = __dmul_rn(p[a], (double)(int)lds_u32(cell0 + a * Cfg::BC * 4));     // pk_value
+                                v[k][a] = q;
+                                nz += q != 0.0;
+                            }
+                        } else {
+#pragma unroll
+                            for (int a = 0; a < S; ++a) {
+                                int cnt = (int)lds_u32(cell0 + a * Cfg::BC * 4);
+                                // below the main diagonal (only when d < 2W): the symmetric cell, read directly
+                                if (d + b - a < 0) cnt = __ldg(prm.band2 + ((long long)(y0 + b) * prm.P2 + (a - b - d)));
+                                double q = __dmul_rn(p[a], (double)cnt);                  // pk_value
+                                q = isfinite(q) ? q : 0.0;
+                                if (cnt == 0) q = 0.0;
+                                v[k][a] = q;
+                                nz += q != 0.0;
+                            }
+                        }
+                        atomicAdd(&g_nz[i], nz);
+                        const uint32_t scr = scr_base(i);
+                        if (b < W) {
+#pragma unroll
+                            for (int a = 0; a < W; ++a) sts_f64(scr + (uint32_t)(a * W + b) * 8u, v[k][a]);
+                        }
+                        if (b == W) sts_f64(scr + (uint32_t)(W * W) * 8u, v[k][W]);
+                    }
+                }
+                gphase ^= 1u;
+            }
+            PK_TICK(11);
+            gsync();
+            PK_TICK(1);
+            // ---- A2 (TM): the reference's filters, one thread per window
+            {
+                const int i = lane * NWG + gw;
+                if (i < take) {
+                    const int nz = g_nz[i];
+                    bool ok = nz >= 0 && !((double)nz < (double)F * 0.1);        // utils.py:225
+                    const uint32_t scr = scr_base(i);
+                    if (ok) {
+                        double s = 0.0;                                            // utils.py:228 (numba order)
+#pragma unroll
+                        for (int q = 0; q < W * W; ++q) s = __dadd_rn(s, lds_f64(scr + (uint32_t)q * 8u));
+                        const double ll = __ddiv_rn(s, (double)(W * W));
+                        ok = (ll > 0.0) && (__ddiv_rn(lds_f64(scr + (uint32_t)(W * W) * 8u), ll) > 0.1);  // utils.py:229-232
+                    }
+                    if (ok) {
+                        const int kl = atomicAdd(&s_gnkt[grp], 1);
+                        const int slot = atomicAdd(&s_nkept, 1);
+                        const long long ci = start + i;
+                        g_kl[kl] = (uint16_t)i;
+                        g_ks[kl] = (uint16_t)slot;
+                        g_slot[i] = (int16_t)slot;
+                        s_idx[slot] = (int)ci;
+                        prm.keep[ci] = 1;
+                        atomicAdd(&prm.batch_win[g_rank[i] / PK_BATCH], 1);
+                        s_nan[slot] = 0;
+                    }
+                }
+            }
+            gsync();
+            PK_TICK(2);
+            {
+                const int nkt_ = s_gnkt[grp];
+                if (gtid == 0 && nkt_ < take) atomicSub(&s_reserved, take - nkt_);    // rejected windows free their slots
+            }
+            const bool fastdiv = !s_expbad;
+            // ---- A3b (TM): distance normalisation + vertical Gaussian pass of the kept windows, from the registers,
+            //      written as the float64 window over the box (every box cell was read before the barriers above)
+#pragma unroll
+            for (int k = 0; k < Cfg::NIT; ++k) {
+                const int item = gtid + k * NTG;
+                const int i = item / S, b = item - i * S;
+                if (item >= take * S || g_slot[i] < 0) continue;
+                const int d = g_cd[i];
+                const uint32_t col_addr = win_base(i) + (uint32_t)b * 8u;     // V[a][b] = col_addr + a*S*8
+                double u[S], g[S];
+                // utils.py:187-200: V[a][b] / exp[|d + b - a|]
+                if (fastdiv && d + b >= S - 1) {
+                    const uint32_t e0 = exp_addr + (uint32_t)(d + b) * 8u, r0 = rexp_addr + (uint32_t)(d + b) * 8u;
+#pragma unroll
+                    for (int a = 0; a < S; ++a) u[a] = pk_div_r(v[k][a], lds_f64(e0 - a * 8), lds_f64(r0 - a * 8));
+                } else if (fastdiv) {
+#pragma unroll
+                    for (int a = 0; a < S; ++a) {
+                        int dd = d + b - a;
+                        dd = dd < 0 ? -dd : dd;
+                        u[a] = pk_div_r(v[k][a], lds_f64(exp_addr + dd * 8), lds_f64(rexp_addr + dd * 8));
+                    }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < S; ++a) {
+                        int dd = d + b - a;
+                        dd = dd < 0 ? -dd : dd;
+                        u[a] = __ddiv_rn(v[k][a], lds_f64(exp_addr + dd * 8));
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < S; ++a) {
+                    double t = __dmul_rn(u[a], PK_GK[4]);
+#pragma unroll
+                    for (int jj = 4; jj >= 1; --jj)
+                        t = __dadd_rn(t, __dmul_rn(__dadd_rn(u[pk_reflect(a - jj, S)], u[pk_reflect(a + jj, S)]), PK_GK[4 - jj]));
+                    g[a] = t;
+                }
+#pragma unroll
+                for (int a = 0; a < S; ++a) sts_f64(col_addr + a * S * 8, g[a]);
+            }
+            gsync();
+            PK_TICK(3);
+            } else {
             // ---- A1: gather + balance. A warp owns NPW window pairs of the take; all 32 lanes share the
             //      2*F cells of a pair. Every band load of the take is issued before the first is used.
             {
@@ -353,7 +573,7 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                     }
                 }
 #ifdef PK_FUSED_CLOCK
-                if (__shfl_sync(0xffffffffu, myx, 0) == -12345) clk[11] = 1;
+                if (__shfl_sync(0xffffffffu, myx, 0) == -12345) clk[12] = 1;
                 PK_TICK(8);
 #endif
                 // this lane's cells of a pair (the same for every pair)
@@ -518,11 +738,13 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
             }
             gsync();
             PK_TICK(3);
+            }
+            const int nkt = s_gnkt[grp];
             // ---- A4: horizontal pass, one thread per window row, in place
             for (int item = gtid; item < nkt * S; item += NTG) {
                 const int kl = item / S, a = item - kl * S;
                 const int i = g_kl[kl];
-                const uint32_t row_addr = V_addr + (uint32_t)(i * F + a * S) * 8u;
+                const uint32_t row_addr = win_base(i) + (uint32_t)(a * S) * 8u;
                 double t[S];
 #pragma unroll
                 for (int b = 0; b < S; ++b) t[b] = lds_f64(row_addr + b * 8);
@@ -564,7 +786,7 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
                     const int kl = kl0 + u * NWG;
                     have[u] = kl < nkt;
                     const int klc = have[u] ? kl : kl0;
-                    win[u] = V_addr + (uint32_t)(g_kl[klc] * F) * 8u + (uint32_t)lane * 8u;
+                    win[u] = win_base(g_kl[klc]) + (uint32_t)lane * 8u;
                     slot[u] = g_ks[klc];
                     frow[u] = fea_addr + (uint32_t)(slot[u] * F) * 4u;
                     klo[u][0] = 0xffffffffu; khi[u][0] = 0xffffffffu; klo[u][1] = 0u; khi[u][1] = 0u;
@@ -802,7 +1024,7 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
     }
 #ifdef PK_FUSED_CLOCK
     if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) {
-        printf("cta %d A1 detail: coords %lld issue %lld process %lld\n", blockIdx.x, clk[8], clk[9], clk[10]);
+        printf("cta %d A1 detail: coords %lld issue %lld process %lld (TM: request %lld weights %lld wait %lld columns %lld)\n", blockIdx.x, clk[8], clk[9], clk[10], clk[8], clk[9], clk[10], clk[11]);
         printf("cta %d forest cycles per tree group: %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", blockIdx.x, clkg[0], clkg[1],
                clkg[2], clkg[3], clkg[4], clkg[5], clkg[6], clkg[7], clkg[8], clkg[9], clkg[10], clkg[11], clkg[12], clkg[13], clkg[14], clkg[15]);
         printf("cta %d forest chunk (thread 0): setup %lld walk %lld handover+mbar %lld barrier %lld refill %lld accumulate %lld\n", blockIdx.x, clkq[0], clkq[1], clkq[2], clkq[3], clkq[4], clkq[5]);
@@ -813,24 +1035,30 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const FusedParams prm)
     // every issued group has been waited for (issued == consumed after a batch): nothing to drain
 }
 
-template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH = P * TPP, int NGR = 2, int XSTAGE = 0, int CF = 0>
-static int launch_fused_t(FusedParams prm, pk_forest* f, int ND, int sm_count, cudaStream_t stream) {
-    using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH, NGR, XSTAGE, CF>;
+template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH = P * TPP, int NGR = 2, int XSTAGE = 0, int CF = 0, int TM = 0>
+static int launch_fused_t(const FusedParams& prm_in, pk_forest* f, int ND, int sm_count, cudaStream_t stream) {
+    using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH, NGR, XSTAGE, CF, TM>;
+    FusedParams prm = prm_in;
     prm.nodes = CF ? f->d_nodes_f1 : f->d_nodes_f0;
     prm.rootfeat = f->d_rootfeat;
     prm.nodes_classic = f->d_nodes;
     PK_CHECK(pk_forest_groups(f, TBN, Cfg::CHUNK, &prm.groups, &prm.n_groups));
     const size_t smem = Cfg::total(ND, prm.n_trees);
     if (OCC * (smem + 1024) > 228 * 1024) { pk_set_error("fused kernel: %zu bytes of shared memory needed (x%d per SM)", smem, OCC); return PK_EUNSUPPORTED; }
-    PK_OPT_IN_SMEM((k_score_fused<W, P, TPP, TBN, CH, OCC, NTH, NGR, XSTAGE, CF>), smem, f->device);
+    PK_OPT_IN_SMEM((k_score_fused<W, P, TPP, TBN, CH, OCC, NTH, NGR, XSTAGE, CF, TM>), smem, f->device);
     unsigned grid = (unsigned)(sm_count * OCC);        // persistent: CTAs without work exit at once
-    k_score_fused<W, P, TPP, TBN, CH, OCC, NTH, NGR, XSTAGE, CF><<<grid, NTH, smem, stream>>>(prm);
+    k_score_fused<W, P, TPP, TBN, CH, OCC, NTH, NGR, XSTAGE, CF, TM><<<grid, NTH, smem, stream>>>(prm);
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
 
-int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms, int child_features, float* fea_tap) {
+int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int reserve_sms, int child_features, int tma, float* fea_tap) {
     FusedParams prm;
+    // windows as TMA boxes of the row-major band copy (default variants only)
+    const bool tm = tma && (variant == 0 || variant >= 5) && c->d_band2 && c->band2_valid && c->tmap_ok;
+    if (variant >= 5 && variant != 11 && !tm) { pk_set_error("fused variant %d needs the row-major band copy (tuning 'tma')", variant); return PK_EUNSUPPORTED; }
+    prm.band2 = c->d_band2; prm.P2 = c->P2;
+    if (tm) prm.tmap = c->tmap; else memset(&prm.tmap, 0, sizeof prm.tmap);
     prm.fea_tap = fea_tap;
     prm.band = c->d_band; prm.w = c->d_w; prm.expv = c->d_exp;
     prm.n = c->n; prm.pitch = c->pitch; prm.balanced = c->balanced; prm.ND = c->ND;
@@ -865,16 +1093,33 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int res
         case 2: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 1>(prm, f, c->ND, sm, st);
         case 3: return launch_fused_t<5, 128, 2, 2112, 2, 2, 256, 2>(prm, f, c->ND, sm, st);      // two CTAs per SM: their phases drift apart and overlap
         case 4: return launch_fused_t<5, 128, 2, 2112, 4, 2, 256, 2>(prm, f, c->ND, sm, st);
-        default: return cf ? launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4, 0, 1>(prm, f, c->ND, sm, st)
-                           : launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4>(prm, f, c->ND, sm, st);
+        case 5: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 8, 0, 0, 1>(prm, f, c->ND, sm, st);      // TMA windows, 8 groups of 2 warps
+        case 6: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 2, 0, 0, 1>(prm, f, c->ND, sm, st);      // TMA windows, 2 groups of 8 warps
+        case 7: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 16, 0, 0, 1>(prm, f, c->ND, sm, st);     // TMA windows, a warp per group
+        default:
+            if (tm) return cf ? launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4, 0, 1, 1>(prm, f, c->ND, sm, st)
+                              : launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4, 0, 0, 1>(prm, f, c->ND, sm, st);
+            return cf ? launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4, 0, 1>(prm, f, c->ND, sm, st)
+                      : launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4>(prm, f, c->ND, sm, st);
         }
     }
     if (c->w == 7) {
         switch (variant) {
         case 1: return launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 2, 32768>(prm, f, c->ND, sm, st);
         case 2: return launch_fused_t<7, 128, 2, 3200, 2, 1, 512, 2, 32768>(prm, f, c->ND, sm, st);
-        default: return cf ? launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 1, 32768, 1>(prm, f, c->ND, sm, st)
-                           : launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 1, 32768>(prm, f, c->ND, sm, st);
+        case 5: return launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 2, 32768, 1, 1>(prm, f, c->ND, sm, st);  // TMA windows, 2 groups of 6 warps
+        case 6: return launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 3, 32768, 1, 1>(prm, f, c->ND, sm, st);  // TMA windows, 3 groups of 4 warps
+        case 7: return launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 6, 32768, 1, 1>(prm, f, c->ND, sm, st);  // TMA windows, 6 groups of 2 warps
+        // eight trees per forest round (four chains per thread, buffers of 6400 nodes) on batches of 112 pixels
+        case 8: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 1, 0, 1, 1>(prm, f, c->ND, sm, st);
+        case 9: return launch_fused_t<7, 112, 2, 6400, 4, 1, 320, 1, 0, 1, 1>(prm, f, c->ND, sm, st);
+        case 10: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 1, 0, 0, 1>(prm, f, c->ND, sm, st);
+        case 11: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 1, 0, 1, 0>(prm, f, c->ND, sm, st);
+        default:
+            if (tm) return cf ? launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 1, 32768, 1, 1>(prm, f, c->ND, sm, st)
+                              : launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 1, 32768, 0, 1>(prm, f, c->ND, sm, st);
+            return cf ? launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 1, 32768, 1>(prm, f, c->ND, sm, st)
+                      : launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 1, 32768>(prm, f, c->ND, sm, st);
         }
     }
     return PK_EUNSUPPORTED;

@@ -184,6 +184,38 @@ __global__ void __launch_bounds__(256) k_band_rows(
     pk_tile_writeout(s_tile, TP, R, band, pitch, x0, n, ND, lane, wib);
 }
 
+// ---------------------------------------------------------------------------
+// S1''  row-major copy of the band (pk_chrom.d_band2) for the fused kernel's TMA window fetch: a tiled
+//       transpose band[o][r] -> band2[r][o], 32 x 32 cells per CTA step, coalesced on both sides (the band
+//       was just written and sits in L2). Columns o >= ND - 1 (the trimmed diagonal, padding) are zeroed.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_band_rowmajor(const int32_t* __restrict__ band, long long pitch, int n, int ND,
+                                                       int32_t* __restrict__ band2, int P2) {
+    __shared__ int32_t t[32][33];
+    const int r0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int o0 = 0; o0 < P2; o0 += 32) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int o = o0 + ty + 8 * k, r = r0 + tx;
+            t[ty + 8 * k][tx] = (o < ND - 1 && r < n) ? band[(long long)o * pitch + r] : 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = r0 + ty + 8 * k, o = o0 + tx;
+            if (r < n && o < P2) band2[(long long)r * P2 + o] = t[tx][ty + 8 * k];
+        }
+        __syncthreads();
+    }
+}
+
+int pk_launch_band_rowmajor(pk_chrom* c) {
+    k_band_rowmajor<<<(unsigned)((c->n + 31) / 32), 256, 0, c->stream>>>(c->d_band, c->pitch, c->n, c->ND, c->d_band2, (int)c->P2);
+    PK_CUDA(cudaGetLastError());
+    c->band2_valid = true;
+    return PK_OK;
+}
+
 // escaped counts (>= 255) of the packed rows: a few per row at most, written after the tiles
 __global__ void __launch_bounds__(256) k_band_escapes(const PkRowsView v, const double* __restrict__ w, int n, int ND,
                                                       long long pitch, int balanced, int32_t* __restrict__ band,

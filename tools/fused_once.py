@@ -7,9 +7,11 @@ from peakachu_b200.forest import FlatForest
 from peakachu_b200.scoreUtils import Chromosome
 
 which = sys.argv[1] if len(sys.argv) > 1 else "c2"
+from peakachu_b200 import _lib
 if len(sys.argv) > 2:
-    from peakachu_b200 import _lib
     _lib.check(_lib.lib().pk_set_tuning(b"fused", int(sys.argv[2])))
+if len(sys.argv) > 3:
+    _lib.check(_lib.lib().pk_set_tuning(b"tma", int(sys.argv[3])))
 if which == "c2":
     n, w, lower, upper, forest = 24900, 5, 6, 300, "bench_data/c2_forest.npz"
 else:

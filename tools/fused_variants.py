@@ -17,11 +17,13 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--variants", default="-1,2,3,4,5")
     ap.add_argument("--reps", type=int, default=7)
+    ap.add_argument("--tma", type=int, default=2, help="pk_set_tuning('tma'): windows fetched as TMA boxes (default variant only)")
     args = ap.parse_args()
     from peakachu_b200 import _lib
     from peakachu_b200.forest import FlatForest
     from peakachu_b200.scoreUtils import Chromosome, DeviceForest
     L = _lib.lib()
+    _lib.check(L.pk_set_tuning(b"tma", args.tma))
     wl = bench.WORKLOADS[args.workload]
     flat = FlatForest.load(os.path.join(ROOT, "bench_data", wl["forest"] + "_forest.npz"))
     forest = DeviceForest.of(flat, 0)
@@ -35,11 +37,12 @@ def main():
         ts = []
         for _ in range(args.reps):
             rec = X.score_records(0.5)
-            ts.append(X.stage_ms()["features"])
+            st = X.stage_ms()
+            ts.append(st["features"])
         if ref is None:
             ref = rec
         same = all(np.array_equal(a, b) for a, b in zip(ref, rec))
-        print("fused=%d: %.1f us (min %.1f), records %d, identical %s" % (v, 1e3 * float(np.median(ts)), 1e3 * min(ts), rec[0].size, same))
+        print("tma=%d fused=%d: %.1f us (min %.1f), records %d, identical %s" % (args.tma, v, 1e3 * float(np.median(ts)), 1e3 * min(ts), rec[0].size, same), "band_build %.1f us" % (1e3 * st["band_build"]))
     _lib.check(L.pk_set_tuning(b"fused", -1))
     X.close()
 
