@@ -340,6 +340,61 @@ def run_genome(args, name, flat, rank, world, local, steps, encodings):
 
 
 # ---------------------------------------------------------------------------
+# file -> bedpe: the CLI's own call (score_chromosome.main) on a map file of the workload's chromosome
+# ---------------------------------------------------------------------------
+def run_file_e2e(wl, ch, local, reps=3):
+    """Wall time of `peakachu_b200 score_chromosome -p FILE -C chr1 -m MODEL -O out.bedpe` for the workload's
+    chromosome stored (a) as an HDF5 cooler file, chunked + gzip + shuffle like cooler writes them, read by the
+    built-in h5mini reader, and (b) as the repo's .pkcool container (packed pixel rows). The model is the
+    workload's .pkl (joblib); the bedpe is written to local disk. Best of `reps` runs after one warm-up."""
+    import argparse
+    import contextlib
+    import io
+    import tempfile
+
+    from peakachu_b200 import coolio, score_chromosome
+    from tests import h5write                      # the HDF5 writer of the test fixtures (bench input only)
+    tmp = tempfile.mkdtemp(prefix="pk_file_e2e_")
+    px = band_pixels(ch.n, wl["lower"], wl["upper"], wl["w"])
+    paths = {"cool": os.path.join(tmp, "wl.cool"), "pkcool": os.path.join(tmp, "wl.pkcool")}
+    t0 = time.perf_counter()
+    h5write.write_cool(paths["cool"], [ch], wl["res"])
+    t_write = time.perf_counter() - t0
+    coolio.PKCool.write(paths["pkcool"], [ch], wl["res"])
+    out = {}
+    for kind, path in paths.items():
+        ns = argparse.Namespace(path=path, model=os.path.join(ROOT, "bench_data", wl["forest"] + ".pkl"), output=os.path.join(tmp, kind + ".bedpe"),
+                                resolution=wl["res"], lower=wl["lower"], upper=wl["upper"], minimum_prob=0.5,
+                                clr_weight_name="weight", chrom=ch.name, device=local)
+        best, read_best = None, None
+        for r in range(reps + 1):
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                score_chromosome.main(ns)
+            dt = time.perf_counter() - t0
+            # the reader's share: open the file and pull the chromosome's columns the way from_map does
+            t1 = time.perf_counter()
+            Lib = coolio.open_map(path)
+            n = Lib.nbins(ch.name)
+            from peakachu_b200 import shard
+            shard._unit_columns(Lib, ch.name, min(wl["upper"], n - 2 * wl["w"]) + 2 * wl["w"] + 1, None)
+            shard.map_weights(Lib, ch.name, "weight")
+            dr = time.perf_counter() - t1
+            if r > 0:
+                best = dt if best is None else min(best, dt)
+                read_best = dr if read_best is None else min(read_best, dr)
+        out[kind] = {"ms": 1e3 * best, "pixels_per_s": px / best, "read_ms": 1e3 * read_best,
+                     "file_bytes": os.path.getsize(path), "records": sum(1 for _ in open(ns.output))}
+    out["note"] = ("score_chromosome.main(args) from the file path to the bedpe on disk: model load (joblib .pkl -> node tables), "
+                   "file read (read_ms: open + the chromosome's pixel columns + weights, measured separately), upload, kernels, "
+                   "record fetch, bedpe text. The .cool is written by tests/h5write.py (%.1f s, not timed) with cooler's layout: "
+                   "chunked, gzip-6 + shuffle." % t_write)
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
+# ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
 METRIC = "candidate pixels scored/sec (window features + RF proba)"
@@ -358,6 +413,7 @@ def main():
     ap.add_argument("--genome", default="auto", help="score_genome blocks in the JSON line: auto (c3 at every N, c4 too at N = 8), "
                                                      "none, or a comma list of c3,c4")
     ap.add_argument("--genome-steps", type=int, default=0, help="timed passes of a genome block (0: min(steps, 10))")
+    ap.add_argument("--no-file-e2e", action="store_true", help="skip the file -> bedpe block (N = 1, about 40 s of host work)")
     ap.add_argument("--numa", type=int, default=1, help="N > 1: run each rank on the NUMA node of its GPU (0: leave the affinity alone)")
     ap.add_argument("--fused", type=int, default=-1, help="pk_set_tuning('fused'): -1 auto, 0 off, 1, 2")
     ap.add_argument("--prune", type=int, default=1, help="pk_set_tuning('prune'): retire pixels that cannot exceed min_prob")
@@ -544,8 +600,8 @@ def main():
     dom_ms = stage[dom]
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(dom, {}).get("dram_bytes")
-    except OSError:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.workload, {}).get(dom, {}).get("dram_bytes")
+    except (OSError, ValueError):
         pass
     kernel_names = {"features": "k_score_fused (window features + forest, fused)", "forest": "k_forest",
                     "band_build": "k_band_csr", "diag_sums": "k_diag_sums", "expected_fit": "k_fit_expected",
@@ -594,6 +650,8 @@ def main():
     for enc in encs[1:]:
         line["e2e_%s_columns" % ("uint16" if enc == "csr16" else "int32")] = e2e_block(enc)
     line["genome"] = genome
+    if world == 1 and not args.no_file_e2e and args.workload != "c4":
+        line["e2e_file"] = run_file_e2e(wl, ch, local)
     line["gpu_launches"] = KERNELS_PER_STEP * steps
     line["clocks"] = clocks
     print(json.dumps(line))

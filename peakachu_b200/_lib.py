@@ -142,3 +142,52 @@ def ptr(a, typ=None):
 
 def as_c(a, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+# ---------------------------------------------------------------------------
+# The expected-curve fit on the device (k_fit_expected) restates, operation for operation, what the
+# reference gets from its environment: scipy.optimize.isotonic_regression's PAVA, scikit-learn's
+# IsotonicRegression knot trimming and numpy.interp (utils.py:173-176). That arithmetic is pinned to the
+# versions the golden fixtures were made with; other versions of those packages may round differently.
+# ---------------------------------------------------------------------------
+PINNED_VERSIONS = {"sklearn": "1.9", "scipy": "1.18", "numpy": "2.3"}
+_expected_mode = None
+
+
+def _major_minor(v):
+    return ".".join(str(v).split(".")[:2])
+
+
+def installed_versions():
+    out = {}
+    for mod in PINNED_VERSIONS:
+        try:
+            out[mod] = _major_minor(__import__(mod).__version__)
+        except Exception:
+            out[mod] = None
+    return out
+
+
+def expected_mode():
+    """Where the expected curve is fitted: "device" (the library's own fit) or "host" (the installed
+    scikit-learn, handed over with pk_chrom_set_expected). PEAKACHU_B200_EXPECTED = device | host | auto;
+    auto (the default) takes the device and warns once when the environment's scikit-learn / scipy / numpy
+    are not the versions the device arithmetic is pinned to."""
+    global _expected_mode
+    if _expected_mode is None:
+        want = os.environ.get("PEAKACHU_B200_EXPECTED", "auto").lower()
+        if want not in ("auto", "device", "host"):
+            raise ValueError("PEAKACHU_B200_EXPECTED must be auto, device or host")
+        if want == "auto":
+            have = installed_versions()
+            off = {m: v for m, v in have.items() if v is not None and v != PINNED_VERSIONS[m]}
+            if off:
+                import warnings
+                warnings.warn("peakachu_b200 fits the expected curve on the GPU with the arithmetic of %s; this environment has %s, "
+                              "whose IsotonicRegression may round the last bits differently. Set PEAKACHU_B200_EXPECTED=host to fit "
+                              "the curve with the installed scikit-learn instead (slower: one host round trip per chromosome)."
+                              % (", ".join("%s %s" % kv for kv in PINNED_VERSIONS.items()),
+                                 ", ".join("%s %s" % kv for kv in off.items())), RuntimeWarning, stacklevel=2)
+            want = "device"
+        _expected_mode = want
+    return _expected_mode

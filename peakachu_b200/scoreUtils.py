@@ -83,14 +83,35 @@ def _upper_pixels_from_csr(raw_M):
     return up.row.astype(np.int32), up.col.astype(np.int32), icnt
 
 
+def _check_balanced_matrix(M, b1, b2, cnt, weights, sample=4096):
+    """The device recomputes balanced values as ``(w[row] * w[col]) * count``; a caller whose ``M`` was balanced
+    some other way (another weight column, a divisive one, a scaled matrix) would silently get different
+    numbers. Compare a sample of ``M``'s stored pixels with that product and refuse a mismatch."""
+    if b1.size == 0:
+        return
+    pick = np.unique(np.linspace(0, b1.size - 1, num=min(sample, b1.size)).astype(np.int64))
+    r, c = b1[pick], b2[pick]
+    have = np.asarray(M[r, c]).ravel().astype(np.float64)
+    with np.errstate(invalid="ignore", over="ignore"):
+        want = (weights[r] * weights[c]) * cnt[pick].astype(np.float64)
+    same = (have == want) | (~np.isfinite(want) & (~np.isfinite(have) | (have == 0)))     # NaN pixels may be stored or dropped
+    if not np.all(same):
+        k = int(np.flatnonzero(~same)[0])
+        raise ValueError("Chromosome: M[%d, %d] = %r but (weights[%d] * weights[%d]) * raw_M[%d, %d] = %r; the CUDA path "
+                         "balances raw_M with `weights` itself, so M must be that product (cooler's balance=<the same "
+                         "column>). Pass the weights that made M, or use weights=None with raw counts."
+                         % (r[k], c[k], have[k], r[k], c[k], r[k], c[k], want[k]))
+
+
 class Chromosome:
     """Drop-in for ``peakachu.scoreUtils.Chromosome`` (scoreUtils.py:9-38).
 
     Reference call sites: score_chromosome.py:45-48,51-54 and score_genome.py:58-61,64-67.
     ``M`` / ``raw_M`` are scipy CSR matrices as there; in balanced mode the balanced
     values are recomputed on the device from ``raw_M`` and ``weights`` as
-    ``(w[row] * w[col]) * count`` (what ``cooler`` yields), so ``M`` is only
-    consulted for its shape. Use :meth:`from_pixels` to skip building matrices.
+    ``(w[row] * w[col]) * count`` (what ``cooler`` yields); ``M`` gives the shape and is
+    checked against that product on a sample of pixels (a differently balanced ``M`` is
+    refused rather than silently ignored). Use :meth:`from_pixels` to skip building matrices.
     """
 
     def __init__(self, M, model, raw_M=None, weights=None, lower=6, upper=300,
@@ -102,6 +123,8 @@ class Chromosome:
                 "weights=None with M is not raw_M is the reference's .hic (KR/NONE via straw) branch, "
                 "which is outside this path")
         b1, b2, cnt = _upper_pixels_from_csr(raw_M)
+        if weights is not None and M is not raw_M:
+            _check_balanced_matrix(M, b1, b2, cnt, np.asarray(weights, dtype=np.float64))
         self._init(b1, b2, cnt, weights, int(M.shape[0]), model, lower, upper, cname, res, width, device, stream,
                    sorted_pixels=None)
 
@@ -154,14 +177,14 @@ class Chromosome:
 
     @classmethod
     def from_map(cls, Lib, key, weights, model, lower=6, upper=300, cname="chrm", res=10000, width=5, device=0,
-                 encoding=None):
+                 encoding=None, first_tile=None):
         """Build from an opened map (``coolio.open_map``), taking the chromosome's pixels in the most
         compact column format the reader offers: packed rows, uint16 columns, cooler's CSR columns."""
         from . import shard
         n = Lib.nbins(key)
         nd_need = min(upper, n - 2 * width) + 2 * width + 1
         enc, a, b, c, _ = shard._unit_columns(Lib, key, nd_need, encoding)
-        kw = dict(lower=lower, upper=upper, cname=cname, res=res, width=width, device=device)
+        kw = dict(lower=lower, upper=upper, cname=cname, res=res, width=width, device=device, first_tile=first_tile)
         if enc == _lib.PK_ENC_ROWS:
             return cls.from_rows(a, weights, n, model, **kw)
         if enc == _lib.PK_ENC_CSR16:
@@ -233,8 +256,27 @@ class Chromosome:
         _lib.check(L.pk_chrom_find_candidates(self._h, 0, self.n, None))
         self._ncand = self._cand = None
 
+    def _fit_expected_host(self, L):
+        """PEAKACHU_B200_EXPECTED=host: the reference's own fit (utils.py:159-176) with the installed
+        scikit-learn on the per-distance means the device computed, handed back with pk_chrom_set_expected."""
+        from sklearn.isotonic import IsotonicRegression
+        s = np.zeros(self._exp_len, dtype=np.float64)
+        cnt = np.zeros(self._exp_len, dtype=np.int64)
+        _lib.check(L.pk_chrom_diag_sums(self._h, _lib.ptr(s, _lib.c_f64p), _lib.ptr(cnt, _lib.c_i64p)))
+        exp = np.zeros(self._exp_len)
+        big = cnt > 10
+        exp[big] = s[big] / cnt[big]
+        d = np.where(exp > 0)[0]
+        IR = IsotonicRegression(increasing=False, out_of_bounds="clip")
+        IR.fit(d, exp[d])
+        exp = np.ascontiguousarray(IR.predict(list(range(self._exp_len))), dtype=np.float64)
+        _lib.check(L.pk_chrom_set_expected(self._h, _lib.ptr(exp, _lib.c_f64p), _lib.ptr(exp, _lib.c_f64p)))
+
     def _after_upload(self, L, first_tile, n):
-        _lib.check(L.pk_chrom_fit_expected(self._h))
+        if _lib.expected_mode() == "host":
+            self._fit_expected_host(L)
+        else:
+            _lib.check(L.pk_chrom_fit_expected(self._h))
         self._exp = None
         # asynchronous: the candidate count is read back only when somebody asks for it
         ra, rb = first_tile if first_tile is not None else (0, n)     # band row tile (multi-GPU seam)
@@ -318,8 +360,10 @@ class Chromosome:
         return keep.astype(bool), f32
 
     # -- scoring (scoreUtils.py:95-125) -----------------------------------------------
-    def score_records(self, thre=0.5):
-        """(x, y, prob, value) numpy arrays sorted by (x, y)."""
+    def score_records(self, thre=0.5, with_batches=False):
+        """(x, y, prob, value) numpy arrays sorted by (x, y); ``with_batches`` adds the records' reference
+        batch ids and the surviving windows per batch (the row-tile seam: scoreUtils.py:104-108 is applied
+        by the caller on the sums over the tiles)."""
         L = _lib.lib()
         if self._forest is None:
             self._forest = DeviceForest.of(self.model, self.device)
@@ -331,9 +375,15 @@ class Chromosome:
         self._ncand = ncand.value
         x, y = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
         p, v = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.float64)
-        _lib.check(L.pk_chrom_fetch_results(self._h, _lib.ptr(x), _lib.ptr(y), _lib.ptr(p), _lib.ptr(v), None,
+        b = np.empty(n, dtype=np.int32) if with_batches else None
+        _lib.check(L.pk_chrom_fetch_results(self._h, _lib.ptr(x), _lib.ptr(y), _lib.ptr(p), _lib.ptr(v), _lib.ptr(b),
                                             n, _lib.PK_MEM_HOST))
-        return x, y, p, v
+        if not with_batches:
+            return x, y, p, v
+        nb = C.c_int64()
+        bw = np.zeros(max(1, self._ncand // 100000 + 2), dtype=np.int64)
+        _lib.check(L.pk_chrom_batch_windows(self._h, _lib.ptr(bw, _lib.c_i64p), bw.size, C.byref(nb)))
+        return x, y, p, v, b, bw[:nb.value]
 
     def score(self, thre=0.5):
         from scipy import sparse

@@ -475,6 +475,8 @@ def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_pro
     from .scoreUtils import DeviceForest
     _lib.require_device()
     forest = DeviceForest.of(flat, device)
+    if _lib.expected_mode() == "host":
+        return _score_units_host_fit(Lib, units, forest, correct, lower, upper, res, device, min_prob, encoding)
     eng = Engine.of(forest, lower, upper, device, depth)
     w = forest.width
     keys = []
@@ -495,6 +497,26 @@ def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_pro
     out = {}
     for key, r in zip(keys, results):
         out.setdefault(key, []).append(r)
+    return out
+
+
+def _score_units_host_fit(Lib, units, forest, correct, lower, upper, res, device, min_prob, encoding):
+    """PEAKACHU_B200_EXPECTED=host: the engine fits the expected curve on the device, so in this mode the units
+    go one at a time through ``scoreUtils.Chromosome`` (which then fits with the installed scikit-learn)."""
+    from .scoreUtils import Chromosome
+    out = {}
+    for key, a, b in units:
+        n = Lib.nbins(key)
+        weights, pweights = map_weights(Lib, key, correct)
+        X = Chromosome.from_map(Lib, key, weights, forest, lower=lower, upper=upper, cname=key, res=res,
+                                width=forest.width, device=device, encoding=encoding, first_tile=(a, b))
+        if pweights is not None:
+            X.set_poisson_weights(pweights)
+        x, y, p, v, batch, bw = X.score_records(min_prob, with_batches=True)
+        whole = a == 0 and b == n
+        out.setdefault(key, []).append(dict(tag=len(out), row_begin=a, whole=whole, x=x, y=y, p=p, v=v, batch=batch,
+                                            batch_windows=bw, n_candidates=int(X.n_candidates), n_windows=int(X.n_windows)))
+        X.close()
     return out
 
 

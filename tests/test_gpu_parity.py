@@ -165,6 +165,61 @@ def test_bedpe_identical_to_reference(name, fused, tuning, tmp_path):
             assert rows[(f[0], f[1], f[4])] == f[6:8]
 
 
+@pytest.mark.parametrize("name", ["tiny", "tiny_raw", "genome", "gnames"])
+def test_expected_fit_on_the_host(name, tmp_path, monkeypatch):
+    """PEAKACHU_B200_EXPECTED=host: the curve comes from the installed scikit-learn (the reference's own
+    calls, utils.py:173-176) on the device's per-distance means and goes back with pk_chrom_set_expected;
+    score_genome then runs its units through scoreUtils.Chromosome instead of the engine. With the pinned
+    versions installed both modes give the reference's bedpe."""
+    from peakachu_b200 import _lib, score_chromosome, score_genome
+    monkeypatch.setenv("PEAKACHU_B200_EXPECTED", "host")
+    monkeypatch.setattr(_lib, "_expected_mode", None)
+    assert _lib.expected_mode() == "host"
+    case = Case(name)
+    cfg = case.cfg
+    cool = case.write_cool(tmp_path)
+    out = os.path.join(str(tmp_path), "gpu.bedpe")
+    ns = argparse.Namespace(path=cool, model=case.pkl, output=out, resolution=cfg["res"], lower=cfg["lower"],
+                            upper=cfg["upper"], minimum_prob=cfg["min_prob"], clr_weight_name=cfg["weight"])
+    if cfg.get("genome"):
+        ns.chroms = case.chroms_arg()
+        score_genome.main(ns)
+    else:
+        ns.chrom = case.chroms[0].name
+        score_chromosome.main(ns)
+    assert open(out).read() == case.bedpe
+    monkeypatch.setattr(_lib, "_expected_mode", None)
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_raw", "lowdepth", "c1", "w7"])
+def test_windows_as_tma_boxes(name, tmp_path):
+    """pk_set_tuning("tma", 2): the fused kernel of both widths fetches every window as one TMA box from the
+    row-major band copy (the default does so for w = 7 only). Float32 features inside the kernel (the tap) and
+    the bedpe are the reference's."""
+    from peakachu_b200 import _lib, score_chromosome
+    L = _lib.lib()
+    case = Case(name)
+    cfg = case.cfg
+    try:
+        _lib.check(L.pk_set_tuning(b"tma", 2))
+        import hashlib
+        for ch in case.chroms:
+            X = _gpu_chromosome(case, ch)
+            keep, f32 = X.fused_window_features()
+            assert hashlib.sha256(np.ascontiguousarray(f32[keep]).tobytes()).hexdigest() == case.meta["sha"][ch.name]["fea32"]
+            if name in FULL_TAP_CASES:
+                assert np.array_equal(f32[keep], case.z[ch.name + "/fea32"])
+            X.close()
+        cool = case.write_cool(tmp_path)
+        out = os.path.join(str(tmp_path), "gpu.bedpe")
+        score_chromosome.main(argparse.Namespace(path=cool, model=case.pkl, output=out, resolution=cfg["res"], lower=cfg["lower"],
+                                                 upper=cfg["upper"], minimum_prob=cfg["min_prob"], clr_weight_name=cfg["weight"],
+                                                 chrom=case.chroms[0].name))
+        assert open(out).read() == case.bedpe
+    finally:
+        _lib.check(L.pk_set_tuning(b"tma", 1))
+
+
 @pytest.mark.parametrize("name,group", [("tiny", ""), ("tiny_raw", ""), ("genome", "resolutions/10000")])
 def test_bedpe_from_a_real_cool_file(name, group, tmp_path):
     """SURVEY.md 8(f) row 1: the same CLI on an HDF5 cooler file (.cool / .mcool::group, read by
@@ -680,6 +735,64 @@ def test_depth_matches_dense_triu_sum(tmp_path, capsys):
     assert out[-3] == "num of intra reads in your data: %d" % total
     assert out[-1].startswith("suggested model: ")
     assert out[:len(case.chroms)] == [c.name for c in case.chroms]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,min_dis", [("c5", 0), ("c5", 20000), ("genome", 0), ("gnames", 30000), ("tiny", 0), ("lowdepth", 50000)])
+def test_depth_prints_what_the_reference_prints(name, min_dis, tmp_path, capsys):
+    """`depth` against the reference's own stdout (tests/golden/depth.json, made by running the unmodified
+    calculate_depth.main: make_depth_golden.py): chromosome names, contact total, human-equivalent depth and the
+    suggested model, byte for byte."""
+    import json
+
+    from peakachu_b200 import cli
+    from tests.cases import GOLDEN
+    want = json.load(open(os.path.join(GOLDEN, "depth.json")))[name][str(min_dis)]
+    path = Case(name).write_cool(tmp_path)
+    capsys.readouterr()
+    cli.run(["depth", "-p", path, "--min-dis", str(min_dis)])
+    assert capsys.readouterr().out == want
+
+
+@pytest.mark.gpu
+def test_c5_as_specified_depth_selects_the_forest(tmp_path, capsys):
+    """BASELINE.json configs[4] end to end: `depth` on the low-depth map suggests a model (calculate_depth.py:42-70),
+    the forest is taken from a bank by that label, score_genome runs at --minimum-prob 0.6 and the reference's
+    `pool` output at 0.6 and 0.9 (golden) consists of rows of our bedpe."""
+    import json
+
+    from peakachu_b200 import cli
+    from tests.cases import GOLDEN
+    case = Case("c5")
+    cfg = case.cfg
+    path = case.write_cool(tmp_path)
+    capsys.readouterr()
+    cli.run(["depth", "-p", path])
+    printed = capsys.readouterr().out
+    assert printed == json.load(open(os.path.join(GOLDEN, "depth.json")))["c5"]["0"]
+    label = printed.strip().splitlines()[-1].split(": ", 1)[1]
+    # the bank: the forest fitted at the map's own depth sits under the label the reference suggests for it,
+    # forests of deeper maps under theirs (Case("genome") is a 300x map: "500 million")
+    bank = {"10 million": case.pkl, "500 million": Case("genome").pkl, "450 million": Case("tiny").pkl}
+    assert label == "10 million"
+    out = os.path.join(str(tmp_path), "c5.bedpe")
+    cli.run(["score_genome", "-p", path, "-m", bank[label], "-O", out, "-r", str(cfg["res"]), "-l", str(cfg["lower"]),
+             "-u", str(cfg["upper"]), "--minimum-prob", str(cfg["min_prob"]), "--clr-weight-name", cfg["weight"],
+             "-C"] + case.chroms_arg())
+    txt = open(out).read()
+    assert txt == case.bedpe
+    rows = {tuple(ln.split("\t")[i] for i in (0, 1, 4)): ln.split("\t")[6:8] for ln in txt.splitlines()}
+    for thr in (0.9, cfg["min_prob"]):
+        pooled = [ln.split("\t") for ln in case.pool(thr).splitlines() if not ln.startswith("ERROR")]
+        assert pooled or thr == 0.9
+        for f in pooled:
+            assert rows[(f[0], f[1], f[4])] == f[6:8]
+    # a forest of the wrong depth gives a different loop set: the selection step matters
+    out2 = os.path.join(str(tmp_path), "c5_wrong.bedpe")
+    cli.run(["score_genome", "-p", path, "-m", bank["500 million"], "-O", out2, "-r", str(cfg["res"]), "-l", str(cfg["lower"]),
+             "-u", str(cfg["upper"]), "--minimum-prob", str(cfg["min_prob"]), "--clr-weight-name", cfg["weight"],
+             "-C"] + case.chroms_arg())
+    assert open(out2).read() != txt
 
 
 @pytest.mark.gpu

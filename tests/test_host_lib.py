@@ -110,3 +110,53 @@ def test_plan_covers_every_row_once_and_balances():
             assert all(t0[1] == t1[0] for t0, t1 in zip(tiles, tiles[1:]))
         loads = [sum(shard.band_pixels(sizes[k], 6, 300, 5) * (b - a) / sizes[k] for k, a, b in u) for u in asg]
         assert max(loads) <= 1.35 * (sum(loads) / world) + 1
+
+
+def test_expected_fit_mode_follows_the_environment(monkeypatch):
+    """The device fit is pinned to the arithmetic of one scikit-learn / scipy / numpy generation: with other
+    versions installed `auto` warns (once) and still fits on the device; PEAKACHU_B200_EXPECTED selects the mode."""
+    import warnings
+
+    from peakachu_b200 import _lib
+    have = _lib.installed_versions()
+    assert set(have) == set(_lib.PINNED_VERSIONS)
+    monkeypatch.delenv("PEAKACHU_B200_EXPECTED", raising=False)
+    monkeypatch.setattr(_lib, "_expected_mode", None)
+    monkeypatch.setattr(_lib, "PINNED_VERSIONS", dict(have))
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        assert _lib.expected_mode() == "device"                       # matching environment: silent
+    monkeypatch.setattr(_lib, "_expected_mode", None)
+    monkeypatch.setattr(_lib, "PINNED_VERSIONS", dict(have, sklearn="0.0"))
+    with pytest.warns(RuntimeWarning, match="PEAKACHU_B200_EXPECTED=host"):
+        assert _lib.expected_mode() == "device"
+    for mode in ("host", "device"):
+        monkeypatch.setattr(_lib, "_expected_mode", None)
+        monkeypatch.setenv("PEAKACHU_B200_EXPECTED", mode)
+        assert _lib.expected_mode() == mode
+    monkeypatch.setattr(_lib, "_expected_mode", None)
+    monkeypatch.setenv("PEAKACHU_B200_EXPECTED", "sometimes")
+    with pytest.raises(ValueError):
+        _lib.expected_mode()
+    monkeypatch.setattr(_lib, "_expected_mode", None)
+
+
+def test_dropin_constructor_refuses_a_differently_balanced_matrix(tmp_path):
+    """Chromosome(M, model, raw_M, weights): the device balances raw_M with `weights` itself, so an M that is not
+    (w[r] * w[c]) * raw -- another weight column, a scaled matrix -- is refused on the host, before any device work."""
+    from scipy import sparse
+
+    from peakachu_b200 import synth
+    from peakachu_b200.scoreUtils import Chromosome, _check_balanced_matrix
+    ch = synth.make_chromosome("chr1", 300, seed=3, depth=100.0, band=60, n_loops=10, loop_max=40)
+    raw = sparse.coo_matrix((ch.count, (ch.bin1, ch.bin2)), shape=(ch.n, ch.n)).tocsr()
+    raw = raw + sparse.triu(raw, k=1).T
+    w = ch.weights
+    rc = raw.tocoo()
+    good = sparse.csr_matrix(((w[rc.row] * w[rc.col]) * rc.data, (rc.row, rc.col)), shape=raw.shape)
+    b1, b2 = ch.bin1.astype(np.int32), ch.bin2.astype(np.int32)
+    _check_balanced_matrix(good, b1, b2, ch.count, w)                       # the product itself: accepted
+    with pytest.raises(ValueError, match="balances raw_M"):
+        _check_balanced_matrix(good * 1.5, b1, b2, ch.count, w)
+    with pytest.raises(ValueError, match="balances raw_M"):
+        Chromosome(good, model=None, raw_M=raw, weights=w * 1.01)           # raised before the device is touched
