@@ -295,13 +295,16 @@ def run_genome(args, name, flat, rank, world, local, steps, encodings):
             res = shard.score_units(pm, mine, flat, correct="weight", lower=wl["lower"], upper=wl["upper"],
                                     res=wl["res"], device=local, min_prob=0.5, copy=False, encoding=enc)
             t_b = time.perf_counter()
-            gathered = shard.gather_to_rank0(res, rank, world)
+            gathered = shard.gather_to_rank0(res, rank, world, copy=False)
             t_c = time.perf_counter()
             n_out = 0
             if rank == 0:
                 merged = {k: shard.merge_tiles(sorted([q for g in gathered for q in g.get(k, [])],
                                                       key=lambda q: q["row_begin"])) for k in queue}
                 n_out = sum(int(m[0].size) for m in merged.values())
+                chk = sum(int(m[0][-1]) for m in merged.values() if m[0].size)      # touch the gathered columns
+                shard.release_gathered()                                            # ... before handing the blocks back
+                n_out += 0 * chk
             t_d = time.perf_counter()
             phase[:] += (t_b - t_a, t_c - t_b, t_d - t_c)
             return n_out

@@ -130,7 +130,7 @@ def _host_group():
 #   segment, [128 + 8 r] rank 0 only: last pass of rank r it has finished reading
 _CTL_BYTES = 4096
 _SHM = {"mode": None, "pass": 0, "ctl": None, "seg": None, "cap": 0, "ctl_peers": {}, "peers": {}, "peer_names": {},
-        "fence": None}
+        "fence": None, "held": None, "world": 1}
 
 
 def _strip_arrays(obj, arrays):
@@ -159,6 +159,7 @@ def _release_shm():
     # A rank other than 0 must not unlink its data segment before rank 0 has read the last pass it
     # published: rank 0 attaches a peer's data segment lazily, at its first read, and usually finishes
     # last (the greedy plan gives it the largest unit). Wait for its acknowledgement first.
+    release_gathered()                    # rank 0: views of the last pass are not needed any more
     root_name = _SHM.get("root_ctl")
     if _SHM["mode"] == "shm" and root_name is not None and _SHM["pass"] > 0 and _SHM.get("rank", 0) != 0:
         root = _SHM["ctl_peers"].get(root_name)
@@ -252,10 +253,28 @@ def _setup_shm(rank, world, group):
         _SHM["root_ctl"] = info[0][1]
 
 
-def _gather_shm(obj, rank, world):
+def release_gathered():
+    """Rank 0: done with the views a ``gather_to_rank0(..., copy=False)`` returned -- acknowledge the pass, so
+    that the other ranks may overwrite their blocks. A no-op elsewhere, and when nothing is held."""
+    import struct
+    p = _SHM.get("held")
+    if p is None or _SHM["ctl"] is None:
+        _SHM["held"] = None
+        return
+    _fence()
+    mine = _SHM["ctl"].buf
+    for r in range(1, _SHM["world"]):
+        struct.pack_into("<Q", mine, 128 + 8 * r, p)
+    _SHM["held"] = None
+
+
+def _gather_shm(obj, rank, world, copy=True):
     import pickle
     import struct
     from multiprocessing import shared_memory
+    if rank == 0:
+        release_gathered()                # views of the previous pass die here at the latest
+    _SHM["world"] = world
     p = _SHM["pass"] = _SHM["pass"] + 1
     if rank != 0:
         arrays = []
@@ -299,31 +318,42 @@ def _gather_shm(obj, rank, world):
         seg = _SHM["peers"].get(r)
         if seg is None or _SHM["peer_names"].get(r) != name:      # first pass, or rank r grew its segment
             if seg is not None:
-                seg.close()
+                try:
+                    seg.close()
+                except BufferError:               # views of a released pass are still referenced somewhere
+                    _SHM.setdefault("stale", []).append(seg)
             seg = _attach(name, {})
             _SHM["peers"][r] = seg
             _SHM["peer_names"][r] = name
         hlen, base = struct.unpack_from("<QQ", seg.buf, 0)
         meta, layout = pickle.loads(bytes(seg.buf[16:16 + hlen]))
         got = [np.frombuffer(seg.buf, dtype=np.dtype(dt), count=int(np.prod(shape, dtype=np.int64)), offset=base + o)
-               .reshape(shape).copy() for dt, shape, o in layout]
+               .reshape(shape) for dt, shape, o in layout]
+        if copy:
+            got = [a.copy() for a in got]
         result.append(_restore_arrays(meta, got))
-        _fence()
-        struct.pack_into("<Q", mine, 128 + 8 * r, p)      # acknowledge: rank r may overwrite its block
+        if copy:
+            _fence()
+            struct.pack_into("<Q", mine, 128 + 8 * r, p)      # acknowledge: rank r may overwrite its block
+    if not copy:
+        _SHM["held"] = p                  # acknowledged by release_gathered() (or the next gather, or at exit)
     return result
 
 
-def gather_to_rank0(obj, rank, world):
+def gather_to_rank0(obj, rank, world, copy=True):
     """Host-side gather of the ranks' records to rank 0: numpy columns through shared memory when every
     rank runs on the same host (PEAKACHU_B200_GATHER=shm, the default), else pickled through gloo's
-    gather_object. Returns the list of per-rank objects on rank 0, None elsewhere."""
+    gather_object. Returns the list of per-rank objects on rank 0, None elsewhere. With ``copy=False`` the
+    arrays of the other ranks are views of their shared-memory blocks (no copy on rank 0: 8 MB per pass of the
+    hg19-shaped genome, 1.1 ms of a 2.6 ms pass on 8 GPUs); they stay valid until ``release_gathered()``, which
+    the caller owes the other ranks as soon as it has consumed them (the next gather releases them at the latest)."""
     if world == 1:
         return [obj]
     import torch.distributed as dist
     if _SHM["mode"] is None:
         _setup_shm(rank, world, _host_group())
     if _SHM["mode"] == "shm":
-        return _gather_shm(obj, rank, world)
+        return _gather_shm(obj, rank, world, copy=copy)
     out = [None] * world if rank == 0 else None
     dist.gather_object(obj, out, dst=0, group=_host_group())
     return out
@@ -575,7 +605,9 @@ def score_chromosomes(Lib, queue, flat, *, correct, lower, upper, res, min_prob,
     order = sorted(assignment[rank], key=lambda u: band_pixels(sizes[u[0]], lower, upper, flat.width) * (u[2] - u[1]) / max(sizes[u[0]], 1))
     mine = score_units(Lib, order, flat, correct=correct, lower=lower, upper=upper, res=res,
                        device=device, min_prob=min_prob)
-    gathered = gather_to_rank0(mine, rank, world)
+    gathered = gather_to_rank0(mine, rank, world, copy=False)
     if rank != 0:
         return {}
-    return assemble_text(queue, gathered, res, verbose=verbose)
+    text = assemble_text(queue, gathered, res, verbose=verbose)
+    release_gathered()                    # the text holds everything: the other ranks may go on (or exit)
+    return text

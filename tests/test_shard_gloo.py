@@ -46,10 +46,15 @@ def _worker(rank, world, port, tmp):
     mine = _fake_units(asg[rank], rec)
     for i in range(4):                 # the shared-memory segments are reused from pass to pass, and regrown
         big = dict(mine, pad=[dict(row_begin=0, junk=np.arange((i % 2) * 400000 + rank, dtype=np.int64))]) if i < 3 else mine
-        gathered = shard.gather_to_rank0(big, rank, world)
+        zero_copy = i == 1                     # rank 0 reads views of the peers' blocks and hands them back itself
+        gathered = shard.gather_to_rank0(big, rank, world, copy=not zero_copy)
         if rank == 0 and i < 3:
             for r in range(world):
                 assert np.array_equal(gathered[r]["pad"][0]["junk"], np.arange((i % 2) * 400000 + r))
+            if zero_copy:
+                assert shard._SHM["mode"] != "shm" or not gathered[1]["pad"][0]["junk"].flags["OWNDATA"]
+                gathered = None
+                shard.release_gathered()
     assert shard._SHM["mode"] == os.environ.get("PEAKACHU_B200_GATHER", "shm")
     if rank == 0:
         assert len(gathered) == world

@@ -11,9 +11,14 @@ import sys
 
 import numpy as np
 
-STAGE = [("k_score_fused", "features"), ("k_band_", "band_build"), ("k_valid_bits", "diag_sums"), ("k_diag_", "diag_sums"),
+STAGE = [("k_score_fused", "features"), ("k_band_csr<int, int", "band_build"), ("k_band_rowmajor", "band_build"),
+         ("k_band_csr<unsigned short", "band_build_uint16_columns"), ("k_band_rows", "band_build_packed_rows"),
+         ("k_band_escapes", "band_build_packed_rows"), ("k_scatter_pixels", "band_build_coo"),
+         ("k_valid_bits", "diag_sums"), ("k_diag_", "diag_sums"),
          ("k_fit_expected", "expected_fit"), ("k_cand_", "candidate_scan"), ("k_emit", "emit"), ("k_row_offsets", "emit"),
          ("k_record_", "emit"), ("k_features", "features_unfused"), ("k_forest", "forest_unfused")]
+# band_build is the device-resident upload bench.py times per stage (cooler's int32 columns, plus the row-major copy
+# where the fused kernel wants it); the other upload encodings of the end-to-end passes are listed beside it
 
 
 def unit_scale(u):
