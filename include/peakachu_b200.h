@@ -260,10 +260,17 @@ int pk_chrom_set_score_stream(pk_chrom* c, void* stream);
 /* return the library's cached device blocks (of destroyed handles) to the driver */
 int pk_release_memory(void);
 
-/* process-wide tuning knob, for benchmarking: key "fused" = -1 auto (default),
- * 0 separate feature + forest kernels, 1 / 2 the two fused-kernel tile sizes;
- * key "prune" = 1 (default) lets the fused kernel stop walking trees for pixels whose
- * probability can no longer exceed min_prob (emitted records are unaffected), 0 walks all */
+/* process-wide tuning knobs, for benchmarking and A/B runs (results are identical under every setting):
+ *   "fused"           -1 auto (default), 0 separate feature + forest kernels, 1 + v: fused-kernel variant v
+ *                     (tile sizes, warp groups; the list is in pk_fused.cu, pk_launch_fused)
+ *   "prune"           1 (default): the fused kernel stops walking trees for pixels whose probability can no
+ *                     longer exceed min_prob (emitted records are unaffected); 0 walks every tree
+ *   "child_features"  forest walk on the node encoding that names the children's features: -1 where measured
+ *                     faster (w = 7), 0 off, 1 on
+ *   "tma"             windows fetched as TMA boxes (cp.async.bulk.tensor.2d) from a row-major copy of the band:
+ *                     1 (default) where measured faster (w = 7), 2 always (w = 5 too), 0 never. Read when a
+ *                     chromosome handle is created (the copy is allocated there).
+ *   "reserve_sms"     SMs the fused kernel leaves free for the short stages of other chromosomes in flight */
 int pk_set_tuning(const char* key, int value);
 
 /* time spent (ms, CUDA events) in each stage of the last upload/fit/find/score of
