@@ -121,7 +121,7 @@ def workload_config(wl, args):
             "per_rank": "one chromosome of the workload per rank per step (weak scaling); the `genome` block of the "
                         "GPU arm is score_genome on the hg19-shaped map sharded over the ranks (strong scaling)",
             "forest": "bench_data/%s.pkl" % wl["forest"],
-            "l2": "value: three chromosomes in flight, 3 x ~150 MB of working set > 126 MB L2; stage_ms / roofline: "
+            "l2": "value: several chromosomes in flight, each ~150 MB of working set, together > 126 MB L2; stage_ms / roofline: "
                   "one chromosome at a time with a 256 MiB L2 flush between steps; e2e: every step uploads its "
                   "inputs from pinned host memory (the host is the cold side)"}
 
@@ -416,6 +416,8 @@ def main():
     ap.add_argument("--genome", default="auto", help="score_genome blocks in the JSON line: auto (c3 at every N, c4 too at N = 8), "
                                                      "none, or a comma list of c3,c4")
     ap.add_argument("--genome-steps", type=int, default=0, help="timed passes of a genome block (0: min(steps, 10))")
+    ap.add_argument("--reserve-sms", type=int, default=8, help="pk_set_tuning('reserve_sms'): SMs the fused kernel leaves to the short stages of the chromosomes queued behind (engine passes)")
+    ap.add_argument("--inflight", type=int, default=4, help="chromosomes in flight (streams) of the device-resident `value` pass")
     ap.add_argument("--no-file-e2e", action="store_true", help="skip the file -> bedpe block (N = 1, about 40 s of host work)")
     ap.add_argument("--numa", type=int, default=1, help="N > 1: run each rank on the NUMA node of its GPU (0: leave the affinity alone)")
     ap.add_argument("--fused", type=int, default=-1, help="pk_set_tuning('fused'): -1 auto, 0 off, 1, 2")
@@ -448,6 +450,7 @@ def main():
     _lib.check(L.pk_set_tuning(b"fused", args.fused))
     _lib.check(L.pk_set_tuning(b"prune", args.prune))
     _lib.check(L.pk_set_tuning(b"child_features", args.child_features))
+    _lib.check(L.pk_set_tuning(b"reserve_sms", args.reserve_sms))
     args.warmup = max(args.warmup, 3)
 
     flat = FlatForest.load(os.path.join(ROOT, "bench_data", wl["forest"] + "_forest.npz"))
@@ -505,14 +508,23 @@ def main():
     nrec, ncand, nwin = C.c_int64(), C.c_int64(), C.c_int64()
     _lib.check(L.pk_chrom_result_count(h, C.byref(nrec), C.byref(ncand), C.byref(nwin)))
 
-    # ---- pass 2 (the reported value): K chromosomes, three in flight on three streams, as
-    # score_genome runs them. Three working sets (3 x ~150 MB) exceed L2, so no flush is needed.
-    NFLIGHT = 3
-    streams = [torch.cuda.Stream(device=local) for _ in range(NFLIGHT)]
+    # ---- pass 2 (the reported value): K chromosomes, NFLIGHT in flight, arranged as score_genome's engine runs
+    # them (pk_engine_*): every handle has a high-priority stream for its upload and short stages, the fused
+    # scoring kernels go back to back to one ordinary stream (pk_chrom_set_score_stream) and leave a few SMs to
+    # the short stages of the chromosomes queued behind (tuning "reserve_sms"). The working sets in flight
+    # (NFLIGHT x ~150 MB) exceed L2, so no flush is needed.
+    NFLIGHT = args.inflight
+    streams = []
+    for _ in range(NFLIGHT):
+        sp = C.c_void_p()
+        _lib.check(L.pk_stream_create_priority(local, 1, C.byref(sp)))
+        streams.append(torch.cuda.ExternalStream(sp.value, device=local))
+    score_stream = torch.cuda.Stream(device=local)
     handles = []
     for st in streams:
         hh = C.c_void_p()
         _lib.check(L.pk_chrom_create(local, n, w, wl["lower"], wl["upper"], 1, C.c_void_p(st.cuda_stream), C.byref(hh)))
+        _lib.check(L.pk_chrom_set_score_stream(hh, C.c_void_p(score_stream.cuda_stream)))
         handles.append(hh)
     for i in range(2 * NFLIGHT):
         device_step(handles[i % NFLIGHT])
@@ -533,6 +545,8 @@ def main():
         _lib.check(L.pk_chrom_result_count(hh, C.byref(nr2), None, None))   # also checks the device flags
         assert nr2.value == nrec.value
         _lib.check(L.pk_chrom_destroy(hh))
+    for st in streams:
+        _lib.check(L.pk_stream_destroy(local, C.c_void_p(st.cuda_stream)))
     _lib.check(L.pk_chrom_destroy(h))
     del d_rp, d_b2, d_cnt, d_w
 
@@ -646,7 +660,7 @@ def main():
         "dtype": "f64", "data": "synthetic", "config": workload_config(wl, args),
         "run": {"candidates_per_step": int(ncand.value), "windows_per_step": int(nwin.value),
                 "records_per_step": int(nrec.value), "forest": "%d trees, %d nodes" % (flat.n_trees, flat.n_nodes),
-                "timed": "%d chromosomes, three in flight on three streams (device-resident CSR columns)" % steps},
+                "timed": "%d chromosomes, %d in flight (device-resident CSR columns; short stages on high-priority streams, fused kernels back to back on one stream)" % (steps, args.inflight)},
         "candidates_per_s": world * int(ncand.value) * steps / (dev_ms * 1e-3),
         "stage_ms": stage, "roofline": roofline, "cpu_baseline": cpu, "e2e": head,
     }

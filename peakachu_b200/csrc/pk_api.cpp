@@ -50,7 +50,8 @@ static int g_tune_cf = -1;       // fused forest walk on the child-feature node 
 // fused kernel fetches windows as TMA boxes from a row-major copy of the band: 1 = where measured faster (w = 7: -8 %;
 // the w = 5 kernel is 6 % slower with it, profiles/r2_summary.md), 2 = always, 0 = never (per-cell gather)
 static int g_tune_tma = 1;
-static int g_tune_reserve = 0;   // SMs the fused kernel leaves to the short stages of other chromosomes (pipelined use)     // retire pixels that cannot exceed min_prob (exact for every emitted record)
+static int g_tune_reserve = 8;   // SMs the fused kernel leaves to the short stages of other chromosomes (pipelined use: handles with a
+                                 // score stream; measured on the c2 chromosome end to end: 0.663 ms with 0, 0.633-0.641 with 4-12, profiles/r2_summary.md)     // retire pixels that cannot exceed min_prob (exact for every emitted record)
 
 extern "C" int pk_set_tuning(const char* key, int value) {
     if (key && !strcmp(key, "fused")) { g_tune_fused = value; return PK_OK; }
