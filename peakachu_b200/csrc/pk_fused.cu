@@ -108,7 +108,8 @@ struct FusedCfg {
     static constexpr int VSTEP = !TM ? 0 : (VSLACK / 3 >= 40 ? ((VSLACK / 3) & ~7) : (VSLACK & ~7));
     static constexpr int VMASK = VSLACK / 3 >= 40 ? 3 : 1;
     static constexpr int SSTEP = !TM ? 0 : ((SSLACK / 3) & ~7);
-    static constexpr int PB_raw = (int)(stage_bytes / NG / (size_t)WSTRIDE) & ~1;
+    static constexpr int NBUF = TM == 2 ? 2 : 1;              // TM == 2: the boxes of the next take land while this one is processed
+    static constexpr int PB_raw = (int)(stage_bytes / NG / NBUF / (size_t)WSTRIDE) & ~1;
     static constexpr int PB = PB_raw < P ? PB_raw : P;        // windows staged per take and group (even)
     static constexpr int NIT = (PB * S + NTG - 1) / NTG;      // TM: window columns per thread and take
     static constexpr int NIW = (PB + 31) / 32;                // TM: warps of a group that request boxes
@@ -117,10 +118,10 @@ struct FusedCfg {
     static_assert(F * 4 >= S * 16, "row extrema do not fit a feature row");
     static constexpr int NPW = (PB / 2 + NWG - 1) / NWG;      // window pairs per warp per take
     static size_t total(int ND, int n_trees) {
-        return stage_bytes + fea_bytes + 2 * (size_t)((ND + 1) & ~1) * 8 + (size_t)NG * PB * 4 + 2 * (size_t)F * 8 +
-               (size_t)P * 4 + 2 * (size_t)NG * PB * 4 + (size_t)n_trees * 4 + (size_t)((n_trees + 3) & ~3) +
+        return stage_bytes + fea_bytes + 2 * (size_t)((ND + 1) & ~1) * 8 + (size_t)NG * NBUF * PB * 4 + 2 * (size_t)F * 8 +
+               (size_t)P * 4 + 2 * (size_t)NG * NBUF * PB * 4 + (size_t)n_trees * 4 + (size_t)((n_trees + 3) & ~3) +
                2 * (size_t)NG * PB * 2 + (size_t)P + 64 + (CF ? (size_t)((n_trees + 3) & ~3) : 0) +
-               (TM ? (size_t)NG * PB * 6 + 16 : 0);
+               (TM ? (size_t)NG * NBUF * PB * 6 + 16 : 0);
     }
 };
 
@@ -225,7 +226,7 @@ template <int W, int P, int TPP, int TBN, int CH, int OCC, int NTH, int NGR, int
 __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const __grid_constant__ FusedParams prm) {
     using Cfg = FusedCfg<W, P, TPP, TBN, CH, NTH, NGR, XSTAGE, CF, TM>;
     constexpr int S = Cfg::S, F = Cfg::F, NT = Cfg::NT, NW = Cfg::NW, NS = Cfg::NS, NM = Cfg::NM, CHUNK = Cfg::CHUNK;
-    constexpr int PB = Cfg::PB, NG = Cfg::NG, NTG = Cfg::NTG, NWG = Cfg::NWG, WSTRIDE = Cfg::WSTRIDE;
+    constexpr int PB = Cfg::PB, NG = Cfg::NG, NTG = Cfg::NTG, NWG = Cfg::NWG, WSTRIDE = Cfg::WSTRIDE, NBUF = Cfg::NBUF;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [tree buffers | hand-over]  (= window staging during phase A) | features | exp | 1/exp |
     //         candidate rank | gather order | slot->candidate | window distance |
@@ -238,11 +239,11 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const __grid_constant_
     const int ND = prm.ND, NDp = (ND + 1) & ~1;
     double* s_rexp = s_exp + NDp;                                 // RN(1 / exp)
     int32_t* s_rank = reinterpret_cast<int32_t*>(s_rexp + NDp);   // [NG][PB] candidate rank (PB even)
-    int2* s_cell = reinterpret_cast<int2*>(s_rank + NG * PB);     // [2F] gather order of a window pair
+    int2* s_cell = reinterpret_cast<int2*>(s_rank + NG * NBUF * PB);     // [2F] gather order of a window pair
     int32_t* s_idx = reinterpret_cast<int32_t*>(s_cell + 2 * F);  // [P]
     int32_t* s_cd = s_idx + P;                                    // [NG][PB]
-    int32_t* s_nz = s_cd + NG * PB;                               // [NG][PB]
-    uint32_t* s_root = reinterpret_cast<uint32_t*>(s_nz + NG * PB);   // [n_trees]
+    int32_t* s_nz = s_cd + NG * NBUF * PB;                        // [NG][NBUF][PB]
+    uint32_t* s_root = reinterpret_cast<uint32_t*>(s_nz + NG * NBUF * PB);   // [n_trees]
     uint8_t* s_depth = reinterpret_cast<uint8_t*>(s_root + prm.n_trees);     // [n_trees] (padded to 4)
     uint16_t* s_kl = reinterpret_cast<uint16_t*>(s_depth + ((prm.n_trees + 3) & ~3));    // [NG][PB] kept windows of a take
     uint16_t* s_ks = s_kl + NG * PB;                              // [NG][PB] their feature slots
@@ -250,14 +251,14 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const __grid_constant_
     uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_nan + P) + 15) & ~(uintptr_t)15);
     uint8_t* s_rootfeat = reinterpret_cast<uint8_t*>(s_bar + 4);  // [n_trees] (CF only)
     int32_t* s_cx = reinterpret_cast<int32_t*>(s_rootfeat + (CF ? ((prm.n_trees + 3) & ~3) : 0));   // [NG][PB] window row (TM only)
-    int16_t* s_slot = reinterpret_cast<int16_t*>(s_cx + NG * PB);  // [NG][PB] feature slot of a kept window, else -1 (TM only)
-    __shared__ uint64_t s_gbar[NG];                               // TM: a group's boxes have landed
+    int16_t* s_slot = reinterpret_cast<int16_t*>(s_cx + NG * NBUF * PB);  // [NG][NBUF][PB] feature slot of a kept window, else -1 (TM only)
+    __shared__ uint64_t s_gbar[NG * NBUF];                        // TM: the boxes of a group's take have landed
     // phase B: leaf hand-over, running sums, list of pixels still walking
     double* s_lv = s_hand;                                        // [2][CH][P] (TPP == 2)
     double* s_acc = s_hand + (TPP == 2 ? 2 * CH * P : 0);         // [P]
     uint16_t* s_list = reinterpret_cast<uint16_t*>(s_acc + P);    // [2][P]
-    __shared__ int s_gnkt[NG], s_gtake[NG], s_gstop[NG], s_reserved, s_nkept, s_done, s_expbad, s_wc[32];
-    __shared__ long long s_gstart[NG];
+    __shared__ int s_gnkt[NG], s_gtake[NG * NBUF], s_gstop[NG * NBUF], s_reserved, s_nkept, s_done, s_expbad, s_wc[32];
+    __shared__ long long s_gstart[NG * NBUF];
     constexpr int GCACHE = 64;                   // tree-group table kept in shared memory when it fits
     __shared__ int4 s_grp[GCACHE];
 
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const __grid_constant_
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
         if (TM)
-            for (int g = 0; g < NG; ++g) mbar_init(&s_gbar[g], Cfg::NIW);
+            for (int g = 0; g < NG * NBUF; ++g) mbar_init(&s_gbar[g], Cfg::NIW);
         mbar_fence_init();
         s_done = 0;
     }
@@ -325,19 +326,21 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const __grid_constant_
         }
     };
 
-    const uint32_t V_addr = smem_u32(s_V) + (uint32_t)(grp * PB) * (uint32_t)WSTRIDE;     // this group's staging buffer
+    int cur = 0;                                 // TM == 2: which of the group's two slot sets holds the take being processed
+    const uint32_t V_base = smem_u32(s_V) + (uint32_t)(grp * NBUF * PB) * (uint32_t)WSTRIDE;   // this group's staging buffer(s)
+    uint32_t V_addr = V_base;
     auto win_base = [&](int i) -> uint32_t {     // float64 window of the take's window i
         return V_addr + (uint32_t)i * (uint32_t)WSTRIDE + (uint32_t)((i & Cfg::VMASK) * Cfg::VSTEP);
     };
     auto scr_base = [&](int i) -> uint32_t {     // TM: parked lower-left block + centre of window i
         return V_addr + (uint32_t)i * (uint32_t)WSTRIDE + (uint32_t)(Cfg::SCR_OFF + ((i >> 2) & 3) * Cfg::SSTEP);
     };
-    int32_t* g_cx = s_cx + grp * PB;
-    int16_t* g_slot = s_slot + grp * PB;
-    uint32_t gphase = 0;                         // TM: parity of the group's box barrier
-    int32_t* g_rank = s_rank + grp * PB;
-    int32_t* g_cd = s_cd + grp * PB;
-    int32_t* g_nz = s_nz + grp * PB;
+    int32_t* g_cx = s_cx + grp * NBUF * PB;
+    int16_t* g_slot = s_slot + grp * NBUF * PB;
+    uint32_t gphase = 0;                         // TM: parity of the group's box barrier(s), one bit per slot set
+    int32_t* g_rank = s_rank + grp * NBUF * PB;
+    int32_t* g_cd = s_cd + grp * NBUF * PB;
+    int32_t* g_nz = s_nz + grp * NBUF * PB;
     uint16_t* g_kl = s_kl + grp * PB;
     uint16_t* g_ks = s_ks + grp * PB;
     const uint32_t exp_addr = smem_u32(s_exp), rexp_addr = smem_u32(s_rexp), fea_addr = smem_u32(s_fea);
@@ -355,54 +358,92 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const __grid_constant_
         // with all threads of the group.
         if (tid == 0) { s_reserved = 0; s_nkept = 0; }
         __syncthreads();
+        // reserve feature slots, then candidates, for the take that slot set `set` will hold (thread 0 of the group)
+        auto grab = [&](int set) {
+            const int prev = atomicAdd(&s_reserved, PB);
+            const int sz = max(0, min(PB, P - prev));
+            int take = 0;
+            long long st = 0;
+            bool stop = true;
+            if (sz > 0) {
+                st = (long long)atomicAdd(prm.next, (unsigned long long)sz);
+                const long long rem = n_cand - st;
+                take = rem <= 0 ? 0 : (int)(rem < sz ? rem : sz);
+                stop = rem <= sz;                      // every candidate has been handed out
+                if (stop) s_done = 1;
+            }
+            s_gstart[grp * NBUF + set] = st;
+            s_gtake[grp * NBUF + set] = take;
+            s_gstop[grp * NBUF + set] = stop;
+        };
+        auto use_set = [&](int set) {                  // the slot set whose take is processed
+            cur = set;
+            V_addr = V_base + (uint32_t)(set * PB) * (uint32_t)WSTRIDE;
+            g_rank = s_rank + (grp * NBUF + set) * PB;
+            g_cd = s_cd + (grp * NBUF + set) * PB;
+            g_nz = s_nz + (grp * NBUF + set) * PB;
+            g_cx = s_cx + (grp * NBUF + set) * PB;
+            g_slot = s_slot + (grp * NBUF + set) * PB;
+        };
+        // TM: one lane per window writes the take's coordinates and requests the window's band cells from the TMA
+        // unit: rows x-W..x+W, columns from (y-W) & ~3 of the dense-matrix view of the row-major band (one
+        // cp.async.bulk.tensor.2d per window, SASS UTMALDG.2D), completing on the slot set's mbarrier. Called by the
+        // whole issuing warps with the window's coordinates already in registers.
+        auto request = [&](int set, int take, int i, int x, int d, int rank) {
+            const int o = (grp * NBUF + set) * PB;
+            const bool ok = i < take && (x - W >= 0) && (x + d + W + 1 <= prm.n);             // scoreUtils.py:75
+            if (i < take) {
+                s_rank[o + i] = rank;
+                s_cd[o + i] = d; s_cx[o + i] = x; s_nz[o + i] = ok ? 0 : -1; s_slot[o + i] = -1;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            // the slots were last touched through the generic proxy (an earlier take, the forest phase)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (lane == 0) mbar_expect_tx(&s_gbar[grp * NBUF + set], (uint32_t)__popc(m) * (uint32_t)Cfg::BOX_BYTES);
+            __syncwarp();
+            if (ok) tma_box_2d(V_base + (uint32_t)(set * PB + i) * (uint32_t)WSTRIDE, &prm.tmap, (x + d - W) & ~3, x - W,
+                               smem_u32(&s_gbar[grp * NBUF + set]));
+        };
+        if constexpr (TM == 2) {
+            // prologue: the first take of the batch is requested here; inside the loop every take requests its successor
+            use_set(0);
+            if (gtid == 0) grab(0);
+            gsync();
+            if (gtid < Cfg::NIW * 32) {
+                const int take0 = s_gtake[grp * NBUF], i = gtid;
+                const long long start0 = s_gstart[grp * NBUF];
+                int x = 0, d = 0, rk = 0;
+                if (i < take0) { x = prm.cx[start0 + i]; d = prm.cd[start0 + i]; rk = __ldg(prm.crank + start0 + i); }
+                request(0, take0, i, x, d, rk);
+            }
+        }
         for (;;) {
-            if (gtid == 0) {
-                // reserve feature slots, then candidates
-                const int prev = atomicAdd(&s_reserved, PB);
-                const int sz = max(0, min(PB, P - prev));
-                int take = 0;
-                long long st = 0;
-                bool stop = true;
-                if (sz > 0) {
-                    st = (long long)atomicAdd(prm.next, (unsigned long long)sz);
-                    const long long rem = n_cand - st;
-                    take = rem <= 0 ? 0 : (int)(rem < sz ? rem : sz);
-                    stop = rem <= sz;                      // every candidate has been handed out
-                    if (stop) s_done = 1;
-                }
-                s_gstart[grp] = st;
-                s_gtake[grp] = take;
-                s_gstop[grp] = stop;
-                s_gnkt[grp] = 0;
+            if constexpr (TM == 2) {
+                if (gtid == 0) s_gnkt[grp] = 0;
+            } else {
+                if (gtid == 0) { grab(0); s_gnkt[grp] = 0; }
             }
             gsync();
             PK_TICK(0);
-            const int take = s_gtake[grp];
-            const long long start = s_gstart[grp];
-            const bool stop = s_gstop[grp] != 0;
+            const int take = s_gtake[grp * NBUF + cur];
+            const long long start = s_gstart[grp * NBUF + cur];
+            const bool stop = s_gstop[grp * NBUF + cur] != 0;
+            // TM == 2: the successor take is reserved now (the answer is needed two barriers further down) ...
+            if (TM == 2 && gtid == 0) {
+                if (!stop) grab(cur ^ 1);
+            }
+            int nx_x = 0, nx_d = 0, nx_rank = 0, nx_take = 0;      // ... its coordinates are loaded after the column step ...
             if constexpr (TM) {
-            // ---- T1 (TM): one lane per window reads its coordinates and requests the window's band cells from the
-            //      TMA unit: rows x-W..x+W, columns from (y-W) & ~3 of the dense-matrix view of the row-major band
-            //      (one cp.async.bulk.tensor.2d per window, SASS UTMALDG.2D), completing on the group's mbarrier.
+            if constexpr (TM == 1) {
+            // ---- T1 (TM == 1): coordinates and box requests of this take
             if (gtid < Cfg::NIW * 32) {
                 const int i = gtid;
-                int x = 0, d = 0;
-                bool ok = false;
-                if (i < take) {
-                    x = prm.cx[start + i];
-                    d = prm.cd[start + i];
-                    ok = (x - W >= 0) && (x + d + W + 1 <= prm.n);                         // scoreUtils.py:75
-                    g_rank[i] = __ldg(prm.crank + start + i);
-                    g_cd[i] = d; g_cx[i] = x; g_nz[i] = ok ? 0 : -1; g_slot[i] = -1;
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                // the slots were last touched through the generic proxy (previous take, forest phase)
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                if (lane == 0) mbar_expect_tx(&s_gbar[grp], (uint32_t)__popc(m) * (uint32_t)Cfg::BOX_BYTES);
-                __syncwarp();
-                if (ok) tma_box_2d(V_addr + (uint32_t)i * (uint32_t)WSTRIDE, &prm.tmap, (x + d - W) & ~3, x - W, smem_u32(&s_gbar[grp]));
+                int x = 0, d = 0, rk = 0;
+                if (i < take) { x = prm.cx[start + i]; d = prm.cd[start + i]; rk = __ldg(prm.crank + start + i); }
+                request(0, take, i, x, d, rk);
             }
             gsync();
+            }
             PK_TICK(8);
             // ---- A3a (TM): one thread per window column: counts from the box, balanced values into registers,
             //      non-zeros counted, the lower-left block and the centre parked for the filters
@@ -428,7 +469,7 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const __grid_constant_
                             for (int a = 0; a < S; ++a) wr[a] = __ldg(prm.w + (x - W + a));
                         }
                     }
-                    if (!waited) { PK_TICK(9); mbar_wait(&s_gbar[grp], gphase); waited = true; PK_TICK(10); }
+                    if (!waited) { PK_TICK(9); mbar_wait(&s_gbar[grp * NBUF + cur], (gphase >> cur) & 1u); waited = true; PK_TICK(10); }
                     if (have) {
                         const int y0 = x + d - W;
                         const uint32_t cell0 = V_addr + (uint32_t)i * (uint32_t)WSTRIDE + (uint32_t)((y0 & 3) + b) * 4u;
@@ -473,11 +514,19 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const __grid_constant_
                         if (b == W) sts_f64(scr + (uint32_t)(W * W) * 8u, v[k][W]);
                     }
                 }
-                gphase ^= 1u;
+                gphase ^= 1u << cur;
             }
             PK_TICK(11);
             gsync();
             PK_TICK(1);
+            if constexpr (TM == 2) {
+                // ... (the reservation made at the top of the loop is visible now; the loads fly during the filter step) ...
+                if (!stop && gtid < Cfg::NIW * 32) {
+                    nx_take = s_gtake[grp * NBUF + (cur ^ 1)];
+                    const long long nstart = s_gstart[grp * NBUF + (cur ^ 1)];
+                    if (gtid < nx_take) { nx_x = prm.cx[nstart + gtid]; nx_d = prm.cd[nstart + gtid]; nx_rank = __ldg(prm.crank + nstart + gtid); }
+                }
+            }
             // ---- A2 (TM): the reference's filters, one thread per window
             {
                 const int i = lane * NWG + gw;
@@ -511,6 +560,10 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const __grid_constant_
             {
                 const int nkt_ = s_gnkt[grp];
                 if (gtid == 0 && nkt_ < take) atomicSub(&s_reserved, take - nkt_);    // rejected windows free their slots
+            }
+            if constexpr (TM == 2) {
+                // ... and its boxes are requested into the other slot set, whose last reader was the previous take
+                if (!stop && gtid < Cfg::NIW * 32) request(cur ^ 1, nx_take, gtid, nx_x, nx_d, nx_rank);
             }
             const bool fastdiv = !s_expbad;
             // ---- A3b (TM): distance normalisation + vertical Gaussian pass of the kept windows, from the registers,
@@ -839,7 +892,8 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const __grid_constant_
                 }
             }
             if (stop) break;                     // uniform in the group
-            gsync();                             // the staging buffer and the grab variables are free again
+            if constexpr (TM == 2) use_set(cur ^ 1);      // the barrier at the top of the loop separates the takes
+            else gsync();                        // the staging buffer and the grab variables are free again
             PK_TICK(5);
         }
         __syncthreads();
@@ -1096,6 +1150,10 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int res
         case 5: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 8, 0, 0, 1>(prm, f, c->ND, sm, st);      // TMA windows, 8 groups of 2 warps
         case 6: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 2, 0, 0, 1>(prm, f, c->ND, sm, st);      // TMA windows, 2 groups of 8 warps
         case 7: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 16, 0, 0, 1>(prm, f, c->ND, sm, st);     // TMA windows, a warp per group
+        case 8: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4, 0, 0, 2>(prm, f, c->ND, sm, st);      // TMA windows requested a take ahead (two slot sets), 4 groups
+        case 9: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 2, 0, 0, 2>(prm, f, c->ND, sm, st);      // same, 2 groups
+        case 10: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 8, 0, 0, 2>(prm, f, c->ND, sm, st);     // same, 8 groups
+        case 11: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 16, 0, 0, 2>(prm, f, c->ND, sm, st);    // same, a warp per group
         default:
             if (tm) return cf ? launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4, 0, 1, 1>(prm, f, c->ND, sm, st)
                               : launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4, 0, 0, 1>(prm, f, c->ND, sm, st);
@@ -1112,13 +1170,20 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int res
         case 7: return launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 6, 32768, 1, 1>(prm, f, c->ND, sm, st);  // TMA windows, 6 groups of 2 warps
         // eight trees per forest round (four chains per thread, buffers of 6400 nodes) on batches of 112 pixels
         case 8: return launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 1, 32768, 1, 1>(prm, f, c->ND, sm, st);  // TMA windows, four trees per round
+        case 12: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 1, 0, 1, 2>(prm, f, c->ND, sm, st);     // the default with boxes requested a take ahead
+        case 13: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 2, 0, 1, 2>(prm, f, c->ND, sm, st);     // same, 2 groups of 6 warps
+        case 14: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 3, 0, 1, 2>(prm, f, c->ND, sm, st);     // same, 3 groups of 4 warps
+        case 15: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 4, 0, 1, 2>(prm, f, c->ND, sm, st);     // same, 4 groups of 3 warps
+        case 16: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 6, 0, 1, 2>(prm, f, c->ND, sm, st);     // same, 6 groups of 2 warps
+        case 17: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 1, 0, 1, 1>(prm, f, c->ND, sm, st);     // one group, boxes requested by the take itself
         case 9: return launch_fused_t<7, 112, 2, 6400, 4, 1, 320, 1, 0, 1, 1>(prm, f, c->ND, sm, st);
         case 10: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 1, 0, 0, 1>(prm, f, c->ND, sm, st);
         case 11: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 1, 0, 1, 0>(prm, f, c->ND, sm, st);
         default:
             // TMA windows; with the child-feature encoding also eight trees per forest round (four chains per thread,
-            // buffers of 6400 nodes, batches of 112 pixels): 5.53 -> 5.13 -> 4.81 ms on the C4 chromosome
-            if (tm) return cf ? launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 1, 0, 1, 1>(prm, f, c->ND, sm, st)
+            // buffers of 6400 nodes, batches of 112 pixels) and every warp its own group whose boxes are requested a
+            // take ahead: 5.53 -> 5.13 -> 4.81 -> 4.59 ms on the C4 chromosome
+            if (tm) return cf ? launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 12, 0, 1, 2>(prm, f, c->ND, sm, st)
                               : launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 1, 32768, 0, 1>(prm, f, c->ND, sm, st);
             return cf ? launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 1, 32768, 1>(prm, f, c->ND, sm, st)
                       : launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 1, 32768>(prm, f, c->ND, sm, st);
