@@ -18,6 +18,10 @@ ncu --set full --clock-control none --import-source on -k regex:k_score_fused -s
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --genome none --no-file-e2e > $out/ncu_full.log 2>&1
 ncu -i $out/fused.ncu-rep --page raw --csv > $out/fused_raw.csv 2>/dev/null
 ncu -i $out/fused.ncu-rep --page source --csv > $out/fused_src.csv 2>/dev/null
+ncu --set full --clock-control none --import-source on -k regex:k_score_fused -s 2 -c 1 -f -o $out/fused_c4 \
+    python bench.py --workload c4 --steps 3 --warmup 3 --no-cpu-baseline --genome none --no-file-e2e > $out/ncu_full_c4.log 2>&1
+ncu -i $out/fused_c4.ncu-rep --page raw --csv > $out/fused_c4_raw.csv 2>/dev/null
+ncu -i $out/fused_c4.ncu-rep --page source --csv > $out/fused_c4_src.csv 2>/dev/null
 python - <<'PY'
 import json, os
 for w in ("c2", "c1", "c4"):
