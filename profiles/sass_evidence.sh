@@ -3,7 +3,7 @@
 # UBLKCP = cp.async.bulk), mbarrier (SYNCS.*), warp reductions (CREDUX / REDUX), async-proxy fences.
 #   bash profiles/sass_evidence.sh > profiles/r2_sass_excerpt.txt
 so=${1:-peakachu_b200/libpeakachu_b200.so}
-for k in ILi5ELi256ELi2ELi4224ELi4ELi1ELi512ELi4ELi0ELi0ELi0E ILi7ELi112ELi2ELi6400ELi4ELi1ELi384ELi1ELi0ELi1ELi1E; do
+for k in ILi5ELi256ELi2ELi4224ELi4ELi1ELi512ELi4ELi0ELi0ELi0E ILi7ELi112ELi2ELi6400ELi4ELi1ELi384ELi12ELi0ELi1ELi2E; do
   echo "== k_score_fused$k  ($(cuobjdump -sass $so | awk -v k="$k" '/Function :/ {on = index($0, "k_score_fused" k) > 0} on' | grep -c '^ *\/\*[0-9a-f]*\*\/') SASS instructions, target $(cuobjdump -lelf $so | grep -o 'sm_[0-9a-z]*' | sort -u | tr '\n' ' '))"
   cuobjdump -sass $so | awk -v k="$k" '/Function :/ {on = index($0, "k_score_fused" k) > 0} on' \
     | grep -E "UTMALDG|UBLKCP|SYNCS\.|CREDUX|REDUX|FENCE\.VIEW\.ASYNC|BAR\.SYNC|DFMA|LDS\.64|DMUL" \
