@@ -625,6 +625,68 @@ def test_fused_walk_with_nan_windows():
             assert np.array_equal(a, b), key
 
 
+@pytest.mark.parametrize("w,case_name,combos", [
+    (5, "lowdepth", [(0, -1), (2, -1), (2, 9), (2, 8)]),          # gather | TMA boxes | boxes a take ahead | a warp per group
+    (7, "w7", [(0, -1), (1, -1), (1, 18), (1, 9)])])              # gather | default (boxes a take ahead, warp groups) | one group | 4 trees per round
+def test_fused_kernels_on_hostile_weights(w, case_name, combos):
+    """Every fused-kernel arrangement against the separate feature / forest kernels (pinned to the reference by the
+    golden tests) on a balanced map whose weight column holds NaN, zero, negative, infinite, huge and tiny entries:
+    the TMA kernels decide per window column whether (w_r w_c) count needs a finiteness test at all, from the
+    largest high word of the weight products. Float32 features inside the kernel (bit patterns, NaN included) and
+    the probabilities of all windows must be identical."""
+    from peakachu_b200 import _lib
+    from peakachu_b200.scoreUtils import Chromosome
+    L = _lib.lib()
+    case = Case(case_name)
+    n, lower, upper = 520, 6, 70
+    rng = np.random.default_rng(100 + w)
+    b1, b2 = np.nonzero(np.triu(np.ones((n, n), bool)) & ~np.triu(np.ones((n, n), bool), upper + 2 * w + 1))
+    keep = rng.random(b1.size) < 0.8
+    b1, b2 = b1[keep].astype(np.int32), b2[keep].astype(np.int32)
+    cnt = rng.integers(1, 30, b1.size).astype(np.int32)
+    weights = np.exp(rng.normal(0.0, 0.3, n))
+    special = rng.random(n)
+    weights[special < 0.05] = np.nan
+    weights[(special >= 0.05) & (special < 0.07)] = 0.0
+    weights[(special >= 0.07) & (special < 0.08)] = -1.3
+    weights[(special >= 0.08) & (special < 0.09)] = 1e160
+    weights[(special >= 0.09) & (special < 0.10)] = 1e-170
+    weights[(special >= 0.10) & (special < 0.105)] = np.inf
+    weights[(special >= 0.105) & (special < 0.11)] = 1e-320           # denormal
+    got = {}
+    try:
+        for tma, fused in [(0, 0)] + combos:
+            _lib.check(L.pk_set_tuning(b"tma", tma))
+            _lib.check(L.pk_set_tuning(b"fused", fused))
+            X = Chromosome.from_pixels(b1, b2, cnt, weights, n, case.forest, lower=lower, upper=upper, cname="chr1",
+                                       res=10000, width=w, sorted_pixels=True)
+            el = X._exp_len
+            exp = np.ascontiguousarray(5.0 / (1.0 + np.arange(el)) + 0.05)
+            _lib.check(L.pk_chrom_set_expected(X._h, exp.ctypes.data_as(_lib.c_f64p), exp.ctypes.data_as(_lib.c_f64p)))
+            _lib.check(L.pk_chrom_find_candidates(X._h, 0, n, None))
+            X._ncand = X._cand = None
+            if fused == 0:
+                k0, f0 = X.window_features()[:2]
+                got["tap"] = (k0, f0[k0].view(np.uint32).copy())
+            else:
+                kf, ff = X.fused_window_features()
+                assert np.array_equal(kf, got["tap"][0]), (tma, fused)
+                assert np.array_equal(ff[kf].view(np.uint32), got["tap"][1]), (tma, fused)
+            got[(tma, fused)] = X.score_records(-1.0)
+            X.close()
+    finally:
+        _lib.check(L.pk_set_tuning(b"fused", -1))
+        _lib.check(L.pk_set_tuning(b"tma", 1))
+    base = got[(0, 0)]
+    assert base[0].size > 2000
+    odd = ~np.isfinite(weights) | (weights <= 0) | (weights > 1e100) | (weights < 1e-100)
+    near = np.convolve(odd.astype(int), np.ones(2 * w + 1, int), mode="same") > 0
+    assert (near[base[0]] | near[base[1]]).sum() > 500            # windows that hold pixels of such bins: the slow path ran
+    for key in combos:
+        for a, b in zip(base, got[key]):
+            assert np.array_equal(a, b, equal_nan=True), key
+
+
 def test_forest_nan_features_follow_missing_go_to_left():
     """sklearn routes NaN features by missing_go_to_left; the forest tap must
     give the same leaves and probabilities on rows with NaNs."""
