@@ -756,6 +756,13 @@ __global__ void __launch_bounds__(PK_FIT_THREADS) k_fit_expected(
 // ---------------------------------------------------------------------------
 #define PK_CTILE 4096
 
+// the exact test of a slot whose approximate comparison is too close to call (rare): kept out of line so that the
+// sixteen unrolled slots of a thread do not each carry a division
+__device__ __noinline__ bool pk_poisson_exact(double e, double p, double cr) {
+    const double mu = __ddiv_rn(e, p);
+    return (mu >= 0.0) && (mu < cr);
+}
+
 __global__ void __launch_bounds__(256) k_cand_mark(
     const int32_t* __restrict__ band, const double* __restrict__ w, const double* __restrict__ bg,
     int n, long long pitch, int balanced, int lower, const double* __restrict__ crit, int kmax,
@@ -770,6 +777,7 @@ __global__ void __launch_bounds__(256) k_cand_mark(
     const long long tile = (long long)di * n_chunks + chunk;
     __shared__ int s_a[8], s_t[8];
     int tot_a = 0, tot_t = 0;
+    bool over = false;                           // a count beyond the table of critical means
     // mu < crit[k]  <=>  e / p < crit[k], p = w_x w_y. The division is only needed when e and crit[k] * p are
     // within 2^-40 of each other: both roundings (of the product here, of the quotient there) are below
     // 2^-52 relative, so outside that band the comparison of e with crit[k] * p decides -- and decides the
@@ -795,7 +803,7 @@ __global__ void __launch_bounds__(256) k_cand_mark(
         for (int j = 0; j < 8; ++j) {
             bool c = false;
             if (k[j] > 0) {
-                if (k[j] > kmax) atomicOr(&flags[0], 1);
+                if (k[j] > kmax) over = true;
                 else {
                     const double cr = crit[k[j]];
                     if (!balanced) c = (e >= 0.0) && (e < cr);
@@ -804,7 +812,7 @@ __global__ void __launch_bounds__(256) k_cand_mark(
                         const double t = __dmul_rn(cr, p);
                         if (approx_ok && t > e_hi) c = true;
                         else if (approx_ok && t < e_lo) c = false;
-                        else { const double mu = __ddiv_rn(e, p); c = (mu >= 0.0) && (mu < cr); }
+                        else c = pk_poisson_exact(e, p, cr);
                     }
                 }
             }
@@ -819,6 +827,7 @@ __global__ void __launch_bounds__(256) k_cand_mark(
             tot_t += __popc(bt);
         }
     }
+    if (__any_sync(0xffffffffu, over) && lane == 0) atomicOr(&flags[0], 1);
     if (lane == 0) { s_a[wid] = tot_a; s_t[wid] = tot_t; }
     __syncthreads();
     if (tid == 0) {

@@ -971,6 +971,77 @@ def test_full_size_matches_reference(name, tmp_path):
     assert hashlib.sha256(txt.encode()).hexdigest() == case.meta["bedpe_sha"]
 
 
+class _MemMap:
+    """Chromosomes held in memory behind the interface shard.score_units reads a map through."""
+
+    def __init__(self, nd_enc):
+        self.nd_enc, self.ch = nd_enc, {}
+
+    def add(self, ch):
+        from peakachu_b200 import rowpack
+        rp = np.searchsorted(ch.bin1, np.arange(ch.n + 1)).astype(np.int64)
+        self.ch[ch.name] = dict(n=ch.n, w=ch.weights, rows=rowpack.pack_rows(rp, ch.bin2, ch.count, ch.n, self.nd_enc))
+
+    def nbins(self, key): return self.ch[key]["n"]
+    def weights(self, key, name): return self.ch[key]["w"]
+    def upper_pixels_rows(self, key, nd_min): return self.ch[key]["rows"] if self.nd_enc >= nd_min else None
+
+
+@pytest.mark.gpu
+def test_full_size_genome_matches_reference():
+    """BASELINE configs[2] at full size: score_genome's path (plan, engine, gather, bedpe text) on the hg19-shaped
+    10 kb genome the bench scores -- 23 chromosomes, 303,641 bins, 88.5 M band pixels -- against the checksums of the
+    REFERENCE's own bedpe for every chromosome (tests/golden/fullsize.json, made by make_fullsize_golden.py from the
+    unmodified score_genome.main)."""
+    import hashlib
+    import json
+
+    import bench
+    from peakachu_b200 import shard, synth
+    from peakachu_b200.forest import FlatForest
+    from tests.cases import GOLDEN
+    gold = json.load(open(os.path.join(GOLDEN, "fullsize.json")))["c3"]["chroms"]
+    wl = bench.GENOMES["c3"]
+    sizes = synth.hg19_bins(wl["res"])
+    assert list(gold) == list(sizes)
+    mm = _MemMap((wl["upper"] + 2 * wl["w"] + 1 + 31) // 32 * 32)
+    for idx, (name, n) in enumerate(sizes.items()):
+        ch = synth.make_chromosome(name, n, seed=5000 + idx, depth=wl["depth"], band=wl["band"])
+        assert ch.checksum() == gold[name]["input_checksum"], name
+        mm.add(ch)
+    flat = FlatForest.load(os.path.join(bench.ROOT, "bench_data", wl["forest"] + "_forest.npz"))
+    text = shard.score_chromosomes(mm, list(sizes), flat, correct="weight", lower=wl["lower"], upper=wl["upper"],
+                                   res=wl["res"], min_prob=0.5, device=0)
+    for name in sizes:
+        assert text[name].count("\n") == gold[name]["rows"], name
+        assert hashlib.sha256(text[name].encode()).hexdigest() == gold[name]["sha256"], name
+
+
+@pytest.mark.gpu
+def test_full_size_c4_chromosome_matches_reference(tmp_path):
+    """BASELINE configs[3]'s shape at full size (49,850 bins at 5 kb, w = 7, -u 600, the 200-tree bench forest):
+    the CLI's bedpe against the checksum of the reference's own (tests/golden/fullsize.json)."""
+    import hashlib
+    import json
+
+    import bench
+    from peakachu_b200 import coolio, score_chromosome
+    from tests.cases import GOLDEN
+    gold = json.load(open(os.path.join(GOLDEN, "fullsize.json")))["c4_chr1"]
+    wl = bench.WORKLOADS["c4"]
+    ch = bench.make_map(wl, seed=1234)
+    assert ch.checksum() == gold["input_checksum"]
+    path = os.path.join(str(tmp_path), "c4.pkcool")
+    coolio.PKCool.write(path, [ch], wl["res"], rows_nd=(wl["upper"] + 2 * wl["w"] + 1 + 31) // 32 * 32)
+    out = os.path.join(str(tmp_path), "c4.bedpe")
+    score_chromosome.main(argparse.Namespace(path=path, model=os.path.join(bench.ROOT, "bench_data", wl["forest"] + ".pkl"),
+                                             output=out, resolution=wl["res"], lower=wl["lower"], upper=wl["upper"],
+                                             minimum_prob=0.5, clr_weight_name="weight", chrom=ch.name))
+    txt = open(out).read()
+    assert txt.count("\n") == gold["rows"]
+    assert hashlib.sha256(txt.encode()).hexdigest() == gold["sha256"]
+
+
 def test_batch_rule_whole_chromosome_and_row_tiles():
     """scoreUtils.py:104-108 on the fixture made for it (> 340,000 candidates; four reference batches keep
     2 / 1 / 0 / 3 windows): the whole-chromosome pass drops the lone window of the second batch on the
