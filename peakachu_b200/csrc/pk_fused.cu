@@ -1139,21 +1139,17 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int res
     int sm = 148;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, c->device);
     sm = std::max(1, sm - reserve_sms);
-    // variant 0 is the default; the others are tuning experiments (pk_set_tuning("fused", 1 + variant))
+    // variant 0 is the default; the others are tuning experiments (pk_set_tuning("fused", 1 + variant)). Arrangements that
+    // were measured and dropped from the build are listed with their times in profiles/r2_summary.md.
     cudaStream_t st = c->stream;
     if (c->w == 5) {
         switch (variant) {
         case 1: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 2>(prm, f, c->ND, sm, st);
         case 2: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 1>(prm, f, c->ND, sm, st);
         case 3: return launch_fused_t<5, 128, 2, 2112, 2, 2, 256, 2>(prm, f, c->ND, sm, st);      // two CTAs per SM: their phases drift apart and overlap
-        case 4: return launch_fused_t<5, 128, 2, 2112, 4, 2, 256, 2>(prm, f, c->ND, sm, st);
-        case 5: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 8, 0, 0, 1>(prm, f, c->ND, sm, st);      // TMA windows, 8 groups of 2 warps
-        case 6: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 2, 0, 0, 1>(prm, f, c->ND, sm, st);      // TMA windows, 2 groups of 8 warps
         case 7: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 16, 0, 0, 1>(prm, f, c->ND, sm, st);     // TMA windows, a warp per group
         case 8: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4, 0, 0, 2>(prm, f, c->ND, sm, st);      // TMA windows requested a take ahead (two slot sets), 4 groups
         case 9: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 2, 0, 0, 2>(prm, f, c->ND, sm, st);      // same, 2 groups
-        case 10: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 8, 0, 0, 2>(prm, f, c->ND, sm, st);     // same, 8 groups
-        case 11: return launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 16, 0, 0, 2>(prm, f, c->ND, sm, st);    // same, a warp per group
         default:
             if (tm) return cf ? launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4, 0, 1, 1>(prm, f, c->ND, sm, st)
                               : launch_fused_t<5, 256, 2, 4224, 4, 1, 512, 4, 0, 0, 1>(prm, f, c->ND, sm, st);
@@ -1165,20 +1161,12 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int res
         switch (variant) {
         case 1: return launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 2, 32768>(prm, f, c->ND, sm, st);
         case 2: return launch_fused_t<7, 128, 2, 3200, 2, 1, 512, 2, 32768>(prm, f, c->ND, sm, st);
-        case 5: return launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 2, 32768, 1, 1>(prm, f, c->ND, sm, st);  // TMA windows, 2 groups of 6 warps
-        case 6: return launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 3, 32768, 1, 1>(prm, f, c->ND, sm, st);  // TMA windows, 3 groups of 4 warps
-        case 7: return launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 6, 32768, 1, 1>(prm, f, c->ND, sm, st);  // TMA windows, 6 groups of 2 warps
         // eight trees per forest round (four chains per thread, buffers of 6400 nodes) on batches of 112 pixels
         case 8: return launch_fused_t<7, 128, 2, 3200, 2, 1, 384, 1, 32768, 1, 1>(prm, f, c->ND, sm, st);  // TMA windows, four trees per round
-        case 12: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 1, 0, 1, 2>(prm, f, c->ND, sm, st);     // the default with boxes requested a take ahead
-        case 13: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 2, 0, 1, 2>(prm, f, c->ND, sm, st);     // same, 2 groups of 6 warps
-        case 14: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 3, 0, 1, 2>(prm, f, c->ND, sm, st);     // same, 3 groups of 4 warps
-        case 15: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 4, 0, 1, 2>(prm, f, c->ND, sm, st);     // same, 4 groups of 3 warps
-        case 16: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 6, 0, 1, 2>(prm, f, c->ND, sm, st);     // same, 6 groups of 2 warps
+        case 14: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 3, 0, 1, 2>(prm, f, c->ND, sm, st);     // the default's arrangement with 3 groups of 4 warps
+        case 16: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 6, 0, 1, 2>(prm, f, c->ND, sm, st);     // ... with 6 groups of 2 warps
         case 17: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 1, 0, 1, 1>(prm, f, c->ND, sm, st);     // one group, boxes requested by the take itself
-        case 9: return launch_fused_t<7, 112, 2, 6400, 4, 1, 320, 1, 0, 1, 1>(prm, f, c->ND, sm, st);
-        case 10: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 1, 0, 0, 1>(prm, f, c->ND, sm, st);
-        case 11: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 1, 0, 1, 0>(prm, f, c->ND, sm, st);
+        case 11: return launch_fused_t<7, 112, 2, 6400, 4, 1, 384, 1, 0, 1, 0>(prm, f, c->ND, sm, st);     // eight trees per round on the per-cell gather
         default:
             // TMA windows; with the child-feature encoding also eight trees per forest round (four chains per thread,
             // buffers of 6400 nodes, batches of 112 pixels) and every warp its own group whose boxes are requested a

@@ -15,7 +15,7 @@ import bench  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--variants", default="-1,2,3,4,5")
+    ap.add_argument("--variants", default="-1,2,3,4")
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--tma", type=int, default=2, help="pk_set_tuning('tma'): windows fetched as TMA boxes (default variant only)")
     args = ap.parse_args()
