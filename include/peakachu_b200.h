@@ -244,6 +244,15 @@ int pk_selftest_divide(int device, int64_t n, uint64_t seed, int64_t* mismatches
 int pk_format_bedpe(const char* chrom, int64_t res, const int32_t* x, const int32_t* y, const double* prob,
                     const double* val, int64_t n, char* out, int64_t capacity, int64_t* written);
 
+/* Host-only helper of the built-in .cool reader (peakachu_b200/h5mini.py; cooler's own reader is h5py / libhdf5,
+ * score_chromosome.py:33-43): decode the chunks of a 1-D HDF5 dataset that cover elements [lo, hi) straight from the
+ * memory-mapped file into `out` ([hi - lo] elements) on n_threads host threads (0: all). chunk_off / chunk_bytes locate
+ * the filtered chunks in `file`, first_elem is each chunk's first element; filters as flags: deflate (zlib), shuffle,
+ * fletcher32 (its 4 trailing bytes are dropped, not verified). */
+int pk_h5_decode_chunks(const uint8_t* file, int64_t n_chunks, const int64_t* chunk_off, const int64_t* chunk_bytes,
+                        const int64_t* first_elem, int64_t chunk_elems, int32_t elem_size, int32_t deflate,
+                        int32_t shuffle, int32_t fletcher32, int64_t lo, int64_t hi, void* out, int32_t n_threads);
+
 /* a non-blocking CUDA stream for pk_chrom_create, for callers that do not bring their own
  * (two handles on two streams overlap one chromosome's upload with another's kernels) */
 int pk_stream_create(int device, void** out);

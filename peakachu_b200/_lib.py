@@ -70,6 +70,8 @@ SIGNATURES = {
     "pk_format_bedpe": (C.c_int, [C.c_char_p, C.c_int64, c_i32p, c_i32p, c_f64p, c_f64p, C.c_int64, C.c_char_p,
                                   C.c_int64, c_i64p]),
     "pk_stream_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "pk_h5_decode_chunks": (C.c_int, [C.c_void_p, C.c_int64, c_i64p, c_i64p, c_i64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int32]),
     "pk_stream_destroy": (C.c_int, [C.c_int, C.c_void_p]),
     "pk_stream_create_priority": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "pk_chrom_set_score_stream": (C.c_int, [C.c_void_p, C.c_void_p]),

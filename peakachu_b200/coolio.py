@@ -343,22 +343,32 @@ class H5Cool:
             r1 = int(np.searchsorted(rp, rp[r0] + BLOCK, side="right")) - 1
             r1 = min(n, max(r1, r0 + 1))
             a, b = p0 + int(rp[r0]), p0 + int(rp[r1])
-            b2 = self._bin2.read(a, b).astype(np.int64)
+            b2 = self._bin2.read(a, b)
             cnt = self._count.read(a, b)
             if cnt.dtype.kind == "f" and not np.all(cnt == np.rint(cnt)):
                 raise ValueError("%s: non-integer pixel counts; the Poisson filter "
                                  "(scoreUtils.py:59-60) needs raw counts" % self.path)
             if cnt.size and (cnt.min() < 0 or cnt.max() > np.iinfo(np.int32).max):
                 raise ValueError("%s: pixel counts outside int32" % self.path)
-            rows = np.repeat(np.arange(r0, r1, dtype=np.int64), np.diff(rp[r0:r1 + 1]))
-            if b2.size and np.any(b2 - lo < rows):
-                raise ValueError("%s: pixels below the diagonal (storage-mode is not symmetric-upper)" % self.path)
+            # per-row work goes through the row pointer (reduceat over the non-empty rows), not through a
+            # row index per pixel: the columns of a chr1-scale chromosome are 7 M pixels
+            starts = (rp[r0:r1] - rp[r0]).astype(np.int64)
+            lens = np.diff(rp[r0:r1 + 1])
+            full = np.flatnonzero(lens > 0)
+            if b2.size:
+                # cooler stores pixels sorted by (bin1, bin2): the smallest bin2 of a row must not lie below the diagonal
+                if np.any(np.minimum.reduceat(b2, starts[full]) - lo < full + r0):
+                    raise ValueError("%s: pixels below the diagonal (storage-mode is not symmetric-upper)" % self.path)
             cis = b2 < hi
-            if not cis.all():                                # drop inter-chromosomal pixels
-                rows, b2, cnt = rows[cis], b2[cis], cnt[cis]
-            row_counts[r0:r1] = np.bincount(rows - r0, minlength=r1 - r0)
+            if cis.all():
+                row_counts[r0:r1] = lens
+            else:                                            # drop inter-chromosomal pixels
+                kept = np.zeros(r1 - r0, dtype=np.int64)
+                kept[full] = np.add.reduceat(cis.astype(np.int64), starts[full])
+                row_counts[r0:r1] = kept
+                b2, cnt = b2[cis], cnt[cis]
             kept_b2.append((b2 - lo).astype(np.int32))
-            kept_cnt.append(cnt.astype(np.int32))
+            kept_cnt.append(cnt.astype(np.int32, copy=False))
             r0 = r1
         rp = np.concatenate([[0], np.cumsum(row_counts)]).astype(np.int64)
         b2l = np.concatenate(kept_b2) if kept_b2 else np.zeros(0, np.int32)

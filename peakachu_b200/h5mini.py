@@ -618,6 +618,42 @@ class Dataset:
         cdims = self._layout[2]
         return np.frombuffer(raw, dtype=self.dtype, count=int(np.prod(cdims))).reshape(cdims)
 
+    def _decode_native(self, hits, lo: int, hi: int, out: np.ndarray) -> bool:
+        """Large reads of 1-D columns (a chromosome's pixel columns) go to the library's threaded decoder
+        (``pk_h5_decode_chunks``: zlib + un-shuffle from the mapped file into ``out``). Returns False when the
+        read is small, the filter pipeline is not [shuffle,] deflate [, fletcher32], or the library is not built --
+        the Python loop below then does the same work."""
+        if len(self.shape) != 1 or len(hits) < 4 or sum(rec[2] for rec in hits) < (1 << 20) or not self.filters:
+            return False
+        if self.dtype.byteorder == ">" or self.dtype.kind not in "iuf" or any(rec[3] for rec in hits):
+            return False
+        ids = [fid for fid, _ in self.filters]
+        if ids not in ([1], [2, 1], [1, 3], [2, 1, 3]):
+            return False
+        if 2 in ids:
+            vals = dict(self.filters)[2]
+            if vals and vals[0] != self.dtype.itemsize:
+                return False
+        try:
+            from . import _lib
+            L = _lib.lib()
+        except Exception:
+            return False
+        import ctypes as C
+        b = self._f._b
+        view = np.frombuffer(b.d, dtype=np.uint8)              # the mapped file, no copy
+        off = np.array([b.base + rec[1] for rec in hits], dtype=np.int64)
+        size = np.array([rec[2] for rec in hits], dtype=np.int64)
+        first = np.array([rec[0][0] for rec in hits], dtype=np.int64)
+        if int((off + size).max()) > view.size:
+            return False
+        rc = L.pk_h5_decode_chunks(C.c_void_p(view.ctypes.data), len(hits), _lib.ptr(off, _lib.c_i64p), _lib.ptr(size, _lib.c_i64p),
+                                   _lib.ptr(first, _lib.c_i64p), int(self._layout[2][0]), self.dtype.itemsize, 1, int(2 in ids),
+                                   int(3 in ids), int(lo), int(hi), C.c_void_p(out.ctypes.data), 0)
+        if rc != 0:
+            raise H5Error("%s: %s" % (self.name, L.pk_last_error().decode("utf-8", "replace")))
+        return True
+
     # ---- reads -----------------------------------------------------------
     def read(self, lo: int = 0, hi: int | None = None) -> np.ndarray:
         """Rows [lo, hi) along the first axis, as a native-endian array."""
@@ -643,6 +679,8 @@ class Dataset:
         out = np.zeros(out_shape, dtype=native)
         cdims = self._layout[2]
         hits = [rec for rec in self._chunk_list() if rec[0][0] + cdims[0] > lo and rec[0][0] < hi]
+        if self._decode_native(hits, lo, hi, out):
+            return out
         # zlib releases the GIL: inflate the chunks of a large read on a few threads (a chromosome of a
         # genome-wide cooler is hundreds of megabytes of pixel columns)
         if len(hits) >= 4 and sum(rec[2] for rec in hits) >= (1 << 20) and self.filters:

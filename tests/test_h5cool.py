@@ -214,3 +214,38 @@ def test_odd_pixel_columns_fail_loudly(tmp_path):
     _mini_cool(p, b1, b2, np.full(120, 2**31 + 5, np.int64))
     with pytest.raises(ValueError, match="outside int32"):
         coolio.open_map(p).upper_pixels("chrZ")
+
+
+@pytest.mark.parametrize("latest", [False, True])
+def test_native_chunk_decoder_equals_the_python_one(tmp_path, latest, monkeypatch):
+    """Large reads of 1-D columns are decoded by the library (pk_h5_decode_chunks: zlib + un-shuffle on host threads,
+    straight from the mapped file); small reads and other pipelines by the Python loop. Same arrays either way, for
+    every filter pipeline the native path takes, whole columns and ranges that start and end inside chunks."""
+    W = (h5write.Writer2 if latest else h5write.Writer)()
+    rng = np.random.default_rng(7)
+    cols = {"i8": rng.integers(-2**60, 2**60, 400000),                                   # incompressible: > 1 MB of chunks
+            "i4": rng.integers(-2**31, 2**31 - 1, 700000).astype(np.int32),
+            "f8": rng.normal(size=300000),
+            "u2": rng.integers(0, 65535, 1500000).astype(np.uint16)}
+    kids = {"i8": W.dataset(cols["i8"], chunk=8192, gzip=6, shuffle=True),
+            "i4": W.dataset(cols["i4"], chunk=50000, gzip=1),
+            "f8": W.dataset(cols["f8"], chunk=4096, gzip=4, shuffle=True, fletcher=True),
+            "u2": W.dataset(cols["u2"], chunk=100000, gzip=6, fletcher=True)}
+    path = str(tmp_path / "big.h5")
+    W.finish(W.group(kids), path)
+    calls = []
+    real = h5mini.Dataset._decode_native
+
+    def spy(self, hits, lo, hi, out):
+        ok = real(self, hits, lo, hi, out)
+        calls.append(ok)
+        return ok
+    with h5mini.File(path) as f:
+        for name, want in cols.items():
+            for lo, hi in [(0, want.size), (12345, want.size - 777), (want.size // 2, want.size // 2 + 5)]:
+                monkeypatch.setattr(h5mini.Dataset, "_decode_native", spy)
+                got = f[name].read(lo, hi)
+                monkeypatch.setattr(h5mini.Dataset, "_decode_native", lambda self, *a: False)
+                ref = f[name].read(lo, hi)
+                assert got.dtype == ref.dtype and np.array_equal(got, ref) and np.array_equal(got, want[lo:hi]), (name, lo, hi)
+    assert calls.count(True) == 8 and calls.count(False) == 4          # whole columns and long ranges natively, 5-element reads not
