@@ -45,26 +45,74 @@ class PKCool:
             raise FileNotFoundError(path)
         z = np.load(path, allow_pickle=False)
         self.path = path
+        self._z = z
+        self._cache = {}
         self.binsize = int(z["binsize"])
         self.chromnames = [str(s) for s in z["chrom_names"]]
         self.chrom_lengths = z["chrom_lengths"].astype(np.int64)      # bp
         self.chrom_offset = z["chrom_offset"].astype(np.int64)        # bins, len nchrom+1
-        self.bin1_id = z["bin1_id"]
-        self.bin2_id = z["bin2_id"]
-        self.count = z["count"]
-        # optional narrow pixel columns (bin2 - bin1 and count as uint16), written when every
-        # pixel is representable: half the bytes to move to the GPU
-        self.delta16 = z["delta16"] if "delta16" in z.files else None
-        self.count16 = z["count16"] if "count16" in z.files else None
-        # optional packed pixel rows, one blob per chromosome (peakachu_b200.rowpack): what crosses the bus
+        # The pixel columns (bin1_id, bin2_id, count; optionally delta16 / count16 = bin2 - bin1 and count as
+        # uint16, written when every pixel is representable; optionally one blob of packed pixel rows per
+        # chromosome, peakachu_b200.rowpack: what crosses the bus) are mapped on first use: a scoring run that
+        # finds its packed rows never touches the plain columns, which are ten times the bytes.
         self.rows_nd = int(z["rows_nd"]) if "rows_nd" in z.files else 0
-        self._rows = {int(k[len("rows_"):]): z[k] for k in z.files if k.startswith("rows_") and k != "rows_nd"}
+        self._row_keys = {int(k[len("rows_"):]): k for k in z.files if k.startswith("rows_") and k != "rows_nd"}
         self.weight_columns = {k[len("bins_"):]: z[k] for k in z.files if k.startswith("bins_")}
         # weight columns cooler would invert (column attribute `divisive_weights`, e.g. hic2cool's KR / VC)
         self.divisive = {str(s) for s in z["divisive_columns"]} if "divisive_columns" in z.files else set()
-        # pixel range of each chromosome (bin1 sorted, intra-chromosomal only)
-        self._pix_lo = np.searchsorted(self.bin1_id, self.chrom_offset[:-1], side="left")
-        self._pix_hi = np.searchsorted(self.bin1_id, self.chrom_offset[1:], side="left")
+
+    def _col(self, key: str):
+        """Column ``key`` of the container (None when absent). Members stored without compression (what ``write``
+        produces) are memory-mapped in place -- no copy, no CRC pass; anything else is read through numpy."""
+        if key in self._cache:
+            return self._cache[key]
+        a = None
+        if key in self._z.files:
+            a = self._map_member(key + ".npy")
+            if a is None:
+                a = self._z[key]
+        self._cache[key] = a
+        return a
+
+    def _map_member(self, member: str):
+        import struct
+        import zipfile
+        from numpy.lib import format as npf
+        try:
+            info = self._z.zip.getinfo(member)
+            if info.compress_type != zipfile.ZIP_STORED:
+                return None
+            with open(self.path, "rb") as fh:
+                fh.seek(info.header_offset)
+                hdr = fh.read(30)
+                if hdr[:4] != b"PK\x03\x04":
+                    return None
+                n_name, n_extra = struct.unpack("<HH", hdr[26:30])
+                fh.seek(info.header_offset + 30 + n_name + n_extra)
+                major, minor = npf.read_magic(fh)
+                shape, fortran, dtype = (npf.read_array_header_1_0 if major == 1 else npf.read_array_header_2_0)(fh)
+                if dtype.hasobject or fortran or len(shape) != 1:
+                    return None
+                off = fh.tell()
+            if shape[0] == 0:
+                return np.zeros(0, dtype=dtype)
+            return np.memmap(self.path, dtype=dtype, mode="r", offset=off, shape=shape)
+        except Exception:
+            return None
+
+    bin1_id = property(lambda self: self._col("bin1_id"))
+    bin2_id = property(lambda self: self._col("bin2_id"))
+    count = property(lambda self: self._col("count"))
+    delta16 = property(lambda self: self._col("delta16"))
+    count16 = property(lambda self: self._col("count16"))
+
+    def _pix_range(self, i: int):
+        """pixel range of chromosome i (bin1 sorted, intra-chromosomal only)"""
+        if "_pix" not in self._cache:
+            self._cache["_pix"] = (np.searchsorted(self.bin1_id, self.chrom_offset[:-1], side="left"),
+                                   np.searchsorted(self.bin1_id, self.chrom_offset[1:], side="left"))
+        lo, hi = self._cache["_pix"]
+        return int(lo[i]), int(hi[i])
 
     # -- writer -----------------------------------------------------------
     @staticmethod
@@ -117,7 +165,7 @@ class PKCool:
     def upper_pixels(self, chrom: str):
         """(bin1, bin2, count) int32 arrays with chromosome-local bin ids."""
         i = self._cid(chrom)
-        lo, hi = self._pix_lo[i], self._pix_hi[i]
+        lo, hi = self._pix_range(i)
         off = self.chrom_offset[i]
         b1 = (self.bin1_id[lo:hi] - off).astype(np.int32)
         b2 = (self.bin2_id[lo:hi] - off).astype(np.int32)
@@ -127,7 +175,7 @@ class PKCool:
         """(bin1_offset int64[n+1] rebased to 0, bin2 int32, count int32): cooler's
         ``indexes/bin1_offset`` restricted to the chromosome plus its pixel columns."""
         i = self._cid(chrom)
-        lo, hi = self._pix_lo[i], self._pix_hi[i]
+        lo, hi = self._pix_range(i)
         off = self.chrom_offset[i]
         n = self.nbins(chrom)
         rp = np.searchsorted(self.bin1_id[lo:hi], np.arange(off, off + n + 1), side="left").astype(np.int64)
@@ -140,7 +188,7 @@ class PKCool:
         if self.delta16 is None or self.count16 is None:
             return None
         i = self._cid(chrom)
-        lo, hi = self._pix_lo[i], self._pix_hi[i]
+        lo, hi = self._pix_range(i)
         off = self.chrom_offset[i]
         n = self.nbins(chrom)
         rp = np.searchsorted(self.bin1_id[lo:hi], np.arange(off, off + n + 1), side="left").astype(np.int64)
@@ -154,7 +202,8 @@ class PKCool:
         container holds them and they cover ``nd_min`` distances, else None."""
         if self.rows_nd < nd_min:
             return None
-        return self._rows.get(self._cid(chrom))
+        key = self._row_keys.get(self._cid(chrom))
+        return None if key is None else np.asarray(self._col(key))
 
     def weights(self, chrom: str, name: str) -> np.ndarray:
         if name not in self.weight_columns:
