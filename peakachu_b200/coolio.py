@@ -429,6 +429,10 @@ class H5Cool:
     def upper_pixels_csr(self, chrom: str):
         return self._fetch(chrom)
 
+    def prefetch(self, chrom: str) -> None:
+        """Read and keep the chromosome's pixel columns (the next upper_pixels* call for it is served from memory)."""
+        self._fetch(chrom)
+
     def upper_pixels(self, chrom: str):
         rp, b2, cnt = self._fetch(chrom)
         b1 = np.repeat(np.arange(rp.size - 1, dtype=np.int32), np.diff(rp))

@@ -16,7 +16,7 @@ numpy + zlib:
 * datasets with fixed-point, floating-point, fixed-length string and enum
   element types; layouts compact, contiguous and chunked (v1 B-tree chunk
   index; for the version-4 layout message: single-chunk, implicit and
-  fixed-array indexes); filters deflate, shuffle and fletcher32,
+  fixed-array indexes, paged or not); filters deflate, shuffle and fletcher32,
 * scalar numeric / fixed-string attributes (enough for cooler's ``bin-size``).
 
 Anything else raises ``H5Unsupported`` naming the feature, never a silent guess.
@@ -53,6 +53,44 @@ def _pool():
 
 class H5Error(Exception):
     pass
+
+
+def lookup3(data: bytes, init: int = 0) -> int:
+    """Bob Jenkins' lookup3 ``hashlittle``: the checksum HDF5 puts behind its version-2 metadata structures
+    (``H5_checksum_metadata``). Known answer: ``lookup3(b"Four score and seven years ago") == 0x17770551``."""
+    M = 0xFFFFFFFF
+
+    def rot(x, k):
+        return ((x << k) | (x >> (32 - k))) & M
+    n = len(data)
+    a = b = c = (0xDEADBEEF + n + init) & M
+    i = 0
+    while n - i > 12:
+        a = (a + int.from_bytes(data[i:i + 4], "little")) & M
+        b = (b + int.from_bytes(data[i + 4:i + 8], "little")) & M
+        c = (c + int.from_bytes(data[i + 8:i + 12], "little")) & M
+        a = (a - c) & M; a ^= rot(c, 4); c = (c + b) & M
+        b = (b - a) & M; b ^= rot(a, 6); a = (a + c) & M
+        c = (c - b) & M; c ^= rot(b, 8); b = (b + a) & M
+        a = (a - c) & M; a ^= rot(c, 16); c = (c + b) & M
+        b = (b - a) & M; b ^= rot(a, 19); a = (a + c) & M
+        c = (c - b) & M; c ^= rot(b, 4); b = (b + a) & M
+        i += 12
+    tail = data[i:]
+    if not tail:
+        return c
+    tail = tail + b"\0" * (12 - len(tail))
+    a = (a + int.from_bytes(tail[0:4], "little")) & M
+    b = (b + int.from_bytes(tail[4:8], "little")) & M
+    c = (c + int.from_bytes(tail[8:12], "little")) & M
+    c ^= b; c = (c - rot(b, 14)) & M
+    a ^= c; a = (a - rot(c, 11)) & M
+    b ^= a; b = (b - rot(a, 25)) & M
+    c ^= b; c = (c - rot(b, 16)) & M
+    a ^= c; a = (a - rot(c, 4)) & M
+    b ^= a; b = (b - rot(a, 14)) & M
+    c ^= b; c = (c - rot(b, 24)) & M
+    return c
 
 
 class H5Unsupported(H5Error):
@@ -572,19 +610,51 @@ class Dataset:
                 db = b.base + b.off(a + 8 + b.sl)
                 if d[db:db + 4] != b"FADB":
                     raise H5Error("%s: bad fixed array data block" % self.name)
-                if nent > (1 << pbits):
-                    raise H5Unsupported("%s: paged fixed array chunk index" % self.name)
-                q = db + 6 + b.so
-                for i, idx in enumerate(np.ndindex(*grid)):
-                    e = q + i * esize
+                def entry(e, idx):
                     ca = b.off(e)
                     if ca == UNDEF:
-                        continue
+                        return
                     if client == 1:                  # filtered chunks: address, size, mask
                         sw = esize - b.so - 4
                         out.append((tuple(i_ * c for i_, c in zip(idx, cdims)), ca, b.u(e + b.so, sw), b.u(e + b.so + sw, 4)))
                     else:
                         out.append((tuple(i_ * c for i_, c in zip(idx, cdims)), ca, cbytes, 0))
+                cells = list(np.ndindex(*grid))
+                if len(cells) > nent:
+                    raise H5Error("%s: fixed array holds %d entries for %d chunks" % (self.name, nent, len(cells)))
+                if len(self.shape) > 1 and nent != len(cells):
+                    # sized for the maximum dimensions: entries are numbered over that grid, not the current one
+                    raise H5Unsupported("%s: fixed array of a multi-dimensional dataset below its maximum size" % self.name)
+                per_page = 1 << pbits
+                if nent <= per_page:                 # the elements sit in the data block itself
+                    q = db + 6 + b.so
+                    for i, idx in enumerate(cells):
+                        entry(q + i * esize, idx)
+                else:
+                    # paged data block: a bitmap of initialised pages closes the prefix; the pages follow it back
+                    # to back, 2^pbits elements + a checksum each (the last one holds the remainder). Every
+                    # checksum on the way is verified (lookup3), so a file laid out differently from this
+                    # reading of the format fails here instead of yielding chunk addresses from the wrong bytes.
+                    npages = -(-nent // per_page)
+                    nbitmap = (npages + 7) // 8
+                    bm = db + 6 + b.so
+                    prefix_end = bm + nbitmap
+                    if b.u(prefix_end, 4) != lookup3(bytes(d[db:prefix_end])):
+                        raise H5Error("%s: fixed array data block checksum mismatch" % self.name)
+                    first_page = prefix_end + 4
+                    page_bytes = per_page * esize + 4
+                    for pg in range(npages):
+                        if not (d[bm + pg // 8] >> (7 - pg % 8)) & 1:        # page never written: all chunks absent
+                            continue
+                        lo_e = pg * per_page
+                        cnt = min(per_page, nent - lo_e)
+                        q = first_page + pg * page_bytes
+                        if q + cnt * esize + 4 > len(d):
+                            raise H5Error("%s: fixed array page beyond the end of the file" % self.name)
+                        if b.u(q + cnt * esize, 4) != lookup3(bytes(d[q:q + cnt * esize])):
+                            raise H5Error("%s: fixed array page %d checksum mismatch" % (self.name, pg))
+                        for i in range(lo_e, min(lo_e + cnt, len(cells))):
+                            entry(q + (i - lo_e) * esize, cells[i])
         out.sort(key=lambda t: t[0])
         self._chunks = out
         return out

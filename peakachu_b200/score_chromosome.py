@@ -15,12 +15,35 @@ def main(args):
     if os.path.exists(args.output):                       # score_chromosome.py:11-12
         os.remove(args.output)
 
-    flat, _ = load_model(args.model)                      # :14
+    # :14 -- unpickling a 100-tree forest is ~0.1 s of interpreter time; the file's pixel columns are inflated by the
+    # library's host threads meanwhile (H5Cool keeps the fetched chromosome for from_map below)
+    import threading
+    loaded = {}
+
+    def _load():
+        try:
+            loaded["flat"] = load_model(args.model)[0]
+        except BaseException as e:                        # re-raised on the calling thread
+            loaded["error"] = e
+    loader = threading.Thread(target=_load, name="pk-model-load")
+    loader.start()
+    map_error = None
+    try:
+        Lib = coolio.open_map(args.path)                  # :33-34 (.hic is outside this path)
+        if hasattr(Lib, "prefetch"):
+            Lib.prefetch(args.chrom)
+    except Exception as e:
+        map_error = e
+    loader.join()
+    if "error" in loaded:                                 # the reference fails on the model first
+        raise loaded["error"]
+    if map_error is not None:
+        raise map_error
+    flat = loaded["flat"]
     correct = False if args.clr_weight_name.lower() == "raw" else args.clr_weight_name   # :17-20
     width = flat.width                                    # :23
     device = int(getattr(args, "device", 0) or 0)
 
-    Lib = coolio.open_map(args.path)                      # :33-34 (.hic is outside this path)
     ccname = args.chrom
     cikada = "chr" + ccname.lstrip("chr")                 # :37-38
 

@@ -309,7 +309,9 @@ class Writer2(Writer):
         return self.alloc(b"OHDR" + struct.pack("<BB", 2, 0x22) + b"\0" * 16 + struct.pack("<I", len(head)) + head + b"\0" * 4)
 
     def dataset(self, arr, chunk=None, gzip=None, shuffle=False, fletcher=False, unlimited=False,
-                enum=None, attrs=None, compact=False, skip_filter_on=None) -> int:
+                enum=None, attrs=None, compact=False, skip_filter_on=None, page_bits=10, absent_pages=()) -> int:
+        """``page_bits``: a fixed-array chunk index with more than 2**page_bits entries is written paged (libhdf5's
+        default is 10); ``absent_pages``: pages left uninitialised (their chunks do not exist and read as zeros)."""
         arr = np.ascontiguousarray(arr)
         msgs = [(0x01, self.space_msg(arr.shape, unlimited)), (0x03, self.dtype_msg(arr.dtype, enum)),
                 (0x05, struct.pack("<BB", 3, 0x09))]
@@ -358,13 +360,33 @@ class Writer2(Writer):
                 first = self.alloc(b"".join(bytes(self.buf[self.base + a: self.base + a + n]) for a, n, _ in records))
                 lay = head + struct.pack("<BQ", 2, first)
             else:                                      # fixed array of (address, size, mask) entries
+                from peakachu_b200.h5mini import lookup3
                 esize = 8 + 4 + 4
                 fahd = self.alloc(b"\0" * (4 + 4 + 8 + 8 + 4))
-                body = b"FADB" + struct.pack("<BBQ", 0, 1, fahd)
-                body += b"".join(struct.pack("<QII", a, n, m) for a, n, m in records) + b"\0" * 4
+                ents = [struct.pack("<QII", a, n, m) for a, n, m in records]
+                per_page = 1 << page_bits
+                if len(ents) <= per_page:
+                    body = b"FADB" + struct.pack("<BBQ", 0, 1, fahd) + b"".join(ents) + b"\0" * 4
+                else:
+                    # paged: prefix = signature .. page bitmap (MSB first) + checksum, then the pages, each
+                    # 2**page_bits entries (the last one the remainder) + checksum; an absent page keeps its room
+                    npages = -(-len(ents) // per_page)
+                    bitmap = bytearray((npages + 7) // 8)
+                    pages = b""
+                    for pg in range(npages):
+                        part = b"".join(ents[pg * per_page:(pg + 1) * per_page])
+                        if pg in absent_pages:
+                            pages += b"\xAA" * (len(part) + 4)
+                        else:
+                            bitmap[pg // 8] |= 0x80 >> (pg % 8)
+                            pages += part + struct.pack("<I", lookup3(part))
+                            if pg < npages - 1:
+                                assert len(part) == per_page * esize
+                    prefix = b"FADB" + struct.pack("<BBQ", 0, 1, fahd) + bytes(bitmap)
+                    body = prefix + struct.pack("<I", lookup3(prefix)) + pages
                 fadb = self.alloc(body)
-                self.buf[self.base + fahd: self.base + fahd + 28] = b"FAHD" + struct.pack("<BBBBQQ", 0, 1, esize, 10, len(records), fadb) + b"\0" * 4
-                lay = head + struct.pack("<BBQ", 3, 10, fahd)
+                self.buf[self.base + fahd: self.base + fahd + 28] = b"FAHD" + struct.pack("<BBBBQQ", 0, 1, esize, page_bits, len(records), fadb) + b"\0" * 4
+                lay = head + struct.pack("<BBQ", 3, page_bits, fahd)
             msgs.append((0x08, lay))
         split = None
         if attrs:

@@ -54,11 +54,7 @@ def test_cool_round_trip(tmp_path, userblock, group, chunk, latest):
     uri = path + ("::/" + group if group else "")
     lib = coolio.open_map(uri)
     assert isinstance(lib, coolio.H5Cool)
-    if latest and chunk == 37:
-        # more than 1024 chunks: libhdf5 pages the fixed-array index, which the subset reader refuses loudly
-        with pytest.raises(h5mini.H5Unsupported, match="paged fixed array"):
-            lib.upper_pixels(chroms[0].name)
-        return
+    # (latest, chunk 37: more than 1024 chunks per pixel column, so the fixed-array index is paged like libhdf5 pages it)
     assert lib.chromnames == [c.name for c in chroms]
     assert lib.binsize == 10000
     off = 0
@@ -249,3 +245,41 @@ def test_native_chunk_decoder_equals_the_python_one(tmp_path, latest, monkeypatc
                 ref = f[name].read(lo, hi)
                 assert got.dtype == ref.dtype and np.array_equal(got, ref) and np.array_equal(got, want[lo:hi]), (name, lo, hi)
     assert calls.count(True) == 8 and calls.count(False) == 4          # whole columns and long ranges natively, 5-element reads not
+
+
+def test_lookup3_known_answers():
+    """HDF5's metadata checksum (Jenkins lookup3 hashlittle) against the answers printed in lookup3.c's self-test."""
+    assert h5mini.lookup3(b"") == 0xdeadbeef
+    assert h5mini.lookup3(b"", 0xdeadbeef) == 0xbd5b7dde
+    assert h5mini.lookup3(b"Four score and seven years ago") == 0x17770551
+    assert h5mini.lookup3(b"Four score and seven years ago", 1) == 0xcd628161
+
+
+def test_paged_fixed_array_chunk_index(tmp_path):
+    """Version-4 layout with a fixed-array index of more entries than a page holds: pages behind the data block,
+    a bitmap of the pages that exist, a checksum per page. Uninitialised pages read as zeros (absent chunks);
+    a page whose checksum does not match fails loudly."""
+    rng = np.random.default_rng(3)
+    a = rng.integers(1, 1000, 1003).astype(np.int32)
+    for bits, absent in ((2, ()), (3, (1,)), (4, (0, 6)), (10, ())):
+        W = h5write.Writer2()
+        path = str(tmp_path / ("p%d.h5" % bits))
+        W.finish(W.group({"x": W.dataset(a, chunk=10, gzip=4, shuffle=True, page_bits=bits, absent_pages=absent)}), path)
+        want = a.copy()
+        for pg in absent:
+            want[pg * (1 << bits) * 10:(pg + 1) * (1 << bits) * 10] = 0
+        with h5mini.File(path) as f:
+            np.testing.assert_array_equal(f["x"].read(), want)
+            np.testing.assert_array_equal(f["x"].read(95, 407), want[95:407])
+    # flip one byte inside the second page of the 2-bit file: the reader must not hand out chunk addresses from it
+    path = str(tmp_path / "p2.h5")
+    raw = bytearray(open(path, "rb").read())
+    at = raw.index(b"FADB")
+    npages = -(-101 // 4)
+    first_page = at + 6 + 8 + (npages + 7) // 8 + 4
+    raw[first_page + (4 * 16 + 4) + 9] ^= 0x40
+    bad = str(tmp_path / "bad.h5")
+    open(bad, "wb").write(raw)
+    with h5mini.File(bad) as f:
+        with pytest.raises(h5mini.H5Error, match="page 1 checksum"):
+            f["x"].read()
