@@ -253,6 +253,18 @@ int pk_h5_decode_chunks(const uint8_t* file, int64_t n_chunks, const int64_t* ch
                         const int64_t* first_elem, int64_t chunk_elems, int32_t elem_size, int32_t deflate,
                         int32_t shuffle, int32_t fletcher32, int64_t lo, int64_t hi, void* out, int32_t n_threads);
 
+/* Host-only: packed pixel rows (the blob of pk_chrom_upload_rows, byte for byte what peakachu_b200/rowpack.py writes)
+ * from the rows of ONE chromosome as a cooler file stores them (score_chromosome.py:42-43 fetches this block through
+ * cooler): bin1_offset int64[n_bins + 1] relative to the first pixel handed in, bin2 as int32 / int64 (bin2_bytes 4 | 8)
+ * genome-wide ids of which bin2_base (the chromosome's first bin) is subtracted -- pixels behind the chromosome are
+ * inter-chromosomal and dropped --, count as int32 / int64 / float64 (count_kind 0 | 1 | 2). Duplicates are summed and
+ * zero counts dropped as utils.tocsr would (utils.py:10-15). Call with out = NULL to learn the size (*needed), then with
+ * a buffer of at least that many bytes. PK_EINVAL names the first offending row: pixels below the diagonal, out of
+ * order, negative, beyond int32 or fractional counts. n_threads 0: all host threads. */
+int pk_rows_pack(const int64_t* bin1_offset, const void* bin2, int32_t bin2_bytes, int64_t bin2_base, const void* count,
+                 int32_t count_kind, int64_t n_bins, int32_t nd_enc, void* out, int64_t capacity, int64_t* needed,
+                 int32_t n_threads);
+
 /* a non-blocking CUDA stream for pk_chrom_create, for callers that do not bring their own
  * (two handles on two streams overlap one chromosome's upload with another's kernels) */
 int pk_stream_create(int device, void** out);

@@ -356,6 +356,7 @@ class H5Cool:
         self._bin2 = g["pixels/bin2_id"]
         self._count = g["pixels/count"]
         self._cache = (None, None)
+        self._raw = (None, None)
 
     def close(self):
         self._f.close()
@@ -386,14 +387,18 @@ class H5Cool:
         # genome-wide 10 kb file): read bin2 / count in blocks of rows and keep the intra-chromosomal
         # pixels of each block only.
         BLOCK = 1 << 24                                       # pixels per block
+        raw = self._raw[1] if self._raw[0] == chrom else None
         kept_b2, kept_cnt, row_counts = [], [], np.zeros(n, dtype=np.int64)
         r0 = 0
         while r0 < n:
             r1 = int(np.searchsorted(rp, rp[r0] + BLOCK, side="right")) - 1
             r1 = min(n, max(r1, r0 + 1))
             a, b = p0 + int(rp[r0]), p0 + int(rp[r1])
-            b2 = self._bin2.read(a, b)
-            cnt = self._count.read(a, b)
+            if raw is not None:                              # already decoded for the packed rows
+                b2, cnt = raw[1][a - p0:b - p0], raw[2][a - p0:b - p0]
+            else:
+                b2 = self._bin2.read(a, b)
+                cnt = self._count.read(a, b)
             if cnt.dtype.kind == "f" and not np.all(cnt == np.rint(cnt)):
                 raise ValueError("%s: non-integer pixel counts; the Poisson filter "
                                  "(scoreUtils.py:59-60) needs raw counts" % self.path)
@@ -429,9 +434,47 @@ class H5Cool:
     def upper_pixels_csr(self, chrom: str):
         return self._fetch(chrom)
 
+    # pixels (cis + trans) of one chromosome's rows up to which the raw columns are held whole for the native packer
+    RAW_LIMIT = 1 << 27
+
+    def _raw_columns(self, chrom: str):
+        """(row pointer int64[n+1] rebased to 0, bin2 as stored (genome-wide ids), count as stored, first bin) of the
+        chromosome's rows, decoded once and kept for the next call; None when the rows hold more than RAW_LIMIT
+        pixels (a genome-wide file with deep inter-chromosomal rows: the block-wise ``_fetch`` bounds the memory)."""
+        if self._raw[0] == chrom:
+            return self._raw[1]
+        i = self._cid(chrom)
+        lo, hi = int(self.chrom_offset[i]), int(self.chrom_offset[i + 1])
+        rp = self._bin1_offset.read(lo, hi + 1).astype(np.int64)
+        p0 = int(rp[0]) if rp.size else 0
+        rp -= p0
+        if rp.size != hi - lo + 1 or np.any(np.diff(rp) < 0):
+            raise ValueError("%s: indexes/bin1_offset is not a row pointer of the pixel table" % self.path)
+        out = None
+        if int(rp[-1]) <= self.RAW_LIMIT:
+            out = (rp, self._bin2.read(p0, p0 + int(rp[-1])), self._count.read(p0, p0 + int(rp[-1])), lo)
+        self._raw = (chrom, out)
+        return out
+
     def prefetch(self, chrom: str) -> None:
-        """Read and keep the chromosome's pixel columns (the next upper_pixels* call for it is served from memory)."""
-        self._fetch(chrom)
+        """Decode and keep the chromosome's pixel columns (the next upper_pixels* call for it starts from memory)."""
+        if self._raw_columns(chrom) is None:
+            self._fetch(chrom)
+
+    def upper_pixels_rows(self, chrom: str, nd_min: int):
+        """Packed pixel rows of the chromosome covering ``nd_min`` distances (uint8 blob for ``pk_chrom_upload_rows``),
+        packed by the library straight from the file's columns (``pk_rows_pack``: trans pixels dropped, the
+        symmetric-upper / order / count checks of ``_fetch`` made on the way); None when the rows are too many to
+        hold whole -- the caller then takes the block-wise columns."""
+        from . import rowpack
+        raw = self._raw_columns(chrom)
+        if raw is None:
+            return None
+        rp, b2, cnt, lo = raw
+        try:
+            return rowpack.pack_rows_native(rp, b2, cnt, rp.size - 1, int(nd_min), bin2_base=lo)
+        except ValueError as e:
+            raise ValueError("%s: %s" % (self.path, e)) from None
 
     def upper_pixels(self, chrom: str):
         rp, b2, cnt = self._fetch(chrom)

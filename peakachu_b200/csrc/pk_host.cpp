@@ -399,3 +399,186 @@ extern "C" int pk_h5_decode_chunks(const uint8_t* file, int64_t n_chunks, const 
     }
     return PK_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Packed pixel rows straight from cooler's columns (the format of pk_chrom_upload_rows; the same bytes
+// peakachu_b200/rowpack.py::pack_rows writes): one threaded pass counts every row's band pixels, escapes and far
+// pixels, a serial prefix over the rows places them, a second threaded pass writes the sections. The columns are
+// the rows of ONE chromosome as the file stores them: genome-wide bin2 ids (pixels whose bin2 lies behind the
+// chromosome are inter-chromosomal and dropped, score_chromosome.py:42-43 fetches the cis block), duplicates summed
+// and zero counts dropped as utils.tocsr would (utils.py:10-15).
+// ---------------------------------------------------------------------------
+namespace {
+
+struct RowsIn {
+    const int64_t* rp;      // [n + 1], relative to the first pixel handed in
+    const void* b2;
+    int b2_bytes;           // 4 | 8
+    int64_t b2_base;        // first bin of the chromosome (subtracted)
+    const void* cnt;
+    int cnt_kind;           // 0: int32, 1: int64, 2: float64
+    int64_t n;
+    int64_t nd;
+};
+
+struct RowTally { uint32_t band; uint32_t esc; int64_t far; };
+
+enum { ROWS_OK = 0, ROWS_LOWER = 1, ROWS_ORDER = 2, ROWS_NEG = 3, ROWS_BIG = 4, ROWS_FRAC = 5 };
+
+inline int64_t rows_b2(const RowsIn& in, int64_t p) {
+    return (in.b2_bytes == 8 ? static_cast<const int64_t*>(in.b2)[p] : (int64_t)static_cast<const int32_t*>(in.b2)[p]) - in.b2_base;
+}
+inline bool rows_cnt(const RowsIn& in, int64_t p, int64_t* out) {       // false: not an integer
+    if (in.cnt_kind == 0) { *out = static_cast<const int32_t*>(in.cnt)[p]; return true; }
+    if (in.cnt_kind == 1) { *out = static_cast<const int64_t*>(in.cnt)[p]; return true; }
+    const double v = static_cast<const double*>(in.cnt)[p];
+    if (!(v == std::floor(v)) || !(std::fabs(v) < 9.0e18)) return false;
+    *out = (int64_t)v;
+    return true;
+}
+
+// walks the de-duplicated cis pixels of row x in order: f(d, count) for count > 0
+template <class F>
+inline int rows_walk(const RowsIn& in, int64_t x, F&& f) {
+    int64_t p = in.rp[x];
+    const int64_t pe = in.rp[x + 1];
+    int64_t prev = -1;
+    while (p < pe) {
+        const int64_t c2 = rows_b2(in, p);
+        if (c2 >= in.n) {                                   // the rest of the row is inter-chromosomal (sorted by bin2)
+            for (int64_t q = p + 1; q < pe; ++q)
+                if (rows_b2(in, q) < in.n) return ROWS_ORDER;
+            break;
+        }
+        if (c2 < x) return ROWS_LOWER;
+        if (c2 < prev) return ROWS_ORDER;
+        int64_t sum = 0;
+        while (p < pe && rows_b2(in, p) == c2) {            // duplicates are summed
+            int64_t v;
+            if (!rows_cnt(in, p, &v)) return ROWS_FRAC;
+            if (v < 0) return ROWS_NEG;
+            if (v > INT32_MAX || (sum += v) > INT32_MAX) return ROWS_BIG;
+            ++p;
+        }
+        prev = c2;
+        if (sum > 0) f(c2 - x, sum);
+    }
+    return ROWS_OK;
+}
+
+inline int64_t align16(int64_t v) { return (v + 15) / 16 * 16; }
+
+template <class F>
+void rows_parallel(int64_t n, int n_threads, F&& body) {
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(nt, 32), n / 256 + 1));
+    std::atomic<int64_t> next(0);
+    const int64_t step = 128;
+    auto work = [&]() {
+        for (;;) {
+            const int64_t x0 = next.fetch_add(step);
+            if (x0 >= n) return;
+            body(x0, std::min(n, x0 + step));
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+}
+
+}  // namespace
+
+extern "C" int pk_rows_pack(const int64_t* bin1_offset, const void* bin2, int32_t bin2_bytes, int64_t bin2_base,
+                            const void* count, int32_t count_kind, int64_t n_bins, int32_t nd_enc, void* out,
+                            int64_t capacity, int64_t* needed, int32_t n_threads) {
+    if (!bin1_offset || n_bins < 0 || nd_enc < 1 || (bin2_bytes != 4 && bin2_bytes != 8) || count_kind < 0 || count_kind > 2 ||
+        !needed || bin1_offset[0] < 0 || (bin1_offset[n_bins] > bin1_offset[0] && (!bin2 || !count))) {
+        pk_set_error("pk_rows_pack: bad argument");
+        return PK_EINVAL;
+    }
+    for (int64_t x = 0; x < n_bins; ++x)
+        if (bin1_offset[x + 1] < bin1_offset[x]) {
+            pk_set_error("pk_rows_pack: bin1_offset is not a row pointer (row %lld)", (long long)x);
+            return PK_EINVAL;
+        }
+    const RowsIn in{bin1_offset, bin2, bin2_bytes, bin2_base, count, count_kind, n_bins, nd_enc};
+    const int64_t n = n_bins, W = (nd_enc + 31) / 32;
+    std::vector<RowTally> tally((size_t)n);
+    std::atomic<int> bad(0);
+    std::atomic<int64_t> bad_row(-1);
+    rows_parallel(n, n_threads, [&](int64_t x0, int64_t x1) {
+        for (int64_t x = x0; x < x1 && !bad.load(std::memory_order_relaxed); ++x) {
+            RowTally t{0, 0, 0};
+            const int rc = rows_walk(in, x, [&](int64_t d, int64_t c) {
+                if (d < in.nd) { ++t.band; t.esc += c >= 255; } else ++t.far;
+            });
+            if (rc != ROWS_OK) { bad.store(rc); bad_row.store(x); return; }
+            tally[(size_t)x] = t;
+        }
+    });
+    if (bad.load()) {
+        static const char* why[] = {"", "pixels below the diagonal (storage-mode is not symmetric-upper)", "pixels are not in cooler order (bin1, then bin2)",
+                                    "negative pixel counts", "pixel counts outside int32", "non-integer pixel counts; the Poisson filter (scoreUtils.py:59-60) needs raw counts"};
+        pk_set_error("pk_rows_pack: row %lld: %s", (long long)bad_row.load(), why[bad.load()]);
+        return PK_EINVAL;
+    }
+    // placement
+    std::vector<int64_t> band_at((size_t)n + 1), esc_at((size_t)n + 1), far_at((size_t)n + 1);
+    int64_t nb = 0, ne = 0, nf = 0;
+    for (int64_t x = 0; x < n; ++x) {
+        band_at[(size_t)x] = nb; esc_at[(size_t)x] = ne; far_at[(size_t)x] = nf;
+        nb += tally[(size_t)x].band; ne += tally[(size_t)x].esc; nf += tally[(size_t)x].far;
+    }
+    band_at[(size_t)n] = nb; esc_at[(size_t)n] = ne; far_at[(size_t)n] = nf;
+    if (nb >= (1LL << 32)) {
+        pk_set_error("pk_rows_pack: more than 2^32 band pixels in one chromosome");
+        return PK_EUNSUPPORTED;
+    }
+    const int64_t sizes[7] = {n * W * 4, (n + 1) * 4, nb, 3 * ne * 4, (n + 1) * 8, nf * 4, nf * 4};
+    int64_t offs[7], at = 16 * 8;
+    for (int i = 0; i < 7; ++i) { at = align16(at); offs[i] = at; at += sizes[i]; }
+    const int64_t total = align16(at);
+    *needed = total;
+    if (!out || capacity < total) {
+        if (out) pk_set_error("pk_rows_pack: the blob needs %lld bytes, the buffer holds %lld", (long long)total, (long long)capacity);
+        return out ? PK_ECAPACITY : PK_OK;
+    }
+    uint8_t* blob = static_cast<uint8_t*>(out);
+    const int64_t head[16] = {PK_ROWS_MAGIC, n, nd_enc, W, nb, ne, nf, offs[0], offs[1], offs[2], offs[3], offs[4], offs[5], offs[6], total, 0};
+    memcpy(blob, head, sizeof head);
+    // alignment gaps and the tail are zero, like the Python packer's
+    int64_t end = 128;
+    for (int i = 0; i < 7; ++i) { memset(blob + end, 0, (size_t)(offs[i] - end)); end = offs[i] + sizes[i]; }
+    memset(blob + end, 0, (size_t)(total - end));
+    uint32_t* bits = reinterpret_cast<uint32_t*>(blob + offs[0]);
+    uint32_t* cnt_off = reinterpret_cast<uint32_t*>(blob + offs[1]);
+    uint8_t* cnt8 = blob + offs[2];
+    int32_t* esc = reinterpret_cast<int32_t*>(blob + offs[3]);
+    int64_t* far_off = reinterpret_cast<int64_t*>(blob + offs[4]);
+    int32_t* far_b2 = reinterpret_cast<int32_t*>(blob + offs[5]);
+    int32_t* far_cnt = reinterpret_cast<int32_t*>(blob + offs[6]);
+    cnt_off[n] = (uint32_t)nb;
+    far_off[n] = nf;
+    rows_parallel(n, n_threads, [&](int64_t x0, int64_t x1) {
+        for (int64_t x = x0; x < x1; ++x) {
+            uint32_t* brow = bits + x * W;
+            for (int64_t k = 0; k < W; ++k) brow[k] = 0;
+            int64_t ib = band_at[(size_t)x], ie = esc_at[(size_t)x], jf = far_at[(size_t)x];
+            cnt_off[x] = (uint32_t)ib;
+            far_off[x] = jf;
+            rows_walk(in, x, [&](int64_t d, int64_t c) {
+                if (d < in.nd) {
+                    brow[d >> 5] |= 1u << (d & 31);
+                    cnt8[ib++] = (uint8_t)std::min<int64_t>(c, 255);
+                    if (c >= 255) { esc[ie] = (int32_t)x; esc[ne + ie] = (int32_t)d; esc[2 * ne + ie] = (int32_t)c; ++ie; }
+                } else {
+                    far_b2[jf] = (int32_t)(x + d);
+                    far_cnt[jf] = (int32_t)c;
+                    ++jf;
+                }
+            });
+        }
+    });
+    return PK_OK;
+}

@@ -145,3 +145,40 @@ def unpack_rows(blob):
     rows, b2, cc = rows[order], b2[order], cc[order]
     rp = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n))]).astype(np.int64)
     return rp, b2.astype(np.int32), cc.astype(np.int32)
+
+
+def pack_rows_native(bin1_offset, bin2, count, n_bins: int, nd_enc: int, bin2_base: int = 0, n_threads: int = 0) -> np.ndarray:
+    """``pack_rows`` by the library (``pk_rows_pack``: two threaded passes over the columns, no temporaries): the
+    same blob, from the rows of one chromosome as a cooler file stores them -- ``bin2`` may hold genome-wide ids
+    (``bin2_base`` = the chromosome's first bin is subtracted; pixels behind the chromosome are dropped) and keeps
+    the file's integer width, ``count`` its type."""
+    import ctypes as C
+
+    from . import _lib
+    L = _lib.lib()
+    rp = np.ascontiguousarray(bin1_offset, dtype=np.int64)
+    if rp.size != int(n_bins) + 1:
+        raise ValueError("bin1_offset must have n_bins + 1 entries")
+    b2 = np.ascontiguousarray(bin2)
+    if b2.dtype not in (np.dtype(np.int32), np.dtype(np.int64)):
+        b2 = b2.astype(np.int64)
+    cnt = np.ascontiguousarray(count)
+    kind = {np.dtype(np.int32): 0, np.dtype(np.int64): 1, np.dtype(np.float64): 2}.get(cnt.dtype)
+    if kind is None:
+        if cnt.dtype.kind == "u" and cnt.dtype.itemsize == 8 and cnt.size and int(cnt.max()) > np.iinfo(np.int64).max:
+            raise ValueError("pixel counts outside int32")
+        cnt = cnt.astype(np.float64 if cnt.dtype.kind == "f" else np.int64)
+        kind = 2 if cnt.dtype.kind == "f" else 1
+    if b2.size != cnt.size or (rp.size and int(rp[-1]) > b2.size):
+        raise ValueError("bin1_offset points behind the pixel columns")
+    need = C.c_int64()
+    args = (_lib.ptr(rp, _lib.c_i64p), C.c_void_p(b2.ctypes.data), b2.dtype.itemsize, int(bin2_base),
+            C.c_void_p(cnt.ctypes.data), kind, int(n_bins), int(nd_enc))
+    rc = L.pk_rows_pack(*args, None, 0, C.byref(need), int(n_threads))
+    if rc != 0:
+        raise ValueError(L.pk_last_error().decode("utf-8", "replace"))
+    blob = np.empty(need.value, dtype=np.uint8)
+    rc = L.pk_rows_pack(*args, C.c_void_p(blob.ctypes.data), blob.size, C.byref(need), int(n_threads))
+    if rc != 0:
+        raise ValueError(L.pk_last_error().decode("utf-8", "replace"))
+    return blob

@@ -283,3 +283,44 @@ def test_paged_fixed_array_chunk_index(tmp_path):
     with h5mini.File(bad) as f:
         with pytest.raises(h5mini.H5Error, match="page 1 checksum"):
             f["x"].read()
+
+
+@pytest.mark.parametrize("latest", [False, True])
+def test_packed_rows_straight_from_the_file(tmp_path, latest):
+    """H5Cool.upper_pixels_rows: the file's columns (genome-wide int64 bin2 ids, trans pixels, the file's count type)
+    packed by pk_rows_pack are the blob rowpack.pack_rows makes of the chromosome's cis columns; the plain columns
+    asked for afterwards come from the same decoded arrays; odd files fail as loudly on this path."""
+    from peakachu_b200 import rowpack
+    chroms = _genome()
+    rng = np.random.default_rng(1)
+    path = str(tmp_path / "t.cool")
+    h5write.write_cool(path, chroms, 10000, trans=_trans(chroms, rng), chunk=500, latest=latest)
+    lib = coolio.open_map(path)
+    for c in chroms:
+        for nd in (1, 40, 331):
+            blob = lib.upper_pixels_rows(c.name, nd)
+            order = np.lexsort((c.bin2, c.bin1))
+            rp = np.searchsorted(c.bin1[order], np.arange(c.n + 1)).astype(np.int64)
+            assert np.array_equal(blob, rowpack.pack_rows(rp, c.bin2[order], c.count[order], c.n, nd))
+        rp2, b2, cnt = lib.upper_pixels_csr(c.name)          # served from the columns decoded above
+        assert np.array_equal(rp2, rp) and np.array_equal(b2, c.bin2[order]) and np.array_equal(cnt, c.count[order])
+    # too many pixels to hold whole: the caller is sent to the block-wise columns
+    lib2 = coolio.open_map(path)
+    lib2.RAW_LIMIT = 10
+    assert lib2.upper_pixels_rows(chroms[0].name, 40) is None
+    lib2.prefetch(chroms[0].name)
+    assert lib2._cache[0] == chroms[0].name
+    # loud failures
+    b1 = np.repeat(np.arange(40), 3)
+    b2 = b1 + np.tile(np.arange(3), 40)
+    for cnt, what in ((np.full(120, 2.5), "non-integer"), (np.full(120, 2**31 + 5, np.int64), "outside int32")):
+        p = str(tmp_path / ("odd_%s.cool" % what[:3]))
+        _mini_cool(p, b1, b2, cnt)
+        with pytest.raises(ValueError, match=what):
+            coolio.open_map(p).upper_pixels_rows("chrZ", 8)
+    b2l = b2.copy()
+    b2l[30] = b1[30] - 2
+    p = str(tmp_path / "lower.cool")
+    _mini_cool(p, b1, b2l, np.ones(120, np.int32))
+    with pytest.raises(ValueError, match="below the diagonal"):
+        coolio.open_map(p).upper_pixels_rows("chrZ", 8)
