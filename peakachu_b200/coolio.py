@@ -471,6 +471,8 @@ class H5Cool:
         if raw is None:
             return None
         rp, b2, cnt, lo = raw
+        if nd_min < 1:                                       # any coverage will do (`depth`): PKCool.write's default
+            nd_min = 352
         try:
             return rowpack.pack_rows_native(rp, b2, cnt, rp.size - 1, int(nd_min), bin2_base=lo)
         except ValueError as e:
