@@ -465,6 +465,7 @@ class Dataset:
         if self.shape is None or self.dtype is None or self._layout is None:
             raise H5Error("%s: incomplete dataset header" % name)
         self._chunks = None
+        self._firsts = None
 
     def __len__(self):
         return self.shape[0] if self.shape else 1
@@ -748,7 +749,17 @@ class Dataset:
             return np.frombuffer(buf, dtype=self.dtype).reshape(out_shape).astype(native, copy=True)
         out = np.zeros(out_shape, dtype=native)
         cdims = self._layout[2]
-        hits = [rec for rec in self._chunk_list() if rec[0][0] + cdims[0] > lo and rec[0][0] < hi]
+        chunks = self._chunk_list()
+        if len(shape) == 1:
+            # sorted by first element: the chunks of a range by bisection (a genome-wide cooler column has tens of
+            # thousands of chunks and is read once per chromosome)
+            if self._firsts is None:
+                self._firsts = np.array([rec[0][0] for rec in chunks], dtype=np.int64)
+            i0 = int(np.searchsorted(self._firsts, lo - cdims[0], side="right"))
+            i1 = int(np.searchsorted(self._firsts, hi, side="left"))
+            hits = chunks[i0:i1]
+        else:
+            hits = [rec for rec in chunks if rec[0][0] + cdims[0] > lo and rec[0][0] < hi]
         if self._decode_native(hits, lo, hi, out):
             return out
         # zlib releases the GIL: inflate the chunks of a large read on a few threads (a chromosome of a
