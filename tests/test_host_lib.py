@@ -160,3 +160,19 @@ def test_dropin_constructor_refuses_a_differently_balanced_matrix(tmp_path):
         _check_balanced_matrix(good * 1.5, b1, b2, ch.count, w)
     with pytest.raises(ValueError, match="balances raw_M"):
         Chromosome(good, model=None, raw_M=raw, weights=w * 1.01)           # raised before the device is touched
+
+
+def test_score_chromosome_reports_the_model_before_the_map(tmp_path):
+    """score_chromosome.main unpickles the model on a thread while the map is read; like the reference
+    (score_chromosome.py:14 comes before :33) a missing model is the error of a run that lacks both."""
+    import argparse
+
+    from peakachu_b200 import score_chromosome
+    ns = argparse.Namespace(path=str(tmp_path / "none.cool"), model=str(tmp_path / "none.pkl"), output=str(tmp_path / "o.bedpe"),
+                            chrom="chr1", lower=6, upper=300, minimum_prob=0.5, resolution=10000, clr_weight_name="weight")
+    with pytest.raises(FileNotFoundError, match="none.pkl"):
+        score_chromosome.main(ns)
+    import os
+    ns.model = os.path.join(os.path.dirname(__file__), "golden", "tiny_forest.npz")
+    with pytest.raises(FileNotFoundError, match="none.cool"):
+        score_chromosome.main(ns)
