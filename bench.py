@@ -420,7 +420,6 @@ def main():
     ap.add_argument("--inflight", type=int, default=4, help="chromosomes in flight (streams) of the device-resident `value` pass")
     ap.add_argument("--no-file-e2e", action="store_true", help="skip the file -> bedpe block (N = 1, about 40 s of host work)")
     ap.add_argument("--numa", type=int, default=1, help="N > 1: run each rank on the NUMA node of its GPU (0: leave the affinity alone)")
-    ap.add_argument("--balance-tail", type=int, default=1, help="pk_set_tuning('balance_tail'): the fused kernel shares its last round of candidates out evenly among the CTAs")
     ap.add_argument("--fused", type=int, default=-1, help="pk_set_tuning('fused'): -1 auto, 0 off, 1, 2")
     ap.add_argument("--prune", type=int, default=1, help="pk_set_tuning('prune'): retire pixels that cannot exceed min_prob")
     ap.add_argument("--child-features", type=int, default=-1, help="pk_set_tuning('child_features'): forest walk on the child-feature node encoding (-1 auto, 0 off, 1 on)")
@@ -452,7 +451,6 @@ def main():
     _lib.check(L.pk_set_tuning(b"prune", args.prune))
     _lib.check(L.pk_set_tuning(b"child_features", args.child_features))
     _lib.check(L.pk_set_tuning(b"reserve_sms", args.reserve_sms))
-    _lib.check(L.pk_set_tuning(b"balance_tail", args.balance_tail))
     args.warmup = max(args.warmup, 3)
 
     flat = FlatForest.load(os.path.join(ROOT, "bench_data", wl["forest"] + "_forest.npz"))

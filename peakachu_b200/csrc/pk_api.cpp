@@ -50,9 +50,6 @@ static int g_tune_cf = -1;       // fused forest walk on the child-feature node 
 // fused kernel fetches windows as TMA boxes from a row-major copy of the band: 1 = where measured faster (w = 7: -8 %;
 // the w = 5 kernel is 6 % slower with it, profiles/r2_summary.md), 2 = always, 0 = never (per-cell gather)
 static int g_tune_tma = 1;
-// the fused kernel shares the last round of candidates out evenly among its CTAs instead of first come first served
-// (pk_fused.cu, top of a batch): without it a chromosome's last batches fill some SMs and idle the rest
-int g_tune_balance_tail = 1;
 static int g_tune_reserve = 8;   // SMs the fused kernel leaves to the short stages of other chromosomes (pipelined use: handles with a
                                  // score stream; measured on the c2 chromosome end to end: 0.663 ms with 0, 0.633-0.641 with 4-12, profiles/r2_summary.md)     // retire pixels that cannot exceed min_prob (exact for every emitted record)
 
@@ -62,7 +59,6 @@ extern "C" int pk_set_tuning(const char* key, int value) {
     if (key && !strcmp(key, "child_features")) { g_tune_cf = value; return PK_OK; }
     if (key && !strcmp(key, "tma")) { g_tune_tma = value; return PK_OK; }
     if (key && !strcmp(key, "reserve_sms")) { g_tune_reserve = value < 0 ? 0 : value; return PK_OK; }
-    if (key && !strcmp(key, "balance_tail")) { g_tune_balance_tail = value != 0; return PK_OK; }
     pk_set_error("pk_set_tuning: unknown key %s", key ? key : "(null)");
     return PK_EINVAL;
 }

@@ -26,8 +26,6 @@
 #include <algorithm>
 #include <cstring>
 
-extern int g_tune_balance_tail;    // pk_api.cpp, pk_set_tuning("balance_tail")
-
 struct FusedParams {
     const int32_t* band; const double* w; const double* expv;
     int n; long long pitch; int balanced; int ND;
@@ -41,7 +39,6 @@ struct FusedParams {
     unsigned long long* next;      // global work counter (candidates handed out)
     const int32_t* flags;          // handle's device flags
     double thre;                   // --minimum-prob: pixels that can no longer exceed it stop walking trees
-    int balance_tail;              // share the last round of candidates out evenly among the CTAs (pk_set_tuning("balance_tail"))
     float* fea_tap;                // parity tap (pk_chrom_fused_features): [n_cand][F] copy of the shared-memory feature rows, else NULL
     const int32_t* band2; long long P2;   // TM kernels: row-major band copy (pk_common.cuh) ...
     alignas(64) CUtensorMap tmap;         // ... and the skewed tensor map whose boxes are windows
@@ -261,7 +258,6 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const __grid_constant_
     double* s_acc = s_hand + (TPP == 2 ? 2 * CH * P : 0);         // [P]
     uint16_t* s_list = reinterpret_cast<uint16_t*>(s_acc + P);    // [2][P]
     __shared__ int s_gnkt[NG], s_gtake[NG * NBUF], s_gstop[NG * NBUF], s_reserved, s_nkept, s_done, s_expbad, s_wc[32];
-    __shared__ int s_share, s_grabbed;           // candidates this batch may take / has taken (the last round is shared out evenly)
     __shared__ long long s_gstart[NG * NBUF];
     constexpr int GCACHE = 64;                   // tree-group table kept in shared memory when it fits
     __shared__ int4 s_grp[GCACHE];
@@ -360,30 +356,12 @@ __global__ void __launch_bounds__(NTH, OCC) k_score_fused(const __grid_constant_
         // Windows are staged PB at a time ("a take") in the shared memory the tree buffers use during
         // phase B. Each group of warps runs its own takes; every step below runs over the whole take
         // with all threads of the group.
-        if (tid == 0) {
-            s_reserved = 0; s_nkept = 0; s_grabbed = 0;
-            // The last round: once fewer candidates are left than the CTAs could take in one round of full batches,
-            // first come first served would fill some CTAs' batches and leave the others idle for a whole batch
-            // (a batch of 256 windows is 1/5 of a chr1-scale chromosome's work per SM, and all of a small
-            // chromosome's). Each CTA then takes an equal share of what is left among the CTAs that have not taken
-            // theirs yet (counters[3] counts those that have); a CTA that comes back afterwards takes the crumbs.
-            int share = 0x7fffffff;
-            const long long rem = n_cand - (long long)*reinterpret_cast<volatile unsigned long long*>(prm.next);
-            if (prm.balance_tail && rem > 0 && rem < (long long)gridDim.x * P) {
-                const unsigned long long k = atomicAdd(&prm.counters[3], 1ull);
-                if (k < (unsigned long long)gridDim.x) share = (int)((rem + (long long)(gridDim.x - k) - 1) / (long long)(gridDim.x - k));
-            }
-            s_share = share;
-        }
+        if (tid == 0) { s_reserved = 0; s_nkept = 0; }
         __syncthreads();
         // reserve feature slots, then candidates, for the take that slot set `set` will hold (thread 0 of the group)
         auto grab = [&](int set) {
             const int prev = atomicAdd(&s_reserved, PB);
-            int sz = max(0, min(PB, P - prev));
-            if (sz > 0 && s_share != 0x7fffffff) {
-                const int g = atomicAdd(&s_grabbed, sz);
-                sz = max(0, min(sz, s_share - g));
-            }
+            const int sz = max(0, min(PB, P - prev));
             int take = 0;
             long long st = 0;
             bool stop = true;
@@ -1147,8 +1125,7 @@ int pk_launch_fused(pk_chrom* c, pk_forest* f, int variant, double thre, int res
     // per thread, latency-bound), +3 % on the w = 5 kernel (four chains per thread, closer to issue-bound).
     const bool cf = f->cf_ok && (child_features < 0 ? c->w == 7 : child_features != 0);
     prm.keep = c->d_keep; prm.prob = c->d_prob; prm.batch_win = c->d_batch_win; prm.counters = c->d_counters;
-    prm.next = c->d_counters + 2;               // counters[3] (zeroed with the others before every pass): CTAs that took a last-round share
-    prm.balance_tail = g_tune_balance_tail;
+    prm.next = c->d_counters + 2;
     prm.flags = c->d_flags;
     prm.thre = thre;
     if (!f->fused_ok) {         // a right child 4096 or more nodes away: the fused kernel's node encodings cannot hold it
