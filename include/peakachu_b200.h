@@ -258,12 +258,17 @@ int pk_h5_decode_chunks(const uint8_t* file, int64_t n_chunks, const int64_t* ch
  * cooler): bin1_offset int64[n_bins + 1] relative to the first pixel handed in, bin2 as int32 / int64 (bin2_bytes 4 | 8)
  * genome-wide ids of which bin2_base (the chromosome's first bin) is subtracted -- pixels behind the chromosome are
  * inter-chromosomal and dropped --, count as int32 / int64 / float64 (count_kind 0 | 1 | 2). Duplicates are summed and
- * zero counts dropped as utils.tocsr would (utils.py:10-15). Call with out = NULL to learn the size (*needed), then with
- * a buffer of at least that many bytes. PK_EINVAL names the first offending row: pixels below the diagonal, out of
- * order, negative, beyond int32 or fractional counts. n_threads 0: all host threads. */
+ * zero counts dropped as utils.tocsr would (utils.py:10-15). far_mode 0 keeps every pixel with bin2 - bin1 >= nd_enc in
+ * the far lists (what `depth` needs); far_mode 1 keeps only those the scoring path needs: a far pixel never enters the
+ * band, it only makes its two bins `valid` (utils.py:146-156), so it is dropped unless it is finite -- count > 0 and,
+ * with `weights` (float64[n_bins], the balancing weights; NULL: raw counts), isfinite((w_x w_y) count) -- and one of
+ * its bins has no finite pixel inside nd_enc; the `valid` mask the device derives is the same, and a deep genome-wide
+ * map sheds the bulk of its bytes. Call with out = NULL to learn the size (*needed), then with a buffer of at least
+ * that many bytes. PK_EINVAL names the first offending row: pixels below the diagonal, out of order, negative,
+ * beyond int32 or fractional counts. n_threads 0: all host threads. */
 int pk_rows_pack(const int64_t* bin1_offset, const void* bin2, int32_t bin2_bytes, int64_t bin2_base, const void* count,
-                 int32_t count_kind, int64_t n_bins, int32_t nd_enc, void* out, int64_t capacity, int64_t* needed,
-                 int32_t n_threads);
+                 int32_t count_kind, int64_t n_bins, int32_t nd_enc, int32_t far_mode, const double* weights, void* out,
+                 int64_t capacity, int64_t* needed, int32_t n_threads);
 
 /* a non-blocking CUDA stream for pk_chrom_create, for callers that do not bring their own
  * (two handles on two streams overlap one chromosome's upload with another's kernels) */

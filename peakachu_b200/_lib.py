@@ -72,8 +72,8 @@ SIGNATURES = {
     "pk_stream_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "pk_h5_decode_chunks": (C.c_int, [C.c_void_p, C.c_int64, c_i64p, c_i64p, c_i64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int32]),
-    "pk_rows_pack": (C.c_int, [c_i64p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p,
-                               C.c_int64, c_i64p, C.c_int32]),
+    "pk_rows_pack": (C.c_int, [c_i64p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                               C.c_void_p, C.c_void_p, C.c_int64, c_i64p, C.c_int32]),
     "pk_stream_destroy": (C.c_int, [C.c_int, C.c_void_p]),
     "pk_stream_create_priority": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "pk_chrom_set_score_stream": (C.c_int, [C.c_void_p, C.c_void_p]),

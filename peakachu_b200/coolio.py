@@ -333,6 +333,8 @@ class H5Cool:
     (``score_chromosome.py:42-43``) is the intra-chromosomal block: pixels of the chromosome's
     rows whose ``bin2`` also lies in the chromosome."""
 
+    packs_rows_on_the_fly = True       # upper_pixels_rows packs per call and takes `scoring_weights`
+
     def __init__(self, uri: str):
         from . import h5mini
         path, _, group = uri.partition("::")
@@ -461,11 +463,16 @@ class H5Cool:
         if self._raw_columns(chrom) is None:
             self._fetch(chrom)
 
-    def upper_pixels_rows(self, chrom: str, nd_min: int):
+    def upper_pixels_rows(self, chrom: str, nd_min: int, scoring_weights=False):
         """Packed pixel rows of the chromosome covering ``nd_min`` distances (uint8 blob for ``pk_chrom_upload_rows``),
         packed by the library straight from the file's columns (``pk_rows_pack``: trans pixels dropped, the
         symmetric-upper / order / count checks of ``_fetch`` made on the way); None when the rows are too many to
-        hold whole -- the caller then takes the block-wise columns."""
+        hold whole -- the caller then takes the block-wise columns.
+
+        ``scoring_weights``: the scoring path passes the weights the values are balanced with (None for raw
+        counts); the pixels beyond ``nd_min`` -- most of a deep genome-wide map, none of which enters the band -- are
+        then reduced to those that make a bin ``valid`` which no nearer pixel does (``utils.py:146-156``). The
+        default (False) keeps them all, as ``depth`` needs."""
         from . import rowpack
         raw = self._raw_columns(chrom)
         if raw is None:
@@ -473,8 +480,10 @@ class H5Cool:
         rp, b2, cnt, lo = raw
         if nd_min < 1:                                       # any coverage will do (`depth`): PKCool.write's default
             nd_min = 352
+        slim = scoring_weights is not False
         try:
-            return rowpack.pack_rows_native(rp, b2, cnt, rp.size - 1, int(nd_min), bin2_base=lo)
+            return rowpack.pack_rows_native(rp, b2, cnt, rp.size - 1, int(nd_min), bin2_base=lo, valid_only_far=slim,
+                                            weights=scoring_weights if slim else None)
         except ValueError as e:
             raise ValueError("%s: %s" % (self.path, e)) from None
 

@@ -490,10 +490,10 @@ void rows_parallel(int64_t n, int n_threads, F&& body) {
 }  // namespace
 
 extern "C" int pk_rows_pack(const int64_t* bin1_offset, const void* bin2, int32_t bin2_bytes, int64_t bin2_base,
-                            const void* count, int32_t count_kind, int64_t n_bins, int32_t nd_enc, void* out,
-                            int64_t capacity, int64_t* needed, int32_t n_threads) {
+                            const void* count, int32_t count_kind, int64_t n_bins, int32_t nd_enc, int32_t far_mode,
+                            const double* weights, void* out, int64_t capacity, int64_t* needed, int32_t n_threads) {
     if (!bin1_offset || n_bins < 0 || nd_enc < 1 || (bin2_bytes != 4 && bin2_bytes != 8) || count_kind < 0 || count_kind > 2 ||
-        !needed || bin1_offset[0] < 0 || (bin1_offset[n_bins] > bin1_offset[0] && (!bin2 || !count))) {
+        far_mode < 0 || far_mode > 1 || !needed || bin1_offset[0] < 0 || (bin1_offset[n_bins] > bin1_offset[0] && (!bin2 || !count))) {
         pk_set_error("pk_rows_pack: bad argument");
         return PK_EINVAL;
     }
@@ -507,11 +507,30 @@ extern "C" int pk_rows_pack(const int64_t* bin1_offset, const void* bin2, int32_
     std::vector<RowTally> tally((size_t)n);
     std::atomic<int> bad(0);
     std::atomic<int64_t> bad_row(-1);
+    // far_mode 1: a far pixel only matters as the witness that makes a bin `valid` (utils.py:146-156: a bin with any
+    // finite pixel, k_band_rows' far loop); bins that a pixel of the bitmap section already makes valid need none.
+    // The judgement is the device's: count > 0 and, with weights, isfinite((w_x w_y) count) (this file is compiled
+    // without contraction: the same two roundings as __dmul_rn).
+    std::vector<std::atomic<uint8_t>> wit(far_mode ? (size_t)n : 0);
+    for (auto& a : wit) a.store(0, std::memory_order_relaxed);
+    auto finite_px = [&](int64_t x, int64_t d, int64_t c) -> bool {
+        return !weights || std::isfinite((weights[x] * weights[x + d]) * (double)c);
+    };
+    auto keep_far = [&](int64_t x, int64_t d, int64_t c) -> bool {
+        if (!far_mode) return true;
+        return finite_px(x, d, c) && !(wit[(size_t)x].load(std::memory_order_relaxed) && wit[(size_t)(x + d)].load(std::memory_order_relaxed));
+    };
     rows_parallel(n, n_threads, [&](int64_t x0, int64_t x1) {
         for (int64_t x = x0; x < x1 && !bad.load(std::memory_order_relaxed); ++x) {
             RowTally t{0, 0, 0};
             const int rc = rows_walk(in, x, [&](int64_t d, int64_t c) {
-                if (d < in.nd) { ++t.band; t.esc += c >= 255; } else ++t.far;
+                if (d < in.nd) {
+                    ++t.band; t.esc += c >= 255;
+                    if (far_mode && finite_px(x, d, c)) {
+                        wit[(size_t)x].store(1, std::memory_order_relaxed);
+                        wit[(size_t)(x + d)].store(1, std::memory_order_relaxed);
+                    }
+                } else ++t.far;
             });
             if (rc != ROWS_OK) { bad.store(rc); bad_row.store(x); return; }
             tally[(size_t)x] = t;
@@ -523,6 +542,15 @@ extern "C" int pk_rows_pack(const int64_t* bin1_offset, const void* bin2, int32_
         pk_set_error("pk_rows_pack: row %lld: %s", (long long)bad_row.load(), why[bad.load()]);
         return PK_EINVAL;
     }
+    if (far_mode)                                            // the witnesses are complete: which far pixels stay
+        rows_parallel(n, n_threads, [&](int64_t x0, int64_t x1) {
+            for (int64_t x = x0; x < x1; ++x) {
+                if (tally[(size_t)x].far == 0) continue;
+                int64_t kept = 0;
+                rows_walk(in, x, [&](int64_t d, int64_t c) { if (d >= in.nd && keep_far(x, d, c)) ++kept; });
+                tally[(size_t)x].far = kept;
+            }
+        });
     // placement
     std::vector<int64_t> band_at((size_t)n + 1), esc_at((size_t)n + 1), far_at((size_t)n + 1);
     int64_t nb = 0, ne = 0, nf = 0;
@@ -572,7 +600,7 @@ extern "C" int pk_rows_pack(const int64_t* bin1_offset, const void* bin2, int32_
                     brow[d >> 5] |= 1u << (d & 31);
                     cnt8[ib++] = (uint8_t)std::min<int64_t>(c, 255);
                     if (c >= 255) { esc[ie] = (int32_t)x; esc[ne + ie] = (int32_t)d; esc[2 * ne + ie] = (int32_t)c; ++ie; }
-                } else {
+                } else if (keep_far(x, d, c)) {
                     far_b2[jf] = (int32_t)(x + d);
                     far_cnt[jf] = (int32_t)c;
                     ++jf;

@@ -147,11 +147,14 @@ def unpack_rows(blob):
     return rp, b2.astype(np.int32), cc.astype(np.int32)
 
 
-def pack_rows_native(bin1_offset, bin2, count, n_bins: int, nd_enc: int, bin2_base: int = 0, n_threads: int = 0) -> np.ndarray:
+def pack_rows_native(bin1_offset, bin2, count, n_bins: int, nd_enc: int, bin2_base: int = 0, n_threads: int = 0,
+                     valid_only_far: bool = False, weights=None) -> np.ndarray:
     """``pack_rows`` by the library (``pk_rows_pack``: two threaded passes over the columns, no temporaries): the
     same blob, from the rows of one chromosome as a cooler file stores them -- ``bin2`` may hold genome-wide ids
     (``bin2_base`` = the chromosome's first bin is subtracted; pixels behind the chromosome are dropped) and keeps
-    the file's integer width, ``count`` its type."""
+    the file's integer width, ``count`` its type. ``valid_only_far``: of the pixels beyond ``nd_enc`` keep only those
+    the scoring path needs -- the finite ones (``weights``: the balancing weights, None for raw counts) that make a
+    bin valid which no pixel inside ``nd_enc`` makes valid (``utils.py:146-156``); ``depth`` needs them all."""
     import ctypes as C
 
     from . import _lib
@@ -172,8 +175,14 @@ def pack_rows_native(bin1_offset, bin2, count, n_bins: int, nd_enc: int, bin2_ba
     if b2.size != cnt.size or (rp.size and int(rp[-1]) > b2.size):
         raise ValueError("bin1_offset points behind the pixel columns")
     need = C.c_int64()
+    w = None
+    if weights is not None:
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        if w.size != int(n_bins):
+            raise ValueError("weights must have n_bins entries")
     args = (_lib.ptr(rp, _lib.c_i64p), C.c_void_p(b2.ctypes.data), b2.dtype.itemsize, int(bin2_base),
-            C.c_void_p(cnt.ctypes.data), kind, int(n_bins), int(nd_enc))
+            C.c_void_p(cnt.ctypes.data), kind, int(n_bins), int(nd_enc), 1 if valid_only_far else 0,
+            C.c_void_p(w.ctypes.data) if w is not None else None)
     rc = L.pk_rows_pack(*args, None, 0, C.byref(need), int(n_threads))
     if rc != 0:
         raise ValueError(L.pk_last_error().decode("utf-8", "replace"))

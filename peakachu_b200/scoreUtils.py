@@ -183,7 +183,8 @@ class Chromosome:
         from . import shard
         n = Lib.nbins(key)
         nd_need = min(upper, n - 2 * width) + 2 * width + 1
-        enc, a, b, c, _ = shard._unit_columns(Lib, key, nd_need, encoding)
+        enc, a, b, c, _ = shard._unit_columns(Lib, key, nd_need, encoding,
+                                              scoring_weights=None if weights is None else np.asarray(weights, dtype=np.float64))
         kw = dict(lower=lower, upper=upper, cname=cname, res=res, width=width, device=device, first_tile=first_tile)
         if enc == _lib.PK_ENC_ROWS:
             return cls.from_rows(a, weights, n, model, **kw)

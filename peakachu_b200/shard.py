@@ -460,13 +460,25 @@ def map_weights(Lib, key, correct):
     return w, None
 
 
-def _unit_columns(Lib, key, nd_need, encoding):
+def _slim_far():
+    """PEAKACHU_B200_SLIM_FAR=0 makes a cooler file's packed rows carry every pixel beyond the band, not only
+    the ones the `valid` mask needs (see H5Cool.upper_pixels_rows)."""
+    import os
+    return os.environ.get("PEAKACHU_B200_SLIM_FAR", "1") != "0"
+
+
+def _unit_columns(Lib, key, nd_need, encoding, scoring_weights=False):
     """The pixel columns of one chromosome in the most compact form the reader offers (or the one asked
-    for): (PK_ENC_*, a, b, c, size)."""
+    for): (PK_ENC_*, a, b, c, size). ``scoring_weights`` (the balancing weights, None for raw counts): the caller
+    scores the chromosome, so a reader that packs rows on the fly may leave out the pixels beyond the band that the
+    `valid` mask does not need."""
     from . import _lib
     n = Lib.nbins(key)
     if encoding in (None, "rows") and hasattr(Lib, "upper_pixels_rows"):
-        blob = Lib.upper_pixels_rows(key, nd_need)
+        if scoring_weights is not False and _slim_far() and getattr(Lib, "packs_rows_on_the_fly", False):
+            blob = Lib.upper_pixels_rows(key, nd_need, scoring_weights=scoring_weights)
+        else:
+            blob = Lib.upper_pixels_rows(key, nd_need)
         if blob is not None:
             blob = _lib.as_c(blob, np.uint8)
             return _lib.PK_ENC_ROWS, blob, None, None, blob.size
@@ -514,10 +526,10 @@ def score_units(Lib, units, flat, *, correct, lower, upper, res, device, min_pro
         for key, a, b in units:
             n = Lib.nbins(key)
             nd_need = min(upper, n - 2 * w) + 2 * w + 1              # stored distances (scoreUtils.py:14,31)
-            enc, ca, cb, cc, size = _unit_columns(Lib, key, nd_need, encoding)
             weights, pweights = map_weights(Lib, key, correct)
             if weights is not None and weights.size != n:
                 raise ValueError("weight column of %s has %d entries for %d bins" % (key, weights.size, n))
+            enc, ca, cb, cc, size = _unit_columns(Lib, key, nd_need, encoding, scoring_weights=weights)
             eng.submit(len(keys), n, a, b, enc, ca, cb, cc, size, weights, min_prob, pweights)
             keys.append(key)
         results = eng.collect(copy=copy)

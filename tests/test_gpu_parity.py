@@ -1143,3 +1143,52 @@ def test_long_chromosome_matches_oracle(tmp_path):
     assert np.array_equal(x, r) and np.array_equal(y, c)
     assert np.array_equal(p, np.asarray(prob[r, c]).ravel()) and np.array_equal(v, np.asarray(val[r, c]).ravel())
     X.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("raw", [False, True])
+def test_rows_without_the_far_pixels_valid_does_not_need(raw, tmp_path, monkeypatch):
+    """From a cooler file the scoring path uploads packed rows whose far lists hold only the pixels that make a bin
+    valid which no pixel inside the band does (pk_rows_pack far_mode 1). On a map with pixels far beyond the band,
+    NaN / overflowing weights and bins that are valid through far pixels alone, the `valid`-dependent expected
+    curve, the candidates and the records equal those of the rows with every far pixel, and of the plain columns."""
+    import copy
+    from peakachu_b200 import coolio, rowpack
+    from peakachu_b200.scoreUtils import Chromosome
+    from tests import h5write
+    case = Case("tiny")
+    ch = copy.copy(case.chroms[0])
+    rng = np.random.default_rng(5)
+    n = ch.n
+    # bins 100..119 lose every pixel within 80 bins (rows and columns) and get pixels at distance >= 90 instead
+    lonely = np.arange(100, 120)
+    keep = ~((np.isin(ch.bin1, lonely) | np.isin(ch.bin2, lonely)) & (ch.bin2 - ch.bin1 < 80))
+    fb1 = np.repeat(lonely, 3)
+    fb2 = fb1 + rng.integers(90, 200, fb1.size)
+    far_b1 = rng.integers(0, n - 150, 400)
+    far_b2 = far_b1 + rng.integers(75, 150, 400)
+    b1 = np.concatenate([ch.bin1[keep], fb1, far_b1]); b2 = np.concatenate([ch.bin2[keep], fb2, far_b2])
+    cnt = np.concatenate([ch.count[keep], np.full(fb1.size, 2), rng.integers(1, 4, 400)])
+    key, first = np.unique(b1.astype(np.int64) * n + b2, return_index=True)
+    ch.bin1, ch.bin2, ch.count = (key // n).astype(np.int32), (key % n).astype(np.int32), cnt[first].astype(np.int32)
+    w = ch.weights.copy()
+    w[105] = np.nan; w[110] = 1e200; w[300] = 1e200; w[111] = np.inf
+    ch.weights = w
+    path = str(tmp_path / "far.cool")
+    h5write.write_cool(path, [ch], 10000, chunk=3000)
+    lib = coolio.open_map(path)
+    weights = None if raw else lib.weights(ch.name, "weight")
+    kw = dict(lower=6, upper=60, cname="chr1", res=10000, width=5)
+    got = {}
+    for mode in ("1", "0", "csr32"):
+        monkeypatch.setenv("PEAKACHU_B200_SLIM_FAR", "0" if mode == "csr32" else mode)
+        X = Chromosome.from_map(lib, ch.name, weights, case.forest, encoding="csr32" if mode == "csr32" else None, **kw)
+        got[mode] = (X.exp_arr.copy(), X.ridx.copy(), X.cidx.copy()) + tuple(X.score_records(0.5))
+        X.close()
+    nd = 60 + 2 * 5 + 1
+    slim, full = lib.upper_pixels_rows(ch.name, nd, scoring_weights=weights), lib.upper_pixels_rows(ch.name, nd)
+    assert 0 < rowpack.header(slim)["n_far"] < rowpack.header(full)["n_far"]
+    assert got["1"][1].size > 0 and got["1"][3].size > 0
+    for mode in ("0", "csr32"):
+        for a, b in zip(got["1"], got[mode]):
+            assert np.array_equal(a, b, equal_nan=True), mode

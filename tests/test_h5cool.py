@@ -324,3 +324,34 @@ def test_packed_rows_straight_from_the_file(tmp_path, latest):
     _mini_cool(p, b1, b2l, np.ones(120, np.int32))
     with pytest.raises(ValueError, match="below the diagonal"):
         coolio.open_map(p).upper_pixels_rows("chrZ", 8)
+
+
+def test_scoring_rows_leave_out_the_far_pixels_valid_does_not_need(tmp_path, monkeypatch):
+    """The scoring path asks H5Cool for rows with the balancing weights: pixels beyond the band stay only where they
+    make a bin valid that no nearer pixel does; the band sections are the full blob's, `depth` still gets everything."""
+    from peakachu_b200 import rowpack, shard
+    from tests.test_rowpack import _valid_mask
+    chroms = _genome()
+    path = str(tmp_path / "t.cool")
+    h5write.write_cool(path, chroms, 10000, trans=_trans(chroms, np.random.default_rng(2)), chunk=700)
+    lib = coolio.open_map(path)
+    seen = 0
+    for c in chroms:
+        nd = 25
+        w = lib.weights(c.name, "weight")
+        full = lib.upper_pixels_rows(c.name, nd)
+        for weights in (w, None):
+            slim = lib.upper_pixels_rows(c.name, nd, scoring_weights=weights)
+            hf, hs = rowpack.header(full), rowpack.header(slim)
+            assert hs["n_far"] <= hf["n_far"] and hs["nnz_band"] == hf["nnz_band"]
+            assert np.array_equal(full[hf["off_bits"]:hf["off_far_off"]], slim[hs["off_bits"]:hs["off_far_off"]])
+            assert np.array_equal(_valid_mask(slim, weights), _valid_mask(full, weights))
+            seen += hf["n_far"] - hs["n_far"]
+        # what score_units / Chromosome.from_map hand to the engine
+        monkeypatch.setenv("PEAKACHU_B200_SLIM_FAR", "1")
+        enc, blob, _, _, size = shard._unit_columns(lib, c.name, nd, None, scoring_weights=w)
+        assert np.array_equal(blob, lib.upper_pixels_rows(c.name, nd, scoring_weights=w)) and size == blob.size
+        monkeypatch.setenv("PEAKACHU_B200_SLIM_FAR", "0")
+        assert np.array_equal(shard._unit_columns(lib, c.name, nd, None, scoring_weights=w)[1], full)
+        assert np.array_equal(shard._unit_columns(lib, c.name, nd, None)[1], full)          # `depth`, tools: everything
+    assert seen > 0

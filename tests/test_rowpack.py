@@ -108,3 +108,71 @@ def test_native_packer_refuses_what_the_numpy_one_refuses():
     assert rowpack.unpack_rows(blob)[0].tolist() == [0, 0, 1]
     blob = rowpack.pack_rows_native(np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32), 0, 8)
     assert rowpack.header(blob)["n_bins"] == 0
+
+
+def _valid_mask(blob, weights):
+    """The `valid` mask the band build derives from a blob (k_band_rows / k_band_escapes, utils.py:146-156): a pixel
+    with count > 0 and -- with weights -- a finite balanced value (w_x w_y) count makes both its bins valid."""
+    rp, b2, cnt = rowpack.unpack_rows(blob)
+    n = rp.size - 1
+    x = np.repeat(np.arange(n), np.diff(rp))
+    fin = cnt > 0
+    if weights is not None:
+        with np.errstate(all="ignore"):
+            fin &= np.isfinite((weights[x] * weights[b2]) * cnt.astype(np.float64))
+    valid = np.zeros(n, bool)
+    valid[x[fin]] = True
+    valid[b2[fin]] = True
+    return valid
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_far_pixels_reduced_to_the_witnesses_of_valid(seed):
+    """valid_only_far (what the scoring path uploads from a cooler file): the sections the band is built from are
+    untouched, the far lists shrink to a subset, and the `valid` mask is the one the full blob gives -- with NaN,
+    infinite, zero, negative and overflowing weights, bins whose only finite pixels are far, escaped counts, and
+    in raw mode."""
+    rng = np.random.default_rng(seed)
+    n, nd = 260, 12
+    rows_b2, rows_c = [], []
+    sparse_rows = set(rng.choice(n, 60, replace=False).tolist())          # rows without pixels inside nd
+    for x in range(n):
+        near = np.arange(x, min(n, x + nd))
+        near = near[(rng.random(near.size) < (0.0 if x in sparse_rows else 0.6)) & ~np.isin(near, list(sparse_rows))]
+        far = np.arange(min(n, x + nd), n)
+        far = far[rng.random(far.size) < 0.04]
+        b2 = np.concatenate([near, far])
+        rows_b2.append(b2)
+        rows_c.append(rng.choice([1, 2, 3, 300, 7], b2.size))
+    rp = np.concatenate([[0], np.cumsum([b.size for b in rows_b2])]).astype(np.int64)
+    b2 = np.concatenate(rows_b2).astype(np.int32)
+    cnt = np.concatenate(rows_c).astype(np.int32)
+    w = rng.uniform(0.5, 1.5, n)
+    w[rng.choice(n, 25, replace=False)] = np.nan
+    w[rng.choice(n, 6, replace=False)] = np.inf
+    w[rng.choice(n, 6, replace=False)] = 1e200                            # products of two overflow
+    w[rng.choice(n, 6, replace=False)] = 0.0
+    w[rng.choice(n, 6, replace=False)] = -1.0
+    for weights in (w, None):
+        full = rowpack.pack_rows_native(rp, b2, cnt, n, nd)
+        assert np.array_equal(full, rowpack.pack_rows(rp, b2, cnt, n, nd))
+        slim = rowpack.pack_rows_native(rp, b2, cnt, n, nd, valid_only_far=True, weights=weights, n_threads=1 + seed % 3)
+        hf, hs = rowpack.header(full), rowpack.header(slim)
+        for k in ("n_bins", "nd_enc", "words_per_row", "nnz_band", "n_esc"):
+            assert hf[k] == hs[k]
+        assert hs["n_far"] < hf["n_far"] and hs["total_bytes"] < hf["total_bytes"]
+        assert np.array_equal(full[hf["off_bits"]:hf["off_far_off"]], slim[hs["off_bits"]:hs["off_far_off"]])
+        assert np.array_equal(_valid_mask(slim, weights), _valid_mask(full, weights))
+        # the kept far pixels are pixels of the full list, each finite and a witness of a bin nothing nearer makes valid
+        rf, bf, cf = rowpack.unpack_rows(full)
+        rs, bs, cs = rowpack.unpack_rows(slim)
+        key = lambda r, b: set(zip(np.repeat(np.arange(n), np.diff(r)).tolist(), b.tolist()))
+        assert key(rs, bs) <= key(rf, bf)
+        xs = np.repeat(np.arange(n), np.diff(rs))
+        far = (bs - xs) >= nd
+        near_only = rowpack.pack_rows_native(rs, bs, np.where(far, 0, cs).astype(np.int32), n, nd)      # far counts zeroed: dropped
+        near_valid = _valid_mask(near_only, weights)
+        assert far.sum() == hs["n_far"] > 0 and np.all(~near_valid[xs[far]] | ~near_valid[bs[far]])
+        assert not np.array_equal(near_valid, _valid_mask(full, weights))      # some bins are valid through far pixels only
+    with pytest.raises(ValueError, match="n_bins"):
+        rowpack.pack_rows_native(rp, b2, cnt, n, nd, valid_only_far=True, weights=w[:-1])
