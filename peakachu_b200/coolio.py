@@ -437,7 +437,14 @@ class H5Cool:
         return self._fetch(chrom)
 
     # pixels (cis + trans) of one chromosome's rows up to which the raw columns are held whole for the native packer
+    # (12 bytes per pixel as stored + the blob): 2^27 at least, more when the host has the memory for it
     RAW_LIMIT = 1 << 27
+    try:
+        import psutil as _psutil
+        RAW_LIMIT = int(min(1 << 30, max(1 << 27, _psutil.virtual_memory().available // 64)))
+        del _psutil
+    except Exception:                                        # pragma: no cover - psutil is optional
+        pass
 
     def _raw_columns(self, chrom: str):
         """(row pointer int64[n+1] rebased to 0, bin2 as stored (genome-wide ids), count as stored, first bin) of the
